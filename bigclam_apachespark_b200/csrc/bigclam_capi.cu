@@ -1,0 +1,633 @@
+// bigclam_capi.cu — C ABI (include/bigclam_b200.h) over the sm_100a kernels.
+// No CPU fallback: every compute entry point launches CUDA kernels or fails.
+#include "../../include/bigclam_b200.h"
+#include "bigclam_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace bigclam;
+
+struct bigclam_ctx {
+    bigclam_params p{};
+    int64_t n = 0, nnz = 0;
+    int32_t ld = 0, c2 = 0;
+    int device = 0;
+    int num_sms = 0;
+    int grid = 0;
+    size_t smem_bytes = 0;
+    int nsteps = 0;
+    double steps[kMaxSteps]{};
+
+    int64_t *d_rowptr = nullptr;
+    int32_t *d_col = nullptr;
+    int32_t *d_order = nullptr;
+    int64_t order_n = 0;
+    int64_t lo = 0, hi = 0;
+    double *d_F[2] = {nullptr, nullptr};
+    double *d_sumF[2] = {nullptr, nullptr};
+    int cur = 0;                // index of the current F / sumF buffer
+    double *d_partials = nullptr;
+    int8_t *d_accepted = nullptr;
+    uint8_t *d_mask = nullptr;
+    int32_t *d_done = nullptr;
+    RunState *d_state = nullptr;
+    double *d_trace = nullptr;
+    int64_t trace_cap = 0;
+    double *h_pinned = nullptr; // small pinned staging (partials / state)
+
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    double last_step_ms = 0.0;
+    int64_t last_step_launches = 0, last_all_launches = 0;
+
+    std::string err;
+};
+
+static std::string g_create_err;
+
+static int fail(bigclam_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c != nullptr) c->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return fail(ctx, BIGCLAM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                      \
+    } while (0)
+
+extern "C" const char *bigclam_version(void) { return "bigclam_b200 0.1 (sm_100a)"; }
+
+extern "C" int bigclam_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return BIGCLAM_ECUDA; }
+    return n;
+}
+
+extern "C" int bigclam_default_params(bigclam_params *p, int32_t k) {
+    if (p == nullptr || k <= 0) return BIGCLAM_EINVAL;
+    p->k = k;
+    p->max_inter = 15;
+    p->alpha = 0.05;
+    p->beta = 0.1;
+    p->min_p = 0.0001;
+    p->max_p = 0.9999;
+    p->min_f = 0.0;
+    p->max_f = 1000.0;
+    p->device = -1;
+    p->flags = 0;
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_step_sizes(double beta, int32_t max_inter, double *out) {
+    if (out == nullptr || max_inter < 0) return BIGCLAM_EINVAL;
+    double s = 1.0;                       // bigclam4-7.scala:28
+    out[0] = s;
+    for (int i = 1; i <= max_inter; ++i) { s *= beta; out[i] = s; }   // :31-32
+    return BIGCLAM_OK;
+}
+
+extern "C" const char *bigclam_last_error(const bigclam_ctx *ctx) {
+    return ctx != nullptr ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+static void free_ctx(bigclam_ctx *c) {
+    if (c == nullptr) return;
+    cudaSetDevice(c->device);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    cudaFree(c->d_rowptr); cudaFree(c->d_col); cudaFree(c->d_order);
+    cudaFree(c->d_F[0]); cudaFree(c->d_F[1]);
+    cudaFree(c->d_sumF[0]); cudaFree(c->d_sumF[1]);
+    cudaFree(c->d_partials); cudaFree(c->d_accepted); cudaFree(c->d_mask);
+    cudaFree(c->d_done); cudaFree(c->d_state); cudaFree(c->d_trace);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" void bigclam_destroy(bigclam_ctx *ctx) { free_ctx(ctx); }
+
+template <int C2>
+static cudaError_t configure_kernel(size_t smem, int *blocks_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(step_kernel<C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<C2>, kBlockThreads, smem);
+}
+
+template <int C2>
+static void launch_step_t(const StepArgs &a, int grid, size_t smem, cudaStream_t st) {
+    step_kernel<C2><<<grid, kBlockThreads, smem, st>>>(a);
+}
+
+static void launch_step(int c2, const StepArgs &a, int grid, size_t smem, cudaStream_t st) {
+    switch (c2) {
+        case 1: launch_step_t<1>(a, grid, smem, st); break;
+        case 2: launch_step_t<2>(a, grid, smem, st); break;
+        case 4: launch_step_t<4>(a, grid, smem, st); break;
+        case 8: launch_step_t<8>(a, grid, smem, st); break;
+        default: launch_step_t<16>(a, grid, smem, st); break;
+    }
+}
+
+static int rebuild_order(bigclam_ctx *ctx, const std::vector<int64_t> &rowptr_host) {
+    // Processing order over the owned range: degree descending (hubs first so the tail of the
+    // launch is made of cheap nodes), ties by id.
+    const int64_t cnt = ctx->hi - ctx->lo;
+    std::vector<int32_t> order((size_t)cnt);
+    std::iota(order.begin(), order.end(), (int32_t)ctx->lo);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        return (rowptr_host[a + 1] - rowptr_host[a]) > (rowptr_host[b + 1] - rowptr_host[b]);
+    });
+    if (ctx->d_order == nullptr) CU(cudaMalloc(&ctx->d_order, sizeof(int32_t) * std::max<size_t>(1, (size_t)ctx->n)));
+    if (cnt > 0) CU(cudaMemcpy(ctx->d_order, order.data(), sizeof(int32_t) * (size_t)cnt, cudaMemcpyHostToDevice));
+    ctx->order_n = cnt;
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowptr, const int32_t *col,
+                              const bigclam_params *params) {
+    bigclam_ctx *ctx = nullptr;   // errors before allocation go to g_create_err
+    if (out == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_create: out is NULL");
+    *out = nullptr;
+    if (params == nullptr || rowptr == nullptr || n <= 0 || n >= ((int64_t)1 << 31))
+        return fail(ctx, BIGCLAM_EINVAL, "bigclam_create: bad n/rowptr/params");
+    if (params->k <= 0) return fail(ctx, BIGCLAM_EINVAL, "bigclam_create: k must be > 0");
+    if (params->max_inter < 0 || params->max_inter + 1 > kMaxSteps)
+        return fail(ctx, BIGCLAM_EUNSUPPORTED, "bigclam_create: max_inter must be in [0,%d]", kMaxSteps - 1);
+    if (!(params->min_p > 0.0 && params->min_p < params->max_p && params->max_p < 1.0))
+        return fail(ctx, BIGCLAM_EINVAL, "bigclam_create: need 0 < min_p < max_p < 1");
+    if (!(params->min_f <= params->max_f)) return fail(ctx, BIGCLAM_EINVAL, "bigclam_create: min_f > max_f");
+    const int32_t ld = (params->k + 3) & ~3;
+    if (ld > 1024)
+        return fail(ctx, BIGCLAM_EUNSUPPORTED, "bigclam_create: k = %d > 1024 not supported by this build", params->k);
+    const int64_t nnz = rowptr[n];
+    if (rowptr[0] != 0 || nnz < 0) return fail(ctx, BIGCLAM_EINVAL, "bigclam_create: rowptr[0] != 0 or nnz < 0");
+    for (int64_t u = 0; u < n; ++u)
+        if (rowptr[u + 1] < rowptr[u]) return fail(ctx, BIGCLAM_EINVAL, "bigclam_create: rowptr not monotone at %lld", (long long)u);
+    if (nnz > 0 && col == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_create: col is NULL");
+    for (int64_t e = 0; e < nnz; ++e)
+        if (col[e] < 0 || col[e] >= n) return fail(ctx, BIGCLAM_EINVAL, "bigclam_create: col[%lld] out of range", (long long)e);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        (void)cudaGetLastError();
+        return fail(ctx, BIGCLAM_ECUDA, "bigclam_create: no CUDA device (this library has no CPU fallback)");
+    }
+    int dev = params->device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) return fail(ctx, BIGCLAM_EINVAL, "bigclam_create: device %d of %d", dev, ndev);
+
+    ctx = new (std::nothrow) bigclam_ctx();
+    if (ctx == nullptr) return fail(nullptr, BIGCLAM_ENOMEM, "bigclam_create: out of host memory");
+    ctx->p = *params;
+    ctx->n = n;
+    ctx->nnz = nnz;
+    ctx->ld = ld;
+    ctx->device = dev;
+    ctx->lo = 0;
+    ctx->hi = n;
+    ctx->nsteps = params->max_inter + 1;
+    bigclam_step_sizes(params->beta, params->max_inter, ctx->steps);
+    const int ld2 = ld / 2;
+    const int c2raw = (ld2 + 31) / 32;
+    ctx->c2 = c2raw <= 1 ? 1 : c2raw <= 2 ? 2 : c2raw <= 4 ? 4 : c2raw <= 8 ? 8 : 16;
+    ctx->smem_bytes = sizeof(double) * ((size_t)ld * (1 + 2 * kWarpsPerBlock) + (size_t)kWarpsPerBlock * 3 * kMaxActive);
+
+#define CUC(call)                                                                                 \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            fail(nullptr, BIGCLAM_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__));        \
+            free_ctx(ctx);                                                                        \
+            return BIGCLAM_ECUDA;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+    CUC(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, dev));
+    ctx->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        fail(nullptr, BIGCLAM_ECUDA, "bigclam_create: device sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor);
+        free_ctx(ctx);
+        return BIGCLAM_ECUDA;
+    }
+    int bps = 0;
+    cudaError_t ce;
+    switch (ctx->c2) {
+        case 1: ce = configure_kernel<1>(ctx->smem_bytes, &bps); break;
+        case 2: ce = configure_kernel<2>(ctx->smem_bytes, &bps); break;
+        case 4: ce = configure_kernel<4>(ctx->smem_bytes, &bps); break;
+        case 8: ce = configure_kernel<8>(ctx->smem_bytes, &bps); break;
+        default: ce = configure_kernel<16>(ctx->smem_bytes, &bps); break;
+    }
+    if (ce != cudaSuccess || bps <= 0) {
+        fail(nullptr, BIGCLAM_ECUDA, "bigclam_create: kernel configuration failed: %s (smem %zu B)",
+             cudaGetErrorString(ce), ctx->smem_bytes);
+        free_ctx(ctx);
+        return BIGCLAM_ECUDA;
+    }
+    ctx->grid = ctx->num_sms * bps;
+
+    CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    const size_t fbytes = sizeof(double) * (size_t)n * (size_t)ld;
+    CUC(cudaMalloc(&ctx->d_rowptr, sizeof(int64_t) * ((size_t)n + 1)));
+    CUC(cudaMalloc(&ctx->d_col, sizeof(int32_t) * std::max<size_t>(1, (size_t)nnz)));
+    CUC(cudaMalloc(&ctx->d_F[0], fbytes));
+    CUC(cudaMalloc(&ctx->d_F[1], fbytes));
+    CUC(cudaMalloc(&ctx->d_sumF[0], sizeof(double) * ld));
+    CUC(cudaMalloc(&ctx->d_sumF[1], sizeof(double) * ld));
+    CUC(cudaMalloc(&ctx->d_partials, sizeof(double) * (2 * (size_t)ld + 2)));
+    CUC(cudaMalloc(&ctx->d_accepted, (size_t)n));
+    CUC(cudaMalloc(&ctx->d_mask, (size_t)n));
+    CUC(cudaMalloc(&ctx->d_done, sizeof(int32_t)));
+    CUC(cudaMalloc(&ctx->d_state, sizeof(RunState)));
+    CUC(cudaMallocHost(&ctx->h_pinned, sizeof(double) * (2 * (size_t)ld + 2) + sizeof(RunState) + 64));
+    CUC(cudaMemcpy(ctx->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
+    if (nnz > 0) CUC(cudaMemcpy(ctx->d_col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
+    CUC(cudaMemset(ctx->d_F[0], 0, fbytes));
+    CUC(cudaMemset(ctx->d_F[1], 0, fbytes));
+    CUC(cudaMemset(ctx->d_sumF[0], 0, sizeof(double) * ld));
+    CUC(cudaMemset(ctx->d_sumF[1], 0, sizeof(double) * ld));
+    CUC(cudaMemset(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ld + 2)));
+    CUC(cudaMemset(ctx->d_accepted, 0xff, (size_t)n));
+    CUC(cudaMemset(ctx->d_done, 0, sizeof(int32_t)));
+    CUC(cudaMemset(ctx->d_state, 0, sizeof(RunState)));
+#undef CUC
+    {
+        std::vector<int64_t> rp(rowptr, rowptr + n + 1);
+        int rc = rebuild_order(ctx, rp);
+        if (rc != BIGCLAM_OK) { g_create_err = ctx->err; free_ctx(ctx); return rc; }
+    }
+    *out = ctx;
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_set_stream(bigclam_ctx *ctx, void *cuda_stream) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_device_state(bigclam_ctx *ctx, void **F_dev, void **F_next_dev, void **sumF_dev, int64_t *ld) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (F_dev) *F_dev = ctx->d_F[ctx->cur];
+    if (F_next_dev) *F_next_dev = ctx->d_F[ctx->cur ^ 1];
+    if (sumF_dev) *sumF_dev = ctx->d_sumF[ctx->cur];
+    if (ld) *ld = ctx->ld;
+    return BIGCLAM_OK;
+}
+
+static int colsum_current(bigclam_ctx *ctx) {
+    const int blocks = (ctx->ld + 31) / 32;
+    colsum_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_F[ctx->cur], ctx->n, ctx->ld, ctx->d_sumF[ctx->cur]);
+    CU(cudaGetLastError());
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (F == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_F: F is NULL");
+    CU(cudaSetDevice(ctx->device));
+    const int k = ctx->p.k, ld = ctx->ld;
+    // values must already satisfy the invariant the reference maintains: MIN_F <= F <= MAX_F
+    CU(cudaMemsetAsync(ctx->d_F[ctx->cur], 0, sizeof(double) * (size_t)ctx->n * ld, ctx->stream));
+    CU(cudaMemcpy2DAsync(ctx->d_F[ctx->cur], sizeof(double) * ld, F, sizeof(double) * k, sizeof(double) * k,
+                         (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = colsum_current(ctx);
+    if (rc != BIGCLAM_OK) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_set_sumF(bigclam_ctx *ctx, const double *sumF) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (sumF == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_sumF: sumF is NULL");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemsetAsync(ctx->d_sumF[ctx->cur], 0, sizeof(double) * ctx->ld, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_sumF[ctx->cur], sumF, sizeof(double) * ctx->p.k, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_get_F(bigclam_ctx *ctx, double *F_out) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (F_out == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_get_F: F_out is NULL");
+    CU(cudaSetDevice(ctx->device));
+    const int k = ctx->p.k, ld = ctx->ld;
+    CU(cudaMemcpy2DAsync(F_out, sizeof(double) * k, ctx->d_F[ctx->cur], sizeof(double) * ld, sizeof(double) * k,
+                         (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_get_sumF(bigclam_ctx *ctx, double *sumF_out) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (sumF_out == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_get_sumF: out is NULL");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(sumF_out, ctx->d_sumF[ctx->cur], sizeof(double) * ctx->p.k, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_get_accepted(bigclam_ctx *ctx, int8_t *accepted_out) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (accepted_out == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_get_accepted: out is NULL");
+    if (!(ctx->p.flags & BIGCLAM_F_RECORD_ACCEPTED))
+        return fail(ctx, BIGCLAM_EINVAL, "bigclam_get_accepted: context created without BIGCLAM_F_RECORD_ACCEPTED");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(accepted_out, ctx->d_accepted, (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BIGCLAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static void fill_args(bigclam_ctx *ctx, StepArgs &a, bool linesearch, const uint8_t *d_mask, bool use_done) {
+    const bigclam_params &p = ctx->p;
+    a.n = ctx->n;
+    a.rowptr = ctx->d_rowptr;
+    a.col = ctx->d_col;
+    a.F_in = ctx->d_F[ctx->cur];
+    a.F_out = ctx->d_F[ctx->cur ^ 1];
+    a.sumF = ctx->d_sumF[ctx->cur];
+    a.k = p.k;
+    a.ld = ctx->ld;
+    a.nsteps = ctx->nsteps;
+    for (int i = 0; i < kMaxSteps; ++i) a.steps[i] = i < ctx->nsteps ? ctx->steps[i] : 0.0;
+    a.alpha = p.alpha;
+    a.min_p = p.min_p; a.max_p = p.max_p; a.min_f = p.min_f; a.max_f = p.max_f;
+    // exp(-x) >= max_p  <=>  x <= -log(max_p);  exp(-x) <= min_p  <=>  x >= -log(min_p)
+    a.x_lo = -std::log(p.max_p) * (1.0 - 1e-12);
+    a.x_hi = -std::log(p.min_p) * (1.0 + 1e-12);
+    a.t_lo = std::log(1.0 - p.max_p);
+    a.t_hi = std::log(1.0 - p.min_p);
+    a.w_lo = 1.0 / (1.0 - p.max_p);
+    a.w_hi = 1.0 / (1.0 - p.min_p);
+    a.order = ctx->d_order;
+    a.order_n = ctx->order_n;
+    a.node_mask = d_mask;
+    a.partials = ctx->d_partials;
+    a.accepted = (linesearch && (p.flags & BIGCLAM_F_RECORD_ACCEPTED)) ? ctx->d_accepted : nullptr;
+    a.done_flag = use_done ? ctx->d_done : nullptr;
+    a.do_linesearch = linesearch ? 1 : 0;
+}
+
+static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
+    const bool timing = (ctx->p.flags & BIGCLAM_F_TIME_KERNELS) && is_step;
+    if (timing) {
+        while (ctx->ev_pool.size() < ctx->ev_used + 2) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            ctx->ev_pool.push_back(e);
+        }
+        CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
+    }
+    launch_step(ctx->c2, a, ctx->grid, ctx->smem_bytes, ctx->stream);
+    CU(cudaGetLastError());
+    if (timing) {
+        CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
+        ctx->ev_used += 2;
+    }
+    if (is_step) ++ctx->last_step_launches;
+    ++ctx->last_all_launches;
+    return BIGCLAM_OK;
+}
+
+static int collect_timing(bigclam_ctx *ctx) {
+    ctx->last_step_ms = 0.0;
+    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
+        ctx->last_step_ms += ms;
+    }
+    ctx->ev_used = 0;
+    return BIGCLAM_OK;
+}
+
+static int launch_finish(bigclam_ctx *ctx, long long kernel_index, int variant, double rel_tol, bool apply,
+                         bool llh_is_final) {
+    FinishArgs f;
+    f.partials = ctx->d_partials;
+    f.sumF_cur = ctx->d_sumF[ctx->cur];
+    f.sumF_next = ctx->d_sumF[ctx->cur ^ 1];
+    f.ld = ctx->ld;
+    f.st = ctx->d_state;
+    f.done_flag = ctx->d_done;
+    f.trace = ctx->d_trace;
+    f.trace_cap = ctx->trace_cap;
+    f.kernel_index = kernel_index;
+    f.variant = variant;
+    f.rel_tol = rel_tol;
+    f.apply = apply ? 1 : 0;
+    f.llh_is_final = llh_is_final ? 1 : 0;
+    finish_kernel<<<1, 256, 0, ctx->stream>>>(f);
+    CU(cudaGetLastError());
+    ++ctx->last_all_launches;
+    return BIGCLAM_OK;
+}
+
+static int reset_run_state(bigclam_ctx *ctx) {
+    CU(cudaMemsetAsync(ctx->d_done, 0, sizeof(int32_t), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_state, 0, sizeof(RunState), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
+    ctx->last_step_launches = 0;
+    ctx->last_all_launches = 0;
+    ctx->ev_used = 0;
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_loglikelihood(bigclam_ctx *ctx, double *llh_out) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (llh_out == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_loglikelihood: llh_out is NULL");
+    CU(cudaSetDevice(ctx->device));
+    int rc = reset_run_state(ctx);
+    if (rc) return rc;
+    StepArgs a;
+    fill_args(ctx, a, false, nullptr, false);
+    rc = timed_launch(ctx, a, false);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials + 2 * ctx->ld, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *llh_out = ctx->h_pinned[0];
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *llh_out, int64_t *n_updated_out) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    int rc = reset_run_state(ctx);
+    if (rc) return rc;
+    const uint8_t *d_mask = nullptr;
+    if (node_mask != nullptr) {
+        CU(cudaMemcpyAsync(ctx->d_mask, node_mask, (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+        d_mask = ctx->d_mask;
+    }
+    StepArgs a;
+    fill_args(ctx, a, true, d_mask, false);
+    rc = timed_launch(ctx, a, true);                       // PRE + LS + swap
+    if (rc) return rc;
+    rc = launch_finish(ctx, 0, 0, 0.0, true, false);       // sumF update (:192), zero partials
+    if (rc) return rc;
+    ctx->cur ^= 1;
+    fill_args(ctx, a, false, nullptr, false);              // LLH with new F, new sumF (:196-219)
+    rc = timed_launch(ctx, a, false);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials + 2 * ctx->ld, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_state, sizeof(RunState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (llh_out) *llh_out = ctx->h_pinned[0];
+    if (n_updated_out) *n_updated_out = reinterpret_cast<RunState *>(ctx->h_pinned + 8)->n_updated;
+    return collect_timing(ctx);
+}
+
+extern "C" int bigclam_run(bigclam_ctx *ctx, int32_t variant, double rel_tol, int64_t max_outer,
+                           double *llh_out, int64_t *calls_out, double *llh_trace, int64_t trace_cap) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (variant != 2 && variant != 3 && variant != 4) return fail(ctx, BIGCLAM_EINVAL, "bigclam_run: variant must be 2, 3 or 4");
+    if (max_outer < 0 || trace_cap < 0) return fail(ctx, BIGCLAM_EINVAL, "bigclam_run: negative max_outer/trace_cap");
+    CU(cudaSetDevice(ctx->device));
+    int rc = reset_run_state(ctx);
+    if (rc) return rc;
+    if (llh_trace != nullptr && trace_cap > 0) {
+        if (ctx->trace_cap < trace_cap) {
+            cudaFree(ctx->d_trace);
+            ctx->d_trace = nullptr;
+            ctx->trace_cap = 0;
+            CU(cudaMalloc(&ctx->d_trace, sizeof(double) * (size_t)trace_cap));
+            ctx->trace_cap = trace_cap;
+        }
+    }
+    const int64_t saved_cap = ctx->trace_cap;
+    if (llh_trace == nullptr) ctx->trace_cap = 0; else ctx->trace_cap = trace_cap;
+
+    RunState *hst = reinterpret_cast<RunState *>(ctx->h_pinned + 8);
+    const int start_cur = ctx->cur;
+    const int64_t batch = 8;
+    int64_t c = 0;                 // step kernels enqueued so far (kernel c maps S_{c-1} -> S_c)
+    bool done = false;
+    StepArgs a;
+    while (!done) {
+        int64_t todo = batch;
+        if (max_outer > 0) todo = std::min<int64_t>(batch, max_outer - c);
+        for (int64_t i = 0; i < todo; ++i) {
+            ++c;
+            ctx->cur = (start_cur + (int)((c - 1) & 1)) & 1;       // S_{c-1} lives in buffer (c-1)%2
+            fill_args(ctx, a, true, nullptr, true);
+            rc = timed_launch(ctx, a, true);
+            if (rc) return rc;
+            rc = launch_finish(ctx, c, variant, rel_tol, true, false);   // tests call c-1, builds sumF_c
+            if (rc) return rc;
+        }
+        CU(cudaMemcpyAsync(hst, ctx->d_state, sizeof(RunState), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (hst->done) { done = true; break; }
+        if (max_outer > 0 && c >= max_outer) break;
+    }
+    int64_t calls;
+    if (done) {
+        calls = hst->conv_call;                                   // final state S_calls, untouched
+    } else {
+        calls = c;                                                // cut by max_outer: need LLH(S_c)
+        ctx->cur = (start_cur + (int)(c & 1)) & 1;
+        fill_args(ctx, a, false, nullptr, false);
+        rc = timed_launch(ctx, a, false);
+        if (rc) return rc;
+        rc = launch_finish(ctx, c, variant, rel_tol, false, true);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(hst, ctx->d_state, sizeof(RunState), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->cur = (start_cur + (int)(calls & 1)) & 1;
+    if (llh_out) *llh_out = hst->ret_llh;
+    if (calls_out) *calls_out = calls;
+    if (llh_trace != nullptr && trace_cap > 0) {
+        const int64_t cnt = std::min<int64_t>(calls, trace_cap);
+        if (cnt > 0) CU(cudaMemcpy(llh_trace, ctx->d_trace, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
+    }
+    ctx->trace_cap = saved_cap;
+    return collect_timing(ctx);
+}
+
+extern "C" int bigclam_get_kernel_time(bigclam_ctx *ctx, double *step_kernel_ms_sum, int64_t *step_kernel_launches,
+                                       int64_t *all_kernel_launches) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (step_kernel_ms_sum) *step_kernel_ms_sum = ctx->last_step_ms;
+    if (step_kernel_launches) *step_kernel_launches = ctx->last_step_launches;
+    if (all_kernel_launches) *all_kernel_launches = ctx->last_all_launches;
+    return BIGCLAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Node-partitioned pieces.
+extern "C" int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (lo < 0 || hi < lo || hi > ctx->n) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_owned_range: bad range");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<int64_t> rp((size_t)ctx->n + 1);
+    CU(cudaMemcpy(rp.data(), ctx->d_rowptr, sizeof(int64_t) * rp.size(), cudaMemcpyDeviceToHost));
+    ctx->lo = lo;
+    ctx->hi = hi;
+    return rebuild_order(ctx, rp);
+}
+
+extern "C" int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    ctx->ev_used = 0;
+    ctx->last_step_launches = 0;
+    ctx->last_all_launches = 0;
+    StepArgs a;
+    fill_args(ctx, a, true, nullptr, false);
+    int rc = timed_launch(ctx, a, true);
+    if (rc) return rc;
+    if (partials_dev) *partials_dev = ctx->d_partials;
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64_t *n_updated_out) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials + 2 * ctx->ld, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = launch_finish(ctx, 0, 0, 0.0, true, false);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->cur ^= 1;
+    if (llh_pre_out) *llh_pre_out = ctx->h_pinned[0];
+    if (n_updated_out) *n_updated_out = (int64_t)(ctx->h_pinned[1] + 0.5);
+    return collect_timing(ctx);
+}
+
+extern "C" int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
+    StepArgs a;
+    fill_args(ctx, a, false, nullptr, false);
+    int rc = timed_launch(ctx, a, false);
+    if (rc) return rc;
+    if (partials_dev) *partials_dev = ctx->d_partials;
+    return BIGCLAM_OK;
+}

@@ -1,0 +1,93 @@
+"""Graph containers either side of the hot path: compact .npz fixtures of the SNAP graphs the
+reference ships (data/*.txt), and synthetic generators for BASELINE.json's configs 3-5.
+
+All of this is one-off host-side integer work (CSR construction); the hot path never sees it.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIXTURE_DIR = os.path.join(_REPO, "tests", "golden", "graphs")
+
+
+def csr_from_undirected(n: int, u: np.ndarray, v: np.ndarray):
+    """Simple undirected graph given each edge once (u != v) -> symmetric CSR, lists sorted."""
+    a = np.concatenate([u, v]).astype(np.int64)
+    b = np.concatenate([v, u]).astype(np.int64)
+    order = np.lexsort((b, a))
+    a, b = a[order], b[order]
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(a, minlength=n), out=rowptr[1:])
+    return rowptr, b.astype(np.int32)
+
+
+def save_npz_graph(path: str, rowptr: np.ndarray, col: np.ndarray, ids: np.ndarray) -> None:
+    """Stores the upper triangle (u < v) of a simple undirected CSR, plus the original ids."""
+    n = len(rowptr) - 1
+    u = np.repeat(np.arange(n, dtype=np.int64), np.diff(rowptr))
+    m = u < col
+    contiguous = bool(np.array_equal(ids, np.arange(ids[0], ids[0] + n)))
+    np.savez_compressed(
+        path, n=np.int64(n), deg_upper=np.bincount(u[m], minlength=n).astype(np.int32),
+        v=col[m].astype(np.int32),
+        ids=(np.array([ids[0]], dtype=np.int64) if contiguous else np.diff(ids, prepend=0).astype(np.int64)),
+        ids_contiguous=np.bool_(contiguous))
+
+
+def load_npz_graph(name_or_path: str):
+    """Returns (rowptr int64, col int32, ids int64) of a fixture written by save_npz_graph."""
+    path = name_or_path if os.path.exists(name_or_path) else os.path.join(FIXTURE_DIR, name_or_path + ".npz")
+    z = np.load(path)
+    n = int(z["n"])
+    u = np.repeat(np.arange(n, dtype=np.int32), z["deg_upper"])
+    rowptr, col = csr_from_undirected(n, u, z["v"])
+    ids = (np.arange(n, dtype=np.int64) + int(z["ids"][0])) if bool(z["ids_contiguous"]) else np.cumsum(z["ids"])
+    return rowptr, col, ids.astype(np.int64)
+
+
+def have_fixture(name: str) -> bool:
+    return os.path.exists(os.path.join(FIXTURE_DIR, name + ".npz"))
+
+
+def synthetic_F0(n: int, k: int, seed: int = 1234, density: float = 0.05) -> np.ndarray:
+    """BASELINE.md synthetic init: F0[u,c] = U[0,1) with probability `density`, else 0 (fp64)."""
+    rng = np.random.default_rng(seed)
+    F = rng.random((n, k))
+    F *= rng.random((n, k)) < density
+    return F
+
+
+def rmat_graph(scale_n: int, n_edges: int, a=0.57, b=0.19, c=0.19, seed: int = 42, permute: bool = True):
+    """R-MAT (a,b,c,d) edge generator -> simple undirected CSR over n = scale_n nodes
+    (n need not be a power of two: endpoints are drawn in the next power of two and rejected
+    when >= n).  Self loops and duplicate pairs are removed, ids randomly permuted."""
+    rng = np.random.default_rng(seed)
+    bits = int(np.ceil(np.log2(max(scale_n, 2))))
+    us, vs = [], []
+    need = n_edges
+    while need > 0:
+        m = int(need * 1.3) + 1024
+        u = np.zeros(m, dtype=np.int64)
+        v = np.zeros(m, dtype=np.int64)
+        for _ in range(bits):
+            r = rng.random(m)
+            right = (r >= a) & (r < a + b) | (r >= a + b + c)      # quadrants b, d: column bit set
+            down = r >= a + b                                       # quadrants c, d: row bit set
+            u = (u << 1) | down
+            v = (v << 1) | right
+        ok = (u < scale_n) & (v < scale_n) & (u != v)
+        us.append(u[ok])
+        vs.append(v[ok])
+        lo = np.minimum(np.concatenate(us), np.concatenate(vs))
+        hi = np.maximum(np.concatenate(us), np.concatenate(vs))
+        key = np.unique(lo * scale_n + hi)
+        us, vs = [key // scale_n], [key % scale_n]
+        need = n_edges - len(key)
+    u, v = us[0][:n_edges], vs[0][:n_edges]
+    if permute:
+        perm = rng.permutation(scale_n)
+        u, v = perm[u], perm[v]
+    return csr_from_undirected(scale_n, u, v)

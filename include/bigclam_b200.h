@@ -1,0 +1,162 @@
+/*
+ * bigclam_b200.h — C ABI of the B200-native BigCLAM F-gradient / line-search step.
+ *
+ * The reference (thangdnsf/BigCLAM-ApacheSpark) has no FFI or plugin interface; its boundary is
+ * the implicit signature of one spark-shell function and the globals it touches:
+ *
+ *     def backtrackingLineSearchs(uset: List[Long]): Double      codes/bigclam4-7.scala:152
+ *       reads   collectNeighbor / Neightborbc (adjacency)         codes/bigclam4-7.scala:50-51
+ *               K, liststepSizeRDD, alpha, MIN_P_/MAX_P_/MIN_F_/MAX_F_   :134,:28-34,:22,:39-43
+ *       reads+writes  F (N x K affiliation rows), sumF (K)        codes/bigclam4-7.scala:36,38,190,192
+ *       returns the log-likelihood after the update               codes/bigclam4-7.scala:196-222
+ *
+ * Every entry point below names the reference lines it replaces.  A JVM binding (JNI) that the
+ * Scala driver would use is shown in INTEGRATION.md; the Python ctypes binding used by the tests
+ * lives in bigclam_apachespark_b200/_lib.py.
+ *
+ * Conventions: plain C, no exceptions cross the boundary.  Every function returns 0 on success
+ * and a negative BIGCLAM_E* code on failure; bigclam_last_error() gives the message.  The caller
+ * owns all host buffers; the context owns all device memory.  A context is driven by one thread
+ * at a time; distinct contexts are independent.  All calls are synchronous on return unless noted.
+ * There is NO CPU fallback: creating a context without a usable CUDA device fails.
+ */
+#ifndef BIGCLAM_B200_H
+#define BIGCLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BIGCLAM_OK            0
+#define BIGCLAM_EINVAL      (-1)   /* bad argument */
+#define BIGCLAM_ECUDA       (-2)   /* CUDA runtime / driver error, or no device */
+#define BIGCLAM_ENOMEM      (-3)   /* host or device allocation failed */
+#define BIGCLAM_EIO         (-4)   /* edge-list file unreadable / malformed */
+#define BIGCLAM_EUNSUPPORTED (-5)  /* parameter combination the kernels do not cover */
+
+typedef struct bigclam_ctx bigclam_ctx;
+
+/* Script-level variables of the reference, one field each. */
+typedef struct {
+    int32_t k;           /* K.value: number of communities            bigclam4-7.scala:134,249 */
+    int32_t max_inter;   /* MaxInter = 15 -> 16 step sizes            bigclam4-7.scala:26-34   */
+    double  alpha;       /* 0.05  Armijo slope                        bigclam4-7.scala:22      */
+    double  beta;        /* 0.1   step shrink factor                  bigclam4-7.scala:24      */
+    double  min_p;       /* MIN_P_ = 0.0001                           bigclam4-7.scala:40      */
+    double  max_p;       /* MAX_P_ = 0.9999                           bigclam4-7.scala:41      */
+    double  min_f;       /* MIN_F_ = 0.0                              bigclam4-7.scala:42      */
+    double  max_f;       /* MAX_F_ = 1000.0                           bigclam4-7.scala:43      */
+    int32_t device;      /* CUDA ordinal; -1 = the calling thread's current device */
+    int32_t flags;       /* BIGCLAM_F_* */
+} bigclam_params;
+
+#define BIGCLAM_F_TIME_KERNELS   1   /* record CUDA events around every step-kernel launch */
+#define BIGCLAM_F_RECORD_ACCEPTED 2  /* keep the accepted step index per node (diagnostics/tests) */
+
+/* Fills *p with the reference's constants for a given K. */
+int bigclam_default_params(bigclam_params *p, int32_t k);
+
+/* The 16 candidate step sizes, built by repeated `*= beta` exactly as bigclam4-7.scala:28-34
+ * (out[0] = 1.0, out[j] = out[j-1]*beta; max_inter+1 values). */
+int bigclam_step_sizes(double beta, int32_t max_inter, double *out);
+
+/*
+ * Context = the hot path's resident state: CSR adjacency (collectNeighbor, :50-51), F double
+ * buffer, sumF.  rowptr has n+1 entries, col has rowptr[n] entries in [0,n); neighbour lists are
+ * taken as given (multiplicity and order preserved, like collectNeighborIds(Either)).
+ * Replaces: Neightborbc broadcast (:51) and the per-call Fbc broadcast (:154).
+ */
+int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowptr, const int32_t *col,
+                   const bigclam_params *params);
+void bigclam_destroy(bigclam_ctx *ctx);
+const char *bigclam_last_error(const bigclam_ctx *ctx);   /* ctx may be NULL: last create error */
+
+/* F <- host row-major n x k; sumF <- exact column sums (initNeighborComF, :105-107). */
+int bigclam_set_F(bigclam_ctx *ctx, const double *F);
+/* Optional: inject a sumF that has drifted from colsum(F) (the reference never recomputes it, :192). */
+int bigclam_set_sumF(bigclam_ctx *ctx, const double *sumF);
+int bigclam_get_F(bigclam_ctx *ctx, double *F_out);        /* n x k row-major */
+int bigclam_get_sumF(bigclam_ctx *ctx, double *sumF_out);  /* k */
+
+/*
+ * One call of backtrackingLineSearchs(uset)  (bigclam4-7.scala:152-223): PRE (:157-169), 16-candidate
+ * Armijo line search keeping the max passing step (:172-184), Jacobi row swap + incremental sumF
+ * (:186-193), LLH with the new F and sumF (:196-219, returned).  node_mask: NULL = all vertices
+ * (the reference always passes all, :227); otherwise n bytes, u is in uset iff node_mask[u] != 0.
+ * Nodes with an empty neighbour list are never updated (the reference would throw).
+ */
+int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *llh_out, int64_t *n_updated_out);
+
+/* loglikelihood() (bigclamv3-7.scala:106-120, Bigclamv2.scala:187-200) on the current F, sumF. */
+int bigclam_loglikelihood(bigclam_ctx *ctx, double *llh_out);
+
+/*
+ * Outer loop on the device, LLH of step t taken from step t+1's PRE pass (they are the same sum).
+ *   variant 4: SGDFindC  (bigclam4-7.scala:225-243)  LLHold = first step; returns LLHold as coded at :242
+ *   variant 3: MBSGD     (bigclamv3-7.scala:206-222) LLHold = 0.0
+ *   variant 2: MBSGD     (Bigclamv2.scala:203-219)   LLHold = loglikelihood()
+ * Stops when |1 - new/old| < rel_tol (:237) or after max_outer hot-path calls (0 = unbounded, like
+ * the reference).  llh_trace (optional, trace_cap doubles) receives every call's returned LLH.
+ * On return F/sumF are exactly the state after `*calls_out` calls.
+ */
+int bigclam_run(bigclam_ctx *ctx, int32_t variant, double rel_tol, int64_t max_outer,
+                double *llh_out, int64_t *calls_out, double *llh_trace, int64_t trace_cap);
+
+/* Diagnostics (BIGCLAM_F_RECORD_ACCEPTED): index of the accepted step size per node for the
+ * most recent step, -1 = row unchanged. */
+int bigclam_get_accepted(bigclam_ctx *ctx, int8_t *accepted_out);
+
+/* Timing of the most recent bigclam_step / bigclam_run (BIGCLAM_F_TIME_KERNELS), CUDA events on
+ * the context's stream: total device ms of the step kernels and how many were launched. */
+int bigclam_get_kernel_time(bigclam_ctx *ctx, double *step_kernel_ms_sum, int64_t *step_kernel_launches,
+                            int64_t *all_kernel_launches);
+
+/* Interop with the host framework's plumbing (torch streams / NCCL buffers): use an existing
+ * cudaStream_t, and expose device pointers of the current F (n x ld doubles, ld = row pitch) and sumF. */
+int bigclam_set_stream(bigclam_ctx *ctx, void *cuda_stream);
+int bigclam_device_state(bigclam_ctx *ctx, void **F_dev, void **F_next_dev, void **sumF_dev, int64_t *ld);
+
+/*
+ * Multi-GPU (node-partitioned) pieces: a context created with an owned node range only updates
+ * rows [lo,hi); rows outside are halo (read-only copies refreshed by the caller's collective).
+ * See DESIGN.md (e).  bigclam_step_local runs PRE+LS+row swap for owned rows and leaves the partial
+ * reductions [sum_old(k) | sum_new(k) | llh_pre | n_updated] in a device buffer of 2k+2 doubles that
+ * the caller all-reduces; bigclam_finish_local applies the reduced values (sumF update, :192).
+ */
+int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi);
+int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev /* 2k+2 doubles */);
+int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64_t *n_updated_out);
+int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev /* llh at [2k] */);
+
+/*
+ * Edge-list reader with GraphX semantics (GraphLoader.edgeListFile, bigclam4-7.scala:45;
+ * collectNeighborIds(EdgeDirection.Either), :50): '#' and blank lines skipped, whitespace split,
+ * CRLF safe; each edge line adds dst to src's list and src to dst's list.  Vertex ids are relabelled
+ * to 0..n-1 in ascending id order (ids_out gives the original id of each dense index).
+ * multiplicity: 0 = keep (literal GraphX), 1 = dedup (simple undirected graph, self loops dropped).
+ * Neighbour lists are sorted ascending.  Buffers are malloc'ed by the library; release with
+ * bigclam_graph_free.
+ */
+typedef struct {
+    int64_t  n;
+    int64_t  nnz;
+    int64_t *rowptr;   /* n+1 */
+    int32_t *col;      /* nnz */
+    int64_t *ids;      /* n: original vertex id of dense index i */
+    int64_t  n_edge_lines;
+} bigclam_graph;
+
+int  bigclam_graph_read_edgelist(const char *path, int32_t multiplicity, bigclam_graph *out,
+                                 char *errbuf, int64_t errbuf_len);
+void bigclam_graph_free(bigclam_graph *g);
+
+/* Library / device probe (no compute): returns the number of visible CUDA devices or <0. */
+int bigclam_device_count(void);
+const char *bigclam_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIGCLAM_B200_H */
