@@ -27,7 +27,8 @@ struct bigclam_ctx {
 
     int64_t *d_rowptr = nullptr;
     int32_t *d_col = nullptr;
-    int32_t *d_order = nullptr;
+    NodeMeta *d_meta = nullptr;
+    int32_t maxm = 0;
     int64_t order_n = 0;
     int64_t lo = 0, hi = 0;
     double *d_F[2] = {nullptr, nullptr};
@@ -37,6 +38,7 @@ struct bigclam_ctx {
     int8_t *d_accepted = nullptr;
     uint8_t *d_mask = nullptr;
     int32_t *d_done = nullptr;
+    unsigned int *d_work = nullptr;
     RunState *d_state = nullptr;
     double *d_trace = nullptr;
     int64_t trace_cap = 0;
@@ -49,6 +51,8 @@ struct bigclam_ctx {
     size_t ev_used = 0;
     double last_step_ms = 0.0;
     int64_t last_step_launches = 0, last_all_launches = 0;
+
+    unsigned int h_work_init = 0;
 
     std::string err;
 };
@@ -113,11 +117,11 @@ static void free_ctx(bigclam_ctx *c) {
     if (c == nullptr) return;
     cudaSetDevice(c->device);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
-    cudaFree(c->d_rowptr); cudaFree(c->d_col); cudaFree(c->d_order);
+    cudaFree(c->d_rowptr); cudaFree(c->d_col); cudaFree(c->d_meta);
     cudaFree(c->d_F[0]); cudaFree(c->d_F[1]);
     cudaFree(c->d_sumF[0]); cudaFree(c->d_sumF[1]);
     cudaFree(c->d_partials); cudaFree(c->d_accepted); cudaFree(c->d_mask);
-    cudaFree(c->d_done); cudaFree(c->d_state); cudaFree(c->d_trace);
+    cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_state); cudaFree(c->d_trace);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -126,15 +130,19 @@ static void free_ctx(bigclam_ctx *c) {
 extern "C" void bigclam_destroy(bigclam_ctx *ctx) { free_ctx(ctx); }
 
 template <int C2>
+struct RowsInFlight { static constexpr int value = (C2 <= 4) ? 4 : (C2 <= 8 ? 2 : 1); };
+
+template <int C2>
 static cudaError_t configure_kernel(size_t smem, int *blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(step_kernel<C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    constexpr int R = RowsInFlight<C2>::value;
+    cudaError_t e = cudaFuncSetAttribute(step_kernel<C2, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<C2>, kBlockThreads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<C2, R>, kBlockThreads, smem);
 }
 
 template <int C2>
 static void launch_step_t(const StepArgs &a, int grid, size_t smem, cudaStream_t st) {
-    step_kernel<C2><<<grid, kBlockThreads, smem, st>>>(a);
+    step_kernel<C2, RowsInFlight<C2>::value><<<grid, kBlockThreads, smem, st>>>(a);
 }
 
 static void launch_step(int c2, const StepArgs &a, int grid, size_t smem, cudaStream_t st) {
@@ -149,15 +157,23 @@ static void launch_step(int c2, const StepArgs &a, int grid, size_t smem, cudaSt
 
 static int rebuild_order(bigclam_ctx *ctx, const std::vector<int64_t> &rowptr_host) {
     // Processing order over the owned range: degree descending (hubs first so the tail of the
-    // launch is made of cheap nodes), ties by id.
+    // launch is made of cheap nodes), ties by id; packed as NodeMeta so one 16-byte load gives a
+    // warp everything it needs to start a node.
     const int64_t cnt = ctx->hi - ctx->lo;
     std::vector<int32_t> order((size_t)cnt);
     std::iota(order.begin(), order.end(), (int32_t)ctx->lo);
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
         return (rowptr_host[a + 1] - rowptr_host[a]) > (rowptr_host[b + 1] - rowptr_host[b]);
     });
-    if (ctx->d_order == nullptr) CU(cudaMalloc(&ctx->d_order, sizeof(int32_t) * std::max<size_t>(1, (size_t)ctx->n)));
-    if (cnt > 0) CU(cudaMemcpy(ctx->d_order, order.data(), sizeof(int32_t) * (size_t)cnt, cudaMemcpyHostToDevice));
+    std::vector<NodeMeta> meta((size_t)cnt);
+    for (int64_t i = 0; i < cnt; ++i) {
+        const int32_t u = order[(size_t)i];
+        meta[(size_t)i].u = u;
+        meta[(size_t)i].deg = (int32_t)(rowptr_host[u + 1] - rowptr_host[u]);
+        meta[(size_t)i].e0 = rowptr_host[u];
+    }
+    if (ctx->d_meta == nullptr) CU(cudaMalloc(&ctx->d_meta, sizeof(NodeMeta) * std::max<size_t>(1, (size_t)ctx->n)));
+    if (cnt > 0) CU(cudaMemcpy(ctx->d_meta, meta.data(), sizeof(NodeMeta) * (size_t)cnt, cudaMemcpyHostToDevice));
     ctx->order_n = cnt;
     return BIGCLAM_OK;
 }
@@ -209,7 +225,8 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     const int ld2 = ld / 2;
     const int c2raw = (ld2 + 31) / 32;
     ctx->c2 = c2raw <= 1 ? 1 : c2raw <= 2 ? 2 : c2raw <= 4 ? 4 : c2raw <= 8 ? 8 : 16;
-    ctx->smem_bytes = sizeof(double) * ((size_t)ld * (1 + 2 * kWarpsPerBlock) + (size_t)kWarpsPerBlock * 3 * kMaxActive);
+    ctx->maxm = std::min<int32_t>(ld, kMaxActiveCap);
+    ctx->smem_bytes = block_smem_bytes(ld, ctx->maxm);
 
 #define CUC(call)                                                                                 \
     do {                                                                                          \
@@ -246,6 +263,7 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
         return BIGCLAM_ECUDA;
     }
     ctx->grid = ctx->num_sms * bps;
+    ctx->h_work_init = 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
 
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
@@ -260,6 +278,7 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     CUC(cudaMalloc(&ctx->d_accepted, (size_t)n));
     CUC(cudaMalloc(&ctx->d_mask, (size_t)n));
     CUC(cudaMalloc(&ctx->d_done, sizeof(int32_t)));
+    CUC(cudaMalloc(&ctx->d_work, sizeof(unsigned int)));
     CUC(cudaMalloc(&ctx->d_state, sizeof(RunState)));
     CUC(cudaMallocHost(&ctx->h_pinned, sizeof(double) * (2 * (size_t)ld + 2) + sizeof(RunState) + 64));
     CUC(cudaMemcpy(ctx->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
@@ -386,7 +405,9 @@ static void fill_args(bigclam_ctx *ctx, StepArgs &a, bool linesearch, const uint
     a.t_hi = std::log(1.0 - p.min_p);
     a.w_lo = 1.0 / (1.0 - p.max_p);
     a.w_hi = 1.0 / (1.0 - p.min_p);
-    a.order = ctx->d_order;
+    a.meta = ctx->d_meta;
+    a.work_counter = ctx->d_work;
+    a.maxm = ctx->maxm;
     a.order_n = ctx->order_n;
     a.node_mask = d_mask;
     a.partials = ctx->d_partials;
@@ -404,6 +425,11 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
             ctx->ev_pool.push_back(e);
         }
         CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
+    }
+    {   // positions 0 .. 3*#warps-1 are pre-assigned statically, the rest is handed out dynamically
+        const unsigned int first = 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
+        CU(cudaMemcpyAsync(ctx->d_work, &ctx->h_work_init, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+        (void)first;
     }
     launch_step(ctx->c2, a, ctx->grid, ctx->smem_bytes, ctx->stream);
     CU(cudaGetLastError());

@@ -5,19 +5,31 @@
 //                   llh_u = sum_v (log(1-p)+x) - fu.sumF + fu.fu
 //   LS    :172-182  16 candidates s_j, nf_j = clamp(fu + s_j*grad), Armijo test, max passing s
 //   SWAP  :183-190  F_out[u] = nf_{j*} (or fu when nothing passes)  — Jacobi: only F_in is read
-//   partial reductions for :191-192 (sum of old rows, sum of new rows) and for the LLH
+//   partial reductions for :191-192 (sum over accepted nodes of old - new rows) and for the LLH
 //   (sum_u llh_u == the LLH the previous call returns, :196-219).
 //
 // Layout: F is n x ld fp64 row-major, ld = K rounded up to a multiple of 4 (32-byte sectors,
 // 16-byte double2 loads); padding columns are zero and stay zero.  Lane l of the warp owns the
 // double2 chunks q = l + 32c (components 2q, 2q+1), so a row load is C2 coalesced LDG.128.
 //
-// Line search, sparse path: a component can only matter in nf_j . fv if nf_j is non-zero for
-// some j, i.e. fu_i > 0 or grad_i > 0 (MIN_F_ = 0).  Those "active" components (typically the
-// node's few communities) are compacted into shared memory; lanes then re-map to (trial j, edge
-// parity) and each lane evaluates its own trial for its own edges — every exp/log of the
-// 16 x deg grid is computed by exactly one lane.  Rows with more than MAXM active components,
-// or MIN_F_ != 0, take the dense path (lane-owned components, one trial at a time, early exit).
+// Memory pipeline: nodes are visited hubs-first through a packed 16-byte NodeMeta record handed
+// out by an atomic work counter two nodes ahead; while node i is processed the warp already
+// holds node i+1's neighbour ids and own row and has issued prefetch.global.L2 for node i+1's
+// neighbour rows, so the HBM latency of the gather is off the dependent chain.
+//
+// Line search ("pair list"): a component can only matter in nf_j . fv if nf_j can be non-zero,
+// i.e. fu_i > 0 or grad_i > 0 (MIN_F_ = 0).  Those m "active" components are compacted into shared
+// memory; for every edge the warp gathers fv at the active components with one LDG per 32 of them
+// and keeps only the non-zero products' operands (t, fv_t) — typically ~3 per edge.  Lanes then
+// re-map to (trial j, edge parity) and each lane accumulates its own trial's dot over the pairs
+// and evaluates exp/log for it: every point of the 16 x deg grid is computed by exactly one lane.
+// Rows with more active components than the shared-memory lists hold, or MIN_F_ != 0, take the
+// dense path (lane-owned components, one candidate at a time, early exit).
+//
+// exp/log: the clamped edge term is only evaluated for x in (x_lo, x_hi) = (-log MAX_P, -log MIN_P)
+// (outside, the clamp makes it a constant + x), so exp(-x) and log(1-p) see a small, benign domain
+// and are written branch-free here (<= 1 ulp, checked against mpmath in tests/test_oracle.py's twin
+// of these formulas) instead of paying for libdevice's special-case handling.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,8 +38,14 @@ namespace bigclam {
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
-constexpr int kMaxActive = 64;      // active-set capacity of the sparse line-search path
 constexpr int kMaxSteps = 64;       // MaxInter + 1 <= kMaxSteps
+constexpr int kMaxActiveCap = 256;  // upper bound of the active-set lists (and of pair-list t)
+
+struct NodeMeta {   // one record per visited node, in processing order
+    int32_t u;
+    int32_t deg;
+    int64_t e0;
+};
 
 struct StepArgs {
     int64_t n;
@@ -38,18 +56,31 @@ struct StepArgs {
     const double *sumF;
     int32_t k, ld;
     int32_t nsteps;
+    int32_t maxm;             // capacity of the active-set / pair lists (per warp)
     double steps[kMaxSteps];
     double alpha, min_p, max_p, min_f, max_f;
-    // thresholds/constants of the clamped edge term (exact shortcuts, see edge_eval)
+    // thresholds/constants of the clamped edge term (exact shortcuts, see edge_term)
     double x_lo, x_hi, t_lo, t_hi, w_lo, w_hi;
-    const int32_t *order;     // processing order (degree descending) over the owned nodes
+    const NodeMeta *meta;     // processing order (degree descending) over the owned nodes
     int64_t order_n;
+    unsigned int *work_counter;   // next position to hand out (host sets it to 3 * #warps)
     const uint8_t *node_mask; // optional uset
-    double *partials;         // [A(ld) | B(ld) | llh | n_updated]
+    double *partials;         // [D(ld) = sum(old - new) | unused(ld) | llh | n_updated]
     int8_t *accepted;         // optional, n
     const int32_t *done_flag; // optional: non-zero -> the launch is a no-op
     int32_t do_linesearch;    // 0: PRE/LLH only (loglikelihood())
 };
+
+// shared-memory carve-up per warp; must match host sizing
+//   D[ld] f64 | afg[maxm] (fu,g) double2 | pval[maxm] f64 | aidx[maxm] u16 | poff[34] u16 | pt[maxm] u8
+__host__ __device__ inline size_t warp_smem_bytes(int ld, int maxm) {
+    size_t b = sizeof(double) * ((size_t)ld + 3 * (size_t)maxm) + 2 * (size_t)maxm + 2 * 34 + (size_t)maxm;
+    return (b + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t block_smem_bytes(int ld, int maxm) {
+    // sumF[ld] | steps[kMaxSteps] | per-warp regions
+    return sizeof(double) * ((size_t)ld + kMaxSteps) + (size_t)kWarpsPerBlock * warp_smem_bytes(ld, maxm);
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -61,32 +92,165 @@ __device__ __forceinline__ double2 ldg2(const double *p) {
     return __ldg(reinterpret_cast<const double2 *>(p));
 }
 
-// step(), bigclam4-7.scala:110-113: product and sum rounded separately (the JVM never fuses).
-__device__ __forceinline__ double clamp_step(double f, double s, double g, double lo, double hi) {
-    return fmin(fmax(__dadd_rn(f, __dmul_rn(s, g)), lo), hi);
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+
+// ---------------------------------------------------------------------------------------------
+// exp(-x) for x in (0, ~9.3): n = rint(-x log2 e), r = -x - n ln2 (two-step FMA reduction),
+// degree-13 Taylor of e^r on |r| <= ln2/2 (truncation 4e-18), scale by adding n to the exponent.
+__device__ __forceinline__ double exp_neg(double x) {
+    const double kMagic = 6755399441055744.0;                       // 1.5 * 2^52
+    const double t = fma(-x, 1.4426950408889634, kMagic);
+    const int n = __double2loint(t);
+    const double nf = t - kMagic;
+    double r = fma(nf, -0.6931471805599453094, -x);
+    r = fma(nf, -2.3190468138462996e-17, r);
+    double p = 1.6059043836821613e-10;                               // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);                             // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);                            // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);                            // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);                           // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);                             // 1/8!
+    p = fma(p, r, 0.0001984126984126984);                            // 1/7!
+    p = fma(p, r, 0.001388888888888889);                             // 1/6!
+    p = fma(p, r, 0.008333333333333333);                             // 1/5!
+    p = fma(p, r, 0.041666666666666664);                             // 1/4!
+    p = fma(p, r, 0.16666666666666666);                              // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+// 1/d for normal positive d: rcp.approx (2^-23) + two Newton steps.
+__device__ __forceinline__ double rcp_pos(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
+
+// log(y) for normal y in (0, 1]: y = 2^e m, m in [sqrt(1/2), sqrt 2], s = (m-1)/(m+1),
+// log m = 2s + s z (2/3 + 2/5 z + ... + 2/23 z^10), z = s^2 <= 0.0295 (truncation 6e-19).
+__device__ __forceinline__ double log_pos(double y) {
+    const int hi = __double2hiint(y);
+    int e = (hi >> 20) - 1023;
+    int mh = (hi & 0x000fffff) | 0x3ff00000;
+    if (mh > 0x3ff6a09e) { mh -= 0x00100000; e += 1; }
+    const double m = __hiloint2double(mh, __double2loint(y));
+    const double f = m - 1.0, d = m + 1.0;
+    const double rd = rcp_pos(d);
+    double s = f * rd;
+    s = fma(fma(-d, s, f), rd, s);
+    const double z = s * s;
+    double q = 0.08695652173913043;          // 2/23
+    q = fma(q, z, 0.09523809523809523);      // 2/21
+    q = fma(q, z, 0.10526315789473684);      // 2/19
+    q = fma(q, z, 0.11764705882352941);      // 2/17
+    q = fma(q, z, 0.13333333333333333);      // 2/15
+    q = fma(q, z, 0.15384615384615385);      // 2/13
+    q = fma(q, z, 0.18181818181818182);      // 2/11
+    q = fma(q, z, 0.2222222222222222);       // 2/9
+    q = fma(q, z, 0.2857142857142857);       // 2/7
+    q = fma(q, z, 0.4);                      // 2/5
+    q = fma(q, z, 0.6666666666666666);       // 2/3
+    const double ed = (double)e;
+    const double inner = fma(ed, 2.3190468138462996e-17, (s * z) * q);
+    return fma(ed, 0.6931471805599453094, fma(2.0, s, inner));
+}
+
+// Constants of the clamped edge term kept in registers.
+struct EdgeConst {
+    double x_lo, x_hi, t_lo, t_hi, w_lo, w_hi;
+};
 
 // log(1 - clamp(exp(-x), MIN_P, MAX_P)) + x and 1/(1 - p)   (bigclam4-7.scala:166-167).
-// Shortcuts are exact: x == 0 or x <= x_lo gives p == MAX_P after the clamp, x >= x_hi gives
-// p == MIN_P; x_lo/x_hi carry a 1e-12 safety margin so the clamp outcome is never in doubt.
+// Exact shortcuts: x <= x_lo gives p == MAX_P after the clamp, x >= x_hi gives p == MIN_P
+// (x_lo/x_hi carry a 1e-12 safety margin so the clamp outcome is never in doubt); in between the
+// clamp is a no-op.  Must be called by all 32 lanes (warp-uniform skip of the transcendental).
 template <bool kNeedW>
-__device__ __forceinline__ void edge_eval(double x, const StepArgs &a, double &t, double &w) {
-    if (x <= a.x_lo) { t = a.t_lo + x; if (kNeedW) w = a.w_lo; return; }
-    if (x >= a.x_hi) { t = a.t_hi + x; if (kNeedW) w = a.w_hi; return; }
-    double p = fmin(fmax(exp(-x), a.min_p), a.max_p);
-    double omp = 1.0 - p;
-    t = log(omp) + x;
-    if (kNeedW) w = 1.0 / omp;
+__device__ __forceinline__ double edge_term(double x, const EdgeConst &c, double &w) {
+    const bool low = x <= c.x_lo;
+    const bool need = !low && (x < c.x_hi);
+    double t = low ? c.t_lo : c.t_hi;
+    if (kNeedW) w = low ? c.w_lo : c.w_hi;
+    if (__any_sync(0xffffffffu, need)) {
+        const double xs = need ? x : 1.0;
+        const double omp = 1.0 - exp_neg(xs);
+        const double tf = log_pos(omp);
+        t = need ? tf : t;
+        if (kNeedW) {
+            const double wf = rcp_pos(omp);
+            w = need ? wf : w;
+        }
+    }
+    return t + x;
 }
 
-template <int C2> struct RowsInFlight { static constexpr int value = (C2 <= 4) ? 4 : (C2 <= 8 ? 2 : 1); };
+// step(), bigclam4-7.scala:110-113: product and sum rounded separately (the JVM never fuses).
+__device__ __forceinline__ double clamp_step(double f, double s, double g, double lo, double hi) {
+    double x = __dadd_rn(f, __dmul_rn(s, g));
+    x = (x < lo) ? lo : x;
+    return (x > hi) ? hi : x;
+}
+// Same with MIN_F_ == 0: the lower clamp is a sign test (also maps -0.0 to +0.0 like Math.max).
+__device__ __forceinline__ double clamp_step0(double f, double s, double g, double hi) {
+    double x = __dadd_rn(f, __dmul_rn(s, g));
+    x = (__double2hiint(x) < 0) ? 0.0 : x;
+    return (x > hi) ? hi : x;
+}
+
+// L2 prefetch of the rows of up to 32 neighbours (lane l < cnt owns row myv).
+__device__ __forceinline__ void prefetch_rows(const double *F, int ld, int lane, int myv, int cnt) {
+    if (lane < cnt) {
+        const char *row = reinterpret_cast<const char *>(F + (size_t)myv * ld);
+        const int bytes = ld * 8;
+        for (int off = 0; off < bytes; off += 128) prefetch_l2(row + off);
+        prefetch_l2(row + bytes - 8);
+    }
+}
+
+// Sum R per-lane partials across the warp; the total of partial r is returned to lane (eb + r).
+template <int R>
+__device__ __forceinline__ double reduce_to_lanes(double (&part)[R], int lane, int eb, double myx) {
+    if constexpr (R == 4) {
+        // transposed butterfly: 6 shuffles instead of 20
+        const bool b4 = lane & 16, b3 = lane & 8;
+        double k0 = b4 ? part[2] : part[0], k1 = b4 ? part[3] : part[1];
+        const double s0 = b4 ? part[0] : part[2], s1 = b4 ? part[1] : part[3];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        double k = b3 ? k1 : k0;
+        const double sd = b3 ? k0 : k1;
+        k += __shfl_xor_sync(0xffffffffu, sd, 8);
+        k += __shfl_xor_sync(0xffffffffu, k, 4);
+        k += __shfl_xor_sync(0xffffffffu, k, 2);
+        k += __shfl_xor_sync(0xffffffffu, k, 1);
+        // total of part[r] now sits in the lanes with (bit4, bit3) == (r >> 1, r & 1)
+        const int r = (lane - eb) & 3;
+        const double got = __shfl_sync(0xffffffffu, k, ((r & 2) << 3) | ((r & 1) << 3));
+        return ((unsigned)(lane - eb) < 4u) ? got : myx;
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) part[r] += __shfl_xor_sync(0xffffffffu, part[r], o);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (lane == eb + r) myx = part[r];
+        return myx;
+    }
+}
 
 // Dots of `vec` (lane-owned components) with the rows of up to 32 neighbours; lane e returns
-// the dot for neighbour e of the chunk.
-template <int C2>
+// the dot for neighbour e of the chunk.  R rows are in flight per batch.
+template <int C2, int R>
 __device__ __forceinline__ double chunk_dots(const double2 (&vec)[C2], const double *__restrict__ F,
                                              int ld, int ld2, int lane, int myv, int cnt) {
-    constexpr int R = RowsInFlight<C2>::value;
     double myx = 0.0;
     for (int eb = 0; eb < cnt; eb += R) {
         double part[R];
@@ -109,56 +273,128 @@ __device__ __forceinline__ double chunk_dots(const double2 (&vec)[C2], const dou
             }
             part[r] = p;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) part[r] += __shfl_xor_sync(0xffffffffu, part[r], o);
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (lane == eb + r) myx = part[r];
+        myx = reduce_to_lanes<R>(part, lane, eb, myx);
     }
     return myx;
 }
 
-template <int C2>
-__global__ void __launch_bounds__(kBlockThreads) step_kernel(const StepArgs a) {
+// Dense line search (cold path): lane-owned components, candidates in descending order, early exit.
+template <int C2, int R>
+__device__ __noinline__ int dense_linesearch(const StepArgs &a, const double2 (&fu)[C2], const double2 (&g)[C2],
+                                             const double *s_sumF, int64_t e0, int deg, int lane,
+                                             double llh_u, double G2) {
+    const int ld = a.ld, ld2 = a.ld >> 1;
+    const double *__restrict__ F = a.F_in;
+    const EdgeConst ec = {a.x_lo, a.x_hi, a.t_lo, a.t_hi, a.w_lo, a.w_hi};
+    for (int j = 0; j < a.nsteps; ++j) {
+        const double s = a.steps[j];
+        double2 nf[C2];
+        double oa = 0.0, ob = 0.0;
+#pragma unroll
+        for (int c = 0; c < C2; ++c) {
+            const int q = lane + 32 * c;
+            nf[c] = make_double2(0.0, 0.0);
+            if (q < ld2) {
+                const double2 sf = *reinterpret_cast<const double2 *>(s_sumF + 2 * q);
+                nf[c].x = clamp_step(fu[c].x, s, g[c].x, a.min_f, a.max_f);
+                nf[c].y = clamp_step(fu[c].y, s, g[c].y, a.min_f, a.max_f);
+                oa = fma(nf[c].x, (sf.x - fu[c].x) + nf[c].x, oa);
+                oa = fma(nf[c].y, (sf.y - fu[c].y) + nf[c].y, oa);
+                ob = fma(nf[c].x, nf[c].x, ob);
+                ob = fma(nf[c].y, nf[c].y, ob);
+            }
+        }
+        oa = warp_sum(oa);
+        ob = warp_sum(ob);
+        double sumterms = 0.0;
+        for (int cb = 0; cb < deg; cb += 32) {
+            const int cnt = min(32, deg - cb);
+            const int myv = (lane < cnt) ? a.col[e0 + cb + lane] : 0;
+            const double myx = chunk_dots<C2, R>(nf, F, ld, ld2, lane, myv, cnt);
+            double w;
+            const double t = edge_term<false>(myx, ec, w);
+            sumterms += warp_sum(lane < cnt ? t : 0.0);
+        }
+        const double result = (sumterms - oa) + ob;
+        const double rhs = llh_u + (a.alpha * s) * G2;
+        if (result >= rhs) return j;
+    }
+    return -1;
+}
+
+template <int C2, int R>
+__global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(const StepArgs a) {
     if (a.done_flag != nullptr && *a.done_flag != 0) return;
 
-    extern __shared__ double smem[];
-    const int ld = a.ld, ld2 = a.ld >> 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ld = a.ld, ld2 = a.ld >> 1, maxm = a.maxm;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double *s_sumF = smem;                                  // ld
-    double *s_A = smem + ld + (size_t)wib * 2 * ld;         // per warp: A(ld) | B(ld)
-    double *s_B = s_A + ld;
-    double *s_lists = smem + ld + (size_t)kWarpsPerBlock * 2 * ld;
-    double *s_afu = s_lists + (size_t)wib * 3 * kMaxActive; // per warp: fu | g | idx (as int)
-    double *s_ag = s_afu + kMaxActive;
-    int *s_aidx = reinterpret_cast<int *>(s_ag + kMaxActive);
+    double *s_sumF = reinterpret_cast<double *>(smem_raw);
+    double *s_steps = s_sumF + ld;
+    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_steps + kMaxSteps) + (size_t)wib * warp_smem_bytes(ld, maxm);
+    double *s_D = reinterpret_cast<double *>(wbase);
+    double2 *s_afg = reinterpret_cast<double2 *>(s_D + ld);
+    double *s_pval = reinterpret_cast<double *>(s_afg + maxm);
+    unsigned short *s_aidx = reinterpret_cast<unsigned short *>(s_pval + maxm);
+    unsigned short *s_poff = s_aidx + maxm;
+    unsigned char *s_pt = reinterpret_cast<unsigned char *>(s_poff + 34);
 
     for (int i = threadIdx.x; i < ld; i += kBlockThreads) s_sumF[i] = a.sumF[i];
-    for (int i = lane; i < 2 * ld; i += 32) s_A[i] = 0.0;
+    for (int i = threadIdx.x; i < kMaxSteps; i += kBlockThreads) s_steps[i] = a.steps[i];
+    for (int i = lane; i < ld; i += 32) s_D[i] = 0.0;
     __syncthreads();
 
+    const EdgeConst ec = {a.x_lo, a.x_hi, a.t_lo, a.t_hi, a.w_lo, a.w_hi};
+    const double max_f = a.max_f;
+    const int nsteps = a.nsteps;
+    const int64_t order_n = a.order_n;
     double llh_acc = 0.0;
     double nupd_acc = 0.0;
-    const int64_t warp_global = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
     const double *__restrict__ F = a.F_in;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
-    for (int64_t pos = warp_global; pos < a.order_n; pos += nwarps) {
-        const int64_t u = a.order[pos];
-        const int64_t e0 = a.rowptr[u];
-        const int deg = (int)(a.rowptr[u + 1] - e0);
-        const double *frow = F + (size_t)u * ld;
+    // software pipeline: cur (being processed), nxt (meta in registers; ids + own row loaded at the
+    // top of cur's iteration, rows prefetched to L2), pos_nn (position handed out for the node after)
+    int64_t pos = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+    int64_t pos_n = pos + nwarps, pos_nn = pos + 2 * nwarps;
+    NodeMeta cur = {0, 0, 0}, nxt = {0, 0, 0};
+    if (pos < order_n) cur = a.meta[pos];
+    if (pos_n < order_n) nxt = a.meta[pos_n];
+    int myv = (lane < min(32, cur.deg)) ? a.col[cur.e0 + lane] : 0;
+    double2 fu[C2];
+#pragma unroll
+    for (int c = 0; c < C2; ++c) {
+        const int q = lane + 32 * c;
+        fu[c] = (pos < order_n && q < ld2) ? ldg2(F + (size_t)cur.u * ld + 2 * q) : make_double2(0.0, 0.0);
+    }
+    prefetch_rows(F, ld, lane, myv, min(32, cur.deg));
+
+    while (pos < order_n) {
+        const int64_t u = cur.u;
+        const int64_t e0 = cur.e0;
+        const int deg = cur.deg;
         double *orow = a.F_out + (size_t)u * ld;
 
-        double2 fu[C2];
+        // ---- issue the next nodes' loads (consumed at the bottom of this iteration) ----
+        const bool has_next = pos_n < order_n;
+        NodeMeta nn = {0, 0, 0};
+        if (pos_nn < order_n) nn = a.meta[pos_nn];
+        unsigned int fetched = 0;
+        if (lane == 0) fetched = atomicAdd(a.work_counter, 1u);
+        const int ncnt = has_next ? min(32, nxt.deg) : 0;
+        const int nmyv = (lane < ncnt) ? a.col[nxt.e0 + lane] : 0;
+        double2 nfu[C2];
+#pragma unroll
+        for (int c = 0; c < C2; ++c) {
+            const int q = lane + 32 * c;
+            nfu[c] = (has_next && q < ld2) ? ldg2(F + (size_t)nxt.u * ld + 2 * q) : make_double2(0.0, 0.0);
+        }
+
         double fusf = 0.0, fufu = 0.0;
 #pragma unroll
         for (int c = 0; c < C2; ++c) {
             const int q = lane + 32 * c;
-            fu[c] = (q < ld2) ? ldg2(frow + 2 * q) : make_double2(0.0, 0.0);
             if (q < ld2) {
                 const double2 sf = *reinterpret_cast<const double2 *>(s_sumF + 2 * q);
                 fusf = fma(fu[c].x, sf.x, fusf); fusf = fma(fu[c].y, sf.y, fusf);
@@ -175,12 +411,17 @@ __global__ void __launch_bounds__(kBlockThreads) step_kernel(const StepArgs a) {
         double S1 = 0.0;
         for (int cb = 0; cb < deg; cb += 32) {
             const int cnt = min(32, deg - cb);
-            const int myv = (lane < cnt) ? a.col[e0 + cb + lane] : 0;
-            const double myx = chunk_dots<C2>(fu, F, ld, ld2, lane, myv, cnt);
-            double t = 0.0, w = 0.0;
-            if (lane < cnt) edge_eval<true>(myx, a, t, w);
-            S1 += warp_sum(t);
+            // neighbour ids of the chunk after this one (hubs): loaded now, prefetched after the dots
+            const int cnt2 = min(32, max(0, deg - cb - 32));
+            const int myv2 = (lane < cnt2) ? a.col[e0 + cb + 32 + lane] : 0;
+            const double myx = chunk_dots<C2, R>(fu, F, ld, ld2, lane, myv, cnt);
+            if (cb == 0) prefetch_rows(F, ld, lane, nmyv, ncnt);
+            if (cnt2 > 0) prefetch_rows(F, ld, lane, myv2, cnt2);
+            double w;
+            const double t = edge_term<true>(myx, ec, w);
+            S1 += warp_sum(lane < cnt ? t : 0.0);
             if (a.do_linesearch) {
+#pragma unroll 2
                 for (int e = 0; e < cnt; ++e) {
                     const int v = __shfl_sync(0xffffffffu, myv, e);
                     const double we = __shfl_sync(0xffffffffu, w, e);
@@ -196,7 +437,9 @@ __global__ void __launch_bounds__(kBlockThreads) step_kernel(const StepArgs a) {
                     }
                 }
             }
+            myv = myv2;
         }
+        if (deg == 0) prefetch_rows(F, ld, lane, nmyv, ncnt);
         const double llh_u = (S1 - fusf) + fufu;
         llh_acc += llh_u;
 
@@ -232,62 +475,100 @@ __global__ void __launch_bounds__(kBlockThreads) step_kernel(const StepArgs a) {
                         const double gval = hh ? g[c].y : g[c].x;
                         const bool act = (q < ld2) && (fval > 0.0 || gval > 0.0);
                         const unsigned bal = __ballot_sync(0xffffffffu, act);
-                        if (act) {
-                            const int posn = m + __popc(bal & ((1u << lane) - 1u));
-                            if (posn < kMaxActive) {
-                                s_afu[posn] = fval;
-                                s_ag[posn] = gval;
-                                s_aidx[posn] = 2 * q + hh;
+                        if (bal) {
+                            if (act) {
+                                const int posn = m + __popc(bal & lt_mask);
+                                if (posn < maxm) {
+                                    s_afg[posn] = make_double2(fval, gval);
+                                    s_aidx[posn] = (unsigned short)(2 * q + hh);
+                                }
                             }
+                            m += __popc(bal);
                         }
-                        m += __popc(bal);
                     }
                 }
                 __syncwarp();
             }
 
-            if (sparse_ok && m <= kMaxActive) {
-                // ---------------- LS, sparse path: lane = (trial j, edge parity h) ----------------
+            if (sparse_ok && m <= maxm) {
+                // ---------------- LS, pair-list path ----------------
                 const int j16 = lane & 15, h = lane >> 4;
-                for (int tg = 0; tg < a.nsteps && jstar < 0; tg += 16) {
+                // edges per chunk such that every edge's pairs (<= m) fit the list
+                int ce_max = (m > 0) ? min(32, maxm / m) : 32;
+                if (ce_max > 1) ce_max &= ~1;
+                const int my_idx0 = (lane < m) ? (int)s_aidx[lane] : 0;
+                for (int tg = 0; tg < nsteps && jstar < 0; tg += 16) {
                     const int j = tg + j16;
-                    const bool jok = j < a.nsteps;
-                    const double s = a.steps[jok ? j : 0];
+                    const bool jok = j < nsteps;
+                    const double s = s_steps[jok ? j : 0];
                     double sumterms = 0.0;
-                    for (int cb = 0; cb < deg; cb += 8) {
-                        int v[4];
-                        bool ok[4];
-                        double acc[4];
+                    for (int cb = 0; cb < deg; cb += ce_max) {
+                        const int ce = min(ce_max, deg - cb);
+                        const int cv = (lane < ce) ? a.col[e0 + cb + lane] : 0;
+                        // build: for every edge keep (t, fv[idx_t]) with fv != 0
+                        int np = 0;
+                        if (lane == 0) s_poff[0] = 0;
+                        for (int eb = 0; eb < ce; eb += 4) {
+                            double val[4];
 #pragma unroll
-                        for (int qq = 0; qq < 4; ++qq) {
-                            const int e = cb + 2 * qq + h;
-                            ok[qq] = e < deg;
-                            v[qq] = ok[qq] ? a.col[e0 + e] : 0;
-                            acc[qq] = 0.0;
-                        }
-                        for (int t = 0; t < m; ++t) {
-                            const double nf = clamp_step(s_afu[t], s, s_ag[t], 0.0, a.max_f);
-                            const int idx = s_aidx[t];
+                            for (int r = 0; r < 4; ++r) {          // 4 gathers in flight
+                                const int v = __shfl_sync(0xffffffffu, cv, (eb + r) & 31);
+                                val[r] = (eb + r < ce && lane < m) ? __ldg(F + (size_t)v * ld + my_idx0) : 0.0;
+                            }
 #pragma unroll
-                            for (int qq = 0; qq < 4; ++qq)
-                                if (ok[qq]) acc[qq] = fma(nf, __ldg(F + (size_t)v[qq] * ld + idx), acc[qq]);
-                        }
-#pragma unroll
-                        for (int qq = 0; qq < 4; ++qq) {
-                            if (ok[qq] && jok) {
-                                double t, w;
-                                edge_eval<false>(acc[qq], a, t, w);
-                                sumterms += t;
+                            for (int r = 0; r < 4; ++r) {
+                                if (eb + r < ce) {
+                                    unsigned bal = __ballot_sync(0xffffffffu, val[r] != 0.0);
+                                    if (val[r] != 0.0) {
+                                        const int pp = np + __popc(bal & lt_mask);
+                                        s_pval[pp] = val[r];
+                                        s_pt[pp] = (unsigned char)lane;
+                                    }
+                                    np += __popc(bal);
+                                    if (m > 32) {                  // rare: more than one gather round per edge
+                                        const int v = __shfl_sync(0xffffffffu, cv, (eb + r) & 31);
+                                        const double *fv = F + (size_t)v * ld;
+                                        for (int tb = 32; tb < m; tb += 32) {
+                                            const int t = tb + lane;
+                                            const double vv = (t < m) ? __ldg(fv + s_aidx[t]) : 0.0;
+                                            bal = __ballot_sync(0xffffffffu, vv != 0.0);
+                                            if (vv != 0.0) {
+                                                const int pp = np + __popc(bal & lt_mask);
+                                                s_pval[pp] = vv;
+                                                s_pt[pp] = (unsigned char)t;
+                                            }
+                                            np += __popc(bal);
+                                        }
+                                    }
+                                    if (lane == 0) s_poff[eb + r + 1] = (unsigned short)np;
+                                }
                             }
                         }
+                        __syncwarp();
+                        // consume: lane (j, h) walks the pairs of edge e = 2q + h
+                        for (int e2 = 0; e2 < ce; e2 += 2) {
+                            const int e = e2 + h;
+                            const bool valid = e < ce;
+                            const int i0 = valid ? (int)s_poff[e] : 0;
+                            const int i1 = valid ? (int)s_poff[e + 1] : 0;
+                            double D = 0.0;
+                            for (int i = i0; i < i1; ++i) {
+                                const double2 fg = s_afg[s_pt[i]];
+                                D = fma(clamp_step0(fg.x, s, fg.y, max_f), s_pval[i], D);
+                            }
+                            double w;
+                            const double t = edge_term<false>(D, ec, w);
+                            sumterms += valid ? t : 0.0;
+                        }
+                        __syncwarp();
                     }
                     sumterms += __shfl_xor_sync(0xffffffffu, sumterms, 16);
                     // - newfu.sfT + newfu.newfu with sfT = (sumF - fu) + newfu   (:176,:180)
                     double oa = 0.0, ob = 0.0;
                     for (int t = h; t < m; t += 2) {
-                        const double fut = s_afu[t];
-                        const double nf = clamp_step(fut, s, s_ag[t], 0.0, a.max_f);
-                        const double sf = (s_sumF[s_aidx[t]] - fut) + nf;
+                        const double2 fg = s_afg[t];
+                        const double nf = clamp_step0(fg.x, s, fg.y, max_f);
+                        const double sf = (s_sumF[s_aidx[t]] - fg.x) + nf;
                         oa = fma(nf, sf, oa);
                         ob = fma(nf, nf, ob);
                     }
@@ -298,62 +579,27 @@ __global__ void __launch_bounds__(kBlockThreads) step_kernel(const StepArgs a) {
                     const unsigned pass = __ballot_sync(0xffffffffu, jok && (result >= rhs)) & 0xffffu;
                     if (pass) jstar = tg + __ffs(pass) - 1;   // lowest j == largest step (:182 max)
                 }
-                __syncwarp();
             } else {
-                // ---------------- LS, dense path: one candidate at a time, descending ----------------
-                for (int j = 0; j < a.nsteps && jstar < 0; ++j) {
-                    const double s = a.steps[j];
-                    double2 nf[C2];
-                    double oa = 0.0, ob = 0.0;
-#pragma unroll
-                    for (int c = 0; c < C2; ++c) {
-                        const int q = lane + 32 * c;
-                        nf[c] = make_double2(0.0, 0.0);
-                        if (q < ld2) {
-                            const double2 sf = *reinterpret_cast<const double2 *>(s_sumF + 2 * q);
-                            nf[c].x = clamp_step(fu[c].x, s, g[c].x, a.min_f, a.max_f);
-                            nf[c].y = clamp_step(fu[c].y, s, g[c].y, a.min_f, a.max_f);
-                            oa = fma(nf[c].x, (sf.x - fu[c].x) + nf[c].x, oa);
-                            oa = fma(nf[c].y, (sf.y - fu[c].y) + nf[c].y, oa);
-                            ob = fma(nf[c].x, nf[c].x, ob);
-                            ob = fma(nf[c].y, nf[c].y, ob);
-                        }
-                    }
-                    oa = warp_sum(oa);
-                    ob = warp_sum(ob);
-                    double sumterms = 0.0;
-                    for (int cb = 0; cb < deg; cb += 32) {
-                        const int cnt = min(32, deg - cb);
-                        const int myv = (lane < cnt) ? a.col[e0 + cb + lane] : 0;
-                        const double myx = chunk_dots<C2>(nf, F, ld, ld2, lane, myv, cnt);
-                        double t = 0.0, w;
-                        if (lane < cnt) edge_eval<false>(myx, a, t, w);
-                        sumterms += warp_sum(t);
-                    }
-                    const double result = (sumterms - oa) + ob;
-                    const double rhs = llh_u + (a.alpha * s) * G2;
-                    if (result >= rhs) jstar = j;
-                }
+                jstar = dense_linesearch<C2, R>(a, fu, g, s_sumF, e0, deg, lane, llh_u, G2);
             }
         }
 
         // ---------------- SWAP (:183-190) + partial sums for :191-192 ----------------
         if (jstar >= 0) {
-            const double s = a.steps[jstar];
+            const double s = s_steps[jstar];
 #pragma unroll
             for (int c = 0; c < C2; ++c) {
                 const int q = lane + 32 * c;
                 if (q < ld2) {
                     double2 nr;
-                    nr.x = clamp_step(fu[c].x, s, g[c].x, a.min_f, a.max_f);
-                    nr.y = clamp_step(fu[c].y, s, g[c].y, a.min_f, a.max_f);
+                    nr.x = clamp_step(fu[c].x, s, g[c].x, a.min_f, max_f);
+                    nr.y = clamp_step(fu[c].y, s, g[c].y, a.min_f, max_f);
                     *reinterpret_cast<double2 *>(orow + 2 * q) = nr;
-                    double2 *pa = reinterpret_cast<double2 *>(s_A + 2 * q);
-                    double2 *pb = reinterpret_cast<double2 *>(s_B + 2 * q);
-                    double2 va = *pa, vb = *pb;
-                    va.x += fu[c].x; va.y += fu[c].y;
-                    vb.x += nr.x; vb.y += nr.y;
-                    *pa = va; *pb = vb;
+                    double2 *pd = reinterpret_cast<double2 *>(s_D + 2 * q);
+                    double2 vd = *pd;
+                    vd.x += fu[c].x - nr.x;
+                    vd.y += fu[c].y - nr.y;
+                    *pd = vd;
                 }
             }
             nupd_acc += 1.0;
@@ -365,15 +611,27 @@ __global__ void __launch_bounds__(kBlockThreads) step_kernel(const StepArgs a) {
             }
         }
         if (a.accepted != nullptr && lane == 0) a.accepted[u] = (int8_t)jstar;
+
+        // ---- rotate the pipeline ----
+        cur = nxt;
+        nxt = nn;
+        myv = nmyv;
+#pragma unroll
+        for (int c = 0; c < C2; ++c) fu[c] = nfu[c];
+        pos = pos_n;
+        pos_n = pos_nn;
+        pos_nn = (int64_t)__shfl_sync(0xffffffffu, fetched, 0);
     }
 
     // ---------------- block reduction of the partials, one RED per address per block ----------------
     __syncthreads();
     if (a.do_linesearch) {
-        for (int i = threadIdx.x; i < 2 * ld; i += kBlockThreads) {
+        const unsigned char *w0 = reinterpret_cast<const unsigned char *>(s_steps + kMaxSteps);
+        for (int i = threadIdx.x; i < ld; i += kBlockThreads) {
             double v = 0.0;
 #pragma unroll
-            for (int w = 0; w < kWarpsPerBlock; ++w) v += smem[ld + (size_t)w * 2 * ld + i];
+            for (int w = 0; w < kWarpsPerBlock; ++w)
+                v += reinterpret_cast<const double *>(w0 + (size_t)w * warp_smem_bytes(ld, maxm))[i];
             if (v != 0.0) atomicAdd(a.partials + i, v);
         }
     }
@@ -459,8 +717,8 @@ __global__ void finish_kernel(const FinishArgs f) {
         const bool any = f.partials[2 * ld + 1] > 0.0;
         for (int i = threadIdx.x; i < ld; i += blockDim.x) {
             const double sf = f.sumF_cur[i];
-            // sumF = sumF - (changeFu._1 - changeFu._2)   (:192)
-            f.sumF_next[i] = any ? sf - (f.partials[i] - f.partials[ld + i]) : sf;
+            // sumF = sumF - (changeFu._1 - changeFu._2)   (:192); partials[i] = sum over accepted nodes of (old - new)
+            f.sumF_next[i] = any ? sf - f.partials[i] : sf;
         }
     }
     __syncthreads();

@@ -1,0 +1,19 @@
+"""Small driver for ncu: com-amazon K=200, W warm-up steps then S steps through bigclam_run."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bigclam_apachespark_b200 import BigClam, graphs as G  # noqa: E402
+
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+W = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+name = sys.argv[4] if len(sys.argv) > 4 else "com-amazon"
+rp, col, _ = G.load_npz_graph(name)
+n = len(rp) - 1
+b = BigClam(device=0, time_kernels=True)
+b.set_graph(rp, col).set_K(K).set_F(G.synthetic_F0(n, K, seed=1234, density=0.05))
+b._run(4, 0.0, W)
+b._run(4, 0.0, S)
+ms, nk, nall = b.kernel_time()
+print(f"{name} K={K}: step kernel avg {ms / max(nk, 1):.3f} ms over {nk} launches, llh {b.last_trace[-1]:.6e}")
