@@ -55,53 +55,55 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region through NVML (the same counters
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints), every ~5 ms from a thread."""
 
     def __init__(self, index=0):
-        self.proc = None
-        self.lines = []
         self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml as N
+            N.nvmlInit()
+            self.N = N
+            self.h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+        except Exception as exc:            # noqa: BLE001
+            self.N = None
+            self.err = repr(exc)
+            return
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        N = self.N
+        bits = {"hw_slowdown": N.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": N.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": N.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)))
+                r = N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:               # noqa: BLE001
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx = float(f[1])
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.N is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self._stop.set()
+        self._t.join(timeout=1)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
 def time_oracle(rp, col, F0, steps, warmup):
@@ -227,15 +229,14 @@ def run_single(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
-        if args.steps > 5:
-            args.steps = 5          # bounded: each step is ~2-4 s of all-core CPU work
+        args.steps = min(args.steps, 20)     # bounded: each step is ~1-4 s of all-core CPU work
         args.warmup = min(args.warmup, 1)
         return run_reference(args)
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:

@@ -77,6 +77,7 @@ SIGNATURES = {
     "bigclam_step_local": (C.c_int, [_vp, C.POINTER(_vp)]),
     "bigclam_finish_local": (C.c_int, [_vp, _pd, _pi64]),
     "bigclam_llh_local": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "bigclam_rollback": (C.c_int, [_vp]),
     "bigclam_graph_read_edgelist": (C.c_int, [C.c_char_p, _i32, C.POINTER(Graph), C.c_char_p, _i64]),
     "bigclam_graph_free": (None, [C.POINTER(Graph)]),
     "bigclam_device_count": (C.c_int, []),

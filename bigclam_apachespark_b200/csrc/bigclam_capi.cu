@@ -426,11 +426,8 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
         }
         CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
     }
-    {   // positions 0 .. 3*#warps-1 are pre-assigned statically, the rest is handed out dynamically
-        const unsigned int first = 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
-        CU(cudaMemcpyAsync(ctx->d_work, &ctx->h_work_init, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
-        (void)first;
-    }
+    // positions 0 .. 3*#warps-1 are pre-assigned statically, the rest is handed out dynamically
+    CU(cudaMemcpyAsync(ctx->d_work, &ctx->h_work_init, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
     launch_step(ctx->c2, a, ctx->grid, ctx->smem_bytes, ctx->stream);
     CU(cudaGetLastError());
     if (timing) {
@@ -655,5 +652,11 @@ extern "C" int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev) {
     int rc = timed_launch(ctx, a, false);
     if (rc) return rc;
     if (partials_dev) *partials_dev = ctx->d_partials;
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_rollback(bigclam_ctx *ctx) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    ctx->cur ^= 1;
     return BIGCLAM_OK;
 }

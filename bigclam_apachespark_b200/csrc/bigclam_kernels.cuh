@@ -71,15 +71,19 @@ struct StepArgs {
     int32_t do_linesearch;    // 0: PRE/LLH only (loglikelihood())
 };
 
-// shared-memory carve-up per warp; must match host sizing
-//   D[ld] f64 | afg[maxm] (fu,g) double2 | pval[maxm] f64 | aidx[maxm] u16 | poff[34] u16 | pt[maxm] u8
-__host__ __device__ inline size_t warp_smem_bytes(int ld, int maxm) {
-    size_t b = sizeof(double) * ((size_t)ld + 3 * (size_t)maxm) + 2 * (size_t)maxm + 2 * 34 + (size_t)maxm;
-    return (b + 15) & ~(size_t)15;
-}
-__host__ __device__ inline size_t block_smem_bytes(int ld, int maxm) {
-    // sumF[ld] | steps[kMaxSteps] | per-warp regions
-    return sizeof(double) * ((size_t)ld + kMaxSteps) + (size_t)kWarpsPerBlock * warp_smem_bytes(ld, maxm);
+// Shared-memory carve-up.  Everything whose size does not depend on K sits at compile-time offsets
+// (so the compiler never recomputes list pointers from kernel parameters inside the loops):
+//   block: steps[kMaxSteps] f64 | kWarpsPerBlock x WarpLists | sumF[ld] f64 | kWarpsPerBlock x D[ld] f64
+struct __align__(16) WarpLists {
+    double2 afg[kMaxActiveCap];          // (fu_t, g_t) of the active components
+    double pval[kMaxActiveCap];          // pair list: fv value
+    unsigned short aidx[kMaxActiveCap];  // component index of active t
+    unsigned short poff[40];             // pair-list offsets per edge of the chunk (33 used)
+    unsigned char pt[kMaxActiveCap];     // pair list: active index t
+};
+__host__ __device__ inline size_t block_smem_bytes(int ld, int /*maxm*/) {
+    return sizeof(double) * kMaxSteps + (size_t)kWarpsPerBlock * sizeof(WarpLists) +
+           sizeof(double) * (size_t)ld * (1 + kWarpsPerBlock);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -203,13 +207,12 @@ __device__ __forceinline__ double clamp_step0(double f, double s, double g, doub
     return (x > hi) ? hi : x;
 }
 
-// L2 prefetch of the rows of up to 32 neighbours (lane l < cnt owns row myv).
+// L2 prefetch of the rows of up to 32 neighbours (lane l < cnt owns row myv): one bulk prefetch
+// (cp.async.bulk.prefetch.L2, the TMA path) per row instead of one prefetch per 128-byte line.
 __device__ __forceinline__ void prefetch_rows(const double *F, int ld, int lane, int myv, int cnt) {
     if (lane < cnt) {
-        const char *row = reinterpret_cast<const char *>(F + (size_t)myv * ld);
-        const int bytes = ld * 8;
-        for (int off = 0; off < bytes; off += 128) prefetch_l2(row + off);
-        prefetch_l2(row + bytes - 8);
+        const double *row = F + (size_t)myv * ld;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(ld * 8) : "memory");
     }
 }
 
@@ -279,15 +282,18 @@ __device__ __forceinline__ double chunk_dots(const double2 (&vec)[C2], const dou
 }
 
 // Dense line search (cold path): lane-owned components, candidates in descending order, early exit.
+// fu is re-read from F_in and the gradient from `grow` (the caller parks it in the node's F_out row,
+// which it owns and overwrites afterwards) so that no register array has its address taken.
 template <int C2, int R>
-__device__ __noinline__ int dense_linesearch(const StepArgs &a, const double2 (&fu)[C2], const double2 (&g)[C2],
-                                             const double *s_sumF, int64_t e0, int deg, int lane,
+__device__ __noinline__ int dense_linesearch(const double *__restrict__ F, const int32_t *__restrict__ colp,
+                                             int ld, int nsteps, const double *s_steps, double alpha,
+                                             double min_f, double max_f, EdgeConst ec,
+                                             const double *frow, const double *grow,
+                                             const double *s_sumF, int deg, int lane,
                                              double llh_u, double G2) {
-    const int ld = a.ld, ld2 = a.ld >> 1;
-    const double *__restrict__ F = a.F_in;
-    const EdgeConst ec = {a.x_lo, a.x_hi, a.t_lo, a.t_hi, a.w_lo, a.w_hi};
-    for (int j = 0; j < a.nsteps; ++j) {
-        const double s = a.steps[j];
+    const int ld2 = ld >> 1;
+    for (int j = 0; j < nsteps; ++j) {
+        const double s = s_steps[j];
         double2 nf[C2];
         double oa = 0.0, ob = 0.0;
 #pragma unroll
@@ -296,10 +302,12 @@ __device__ __noinline__ int dense_linesearch(const StepArgs &a, const double2 (&
             nf[c] = make_double2(0.0, 0.0);
             if (q < ld2) {
                 const double2 sf = *reinterpret_cast<const double2 *>(s_sumF + 2 * q);
-                nf[c].x = clamp_step(fu[c].x, s, g[c].x, a.min_f, a.max_f);
-                nf[c].y = clamp_step(fu[c].y, s, g[c].y, a.min_f, a.max_f);
-                oa = fma(nf[c].x, (sf.x - fu[c].x) + nf[c].x, oa);
-                oa = fma(nf[c].y, (sf.y - fu[c].y) + nf[c].y, oa);
+                const double2 fu = ldg2(frow + 2 * q);
+                const double2 g = *reinterpret_cast<const double2 *>(grow + 2 * q);
+                nf[c].x = clamp_step(fu.x, s, g.x, min_f, max_f);
+                nf[c].y = clamp_step(fu.y, s, g.y, min_f, max_f);
+                oa = fma(nf[c].x, (sf.x - fu.x) + nf[c].x, oa);
+                oa = fma(nf[c].y, (sf.y - fu.y) + nf[c].y, oa);
                 ob = fma(nf[c].x, nf[c].x, ob);
                 ob = fma(nf[c].y, nf[c].y, ob);
             }
@@ -309,14 +317,14 @@ __device__ __noinline__ int dense_linesearch(const StepArgs &a, const double2 (&
         double sumterms = 0.0;
         for (int cb = 0; cb < deg; cb += 32) {
             const int cnt = min(32, deg - cb);
-            const int myv = (lane < cnt) ? a.col[e0 + cb + lane] : 0;
+            const int myv = (lane < cnt) ? colp[cb + lane] : 0;
             const double myx = chunk_dots<C2, R>(nf, F, ld, ld2, lane, myv, cnt);
             double w;
             const double t = edge_term<false>(myx, ec, w);
             sumterms += warp_sum(lane < cnt ? t : 0.0);
         }
         const double result = (sumterms - oa) + ob;
-        const double rhs = llh_u + (a.alpha * s) * G2;
+        const double rhs = llh_u + (alpha * s) * G2;
         if (result >= rhs) return j;
     }
     return -1;
@@ -327,17 +335,18 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
     if (a.done_flag != nullptr && *a.done_flag != 0) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int ld = a.ld, ld2 = a.ld >> 1, maxm = a.maxm;
+    const int ld = a.ld, ld2 = a.ld >> 1;
+    constexpr int maxm = kMaxActiveCap;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double *s_sumF = reinterpret_cast<double *>(smem_raw);
-    double *s_steps = s_sumF + ld;
-    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_steps + kMaxSteps) + (size_t)wib * warp_smem_bytes(ld, maxm);
-    double *s_D = reinterpret_cast<double *>(wbase);
-    double2 *s_afg = reinterpret_cast<double2 *>(s_D + ld);
-    double *s_pval = reinterpret_cast<double *>(s_afg + maxm);
-    unsigned short *s_aidx = reinterpret_cast<unsigned short *>(s_pval + maxm);
-    unsigned short *s_poff = s_aidx + maxm;
-    unsigned char *s_pt = reinterpret_cast<unsigned char *>(s_poff + 34);
+    double *s_steps = reinterpret_cast<double *>(smem_raw);
+    WarpLists *wl = reinterpret_cast<WarpLists *>(smem_raw + sizeof(double) * kMaxSteps) + wib;
+    double *s_sumF = reinterpret_cast<double *>(smem_raw + sizeof(double) * kMaxSteps + kWarpsPerBlock * sizeof(WarpLists));
+    double *s_D = s_sumF + (size_t)ld * (1 + wib);
+    double2 *s_afg = wl->afg;
+    double *s_pval = wl->pval;
+    unsigned short *s_aidx = wl->aidx;
+    unsigned short *s_poff = wl->poff;
+    unsigned char *s_pt = wl->pt;
 
     for (int i = threadIdx.x; i < ld; i += kBlockThreads) s_sumF[i] = a.sumF[i];
     for (int i = threadIdx.x; i < kMaxSteps; i += kBlockThreads) s_steps[i] = a.steps[i];
@@ -493,31 +502,36 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
             if (sparse_ok && m <= maxm) {
                 // ---------------- LS, pair-list path ----------------
                 const int j16 = lane & 15, h = lane >> 4;
-                // edges per chunk such that every edge's pairs (<= m) fit the list
-                int ce_max = (m > 0) ? min(32, maxm / m) : 32;
-                if (ce_max > 1) ce_max &= ~1;
                 const int my_idx0 = (lane < m) ? (int)s_aidx[lane] : 0;
+                const int mdiv = max(m, 1);
                 for (int tg = 0; tg < nsteps && jstar < 0; tg += 16) {
                     const int j = tg + j16;
                     const bool jok = j < nsteps;
                     const double s = s_steps[jok ? j : 0];
                     double sumterms = 0.0;
-                    for (int cb = 0; cb < deg; cb += ce_max) {
-                        const int ce = min(ce_max, deg - cb);
-                        const int cv = (lane < ce) ? a.col[e0 + cb + lane] : 0;
-                        // build: for every edge keep (t, fv[idx_t]) with fv != 0
-                        int np = 0;
+                    int e_next = 0;
+                    while (e_next < deg) {
+                        // one chunk: up to 32 edges, as many as the pair list is guaranteed to hold
+                        const int cmax = min(32, deg - e_next);
+                        const int cv = (lane < cmax) ? a.col[e0 + e_next + lane] : 0;
+                        int np = 0, ce = 0;
                         if (lane == 0) s_poff[0] = 0;
-                        for (int eb = 0; eb < ce; eb += 4) {
+                        // build: for every edge keep (t, fv[idx_t]) with fv != 0
+                        while (ce < cmax) {
+                            int nb = min(4, cmax - ce);
+                            if (np + nb * m > maxm) {
+                                nb = (maxm - np) / mdiv;
+                                if (nb == 0) break;
+                            }
                             double val[4];
 #pragma unroll
-                            for (int r = 0; r < 4; ++r) {          // 4 gathers in flight
-                                const int v = __shfl_sync(0xffffffffu, cv, (eb + r) & 31);
-                                val[r] = (eb + r < ce && lane < m) ? __ldg(F + (size_t)v * ld + my_idx0) : 0.0;
+                            for (int r = 0; r < 4; ++r) {          // up to 4 gathers in flight
+                                const int v = __shfl_sync(0xffffffffu, cv, (ce + r) & 31);
+                                val[r] = (r < nb && lane < m) ? __ldg(F + (size_t)v * ld + my_idx0) : 0.0;
                             }
 #pragma unroll
                             for (int r = 0; r < 4; ++r) {
-                                if (eb + r < ce) {
+                                if (r < nb) {
                                     unsigned bal = __ballot_sync(0xffffffffu, val[r] != 0.0);
                                     if (val[r] != 0.0) {
                                         const int pp = np + __popc(bal & lt_mask);
@@ -526,8 +540,9 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
                                     }
                                     np += __popc(bal);
                                     if (m > 32) {                  // rare: more than one gather round per edge
-                                        const int v = __shfl_sync(0xffffffffu, cv, (eb + r) & 31);
+                                        const int v = __shfl_sync(0xffffffffu, cv, (ce + r) & 31);
                                         const double *fv = F + (size_t)v * ld;
+#pragma unroll 1
                                         for (int tb = 32; tb < m; tb += 32) {
                                             const int t = tb + lane;
                                             const double vv = (t < m) ? __ldg(fv + s_aidx[t]) : 0.0;
@@ -540,18 +555,21 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
                                             np += __popc(bal);
                                         }
                                     }
-                                    if (lane == 0) s_poff[eb + r + 1] = (unsigned short)np;
+                                    if (lane == 0) s_poff[ce + r + 1] = (unsigned short)np;
                                 }
                             }
+                            ce += nb;
                         }
                         __syncwarp();
-                        // consume: lane (j, h) walks the pairs of edge e = 2q + h
+                        // consume: lane (j, h) walks the pairs of edge e = e2 + h
+#pragma unroll 1
                         for (int e2 = 0; e2 < ce; e2 += 2) {
                             const int e = e2 + h;
                             const bool valid = e < ce;
                             const int i0 = valid ? (int)s_poff[e] : 0;
                             const int i1 = valid ? (int)s_poff[e + 1] : 0;
                             double D = 0.0;
+#pragma unroll 1
                             for (int i = i0; i < i1; ++i) {
                                 const double2 fg = s_afg[s_pt[i]];
                                 D = fma(clamp_step0(fg.x, s, fg.y, max_f), s_pval[i], D);
@@ -561,10 +579,12 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
                             sumterms += valid ? t : 0.0;
                         }
                         __syncwarp();
+                        e_next += ce;
                     }
                     sumterms += __shfl_xor_sync(0xffffffffu, sumterms, 16);
                     // - newfu.sfT + newfu.newfu with sfT = (sumF - fu) + newfu   (:176,:180)
                     double oa = 0.0, ob = 0.0;
+#pragma unroll 2
                     for (int t = h; t < m; t += 2) {
                         const double2 fg = s_afg[t];
                         const double nf = clamp_step0(fg.x, s, fg.y, max_f);
@@ -580,7 +600,14 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
                     if (pass) jstar = tg + __ffs(pass) - 1;   // lowest j == largest step (:182 max)
                 }
             } else {
-                jstar = dense_linesearch<C2, R>(a, fu, g, s_sumF, e0, deg, lane, llh_u, G2);
+#pragma unroll
+                for (int c = 0; c < C2; ++c) {
+                    const int q = lane + 32 * c;
+                    if (q < ld2) *reinterpret_cast<double2 *>(orow + 2 * q) = g[c];
+                }
+                __syncwarp();
+                jstar = dense_linesearch<C2, R>(F, a.col + e0, ld, nsteps, s_steps, a.alpha, a.min_f, max_f, ec,
+                                                F + (size_t)u * ld, orow, s_sumF, deg, lane, llh_u, G2);
             }
         }
 
@@ -626,12 +653,10 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
     // ---------------- block reduction of the partials, one RED per address per block ----------------
     __syncthreads();
     if (a.do_linesearch) {
-        const unsigned char *w0 = reinterpret_cast<const unsigned char *>(s_steps + kMaxSteps);
         for (int i = threadIdx.x; i < ld; i += kBlockThreads) {
             double v = 0.0;
 #pragma unroll
-            for (int w = 0; w < kWarpsPerBlock; ++w)
-                v += reinterpret_cast<const double *>(w0 + (size_t)w * warp_smem_bytes(ld, maxm))[i];
+            for (int w = 0; w < kWarpsPerBlock; ++w) v += s_sumF[(size_t)ld * (1 + w) + i];
             if (v != 0.0) atomicAdd(a.partials + i, v);
         }
     }

