@@ -17,13 +17,15 @@
 // holds node i+1's neighbour ids and own row and has issued prefetch.global.L2 for node i+1's
 // neighbour rows, so the HBM latency of the gather is off the dependent chain.
 //
-// Line search ("pair list"): a component can only matter in nf_j . fv if nf_j can be non-zero,
-// i.e. fu_i > 0 or grad_i > 0 (MIN_F_ = 0).  Those m "active" components are compacted into shared
-// memory; for every edge the warp gathers fv at the active components with one LDG per 32 of them
-// and keeps only the non-zero products' operands (t, fv_t) — typically ~3 per edge.  Lanes then
-// re-map to (trial j, edge parity) and each lane accumulates its own trial's dot over the pairs
-// and evaluates exp/log for it: every point of the 16 x deg grid is computed by exactly one lane.
-// Rows with more active components than the shared-memory lists hold, or MIN_F_ != 0, take the
+// Line search ("active space"): a component can only matter in nf_j . fv if nf_j can be non-zero,
+// i.e. fu_i > 0 or grad_i > 0 (MIN_F_ = 0).  Those m "active" components (the node's few
+// communities, m ~ 16 of K = 200) are compacted into shared memory.  Lanes then re-map to
+// (trial j, edge parity h): a table nf[t][j] = clamp(fu_t + s_j g_t) is built once per node, the
+// neighbours' values at the active components are gathered with one LDG per edge (lane = t) into a
+// tile val[e][t], and lane (j, h) accumulates its own trial's dot over t for edges e = 2q + h and
+// evaluates exp/log for it: every point of the 16 x deg grid is computed by exactly one lane, two
+// independent exp/log chains per lane are interleaved for ILP.  More than 32 active components are
+// handled in segments of 32; rows with more than kMaxActiveCap of them, or MIN_F_ != 0, take the
 // dense path (lane-owned components, one candidate at a time, early exit).
 //
 // exp/log: the clamped edge term is only evaluated for x in (x_lo, x_hi) = (-log MAX_P, -log MIN_P)
@@ -39,7 +41,8 @@ namespace bigclam {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
 constexpr int kMaxSteps = 64;       // MaxInter + 1 <= kMaxSteps
-constexpr int kMaxActiveCap = 256;  // upper bound of the active-set lists (and of pair-list t)
+constexpr int kMaxActiveCap = 128;  // capacity of the active-set lists
+constexpr int kChunkEdges = 8;      // edges per line-search tile
 
 struct NodeMeta {   // one record per visited node, in processing order
     int32_t u;
@@ -76,10 +79,9 @@ struct StepArgs {
 //   block: steps[kMaxSteps] f64 | kWarpsPerBlock x WarpLists | sumF[ld] f64 | kWarpsPerBlock x D[ld] f64
 struct __align__(16) WarpLists {
     double2 afg[kMaxActiveCap];          // (fu_t, g_t) of the active components
-    double pval[kMaxActiveCap];          // pair list: fv value
+    double tab[32 * 16];                 // nf[t][j] of the current 32-component segment
+    double val[kChunkEdges * 32];        // val[e][t]: neighbour e's value at active component t
     unsigned short aidx[kMaxActiveCap];  // component index of active t
-    unsigned short poff[40];             // pair-list offsets per edge of the chunk (33 used)
-    unsigned char pt[kMaxActiveCap];     // pair list: active index t
 };
 __host__ __device__ inline size_t block_smem_bytes(int ld, int /*maxm*/) {
     return sizeof(double) * kMaxSteps + (size_t)kWarpsPerBlock * sizeof(WarpLists) +
@@ -192,6 +194,24 @@ __device__ __forceinline__ double edge_term(double x, const EdgeConst &c, double
         }
     }
     return t + x;
+}
+
+// Two independent edge terms per lane (ILP 2): same arithmetic as edge_term<false>.
+__device__ __forceinline__ void edge_term2(double xa, double xb, const EdgeConst &c, double &ta, double &tb) {
+    const bool lowa = xa <= c.x_lo, lowb = xb <= c.x_lo;
+    const bool needa = !lowa && (xa < c.x_hi), needb = !lowb && (xb < c.x_hi);
+    ta = lowa ? c.t_lo : c.t_hi;
+    tb = lowb ? c.t_lo : c.t_hi;
+    if (__any_sync(0xffffffffu, needa || needb)) {
+        const double ompa = 1.0 - exp_neg(needa ? xa : 1.0);
+        const double ompb = 1.0 - exp_neg(needb ? xb : 1.0);
+        const double fa = log_pos(ompa);
+        const double fb = log_pos(ompb);
+        ta = needa ? fa : ta;
+        tb = needb ? fb : tb;
+    }
+    ta += xa;
+    tb += xb;
 }
 
 // step(), bigclam4-7.scala:110-113: product and sum rounded separately (the JVM never fuses).
@@ -343,10 +363,9 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
     double *s_sumF = reinterpret_cast<double *>(smem_raw + sizeof(double) * kMaxSteps + kWarpsPerBlock * sizeof(WarpLists));
     double *s_D = s_sumF + (size_t)ld * (1 + wib);
     double2 *s_afg = wl->afg;
-    double *s_pval = wl->pval;
+    double *s_tab = wl->tab;
+    double *s_val = wl->val;
     unsigned short *s_aidx = wl->aidx;
-    unsigned short *s_poff = wl->poff;
-    unsigned char *s_pt = wl->pt;
 
     for (int i = threadIdx.x; i < ld; i += kBlockThreads) s_sumF[i] = a.sumF[i];
     for (int i = threadIdx.x; i < kMaxSteps; i += kBlockThreads) s_steps[i] = a.steps[i];
@@ -500,89 +519,15 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
             }
 
             if (sparse_ok && m <= maxm) {
-                // ---------------- LS, pair-list path ----------------
+                // ---------------- LS, active-space path ----------------
                 const int j16 = lane & 15, h = lane >> 4;
-                const int my_idx0 = (lane < m) ? (int)s_aidx[lane] : 0;
-                const int mdiv = max(m, 1);
+                const int nseg = (m + 31) >> 5;
                 for (int tg = 0; tg < nsteps && jstar < 0; tg += 16) {
                     const int j = tg + j16;
                     const bool jok = j < nsteps;
                     const double s = s_steps[jok ? j : 0];
-                    double sumterms = 0.0;
-                    int e_next = 0;
-                    while (e_next < deg) {
-                        // one chunk: up to 32 edges, as many as the pair list is guaranteed to hold
-                        const int cmax = min(32, deg - e_next);
-                        const int cv = (lane < cmax) ? a.col[e0 + e_next + lane] : 0;
-                        int np = 0, ce = 0;
-                        if (lane == 0) s_poff[0] = 0;
-                        // build: for every edge keep (t, fv[idx_t]) with fv != 0
-                        while (ce < cmax) {
-                            int nb = min(4, cmax - ce);
-                            if (np + nb * m > maxm) {
-                                nb = (maxm - np) / mdiv;
-                                if (nb == 0) break;
-                            }
-                            double val[4];
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {          // up to 4 gathers in flight
-                                const int v = __shfl_sync(0xffffffffu, cv, (ce + r) & 31);
-                                val[r] = (r < nb && lane < m) ? __ldg(F + (size_t)v * ld + my_idx0) : 0.0;
-                            }
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                if (r < nb) {
-                                    unsigned bal = __ballot_sync(0xffffffffu, val[r] != 0.0);
-                                    if (val[r] != 0.0) {
-                                        const int pp = np + __popc(bal & lt_mask);
-                                        s_pval[pp] = val[r];
-                                        s_pt[pp] = (unsigned char)lane;
-                                    }
-                                    np += __popc(bal);
-                                    if (m > 32) {                  // rare: more than one gather round per edge
-                                        const int v = __shfl_sync(0xffffffffu, cv, (ce + r) & 31);
-                                        const double *fv = F + (size_t)v * ld;
-#pragma unroll 1
-                                        for (int tb = 32; tb < m; tb += 32) {
-                                            const int t = tb + lane;
-                                            const double vv = (t < m) ? __ldg(fv + s_aidx[t]) : 0.0;
-                                            bal = __ballot_sync(0xffffffffu, vv != 0.0);
-                                            if (vv != 0.0) {
-                                                const int pp = np + __popc(bal & lt_mask);
-                                                s_pval[pp] = vv;
-                                                s_pt[pp] = (unsigned char)t;
-                                            }
-                                            np += __popc(bal);
-                                        }
-                                    }
-                                    if (lane == 0) s_poff[ce + r + 1] = (unsigned short)np;
-                                }
-                            }
-                            ce += nb;
-                        }
-                        __syncwarp();
-                        // consume: lane (j, h) walks the pairs of edge e = e2 + h
-#pragma unroll 1
-                        for (int e2 = 0; e2 < ce; e2 += 2) {
-                            const int e = e2 + h;
-                            const bool valid = e < ce;
-                            const int i0 = valid ? (int)s_poff[e] : 0;
-                            const int i1 = valid ? (int)s_poff[e + 1] : 0;
-                            double D = 0.0;
-#pragma unroll 1
-                            for (int i = i0; i < i1; ++i) {
-                                const double2 fg = s_afg[s_pt[i]];
-                                D = fma(clamp_step0(fg.x, s, fg.y, max_f), s_pval[i], D);
-                            }
-                            double w;
-                            const double t = edge_term<false>(D, ec, w);
-                            sumterms += valid ? t : 0.0;
-                        }
-                        __syncwarp();
-                        e_next += ce;
-                    }
-                    sumterms += __shfl_xor_sync(0xffffffffu, sumterms, 16);
-                    // - newfu.sfT + newfu.newfu with sfT = (sumF - fu) + newfu   (:176,:180)
+                    // - newfu.sfT + newfu.newfu with sfT = (sumF - fu) + newfu   (:176,:180); when the
+                    // active set fits one segment the same pass fills the table nf[t][j]
                     double oa = 0.0, ob = 0.0;
 #pragma unroll 2
                     for (int t = h; t < m; t += 2) {
@@ -591,9 +536,76 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
                         const double sf = (s_sumF[s_aidx[t]] - fg.x) + nf;
                         oa = fma(nf, sf, oa);
                         ob = fma(nf, nf, ob);
+                        if (nseg == 1) s_tab[t * 16 + j16] = nf;
                     }
+                    if (nseg == 1 && (m & 1) && h == 1) s_tab[m * 16 + j16] = 0.0;   // pad to an even count
                     oa += __shfl_xor_sync(0xffffffffu, oa, 16);
                     ob += __shfl_xor_sync(0xffffffffu, ob, 16);
+                    __syncwarp();
+
+                    double sumterms = 0.0;
+                    for (int cb = 0; cb < deg; cb += kChunkEdges) {
+                        const int ce = min(kChunkEdges, deg - cb);
+                        const int cv = (lane < ce) ? a.col[e0 + cb + lane] : 0;
+                        double D[kChunkEdges / 2];
+#pragma unroll
+                        for (int q = 0; q < kChunkEdges / 2; ++q) D[q] = 0.0;
+                        for (int seg = 0; seg < nseg; ++seg) {
+                            const int t0 = seg << 5;
+                            const int slen = min(32, m - t0);
+                            const int slen2 = (slen + 1) & ~1;
+                            if (nseg > 1) {              // rare: rebuild the table for this segment
+                                __syncwarp();
+                                for (int t = h; t < slen2; t += 2) {
+                                    double nf = 0.0;
+                                    if (t < slen) {
+                                        const double2 fg = s_afg[t0 + t];
+                                        nf = clamp_step0(fg.x, s, fg.y, max_f);
+                                    }
+                                    s_tab[t * 16 + j16] = nf;
+                                }
+                            }
+                            // gather: val[e][t] = fv_e[idx_t], one LDG per edge (lane = t)
+                            const int my_idx = (lane < slen) ? (int)s_aidx[t0 + lane] : -1;
+                            double gv[kChunkEdges];
+#pragma unroll
+                            for (int e = 0; e < kChunkEdges; ++e) {
+                                const int v = __shfl_sync(0xffffffffu, cv, e);
+                                gv[e] = (e < ce && my_idx >= 0) ? __ldg(F + (size_t)v * ld + my_idx) : 0.0;
+                            }
+#pragma unroll
+                            for (int e = 0; e < kChunkEdges; ++e)
+                                if (e < ce + 1) s_val[e * 32 + lane] = gv[e];    // one zero row past the end for h = 1
+                            __syncwarp();
+                            // dot: lane (j, h) accumulates its trial over t for edges 2q + h
+#pragma unroll
+                            for (int q = 0; q < kChunkEdges / 2; ++q) {
+                                if (2 * q < ce) {
+                                    const double *vrow = s_val + (2 * q + h) * 32;
+                                    double acc = D[q];
+#pragma unroll 2
+                                    for (int t = 0; t < slen2; t += 2) {
+                                        const double2 vv = *reinterpret_cast<const double2 *>(vrow + t);
+                                        acc = fma(s_tab[t * 16 + j16], vv.x, acc);
+                                        acc = fma(s_tab[(t + 1) * 16 + j16], vv.y, acc);
+                                    }
+                                    D[q] = acc;
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        // exp/log: two independent chains per lane
+#pragma unroll
+                        for (int q = 0; q < kChunkEdges / 2; q += 2) {
+                            if (2 * q < ce) {
+                                double ta, tb;
+                                edge_term2(D[q], D[q + 1], ec, ta, tb);
+                                sumterms += (2 * q + h < ce) ? ta : 0.0;
+                                sumterms += (2 * q + 2 + h < ce) ? tb : 0.0;
+                            }
+                        }
+                    }
+                    sumterms += __shfl_xor_sync(0xffffffffu, sumterms, 16);
                     const double result = (sumterms - oa) + ob;
                     const double rhs = llh_u + (a.alpha * s) * G2;
                     const unsigned pass = __ballot_sync(0xffffffffu, jok && (result >= rhs)) & 0xffffu;
