@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -39,6 +40,7 @@ struct bigclam_ctx {
     uint8_t *d_mask = nullptr;
     int32_t *d_done = nullptr;
     unsigned int *d_work = nullptr;
+    long long *d_dbg = nullptr;   // BIGCLAM_DEBUG_CYCLES=1: per-node timing scratch (4 x n)
     RunState *d_state = nullptr;
     double *d_trace = nullptr;
     int64_t trace_cap = 0;
@@ -121,7 +123,7 @@ static void free_ctx(bigclam_ctx *c) {
     cudaFree(c->d_F[0]); cudaFree(c->d_F[1]);
     cudaFree(c->d_sumF[0]); cudaFree(c->d_sumF[1]);
     cudaFree(c->d_partials); cudaFree(c->d_accepted); cudaFree(c->d_mask);
-    cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_state); cudaFree(c->d_trace);
+    cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_dbg); cudaFree(c->d_state); cudaFree(c->d_trace);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -279,6 +281,10 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     CUC(cudaMalloc(&ctx->d_mask, (size_t)n));
     CUC(cudaMalloc(&ctx->d_done, sizeof(int32_t)));
     CUC(cudaMalloc(&ctx->d_work, sizeof(unsigned int)));
+    if (std::getenv("BIGCLAM_DEBUG_CYCLES") != nullptr) {
+        CUC(cudaMalloc(&ctx->d_dbg, sizeof(long long) * (4 * (size_t)n + 16)));
+        CUC(cudaMemset(ctx->d_dbg, 0, sizeof(long long) * (4 * (size_t)n + 16)));
+    }
     CUC(cudaMalloc(&ctx->d_state, sizeof(RunState)));
     CUC(cudaMallocHost(&ctx->h_pinned, sizeof(double) * (2 * (size_t)ld + 2) + sizeof(RunState) + 64));
     CUC(cudaMemcpy(ctx->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
@@ -407,6 +413,7 @@ static void fill_args(bigclam_ctx *ctx, StepArgs &a, bool linesearch, const uint
     a.w_hi = 1.0 / (1.0 - p.min_p);
     a.meta = ctx->d_meta;
     a.work_counter = ctx->d_work;
+    a.dbg = linesearch ? ctx->d_dbg : nullptr;
     a.maxm = ctx->maxm;
     a.order_n = ctx->order_n;
     a.node_mask = d_mask;
@@ -658,5 +665,24 @@ extern "C" int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev) {
 extern "C" int bigclam_rollback(bigclam_ctx *ctx) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     ctx->cur ^= 1;
+    return BIGCLAM_OK;
+}
+
+// Debug only (context created with BIGCLAM_DEBUG_CYCLES=1 in the environment and a kernel build that
+// fills StepArgs::dbg): per node [start clock, cycles, smid, m] of the most recent step kernel.
+extern "C" int bigclam_debug_cycles(bigclam_ctx *ctx, int64_t *out) {
+    if (ctx == nullptr || out == nullptr || ctx->d_dbg == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(out, ctx->d_dbg, sizeof(long long) * (4 * (size_t)ctx->n + 16), cudaMemcpyDeviceToHost));
+    CU(cudaMemset(ctx->d_dbg + 4 * (size_t)ctx->n, 0, sizeof(long long) * 16));
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_device_accepted(bigclam_ctx *ctx, void **accepted_dev) {
+    if (ctx == nullptr || accepted_dev == nullptr) return BIGCLAM_EINVAL;
+    if (!(ctx->p.flags & BIGCLAM_F_RECORD_ACCEPTED))
+        return fail(ctx, BIGCLAM_EINVAL, "bigclam_device_accepted: context created without BIGCLAM_F_RECORD_ACCEPTED");
+    *accepted_dev = ctx->d_accepted;
     return BIGCLAM_OK;
 }

@@ -17,15 +17,13 @@
 // holds node i+1's neighbour ids and own row and has issued prefetch.global.L2 for node i+1's
 // neighbour rows, so the HBM latency of the gather is off the dependent chain.
 //
-// Line search ("active space"): a component can only matter in nf_j . fv if nf_j can be non-zero,
-// i.e. fu_i > 0 or grad_i > 0 (MIN_F_ = 0).  Those m "active" components (the node's few
-// communities, m ~ 16 of K = 200) are compacted into shared memory.  Lanes then re-map to
-// (trial j, edge parity h): a table nf[t][j] = clamp(fu_t + s_j g_t) is built once per node, the
-// neighbours' values at the active components are gathered with one LDG per edge (lane = t) into a
-// tile val[e][t], and lane (j, h) accumulates its own trial's dot over t for edges e = 2q + h and
-// evaluates exp/log for it: every point of the 16 x deg grid is computed by exactly one lane, two
-// independent exp/log chains per lane are interleaved for ILP.  More than 32 active components are
-// handled in segments of 32; rows with more than kMaxActiveCap of them, or MIN_F_ != 0, take the
+// Line search ("pair list"): a component can only matter in nf_j . fv if nf_j can be non-zero,
+// i.e. fu_i > 0 or grad_i > 0 (MIN_F_ = 0).  Those m "active" components are compacted into shared
+// memory; for every edge the warp gathers fv at the active components with one LDG per 32 of them
+// and keeps only the non-zero products' operands (t, fv_t) — typically ~3 per edge.  Lanes then
+// re-map to (trial j, edge parity) and each lane accumulates its own trial's dot over the pairs
+// and evaluates exp/log for it: every point of the 16 x deg grid is computed by exactly one lane.
+// Rows with more active components than the shared-memory lists hold, or MIN_F_ != 0, take the
 // dense path (lane-owned components, one candidate at a time, early exit).
 //
 // exp/log: the clamped edge term is only evaluated for x in (x_lo, x_hi) = (-log MAX_P, -log MIN_P)
@@ -38,11 +36,11 @@
 
 namespace bigclam {
 
-constexpr int kWarpsPerBlock = 8;
+constexpr int kWarpsPerBlock = 6;      // 12 warps/SM at ~168 registers: the point where ptxas stops spilling
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
 constexpr int kMaxSteps = 64;       // MaxInter + 1 <= kMaxSteps
-constexpr int kMaxActiveCap = 128;  // capacity of the active-set lists
-constexpr int kChunkEdges = 8;      // edges per line-search tile
+constexpr int kMaxActiveCap = 256;  // upper bound of the active-set lists (and of pair-list t)
+constexpr int kMaxPairs = 512;      // capacity of the pair list of one line-search chunk (<= 32 edges)
 
 struct NodeMeta {   // one record per visited node, in processing order
     int32_t u;
@@ -66,12 +64,13 @@ struct StepArgs {
     double x_lo, x_hi, t_lo, t_hi, w_lo, w_hi;
     const NodeMeta *meta;     // processing order (degree descending) over the owned nodes
     int64_t order_n;
-    unsigned int *work_counter;   // next position to hand out (host sets it to 3 * #warps)
+    unsigned int *work_counter;   // next position to hand out (host sets it to 4 * #warps)
     const uint8_t *node_mask; // optional uset
     double *partials;         // [D(ld) = sum(old - new) | unused(ld) | llh | n_updated]
     int8_t *accepted;         // optional, n
     const int32_t *done_flag; // optional: non-zero -> the launch is a no-op
     int32_t do_linesearch;    // 0: PRE/LLH only (loglikelihood())
+    long long *dbg;           // optional debug scratch (unused in this build)
 };
 
 // Shared-memory carve-up.  Everything whose size does not depend on K sits at compile-time offsets
@@ -79,13 +78,16 @@ struct StepArgs {
 //   block: steps[kMaxSteps] f64 | kWarpsPerBlock x WarpLists | sumF[ld] f64 | kWarpsPerBlock x D[ld] f64
 struct __align__(16) WarpLists {
     double2 afg[kMaxActiveCap];          // (fu_t, g_t) of the active components
-    double tab[32 * 16];                 // nf[t][j] of the current 32-component segment
-    double val[kChunkEdges * 32];        // val[e][t]: neighbour e's value at active component t
+    double pval[kMaxPairs];              // pair list: fv value
     unsigned short aidx[kMaxActiveCap];  // component index of active t
+    unsigned short poff[40];             // pair-list offsets per edge of the chunk (33 used)
+    unsigned char pt[kMaxPairs];         // pair list: active index t
 };
 __host__ __device__ inline size_t block_smem_bytes(int ld, int /*maxm*/) {
+    const int stage = (ld <= 256) ? 4 : 0;      // the cp.async row staging exists only in the C2 <= 4 kernels
+    // ... | sumF[ld] | W x D[ld] | W x rows[4][ld] (cp.async staging of one batch of neighbour rows)
     return sizeof(double) * kMaxSteps + (size_t)kWarpsPerBlock * sizeof(WarpLists) +
-           sizeof(double) * (size_t)ld * (1 + kWarpsPerBlock);
+           sizeof(double) * (size_t)ld * (1 + kWarpsPerBlock + stage * kWarpsPerBlock);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -112,20 +114,18 @@ __device__ __forceinline__ double exp_neg(double x) {
     const double nf = t - kMagic;
     double r = fma(nf, -0.6931471805599453094, -x);
     r = fma(nf, -2.3190468138462996e-17, r);
-    double p = 1.6059043836821613e-10;                               // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);                             // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);                            // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);                            // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);                           // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);                             // 1/8!
-    p = fma(p, r, 0.0001984126984126984);                            // 1/7!
-    p = fma(p, r, 0.001388888888888889);                             // 1/6!
-    p = fma(p, r, 0.008333333333333333);                             // 1/5!
-    p = fma(p, r, 0.041666666666666664);                             // 1/4!
-    p = fma(p, r, 0.16666666666666666);                              // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    // Estrin evaluation (depth 4 instead of 13 dependent FMAs)
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = r + 1.0;
+    const double a1 = fma(0.16666666666666666, r, 0.5);
+    const double a2 = fma(0.008333333333333333, r, 0.041666666666666664);
+    const double a3 = fma(0.0001984126984126984, r, 0.001388888888888889);
+    const double a4 = fma(2.7557319223985893e-06, r, 2.48015873015873e-05);
+    const double a5 = fma(2.505210838544172e-08, r, 2.755731922398589e-07);
+    const double a6 = fma(1.6059043836821613e-10, r, 2.08767569878681e-09);
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+    const double d0 = fma(b1, r4, b0), d1 = fma(a6, r4, b2);
+    const double p = fma(d1, r8, d0);
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
@@ -152,17 +152,14 @@ __device__ __forceinline__ double log_pos(double y) {
     double s = f * rd;
     s = fma(fma(-d, s, f), rd, s);
     const double z = s * s;
-    double q = 0.08695652173913043;          // 2/23
-    q = fma(q, z, 0.09523809523809523);      // 2/21
-    q = fma(q, z, 0.10526315789473684);      // 2/19
-    q = fma(q, z, 0.11764705882352941);      // 2/17
-    q = fma(q, z, 0.13333333333333333);      // 2/15
-    q = fma(q, z, 0.15384615384615385);      // 2/13
-    q = fma(q, z, 0.18181818181818182);      // 2/11
-    q = fma(q, z, 0.2222222222222222);       // 2/9
-    q = fma(q, z, 0.2857142857142857);       // 2/7
-    q = fma(q, z, 0.4);                      // 2/5
-    q = fma(q, z, 0.6666666666666666);       // 2/3
+    const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+    const double a0 = fma(0.4, z, 0.6666666666666666);                     // 2/5, 2/3
+    const double a1 = fma(0.2222222222222222, z, 0.2857142857142857);      // 2/9, 2/7
+    const double a2 = fma(0.15384615384615385, z, 0.18181818181818182);    // 2/13, 2/11
+    const double a3 = fma(0.11764705882352941, z, 0.13333333333333333);    // 2/17, 2/15
+    const double a4 = fma(0.09523809523809523, z, 0.10526315789473684);    // 2/21, 2/19
+    const double b0 = fma(a1, z2, a0), b1 = fma(a3, z2, a2), b2 = fma(0.08695652173913043, z2, a4);   // 2/23
+    const double q = fma(b2, z8, fma(b1, z4, b0));
     const double ed = (double)e;
     const double inner = fma(ed, 2.3190468138462996e-17, (s * z) * q);
     return fma(ed, 0.6931471805599453094, fma(2.0, s, inner));
@@ -227,13 +224,46 @@ __device__ __forceinline__ double clamp_step0(double f, double s, double g, doub
     return (x > hi) ? hi : x;
 }
 
+// Lower clamp only (used when no active component of the node can reach MAX_F_ at step 1).
+__device__ __forceinline__ double clamp_step0_lo(double f, double s, double g) {
+    const double x = __dadd_rn(f, __dmul_rn(s, g));
+    return (__double2hiint(x) < 0) ? 0.0 : x;
+}
+
 // L2 prefetch of the rows of up to 32 neighbours (lane l < cnt owns row myv): one bulk prefetch
 // (cp.async.bulk.prefetch.L2, the TMA path) per row instead of one prefetch per 128-byte line.
 __device__ __forceinline__ void prefetch_rows(const double *F, int ld, int lane, int myv, int cnt) {
     if (lane < cnt) {
         const double *row = F + (size_t)myv * ld;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(ld * 8) : "memory");
+        const char *rp = reinterpret_cast<const char *>(row);
+        const int bytes = ld * 8;
+        (void)rp; (void)bytes;
     }
+}
+
+// cp.async staging of up to 4 neighbour rows (edges first .. first+3 of the id register `ids`) into the
+// warp's shared-memory row buffer; lane l copies the same 16-byte chunks it later reads back.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int C2>
+__device__ __forceinline__ void stage_rows(double *buf, const double *__restrict__ F, int ld, int ld2, int lane,
+                                           int ids, int first, int cnt) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int e = first + r;
+        const int v = __shfl_sync(0xffffffffu, ids, e & 31);
+        if (e < cnt) {
+            const double *fv = F + (size_t)v * ld;
+#pragma unroll
+            for (int c = 0; c < C2; ++c) {
+                const int q = lane + 32 * c;
+                if (q < ld2) cp_async16(buf + r * ld + 2 * q, fv + 2 * q);
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // Sum R per-lane partials across the warp; the total of partial r is returned to lane (eb + r).
@@ -362,10 +392,12 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
     WarpLists *wl = reinterpret_cast<WarpLists *>(smem_raw + sizeof(double) * kMaxSteps) + wib;
     double *s_sumF = reinterpret_cast<double *>(smem_raw + sizeof(double) * kMaxSteps + kWarpsPerBlock * sizeof(WarpLists));
     double *s_D = s_sumF + (size_t)ld * (1 + wib);
+    double *s_rows = s_sumF + (size_t)ld * (1 + kWarpsPerBlock) + (size_t)wib * 4 * ld;
     double2 *s_afg = wl->afg;
-    double *s_tab = wl->tab;
-    double *s_val = wl->val;
+    double *s_pval = wl->pval;
     unsigned short *s_aidx = wl->aidx;
+    unsigned short *s_poff = wl->poff;
+    unsigned char *s_pt = wl->pt;
 
     for (int i = threadIdx.x; i < ld; i += kBlockThreads) s_sumF[i] = a.sumF[i];
     for (int i = threadIdx.x; i < kMaxSteps; i += kBlockThreads) s_steps[i] = a.steps[i];
@@ -396,7 +428,7 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
         const int q = lane + 32 * c;
         fu[c] = (pos < order_n && q < ld2) ? ldg2(F + (size_t)cur.u * ld + 2 * q) : make_double2(0.0, 0.0);
     }
-    prefetch_rows(F, ld, lane, myv, min(32, cur.deg));
+    if constexpr (R == 4) stage_rows<C2>(s_rows, F, ld, ld2, lane, myv, 0, min(32, cur.deg));
 
     while (pos < order_n) {
         const int64_t u = cur.u;
@@ -412,13 +444,6 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
         if (lane == 0) fetched = atomicAdd(a.work_counter, 1u);
         const int ncnt = has_next ? min(32, nxt.deg) : 0;
         const int nmyv = (lane < ncnt) ? a.col[nxt.e0 + lane] : 0;
-        double2 nfu[C2];
-#pragma unroll
-        for (int c = 0; c < C2; ++c) {
-            const int q = lane + 32 * c;
-            nfu[c] = (has_next && q < ld2) ? ldg2(F + (size_t)nxt.u * ld + 2 * q) : make_double2(0.0, 0.0);
-        }
-
         double fusf = 0.0, fufu = 0.0;
 #pragma unroll
         for (int c = 0; c < C2; ++c) {
@@ -439,37 +464,108 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
         double S1 = 0.0;
         for (int cb = 0; cb < deg; cb += 32) {
             const int cnt = min(32, deg - cb);
-            // neighbour ids of the chunk after this one (hubs): loaded now, prefetched after the dots
+            // neighbour ids of the chunk after this one (hubs): loaded now, prefetched after the first batch
             const int cnt2 = min(32, max(0, deg - cb - 32));
             const int myv2 = (lane < cnt2) ? a.col[e0 + cb + 32 + lane] : 0;
-            const double myx = chunk_dots<C2, R>(fu, F, ld, ld2, lane, myv, cnt);
-            if (cb == 0) prefetch_rows(F, ld, lane, nmyv, ncnt);
-            if (cnt2 > 0) prefetch_rows(F, ld, lane, myv2, cnt2);
-            double w;
-            const double t = edge_term<true>(myx, ec, w);
-            S1 += warp_sum(lane < cnt ? t : 0.0);
-            if (a.do_linesearch) {
-#pragma unroll 2
-                for (int e = 0; e < cnt; ++e) {
-                    const int v = __shfl_sync(0xffffffffu, myv, e);
-                    const double we = __shfl_sync(0xffffffffu, w, e);
-                    const double *fv = F + (size_t)v * ld;
+            if constexpr (R == 4) {
+                // batches of 4 rows kept in registers: dots -> exp/log (each group of 8 lanes evaluates one
+                // of the 4 edges) -> axpy from the same registers: every neighbour row is loaded once here
+                const int rsel = (lane >> 3) & 3;
+                for (int eb = 0; eb < cnt; eb += 4) {
+                    // this batch was staged in shared memory one batch (or one node) ago
+                    cp_async_wait_all();
+                    __syncwarp();
+                    double2 x[4][C2];
+                    double part[4];
 #pragma unroll
-                    for (int c = 0; c < C2; ++c) {
-                        const int q = lane + 32 * c;
-                        if (q < ld2) {
-                            const double2 x = ldg2(fv + 2 * q);
-                            g[c].x = fma(we, x.x, g[c].x);
-                            g[c].y = fma(we, x.y, g[c].y);
+                    for (int r = 0; r < 4; ++r) {
+                        const bool ok = eb + r < cnt;
+                        double p = 0.0;
+#pragma unroll
+                        for (int c = 0; c < C2; ++c) {
+                            const int q = lane + 32 * c;
+                            x[r][c] = (ok && q < ld2) ? *reinterpret_cast<const double2 *>(s_rows + r * ld + 2 * q)
+                                                      : make_double2(0.0, 0.0);
+                            p = fma(fu[c].x, x[r][c].x, p);
+                            p = fma(fu[c].y, x[r][c].y, p);
+                        }
+                        part[r] = p;
+                    }
+                    __syncwarp();
+                    // stage the following batch while this one is processed: same 32-group, next group of
+                    // this node, or the first batch of the next node
+                    if (eb + 4 < cnt) stage_rows<C2>(s_rows, F, ld, ld2, lane, myv, eb + 4, cnt);
+                    else if (cnt2 > 0) stage_rows<C2>(s_rows, F, ld, ld2, lane, myv2, 0, cnt2);
+                    else stage_rows<C2>(s_rows, F, ld, ld2, lane, nmyv, 0, ncnt);
+                    // transposed butterfly: afterwards the lanes with ((lane >> 3) & 3) == r hold the dot of edge r
+                    const bool b4 = lane & 16, b3 = lane & 8;
+                    double k0 = b4 ? part[2] : part[0], k1 = b4 ? part[3] : part[1];
+                    const double s0 = b4 ? part[0] : part[2], s1 = b4 ? part[1] : part[3];
+                    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+                    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                    double kx = b3 ? k1 : k0;
+                    const double sd = b3 ? k0 : k1;
+                    kx += __shfl_xor_sync(0xffffffffu, sd, 8);
+                    kx += __shfl_xor_sync(0xffffffffu, kx, 4);
+                    kx += __shfl_xor_sync(0xffffffffu, kx, 2);
+                    kx += __shfl_xor_sync(0xffffffffu, kx, 1);
+                    double w;
+                    double t = edge_term<true>(kx, ec, w);
+                    t = (eb + rsel < cnt) ? t : 0.0;
+                    t += __shfl_xor_sync(0xffffffffu, t, 8);
+                    t += __shfl_xor_sync(0xffffffffu, t, 16);
+                    S1 += t;
+                    if (a.do_linesearch) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const double we = __shfl_sync(0xffffffffu, w, 8 * r);
+#pragma unroll
+                            for (int c = 0; c < C2; ++c) {
+                                g[c].x = fma(we, x[r][c].x, g[c].x);
+                                g[c].y = fma(we, x[r][c].y, g[c].y);
+                            }
+                        }
+                    }
+                }
+            } else {
+                const double myx = chunk_dots<C2, R>(fu, F, ld, ld2, lane, myv, cnt);
+                if (cb == 0) prefetch_rows(F, ld, lane, nmyv, ncnt);
+                if (cnt2 > 0) prefetch_rows(F, ld, lane, myv2, cnt2);
+                double w;
+                const double t = edge_term<true>(myx, ec, w);
+                S1 += warp_sum(lane < cnt ? t : 0.0);
+                if (a.do_linesearch) {
+#pragma unroll 2
+                    for (int e = 0; e < cnt; ++e) {
+                        const int v = __shfl_sync(0xffffffffu, myv, e);
+                        const double we = __shfl_sync(0xffffffffu, w, e);
+                        const double *fv = F + (size_t)v * ld;
+#pragma unroll
+                        for (int c = 0; c < C2; ++c) {
+                            const int q = lane + 32 * c;
+                            if (q < ld2) {
+                                const double2 xx = ldg2(fv + 2 * q);
+                                g[c].x = fma(we, xx.x, g[c].x);
+                                g[c].y = fma(we, xx.y, g[c].y);
+                            }
                         }
                     }
                 }
             }
             myv = myv2;
         }
-        if (deg == 0) prefetch_rows(F, ld, lane, nmyv, ncnt);
+        if constexpr (R == 4) { if (deg == 0) stage_rows<C2>(s_rows, F, ld, ld2, lane, nmyv, 0, ncnt); }
         const double llh_u = (S1 - fusf) + fufu;
         llh_acc += llh_u;
+
+        // own row of the next node: loaded here, after the row registers of PRE are dead, and
+        // consumed when the pipeline rotates (the whole line search hides the latency)
+        double2 nfu[C2];
+#pragma unroll
+        for (int c = 0; c < C2; ++c) {
+            const int q = lane + 32 * c;
+            nfu[c] = (has_next && q < ld2) ? ldg2(F + (size_t)nxt.u * ld + 2 * q) : make_double2(0.0, 0.0);
+        }
 
         const bool in_uset = (a.node_mask == nullptr) || (a.node_mask[u] != 0);
         int jstar = -1;
@@ -519,93 +615,140 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
             }
 
             if (sparse_ok && m <= maxm) {
-                // ---------------- LS, active-space path ----------------
+                // ---------------- LS, pair-list path ----------------
                 const int j16 = lane & 15, h = lane >> 4;
-                const int nseg = (m + 31) >> 5;
+                const int my_idx0 = (lane < m) ? (int)s_aidx[lane] : 0;
+                const int mdiv = max(m, 1);
+                bool hi_lane = false;
+                for (int t = lane; t < m; t += 32) {
+                    const double2 fg = s_afg[t];
+                    hi_lane |= (fg.x + fg.y > max_f);      // step sizes are <= 1 and fu <= MAX_F_
+                }
+                const bool need_hi = __any_sync(0xffffffffu, hi_lane);
                 for (int tg = 0; tg < nsteps && jstar < 0; tg += 16) {
                     const int j = tg + j16;
                     const bool jok = j < nsteps;
                     const double s = s_steps[jok ? j : 0];
-                    // - newfu.sfT + newfu.newfu with sfT = (sumF - fu) + newfu   (:176,:180); when the
-                    // active set fits one segment the same pass fills the table nf[t][j]
+                    double sumterms = 0.0;
+                    // groups of 32 edges (one coalesced load of neighbour ids), split into chunks whose
+                    // pairs fit the list
+                    for (int gb = 0; gb < deg; gb += 32) {
+                      const int gcnt = min(32, deg - gb);
+                      const int cv = (lane < gcnt) ? a.col[e0 + gb + lane] : 0;
+                      int ge = 0;
+                      while (ge < gcnt) {
+                        int np = 0, ce = 0;
+                        if (lane == 0) s_poff[0] = 0;
+                        // build: for every edge keep (t, fv[idx_t]) with fv != 0
+                        if (m <= 32) {
+                            while (ge + ce < gcnt) {
+                                int nb = min(4, gcnt - ge - ce);
+                                if (np + nb * m > kMaxPairs) {
+                                    nb = (kMaxPairs - np) / mdiv;
+                                    if (nb == 0) break;
+                                }
+                                double val[4];
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) {          // up to 4 gathers in flight
+                                    const int v = __shfl_sync(0xffffffffu, cv, (ge + ce + r) & 31);
+                                    val[r] = (r < nb && lane < m) ? __ldg(F + (size_t)v * ld + my_idx0) : 0.0;
+                                }
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) {
+                                    if (r < nb) {
+                                        const unsigned bal = __ballot_sync(0xffffffffu, val[r] != 0.0);
+                                        if (val[r] != 0.0) {
+                                            const int pp = np + __popc(bal & lt_mask);
+                                            s_pval[pp] = val[r];
+                                            s_pt[pp] = (unsigned char)lane;
+                                        }
+                                        np += __popc(bal);
+                                        if (lane == 0) s_poff[ce + r + 1] = (unsigned short)np;
+                                    }
+                                }
+                                ce += nb;
+                            }
+                        } else {
+                            // hubs / dense rows: up to 8 gather rounds per edge, all issued before the ballots;
+                            // the list is filled optimistically and the last edge rolled back if it overflows
+                            while (ge + ce < gcnt) {
+                                const int v = __shfl_sync(0xffffffffu, cv, (ge + ce) & 31);
+                                const double *fv = F + (size_t)v * ld;
+                                double vv[kMaxActiveCap / 32];
+#pragma unroll
+                                for (int r = 0; r < kMaxActiveCap / 32; ++r) {
+                                    const int t = 32 * r + lane;
+                                    vv[r] = (t < m) ? __ldg(fv + s_aidx[t]) : 0.0;
+                                }
+                                const int np0 = np;
+#pragma unroll
+                                for (int r = 0; r < kMaxActiveCap / 32; ++r) {
+                                    if (32 * r < m) {
+                                        const unsigned bal = __ballot_sync(0xffffffffu, vv[r] != 0.0);
+                                        if (vv[r] != 0.0) {
+                                            const int pp = np + __popc(bal & lt_mask);
+                                            if (pp < kMaxPairs) {
+                                                s_pval[pp] = vv[r];
+                                                s_pt[pp] = (unsigned char)(32 * r + lane);
+                                            }
+                                        }
+                                        np += __popc(bal);
+                                    }
+                                }
+                                if (np > kMaxPairs) { np = np0; break; }      // does not fit: flush first
+                                if (lane == 0) s_poff[ce + 1] = (unsigned short)np;
+                                ++ce;
+                            }
+                        }
+                        __syncwarp();
+                        // consume: lane (j, h) walks the pairs of edges e2 + h and e2 + 2 + h (two exp/log chains)
+                        auto pairdot = [&](int e, bool valid) -> double {
+                            const int i0 = valid ? (int)s_poff[e] : 0;
+                            const int i1 = valid ? (int)s_poff[e + 1] : 0;
+                            double D = 0.0;
+                            if (need_hi) {
+#pragma unroll 1
+                                for (int i = i0; i < i1; ++i) {
+                                    const double2 fg = s_afg[s_pt[i]];
+                                    D = fma(clamp_step0(fg.x, s, fg.y, max_f), s_pval[i], D);
+                                }
+                            } else {
+#pragma unroll 1
+                                for (int i = i0; i < i1; ++i) {
+                                    const double2 fg = s_afg[s_pt[i]];
+                                    D = fma(clamp_step0_lo(fg.x, s, fg.y), s_pval[i], D);
+                                }
+                            }
+                            return D;
+                        };
+#pragma unroll 1
+                        for (int e2 = 0; e2 < ce; e2 += 4) {
+                            const int eA = e2 + h, eB = e2 + 2 + h;
+                            const bool vA = eA < ce, vB = eB < ce;
+                            const double DA = pairdot(eA, vA);
+                            const double DB = pairdot(eB, vB);
+                            double tA, tB;
+                            edge_term2(DA, DB, ec, tA, tB);
+                            sumterms += vA ? tA : 0.0;
+                            sumterms += vB ? tB : 0.0;
+                        }
+                        __syncwarp();
+                        ge += ce;
+                      }
+                    }
+                    sumterms += __shfl_xor_sync(0xffffffffu, sumterms, 16);
+                    // - newfu.sfT + newfu.newfu with sfT = (sumF - fu) + newfu   (:176,:180)
                     double oa = 0.0, ob = 0.0;
 #pragma unroll 2
                     for (int t = h; t < m; t += 2) {
                         const double2 fg = s_afg[t];
-                        const double nf = clamp_step0(fg.x, s, fg.y, max_f);
+                        const double nf = need_hi ? clamp_step0(fg.x, s, fg.y, max_f) : clamp_step0_lo(fg.x, s, fg.y);
                         const double sf = (s_sumF[s_aidx[t]] - fg.x) + nf;
                         oa = fma(nf, sf, oa);
                         ob = fma(nf, nf, ob);
-                        if (nseg == 1) s_tab[t * 16 + j16] = nf;
                     }
-                    if (nseg == 1 && (m & 1) && h == 1) s_tab[m * 16 + j16] = 0.0;   // pad to an even count
                     oa += __shfl_xor_sync(0xffffffffu, oa, 16);
                     ob += __shfl_xor_sync(0xffffffffu, ob, 16);
-                    __syncwarp();
-
-                    double sumterms = 0.0;
-                    for (int cb = 0; cb < deg; cb += kChunkEdges) {
-                        const int ce = min(kChunkEdges, deg - cb);
-                        const int cv = (lane < ce) ? a.col[e0 + cb + lane] : 0;
-                        double D[kChunkEdges / 2];
-#pragma unroll
-                        for (int q = 0; q < kChunkEdges / 2; ++q) D[q] = 0.0;
-                        for (int seg = 0; seg < nseg; ++seg) {
-                            const int t0 = seg << 5;
-                            const int slen = min(32, m - t0);
-                            const int slen2 = (slen + 1) & ~1;
-                            if (nseg > 1) {              // rare: rebuild the table for this segment
-                                __syncwarp();
-                                for (int t = h; t < slen2; t += 2) {
-                                    double nf = 0.0;
-                                    if (t < slen) {
-                                        const double2 fg = s_afg[t0 + t];
-                                        nf = clamp_step0(fg.x, s, fg.y, max_f);
-                                    }
-                                    s_tab[t * 16 + j16] = nf;
-                                }
-                            }
-                            // gather: val[e][t] = fv_e[idx_t], one LDG per edge (lane = t)
-                            const int my_idx = (lane < slen) ? (int)s_aidx[t0 + lane] : -1;
-                            double gv[kChunkEdges];
-#pragma unroll
-                            for (int e = 0; e < kChunkEdges; ++e) {
-                                const int v = __shfl_sync(0xffffffffu, cv, e);
-                                gv[e] = (e < ce && my_idx >= 0) ? __ldg(F + (size_t)v * ld + my_idx) : 0.0;
-                            }
-#pragma unroll
-                            for (int e = 0; e < kChunkEdges; ++e)
-                                if (e < ce + 1) s_val[e * 32 + lane] = gv[e];    // one zero row past the end for h = 1
-                            __syncwarp();
-                            // dot: lane (j, h) accumulates its trial over t for edges 2q + h
-#pragma unroll
-                            for (int q = 0; q < kChunkEdges / 2; ++q) {
-                                if (2 * q < ce) {
-                                    const double *vrow = s_val + (2 * q + h) * 32;
-                                    double acc = D[q];
-#pragma unroll 2
-                                    for (int t = 0; t < slen2; t += 2) {
-                                        const double2 vv = *reinterpret_cast<const double2 *>(vrow + t);
-                                        acc = fma(s_tab[t * 16 + j16], vv.x, acc);
-                                        acc = fma(s_tab[(t + 1) * 16 + j16], vv.y, acc);
-                                    }
-                                    D[q] = acc;
-                                }
-                            }
-                            __syncwarp();
-                        }
-                        // exp/log: two independent chains per lane
-#pragma unroll
-                        for (int q = 0; q < kChunkEdges / 2; q += 2) {
-                            if (2 * q < ce) {
-                                double ta, tb;
-                                edge_term2(D[q], D[q + 1], ec, ta, tb);
-                                sumterms += (2 * q + h < ce) ? ta : 0.0;
-                                sumterms += (2 * q + 2 + h < ce) ? tb : 0.0;
-                            }
-                        }
-                    }
-                    sumterms += __shfl_xor_sync(0xffffffffu, sumterms, 16);
                     const double result = (sumterms - oa) + ob;
                     const double rhs = llh_u + (a.alpha * s) * G2;
                     const unsigned pass = __ballot_sync(0xffffffffu, jok && (result >= rhs)) & 0xffffu;

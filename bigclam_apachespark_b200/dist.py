@@ -45,6 +45,11 @@ class _DevMem:
                                          "data": (int(ptr), False), "version": 3}
 
 
+class _DevMemI8:
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "|i1", "data": (int(ptr), False), "version": 3}
+
+
 class CudaEngine:
     """The C-ABI context of one rank (libbigclam_b200.so) behind the engine interface."""
 
@@ -57,6 +62,7 @@ class CudaEngine:
         self.s = solver
         self.ctx = solver._need()
         self.check(self.lib.bigclam_set_owned_range(self.ctx, lo, hi), self.ctx)
+        self.lo, self.hi = int(lo), int(hi)
         self.n, self.k = solver.n, solver.K
         _, _, _, ld = solver.device_state()
         self.ld = ld
@@ -88,6 +94,14 @@ class CudaEngine:
     def rollback(self):
         self.check(self.lib.bigclam_rollback(self.ctx), self.ctx)
 
+    def changed_owned(self):
+        """Global ids (int64, device) of the owned rows whose step was accepted by the last step_local
+        (context created with record_accepted=True)."""
+        p = C.c_void_p()
+        self.check(self.lib.bigclam_device_accepted(self.ctx, C.byref(p)), self.ctx)
+        acc = self.torch.as_tensor(_DevMemI8(p.value, self.n), device="cuda")
+        return self.torch.nonzero(acc[self.lo:self.hi] >= 0).flatten() + self.lo
+
 
 class DistBigClam:
     """backtrackingLineSearchs over node partitions; every rank calls every method collectively."""
@@ -100,25 +114,71 @@ class DistBigClam:
         self.bounds = partition_by_nnz(rowptr, world) if bounds is None else np.asarray(bounds)
         self.exchange = exchange
         self.last_n_updated = 0
+        self.last_delta_rows = 0
+        self._prev_changed = None
+        self._need_sync = True          # first delta step: bring the non-owned rows of F_next up to date
+        if exchange == "delta":
+            import torch
+            self.torch = torch
 
     @property
     def owned(self):
         return int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
 
-    def _exchange_rows(self, F_next):
-        # owners publish their new rows; afterwards every replica of F_next is complete
-        for r in range(self.world):
-            lo, hi = int(self.bounds[r]), int(self.bounds[r + 1])
-            if hi > lo:
-                self.dist.broadcast(F_next[lo:hi], src=r)
+    def _exchange_rows(self, F_cur, F_next):
+        """Afterwards every replica of F_next holds the new F."""
+        if self.exchange == "full":
+            # owners publish their whole row range
+            for r in range(self.world):
+                lo, hi = int(self.bounds[r]), int(self.bounds[r + 1])
+                if hi > lo:
+                    self.dist.broadcast(F_next[lo:hi], src=r)
+            return
+        # delta: only rows whose step was accepted travel.  F_next is the buffer that held the state
+        # before the previous step, so the rows the PREVIOUS step changed are stale in it: refresh the
+        # non-owned ones from the current state, then apply this step's accepted rows.
+        torch = self.torch
+        lo, hi = self.owned
+        if self._need_sync:
+            mask = torch.ones(F_next.shape[0], dtype=torch.bool, device=F_next.device)
+            mask[lo:hi] = False
+            F_next[mask] = F_cur[mask]
+            self._need_sync = False
+        elif self._prev_changed is not None and self._prev_changed.numel():
+            pc = self._prev_changed
+            stale = pc[(pc < lo) | (pc >= hi)]
+            if stale.numel():
+                F_next[stale] = F_cur[stale]
+        idx = self.e.changed_owned()                                   # global ids, int64, on the device
+        cnt = torch.tensor([idx.numel()], dtype=torch.int64, device=F_next.device)
+        counts = torch.empty(self.world, dtype=torch.int64, device=F_next.device)
+        self.dist.all_gather_into_tensor(counts, cnt)
+        maxc = int(counts.max().item())
+        self.last_delta_rows = int(counts.sum().item())
+        if maxc == 0:
+            self._prev_changed = idx
+            return
+        ld = F_next.shape[1]
+        send_idx = torch.full((maxc,), -1, dtype=torch.int64, device=F_next.device)
+        send_rows = torch.zeros((maxc, ld), dtype=F_next.dtype, device=F_next.device)
+        send_idx[: idx.numel()] = idx
+        send_rows[: idx.numel()] = F_next[idx]
+        all_idx = torch.empty(self.world * maxc, dtype=torch.int64, device=F_next.device)
+        all_rows = torch.empty((self.world * maxc, ld), dtype=F_next.dtype, device=F_next.device)
+        self.dist.all_gather_into_tensor(all_idx, send_idx)
+        self.dist.all_gather_into_tensor(all_rows, send_rows)
+        valid = all_idx >= 0
+        gidx = all_idx[valid]
+        F_next[gidx] = all_rows[valid]
+        self._prev_changed = gidx
 
     def step_nollh(self):
         """PRE + line search + row swap + sumF update.  Returns the LLH of the state BEFORE this
         call (== the LLH the previous call returns, the fused identity) and n_updated."""
-        _, F_next, _ = self.e.state()
+        F_cur, F_next, _ = self.e.state()
         part = self.e.step_local()
         self.dist.all_reduce(part)                      # sum over ranks (:191-192, :219)
-        self._exchange_rows(F_next)
+        self._exchange_rows(F_cur, F_next)
         llh_pre, nupd = self.e.finish_local()           # sumF -= sum(old - new) on every rank
         self.last_n_updated = nupd
         return llh_pre, nupd

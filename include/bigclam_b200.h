@@ -117,6 +117,9 @@ int bigclam_get_kernel_time(bigclam_ctx *ctx, double *step_kernel_ms_sum, int64_
  * cudaStream_t, and expose device pointers of the current F (n x ld doubles, ld = row pitch) and sumF. */
 int bigclam_set_stream(bigclam_ctx *ctx, void *cuda_stream);
 int bigclam_device_state(bigclam_ctx *ctx, void **F_dev, void **F_next_dev, void **sumF_dev, int64_t *ld);
+/* Device pointer of the per-node accepted-step index (int8, n entries; BIGCLAM_F_RECORD_ACCEPTED):
+ * lets a multi-GPU caller exchange only the rows that changed. */
+int bigclam_device_accepted(bigclam_ctx *ctx, void **accepted_dev);
 
 /*
  * Multi-GPU (node-partitioned) pieces: a context created with an owned node range only updates

@@ -40,6 +40,7 @@ class OracleEngine:
         r = self.O.step(self.rp, self.col, F, s, self.P, node_mask=self.mask, want_pre=True)
         own = self.mask.astype(bool)
         upd = (r.accepted >= 0) & own
+        self._changed = torch.from_numpy(np.nonzero(upd)[0].astype(np.int64))
         self.F[self.cur ^ 1][torch.from_numpy(own)] = torch.from_numpy(r.F[own])
         self.part.zero_()
         self.part[: self.k] = torch.from_numpy((F[upd] - r.F[upd]).sum(axis=0))
@@ -64,8 +65,11 @@ class OracleEngine:
     def rollback(self):
         self.cur ^= 1
 
+    def changed_owned(self):
+        return self._changed
 
-def _worker(rank, world, port, variant, out):
+
+def _worker(rank, world, port, variant, exchange, out):
     sys.path.insert(0, REPO)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -78,13 +82,13 @@ def _worker(rank, world, port, variant, out):
     sumF = O.colsum(F0)
     bounds = partition_by_nnz(rp, world)
     eng = OracleEngine(O, rp, col, F0, sumF, k, int(bounds[rank]), int(bounds[rank + 1]))
-    d = DistBigClam(eng, rp, rank, world, bounds)
+    d = DistBigClam(eng, rp, rank, world, bounds, exchange=exchange)
     # three single calls
     llhs = [d.backtrackingLineSearchs() for _ in range(3)]
     F3 = eng.state()[0].numpy().copy()
     # then the pipelined loop from the initial state
     eng2 = OracleEngine(O, rp, col, F0, sumF, k, int(bounds[rank]), int(bounds[rank + 1]))
-    d2 = DistBigClam(eng2, rp, rank, world, bounds)
+    d2 = DistBigClam(eng2, rp, rank, world, bounds, exchange=exchange)
     ret, calls, trace = d2.run(variant=variant)
     if rank == 0:
         np.savez(out, llhs=np.array(llhs), F3=F3, ret=ret, calls=calls, trace=np.array(trace),
@@ -99,10 +103,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,variant", [(2, 4), (3, 2), (2, 3)])
-def test_partitioned_path_equals_single_process(tmp_path, oracle, world, variant):
+@pytest.mark.parametrize("world,variant,exchange", [(2, 4, "full"), (3, 2, "delta"), (2, 3, "delta")])
+def test_partitioned_path_equals_single_process(tmp_path, oracle, world, variant, exchange):
     out = str(tmp_path / "res.npz")
-    mp.spawn(_worker, args=(world, _free_port(), variant, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), variant, exchange, out), nprocs=world, join=True)
     z = np.load(out)
     n, k = 300, 6
     rp, col = random_graph(n, 6, seed=17, hub=50)

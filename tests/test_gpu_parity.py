@@ -25,7 +25,7 @@ def _solver(rp, col, K, F0, sumF=None, **kw):
     return b
 
 
-def _check_step(b, r, llh, max_flips=0, where=""):
+def _check_step(b, r, llh, max_flips=0, where="", max_idx_diff=0.02):
     """Rows must agree tightly; a "flip" is a row that does not (an Armijo decision that went the
     other way).  A differing accepted index alone is not a flip: at s ~ 1e-13..1e-15 the slope term
     alpha*s*|g|^2 is below one ulp of llh_u, the test degenerates to `llh' >= llh_u` and its outcome is
@@ -42,7 +42,7 @@ def _check_step(b, r, llh, max_flips=0, where=""):
         # index disagreements are only tolerated at noise-level step sizes (index >= 12 or -1)
         a, o = acc[idx_diff & ~flipped], r.accepted[idx_diff & ~flipped]
         assert ((a < 0) | (a >= 12)).all() and ((o < 0) | (o >= 12)).all(), (where, a, o)
-    assert idx_diff.mean() <= 0.02, where
+    assert idx_diff.mean() <= max_idx_diff, where
     if flips == 0:
         assert np.allclose(b.sumF, r.sumF, rtol=1e-11, atol=1e-9), where
         assert abs(llh - r.llh) <= 1e-10 * abs(r.llh), where
@@ -155,7 +155,7 @@ def test_multiplicity_kept_and_clamp_at_max_f(oracle):
     for it in range(8):
         llh = b.backtrackingLineSearchs()
         r = oracle.step(rp2, col2, F, sumF, P)
-        _check_step(b, r, llh, max_flips=1, where=f"dup it{it}")
+        _check_step(b, r, llh, max_flips=1, where=f"dup it{it}", max_idx_diff=0.25)   # rows pinned at MAX_F_: nf == fu, pure noise decisions
         F, sumF = b.F, b.sumF
         hit_max |= bool((F == 1000.0).any())
     b.close()
