@@ -244,14 +244,14 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rp, col, F0 = load_workload()
     n, nnz = len(rp) - 1, len(col)
-    b = BigClam(device=local, time_kernels=True)
+    b = BigClam(device=local, time_kernels=True, record_accepted=True)
     b.set_graph(rp, col).set_K(K)
     stream = torch.cuda.current_stream()
     b.set_stream(stream.cuda_stream)
     b.set_F(F0)
     bounds = partition_by_nnz(rp, world)
     eng = CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1]))
-    d = DistBigClam(eng, rp, rank, world, bounds)
+    d = DistBigClam(eng, rp, rank, world, bounds, exchange=os.environ.get("BIGCLAM_EXCHANGE", "delta"))
 
     for _ in range(args.warmup):
         d.step_nollh()
