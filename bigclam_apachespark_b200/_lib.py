@@ -77,8 +77,12 @@ SIGNATURES = {
     "bigclam_set_owned_range": (C.c_int, [_vp, _i64, _i64]),
     "bigclam_step_local": (C.c_int, [_vp, C.POINTER(_vp)]),
     "bigclam_finish_local": (C.c_int, [_vp, _pd, _pi64]),
+    "bigclam_collect_timing": (C.c_int, [_vp]),
     "bigclam_llh_local": (C.c_int, [_vp, C.POINTER(_vp)]),
     "bigclam_rollback": (C.c_int, [_vp]),
+    "bigclam_ipc_export": (C.c_int, [_vp, _vp]),
+    "bigclam_ipc_open_peers": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "bigclam_mark_all_changed": (C.c_int, [_vp]),
     "bigclam_graph_read_edgelist": (C.c_int, [C.c_char_p, _i32, C.POINTER(Graph), C.c_char_p, _i64]),
     "bigclam_graph_free": (None, [C.POINTER(Graph)]),
     "bigclam_device_count": (C.c_int, []),

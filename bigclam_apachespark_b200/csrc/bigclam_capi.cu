@@ -40,6 +40,9 @@ struct bigclam_ctx {
     uint8_t *d_mask = nullptr;
     int32_t *d_done = nullptr;
     unsigned int *d_work = nullptr;
+    int8_t *d_changed = nullptr;   // multi-GPU: row changed in the most recent step
+    int n_peers = 0;
+    double *peer_F[2][7] = {{nullptr}};   // peers' F buffers (both halves), IPC-mapped
     long long *d_dbg = nullptr;   // BIGCLAM_DEBUG_CYCLES=1: per-node timing scratch (4 x n)
     RunState *d_state = nullptr;
     double *d_trace = nullptr;
@@ -123,7 +126,8 @@ static void free_ctx(bigclam_ctx *c) {
     cudaFree(c->d_F[0]); cudaFree(c->d_F[1]);
     cudaFree(c->d_sumF[0]); cudaFree(c->d_sumF[1]);
     cudaFree(c->d_partials); cudaFree(c->d_accepted); cudaFree(c->d_mask);
-    cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_dbg); cudaFree(c->d_state); cudaFree(c->d_trace);
+    cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_dbg); cudaFree(c->d_changed);
+    for (int h = 0; h < 2; ++h) for (int r = 0; r < c->n_peers; ++r) if (c->peer_F[h][r]) cudaIpcCloseMemHandle(c->peer_F[h][r]); cudaFree(c->d_state); cudaFree(c->d_trace);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -413,7 +417,9 @@ static void fill_args(bigclam_ctx *ctx, StepArgs &a, bool linesearch, const uint
     a.w_hi = 1.0 / (1.0 - p.min_p);
     a.meta = ctx->d_meta;
     a.work_counter = ctx->d_work;
-    a.dbg = linesearch ? ctx->d_dbg : nullptr;
+    a.n_peers = linesearch ? ctx->n_peers : 0;
+    for (int r = 0; r < 7; ++r) a.peer_out[r] = (r < ctx->n_peers) ? ctx->peer_F[ctx->cur ^ 1][r] : nullptr;
+    a.changed = ctx->d_changed;
     a.maxm = ctx->maxm;
     a.order_n = ctx->order_n;
     a.node_mask = d_mask;
@@ -626,9 +632,6 @@ extern "C" int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi)
 extern "C" int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    ctx->ev_used = 0;
-    ctx->last_step_launches = 0;
-    ctx->last_all_launches = 0;
     StepArgs a;
     fill_args(ctx, a, true, nullptr, false);
     int rc = timed_launch(ctx, a, true);
@@ -640,11 +643,14 @@ extern "C" int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev) {
 extern "C" int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64_t *n_updated_out) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials + 2 * ctx->ld, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    const bool want = (llh_pre_out != nullptr) || (n_updated_out != nullptr);
+    if (want)
+        CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials + 2 * ctx->ld, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     int rc = launch_finish(ctx, 0, 0, 0.0, true, false);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(ctx->stream));
     ctx->cur ^= 1;
+    if (!want) return BIGCLAM_OK;            // fully asynchronous: nothing is read back, no host sync
+    CU(cudaStreamSynchronize(ctx->stream));
     if (llh_pre_out) *llh_pre_out = ctx->h_pinned[0];
     if (n_updated_out) *n_updated_out = (int64_t)(ctx->h_pinned[1] + 0.5);
     return collect_timing(ctx);
@@ -685,4 +691,58 @@ extern "C" int bigclam_device_accepted(bigclam_ctx *ctx, void **accepted_dev) {
         return fail(ctx, BIGCLAM_EINVAL, "bigclam_device_accepted: context created without BIGCLAM_F_RECORD_ACCEPTED");
     *accepted_dev = ctx->d_accepted;
     return BIGCLAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Peer replicas over NVLink (one process per GPU): every rank exports the CUDA IPC handles of its two
+// F buffers, the host framework all-gathers them, every rank opens the others'.  After that the step
+// kernel pushes changed rows straight into the peers' replicas (see StepArgs::peer_out).
+extern "C" int bigclam_ipc_export(bigclam_ctx *ctx, void *handles_out /* 2 x 64 bytes */) {
+    if (ctx == nullptr || handles_out == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h[2];
+    CU(cudaIpcGetMemHandle(&h[0], ctx->d_F[0]));
+    CU(cudaIpcGetMemHandle(&h[1], ctx->d_F[1]));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handles_out, h, sizeof(h));
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_ipc_open_peers(bigclam_ctx *ctx, int32_t world, int32_t rank, const void *all_handles /* world x 2 x 64 */) {
+    if (ctx == nullptr || all_handles == nullptr || world < 1 || world > 8 || rank < 0 || rank >= world)
+        return fail(ctx, BIGCLAM_EINVAL, "bigclam_ipc_open_peers: bad world/rank (at most 8 GPUs)");
+    CU(cudaSetDevice(ctx->device));
+    const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles);
+    int np = 0;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        for (int half = 0; half < 2; ++half) {
+            void *p = nullptr;
+            CU(cudaIpcOpenMemHandle(&p, h[2 * r + half], cudaIpcMemLazyEnablePeerAccess));
+            ctx->peer_F[half][np] = reinterpret_cast<double *>(p);
+        }
+        ++np;
+    }
+    ctx->n_peers = np;
+    if (ctx->d_changed == nullptr) CU(cudaMalloc(&ctx->d_changed, (size_t)ctx->n));
+    // every row counts as changed before the first step, so the first step publishes all owned rows
+    CU(cudaMemset(ctx->d_changed, 1, (size_t)ctx->n));
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_mark_all_changed(bigclam_ctx *ctx) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (ctx->d_changed == nullptr) return BIGCLAM_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemsetAsync(ctx->d_changed, 1, (size_t)ctx->n, ctx->stream));
+    return BIGCLAM_OK;
+}
+
+// Sums the CUDA-event timings recorded since the last collection (asynchronous multi-GPU loops).
+extern "C" int bigclam_collect_timing(bigclam_ctx *ctx) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    int rc = collect_timing(ctx);
+    return rc;
 }

@@ -70,6 +70,12 @@ struct StepArgs {
     int8_t *accepted;         // optional, n
     const int32_t *done_flag; // optional: non-zero -> the launch is a no-op
     int32_t do_linesearch;    // 0: PRE/LLH only (loglikelihood())
+    // node-partitioned multi-GPU: replicas of F_out on the other GPUs of the box (peer memory over
+    // NVLink, opened through CUDA IPC).  A row is pushed to every peer when this step or the previous one
+    // changed it (the previous one makes the peers' copy in this half of the double buffer stale).
+    int32_t n_peers;
+    double *peer_out[7];
+    int8_t *changed;          // n: 1 if the node's row changed in the most recent step (read: previous step)
     long long *dbg;           // optional debug scratch (unused in this build)
 };
 
@@ -767,6 +773,9 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
         }
 
         // ---------------- SWAP (:183-190) + partial sums for :191-192 ----------------
+        // fused exchange: the new row goes to the local replica and, over NVLink, straight into the
+        // peers' replicas (plain stores to IPC-mapped peer memory) while other warps keep computing
+        const bool push = (a.n_peers > 0) && a.do_linesearch && ((jstar >= 0) || (a.changed[u] != 0));
         if (jstar >= 0) {
             const double s = s_steps[jstar];
 #pragma unroll
@@ -782,6 +791,10 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
                     vd.x += fu[c].x - nr.x;
                     vd.y += fu[c].y - nr.y;
                     *pd = vd;
+                    if (push) {
+                        for (int pr = 0; pr < a.n_peers; ++pr)
+                            *reinterpret_cast<double2 *>(a.peer_out[pr] + (size_t)u * ld + 2 * q) = nr;
+                    }
                 }
             }
             nupd_acc += 1.0;
@@ -789,9 +802,16 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
 #pragma unroll
             for (int c = 0; c < C2; ++c) {
                 const int q = lane + 32 * c;
-                if (q < ld2) *reinterpret_cast<double2 *>(orow + 2 * q) = fu[c];
+                if (q < ld2) {
+                    *reinterpret_cast<double2 *>(orow + 2 * q) = fu[c];
+                    if (push) {
+                        for (int pr = 0; pr < a.n_peers; ++pr)
+                            *reinterpret_cast<double2 *>(a.peer_out[pr] + (size_t)u * ld + 2 * q) = fu[c];
+                    }
+                }
             }
         }
+        if (a.n_peers > 0 && a.do_linesearch && lane == 0) a.changed[u] = (jstar >= 0) ? 1 : 0;
         if (a.accepted != nullptr && lane == 0) a.accepted[u] = (int8_t)jstar;
 
         // ---- rotate the pipeline ----

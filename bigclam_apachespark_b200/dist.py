@@ -10,8 +10,10 @@ broadcast to every executor each call (codes/bigclam4-7.scala:154) and driver-si
   * one all-reduce (sum) of the partial reductions [sum(old-new) rows (ld) | - | llh | n_updated]
     replaces the driver-side reduce of :191-192 and :219;
   * the owners' new rows are exchanged so that every replica holds the new F (replaces the
-    re-broadcast of F at the next call, :154).  `exchange="full"` all-gathers the owned row
-    ranges; `exchange="delta"` sends only the rows whose step was accepted.
+    re-broadcast of F at the next call, :154).  `exchange="p2p"` (GPUs): the step kernel itself
+    stores every changed row into the peers' replicas (CUDA IPC peer memory over NVLink) — the exchange
+    is fused into the compute kernel; `"delta"` all-gathers only the accepted rows with NCCL; `"full"`
+    broadcasts every owner's row range.
 
 The collectives go through torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests, where
 a test-side engine stands in for the C-ABI context).  The engine interface is the multi-GPU part of
@@ -85,14 +87,36 @@ class CudaEngine:
         self.check(self.lib.bigclam_llh_local(self.ctx, C.byref(p)), self.ctx)
         return self._view(p.value, 2 * self.ld + 2)
 
-    def finish_local(self):
+    def finish_local(self, sync: bool = True):
+        if not sync:
+            self.check(self.lib.bigclam_finish_local(self.ctx, None, None), self.ctx)
+            return None, None
         llh = C.c_double()
         nupd = C.c_int64()
         self.check(self.lib.bigclam_finish_local(self.ctx, C.byref(llh), C.byref(nupd)), self.ctx)
         return llh.value, nupd.value
 
+    def collect_timing(self):
+        self.check(self.lib.bigclam_collect_timing(self.ctx), self.ctx)
+        return self.s.kernel_time()
+
     def rollback(self):
         self.check(self.lib.bigclam_rollback(self.ctx), self.ctx)
+
+    def open_peers(self, dist, rank: int, world: int):
+        """Exchange the CUDA IPC handles of the F double buffers and map every peer's replica, so that
+        the step kernel can push changed rows straight into them over NVLink (exchange="p2p")."""
+        torch = self.torch
+        mine = (C.c_ubyte * 128)()
+        self.check(self.lib.bigclam_ipc_export(self.ctx, mine), self.ctx)
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).cuda()
+        allh = torch.empty(world * 128, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh, t)
+        buf = (C.c_ubyte * (world * 128)).from_buffer_copy(allh.cpu().numpy().tobytes())
+        self.check(self.lib.bigclam_ipc_open_peers(self.ctx, world, rank, buf), self.ctx)
+
+    def mark_all_changed(self):
+        self.check(self.lib.bigclam_mark_all_changed(self.ctx), self.ctx)
 
     def changed_owned(self):
         """Global ids (int64, device) of the owned rows whose step was accepted by the last step_local
@@ -120,6 +144,8 @@ class DistBigClam:
         if exchange == "delta":
             import torch
             self.torch = torch
+        if exchange == "p2p":
+            engine.open_peers(self.dist, rank, world)
 
     @property
     def owned(self):
@@ -127,6 +153,8 @@ class DistBigClam:
 
     def _exchange_rows(self, F_cur, F_next):
         """Afterwards every replica of F_next holds the new F."""
+        if self.exchange == "p2p":
+            return      # the step kernel already pushed the changed rows into the peers' replicas
         if self.exchange == "full":
             # owners publish their whole row range
             for r in range(self.world):
@@ -172,14 +200,15 @@ class DistBigClam:
         F_next[gidx] = all_rows[valid]
         self._prev_changed = gidx
 
-    def step_nollh(self):
+    def step_nollh(self, sync: bool = True):
         """PRE + line search + row swap + sumF update.  Returns the LLH of the state BEFORE this
-        call (== the LLH the previous call returns, the fused identity) and n_updated."""
+        call (== the LLH the previous call returns, the fused identity) and n_updated; with
+        sync=False nothing is read back and the host does not wait (None, None)."""
         F_cur, F_next, _ = self.e.state()
         part = self.e.step_local()
         self.dist.all_reduce(part)                      # sum over ranks (:191-192, :219)
         self._exchange_rows(F_cur, F_next)
-        llh_pre, nupd = self.e.finish_local()           # sumF -= sum(old - new) on every rank
+        llh_pre, nupd = self.e.finish_local(sync) if sync is False else self.e.finish_local()   # sumF -= sum(old - new)
         self.last_n_updated = nupd
         return llh_pre, nupd
 
@@ -251,7 +280,7 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     b.set_F(F0)
     bounds = partition_by_nnz(rp, world)
     eng = CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1]))
-    d = DistBigClam(eng, rp, rank, world, bounds, exchange=os.environ.get("BIGCLAM_EXCHANGE", "delta"))
+    d = DistBigClam(eng, rp, rank, world, bounds, exchange=os.environ.get("BIGCLAM_EXCHANGE", "p2p"))
 
     for _ in range(args.warmup):
         d.step_nollh()
@@ -263,8 +292,9 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     launches = 0
+    sync = d.exchange != "p2p"       # the NCCL delta exchange sizes its buffers on the host
     for _ in range(args.steps):
-        d.step_nollh()
+        d.step_nollh(sync=sync)
         launches += 2
     llh_end = d.loglikelihood()              # the LLH of the last call (tail pass, inside the timed region)
     launches += 1

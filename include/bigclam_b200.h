@@ -131,11 +131,26 @@ int bigclam_device_accepted(bigclam_ctx *ctx, void **accepted_dev);
  */
 int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi);
 int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev /* 2*ld+2 doubles */);
-int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64_t *n_updated_out);
+int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64_t *n_updated_out);  /* both NULL: asynchronous, no host sync */
+int bigclam_collect_timing(bigclam_ctx *ctx);   /* sync + sum the kernel timings recorded since the last collection */
 int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev /* llh at [2*ld] */);
 /* Undo the most recent bigclam_finish_local (the previous F and sumF are still intact in the other
  * halves of the double buffers): used to drop the speculative step of a pipelined convergence loop. */
 int bigclam_rollback(bigclam_ctx *ctx);
+
+/*
+ * Peer replicas over NVLink (one process per GPU on one box).  bigclam_ipc_export writes the two CUDA IPC
+ * handles (2 x 64 bytes) of this context's F double buffer; the caller all-gathers them over its own
+ * plumbing and hands all of them (world x 2 x 64 bytes, rank order) to bigclam_ipc_open_peers.  From then
+ * on bigclam_step_local pushes every owned row that this step or the previous one changed straight into
+ * the peers' replicas (plain stores to peer memory inside the step kernel): the row exchange that
+ * replaces the reference's re-broadcast of F (bigclam4-7.scala:154) is fused into the compute kernel and
+ * only the all-reduce of the partials remains.  bigclam_mark_all_changed forces a full publish (after
+ * bigclam_set_F).
+ */
+int bigclam_ipc_export(bigclam_ctx *ctx, void *handles_out);
+int bigclam_ipc_open_peers(bigclam_ctx *ctx, int32_t world, int32_t rank, const void *all_handles);
+int bigclam_mark_all_changed(bigclam_ctx *ctx);
 
 /*
  * Edge-list reader with GraphX semantics (GraphLoader.edgeListFile, bigclam4-7.scala:45;

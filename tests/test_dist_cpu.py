@@ -55,7 +55,7 @@ class OracleEngine:
         self.part[2 * self.k] = float(per[self.mask.astype(bool)].sum())
         return self.part
 
-    def finish_local(self):
+    def finish_local(self, sync=True):
         llh, nupd = float(self.part[2 * self.k]), int(round(float(self.part[2 * self.k + 1])))
         s = self.sumF[self.cur]
         self.sumF[self.cur ^ 1].copy_(s - self.part[: self.k] if nupd > 0 else s)

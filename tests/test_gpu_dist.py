@@ -12,7 +12,7 @@ from conftest import REPO, random_graph
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, exchange, out):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, REPO)
@@ -27,15 +27,19 @@ def _worker(rank, world, port, out):
     rng = np.random.default_rng(5)
     F0 = rng.random((n, k)) * (rng.random((n, k)) < 0.2)
     sumF = O.colsum(F0)
-    b = BigClam(device=rank)
+    b = BigClam(device=rank, record_accepted=True)
     b.set_graph(rp, col).set_K(k)
     b.set_stream(torch.cuda.current_stream().cuda_stream)
     b.set_F(F0, sumF=sumF)
     bounds = partition_by_nnz(rp, world)
-    d = DistBigClam(CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1])), rp, rank, world, bounds)
+    d = DistBigClam(CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1])), rp, rank, world, bounds, exchange=exchange)
     llhs = [d.backtrackingLineSearchs() for _ in range(3)]
     F3, s3 = b.F, b.sumF
     b.set_F(F0, sumF=sumF)
+    d._need_sync = True
+    d._prev_changed = None
+    if exchange == "p2p":
+        d.e.mark_all_changed()
     ret, calls, trace = d.run(variant=4, max_outer=40)
     if rank == 0:
         np.savez(out, llhs=np.array(llhs), F3=F3, s3=s3, ret=ret, calls=calls, trace=np.array(trace), Fend=b.F)
@@ -43,7 +47,8 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_gpu_partitioned_equals_oracle(tmp_path, oracle):
+@pytest.mark.parametrize("exchange", ["p2p", "delta", "full"])
+def test_two_gpu_partitioned_equals_oracle(tmp_path, oracle, exchange):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -53,7 +58,7 @@ def test_two_gpu_partitioned_equals_oracle(tmp_path, oracle):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     out = str(tmp_path / "res.npz")
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, exchange, out), nprocs=world, join=True)
     z = np.load(out)
     n, k = 3000, 40
     rp, col = random_graph(n, 8, seed=5, hub=300)
