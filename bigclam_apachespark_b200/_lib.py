@@ -74,6 +74,7 @@ SIGNATURES = {
     "bigclam_set_stream": (C.c_int, [_vp, _vp]),
     "bigclam_device_state": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _pi64]),
     "bigclam_device_accepted": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "bigclam_set_owned_nodes": (C.c_int, [_vp, _vp, _i64]),
     "bigclam_set_owned_range": (C.c_int, [_vp, _i64, _i64]),
     "bigclam_step_local": (C.c_int, [_vp, C.POINTER(_vp)]),
     "bigclam_finish_local": (C.c_int, [_vp, _pd, _pi64]),

@@ -31,6 +31,7 @@ struct bigclam_ctx {
     NodeMeta *d_meta = nullptr;
     int32_t maxm = 0;
     int64_t order_n = 0;
+    int32_t n_hubs = 0;
     int64_t lo = 0, hi = 0;
     double *d_F[2] = {nullptr, nullptr};
     double *d_sumF[2] = {nullptr, nullptr};
@@ -161,13 +162,11 @@ static void launch_step(int c2, const StepArgs &a, int grid, size_t smem, cudaSt
     }
 }
 
-static int rebuild_order(bigclam_ctx *ctx, const std::vector<int64_t> &rowptr_host) {
-    // Processing order over the owned range: degree descending (hubs first so the tail of the
+static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowptr_host, std::vector<int32_t> &order) {
+    // Processing order over the owned nodes: degree descending (hubs first so the tail of the
     // launch is made of cheap nodes), ties by id; packed as NodeMeta so one 16-byte load gives a
     // warp everything it needs to start a node.
-    const int64_t cnt = ctx->hi - ctx->lo;
-    std::vector<int32_t> order((size_t)cnt);
-    std::iota(order.begin(), order.end(), (int32_t)ctx->lo);
+    const int64_t cnt = (int64_t)order.size();
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
         return (rowptr_host[a + 1] - rowptr_host[a]) > (rowptr_host[b + 1] - rowptr_host[b]);
     });
@@ -181,7 +180,26 @@ static int rebuild_order(bigclam_ctx *ctx, const std::vector<int64_t> &rowptr_ho
     if (ctx->d_meta == nullptr) CU(cudaMalloc(&ctx->d_meta, sizeof(NodeMeta) * std::max<size_t>(1, (size_t)ctx->n)));
     if (cnt > 0) CU(cudaMemcpy(ctx->d_meta, meta.data(), sizeof(NodeMeta) * (size_t)cnt, cudaMemcpyHostToDevice));
     ctx->order_n = cnt;
+    // hubs (block-cooperative phase): only the C2 <= 4 kernels have the staging buffers the phase uses
+    int32_t nh = 0;
+    // a node is worth sharing among a block's warps when its serial chain (~ its degree) is a sizeable
+    // fraction of what one warp processes in the whole launch (owned entries / #warps)
+    int64_t own_nnz = 0;
+    for (int64_t i = 0; i < cnt; ++i) own_nnz += meta[(size_t)i].deg;
+    const int64_t per_warp = own_nnz / std::max<int64_t>(1, (int64_t)ctx->grid * kWarpsPerBlock);
+    const int64_t hub_deg = std::max<int64_t>(kHubDegree, per_warp / 5);
+    if (ctx->c2 <= 4) while (nh < cnt && meta[(size_t)nh].deg >= hub_deg) ++nh;
+    ctx->n_hubs = nh;
+    const unsigned int init = (unsigned int)nh + 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
+    ctx->h_work_init = init;
+    if (ctx->d_work != nullptr) CU(cudaMemcpy(ctx->d_work + 1, &init, sizeof(unsigned int), cudaMemcpyHostToDevice));
     return BIGCLAM_OK;
+}
+
+static int rebuild_order(bigclam_ctx *ctx, const std::vector<int64_t> &rowptr_host) {
+    std::vector<int32_t> order((size_t)(ctx->hi - ctx->lo));
+    std::iota(order.begin(), order.end(), (int32_t)ctx->lo);
+    return rebuild_order_list(ctx, rowptr_host, order);
 }
 
 extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowptr, const int32_t *col,
@@ -284,7 +302,8 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     CUC(cudaMalloc(&ctx->d_accepted, (size_t)n));
     CUC(cudaMalloc(&ctx->d_mask, (size_t)n));
     CUC(cudaMalloc(&ctx->d_done, sizeof(int32_t)));
-    CUC(cudaMalloc(&ctx->d_work, sizeof(unsigned int)));
+    CUC(cudaMalloc(&ctx->d_work, 2 * sizeof(unsigned int)));      // [0] live counter, [1] its initial value
+    CUC(cudaMemcpy(ctx->d_work + 1, &ctx->h_work_init, sizeof(unsigned int), cudaMemcpyHostToDevice));
     if (std::getenv("BIGCLAM_DEBUG_CYCLES") != nullptr) {
         CUC(cudaMalloc(&ctx->d_dbg, sizeof(long long) * (4 * (size_t)n + 16)));
         CUC(cudaMemset(ctx->d_dbg, 0, sizeof(long long) * (4 * (size_t)n + 16)));
@@ -422,6 +441,7 @@ static void fill_args(bigclam_ctx *ctx, StepArgs &a, bool linesearch, const uint
     a.changed = ctx->d_changed;
     a.maxm = ctx->maxm;
     a.order_n = ctx->order_n;
+    a.n_hubs = ctx->n_hubs;
     a.node_mask = d_mask;
     a.partials = ctx->d_partials;
     a.accepted = (linesearch && (p.flags & BIGCLAM_F_RECORD_ACCEPTED)) ? ctx->d_accepted : nullptr;
@@ -440,7 +460,7 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
         CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
     }
     // positions 0 .. 3*#warps-1 are pre-assigned statically, the rest is handed out dynamically
-    CU(cudaMemcpyAsync(ctx->d_work, &ctx->h_work_init, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_work, ctx->d_work + 1, sizeof(unsigned int), cudaMemcpyDeviceToDevice, ctx->stream));
     launch_step(ctx->c2, a, ctx->grid, ctx->smem_bytes, ctx->stream);
     CU(cudaGetLastError());
     if (timing) {
@@ -745,4 +765,21 @@ extern "C" int bigclam_collect_timing(bigclam_ctx *ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     int rc = collect_timing(ctx);
     return rc;
+}
+
+// Arbitrary (non-contiguous) owned node set, e.g. the degree-sorted node list dealt round-robin over
+// the ranks so that every rank gets the same mix of hubs and leaves (used with the peer-store exchange).
+extern "C" int bigclam_set_owned_nodes(bigclam_ctx *ctx, const int32_t *nodes, int64_t count) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (count < 0 || count > ctx->n || (count > 0 && nodes == nullptr))
+        return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_owned_nodes: bad node list");
+    for (int64_t i = 0; i < count; ++i)
+        if (nodes[i] < 0 || nodes[i] >= ctx->n) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_owned_nodes: node out of range");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<int64_t> rp((size_t)ctx->n + 1);
+    CU(cudaMemcpy(rp.data(), ctx->d_rowptr, sizeof(int64_t) * rp.size(), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> order(nodes, nodes + count);
+    ctx->lo = 0;
+    ctx->hi = ctx->n;
+    return rebuild_order_list(ctx, rp, order);
 }

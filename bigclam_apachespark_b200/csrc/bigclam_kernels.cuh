@@ -38,6 +38,7 @@ namespace bigclam {
 
 constexpr int kWarpsPerBlock = 6;      // 12 warps/SM at ~168 registers: the point where ptxas stops spilling
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
+constexpr int kHubDegree = 48;      // floor of the degree from which a node is shared by the warps of a block
 constexpr int kMaxSteps = 64;       // MaxInter + 1 <= kMaxSteps
 constexpr int kMaxActiveCap = 256;  // upper bound of the active-set lists (and of pair-list t)
 constexpr int kMaxPairs = 512;      // capacity of the pair list of one line-search chunk (<= 32 edges)
@@ -64,6 +65,7 @@ struct StepArgs {
     double x_lo, x_hi, t_lo, t_hi, w_lo, w_hi;
     const NodeMeta *meta;     // processing order (degree descending) over the owned nodes
     int64_t order_n;
+    int32_t n_hubs;           // the first n_hubs positions (degree >= kHubDegree) are processed one per BLOCK
     unsigned int *work_counter;   // next position to hand out (host sets it to 4 * #warps)
     const uint8_t *node_mask; // optional uset
     double *partials;         // [D(ld) = sum(old - new) | unused(ld) | llh | n_updated]
@@ -337,6 +339,136 @@ __device__ __forceinline__ double chunk_dots(const double2 (&vec)[C2], const dou
     return myx;
 }
 
+// Line search, edge range [ebeg, eend) of one node: per-lane sum over the range's edges e = (chunk edge)
+// with parity h of  log(1 - clamp(exp(-nf_j . fv_e))) + nf_j . fv_e  for the lane's own trial j (step s).
+// Builds the (t, fv_t) pair lists of up to 32 edges at a time in the warp's shared memory, then walks them.
+struct LsLists {
+    double2 *afg;
+    double *pval;
+    unsigned short *aidx;
+    unsigned short *poff;
+    unsigned char *pt;
+};
+__device__ __forceinline__ double ls_edge_range(const double *__restrict__ F, const int32_t *__restrict__ colp,
+                                                int ebeg, int eend, int ld, int m, int my_idx0, unsigned lt_mask,
+                                                int lane, int h, double s, bool need_hi, double max_f,
+                                                const EdgeConst &ec, const LsLists &L) {
+    double2 *s_afg = L.afg;
+    double *s_pval = L.pval;
+    unsigned short *s_aidx = L.aidx;
+    unsigned short *s_poff = L.poff;
+    unsigned char *s_pt = L.pt;
+    const int mdiv = max(m, 1);
+    double sumterms = 0.0;
+    // groups of 32 edges (one coalesced load of neighbour ids), split into chunks whose
+    // pairs fit the list
+    for (int gb = ebeg; gb < eend; gb += 32) {
+      const int gcnt = min(32, eend - gb);
+      const int cv = (lane < gcnt) ? colp[gb + lane] : 0;
+      int ge = 0;
+      while (ge < gcnt) {
+        int np = 0, ce = 0;
+        if (lane == 0) s_poff[0] = 0;
+        // build: for every edge keep (t, fv[idx_t]) with fv != 0
+        if (m <= 32) {
+            while (ge + ce < gcnt) {
+                int nb = min(4, gcnt - ge - ce);
+                if (np + nb * m > kMaxPairs) {
+                    nb = (kMaxPairs - np) / mdiv;
+                    if (nb == 0) break;
+                }
+                double val[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {          // up to 4 gathers in flight
+                    const int v = __shfl_sync(0xffffffffu, cv, (ge + ce + r) & 31);
+                    val[r] = (r < nb && lane < m) ? __ldg(F + (size_t)v * ld + my_idx0) : 0.0;
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (r < nb) {
+                        const unsigned bal = __ballot_sync(0xffffffffu, val[r] != 0.0);
+                        if (val[r] != 0.0) {
+                            const int pp = np + __popc(bal & lt_mask);
+                            s_pval[pp] = val[r];
+                            s_pt[pp] = (unsigned char)lane;
+                        }
+                        np += __popc(bal);
+                        if (lane == 0) s_poff[ce + r + 1] = (unsigned short)np;
+                    }
+                }
+                ce += nb;
+            }
+        } else {
+            // hubs / dense rows: up to 8 gather rounds per edge, all issued before the ballots;
+            // the list is filled optimistically and the last edge rolled back if it overflows
+            while (ge + ce < gcnt) {
+                const int v = __shfl_sync(0xffffffffu, cv, (ge + ce) & 31);
+                const double *fv = F + (size_t)v * ld;
+                double vv[kMaxActiveCap / 32];
+#pragma unroll
+                for (int r = 0; r < kMaxActiveCap / 32; ++r) {
+                    const int t = 32 * r + lane;
+                    vv[r] = (t < m) ? __ldg(fv + s_aidx[t]) : 0.0;
+                }
+                const int np0 = np;
+#pragma unroll
+                for (int r = 0; r < kMaxActiveCap / 32; ++r) {
+                    if (32 * r < m) {
+                        const unsigned bal = __ballot_sync(0xffffffffu, vv[r] != 0.0);
+                        if (vv[r] != 0.0) {
+                            const int pp = np + __popc(bal & lt_mask);
+                            if (pp < kMaxPairs) {
+                                s_pval[pp] = vv[r];
+                                s_pt[pp] = (unsigned char)(32 * r + lane);
+                            }
+                        }
+                        np += __popc(bal);
+                    }
+                }
+                if (np > kMaxPairs) { np = np0; break; }      // does not fit: flush first
+                if (lane == 0) s_poff[ce + 1] = (unsigned short)np;
+                ++ce;
+            }
+        }
+        __syncwarp();
+        // consume: lane (j, h) walks the pairs of edges e2 + h and e2 + 2 + h (two exp/log chains)
+        auto pairdot = [&](int e, bool valid) -> double {
+            const int i0 = valid ? (int)s_poff[e] : 0;
+            const int i1 = valid ? (int)s_poff[e + 1] : 0;
+            double D = 0.0;
+            if (need_hi) {
+#pragma unroll 1
+                for (int i = i0; i < i1; ++i) {
+                    const double2 fg = s_afg[s_pt[i]];
+                    D = fma(clamp_step0(fg.x, s, fg.y, max_f), s_pval[i], D);
+                }
+            } else {
+#pragma unroll 1
+                for (int i = i0; i < i1; ++i) {
+                    const double2 fg = s_afg[s_pt[i]];
+                    D = fma(clamp_step0_lo(fg.x, s, fg.y), s_pval[i], D);
+                }
+            }
+            return D;
+        };
+#pragma unroll 1
+        for (int e2 = 0; e2 < ce; e2 += 4) {
+            const int eA = e2 + h, eB = e2 + 2 + h;
+            const bool vA = eA < ce, vB = eB < ce;
+            const double DA = pairdot(eA, vA);
+            const double DB = pairdot(eB, vB);
+            double tA, tB;
+            edge_term2(DA, DB, ec, tA, tB);
+            sumterms += vA ? tA : 0.0;
+            sumterms += vB ? tB : 0.0;
+        }
+        __syncwarp();
+        ge += ce;
+      }
+    }
+    return sumterms;
+}
+
 // Dense line search (cold path): lane-owned components, candidates in descending order, early exit.
 // fu is re-read from F_in and the gradient from `grow` (the caller parks it in the node's F_out row,
 // which it owns and overwrites afterwards) so that no register array has its address taken.
@@ -386,6 +518,279 @@ __device__ __noinline__ int dense_linesearch(const double *__restrict__ F, const
     return -1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Hub phase: one high-degree node per BLOCK.  A node's edges are independent in PRE (sum over edges)
+// and in the line search (sum over edges per trial), so the block's warps take contiguous slices of
+// the neighbour list, exchange the partial gradient / partial per-trial sums through shared memory, and
+// every warp redundantly derives the (identical) gradient, active set and decision; warp 0 writes the
+// row.  This bounds the serial chain of a degree-d node by d / kWarpsPerBlock edges.
+struct HubArgs {
+    const NodeMeta *meta;
+    const int32_t *col;
+    const double *F_in;
+    double *F_out;
+    const uint8_t *node_mask;
+    int8_t *accepted;
+    int8_t *changed;
+    double *peer_out[7];
+    int32_t n_peers, n_hubs, ld, nsteps, do_linesearch;
+    double alpha, min_f, max_f;
+};
+
+template <int C2>
+__device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, const double *s_sumF, const double *s_steps,
+                                       double *s_D, double *s_rows_all, const LsLists lists, double *hub_small,
+                                       double *llh_acc_io, double *nupd_acc_io) {
+    const int ld = ha.ld, ld2 = ha.ld >> 1;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const double *__restrict__ F = ha.F_in;
+    double *my_part = s_rows_all + (size_t)wib * 4 * ld;           // this warp's partial gradient
+    double *hub_S1 = hub_small;                                     // [kWarpsPerBlock]
+    double *hub_st = hub_small + kWarpsPerBlock;                    // [kWarpsPerBlock][32]
+    int *hub_j = reinterpret_cast<int *>(hub_small + kWarpsPerBlock * 33);
+    const double max_f = ha.max_f;
+
+    for (int hb = blockIdx.x; hb < ha.n_hubs; hb += gridDim.x) {
+        const NodeMeta nm = ha.meta[hb];
+        const int64_t u = nm.u, e0 = nm.e0;
+        const int deg = nm.deg;
+        const int32_t *colp = ha.col + e0;
+        const int per = (((deg + kWarpsPerBlock - 1) / kWarpsPerBlock) + 3) & ~3;
+        const int ebeg = min(deg, wib * per), eend = min(deg, ebeg + per);
+
+        double2 fu[C2];
+        double fusf = 0.0, fufu = 0.0;
+#pragma unroll
+        for (int c = 0; c < C2; ++c) {
+            const int q = lane + 32 * c;
+            fu[c] = (q < ld2) ? ldg2(F + (size_t)u * ld + 2 * q) : make_double2(0.0, 0.0);
+            if (q < ld2) {
+                const double2 sf = *reinterpret_cast<const double2 *>(s_sumF + 2 * q);
+                fusf = fma(fu[c].x, sf.x, fusf); fusf = fma(fu[c].y, sf.y, fusf);
+                fufu = fma(fu[c].x, fu[c].x, fufu); fufu = fma(fu[c].y, fu[c].y, fufu);
+            }
+        }
+        fusf = warp_sum(fusf);
+        fufu = warp_sum(fufu);
+
+        // ---- PRE over this warp's slice (batches of 4 rows straight from global memory) ----
+        double2 g[C2];
+#pragma unroll
+        for (int c = 0; c < C2; ++c) g[c] = make_double2(0.0, 0.0);
+        double S1 = 0.0;
+        const int rsel = (lane >> 3) & 3;
+        for (int gb = ebeg; gb < eend; gb += 32) {
+            const int cnt = min(32, eend - gb);
+            const int myv = (lane < cnt) ? colp[gb + lane] : 0;
+            for (int eb = 0; eb < cnt; eb += 4) {
+                double2 x[4][C2];
+                double part[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int v = __shfl_sync(0xffffffffu, myv, (eb + r) & 31);
+                    const double *fv = F + (size_t)v * ld;
+                    const bool ok = eb + r < cnt;
+                    double p = 0.0;
+#pragma unroll
+                    for (int c = 0; c < C2; ++c) {
+                        const int q = lane + 32 * c;
+                        x[r][c] = (ok && q < ld2) ? ldg2(fv + 2 * q) : make_double2(0.0, 0.0);
+                        p = fma(fu[c].x, x[r][c].x, p);
+                        p = fma(fu[c].y, x[r][c].y, p);
+                    }
+                    part[r] = p;
+                }
+                const bool b4 = lane & 16, b3 = lane & 8;
+                double k0 = b4 ? part[2] : part[0], k1 = b4 ? part[3] : part[1];
+                const double s0 = b4 ? part[0] : part[2], s1 = b4 ? part[1] : part[3];
+                k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+                k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                double kx = b3 ? k1 : k0;
+                const double sd = b3 ? k0 : k1;
+                kx += __shfl_xor_sync(0xffffffffu, sd, 8);
+                kx += __shfl_xor_sync(0xffffffffu, kx, 4);
+                kx += __shfl_xor_sync(0xffffffffu, kx, 2);
+                kx += __shfl_xor_sync(0xffffffffu, kx, 1);
+                double w;
+                double t = edge_term<true>(kx, ec, w);
+                t = (eb + rsel < cnt) ? t : 0.0;
+                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                t += __shfl_xor_sync(0xffffffffu, t, 16);
+                S1 += t;
+                if (ha.do_linesearch) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const double we = __shfl_sync(0xffffffffu, w, 8 * r);
+#pragma unroll
+                        for (int c = 0; c < C2; ++c) {
+                            g[c].x = fma(we, x[r][c].x, g[c].x);
+                            g[c].y = fma(we, x[r][c].y, g[c].y);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- combine the partial gradient and S1 over the block ----
+#pragma unroll
+        for (int c = 0; c < C2; ++c) {
+            const int q = lane + 32 * c;
+            if (q < ld2) *reinterpret_cast<double2 *>(my_part + 2 * q) = g[c];
+        }
+        if (lane == 0) hub_S1[wib] = S1;
+        __syncthreads();
+        S1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < C2; ++c) g[c] = make_double2(0.0, 0.0);
+        for (int w = 0; w < kWarpsPerBlock; ++w) {
+            S1 += hub_S1[w];
+            const double *pw = s_rows_all + (size_t)w * 4 * ld;
+#pragma unroll
+            for (int c = 0; c < C2; ++c) {
+                const int q = lane + 32 * c;
+                if (q < ld2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(pw + 2 * q);
+                    g[c].x += v.x;
+                    g[c].y += v.y;
+                }
+            }
+        }
+        __syncthreads();
+        const double llh_u = (S1 - fusf) + fufu;
+        const bool in_uset = (ha.node_mask == nullptr) || (ha.node_mask[u] != 0);
+        int jstar = -1;
+        if (ha.do_linesearch && in_uset) {
+            double G2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < C2; ++c) {
+                const int q = lane + 32 * c;
+                if (q < ld2) {
+                    const double2 sf = *reinterpret_cast<const double2 *>(s_sumF + 2 * q);
+                    g[c].x = (g[c].x - sf.x) + fu[c].x;
+                    g[c].y = (g[c].y - sf.y) + fu[c].y;
+                    G2 = fma(g[c].x, g[c].x, G2);
+                    G2 = fma(g[c].y, g[c].y, G2);
+                }
+            }
+            G2 = warp_sum(G2);
+            int m = 0;
+            const bool sparse_ok = (ha.min_f == 0.0);
+            if (sparse_ok) {
+#pragma unroll
+                for (int c = 0; c < C2; ++c) {
+                    const int q = lane + 32 * c;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const double fval = hh ? fu[c].y : fu[c].x;
+                        const double gval = hh ? g[c].y : g[c].x;
+                        const bool act = (q < ld2) && (fval > 0.0 || gval > 0.0);
+                        const unsigned bal = __ballot_sync(0xffffffffu, act);
+                        if (bal) {
+                            if (act) {
+                                const int posn = m + __popc(bal & lt_mask);
+                                if (posn < kMaxActiveCap) {
+                                    lists.afg[posn] = make_double2(fval, gval);
+                                    lists.aidx[posn] = (unsigned short)(2 * q + hh);
+                                }
+                            }
+                            m += __popc(bal);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            if (sparse_ok && m <= kMaxActiveCap) {
+                const int j16 = lane & 15, h = lane >> 4;
+                const int my_idx0 = (lane < m) ? (int)lists.aidx[lane] : 0;
+                bool hi_lane = false;
+                for (int t = lane; t < m; t += 32) {
+                    const double2 fg = lists.afg[t];
+                    hi_lane |= (fg.x + fg.y > max_f);
+                }
+                const bool need_hi = __any_sync(0xffffffffu, hi_lane);
+                for (int tg = 0; tg < ha.nsteps && jstar < 0; tg += 16) {
+                    const int j = tg + j16;
+                    const bool jok = j < ha.nsteps;
+                    const double s = s_steps[jok ? j : 0];
+                    double st = ls_edge_range(F, colp, ebeg, eend, ld, m, my_idx0, lt_mask, lane, h, s, need_hi, max_f, ec, lists);
+                    st += __shfl_xor_sync(0xffffffffu, st, 16);
+                    hub_st[wib * 32 + lane] = st;
+                    __syncthreads();
+                    double sumterms = 0.0;
+                    for (int w = 0; w < kWarpsPerBlock; ++w) sumterms += hub_st[w * 32 + lane];
+                    __syncthreads();
+                    double oa = 0.0, ob = 0.0;
+                    for (int t = h; t < m; t += 2) {
+                        const double2 fg = lists.afg[t];
+                        const double nf = need_hi ? clamp_step0(fg.x, s, fg.y, max_f) : clamp_step0_lo(fg.x, s, fg.y);
+                        const double sf = (s_sumF[lists.aidx[t]] - fg.x) + nf;
+                        oa = fma(nf, sf, oa);
+                        ob = fma(nf, nf, ob);
+                    }
+                    oa += __shfl_xor_sync(0xffffffffu, oa, 16);
+                    ob += __shfl_xor_sync(0xffffffffu, ob, 16);
+                    const double result = (sumterms - oa) + ob;
+                    const double rhs = llh_u + (ha.alpha * s) * G2;
+                    const unsigned pass = __ballot_sync(0xffffffffu, jok && (result >= rhs)) & 0xffffu;
+                    if (pass) jstar = tg + __ffs(pass) - 1;
+                }
+            } else {
+                // MIN_F_ != 0 or more active components than the lists hold: warp 0 runs the dense search
+                double *orow = ha.F_out + (size_t)u * ld;
+                if (wib == 0) {
+#pragma unroll
+                    for (int c = 0; c < C2; ++c) {
+                        const int q = lane + 32 * c;
+                        if (q < ld2) *reinterpret_cast<double2 *>(orow + 2 * q) = g[c];
+                    }
+                    __syncwarp();
+                    const int jd = dense_linesearch<C2, 4>(F, colp, ld, ha.nsteps, s_steps, ha.alpha, ha.min_f, max_f, ec,
+                                                            F + (size_t)u * ld, orow, s_sumF, deg, lane, llh_u, G2);
+                    if (lane == 0) hub_j[0] = jd;
+                }
+                __syncthreads();
+                jstar = hub_j[0];
+                __syncthreads();
+            }
+        }
+        // ---- SWAP by warp 0 ----
+        if (wib == 0) {
+            double *orow = ha.F_out + (size_t)u * ld;
+            const bool push = (ha.n_peers > 0) && ha.do_linesearch && ((jstar >= 0) || (ha.changed[u] != 0));
+            if (ha.do_linesearch) {
+                const double s = (jstar >= 0) ? s_steps[jstar] : 0.0;
+#pragma unroll
+                for (int c = 0; c < C2; ++c) {
+                    const int q = lane + 32 * c;
+                    if (q < ld2) {
+                        double2 nr = fu[c];
+                        if (jstar >= 0) {
+                            nr.x = clamp_step(fu[c].x, s, g[c].x, ha.min_f, max_f);
+                            nr.y = clamp_step(fu[c].y, s, g[c].y, ha.min_f, max_f);
+                            double2 *pd = reinterpret_cast<double2 *>(s_D + 2 * q);
+                            double2 vd = *pd;
+                            vd.x += fu[c].x - nr.x;
+                            vd.y += fu[c].y - nr.y;
+                            *pd = vd;
+                        }
+                        *reinterpret_cast<double2 *>(orow + 2 * q) = nr;
+                        if (push) {
+                            for (int pr = 0; pr < ha.n_peers; ++pr)
+                                *reinterpret_cast<double2 *>(ha.peer_out[pr] + (size_t)u * ld + 2 * q) = nr;
+                        }
+                    }
+                }
+                if (jstar >= 0) *nupd_acc_io += 1.0;
+            }
+            *llh_acc_io += llh_u;
+            if (ha.accepted != nullptr && lane == 0) ha.accepted[u] = (int8_t)jstar;
+            if (ha.n_peers > 0 && ha.do_linesearch && lane == 0) ha.changed[u] = (jstar >= 0) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+}
+
+
 template <int C2, int R>
 __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(const StepArgs a) {
     if (a.done_flag != nullptr && *a.done_flag != 0) return;
@@ -404,6 +809,7 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
     unsigned short *s_aidx = wl->aidx;
     unsigned short *s_poff = wl->poff;
     unsigned char *s_pt = wl->pt;
+    const LsLists lists = {s_afg, s_pval, s_aidx, s_poff, s_pt};
 
     for (int i = threadIdx.x; i < ld; i += kBlockThreads) s_sumF[i] = a.sumF[i];
     for (int i = threadIdx.x; i < kMaxSteps; i += kBlockThreads) s_steps[i] = a.steps[i];
@@ -420,9 +826,26 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
     const double *__restrict__ F = a.F_in;
     const unsigned lt_mask = (1u << lane) - 1u;
 
+    // ---------------- hub phase (block-cooperative), then one warp per node ----------------
+    __shared__ double hub_small[kWarpsPerBlock * 33 + 2];
+    if (a.n_hubs > 0) {
+        if constexpr (C2 <= 4) {
+            HubArgs ha;
+            ha.meta = a.meta; ha.col = a.col; ha.F_in = a.F_in; ha.F_out = a.F_out; ha.node_mask = a.node_mask;
+            ha.accepted = a.accepted; ha.changed = a.changed;
+            for (int r = 0; r < 7; ++r) ha.peer_out[r] = a.peer_out[r];
+            ha.n_peers = a.n_peers; ha.n_hubs = a.n_hubs; ha.ld = ld; ha.nsteps = nsteps; ha.do_linesearch = a.do_linesearch;
+            ha.alpha = a.alpha; ha.min_f = a.min_f; ha.max_f = max_f;
+            double hub_llh = 0.0, hub_nupd = 0.0;
+            hub_phase<C2>(ha, ec, s_sumF, s_steps, s_D, s_sumF + (size_t)ld * (1 + kWarpsPerBlock), lists, hub_small, &hub_llh, &hub_nupd);
+            llh_acc += hub_llh;
+            nupd_acc += hub_nupd;
+        }
+    }
+
     // software pipeline: cur (being processed), nxt (meta in registers; ids + own row loaded at the
     // top of cur's iteration, rows prefetched to L2), pos_nn (position handed out for the node after)
-    int64_t pos = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+    int64_t pos = (int64_t)a.n_hubs + (int64_t)blockIdx.x * kWarpsPerBlock + wib;
     int64_t pos_n = pos + nwarps, pos_nn = pos + 2 * nwarps;
     NodeMeta cur = {0, 0, 0}, nxt = {0, 0, 0};
     if (pos < order_n) cur = a.meta[pos];
@@ -635,113 +1058,7 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
                     const int j = tg + j16;
                     const bool jok = j < nsteps;
                     const double s = s_steps[jok ? j : 0];
-                    double sumterms = 0.0;
-                    // groups of 32 edges (one coalesced load of neighbour ids), split into chunks whose
-                    // pairs fit the list
-                    for (int gb = 0; gb < deg; gb += 32) {
-                      const int gcnt = min(32, deg - gb);
-                      const int cv = (lane < gcnt) ? a.col[e0 + gb + lane] : 0;
-                      int ge = 0;
-                      while (ge < gcnt) {
-                        int np = 0, ce = 0;
-                        if (lane == 0) s_poff[0] = 0;
-                        // build: for every edge keep (t, fv[idx_t]) with fv != 0
-                        if (m <= 32) {
-                            while (ge + ce < gcnt) {
-                                int nb = min(4, gcnt - ge - ce);
-                                if (np + nb * m > kMaxPairs) {
-                                    nb = (kMaxPairs - np) / mdiv;
-                                    if (nb == 0) break;
-                                }
-                                double val[4];
-#pragma unroll
-                                for (int r = 0; r < 4; ++r) {          // up to 4 gathers in flight
-                                    const int v = __shfl_sync(0xffffffffu, cv, (ge + ce + r) & 31);
-                                    val[r] = (r < nb && lane < m) ? __ldg(F + (size_t)v * ld + my_idx0) : 0.0;
-                                }
-#pragma unroll
-                                for (int r = 0; r < 4; ++r) {
-                                    if (r < nb) {
-                                        const unsigned bal = __ballot_sync(0xffffffffu, val[r] != 0.0);
-                                        if (val[r] != 0.0) {
-                                            const int pp = np + __popc(bal & lt_mask);
-                                            s_pval[pp] = val[r];
-                                            s_pt[pp] = (unsigned char)lane;
-                                        }
-                                        np += __popc(bal);
-                                        if (lane == 0) s_poff[ce + r + 1] = (unsigned short)np;
-                                    }
-                                }
-                                ce += nb;
-                            }
-                        } else {
-                            // hubs / dense rows: up to 8 gather rounds per edge, all issued before the ballots;
-                            // the list is filled optimistically and the last edge rolled back if it overflows
-                            while (ge + ce < gcnt) {
-                                const int v = __shfl_sync(0xffffffffu, cv, (ge + ce) & 31);
-                                const double *fv = F + (size_t)v * ld;
-                                double vv[kMaxActiveCap / 32];
-#pragma unroll
-                                for (int r = 0; r < kMaxActiveCap / 32; ++r) {
-                                    const int t = 32 * r + lane;
-                                    vv[r] = (t < m) ? __ldg(fv + s_aidx[t]) : 0.0;
-                                }
-                                const int np0 = np;
-#pragma unroll
-                                for (int r = 0; r < kMaxActiveCap / 32; ++r) {
-                                    if (32 * r < m) {
-                                        const unsigned bal = __ballot_sync(0xffffffffu, vv[r] != 0.0);
-                                        if (vv[r] != 0.0) {
-                                            const int pp = np + __popc(bal & lt_mask);
-                                            if (pp < kMaxPairs) {
-                                                s_pval[pp] = vv[r];
-                                                s_pt[pp] = (unsigned char)(32 * r + lane);
-                                            }
-                                        }
-                                        np += __popc(bal);
-                                    }
-                                }
-                                if (np > kMaxPairs) { np = np0; break; }      // does not fit: flush first
-                                if (lane == 0) s_poff[ce + 1] = (unsigned short)np;
-                                ++ce;
-                            }
-                        }
-                        __syncwarp();
-                        // consume: lane (j, h) walks the pairs of edges e2 + h and e2 + 2 + h (two exp/log chains)
-                        auto pairdot = [&](int e, bool valid) -> double {
-                            const int i0 = valid ? (int)s_poff[e] : 0;
-                            const int i1 = valid ? (int)s_poff[e + 1] : 0;
-                            double D = 0.0;
-                            if (need_hi) {
-#pragma unroll 1
-                                for (int i = i0; i < i1; ++i) {
-                                    const double2 fg = s_afg[s_pt[i]];
-                                    D = fma(clamp_step0(fg.x, s, fg.y, max_f), s_pval[i], D);
-                                }
-                            } else {
-#pragma unroll 1
-                                for (int i = i0; i < i1; ++i) {
-                                    const double2 fg = s_afg[s_pt[i]];
-                                    D = fma(clamp_step0_lo(fg.x, s, fg.y), s_pval[i], D);
-                                }
-                            }
-                            return D;
-                        };
-#pragma unroll 1
-                        for (int e2 = 0; e2 < ce; e2 += 4) {
-                            const int eA = e2 + h, eB = e2 + 2 + h;
-                            const bool vA = eA < ce, vB = eB < ce;
-                            const double DA = pairdot(eA, vA);
-                            const double DB = pairdot(eB, vB);
-                            double tA, tB;
-                            edge_term2(DA, DB, ec, tA, tB);
-                            sumterms += vA ? tA : 0.0;
-                            sumterms += vB ? tB : 0.0;
-                        }
-                        __syncwarp();
-                        ge += ce;
-                      }
-                    }
+                    double sumterms = ls_edge_range(F, a.col + e0, 0, deg, ld, m, my_idx0, lt_mask, lane, h, s, need_hi, max_f, ec, lists);
                     sumterms += __shfl_xor_sync(0xffffffffu, sumterms, 16);
                     // - newfu.sfT + newfu.newfu with sfT = (sumF - fu) + newfu   (:176,:180)
                     double oa = 0.0, ob = 0.0;
@@ -775,7 +1092,6 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
         // ---------------- SWAP (:183-190) + partial sums for :191-192 ----------------
         // fused exchange: the new row goes to the local replica and, over NVLink, straight into the
         // peers' replicas (plain stores to IPC-mapped peer memory) while other warps keep computing
-        const bool push = (a.n_peers > 0) && a.do_linesearch && ((jstar >= 0) || (a.changed[u] != 0));
         if (jstar >= 0) {
             const double s = s_steps[jstar];
 #pragma unroll
@@ -791,10 +1107,7 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
                     vd.x += fu[c].x - nr.x;
                     vd.y += fu[c].y - nr.y;
                     *pd = vd;
-                    if (push) {
-                        for (int pr = 0; pr < a.n_peers; ++pr)
-                            *reinterpret_cast<double2 *>(a.peer_out[pr] + (size_t)u * ld + 2 * q) = nr;
-                    }
+                    fu[c] = nr;                 // fu is dead after this point: reuse it for the pushes below
                 }
             }
             nupd_acc += 1.0;
@@ -802,16 +1115,23 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
 #pragma unroll
             for (int c = 0; c < C2; ++c) {
                 const int q = lane + 32 * c;
-                if (q < ld2) {
-                    *reinterpret_cast<double2 *>(orow + 2 * q) = fu[c];
-                    if (push) {
-                        for (int pr = 0; pr < a.n_peers; ++pr)
-                            *reinterpret_cast<double2 *>(a.peer_out[pr] + (size_t)u * ld + 2 * q) = fu[c];
+                if (q < ld2) *reinterpret_cast<double2 *>(orow + 2 * q) = fu[c];
+            }
+        }
+        if (a.n_peers > 0 && a.do_linesearch) {
+            // kept out of the common path: with one GPU this block is never entered
+            if ((jstar >= 0) || (a.changed[u] != 0)) {
+                for (int pr = 0; pr < a.n_peers; ++pr) {
+                    double *prow = a.peer_out[pr] + (size_t)u * ld;
+#pragma unroll
+                    for (int c = 0; c < C2; ++c) {
+                        const int q = lane + 32 * c;
+                        if (q < ld2) *reinterpret_cast<double2 *>(prow + 2 * q) = fu[c];
                     }
                 }
             }
+            if (lane == 0) a.changed[u] = (jstar >= 0) ? 1 : 0;
         }
-        if (a.n_peers > 0 && a.do_linesearch && lane == 0) a.changed[u] = (jstar >= 0) ? 1 : 0;
         if (a.accepted != nullptr && lane == 0) a.accepted[u] = (int8_t)jstar;
 
         // ---- rotate the pipeline ----

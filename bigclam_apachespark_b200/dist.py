@@ -52,10 +52,19 @@ class _DevMemI8:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "|i1", "data": (int(ptr), False), "version": 3}
 
 
+def deal_by_degree(rowptr: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Owned node set of `rank` when the degree-sorted node list is dealt round-robin over the ranks:
+    every rank gets the same mix of hubs and leaves (used with the peer-store exchange, which does not
+    need contiguous ranges)."""
+    deg = np.diff(rowptr)
+    order = np.argsort(-deg, kind="stable")
+    return np.sort(order[rank::world]).astype(np.int32)
+
+
 class CudaEngine:
     """The C-ABI context of one rank (libbigclam_b200.so) behind the engine interface."""
 
-    def __init__(self, solver, lo: int, hi: int):
+    def __init__(self, solver, lo: int, hi: int, nodes=None):
         import torch
         from . import _lib
         self.torch = torch
@@ -63,8 +72,13 @@ class CudaEngine:
         self.check = _lib.check
         self.s = solver
         self.ctx = solver._need()
-        self.check(self.lib.bigclam_set_owned_range(self.ctx, lo, hi), self.ctx)
+        if nodes is None:
+            self.check(self.lib.bigclam_set_owned_range(self.ctx, lo, hi), self.ctx)
+        else:
+            nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+            self.check(self.lib.bigclam_set_owned_nodes(self.ctx, nodes.ctypes.data, len(nodes)), self.ctx)
         self.lo, self.hi = int(lo), int(hi)
+        self._views = {}
         self.n, self.k = solver.n, solver.K
         _, _, _, ld = solver.device_state()
         self.ld = ld
@@ -72,15 +86,21 @@ class CudaEngine:
     def _view(self, ptr, count):
         return self.torch.as_tensor(_DevMem(ptr, count), device="cuda")
 
+    def _cached(self, ptr, count):
+        v = self._views.get((ptr, count))
+        if v is None:
+            v = self._views[(ptr, count)] = self._view(ptr, count)
+        return v
+
     def state(self):
         f, fn, sf, ld = self.s.device_state()
-        return (self._view(f, self.n * ld).view(self.n, ld), self._view(fn, self.n * ld).view(self.n, ld),
-                self._view(sf, ld))
+        return (self._cached(f, self.n * ld).view(self.n, ld), self._cached(fn, self.n * ld).view(self.n, ld),
+                self._cached(sf, ld))
 
     def step_local(self):
         p = C.c_void_p()
         self.check(self.lib.bigclam_step_local(self.ctx, C.byref(p)), self.ctx)
-        return self._view(p.value, 2 * self.ld + 2)
+        return self._cached(p.value, 2 * self.ld + 2)
 
     def llh_local(self):
         p = C.c_void_p()
@@ -204,10 +224,11 @@ class DistBigClam:
         """PRE + line search + row swap + sumF update.  Returns the LLH of the state BEFORE this
         call (== the LLH the previous call returns, the fused identity) and n_updated; with
         sync=False nothing is read back and the host does not wait (None, None)."""
-        F_cur, F_next, _ = self.e.state()
         part = self.e.step_local()
         self.dist.all_reduce(part)                      # sum over ranks (:191-192, :219)
-        self._exchange_rows(F_cur, F_next)
+        if self.exchange != "p2p":
+            F_cur, F_next, _ = self.e.state()
+            self._exchange_rows(F_cur, F_next)
         llh_pre, nupd = self.e.finish_local(sync) if sync is False else self.e.finish_local()   # sumF -= sum(old - new)
         self.last_n_updated = nupd
         return llh_pre, nupd
@@ -279,8 +300,10 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     b.set_stream(stream.cuda_stream)
     b.set_F(F0)
     bounds = partition_by_nnz(rp, world)
-    eng = CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1]))
-    d = DistBigClam(eng, rp, rank, world, bounds, exchange=os.environ.get("BIGCLAM_EXCHANGE", "p2p"))
+    exchange = os.environ.get("BIGCLAM_EXCHANGE", "p2p")
+    nodes = deal_by_degree(rp, rank, world) if exchange == "p2p" else None
+    eng = CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1]), nodes=nodes)
+    d = DistBigClam(eng, rp, rank, world, bounds, exchange=exchange)
 
     for _ in range(args.warmup):
         d.step_nollh()
@@ -305,6 +328,13 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
+    kms, nk, _ = eng.collect_timing()
+    per_rank = torch.zeros(world, device="cuda", dtype=torch.float64)
+    per_rank[rank] = kms / max(nk, 1)
+    dist.all_reduce(per_rank)
+    own0 = deal_by_degree(rp, 0, world) if exchange == "p2p" else np.arange(bounds[0], bounds[1])
+    own_nnz = int(np.diff(rp)[own0].sum())
+    own_n = len(own0)
     ms_per_step = total_ms / args.steps
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -314,10 +344,14 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
             "iters_per_sec": 1e3 / ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "com-amazon topology (SNAP fixture) + synthetic F0",
             "config": {"workload": WORKLOAD, "n": n, "nnz_directed": nnz, "k": K,
-                       "parallelism": f"node-partitioned x{world} (nnz-balanced contiguous ranges), F replicated, "
-                                      f"all-reduce of [sum(old-new), llh, n_updated] + {d.exchange} row exchange per step",
+                       "parallelism": f"node-partitioned x{world} ({'degree-sorted nodes dealt round-robin' if exchange == 'p2p' else 'nnz-balanced contiguous ranges'}), "
+                                      f"F replicated, all-reduce of [sum(old-new), llh, n_updated] + {d.exchange} row exchange per step",
                        "l2": "inputs larger than L2, no flush", "llh_end": llh_end},
             "clocks": clocks, "gpu_launches": launches,
-            "e2e": None, "roofline": None, "cpu_baseline": None,
+            "rank_step_kernel_ms": [round(float(x), 4) for x in per_rank.tolist()],
+            "roofline": {"bound": "hbm", "achieved": alg_bytes(own_n, own_nnz, K) / (float(per_rank[0]) * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg_bytes(own_n, own_nnz, K) / (float(per_rank[0]) * 1e-3) / 1e9 / peak,
+                         "traffic": None, "kernel": "step_kernel<4,4> on rank 0 (owned rows only, incl. NVLink pushes)", "peak_source": peak_src},
+            "e2e": None, "cpu_baseline": None,
         }))
     dist.destroy_process_group()

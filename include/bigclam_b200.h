@@ -130,6 +130,7 @@ int bigclam_device_accepted(bigclam_ctx *ctx, void **accepted_dev);
  * the caller all-reduces; bigclam_finish_local applies the reduced values (sumF update, :192).
  */
 int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi);
+int bigclam_set_owned_nodes(bigclam_ctx *ctx, const int32_t *nodes, int64_t count);   /* arbitrary owned set */
 int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev /* 2*ld+2 doubles */);
 int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64_t *n_updated_out);  /* both NULL: asynchronous, no host sync */
 int bigclam_collect_timing(bigclam_ctx *ctx);   /* sync + sum the kernel timings recorded since the last collection */
