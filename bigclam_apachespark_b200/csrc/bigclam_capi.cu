@@ -350,9 +350,15 @@ extern "C" int bigclam_device_state(bigclam_ctx *ctx, void **F_dev, void **F_nex
 }
 
 static int colsum_current(bigclam_ctx *ctx) {
-    const int blocks = (ctx->ld + 31) / 32;
-    colsum_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_F[ctx->cur], ctx->n, ctx->ld, ctx->d_sumF[ctx->cur]);
+    const int nchunks = (int)((ctx->n + kColsumRows - 1) / kColsumRows);
+    double *part = nullptr;
+    CU(cudaMalloc(&part, sizeof(double) * (size_t)nchunks * ctx->ld));
+    dim3 grid((ctx->ld + 31) / 32, nchunks);
+    colsum_partial_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_F[ctx->cur], ctx->n, ctx->ld, part);
+    colsum_final_kernel<<<(ctx->ld + 127) / 128, 128, 0, ctx->stream>>>(part, nchunks, ctx->ld, ctx->d_sumF[ctx->cur]);
     CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(part));
     return BIGCLAM_OK;
 }
 

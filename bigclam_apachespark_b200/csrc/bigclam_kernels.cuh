@@ -1245,22 +1245,33 @@ __global__ void finish_kernel(const FinishArgs f) {
     for (int i = threadIdx.x; i < 2 * ld + 2; i += blockDim.x) f.partials[i] = 0.0;
 }
 
-// F <-> pitched layout helpers and column sums.
-__global__ void colsum_kernel(const double *F, int64_t n, int ld, double *out) {
-    // one block per 32 columns slice; deterministic order within a thread, tree across threads
+// Column sums of F (initial sumF, bigclam4-7.scala:105-106): pass 1 sums row chunks of kColsumRows rows
+// per block into part[chunk][col] (coalesced: 32 lanes = 32 consecutive columns), pass 2 adds the chunks
+// in chunk order.  Deterministic.
+constexpr int kColsumRows = 2048;
+__global__ void colsum_partial_kernel(const double *F, int64_t n, int ld, double *part) {
     const int col = blockIdx.x * 32 + (threadIdx.x & 31);
     const int rlane = threadIdx.x >> 5;             // 0..7
+    const int64_t r0 = (int64_t)blockIdx.y * kColsumRows;
+    const int64_t r1 = min(n, r0 + kColsumRows);
     double acc = 0.0;
     if (col < ld)
-        for (int64_t r = rlane; r < n; r += 8) acc += F[(size_t)r * ld + col];
+        for (int64_t r = r0 + rlane; r < r1; r += 8) acc += F[(size_t)r * ld + col];
     __shared__ double s[8][33];
     s[rlane][threadIdx.x & 31] = acc;
     __syncthreads();
     if (rlane == 0 && col < ld) {
         double v = 0.0;
         for (int i = 0; i < 8; ++i) v += s[i][threadIdx.x & 31];
-        out[col] = v;
+        part[(size_t)blockIdx.y * ld + col] = v;
     }
+}
+__global__ void colsum_final_kernel(const double *part, int nchunks, int ld, double *out) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ld) return;
+    double v = 0.0;
+    for (int c = 0; c < nchunks; ++c) v += part[(size_t)c * ld + col];
+    out[col] = v;
 }
 
 }  // namespace bigclam

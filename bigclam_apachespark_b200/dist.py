@@ -328,6 +328,17 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
+    # e2e: the reference-facing call (one full backtrackingLineSearchs per step, LLH read back by the host)
+    n_e2e = min(args.steps, 20)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        d.backtrackingLineSearchs()
+    torch.cuda.synchronize()
+    te = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_e2e], device="cuda", dtype=torch.float64)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
     kms, nk, _ = eng.collect_timing()
     per_rank = torch.zeros(world, device="cuda", dtype=torch.float64)
     per_rank[rank] = kms / max(nk, 1)
@@ -352,6 +363,9 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
             "roofline": {"bound": "hbm", "achieved": alg_bytes(own_n, own_nnz, K) / (float(per_rank[0]) * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": alg_bytes(own_n, own_nnz, K) / (float(per_rank[0]) * 1e-3) / 1e9 / peak,
                          "traffic": None, "kernel": "step_kernel<4,4> on rank 0 (owned rows only, incl. NVLink pushes)", "peak_source": peak_src},
-            "e2e": None, "cpu_baseline": None,
+            "e2e": {"value": nnz / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 32 * world,
+                    "ms_per_step": e2e_ms, "note": "DistBigClam.backtrackingLineSearchs(): step kernel + all-reduce + sumF + separate LLH pass + all-reduce, "
+                                                   "LLH and n_updated read back by every rank each step; F replicas stay resident"},
+            "cpu_baseline": None,
         }))
     dist.destroy_process_group()
