@@ -139,17 +139,32 @@ extern "C" void bigclam_destroy(bigclam_ctx *ctx) { free_ctx(ctx); }
 template <int C2>
 struct RowsInFlight { static constexpr int value = (C2 <= 4) ? 4 : (C2 <= 8 ? 2 : 1); };
 
+template <int C2, bool kHub, bool kPush>
+static cudaError_t configure_one(size_t smem, int *blocks_per_sm) {
+    constexpr int R = RowsInFlight<C2>::value;
+    cudaError_t e = cudaFuncSetAttribute(step_kernel<C2, R, kHub, kPush>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<C2, R, kHub, kPush>, kBlockThreads, smem);
+}
+
 template <int C2>
 static cudaError_t configure_kernel(size_t smem, int *blocks_per_sm) {
-    constexpr int R = RowsInFlight<C2>::value;
-    cudaError_t e = cudaFuncSetAttribute(step_kernel<C2, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<C2, R>, kBlockThreads, smem);
+    int b = 0;
+    cudaError_t e = configure_one<C2, false, false>(smem, blocks_per_sm);
+    if (e == cudaSuccess) e = configure_one<C2, true, false>(smem, &b);
+    if (e == cudaSuccess) e = configure_one<C2, false, true>(smem, &b);
+    if (e == cudaSuccess) e = configure_one<C2, true, true>(smem, &b);
+    return e;
 }
 
 template <int C2>
 static void launch_step_t(const StepArgs &a, int grid, size_t smem, cudaStream_t st) {
-    step_kernel<C2, RowsInFlight<C2>::value><<<grid, kBlockThreads, smem, st>>>(a);
+    constexpr int R = RowsInFlight<C2>::value;
+    const bool hub = a.n_hubs > 0, push = a.n_peers > 0;
+    if (hub && push) step_kernel<C2, R, true, true><<<grid, kBlockThreads, smem, st>>>(a);
+    else if (hub) step_kernel<C2, R, true, false><<<grid, kBlockThreads, smem, st>>>(a);
+    else if (push) step_kernel<C2, R, false, true><<<grid, kBlockThreads, smem, st>>>(a);
+    else step_kernel<C2, R, false, false><<<grid, kBlockThreads, smem, st>>>(a);
 }
 
 static void launch_step(int c2, const StepArgs &a, int grid, size_t smem, cudaStream_t st) {
@@ -183,11 +198,12 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
     // hubs (block-cooperative phase): only the C2 <= 4 kernels have the staging buffers the phase uses
     int32_t nh = 0;
     // a node is worth sharing among a block's warps when its serial chain (~ its degree) is a sizeable
-    // fraction of what one warp processes in the whole launch (owned entries / #warps)
+    // fraction of what one warp processes in the whole launch (owned entries / #warps); below that the
+    // hubs-first order already hides it
     int64_t own_nnz = 0;
     for (int64_t i = 0; i < cnt; ++i) own_nnz += meta[(size_t)i].deg;
     const int64_t per_warp = own_nnz / std::max<int64_t>(1, (int64_t)ctx->grid * kWarpsPerBlock);
-    const int64_t hub_deg = std::max<int64_t>(kHubDegree, per_warp / 5);
+    const int64_t hub_deg = std::max<int64_t>(kHubDegree, (3 * per_warp) / 4);
     if (ctx->c2 <= 4) while (nh < cnt && meta[(size_t)nh].deg >= hub_deg) ++nh;
     ctx->n_hubs = nh;
     const unsigned int init = (unsigned int)nh + 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
@@ -480,6 +496,7 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
 
 static int collect_timing(bigclam_ctx *ctx) {
     ctx->last_step_ms = 0.0;
+    if (ctx->p.flags & BIGCLAM_F_TIME_KERNELS) ctx->last_step_launches = (int64_t)(ctx->ev_used / 2);
     for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));

@@ -791,7 +791,9 @@ __device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, con
 }
 
 
-template <int C2, int R>
+// kHub: the launch has block-cooperative hub nodes; kPush: peers' replicas are written (multi-GPU).
+// Both are compile-time so that the single-GPU, hub-free launch carries none of that code.
+template <int C2, int R, bool kHub, bool kPush>
 __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(const StepArgs a) {
     if (a.done_flag != nullptr && *a.done_flag != 0) return;
 
@@ -828,8 +830,8 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
 
     // ---------------- hub phase (block-cooperative), then one warp per node ----------------
     __shared__ double hub_small[kWarpsPerBlock * 33 + 2];
-    if (a.n_hubs > 0) {
-        if constexpr (C2 <= 4) {
+    if constexpr (kHub && C2 <= 4) {
+        if (a.n_hubs > 0) {
             HubArgs ha;
             ha.meta = a.meta; ha.col = a.col; ha.F_in = a.F_in; ha.F_out = a.F_out; ha.node_mask = a.node_mask;
             ha.accepted = a.accepted; ha.changed = a.changed;
@@ -1118,8 +1120,8 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
                 if (q < ld2) *reinterpret_cast<double2 *>(orow + 2 * q) = fu[c];
             }
         }
-        if (a.n_peers > 0 && a.do_linesearch) {
-            // kept out of the common path: with one GPU this block is never entered
+        if (kPush && a.n_peers > 0 && a.do_linesearch) {
+            // multi-GPU launches only (compile-time flag)
             if ((jstar >= 0) || (a.changed[u] != 0)) {
                 for (int pr = 0; pr < a.n_peers; ++pr) {
                     double *prow = a.peer_out[pr] + (size_t)u * ld;

@@ -328,6 +328,7 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
+    kms, nk, _ = eng.collect_timing()        # step-kernel events of the timed (asynchronous) region
     # e2e: the reference-facing call (one full backtrackingLineSearchs per step, LLH read back by the host)
     n_e2e = min(args.steps, 20)
     dist.barrier()
@@ -339,7 +340,6 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     te = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_e2e], device="cuda", dtype=torch.float64)
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
-    kms, nk, _ = eng.collect_timing()
     per_rank = torch.zeros(world, device="cuda", dtype=torch.float64)
     per_rank[rank] = kms / max(nk, 1)
     dist.all_reduce(per_rank)
