@@ -203,7 +203,10 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
     int64_t own_nnz = 0;
     for (int64_t i = 0; i < cnt; ++i) own_nnz += meta[(size_t)i].deg;
     const int64_t per_warp = own_nnz / std::max<int64_t>(1, (int64_t)ctx->grid * kWarpsPerBlock);
-    const int64_t hub_deg = std::max<int64_t>(kHubDegree, (3 * per_warp) / 4);
+    // whole graph on one GPU: the launch is long and the hubs-first order hides all but extreme hubs
+    // (and a hub-free launch uses the leaner kernel variant); a partition's launch is short: share earlier
+    const bool partitioned = cnt < ctx->n;
+    const int64_t hub_deg = std::max<int64_t>(kHubDegree, partitioned ? per_warp / 5 : (3 * per_warp) / 4);
     if (ctx->c2 <= 4) while (nh < cnt && meta[(size_t)nh].deg >= hub_deg) ++nh;
     ctx->n_hubs = nh;
     const unsigned int init = (unsigned int)nh + 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
