@@ -202,6 +202,26 @@ def run_single(args):
            "d2h_bytes_per_step": 72, "ms_per_step": e2e_ms,
            "note": "bigclam_step(): uset mask H2D (pinned) + step kernel + sumF + separate LLH pass + LLH/n_updated D2H; F stays resident like the reference's cached RDD"}
 
+    # ---- workload A of SURVEY §8d: the reference's own init (conductance seeds, 0/1 indicator columns) ----
+    extra_a = None
+    if not args.no_init_a:
+        t0 = time.perf_counter()
+        b.initNeighborComF(K)
+        init_s = time.perf_counter() - t0
+        b._run(4, 0.0, args.warmup)
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        b._run(4, 0.0, args.steps)
+        eb.record(stream)
+        torch.cuda.synchronize()
+        ms_a = ea.elapsed_time(eb) / args.steps
+        kms_a, nk_a, _ = b.kernel_time()
+        extra_a = {"workload": "com-amazon K=200, F0 = initNeighborComF(200) (bigclam4-7.scala:81-108: 0/1 indicator columns of the 200 best-conductance seeds)",
+                   "value": nnz / (ms_a * 1e-3), "unit": "edges/s", "ms_per_step": ms_a, "step_kernel_ms": kms_a / max(nk_a, 1),
+                   "roofline_frac": balg / (kms_a / max(nk_a, 1) * 1e-3) / 1e9 / peak, "host_init_seconds": init_s,
+                   "llh_end": float(b.last_trace[-1])}
+
     # ---- CPU baseline beside it (bounded: 2 faithful steps after 1 warm-up) ----
     cpu = None
     if not args.no_cpu:
@@ -221,7 +241,7 @@ def run_single(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "step_kernel<4>", "kernel_ms": kavg_ms,
                      "alg_bytes_per_launch": balg, "peak_source": peak_src},
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "reference_init_workload": extra_a,
     }))
     b.close()
 
@@ -233,6 +253,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-init-a", action="store_true", help="skip the reference-style-init extra workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -10,7 +10,8 @@ here does arithmetic on F.
     minCom/maxCom/divCom :16-20                    BigClam(minCom, maxCom, divCom), Kset()
     alpha, beta, MaxInter :22-26                   BigClam(alpha, beta, MaxInter)
     GraphLoader.edgeListFile + collectNeighborIds :45,:50   BigClam.load_edge_list / read_edge_list
-    K = sc.broadcast(i); initNeighborComF(K) :249-250       BigClam.set_K(K); BigClam.set_F(F0)
+    conductanceLocalMin() / Sbc :58-75             BigClam.conductanceLocalMin()
+    K = sc.broadcast(i); initNeighborComF(K) :249-250       BigClam.initNeighborComF(K)  (or set_K(K); set_F(F0))
     backtrackingLineSearchs(uset) :152             BigClam.backtrackingLineSearchs(uset=None)
     loglikelihood()    bigclamv3-7.scala:106       BigClam.loglikelihood()
     SGDFindC()         bigclam4-7.scala:225        BigClam.SGDFindC()
@@ -100,6 +101,7 @@ class BigClam:
         self.rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
         self.col = np.ascontiguousarray(col, dtype=np.int32)
         self.ids = ids
+        self.Sbc = None
         return self
 
     @property
@@ -147,6 +149,34 @@ class BigClam:
         out = np.empty(self.K, dtype=np.float64)
         check(_lib.load().bigclam_get_sumF(self._need(), out.ctypes.data), self._ctx)
         return out
+
+    # ---- init of F (conductanceLocalMin + initNeighborComF, bigclam4-7.scala:58-108) ----
+    def conductanceLocalMin(self):
+        """Ranked seed candidates (dense vertex indices) and the conductance of every vertex."""
+        lib = _lib.load()
+        cond = np.empty(self.n, dtype=np.float64)
+        seeds = np.empty(self.n, dtype=np.int32)
+        cnt = C.c_int64()
+        rc = lib.bigclam_conductance_seeds(self.n, self.rowptr.ctypes.data, self.col.ctypes.data, cond.ctypes.data,
+                                           seeds.ctypes.data, C.byref(cnt))
+        if rc != _lib.OK:
+            raise _lib.BigclamError(rc, "bigclam_conductance_seeds failed")
+        self.Sbc = seeds[:cnt.value].copy()             # `Sbc` of the script (:75), reused for every K
+        self.conductance = cond
+        return self.Sbc
+
+    def initNeighborComF(self, K: int, include_self: bool = False, pad_seed: int = 1234):
+        """Builds F0 from the ranked seeds and loads it (sets F and sumF like the script, :105-107)."""
+        if getattr(self, "Sbc", None) is None:
+            self.conductanceLocalMin()
+        F0 = np.empty((self.n, int(K)), dtype=np.float64)
+        rc = _lib.load().bigclam_init_neighbor_com_F(self.n, self.rowptr.ctypes.data, self.col.ctypes.data, int(K),
+                                                     self.Sbc.ctypes.data, len(self.Sbc), 1 if include_self else 0,
+                                                     C.c_uint64(pad_seed), F0.ctypes.data)
+        if rc != _lib.OK:
+            raise _lib.BigclamError(rc, "bigclam_init_neighbor_com_F failed")
+        self.set_F(F0)
+        return F0
 
     # ---- the hot path ----
     def backtrackingLineSearchs(self, uset=None) -> float:
@@ -201,6 +231,26 @@ class BigClam:
 
     def Kset(self) -> list[int]:
         return Kset(self.minCom, self.maxCom, self.divCom)
+
+    def sweep_K(self, rel_gain: float = 0.001, max_outer: int = 0):
+        """The K sweep at the bottom of the script (bigclam4-7.scala:244-266): for K in Kset, initNeighborComF(K),
+        SGDFindC(); stop at the first K whose LLH gain over the previous K is below 0.1 % (`1 - new/old < 0.001`).
+        As coded, LLHKold starts at 0.0 (the `== null` test is never true for a Double), so the first K never
+        stops the sweep.  Returns (KforC, [(K, LLH), ...]); KforC is 0 when the sweep ran out of K values (:245)."""
+        LLHKold, KforC, hist = 0.0, 0, []
+        for i in self.Kset():
+            self.initNeighborComF(i)
+            LLHKnew = self.SGDFindC(max_outer=max_outer)
+            if self.verbose:
+                print(str(i) + " LLH: " + repr(LLHKnew))                                   # :258
+            hist.append((i, LLHKnew))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                gain = 1.0 - np.float64(LLHKnew) / np.float64(LLHKold)
+            if gain < rel_gain:                                                          # :259
+                KforC = i
+                break
+            LLHKold = LLHKnew
+        return KforC, hist
 
     # ---- diagnostics ----
     def accepted(self) -> np.ndarray:

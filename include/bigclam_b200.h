@@ -175,6 +175,22 @@ int  bigclam_graph_read_edgelist(const char *path, int32_t multiplicity, bigclam
                                  char *errbuf, int64_t errbuf_len);
 void bigclam_graph_free(bigclam_graph *g);
 
+/*
+ * Callers in front of the hot path (host side, one-off integer graph work).
+ * bigclam_conductance_seeds = conductanceLocalMin() (bigclam4-7.scala:58-73): ego-net conductance of every
+ * node, candidates = the min-id neighbour of each node (tuple .min at :70), ranked by conductance ascending
+ * (ties by id).  seeds_out has room for n ids; *n_seeds_out receives the number of candidates.
+ * bigclam_init_neighbor_com_F = initNeighborComF(K) (bigclam4-7.scala:81-108): column c of F is the
+ * indicator of the neighbours of the c-th (in id order) of the first K ranked seeds; include_self adds the
+ * seed (Bigclamv2.scala:70); missing columns are random 0/1 from a seeded xorshift64* (the reference's
+ * Random is unseeded).  The result goes to bigclam_set_F.
+ */
+int bigclam_conductance_seeds(int64_t n, const int64_t *rowptr, const int32_t *col, double *conductance_out,
+                              int32_t *seeds_out, int64_t *n_seeds_out);
+int bigclam_init_neighbor_com_F(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k,
+                                const int32_t *ranked_seeds, int64_t n_ranked, int32_t include_self,
+                                uint64_t pad_seed, double *F_out);
+
 /* Library / device probe (no compute): returns the number of visible CUDA devices or <0. */
 int bigclam_device_count(void);
 const char *bigclam_version(void);

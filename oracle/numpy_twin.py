@@ -90,3 +90,40 @@ def backtracking_line_searchs(rowptr, col, F, sumF, alpha=0.05, beta=0.1, max_in
             any_upd = True
     sumF_new = sumF - (old_sum - new_sum) if any_upd else sumF.copy()   # :192
     return F_new, sumF_new, loglikelihood(rowptr, col, F_new, sumF_new), accepted
+
+
+# --------------------------------------------------------------------------------------------
+# Init of F, restated from codes/bigclam4-7.scala:58-108 (test infrastructure, like the rest of this file)
+def conductance_local_min(rowptr, col):
+    """conductanceLocalMin() (:58-73).  Returns (ranked candidate ids, conductance per node).
+    Deterministic where Spark is not: ties in the ranking break by node id."""
+    n = len(rowptr) - 1
+    sigma = int(rowptr[-1])                                  # sum of in+out degrees (:60)
+    cond = np.zeros(n)
+    for x in range(n):
+        y = [x] + list(col[rowptr[x]:rowptr[x + 1]])         # getEgoGraphNodes (:54-56)
+        ys = set(y)
+        z = [i for u_ in y for i in col[rowptr[u_]:rowptr[u_ + 1]]]
+        cut_S = sum(1 for i in z if i not in ys)
+        vol_S = len(z) - cut_S
+        vol_T = sigma - vol_S - cut_S * 2
+        cond[x] = 0.0 if vol_S == 0 else (1.0 if vol_T == 0 else cut_S / min(vol_S, vol_T))
+    best = {}
+    for x in range(n):
+        nb = col[rowptr[x]:rowptr[x + 1]]
+        key, val = (min((int(v), cond[v]) for v in nb) if len(nb) else (x, 10.0))   # tuple .min (:70)
+        best[key] = min(best.get(key, np.inf), val)          # reduceByKey
+    ranked = sorted(best, key=lambda v: (best[v], v))        # sortByKey on the conductance
+    return np.array(ranked, dtype=np.int32), cond
+
+
+def init_neighbor_com_F(rowptr, col, K, ranked, include_self=False):
+    """initNeighborComF(K) (:81-108) without the random padding (callers pass K <= len(ranked))."""
+    n = len(rowptr) - 1
+    S = sorted(int(v) for v in ranked[:K])                   # filter over collectNeighbor + zipWithIndex (:85-86)
+    F = np.zeros((n, K))
+    for c, s in enumerate(S):
+        F[col[rowptr[s]:rowptr[s + 1]], c] = 1.0
+        if include_self:
+            F[s, c] = 1.0
+    return F

@@ -259,3 +259,37 @@ def test_com_amazon_k200_steps_and_properties(oracle, graphs):
     # property (i): LLH trace entry t == standalone loglikelihood of the state after t calls
     assert abs(b.loglikelihood() - b.last_trace[-1]) <= 1e-12 * abs(b.last_trace[-1])
     b.close()
+
+
+def test_reference_style_init_then_steps(oracle, graphs):
+    """F0 from conductanceLocalMin + initNeighborComF (bigclam4-7.scala:58-108), then the hot path: the sparse
+    0/1 start exercises the x == 0 shortcut (p clamped to MAX_P_) and rows that grow from zero."""
+    from bigclam_apachespark_b200 import BigClam
+    rp, col, _ = graphs.load_npz_graph("facebook_combined")
+    K = 10
+    b = BigClam(record_accepted=True)
+    b.set_graph(rp, col)
+    F = b.initNeighborComF(K)
+    assert set(np.unique(F)) <= {0.0, 1.0} and np.array_equal(b.sumF, F.sum(axis=0))
+    sumF = oracle.colsum(F)
+    P = oracle.make_params(K)
+    for it in range(4):
+        llh = b.backtrackingLineSearchs()
+        r = oracle.step(rp, col, F, sumF, P)
+        _check_step(b, r, llh, max_flips=2, where=f"ref-init it{it}", max_idx_diff=0.05)
+        F, sumF = b.F, b.sumF
+    b.close()
+
+
+def test_k_sweep_driver(oracle):
+    """The K sweep of bigclam4-7.scala:244-266 on a small graph: stops at the first K with < 0.1 % LLH gain."""
+    from bigclam_apachespark_b200 import BigClam
+    rp, col = random_graph(400, 6, seed=3, hub=30)
+    b = BigClam(minCom=4, maxCom=16, divCom=4)
+    b.set_graph(rp, col)
+    assert b.Kset() == [4, 5, 7, 9, 12, 16]
+    KforC, hist = b.sweep_K(max_outer=30)
+    assert len(hist) >= 2 and [k for k, _ in hist] == b.Kset()[:len(hist)]
+    if KforC:
+        assert KforC == hist[-1][0] and (1 - hist[-1][1] / hist[-2][1]) < 0.001
+    b.close()
