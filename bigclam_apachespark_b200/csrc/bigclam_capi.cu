@@ -809,3 +809,25 @@ extern "C" int bigclam_set_owned_nodes(bigclam_ctx *ctx, const int32_t *nodes, i
     ctx->hi = ctx->n;
     return rebuild_order_list(ctx, rp, order);
 }
+
+// Community extraction on the current F (Bigclamv2.scala:223-230); see extract_kernel.
+extern "C" int bigclam_extract(bigclam_ctx *ctx, double delta, uint8_t *member_out /* n x k */, double *fmax_out /* n, optional */) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (member_out == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_extract: member_out is NULL");
+    CU(cudaSetDevice(ctx->device));
+    const int k = ctx->p.k;
+    uint8_t *d_member = nullptr;
+    double *d_fmax = nullptr;
+    CU(cudaMalloc(&d_member, (size_t)ctx->n * k));
+    CU(cudaMalloc(&d_fmax, sizeof(double) * (size_t)ctx->n));
+    const int wpb = 8;
+    extract_kernel<<<(unsigned)((ctx->n + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(ctx->d_F[ctx->cur], ctx->n, k, ctx->ld, delta, d_member, d_fmax);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(member_out, d_member, (size_t)ctx->n * k, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && fmax_out != nullptr) e = cudaMemcpyAsync(fmax_out, d_fmax, sizeof(double) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_member);
+    cudaFree(d_fmax);
+    if (e != cudaSuccess) return fail(ctx, BIGCLAM_ECUDA, "bigclam_extract: %s", cudaGetErrorString(e));
+    return BIGCLAM_OK;
+}

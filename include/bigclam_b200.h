@@ -176,6 +176,15 @@ int  bigclam_graph_read_edgelist(const char *path, int32_t multiplicity, bigclam
 void bigclam_graph_free(bigclam_graph *g);
 
 /*
+ * The caller behind the hot path: community extraction, Bigclamv2.scala:223-230.
+ * member_out[u*k + c] = 1 iff F_uc >= delta, or, when the row maximum is below delta, iff F_uc equals the
+ * row maximum (ties included, as coded at :227).  delta is computed by the caller:
+ * sqrt(-log(1 - e)) with e = 2*count/(N*(N-1)) (:223-224; `count` there is the number of vertices that
+ * have edges, not |E|).
+ */
+int bigclam_extract(bigclam_ctx *ctx, double delta, uint8_t *member_out, double *fmax_out);
+
+/*
  * Callers in front of the hot path (host side, one-off integer graph work).
  * bigclam_conductance_seeds = conductanceLocalMin() (bigclam4-7.scala:58-73): ego-net conductance of every
  * node, candidates = the min-id neighbour of each node (tuple .min at :70), ranked by conductance ascending

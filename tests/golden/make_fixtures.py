@@ -67,6 +67,21 @@ def golden_steps():
     print("oracle_steps.npz", os.path.getsize(os.path.join(HERE, "oracle_steps.npz")))
 
 
+def ground_truth():
+    """com-amazon.all.dedup.cmty.txt -> dense vertex indices, sorted + delta-encoded per community."""
+    (rp, col), ids = O.read_edge_list(os.path.join(REF_DATA, "com-amazon.ungraph.txt"), "dedup")
+    idmap = {int(v): i for i, v in enumerate(ids)}
+    sizes, deltas = [], []
+    for line in open(os.path.join(REF_DATA, "com-amazon.all.dedup.cmty.txt"), "rb"):
+        xs = np.sort(np.array([idmap[int(t)] for t in line.split() if int(t) in idmap], dtype=np.int64))
+        sizes.append(len(xs))
+        deltas.append(np.diff(xs, prepend=0))
+    out = os.path.join(HERE, "graphs", "com-amazon.cmty.npz")
+    np.savez_compressed(out, sizes=np.array(sizes, dtype=np.int32), deltas=np.concatenate(deltas).astype(np.int32))
+    print("com-amazon.cmty", len(sizes), os.path.getsize(out))
+
+
 if __name__ == "__main__":
     graphs()
     golden_steps()
+    ground_truth()
