@@ -44,7 +44,6 @@ struct bigclam_ctx {
     int8_t *d_changed = nullptr;   // multi-GPU: row changed in the most recent step
     int n_peers = 0;
     double *peer_F[2][7] = {{nullptr}};   // peers' F buffers (both halves), IPC-mapped
-    long long *d_dbg = nullptr;   // BIGCLAM_DEBUG_CYCLES=1: per-node timing scratch (4 x n)
     RunState *d_state = nullptr;
     double *d_trace = nullptr;
     int64_t trace_cap = 0;
@@ -127,7 +126,7 @@ static void free_ctx(bigclam_ctx *c) {
     cudaFree(c->d_F[0]); cudaFree(c->d_F[1]);
     cudaFree(c->d_sumF[0]); cudaFree(c->d_sumF[1]);
     cudaFree(c->d_partials); cudaFree(c->d_accepted); cudaFree(c->d_mask);
-    cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_dbg); cudaFree(c->d_changed);
+    cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_changed);
     for (int h = 0; h < 2; ++h) for (int r = 0; r < c->n_peers; ++r) if (c->peer_F[h][r]) cudaIpcCloseMemHandle(c->peer_F[h][r]); cudaFree(c->d_state); cudaFree(c->d_trace);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -323,10 +322,6 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     CUC(cudaMalloc(&ctx->d_done, sizeof(int32_t)));
     CUC(cudaMalloc(&ctx->d_work, 2 * sizeof(unsigned int)));      // [0] live counter, [1] its initial value
     CUC(cudaMemcpy(ctx->d_work + 1, &ctx->h_work_init, sizeof(unsigned int), cudaMemcpyHostToDevice));
-    if (std::getenv("BIGCLAM_DEBUG_CYCLES") != nullptr) {
-        CUC(cudaMalloc(&ctx->d_dbg, sizeof(long long) * (4 * (size_t)n + 16)));
-        CUC(cudaMemset(ctx->d_dbg, 0, sizeof(long long) * (4 * (size_t)n + 16)));
-    }
     CUC(cudaMalloc(&ctx->d_state, sizeof(RunState)));
     CUC(cudaMallocHost(&ctx->h_pinned, sizeof(double) * (2 * (size_t)ld + 2) + sizeof(RunState) + 64));
     CUC(cudaMemcpy(ctx->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
@@ -720,16 +715,6 @@ extern "C" int bigclam_rollback(bigclam_ctx *ctx) {
     return BIGCLAM_OK;
 }
 
-// Debug only (context created with BIGCLAM_DEBUG_CYCLES=1 in the environment and a kernel build that
-// fills StepArgs::dbg): per node [start clock, cycles, smid, m] of the most recent step kernel.
-extern "C" int bigclam_debug_cycles(bigclam_ctx *ctx, int64_t *out) {
-    if (ctx == nullptr || out == nullptr || ctx->d_dbg == nullptr) return BIGCLAM_EINVAL;
-    CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaMemcpy(out, ctx->d_dbg, sizeof(long long) * (4 * (size_t)ctx->n + 16), cudaMemcpyDeviceToHost));
-    CU(cudaMemset(ctx->d_dbg + 4 * (size_t)ctx->n, 0, sizeof(long long) * 16));
-    return BIGCLAM_OK;
-}
 
 extern "C" int bigclam_device_accepted(bigclam_ctx *ctx, void **accepted_dev) {
     if (ctx == nullptr || accepted_dev == nullptr) return BIGCLAM_EINVAL;
