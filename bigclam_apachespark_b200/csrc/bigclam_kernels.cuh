@@ -92,7 +92,7 @@ struct __align__(16) WarpLists {
     unsigned char pt[kMaxPairs];         // pair list: active index t
 };
 __host__ __device__ inline size_t block_smem_bytes(int ld, int /*maxm*/) {
-    const int stage = (ld <= 256) ? 4 : 0;      // the cp.async row staging exists only in the C2 <= 4 kernels
+    const int stage = (ld <= 256) ? 4 : (ld <= 512 ? 2 : 1);   // rows per staged batch (= R of the kernel)
     // ... | sumF[ld] | W x D[ld] | W x rows[4][ld] (cp.async staging of one batch of neighbour rows)
     return sizeof(double) * kMaxSteps + (size_t)kWarpsPerBlock * sizeof(WarpLists) +
            sizeof(double) * (size_t)ld * (1 + kWarpsPerBlock + stage * kWarpsPerBlock);
@@ -257,11 +257,11 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-template <int C2>
+template <int C2, int RB>
 __device__ __forceinline__ void stage_rows(double *buf, const double *__restrict__ F, int ld, int ld2, int lane,
                                            int ids, int first, int cnt) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < RB; ++r) {
         const int e = first + r;
         const int v = __shfl_sync(0xffffffffu, ids, e & 31);
         if (e < cnt) {
@@ -274,6 +274,37 @@ __device__ __forceinline__ void stage_rows(double *buf, const double *__restrict
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// Transposed butterfly over RB per-lane partials (RB = 4, 2 or 1): afterwards the lanes of group
+// r = lane / (32 / RB) hold the warp total of part[r].
+template <int RB>
+__device__ __forceinline__ double batch_reduce(const double (&part)[RB], int lane) {
+    double kx;
+    if constexpr (RB == 4) {
+        const bool b4 = lane & 16, b3 = lane & 8;
+        double k0 = b4 ? part[2] : part[0], k1 = b4 ? part[3] : part[1];
+        const double s0 = b4 ? part[0] : part[2], s1 = b4 ? part[1] : part[3];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        kx = b3 ? k1 : k0;
+        const double sd = b3 ? k0 : k1;
+        kx += __shfl_xor_sync(0xffffffffu, sd, 8);
+    } else if constexpr (RB == 2) {
+        const bool b4 = lane & 16;
+        kx = b4 ? part[1] : part[0];
+        const double sd = b4 ? part[0] : part[1];
+        kx += __shfl_xor_sync(0xffffffffu, sd, 16);
+        kx += __shfl_xor_sync(0xffffffffu, kx, 8);
+    } else {
+        kx = part[0];
+        kx += __shfl_xor_sync(0xffffffffu, kx, 16);
+        kx += __shfl_xor_sync(0xffffffffu, kx, 8);
+    }
+    kx += __shfl_xor_sync(0xffffffffu, kx, 4);
+    kx += __shfl_xor_sync(0xffffffffu, kx, 2);
+    kx += __shfl_xor_sync(0xffffffffu, kx, 1);
+    return kx;
 }
 
 // Sum R per-lane partials across the warp; the total of partial r is returned to lane (eb + r).
@@ -807,7 +838,7 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
     WarpLists *wl = reinterpret_cast<WarpLists *>(smem_raw + sizeof(double) * kMaxSteps) + wib;
     double *s_sumF = reinterpret_cast<double *>(smem_raw + sizeof(double) * kMaxSteps + kWarpsPerBlock * sizeof(WarpLists));
     double *s_D = s_sumF + (size_t)ld * (1 + wib);
-    double *s_rows = s_sumF + (size_t)ld * (1 + kWarpsPerBlock) + (size_t)wib * 4 * ld;
+    double *s_rows = s_sumF + (size_t)ld * (1 + kWarpsPerBlock) + (size_t)wib * R * ld;
     double2 *s_afg = wl->afg;
     double *s_pval = wl->pval;
     unsigned short *s_aidx = wl->aidx;
@@ -861,7 +892,7 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
         const int q = lane + 32 * c;
         fu[c] = (pos < order_n && q < ld2) ? ldg2(F + (size_t)cur.u * ld + 2 * q) : make_double2(0.0, 0.0);
     }
-    if constexpr (R == 4) stage_rows<C2>(s_rows, F, ld, ld2, lane, myv, 0, min(32, cur.deg));
+    stage_rows<C2, R>(s_rows, F, ld, ld2, lane, myv, 0, min(32, cur.deg));
 
     while (pos < order_n) {
         const int64_t u = cur.u;
@@ -900,18 +931,19 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
             // neighbour ids of the chunk after this one (hubs): loaded now, prefetched after the first batch
             const int cnt2 = min(32, max(0, deg - cb - 32));
             const int myv2 = (lane < cnt2) ? a.col[e0 + cb + 32 + lane] : 0;
-            if constexpr (R == 4) {
-                // batches of 4 rows kept in registers: dots -> exp/log (each group of 8 lanes evaluates one
-                // of the 4 edges) -> axpy from the same registers: every neighbour row is loaded once here
-                const int rsel = (lane >> 3) & 3;
-                for (int eb = 0; eb < cnt; eb += 4) {
+            {
+                // batches of R rows kept in registers: dots -> exp/log (each group of 32/R lanes evaluates one
+                // of the R edges) -> axpy from the same registers: every neighbour row is loaded once here
+                constexpr int GL = 32 / R;                    // lanes per edge group
+                const int rsel = lane / GL;
+                for (int eb = 0; eb < cnt; eb += R) {
                     // this batch was staged in shared memory one batch (or one node) ago
                     cp_async_wait_all();
                     __syncwarp();
-                    double2 x[4][C2];
-                    double part[4];
+                    double2 x[R][C2];
+                    double part[R];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
+                    for (int r = 0; r < R; ++r) {
                         const bool ok = eb + r < cnt;
                         double p = 0.0;
 #pragma unroll
@@ -927,31 +959,20 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
                     __syncwarp();
                     // stage the following batch while this one is processed: same 32-group, next group of
                     // this node, or the first batch of the next node
-                    if (eb + 4 < cnt) stage_rows<C2>(s_rows, F, ld, ld2, lane, myv, eb + 4, cnt);
-                    else if (cnt2 > 0) stage_rows<C2>(s_rows, F, ld, ld2, lane, myv2, 0, cnt2);
-                    else stage_rows<C2>(s_rows, F, ld, ld2, lane, nmyv, 0, ncnt);
-                    // transposed butterfly: afterwards the lanes with ((lane >> 3) & 3) == r hold the dot of edge r
-                    const bool b4 = lane & 16, b3 = lane & 8;
-                    double k0 = b4 ? part[2] : part[0], k1 = b4 ? part[3] : part[1];
-                    const double s0 = b4 ? part[0] : part[2], s1 = b4 ? part[1] : part[3];
-                    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-                    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                    double kx = b3 ? k1 : k0;
-                    const double sd = b3 ? k0 : k1;
-                    kx += __shfl_xor_sync(0xffffffffu, sd, 8);
-                    kx += __shfl_xor_sync(0xffffffffu, kx, 4);
-                    kx += __shfl_xor_sync(0xffffffffu, kx, 2);
-                    kx += __shfl_xor_sync(0xffffffffu, kx, 1);
+                    if (eb + R < cnt) stage_rows<C2, R>(s_rows, F, ld, ld2, lane, myv, eb + R, cnt);
+                    else if (cnt2 > 0) stage_rows<C2, R>(s_rows, F, ld, ld2, lane, myv2, 0, cnt2);
+                    else stage_rows<C2, R>(s_rows, F, ld, ld2, lane, nmyv, 0, ncnt);
+                    const double kx = batch_reduce<R>(part, lane);
                     double w;
                     double t = edge_term<true>(kx, ec, w);
                     t = (eb + rsel < cnt) ? t : 0.0;
-                    t += __shfl_xor_sync(0xffffffffu, t, 8);
-                    t += __shfl_xor_sync(0xffffffffu, t, 16);
+                    if constexpr (R >= 4) t += __shfl_xor_sync(0xffffffffu, t, 8);
+                    if constexpr (R >= 2) t += __shfl_xor_sync(0xffffffffu, t, 16);
                     S1 += t;
                     if (a.do_linesearch) {
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const double we = __shfl_sync(0xffffffffu, w, 8 * r);
+                        for (int r = 0; r < R; ++r) {
+                            const double we = __shfl_sync(0xffffffffu, w, GL * r);
 #pragma unroll
                             for (int c = 0; c < C2; ++c) {
                                 g[c].x = fma(we, x[r][c].x, g[c].x);
@@ -960,34 +981,10 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
                         }
                     }
                 }
-            } else {
-                const double myx = chunk_dots<C2, R>(fu, F, ld, ld2, lane, myv, cnt);
-                if (cb == 0) prefetch_rows(F, ld, lane, nmyv, ncnt);
-                if (cnt2 > 0) prefetch_rows(F, ld, lane, myv2, cnt2);
-                double w;
-                const double t = edge_term<true>(myx, ec, w);
-                S1 += warp_sum(lane < cnt ? t : 0.0);
-                if (a.do_linesearch) {
-#pragma unroll 2
-                    for (int e = 0; e < cnt; ++e) {
-                        const int v = __shfl_sync(0xffffffffu, myv, e);
-                        const double we = __shfl_sync(0xffffffffu, w, e);
-                        const double *fv = F + (size_t)v * ld;
-#pragma unroll
-                        for (int c = 0; c < C2; ++c) {
-                            const int q = lane + 32 * c;
-                            if (q < ld2) {
-                                const double2 xx = ldg2(fv + 2 * q);
-                                g[c].x = fma(we, xx.x, g[c].x);
-                                g[c].y = fma(we, xx.y, g[c].y);
-                            }
-                        }
-                    }
-                }
             }
             myv = myv2;
         }
-        if constexpr (R == 4) { if (deg == 0) stage_rows<C2>(s_rows, F, ld, ld2, lane, nmyv, 0, ncnt); }
+        if (deg == 0) stage_rows<C2, R>(s_rows, F, ld, ld2, lane, nmyv, 0, ncnt);
         const double llh_u = (S1 - fusf) + fufu;
         llh_acc += llh_u;
 
