@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdint>
 #include <cstdlib>
 #include <numeric>
 #include <string>
@@ -32,6 +33,10 @@ struct bigclam_ctx {
     int32_t maxm = 0;
     int64_t order_n = 0;
     int32_t n_hubs = 0;
+    int32_t n_hub_items = 0, n_mega = 0;
+    HubItem *d_hub_items = nullptr;
+    double *d_hub_scratch = nullptr;
+    unsigned int *d_hub_counters = nullptr;
     int64_t lo = 0, hi = 0;
     double *d_F[2] = {nullptr, nullptr};
     double *d_sumF[2] = {nullptr, nullptr};
@@ -126,7 +131,7 @@ static void free_ctx(bigclam_ctx *c) {
     cudaFree(c->d_F[0]); cudaFree(c->d_F[1]);
     cudaFree(c->d_sumF[0]); cudaFree(c->d_sumF[1]);
     cudaFree(c->d_partials); cudaFree(c->d_accepted); cudaFree(c->d_mask);
-    cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_changed);
+    cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_hub_items); cudaFree(c->d_hub_scratch); cudaFree(c->d_hub_counters); cudaFree(c->d_changed);
     for (int h = 0; h < 2; ++h) for (int r = 0; r < c->n_peers; ++r) if (c->peer_F[h][r]) cudaIpcCloseMemHandle(c->peer_F[h][r]); cudaFree(c->d_state); cudaFree(c->d_trace);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -202,12 +207,57 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
     int64_t own_nnz = 0;
     for (int64_t i = 0; i < cnt; ++i) own_nnz += meta[(size_t)i].deg;
     const int64_t per_warp = own_nnz / std::max<int64_t>(1, (int64_t)ctx->grid * kWarpsPerBlock);
-    // whole graph on one GPU: the launch is long and the hubs-first order hides all but extreme hubs
-    // (and a hub-free launch uses the leaner kernel variant); a partition's launch is short: share earlier
-    const bool partitioned = cnt < ctx->n;
-    const int64_t hub_deg = std::max<int64_t>(kHubDegree, partitioned ? per_warp / 5 : (3 * per_warp) / 4);
+    // When even the largest node's serial chain fits well inside one warp's share of the launch, the
+    // hubs-first order hides it and the launch uses the leaner hub-free kernel variant; otherwise nodes
+    // from a fifth of that share upwards (at most 512 edges) are shared by blocks.
+    const int64_t max_deg = (cnt > 0) ? meta[0].deg : 0;
+    const int64_t hub_deg = (4 * max_deg <= 3 * per_warp) ? INT64_MAX
+                                                          : std::min<int64_t>(512, std::max<int64_t>(kHubDegree, per_warp / 5));
     if (ctx->c2 <= 4) while (nh < cnt && meta[(size_t)nh].deg >= hub_deg) ++nh;
     ctx->n_hubs = nh;
+    // work items of the hub phase: hubs above kHubSlice edges are split into slices handled by different
+    // blocks (phases 1-3), the others are done by one block (phase 0); see hub_phase
+    {
+        std::vector<HubItem> i1, i0, i2, i3;
+        int32_t n_mega = 0;
+        for (int32_t i = 0; i < nh; ++i) {
+            const int32_t deg = meta[(size_t)i].deg;
+            const int32_t nsl = (deg + kHubSlice - 1) / kHubSlice;
+            HubItem it{};
+            it.hub = i;
+            if (nsl > 1 && ctx->nsteps <= 16) {
+                it.mslot = n_mega++;
+                it.nslices = nsl;
+                for (int32_t sl = 0; sl < nsl; ++sl) {
+                    it.slice = sl;
+                    it.phase = 1; i1.push_back(it);
+                    it.phase = 2; i2.push_back(it);
+                }
+                it.slice = 0;
+                it.phase = 3; i3.push_back(it);
+            } else {
+                it.phase = 0; it.nslices = 1; it.mslot = 0;
+                i0.push_back(it);
+            }
+        }
+        std::vector<HubItem> items;
+        items.insert(items.end(), i1.begin(), i1.end());
+        items.insert(items.end(), i0.begin(), i0.end());
+        items.insert(items.end(), i2.begin(), i2.end());
+        items.insert(items.end(), i3.begin(), i3.end());
+        cudaFree(ctx->d_hub_items); ctx->d_hub_items = nullptr;
+        cudaFree(ctx->d_hub_scratch); ctx->d_hub_scratch = nullptr;
+        cudaFree(ctx->d_hub_counters); ctx->d_hub_counters = nullptr;
+        ctx->n_hub_items = (int32_t)items.size();
+        ctx->n_mega = n_mega;
+        if (!items.empty()) {
+            CU(cudaMalloc(&ctx->d_hub_items, sizeof(HubItem) * items.size()));
+            CU(cudaMemcpy(ctx->d_hub_items, items.data(), sizeof(HubItem) * items.size(), cudaMemcpyHostToDevice));
+        }
+        const size_t slots = (size_t)std::max<int32_t>(1, n_mega);
+        CU(cudaMalloc(&ctx->d_hub_scratch, sizeof(double) * slots * ((size_t)ctx->ld + 32)));
+        CU(cudaMalloc(&ctx->d_hub_counters, sizeof(unsigned int) * 2 * slots));
+    }
     const unsigned int init = (unsigned int)nh + 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
     ctx->h_work_init = init;
     if (ctx->d_work != nullptr) CU(cudaMemcpy(ctx->d_work + 1, &init, sizeof(unsigned int), cudaMemcpyHostToDevice));
@@ -462,6 +512,10 @@ static void fill_args(bigclam_ctx *ctx, StepArgs &a, bool linesearch, const uint
     a.maxm = ctx->maxm;
     a.order_n = ctx->order_n;
     a.n_hubs = ctx->n_hubs;
+    a.n_hub_items = ctx->n_hub_items;
+    a.hub_items = ctx->d_hub_items;
+    a.hub_scratch = ctx->d_hub_scratch;
+    a.hub_counters = ctx->d_hub_counters;
     a.node_mask = d_mask;
     a.partials = ctx->d_partials;
     a.accepted = (linesearch && (p.flags & BIGCLAM_F_RECORD_ACCEPTED)) ? ctx->d_accepted : nullptr;
@@ -478,6 +532,10 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
             ctx->ev_pool.push_back(e);
         }
         CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
+    }
+    if (ctx->n_mega > 0) {     // mega-hub scratch and slice counters start every launch at zero
+        CU(cudaMemsetAsync(ctx->d_hub_scratch, 0, sizeof(double) * (size_t)ctx->n_mega * ((size_t)ctx->ld + 32), ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_hub_counters, 0, sizeof(unsigned int) * 2 * (size_t)ctx->n_mega, ctx->stream));
     }
     // positions 0 .. 3*#warps-1 are pre-assigned statically, the rest is handed out dynamically
     CU(cudaMemcpyAsync(ctx->d_work, ctx->d_work + 1, sizeof(unsigned int), cudaMemcpyDeviceToDevice, ctx->stream));

@@ -49,6 +49,7 @@ struct NodeMeta {   // one record per visited node, in processing order
     int64_t e0;
 };
 
+struct HubItem;
 struct StepArgs {
     int64_t n;
     const int64_t *rowptr;
@@ -65,7 +66,11 @@ struct StepArgs {
     double x_lo, x_hi, t_lo, t_hi, w_lo, w_hi;
     const NodeMeta *meta;     // processing order (degree descending) over the owned nodes
     int64_t order_n;
-    int32_t n_hubs;           // the first n_hubs positions (degree >= kHubDegree) are processed one per BLOCK
+    int32_t n_hubs;           // the first n_hubs positions are hub nodes (skipped by the warp-per-node loop)
+    int32_t n_hub_items;      // block-cooperative work items over those hubs (see hub_phase)
+    const struct HubItem *hub_items;
+    double *hub_scratch;
+    unsigned int *hub_counters;
     unsigned int *work_counter;   // next position to hand out (host sets it to 4 * #warps)
     const uint8_t *node_mask; // optional uset
     double *partials;         // [D(ld) = sum(old - new) | unused(ld) | llh | n_updated]
@@ -552,11 +557,31 @@ __device__ __noinline__ int dense_linesearch(const double *__restrict__ F, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Hub phase: one high-degree node per BLOCK.  A node's edges are independent in PRE (sum over edges)
-// and in the line search (sum over edges per trial), so the block's warps take contiguous slices of
-// the neighbour list, exchange the partial gradient / partial per-trial sums through shared memory, and
-// every warp redundantly derives the (identical) gradient, active set and decision; warp 0 writes the
-// row.  This bounds the serial chain of a degree-d node by d / kWarpsPerBlock edges.
+// Hub phase: high-degree nodes are shared by the warps of a BLOCK, very high-degree ones by several blocks.
+// A node's edges are independent in PRE (sum over edges) and in the line search (sum over edges per
+// trial), so the warps take contiguous slices of the neighbour list, exchange the partial gradient / the
+// partial per-trial sums through shared memory, and every warp redundantly derives the (identical)
+// gradient, active set and decision; warp 0 writes the row.
+//
+// Work items (host-built, processed by block b in the order b, b + grid, ...):
+//   phase 0  a hub of at most kHubSlice edges, done completely by one block;
+//   phase 1  PRE of one kHubSlice-edge slice of a mega hub -> partial gradient / S1 added to global scratch;
+//   phase 2  line search of one slice (waits until all phase-1 slices of the hub are in) -> partial
+//            per-trial sums added to global scratch;
+//   phase 3  decision + row write of a mega hub (waits for its phase-2 slices).
+// All phase-1 items precede all phase-2 items precede all phase-3 items and the grid is persistent (every
+// block resident), so a waiting block only ever waits for items that are being processed: no deadlock.
+constexpr int kHubSlice = 384;
+
+struct HubItem {
+    int32_t hub;      // position in meta[]
+    int32_t slice;    // slice index (phases 1, 2)
+    int32_t phase;
+    int32_t mslot;    // scratch / counter slot of the mega hub (0 for phase-0 hubs)
+    int32_t nslices;
+    int32_t pad[3];
+};
+
 struct HubArgs {
     const NodeMeta *meta;
     const int32_t *col;
@@ -566,9 +591,20 @@ struct HubArgs {
     int8_t *accepted;
     int8_t *changed;
     double *peer_out[7];
-    int32_t n_peers, n_hubs, ld, nsteps, do_linesearch;
+    const HubItem *items;
+    double *scratch;            // per mega hub: G[ld] | S1 | ST[16] | pad  (stride ld + 32 doubles)
+    unsigned int *counters;     // per mega hub: [phase-1 slices done, phase-2 slices done]
+    int32_t n_peers, n_items, ld, nsteps, do_linesearch;
     double alpha, min_f, max_f;
 };
+
+__device__ __forceinline__ void hub_wait(const unsigned int *counter, unsigned int target) {
+    if (threadIdx.x == 0) {
+        while (*reinterpret_cast<const volatile unsigned int *>(counter) < target) __nanosleep(200);
+        __threadfence();
+    }
+    __syncthreads();
+}
 
 template <int C2>
 __device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, const double *s_sumF, const double *s_steps,
@@ -583,14 +619,22 @@ __device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, con
     double *hub_st = hub_small + kWarpsPerBlock;                    // [kWarpsPerBlock][32]
     int *hub_j = reinterpret_cast<int *>(hub_small + kWarpsPerBlock * 33);
     const double max_f = ha.max_f;
+    const int j16 = lane & 15, h = lane >> 4;
 
-    for (int hb = blockIdx.x; hb < ha.n_hubs; hb += gridDim.x) {
-        const NodeMeta nm = ha.meta[hb];
+    for (int it = blockIdx.x; it < ha.n_items; it += gridDim.x) {
+        const HubItem item = ha.items[it];
+        const int phase = item.phase;
+        const NodeMeta nm = ha.meta[item.hub];
         const int64_t u = nm.u, e0 = nm.e0;
         const int deg = nm.deg;
         const int32_t *colp = ha.col + e0;
-        const int per = (((deg + kWarpsPerBlock - 1) / kWarpsPerBlock) + 3) & ~3;
-        const int ebeg = min(deg, wib * per), eend = min(deg, ebeg + per);
+        double *scr = ha.scratch + (size_t)item.mslot * (ld + 32);
+        unsigned int *cnt = ha.counters + 2 * (size_t)item.mslot;
+        // edge range of this item, then of this warp inside it
+        const int blk_beg = (phase == 1 || phase == 2) ? item.slice * kHubSlice : 0;
+        const int blk_end = (phase == 1 || phase == 2) ? min(deg, blk_beg + kHubSlice) : deg;
+        const int per = ((((blk_end - blk_beg) + kWarpsPerBlock - 1) / kWarpsPerBlock) + 3) & ~3;
+        const int ebeg = min(blk_end, blk_beg + wib * per), eend = min(blk_end, ebeg + per);
 
         double2 fu[C2];
         double fusf = 0.0, fufu = 0.0;
@@ -607,88 +651,109 @@ __device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, con
         fusf = warp_sum(fusf);
         fufu = warp_sum(fufu);
 
-        // ---- PRE over this warp's slice (batches of 4 rows straight from global memory) ----
         double2 g[C2];
 #pragma unroll
         for (int c = 0; c < C2; ++c) g[c] = make_double2(0.0, 0.0);
         double S1 = 0.0;
-        const int rsel = (lane >> 3) & 3;
-        for (int gb = ebeg; gb < eend; gb += 32) {
-            const int cnt = min(32, eend - gb);
-            const int myv = (lane < cnt) ? colp[gb + lane] : 0;
-            for (int eb = 0; eb < cnt; eb += 4) {
-                double2 x[4][C2];
-                double part[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int v = __shfl_sync(0xffffffffu, myv, (eb + r) & 31);
-                    const double *fv = F + (size_t)v * ld;
-                    const bool ok = eb + r < cnt;
-                    double p = 0.0;
-#pragma unroll
-                    for (int c = 0; c < C2; ++c) {
-                        const int q = lane + 32 * c;
-                        x[r][c] = (ok && q < ld2) ? ldg2(fv + 2 * q) : make_double2(0.0, 0.0);
-                        p = fma(fu[c].x, x[r][c].x, p);
-                        p = fma(fu[c].y, x[r][c].y, p);
-                    }
-                    part[r] = p;
-                }
-                const bool b4 = lane & 16, b3 = lane & 8;
-                double k0 = b4 ? part[2] : part[0], k1 = b4 ? part[3] : part[1];
-                const double s0 = b4 ? part[0] : part[2], s1 = b4 ? part[1] : part[3];
-                k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-                k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                double kx = b3 ? k1 : k0;
-                const double sd = b3 ? k0 : k1;
-                kx += __shfl_xor_sync(0xffffffffu, sd, 8);
-                kx += __shfl_xor_sync(0xffffffffu, kx, 4);
-                kx += __shfl_xor_sync(0xffffffffu, kx, 2);
-                kx += __shfl_xor_sync(0xffffffffu, kx, 1);
-                double w;
-                double t = edge_term<true>(kx, ec, w);
-                t = (eb + rsel < cnt) ? t : 0.0;
-                t += __shfl_xor_sync(0xffffffffu, t, 8);
-                t += __shfl_xor_sync(0xffffffffu, t, 16);
-                S1 += t;
-                if (ha.do_linesearch) {
+
+        if (phase <= 1) {
+            // ---- PRE over this warp's slice (batches of 4 rows straight from global memory) ----
+            const int rsel = (lane >> 3) & 3;
+            for (int gb = ebeg; gb < eend; gb += 32) {
+                const int cnt32 = min(32, eend - gb);
+                const int myv = (lane < cnt32) ? colp[gb + lane] : 0;
+                for (int eb = 0; eb < cnt32; eb += 4) {
+                    double2 x[4][C2];
+                    double part[4];
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const double we = __shfl_sync(0xffffffffu, w, 8 * r);
+                        const int v = __shfl_sync(0xffffffffu, myv, (eb + r) & 31);
+                        const double *fv = F + (size_t)v * ld;
+                        const bool ok = eb + r < cnt32;
+                        double p = 0.0;
 #pragma unroll
                         for (int c = 0; c < C2; ++c) {
-                            g[c].x = fma(we, x[r][c].x, g[c].x);
-                            g[c].y = fma(we, x[r][c].y, g[c].y);
+                            const int q = lane + 32 * c;
+                            x[r][c] = (ok && q < ld2) ? ldg2(fv + 2 * q) : make_double2(0.0, 0.0);
+                            p = fma(fu[c].x, x[r][c].x, p);
+                            p = fma(fu[c].y, x[r][c].y, p);
+                        }
+                        part[r] = p;
+                    }
+                    const double kx = batch_reduce<4>(part, lane);
+                    double w;
+                    double t = edge_term<true>(kx, ec, w);
+                    t = (eb + rsel < cnt32) ? t : 0.0;
+                    t += __shfl_xor_sync(0xffffffffu, t, 8);
+                    t += __shfl_xor_sync(0xffffffffu, t, 16);
+                    S1 += t;
+                    if (ha.do_linesearch) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const double we = __shfl_sync(0xffffffffu, w, 8 * r);
+#pragma unroll
+                            for (int c = 0; c < C2; ++c) {
+                                g[c].x = fma(we, x[r][c].x, g[c].x);
+                                g[c].y = fma(we, x[r][c].y, g[c].y);
+                            }
                         }
                     }
                 }
             }
-        }
-        // ---- combine the partial gradient and S1 over the block ----
-#pragma unroll
-        for (int c = 0; c < C2; ++c) {
-            const int q = lane + 32 * c;
-            if (q < ld2) *reinterpret_cast<double2 *>(my_part + 2 * q) = g[c];
-        }
-        if (lane == 0) hub_S1[wib] = S1;
-        __syncthreads();
-        S1 = 0.0;
-#pragma unroll
-        for (int c = 0; c < C2; ++c) g[c] = make_double2(0.0, 0.0);
-        for (int w = 0; w < kWarpsPerBlock; ++w) {
-            S1 += hub_S1[w];
-            const double *pw = s_rows_all + (size_t)w * 4 * ld;
+            // ---- combine the partial gradient and S1 over the block ----
 #pragma unroll
             for (int c = 0; c < C2; ++c) {
                 const int q = lane + 32 * c;
-                if (q < ld2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(pw + 2 * q);
-                    g[c].x += v.x;
-                    g[c].y += v.y;
+                if (q < ld2) *reinterpret_cast<double2 *>(my_part + 2 * q) = g[c];
+            }
+            if (lane == 0) hub_S1[wib] = S1;
+            __syncthreads();
+            S1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < C2; ++c) g[c] = make_double2(0.0, 0.0);
+            for (int w = 0; w < kWarpsPerBlock; ++w) {
+                S1 += hub_S1[w];
+                const double *pw = s_rows_all + (size_t)w * 4 * ld;
+#pragma unroll
+                for (int c = 0; c < C2; ++c) {
+                    const int q = lane + 32 * c;
+                    if (q < ld2) {
+                        const double2 v = *reinterpret_cast<const double2 *>(pw + 2 * q);
+                        g[c].x += v.x;
+                        g[c].y += v.y;
+                    }
                 }
             }
+            __syncthreads();
+            if (phase == 1) {
+                // publish this slice's partial sums, then signal
+                if (wib == 0) {
+#pragma unroll
+                    for (int c = 0; c < C2; ++c) {
+                        const int q = lane + 32 * c;
+                        if (q < ld2) {
+                            atomicAdd(scr + 2 * q, g[c].x);
+                            atomicAdd(scr + 2 * q + 1, g[c].y);
+                        }
+                    }
+                    if (lane == 0) atomicAdd(scr + ld, S1);
+                    __threadfence();
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) atomicAdd(cnt, 1u);
+                continue;
+            }
+        } else {
+            // phases 2 and 3: the whole node's gradient sum and S1 come from the scratch
+            hub_wait(cnt + (phase == 2 ? 0 : 1), (unsigned int)item.nslices);
+#pragma unroll
+            for (int c = 0; c < C2; ++c) {
+                const int q = lane + 32 * c;
+                if (q < ld2) g[c] = __ldcg(reinterpret_cast<const double2 *>(scr + 2 * q));
+            }
+            S1 = __ldcg(scr + ld);
         }
-        __syncthreads();
+
         const double llh_u = (S1 - fusf) + fufu;
         const bool in_uset = (ha.node_mask == nullptr) || (ha.node_mask[u] != 0);
         int jstar = -1;
@@ -733,7 +798,6 @@ __device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, con
                 __syncwarp();
             }
             if (sparse_ok && m <= kMaxActiveCap) {
-                const int j16 = lane & 15, h = lane >> 4;
                 const int my_idx0 = (lane < m) ? (int)lists.aidx[lane] : 0;
                 bool hi_lane = false;
                 for (int t = lane; t < m; t += 32) {
@@ -741,17 +805,26 @@ __device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, con
                     hi_lane |= (fg.x + fg.y > max_f);
                 }
                 const bool need_hi = __any_sync(0xffffffffu, hi_lane);
+                // mega hubs are restricted (host side) to nsteps <= 16, i.e. a single trial group
                 for (int tg = 0; tg < ha.nsteps && jstar < 0; tg += 16) {
                     const int j = tg + j16;
                     const bool jok = j < ha.nsteps;
                     const double s = s_steps[jok ? j : 0];
-                    double st = ls_edge_range(F, colp, ebeg, eend, ld, m, my_idx0, lt_mask, lane, h, s, need_hi, max_f, ec, lists);
-                    st += __shfl_xor_sync(0xffffffffu, st, 16);
-                    hub_st[wib * 32 + lane] = st;
-                    __syncthreads();
                     double sumterms = 0.0;
-                    for (int w = 0; w < kWarpsPerBlock; ++w) sumterms += hub_st[w * 32 + lane];
-                    __syncthreads();
+                    if (phase != 3) {
+                        double st = ls_edge_range(F, colp, ebeg, eend, ld, m, my_idx0, lt_mask, lane, h, s, need_hi, max_f, ec, lists);
+                        st += __shfl_xor_sync(0xffffffffu, st, 16);
+                        hub_st[wib * 32 + lane] = st;
+                        __syncthreads();
+                        for (int w = 0; w < kWarpsPerBlock; ++w) sumterms += hub_st[w * 32 + lane];
+                        __syncthreads();
+                        if (phase == 2) {
+                            if (wib == 0 && lane < 16) atomicAdd(scr + ld + 1 + lane, sumterms);
+                            break;
+                        }
+                    } else {
+                        sumterms = __ldcg(scr + ld + 1 + j16);
+                    }
                     double oa = 0.0, ob = 0.0;
                     for (int t = h; t < m; t += 2) {
                         const double2 fg = lists.afg[t];
@@ -767,7 +840,7 @@ __device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, con
                     const unsigned pass = __ballot_sync(0xffffffffu, jok && (result >= rhs)) & 0xffffu;
                     if (pass) jstar = tg + __ffs(pass) - 1;
                 }
-            } else {
+            } else if (phase != 2) {
                 // MIN_F_ != 0 or more active components than the lists hold: warp 0 runs the dense search
                 double *orow = ha.F_out + (size_t)u * ld;
                 if (wib == 0) {
@@ -786,7 +859,14 @@ __device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, con
                 __syncthreads();
             }
         }
-        // ---- SWAP by warp 0 ----
+        if (phase == 2) {
+            // this slice's per-trial sums are in the scratch (or there is nothing to add): signal
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(cnt + 1, 1u);
+            continue;
+        }
+        // ---- SWAP by warp 0 (phases 0 and 3) ----
         if (wib == 0) {
             double *orow = ha.F_out + (size_t)u * ld;
             const bool push = (ha.n_peers > 0) && ha.do_linesearch && ((jstar >= 0) || (ha.changed[u] != 0));
@@ -822,7 +902,6 @@ __device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, con
         __syncthreads();
     }
 }
-
 
 // kHub: the launch has block-cooperative hub nodes; kPush: peers' replicas are written (multi-GPU).
 // Both are compile-time so that the single-GPU, hub-free launch carries none of that code.
@@ -869,7 +948,8 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
             ha.meta = a.meta; ha.col = a.col; ha.F_in = a.F_in; ha.F_out = a.F_out; ha.node_mask = a.node_mask;
             ha.accepted = a.accepted; ha.changed = a.changed;
             for (int r = 0; r < 7; ++r) ha.peer_out[r] = a.peer_out[r];
-            ha.n_peers = a.n_peers; ha.n_hubs = a.n_hubs; ha.ld = ld; ha.nsteps = nsteps; ha.do_linesearch = a.do_linesearch;
+            ha.items = a.hub_items; ha.scratch = a.hub_scratch; ha.counters = a.hub_counters;
+            ha.n_peers = a.n_peers; ha.n_items = a.n_hub_items; ha.ld = ld; ha.nsteps = nsteps; ha.do_linesearch = a.do_linesearch;
             ha.alpha = a.alpha; ha.min_f = a.min_f; ha.max_f = max_f;
             double hub_llh = 0.0, hub_nupd = 0.0;
             hub_phase<C2>(ha, ec, s_sumF, s_steps, s_D, s_sumF + (size_t)ld * (1 + kWarpsPerBlock), lists, hub_small, &hub_llh, &hub_nupd);

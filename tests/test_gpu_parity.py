@@ -293,3 +293,47 @@ def test_k_sweep_driver(oracle):
     if KforC:
         assert KforC == hist[-1][0] and (1 - hist[-1][1] / hist[-2][1]) < 0.001
     b.close()
+
+
+def test_rmat_skewed_graph(oracle, graphs):
+    """R-MAT (a,b,c,d) = (.57,.19,.19,.05): a degree-1390 hub (block-cooperative hub phase, > 32 active
+    components) and ~20 % isolated nodes."""
+    rp, col = graphs.rmat_graph(5000, 50000, seed=42)
+    n, k = len(rp) - 1, 24
+    assert np.diff(rp).max() > 1000 and (np.diff(rp) == 0).sum() > 500
+    F0 = graphs.synthetic_F0(n, k, seed=3, density=0.15)
+    sumF = oracle.colsum(F0)
+    P = oracle.make_params(k)
+    b = _solver(rp, col, k, F0, sumF)
+    F, s = F0, sumF
+    for it in range(3):
+        llh = b.backtrackingLineSearchs()
+        r = oracle.step(rp, col, F, s, P)
+        _check_step(b, r, llh, max_flips=2, where=f"rmat it{it}", max_idx_diff=0.05)
+        F, s = b.F, b.sumF
+    b.close()
+
+
+def test_mega_hub_split_over_blocks(oracle, graphs):
+    """A hub above kHubSlice (384) edges is split into slices processed by different blocks (phases 1-3 of
+    the hub phase, partial sums through global scratch); a star-like graph makes it dominate."""
+    rp, col = random_graph(3000, 4, seed=8, hub=2500)           # node 0 has ~2500 neighbours
+    assert np.diff(rp).max() > 2000
+    n, k = len(rp) - 1, 16
+    rng = np.random.default_rng(8)
+    F0 = rng.random((n, k)) * (rng.random((n, k)) < 0.3)
+    sumF = oracle.colsum(F0)
+    P = oracle.make_params(k)
+    b = _solver(rp, col, k, F0, sumF)
+    F, s = F0, sumF
+    for it in range(4):
+        llh = b.backtrackingLineSearchs()
+        r = oracle.step(rp, col, F, s, P)
+        _check_step(b, r, llh, max_flips=2, where=f"mega it{it}", max_idx_diff=0.05)
+        F, s = b.F, b.sumF
+    # the device-side loop uses the same kernels
+    b.set_F(F0, sumF=sumF)
+    b._run(4, 1e-4, 12)
+    Fo, so, llho, callso, tro = oracle.run(rp, col, F0, sumF, P, variant=4, max_outer=12)
+    assert b.last_calls == callso and np.allclose(b.last_trace, tro, rtol=1e-8)
+    b.close()

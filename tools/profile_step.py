@@ -9,7 +9,11 @@ K = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 name = sys.argv[4] if len(sys.argv) > 4 else "com-amazon"
-rp, col, _ = G.load_npz_graph(name)
+if name.startswith("rmat:"):          # rmat:<nodes>:<edges>
+    _, nn, mm = name.split(":")
+    rp, col = G.rmat_graph(int(nn), int(mm), seed=42)
+else:
+    rp, col, _ = G.load_npz_graph(name)
 n = len(rp) - 1
 b = BigClam(device=0, time_kernels=True)
 b.set_graph(rp, col).set_K(K).set_F(G.synthetic_F0(n, K, seed=1234, density=0.05))
