@@ -437,6 +437,8 @@ extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
                          (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
     int rc = colsum_current(ctx);
     if (rc != BIGCLAM_OK) return rc;
+    // with peer replicas every row counts as changed again: the next step publishes all owned rows
+    if (ctx->d_changed != nullptr) CU(cudaMemsetAsync(ctx->d_changed, 1, (size_t)ctx->n, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return BIGCLAM_OK;
 }

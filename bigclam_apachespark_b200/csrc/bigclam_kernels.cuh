@@ -13,9 +13,14 @@
 // double2 chunks q = l + 32c (components 2q, 2q+1), so a row load is C2 coalesced LDG.128.
 //
 // Memory pipeline: nodes are visited hubs-first through a packed 16-byte NodeMeta record handed
-// out by an atomic work counter two nodes ahead; while node i is processed the warp already
-// holds node i+1's neighbour ids and own row and has issued prefetch.global.L2 for node i+1's
-// neighbour rows, so the HBM latency of the gather is off the dependent chain.
+// out by an atomic work counter two nodes ahead.  Neighbour rows arrive in batches of R (4 for K <= 256)
+// through a per-warp shared-memory staging buffer filled by cp.async (LDGSTS): while batch k is processed
+// from registers, batch k+1 — or, during the line search, the next node's first batch — is in flight, so
+// the HBM latency of the gather is off the dependent chain.  (L2 prefetches, per line or TMA bulk, were
+// measured useless-to-harmful here and are not used.)
+//
+// Hubs: nodes whose serial chain would dominate a launch are processed by whole blocks, very large ones
+// by several blocks in three ordered phases (hub_phase below).
 //
 // Line search ("pair list"): a component can only matter in nf_j . fv if nf_j can be non-zero,
 // i.e. fu_i > 0 or grad_i > 0 (MIN_F_ = 0).  Those m "active" components are compacted into shared
@@ -28,8 +33,8 @@
 //
 // exp/log: the clamped edge term is only evaluated for x in (x_lo, x_hi) = (-log MAX_P, -log MIN_P)
 // (outside, the clamp makes it a constant + x), so exp(-x) and log(1-p) see a small, benign domain
-// and are written branch-free here (<= 1 ulp, checked against mpmath in tests/test_oracle.py's twin
-// of these formulas) instead of paying for libdevice's special-case handling.
+// and are written branch-free here (Estrin evaluation; <= 2 ulp, see the NumPy twin of these formulas in
+// tests/test_explog_twin.py) instead of paying for libdevice's special-case handling.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -113,10 +118,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 __device__ __forceinline__ double2 ldg2(const double *p) {
     return __ldg(reinterpret_cast<const double2 *>(p));
-}
-
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -243,17 +244,6 @@ __device__ __forceinline__ double clamp_step0(double f, double s, double g, doub
 __device__ __forceinline__ double clamp_step0_lo(double f, double s, double g) {
     const double x = __dadd_rn(f, __dmul_rn(s, g));
     return (__double2hiint(x) < 0) ? 0.0 : x;
-}
-
-// L2 prefetch of the rows of up to 32 neighbours (lane l < cnt owns row myv): one bulk prefetch
-// (cp.async.bulk.prefetch.L2, the TMA path) per row instead of one prefetch per 128-byte line.
-__device__ __forceinline__ void prefetch_rows(const double *F, int ld, int lane, int myv, int cnt) {
-    if (lane < cnt) {
-        const double *row = F + (size_t)myv * ld;
-        const char *rp = reinterpret_cast<const char *>(row);
-        const int bytes = ld * 8;
-        (void)rp; (void)bytes;
-    }
 }
 
 // cp.async staging of up to 4 neighbour rows (edges first .. first+3 of the id register `ids`) into the
