@@ -42,7 +42,11 @@ struct bigclam_ctx {
     double *d_sumF[2] = {nullptr, nullptr};
     int cur = 0;                // index of the current F / sumF buffer
     double *d_partials = nullptr;
-    int8_t *d_accepted = nullptr;
+    int8_t *d_accepted = nullptr;   // accepted step index per node of the last COMMITTED step
+    int8_t *d_accepted_spec = nullptr;   // written by a speculative step (bigclam_step), swapped in at commit
+    bool spec_valid = false;        // the next step has already been computed speculatively (see bigclam_step)
+    bool spec_null_mask = true;
+    uint64_t spec_mask_hash = 0;
     uint8_t *d_mask = nullptr;
     int32_t *d_done = nullptr;
     unsigned int *d_work = nullptr;
@@ -130,7 +134,7 @@ static void free_ctx(bigclam_ctx *c) {
     cudaFree(c->d_rowptr); cudaFree(c->d_col); cudaFree(c->d_meta);
     cudaFree(c->d_F[0]); cudaFree(c->d_F[1]);
     cudaFree(c->d_sumF[0]); cudaFree(c->d_sumF[1]);
-    cudaFree(c->d_partials); cudaFree(c->d_accepted); cudaFree(c->d_mask);
+    cudaFree(c->d_partials); cudaFree(c->d_accepted); cudaFree(c->d_accepted_spec); cudaFree(c->d_mask);
     cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_hub_items); cudaFree(c->d_hub_scratch); cudaFree(c->d_hub_counters); cudaFree(c->d_changed);
     for (int h = 0; h < 2; ++h) for (int r = 0; r < c->n_peers; ++r) if (c->peer_F[h][r]) cudaIpcCloseMemHandle(c->peer_F[h][r]); cudaFree(c->d_state); cudaFree(c->d_trace);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -368,6 +372,7 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     CUC(cudaMalloc(&ctx->d_sumF[1], sizeof(double) * ld));
     CUC(cudaMalloc(&ctx->d_partials, sizeof(double) * (2 * (size_t)ld + 2)));
     CUC(cudaMalloc(&ctx->d_accepted, (size_t)n));
+    CUC(cudaMalloc(&ctx->d_accepted_spec, (size_t)n));
     CUC(cudaMalloc(&ctx->d_mask, (size_t)n));
     CUC(cudaMalloc(&ctx->d_done, sizeof(int32_t)));
     CUC(cudaMalloc(&ctx->d_work, 2 * sizeof(unsigned int)));      // [0] live counter, [1] its initial value
@@ -428,6 +433,7 @@ static int colsum_current(bigclam_ctx *ctx) {
 
 extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
+    ctx->spec_valid = false;
     if (F == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_F: F is NULL");
     CU(cudaSetDevice(ctx->device));
     const int k = ctx->p.k, ld = ctx->ld;
@@ -445,6 +451,7 @@ extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
 
 extern "C" int bigclam_set_sumF(bigclam_ctx *ctx, const double *sumF) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
+    ctx->spec_valid = false;
     if (sumF == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_sumF: sumF is NULL");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemsetAsync(ctx->d_sumF[ctx->cur], 0, sizeof(double) * ctx->ld, ctx->stream));
@@ -587,6 +594,7 @@ static int launch_finish(bigclam_ctx *ctx, long long kernel_index, int variant, 
 }
 
 static int reset_run_state(bigclam_ctx *ctx) {
+    ctx->spec_valid = false;
     CU(cudaMemsetAsync(ctx->d_done, 0, sizeof(int32_t), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_state, 0, sizeof(RunState), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
@@ -612,28 +620,65 @@ extern "C" int bigclam_loglikelihood(bigclam_ctx *ctx, double *llh_out) {
     return BIGCLAM_OK;
 }
 
+static uint64_t mask_hash(const uint8_t *m, int64_t n) {
+    uint64_t h = 1469598103934665603ULL;
+    int64_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t v;
+        std::memcpy(&v, m + i, 8);
+        h = (h ^ v) * 1099511628211ULL;
+    }
+    for (; i < n; ++i) h = (h ^ m[i]) * 1099511628211ULL;
+    return h;
+}
+
+// One call of backtrackingLineSearchs.  The LLH it has to return is the PRE sum of the NEXT call, so
+// instead of a separate LLH pass the next call's whole step kernel is launched speculatively (same uset):
+// its PRE delivers this call's LLH, and when the next call arrives with the same uset its result is simply
+// committed (sumF update + buffer flip).  Any other entry point that touches the state drops the speculation.
 extern "C" int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *llh_out, int64_t *n_updated_out) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    int rc = reset_run_state(ctx);
-    if (rc) return rc;
-    const uint8_t *d_mask = nullptr;
-    if (node_mask != nullptr) {
-        CU(cudaMemcpyAsync(ctx->d_mask, node_mask, (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
-        d_mask = ctx->d_mask;
-    }
+    const bool speculate = (ctx->n_peers == 0);         // peers' replicas must never see uncommitted rows
+    const bool null_mask = (node_mask == nullptr);
+    const uint64_t hash = null_mask ? 0 : mask_hash(node_mask, ctx->n);
+    const bool hit = speculate && ctx->spec_valid && ctx->spec_null_mask == null_mask && ctx->spec_mask_hash == hash;
+    int rc;
     StepArgs a;
-    fill_args(ctx, a, true, d_mask, false);
-    rc = timed_launch(ctx, a, true);                       // PRE + LS + swap
-    if (rc) return rc;
-    rc = launch_finish(ctx, 0, 0, 0.0, true, false);       // sumF update (:192), zero partials
+    const uint8_t *d_mask = null_mask ? nullptr : ctx->d_mask;
+    if (!hit) {
+        rc = reset_run_state(ctx);
+        if (rc) return rc;
+        if (!null_mask) CU(cudaMemcpyAsync(ctx->d_mask, node_mask, (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+        fill_args(ctx, a, true, d_mask, false);
+        if (a.accepted != nullptr) a.accepted = ctx->d_accepted_spec;
+        rc = timed_launch(ctx, a, true);                   // PRE + LS + swap
+        if (rc) return rc;
+    } else {
+        ctx->last_step_launches = 0;
+        ctx->last_all_launches = 0;
+        // (the mask on the device is the one the speculative kernel used; nothing to upload)
+    }
+    // commit: sumF update (:192), n_updated, zero the partials; the step's accepted[] becomes current
+    rc = launch_finish(ctx, 0, 0, 0.0, true, false);
     if (rc) return rc;
     ctx->cur ^= 1;
-    fill_args(ctx, a, false, nullptr, false);              // LLH with new F, new sumF (:196-219)
-    rc = timed_launch(ctx, a, false);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials + 2 * ctx->ld, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    std::swap(ctx->d_accepted, ctx->d_accepted_spec);
     CU(cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_state, sizeof(RunState), cudaMemcpyDeviceToHost, ctx->stream));
+    if (speculate) {
+        fill_args(ctx, a, true, d_mask, false);            // next call, speculatively: its PRE is this call's LLH
+        if (a.accepted != nullptr) a.accepted = ctx->d_accepted_spec;
+        rc = timed_launch(ctx, a, true);
+        if (rc) return rc;
+        ctx->spec_valid = true;
+        ctx->spec_null_mask = null_mask;
+        ctx->spec_mask_hash = hash;
+    } else {
+        fill_args(ctx, a, false, nullptr, false);          // LLH with new F, new sumF (:196-219)
+        rc = timed_launch(ctx, a, false);
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials + 2 * ctx->ld, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (llh_out) *llh_out = ctx->h_pinned[0];
     if (n_updated_out) *n_updated_out = reinterpret_cast<RunState *>(ctx->h_pinned + 8)->n_updated;
@@ -727,12 +772,14 @@ extern "C" int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi)
     CU(cudaMemcpy(rp.data(), ctx->d_rowptr, sizeof(int64_t) * rp.size(), cudaMemcpyDeviceToHost));
     ctx->lo = lo;
     ctx->hi = hi;
+    ctx->spec_valid = false;
     return rebuild_order(ctx, rp);
 }
 
 extern "C" int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
+    if (ctx->spec_valid) { int rr = reset_run_state(ctx); if (rr) return rr; }   // drop a speculative bigclam_step
     StepArgs a;
     fill_args(ctx, a, true, nullptr, false);
     int rc = timed_launch(ctx, a, true);
@@ -760,6 +807,7 @@ extern "C" int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64
 extern "C" int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
+    if (ctx->spec_valid) { int rr = reset_run_state(ctx); if (rr) return rr; }   // drop a speculative bigclam_step
     CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
     StepArgs a;
     fill_args(ctx, a, false, nullptr, false);
@@ -771,6 +819,7 @@ extern "C" int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev) {
 
 extern "C" int bigclam_rollback(bigclam_ctx *ctx) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
+    ctx->spec_valid = false;
     ctx->cur ^= 1;
     return BIGCLAM_OK;
 }
@@ -852,6 +901,7 @@ extern "C" int bigclam_set_owned_nodes(bigclam_ctx *ctx, const int32_t *nodes, i
     std::vector<int32_t> order(nodes, nodes + count);
     ctx->lo = 0;
     ctx->hi = ctx->n;
+    ctx->spec_valid = false;
     return rebuild_order_list(ctx, rp, order);
 }
 

@@ -86,6 +86,9 @@ int bigclam_get_sumF(bigclam_ctx *ctx, double *sumF_out);  /* k */
  * (:186-193), LLH with the new F and sumF (:196-219, returned).  node_mask: NULL = all vertices
  * (the reference always passes all, :227); otherwise n bytes, u is in uset iff node_mask[u] != 0.
  * Nodes with an empty neighbour list are never updated (the reference would throw).
+ * The returned LLH is the PRE sum of the next call, so the next call's step kernel (same uset) is launched
+ * speculatively to obtain it; a following bigclam_step with the same uset just commits that result.  Every
+ * other entry point that reads or writes the state sees exactly the state after this call.
  */
 int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *llh_out, int64_t *n_updated_out);
 

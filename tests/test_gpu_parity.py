@@ -337,3 +337,35 @@ def test_mega_hub_split_over_blocks(oracle, graphs):
     Fo, so, llho, callso, tro = oracle.run(rp, col, F0, sumF, P, variant=4, max_outer=12)
     assert b.last_calls == callso and np.allclose(b.last_trace, tro, rtol=1e-8)
     b.close()
+
+
+def test_step_speculation_is_invisible(oracle):
+    """bigclam_step launches the next call's kernel speculatively (its PRE is this call's LLH).  Interleaving
+    other entry points, changing the uset or resetting F must give exactly the non-speculative results."""
+    n, k = 500, 10
+    rp, col = random_graph(n, 6, seed=71, hub=80)
+    rng = np.random.default_rng(71)
+    F0 = rng.random((n, k)) * (rng.random((n, k)) < 0.4)
+    sumF = oracle.colsum(F0)
+    P = oracle.make_params(k)
+    b = _solver(rp, col, k, F0, sumF)
+    F, s = F0, sumF
+    masks = [None, None, rng.random(n) < 0.5, rng.random(n) < 0.5, None, None]
+    for it, mk in enumerate(masks):
+        uset = None if mk is None else np.flatnonzero(mk)
+        llh = b.backtrackingLineSearchs(uset=uset)
+        r = oracle.step(rp, col, F, s, P, node_mask=None if mk is None else mk.astype(np.uint8))
+        _check_step(b, r, llh, max_flips=1, where=f"spec it{it}", max_idx_diff=0.05)
+        if it == 1:
+            assert abs(b.loglikelihood() - llh) <= 1e-12 * abs(llh)      # drops the speculation, state unchanged
+        F, s = b.F, b.sumF
+    # a reset in the middle of a speculated sequence
+    b.set_F(F0, sumF=sumF)
+    llh = b.backtrackingLineSearchs()
+    r = oracle.step(rp, col, F0, sumF, P)
+    _check_step(b, r, llh, max_flips=1, where="spec after set_F")
+    # the device loop after speculative single steps
+    b._run(4, 1e-4, 5)
+    Fo, so, llho, callso, tro = oracle.run(rp, col, r.F, r.sumF, P, variant=4, max_outer=5)
+    assert np.allclose(b.last_trace, tro, rtol=1e-8)
+    b.close()
