@@ -200,7 +200,7 @@ def run_single(args):
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     e2e = {"value": nnz / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(n),
            "d2h_bytes_per_step": 72, "ms_per_step": e2e_ms,
-           "note": "bigclam_step(): uset mask H2D (pinned) + step kernel + sumF + separate LLH pass + LLH/n_updated D2H; F stays resident like the reference's cached RDD"}
+           "note": "bigclam_step() per step: uset mask H2D (pinned) + sumF commit + the next call's step kernel launched speculatively (its PRE is this call's LLH) + LLH/n_updated D2H, synchronous; F stays resident like the reference's cached RDD"}
 
     # ---- workload A of SURVEY §8d: the reference's own init (conductance seeds, 0/1 indicator columns) ----
     extra_a = None

@@ -649,7 +649,10 @@ extern "C" int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *
     if (!hit) {
         rc = reset_run_state(ctx);
         if (rc) return rc;
-        if (!null_mask) CU(cudaMemcpyAsync(ctx->d_mask, node_mask, (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // the uset of this call always travels to the device (on a hit it equals what the speculative kernel used)
+    if (!null_mask) CU(cudaMemcpyAsync(ctx->d_mask, node_mask, (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    if (!hit) {
         fill_args(ctx, a, true, d_mask, false);
         if (a.accepted != nullptr) a.accepted = ctx->d_accepted_spec;
         rc = timed_launch(ctx, a, true);                   // PRE + LS + swap
@@ -657,7 +660,6 @@ extern "C" int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *
     } else {
         ctx->last_step_launches = 0;
         ctx->last_all_launches = 0;
-        // (the mask on the device is the one the speculative kernel used; nothing to upload)
     }
     // commit: sumF update (:192), n_updated, zero the partials; the step's accepted[] becomes current
     rc = launch_finish(ctx, 0, 0, 0.0, true, false);
