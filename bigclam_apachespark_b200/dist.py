@@ -229,7 +229,7 @@ class DistBigClam:
         if self.exchange != "p2p":
             F_cur, F_next, _ = self.e.state()
             self._exchange_rows(F_cur, F_next)
-        llh_pre, nupd = self.e.finish_local(sync) if sync is False else self.e.finish_local()   # sumF -= sum(old - new)
+        llh_pre, nupd = self.e.finish_local(sync)       # sumF -= sum(old - new) on every rank
         self.last_n_updated = nupd
         return llh_pre, nupd
 
