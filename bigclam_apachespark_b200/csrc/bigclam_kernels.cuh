@@ -647,29 +647,38 @@ __device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, con
         double S1 = 0.0;
 
         if (phase <= 1) {
-            // ---- PRE over this warp's slice (batches of 4 rows straight from global memory) ----
+            // ---- PRE over this warp's slice: batches of 4 rows through the warp's cp.async staging buffer
+            // (the same buffer later carries this warp's partial gradient), next batch in flight ----
             const int rsel = (lane >> 3) & 3;
-            for (int gb = ebeg; gb < eend; gb += 32) {
-                const int cnt32 = min(32, eend - gb);
-                const int myv = (lane < cnt32) ? colp[gb + lane] : 0;
+            int gb = ebeg;
+            int cnt32 = min(32, max(0, eend - gb));
+            int myv = (lane < cnt32) ? colp[gb + lane] : 0;
+            if (cnt32 > 0) stage_rows<C2, 4>(my_part, F, ld, ld2, lane, myv, 0, cnt32);
+            while (gb < eend) {
+                const int cnt2 = min(32, max(0, eend - gb - 32));
+                const int myv2 = (lane < cnt2) ? colp[gb + 32 + lane] : 0;
                 for (int eb = 0; eb < cnt32; eb += 4) {
+                    cp_async_wait_all();
+                    __syncwarp();
                     double2 x[4][C2];
                     double part[4];
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const int v = __shfl_sync(0xffffffffu, myv, (eb + r) & 31);
-                        const double *fv = F + (size_t)v * ld;
                         const bool ok = eb + r < cnt32;
                         double p = 0.0;
 #pragma unroll
                         for (int c = 0; c < C2; ++c) {
                             const int q = lane + 32 * c;
-                            x[r][c] = (ok && q < ld2) ? ldg2(fv + 2 * q) : make_double2(0.0, 0.0);
+                            x[r][c] = (ok && q < ld2) ? *reinterpret_cast<const double2 *>(my_part + r * ld + 2 * q)
+                                                      : make_double2(0.0, 0.0);
                             p = fma(fu[c].x, x[r][c].x, p);
                             p = fma(fu[c].y, x[r][c].y, p);
                         }
                         part[r] = p;
                     }
+                    __syncwarp();
+                    if (eb + 4 < cnt32) stage_rows<C2, 4>(my_part, F, ld, ld2, lane, myv, eb + 4, cnt32);
+                    else if (cnt2 > 0) stage_rows<C2, 4>(my_part, F, ld, ld2, lane, myv2, 0, cnt2);
                     const double kx = batch_reduce<4>(part, lane);
                     double w;
                     double t = edge_term<true>(kx, ec, w);
@@ -689,7 +698,11 @@ __device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, con
                         }
                     }
                 }
+                gb += 32;
+                cnt32 = cnt2;
+                myv = myv2;
             }
+            __syncwarp();
             // ---- combine the partial gradient and S1 over the block ----
 #pragma unroll
             for (int c = 0; c < C2; ++c) {
