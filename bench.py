@@ -34,9 +34,18 @@ WORKLOAD = "com-amazon K=200, synthetic F0 (p=0.05 U[0,1), seed 1234), fp64"
 K = 200
 
 
+_GRAPH = "com-amazon"
+
+
 def load_workload():
+    """Default: the com-amazon topology fixture.  `--graph rmat:<nodes>:<edges>` generates BASELINE config 5's
+    R-MAT family instead ((a,b,c,d) = (.57,.19,.19,.05), seed 42) — not the headline workload."""
     from bigclam_apachespark_b200 import graphs as G
-    rp, col, _ = G.load_npz_graph("com-amazon")
+    if _GRAPH.startswith("rmat:"):
+        _, nn, mm = _GRAPH.split(":")
+        rp, col = G.rmat_graph(int(nn), int(mm), seed=42)
+    else:
+        rp, col, _ = G.load_npz_graph(_GRAPH)
     n = len(rp) - 1
     F0 = G.synthetic_F0(n, K, seed=1234, density=0.05)
     return rp, col, F0
@@ -254,7 +263,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-init-a", action="store_true", help="skip the reference-style-init extra workload")
+    ap.add_argument("--graph", default="com-amazon", help="fixture name or rmat:<nodes>:<edges> (default: the headline workload)")
     args = ap.parse_args()
+    global _GRAPH, WORKLOAD
+    _GRAPH = args.graph
+    if _GRAPH != "com-amazon":
+        WORKLOAD = f"{_GRAPH} K={K}, synthetic F0 (p=0.05 U[0,1), seed 1234), fp64"
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         args.steps = min(args.steps, 20)     # bounded: each step is ~1-4 s of all-core CPU work
