@@ -144,9 +144,6 @@ static void free_ctx(bigclam_ctx *c) {
 
 extern "C" void bigclam_destroy(bigclam_ctx *ctx) { free_ctx(ctx); }
 
-template <int C2>
-struct RowsInFlight { static constexpr int value = (C2 <= 4) ? 4 : (C2 <= 8 ? 2 : 1); };
-
 template <int C2, bool kHub, bool kPush>
 static cudaError_t configure_one(size_t smem, int *blocks_per_sm) {
     constexpr int R = RowsInFlight<C2>::value;

@@ -101,8 +101,11 @@ struct __align__(16) WarpLists {
     unsigned short poff[40];             // pair-list offsets per edge of the chunk (33 used)
     unsigned char pt[kMaxPairs];         // pair list: active index t
 };
+// Rows per staged batch (the R of step_kernel) for a row of C2 double2 chunks per lane.
+template <int C2>
+struct RowsInFlight { static constexpr int value = (C2 <= 4) ? 4 : (C2 <= 8 ? 2 : 1); };
 __host__ __device__ inline size_t block_smem_bytes(int ld, int /*maxm*/) {
-    const int stage = (ld <= 256) ? 4 : (ld <= 512 ? 2 : 1);   // rows per staged batch (= R of the kernel)
+    const int stage = (ld <= 256) ? RowsInFlight<4>::value : (ld <= 512 ? RowsInFlight<8>::value : RowsInFlight<16>::value);
     // ... | sumF[ld] | W x D[ld] | W x rows[4][ld] (cp.async staging of one batch of neighbour rows)
     return sizeof(double) * kMaxSteps + (size_t)kWarpsPerBlock * sizeof(WarpLists) +
            sizeof(double) * (size_t)ld * (1 + kWarpsPerBlock + stage * kWarpsPerBlock);
@@ -459,32 +462,30 @@ __device__ __forceinline__ double ls_edge_range(const double *__restrict__ F, co
             }
         }
         __syncwarp();
-        // consume: lane (j, h) walks the pairs of edges e2 + h and e2 + 2 + h (two exp/log chains)
-        auto pairdot = [&](int e, bool valid) -> double {
-            const int i0 = valid ? (int)s_poff[e] : 0;
-            const int i1 = valid ? (int)s_poff[e + 1] : 0;
-            double D = 0.0;
-            if (need_hi) {
-#pragma unroll 1
-                for (int i = i0; i < i1; ++i) {
-                    const double2 fg = s_afg[s_pt[i]];
-                    D = fma(clamp_step0(fg.x, s, fg.y, max_f), s_pval[i], D);
-                }
-            } else {
-#pragma unroll 1
-                for (int i = i0; i < i1; ++i) {
-                    const double2 fg = s_afg[s_pt[i]];
-                    D = fma(clamp_step0_lo(fg.x, s, fg.y), s_pval[i], D);
-                }
-            }
-            return D;
-        };
+        // consume: lane (j, h) walks the pairs of edges e2 + h and e2 + 2 + h together (two independent
+        // LDS -> clamp -> FMA chains in flight, then two exp/log chains)
 #pragma unroll 1
         for (int e2 = 0; e2 < ce; e2 += 4) {
             const int eA = e2 + h, eB = e2 + 2 + h;
             const bool vA = eA < ce, vB = eB < ce;
-            const double DA = pairdot(eA, vA);
-            const double DB = pairdot(eB, vB);
+            const int iA = vA ? (int)s_poff[eA] : 0, nA = vA ? (int)s_poff[eA + 1] - iA : 0;
+            const int iB = vB ? (int)s_poff[eB] : 0, nB = vB ? (int)s_poff[eB + 1] - iB : 0;
+            const int nmax = max(nA, nB);
+            double DA = 0.0, DB = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < nmax; ++k) {
+                const bool ka = k < nA, kb = k < nB;
+                const int ia = ka ? iA + k : 0, ib = kb ? iB + k : 0;        // entry 0 is always readable
+                const double2 fa = s_afg[s_pt[ia]], fb = s_afg[s_pt[ib]];
+                const double pa = ka ? s_pval[ia] : 0.0, pb = kb ? s_pval[ib] : 0.0;
+                if (need_hi) {
+                    DA = fma(clamp_step0(fa.x, s, fa.y, max_f), pa, DA);
+                    DB = fma(clamp_step0(fb.x, s, fb.y, max_f), pb, DB);
+                } else {
+                    DA = fma(clamp_step0_lo(fa.x, s, fa.y), pa, DA);
+                    DB = fma(clamp_step0_lo(fb.x, s, fb.y), pb, DB);
+                }
+            }
             double tA, tB;
             edge_term2(DA, DB, ec, tA, tB);
             sumterms += vA ? tA : 0.0;

@@ -3,7 +3,10 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bigclam_apachespark_b200 import BigClam, graphs as G  # noqa: E402
+from bigclam_apachespark_b200 import BigClam, _lib, graphs as G  # noqa: E402
+
+if os.environ.get("BIGCLAM_AB_LIB"):      # dev only: profile a variant built by tools/build_variant.sh
+    _lib.LIB_PATH = os.path.abspath(os.environ["BIGCLAM_AB_LIB"])
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 3
