@@ -46,7 +46,7 @@ struct bigclam_ctx {
     int8_t *d_accepted_spec = nullptr;   // written by a speculative step (bigclam_step), swapped in at commit
     bool spec_valid = false;        // the next step has already been computed speculatively (see bigclam_step)
     bool spec_null_mask = true;
-    uint64_t spec_mask_hash = 0;
+    std::vector<uint8_t> spec_mask;    // the uset the speculative step was computed with (exact comparison)
     uint8_t *d_mask = nullptr;
     int32_t *d_done = nullptr;
     unsigned int *d_work = nullptr;
@@ -71,7 +71,7 @@ struct bigclam_ctx {
     std::string err;
 };
 
-static std::string g_create_err;
+static thread_local std::string g_create_err;   // bigclam_create failures (no context yet), per calling thread
 
 static int fail(bigclam_ctx *c, int code, const char *fmt, ...) {
     char buf[512];
@@ -90,6 +90,14 @@ static int fail(bigclam_ctx *c, int code, const char *fmt, ...) {
             return fail(ctx, BIGCLAM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
                         __FILE__, __LINE__);                                                      \
     } while (0)
+
+// A speculative step (bigclam_step) left its partial sums in d_partials: forget both.
+static int drop_speculation(bigclam_ctx *ctx) {
+    if (!ctx->spec_valid) return BIGCLAM_OK;
+    ctx->spec_valid = false;
+    CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
+    return BIGCLAM_OK;
+}
 
 extern "C" const char *bigclam_version(void) { return "bigclam_b200 0.1 (sm_100a)"; }
 
@@ -136,7 +144,10 @@ static void free_ctx(bigclam_ctx *c) {
     cudaFree(c->d_sumF[0]); cudaFree(c->d_sumF[1]);
     cudaFree(c->d_partials); cudaFree(c->d_accepted); cudaFree(c->d_accepted_spec); cudaFree(c->d_mask);
     cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_hub_items); cudaFree(c->d_hub_scratch); cudaFree(c->d_hub_counters); cudaFree(c->d_changed);
-    for (int h = 0; h < 2; ++h) for (int r = 0; r < c->n_peers; ++r) if (c->peer_F[h][r]) cudaIpcCloseMemHandle(c->peer_F[h][r]); cudaFree(c->d_state); cudaFree(c->d_trace);
+    for (int h = 0; h < 2; ++h)
+        for (int r = 0; r < c->n_peers; ++r)
+            if (c->peer_F[h][r]) cudaIpcCloseMemHandle(c->peer_F[h][r]);
+    cudaFree(c->d_state); cudaFree(c->d_trace);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -422,17 +433,18 @@ static int colsum_current(bigclam_ctx *ctx) {
     dim3 grid((ctx->ld + 31) / 32, nchunks);
     colsum_partial_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_F[ctx->cur], ctx->n, ctx->ld, part);
     colsum_final_kernel<<<(ctx->ld + 127) / 128, 128, 0, ctx->stream>>>(part, nchunks, ctx->ld, ctx->d_sumF[ctx->cur]);
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaFree(part));
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(part);
+    if (e != cudaSuccess) return fail(ctx, BIGCLAM_ECUDA, "column sums of F: %s", cudaGetErrorString(e));
     return BIGCLAM_OK;
 }
 
 extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
-    ctx->spec_valid = false;
     if (F == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_F: F is NULL");
     CU(cudaSetDevice(ctx->device));
+    if (int rd = drop_speculation(ctx)) return rd;
     const int k = ctx->p.k, ld = ctx->ld;
     // values must already satisfy the invariant the reference maintains: MIN_F <= F <= MAX_F
     CU(cudaMemsetAsync(ctx->d_F[ctx->cur], 0, sizeof(double) * (size_t)ctx->n * ld, ctx->stream));
@@ -448,9 +460,9 @@ extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
 
 extern "C" int bigclam_set_sumF(bigclam_ctx *ctx, const double *sumF) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
-    ctx->spec_valid = false;
     if (sumF == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_sumF: sumF is NULL");
     CU(cudaSetDevice(ctx->device));
+    if (int rd = drop_speculation(ctx)) return rd;
     CU(cudaMemsetAsync(ctx->d_sumF[ctx->cur], 0, sizeof(double) * ctx->ld, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_sumF[ctx->cur], sumF, sizeof(double) * ctx->p.k, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -617,18 +629,6 @@ extern "C" int bigclam_loglikelihood(bigclam_ctx *ctx, double *llh_out) {
     return BIGCLAM_OK;
 }
 
-static uint64_t mask_hash(const uint8_t *m, int64_t n) {
-    uint64_t h = 1469598103934665603ULL;
-    int64_t i = 0;
-    for (; i + 8 <= n; i += 8) {
-        uint64_t v;
-        std::memcpy(&v, m + i, 8);
-        h = (h ^ v) * 1099511628211ULL;
-    }
-    for (; i < n; ++i) h = (h ^ m[i]) * 1099511628211ULL;
-    return h;
-}
-
 // One call of backtrackingLineSearchs.  The LLH it has to return is the PRE sum of the NEXT call, so
 // instead of a separate LLH pass the next call's whole step kernel is launched speculatively (same uset):
 // its PRE delivers this call's LLH, and when the next call arrives with the same uset its result is simply
@@ -638,8 +638,9 @@ extern "C" int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *
     CU(cudaSetDevice(ctx->device));
     const bool speculate = (ctx->n_peers == 0);         // peers' replicas must never see uncommitted rows
     const bool null_mask = (node_mask == nullptr);
-    const uint64_t hash = null_mask ? 0 : mask_hash(node_mask, ctx->n);
-    const bool hit = speculate && ctx->spec_valid && ctx->spec_null_mask == null_mask && ctx->spec_mask_hash == hash;
+    const bool hit = speculate && ctx->spec_valid && ctx->spec_null_mask == null_mask &&
+                     (null_mask || (ctx->spec_mask.size() == (size_t)ctx->n &&
+                                    std::memcmp(ctx->spec_mask.data(), node_mask, (size_t)ctx->n) == 0));
     int rc;
     StepArgs a;
     const uint8_t *d_mask = null_mask ? nullptr : ctx->d_mask;
@@ -671,7 +672,7 @@ extern "C" int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *
         if (rc) return rc;
         ctx->spec_valid = true;
         ctx->spec_null_mask = null_mask;
-        ctx->spec_mask_hash = hash;
+        if (!null_mask && !hit) ctx->spec_mask.assign(node_mask, node_mask + ctx->n);   // on a hit it is already equal
     } else {
         fill_args(ctx, a, false, nullptr, false);          // LLH with new F, new sumF (:196-219)
         rc = timed_launch(ctx, a, false);
@@ -771,14 +772,14 @@ extern "C" int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi)
     CU(cudaMemcpy(rp.data(), ctx->d_rowptr, sizeof(int64_t) * rp.size(), cudaMemcpyDeviceToHost));
     ctx->lo = lo;
     ctx->hi = hi;
-    ctx->spec_valid = false;
+    if (int rd = drop_speculation(ctx)) return rd;
     return rebuild_order(ctx, rp);
 }
 
 extern "C" int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    if (ctx->spec_valid) { int rr = reset_run_state(ctx); if (rr) return rr; }   // drop a speculative bigclam_step
+    if (int rd = drop_speculation(ctx)) return rd;
     StepArgs a;
     fill_args(ctx, a, true, nullptr, false);
     int rc = timed_launch(ctx, a, true);
@@ -806,7 +807,7 @@ extern "C" int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64
 extern "C" int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    if (ctx->spec_valid) { int rr = reset_run_state(ctx); if (rr) return rr; }   // drop a speculative bigclam_step
+    if (int rd = drop_speculation(ctx)) return rd;
     CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
     StepArgs a;
     fill_args(ctx, a, false, nullptr, false);
@@ -818,7 +819,8 @@ extern "C" int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev) {
 
 extern "C" int bigclam_rollback(bigclam_ctx *ctx) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
-    ctx->spec_valid = false;
+    CU(cudaSetDevice(ctx->device));
+    if (int rd = drop_speculation(ctx)) return rd;
     ctx->cur ^= 1;
     return BIGCLAM_OK;
 }
@@ -852,6 +854,10 @@ extern "C" int bigclam_ipc_open_peers(bigclam_ctx *ctx, int32_t world, int32_t r
         return fail(ctx, BIGCLAM_EINVAL, "bigclam_ipc_open_peers: bad world/rank (at most 8 GPUs)");
     CU(cudaSetDevice(ctx->device));
     const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles);
+    for (int half = 0; half < 2; ++half)            // a second call replaces the first mapping
+        for (int r = 0; r < ctx->n_peers; ++r)
+            if (ctx->peer_F[half][r]) { cudaIpcCloseMemHandle(ctx->peer_F[half][r]); ctx->peer_F[half][r] = nullptr; }
+    ctx->n_peers = 0;
     int np = 0;
     for (int r = 0; r < world; ++r) {
         if (r == rank) continue;
@@ -900,7 +906,7 @@ extern "C" int bigclam_set_owned_nodes(bigclam_ctx *ctx, const int32_t *nodes, i
     std::vector<int32_t> order(nodes, nodes + count);
     ctx->lo = 0;
     ctx->hi = ctx->n;
-    ctx->spec_valid = false;
+    if (int rd = drop_speculation(ctx)) return rd;
     return rebuild_order_list(ctx, rp, order);
 }
 
@@ -912,11 +918,13 @@ extern "C" int bigclam_extract(bigclam_ctx *ctx, double delta, uint8_t *member_o
     const int k = ctx->p.k;
     uint8_t *d_member = nullptr;
     double *d_fmax = nullptr;
-    CU(cudaMalloc(&d_member, (size_t)ctx->n * k));
-    CU(cudaMalloc(&d_fmax, sizeof(double) * (size_t)ctx->n));
+    cudaError_t e = cudaMalloc(&d_member, (size_t)ctx->n * k);
+    if (e == cudaSuccess) e = cudaMalloc(&d_fmax, sizeof(double) * (size_t)ctx->n);
     const int wpb = 8;
-    extract_kernel<<<(unsigned)((ctx->n + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(ctx->d_F[ctx->cur], ctx->n, k, ctx->ld, delta, d_member, d_fmax);
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        extract_kernel<<<(unsigned)((ctx->n + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(ctx->d_F[ctx->cur], ctx->n, k, ctx->ld, delta, d_member, d_fmax);
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(member_out, d_member, (size_t)ctx->n * k, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && fmax_out != nullptr) e = cudaMemcpyAsync(fmax_out, d_fmax, sizeof(double) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
