@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libbigclam_b200.so")
 OK, EINVAL, ECUDA, ENOMEM, EIO, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 F_TIME_KERNELS = 1
 F_RECORD_ACCEPTED = 2
+F_SPARSE_ROWS = 4
 
 
 class Params(C.Structure):

@@ -2,6 +2,7 @@
 // No CPU fallback: every compute entry point launches CUDA kernels or fails.
 #include "../../include/bigclam_b200.h"
 #include "bigclam_kernels.cuh"
+#include "bigclam_sparse.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -68,6 +69,17 @@ struct bigclam_ctx {
 
     unsigned int h_work_init = 0;
 
+    // sparse rows of F (BIGCLAM_F_SPARSE_ROWS, bigclam_sparse.cuh): header + pool per F buffer
+    bool sparse = false;
+    uint64_t *d_hdr[2] = {nullptr, nullptr};
+    double *d_pool[2] = {nullptr, nullptr};
+    uint64_t pool_cap8 = 0;
+    unsigned long long *d_pool_top = nullptr;   // [2]
+    int32_t *d_overflow = nullptr;
+    int sp_grid = 0;
+    size_t sp_smem = 0;
+    bool dense_valid = true;       // d_F[cur] mirrors the sparse state (set_F; refreshed on demand by ensure_dense)
+
     std::string err;
 };
 
@@ -98,6 +110,9 @@ static int drop_speculation(bigclam_ctx *ctx) {
     CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
     return BIGCLAM_OK;
 }
+
+static int ensure_dense(bigclam_ctx *ctx);
+static int check_overflow(bigclam_ctx *ctx);
 
 extern "C" const char *bigclam_version(void) { return "bigclam_b200 0.1 (sm_100a)"; }
 
@@ -148,6 +163,8 @@ static void free_ctx(bigclam_ctx *c) {
         for (int r = 0; r < c->n_peers; ++r)
             if (c->peer_F[h][r]) cudaIpcCloseMemHandle(c->peer_F[h][r]);
     cudaFree(c->d_state); cudaFree(c->d_trace);
+    cudaFree(c->d_hdr[0]); cudaFree(c->d_hdr[1]); cudaFree(c->d_pool[0]); cudaFree(c->d_pool[1]);
+    cudaFree(c->d_pool_top); cudaFree(c->d_overflow);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -225,7 +242,7 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
     const int64_t max_deg = (cnt > 0) ? meta[0].deg : 0;
     const int64_t hub_deg = (4 * max_deg <= 3 * per_warp) ? INT64_MAX
                                                           : std::min<int64_t>(512, std::max<int64_t>(kHubDegree, per_warp / 5));
-    if (ctx->c2 <= 4) while (nh < cnt && meta[(size_t)nh].deg >= hub_deg) ++nh;
+    if (ctx->c2 <= 4 && !ctx->sparse) while (nh < cnt && meta[(size_t)nh].deg >= hub_deg) ++nh;
     ctx->n_hubs = nh;
     // work items of the hub phase: hubs above kHubSlice edges are split into slices handled by different
     // blocks (phases 1-3), the others are done by one block (phase 0); see hub_phase
@@ -270,7 +287,8 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
         CU(cudaMalloc(&ctx->d_hub_scratch, sizeof(double) * slots * ((size_t)ctx->ld + 32)));
         CU(cudaMalloc(&ctx->d_hub_counters, sizeof(unsigned int) * 2 * slots));
     }
-    const unsigned int init = (unsigned int)nh + 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
+    const unsigned int init = ctx->sparse ? 3u * (unsigned int)ctx->sp_grid * kSpWarps
+                                          : (unsigned int)nh + 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
     ctx->h_work_init = init;
     if (ctx->d_work != nullptr) CU(cudaMemcpy(ctx->d_work + 1, &init, sizeof(unsigned int), cudaMemcpyHostToDevice));
     return BIGCLAM_OK;
@@ -368,6 +386,25 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     }
     ctx->grid = ctx->num_sms * bps;
     ctx->h_work_init = 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
+    if (params->flags & BIGCLAM_F_SPARSE_ROWS) {
+        if (ld > 256 || params->min_f != 0.0 || 2 * ld > kSpEntries) {
+            fail(nullptr, BIGCLAM_EUNSUPPORTED, "bigclam_create: BIGCLAM_F_SPARSE_ROWS needs k <= 256 and min_f == 0");
+            free_ctx(ctx);
+            return BIGCLAM_EUNSUPPORTED;
+        }
+        ctx->sparse = true;
+        ctx->sp_smem = sp_block_smem_bytes(ld);
+        int sbps = 0;
+        CUC(cudaFuncSetAttribute(sparse_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sbps, sparse_step_kernel, kSpThreads, ctx->sp_smem));
+        if (sbps <= 0) {
+            fail(nullptr, BIGCLAM_ECUDA, "bigclam_create: sparse kernel does not fit an SM (smem %zu B)", ctx->sp_smem);
+            free_ctx(ctx);
+            return BIGCLAM_ECUDA;
+        }
+        ctx->sp_grid = ctx->num_sms * sbps;
+        ctx->h_work_init = 3u * (unsigned int)ctx->sp_grid * kSpWarps;
+    }
 
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
@@ -397,6 +434,19 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     CUC(cudaMemset(ctx->d_accepted, 0xff, (size_t)n));
     CUC(cudaMemset(ctx->d_done, 0, sizeof(int32_t)));
     CUC(cudaMemset(ctx->d_state, 0, sizeof(RunState)));
+    if (ctx->sparse) {
+        // worst case: every row full (ld entries) — a step can then never overflow its pool
+        ctx->pool_cap8 = (uint64_t)n * sp_words((uint32_t)ld);
+        for (int b = 0; b < 2; ++b) {
+            CUC(cudaMalloc(&ctx->d_hdr[b], sizeof(uint64_t) * (size_t)n));
+            CUC(cudaMemset(ctx->d_hdr[b], 0, sizeof(uint64_t) * (size_t)n));
+            CUC(cudaMalloc(&ctx->d_pool[b], sizeof(double) * (size_t)ctx->pool_cap8));
+        }
+        CUC(cudaMalloc(&ctx->d_pool_top, 2 * sizeof(unsigned long long)));
+        CUC(cudaMemset(ctx->d_pool_top, 0, 2 * sizeof(unsigned long long)));
+        CUC(cudaMalloc(&ctx->d_overflow, sizeof(int32_t)));
+        CUC(cudaMemset(ctx->d_overflow, 0, sizeof(int32_t)));
+    }
 #undef CUC
     {
         std::vector<int64_t> rp(rowptr, rowptr + n + 1);
@@ -419,6 +469,10 @@ extern "C" int bigclam_set_stream(bigclam_ctx *ctx, void *cuda_stream) {
 
 extern "C" int bigclam_device_state(bigclam_ctx *ctx, void **F_dev, void **F_next_dev, void **sumF_dev, int64_t *ld) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (ctx->sparse) {                       // the dense buffers are only a mirror here: refresh it
+        CU(cudaSetDevice(ctx->device));
+        if (int re = ensure_dense(ctx)) return re;
+    }
     if (F_dev) *F_dev = ctx->d_F[ctx->cur];
     if (F_next_dev) *F_next_dev = ctx->d_F[ctx->cur ^ 1];
     if (sumF_dev) *sumF_dev = ctx->d_sumF[ctx->cur];
@@ -440,6 +494,42 @@ static int colsum_current(bigclam_ctx *ctx) {
     return BIGCLAM_OK;
 }
 
+// Sparse mode: rebuild the sparse rows of the current buffer from its dense mirror d_F[cur].
+static int sparse_from_dense(bigclam_ctx *ctx) {
+    const int b = ctx->cur;
+    CU(cudaMemsetAsync(ctx->d_pool_top + b, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_overflow, 0, sizeof(int32_t), ctx->stream));
+    const int wpb = 8;
+    dense_to_sparse_kernel<<<(unsigned)((ctx->n + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+        ctx->d_F[b], ctx->n, ctx->ld, ctx->d_hdr[b], ctx->d_pool[b], ctx->d_pool_top + b, ctx->pool_cap8, ctx->d_overflow);
+    CU(cudaGetLastError());
+    ctx->dense_valid = true;
+    return BIGCLAM_OK;
+}
+
+// Sparse mode: entry points that hand out dense rows refresh the mirror d_F[cur] first.
+static int ensure_dense(bigclam_ctx *ctx) {
+    if (!ctx->sparse || ctx->dense_valid) return BIGCLAM_OK;
+    const int b = ctx->cur;
+    const int wpb = 8;
+    sparse_to_dense_kernel<<<(unsigned)((ctx->n + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+        ctx->d_hdr[b], ctx->d_pool[b], ctx->n, ctx->ld, ctx->d_F[b]);
+    CU(cudaGetLastError());
+    ctx->dense_valid = true;
+    return BIGCLAM_OK;
+}
+
+// Sparse mode: a step that ran out of pool space left garbage rows; report it (cannot happen with the
+// worst-case pool bigclam_create allocates, kept as a guard for smaller pools).
+static int check_overflow(bigclam_ctx *ctx) {
+    if (!ctx->sparse) return BIGCLAM_OK;
+    int32_t ov = 0;
+    CU(cudaMemcpyAsync(&ov, ctx->d_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ov) return fail(ctx, BIGCLAM_ENOMEM, "sparse row pool exhausted");
+    return BIGCLAM_OK;
+}
+
 extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     if (F == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_F: F is NULL");
@@ -452,6 +542,7 @@ extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
                          (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
     int rc = colsum_current(ctx);
     if (rc != BIGCLAM_OK) return rc;
+    if (ctx->sparse) { rc = sparse_from_dense(ctx); if (rc != BIGCLAM_OK) return rc; }
     // with peer replicas every row counts as changed again: the next step publishes all owned rows
     if (ctx->d_changed != nullptr) CU(cudaMemsetAsync(ctx->d_changed, 1, (size_t)ctx->n, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -473,6 +564,7 @@ extern "C" int bigclam_get_F(bigclam_ctx *ctx, double *F_out) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     if (F_out == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_get_F: F_out is NULL");
     CU(cudaSetDevice(ctx->device));
+    if (int re = ensure_dense(ctx)) return re;
     const int k = ctx->p.k, ld = ctx->ld;
     CU(cudaMemcpy2DAsync(F_out, sizeof(double) * k, ctx->d_F[ctx->cur], sizeof(double) * ld, sizeof(double) * k,
                          (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -557,7 +649,25 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
     }
     // positions 0 .. 3*#warps-1 are pre-assigned statically, the rest is handed out dynamically
     CU(cudaMemcpyAsync(ctx->d_work, ctx->d_work + 1, sizeof(unsigned int), cudaMemcpyDeviceToDevice, ctx->stream));
-    launch_step(ctx->c2, a, ctx->grid, ctx->smem_bytes, ctx->stream);
+    if (ctx->sparse) {
+        // reads hdr/pool of the current buffer, writes the other one (its bump allocator starts at zero)
+        const int in = (a.F_in == ctx->d_F[0]) ? 0 : 1, out = in ^ 1;
+        SparseArgs sp;
+        sp.hdr_in = ctx->d_hdr[in];
+        sp.pool_in = ctx->d_pool[in];
+        sp.hdr_out = ctx->d_hdr[out];
+        sp.pool_out = ctx->d_pool[out];
+        sp.pool_top = ctx->d_pool_top + out;
+        sp.pool_cap8 = ctx->pool_cap8;
+        sp.overflow = ctx->d_overflow;
+        if (a.do_linesearch) {
+            CU(cudaMemsetAsync(sp.pool_top, 0, sizeof(unsigned long long), ctx->stream));
+            ctx->dense_valid = false;
+        }
+        sparse_step_kernel<<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
+    } else {
+        launch_step(ctx->c2, a, ctx->grid, ctx->smem_bytes, ctx->stream);
+    }
     CU(cudaGetLastError());
     if (timing) {
         CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
@@ -663,6 +773,7 @@ extern "C" int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *
     rc = launch_finish(ctx, 0, 0, 0.0, true, false);
     if (rc) return rc;
     ctx->cur ^= 1;
+    ctx->dense_valid = false;
     std::swap(ctx->d_accepted, ctx->d_accepted_spec);
     CU(cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_state, sizeof(RunState), cudaMemcpyDeviceToHost, ctx->stream));
     if (speculate) {
@@ -680,6 +791,7 @@ extern "C" int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *
     }
     CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials + 2 * ctx->ld, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (int ro = check_overflow(ctx)) return ro;
     if (llh_out) *llh_out = ctx->h_pinned[0];
     if (n_updated_out) *n_updated_out = reinterpret_cast<RunState *>(ctx->h_pinned + 8)->n_updated;
     return collect_timing(ctx);
@@ -743,6 +855,8 @@ extern "C" int bigclam_run(bigclam_ctx *ctx, int32_t variant, double rel_tol, in
         CU(cudaStreamSynchronize(ctx->stream));
     }
     ctx->cur = (start_cur + (int)(calls & 1)) & 1;
+    ctx->dense_valid = false;
+    if (int ro = check_overflow(ctx)) return ro;
     if (llh_out) *llh_out = hst->ret_llh;
     if (calls_out) *calls_out = calls;
     if (llh_trace != nullptr && trace_cap > 0) {
@@ -766,6 +880,7 @@ extern "C" int bigclam_get_kernel_time(bigclam_ctx *ctx, double *step_kernel_ms_
 // Node-partitioned pieces.
 extern "C" int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     if (lo < 0 || hi < lo || hi > ctx->n) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_owned_range: bad range");
     CU(cudaSetDevice(ctx->device));
     std::vector<int64_t> rp((size_t)ctx->n + 1);
@@ -778,6 +893,7 @@ extern "C" int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi)
 
 extern "C" int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     CU(cudaSetDevice(ctx->device));
     if (int rd = drop_speculation(ctx)) return rd;
     StepArgs a;
@@ -790,6 +906,7 @@ extern "C" int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev) {
 
 extern "C" int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64_t *n_updated_out) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     CU(cudaSetDevice(ctx->device));
     const bool want = (llh_pre_out != nullptr) || (n_updated_out != nullptr);
     if (want)
@@ -806,6 +923,7 @@ extern "C" int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64
 
 extern "C" int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     CU(cudaSetDevice(ctx->device));
     if (int rd = drop_speculation(ctx)) return rd;
     CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
@@ -822,6 +940,7 @@ extern "C" int bigclam_rollback(bigclam_ctx *ctx) {
     CU(cudaSetDevice(ctx->device));
     if (int rd = drop_speculation(ctx)) return rd;
     ctx->cur ^= 1;
+    ctx->dense_valid = false;
     return BIGCLAM_OK;
 }
 
@@ -840,6 +959,7 @@ extern "C" int bigclam_device_accepted(bigclam_ctx *ctx, void **accepted_dev) {
 // kernel pushes changed rows straight into the peers' replicas (see StepArgs::peer_out).
 extern "C" int bigclam_ipc_export(bigclam_ctx *ctx, void *handles_out /* 2 x 64 bytes */) {
     if (ctx == nullptr || handles_out == nullptr) return BIGCLAM_EINVAL;
+    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     CU(cudaSetDevice(ctx->device));
     cudaIpcMemHandle_t h[2];
     CU(cudaIpcGetMemHandle(&h[0], ctx->d_F[0]));
@@ -852,6 +972,7 @@ extern "C" int bigclam_ipc_export(bigclam_ctx *ctx, void *handles_out /* 2 x 64 
 extern "C" int bigclam_ipc_open_peers(bigclam_ctx *ctx, int32_t world, int32_t rank, const void *all_handles /* world x 2 x 64 */) {
     if (ctx == nullptr || all_handles == nullptr || world < 1 || world > 8 || rank < 0 || rank >= world)
         return fail(ctx, BIGCLAM_EINVAL, "bigclam_ipc_open_peers: bad world/rank (at most 8 GPUs)");
+    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     CU(cudaSetDevice(ctx->device));
     const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles);
     for (int half = 0; half < 2; ++half)            // a second call replaces the first mapping
@@ -896,6 +1017,7 @@ extern "C" int bigclam_collect_timing(bigclam_ctx *ctx) {
 // the ranks so that every rank gets the same mix of hubs and leaves (used with the peer-store exchange).
 extern "C" int bigclam_set_owned_nodes(bigclam_ctx *ctx, const int32_t *nodes, int64_t count) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     if (count < 0 || count > ctx->n || (count > 0 && nodes == nullptr))
         return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_owned_nodes: bad node list");
     for (int64_t i = 0; i < count; ++i)
@@ -915,6 +1037,7 @@ extern "C" int bigclam_extract(bigclam_ctx *ctx, double delta, uint8_t *member_o
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     if (member_out == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_extract: member_out is NULL");
     CU(cudaSetDevice(ctx->device));
+    if (int re = ensure_dense(ctx)) return re;
     const int k = ctx->p.k;
     uint8_t *d_member = nullptr;
     double *d_fmax = nullptr;

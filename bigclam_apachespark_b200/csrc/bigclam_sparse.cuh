@@ -1,0 +1,422 @@
+// bigclam_sparse.cuh — the same step (codes/bigclam4-7.scala:152-223) over SPARSE rows of F.
+//
+// Why: the reference keeps F as Breeze sparse vectors (`BSV[Double]`, bigclam4-7.scala:97-104) because the rows
+// ARE sparse: on the bench workload (com-amazon, K = 200) a row holds ~9 non-zeros of 200 through the whole
+// run and ~17 components are "active" in a line search.  The dense kernel (bigclam_kernels.cuh) moves and
+// multiplies 95 % zeros.  Here a row is (count, ascending component indices, values) in a per-step pool, every
+// neighbour row is read once per step (~120 bytes instead of 1.6 KB), and all per-edge work is proportional
+// to the row's non-zeros.
+//
+// Layout (per F buffer; double-buffered like the dense F):
+//   hdr[u]      uint64: (offset in 8-byte words << 24) | count
+//   pool        row block at `offset`: pad4(count) doubles, then pad4(count) uint16 indices (ascending)
+//   pool_top    bump allocator of the OUTPUT pool (words), zeroed before every step; a warp takes its new
+//               row's block with one atomicAdd.  The input pool is only read (Jacobi), so a step whose pool
+//               overflowed can simply be repeated with a larger pool.
+//
+// Per node (one warp), with fu scattered into a dense shared-memory vector fu_d[ld]:
+//   PRE   the entries of up to 32 neighbour rows are staged in shared memory; lane e walks row e:
+//         x_e = sum_i val_i * fu_d[idx_i] (no reduction: the dot lands in the lane that evaluates exp/log for
+//         that edge, 32 edges per call); the gradient sum g_d[idx] += w_e * val goes neighbour by neighbour
+//         (indices are unique inside a row: no conflicts, fixed order);
+//   scan  one pass over the ld components turns g_d into the gradient (:168), sums |g|^2 and lists the
+//         active components (fu > 0 or g > 0);
+//   LS    lane (trial j, edge parity h) walks the staged entries of its edges:
+//         D = sum_i clamp(fu_d[idx_i] + s_j * g_d[idx_i]) * val_i — an inactive component clamps to 0 and adds
+//         exactly nothing, so no pair list / intersection is needed; two edges per lane in flight;
+//   SWAP  the accepted candidate's non-zeros are compacted (ascending) into the staging buffer, a block is
+//         taken from the output pool, the row and its header are written.
+//
+// Limits of this first version: ld <= 256 (K <= 256), MIN_F_ == 0, single GPU (no peer pushes), no
+// block-cooperative hub phase (a hub is walked by one warp in chunks of 32 edges).
+#pragma once
+#include "bigclam_kernels.cuh"
+
+namespace bigclam {
+
+constexpr int kSpWarps = 8;
+constexpr int kSpThreads = kSpWarps * 32;
+constexpr int kSpEntries = 512;        // staged neighbour entries per chunk; >= 2 * ld so that one row always fits
+
+__host__ __device__ inline uint64_t sp_pack(uint64_t off8, uint32_t cnt) { return (off8 << 24) | (uint64_t)cnt; }
+__host__ __device__ inline uint32_t sp_cnt(uint64_t h) { return (uint32_t)(h & 0xffffffull); }
+__host__ __device__ inline uint64_t sp_off8(uint64_t h) { return h >> 24; }
+__host__ __device__ inline uint32_t sp_pad(uint32_t cnt) { return (cnt + 3u) & ~3u; }
+__host__ __device__ inline uint64_t sp_words(uint32_t cnt) { return (uint64_t)sp_pad(cnt) * 5u / 4u; }   // 8-byte words of a row block
+
+struct SparseArgs {
+    const uint64_t *hdr_in;
+    const double *pool_in;
+    uint64_t *hdr_out;
+    double *pool_out;
+    unsigned long long *pool_top;      // words used of pool_out
+    uint64_t pool_cap8;                // capacity of pool_out in words
+    int32_t *overflow;                 // set when a row did not fit (the step must be repeated with a larger pool)
+};
+
+// per-warp shared memory: fu_d[ld] | g_d[ld] | ent_val[E] | ent_idx[E] u16 | aidx[256] u16 | poff[40] u16
+__host__ __device__ inline size_t sp_warp_bytes(int ld) {
+    return sizeof(double) * 2 * (size_t)ld + (size_t)kSpEntries * 10 + 2 * (size_t)kMaxActiveCap + 2 * 40;
+}
+// block: steps[kMaxSteps] | sumF[ld] | D[ld] | kSpWarps x warp area
+__host__ __device__ inline size_t sp_block_smem_bytes(int ld) {
+    return sizeof(double) * (kMaxSteps + 2 * (size_t)ld) + (size_t)kSpWarps * sp_warp_bytes(ld);
+}
+
+// Stages the rows of up to 32 neighbours (ids colp[0 .. cnt32)) of one node into the warp's entry buffer: the
+// longest prefix of them whose entries fit (at least one: a row has at most ld <= kSpEntries / 2 entries).
+// Returns the number ne of staged neighbours; poff[e] .. poff[e + 1] is row e's range in the buffer.
+// (noinline, scalar arguments only: one copy in the code, called from PRE and from the line search.)
+__device__ __noinline__ int sp_stage_chunk(const uint64_t *__restrict__ hdr_in, const double *__restrict__ pool_in,
+                                           const int32_t *__restrict__ colp, int cnt32, int lane, double *ent_val,
+                                           unsigned short *ent_idx, unsigned short *poff) {
+    const int v = (lane < cnt32) ? colp[lane] : 0;
+    const uint64_t hv = (lane < cnt32) ? __ldg(hdr_in + v) : 0ull;
+    const int cv = (int)sp_cnt(hv);
+    int incl = cv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const unsigned fit = __ballot_sync(0xffffffffu, (lane < cnt32) && (incl <= kSpEntries));
+    const int ne = __popc(fit);                     // incl is monotone: the fitting lanes are 0 .. ne-1
+    const int beg = incl - cv;
+    if (lane == 0) poff[0] = 0;
+    if (lane < ne) poff[lane + 1] = (unsigned short)incl;
+#pragma unroll 2
+    for (int e = 0; e < ne; ++e) {
+        const uint64_t he = __shfl_sync(0xffffffffu, hv, e);
+        const int pe = __shfl_sync(0xffffffffu, beg, e);
+        const int ce = (int)sp_cnt(he);
+        const double *vals = pool_in + sp_off8(he);
+        const unsigned short *idxp = reinterpret_cast<const unsigned short *>(vals + sp_pad((uint32_t)ce));
+        for (int i = lane; i < ce; i += 32) {
+            ent_val[pe + i] = __ldg(vals + i);
+            ent_idx[pe + i] = __ldg(idxp + i);
+        }
+    }
+    __syncwarp();
+    return ne;
+}
+
+__global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepArgs a, const SparseArgs sp) {
+    if (a.done_flag != nullptr && *a.done_flag != 0) return;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ld = a.ld;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *s_steps = reinterpret_cast<double *>(smem_raw);
+    double *s_sumF = s_steps + kMaxSteps;
+    double *s_D = s_sumF + ld;
+    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_D + ld) + (size_t)wib * sp_warp_bytes(ld);
+    double *fu_d = reinterpret_cast<double *>(wbase);
+    double *g_d = fu_d + ld;
+    double *ent_val = g_d + ld;
+    unsigned short *ent_idx = reinterpret_cast<unsigned short *>(ent_val + kSpEntries);
+    unsigned short *aidx = ent_idx + kSpEntries;
+    unsigned short *poff = aidx + kMaxActiveCap;
+
+    for (int i = threadIdx.x; i < ld; i += kSpThreads) { s_sumF[i] = a.sumF[i]; s_D[i] = 0.0; }
+    for (int i = threadIdx.x; i < kMaxSteps; i += kSpThreads) s_steps[i] = a.steps[i];
+    for (int i = lane; i < ld; i += 32) { fu_d[i] = 0.0; g_d[i] = 0.0; }
+    __syncthreads();
+
+    const EdgeConst ec = {a.x_lo, a.x_hi, a.t_lo, a.t_hi, a.w_lo, a.w_hi};
+    const double max_f = a.max_f;
+    const int nsteps = a.nsteps;
+    const int64_t order_n = a.order_n;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    double llh_acc = 0.0, nupd_acc = 0.0;
+    const int64_t nwarps = (int64_t)gridDim.x * kSpWarps;
+
+    // positions 0 .. 3*#warps-1 are pre-assigned, the rest is handed out by the work counter two nodes ahead
+    int64_t pos = (int64_t)blockIdx.x * kSpWarps + wib;
+    int64_t pos_n = pos + nwarps, pos_nn = pos + 2 * nwarps;
+    NodeMeta cur = {0, 0, 0}, nxt = {0, 0, 0};
+    if (pos < order_n) cur = a.meta[pos];
+    if (pos_n < order_n) nxt = a.meta[pos_n];
+
+    while (pos < order_n) {
+        const int64_t u = cur.u, e0 = cur.e0;
+        const int deg = cur.deg;
+        NodeMeta nn = {0, 0, 0};
+        if (pos_nn < order_n) nn = a.meta[pos_nn];
+        unsigned int fetched = 0;
+        if (lane == 0) fetched = atomicAdd(a.work_counter, 1u);
+
+        // ---- own row: scatter into fu_d ----
+        const uint64_t hu = __ldg(sp.hdr_in + u);
+        const int cu = (int)sp_cnt(hu);
+        const double *uval = sp.pool_in + sp_off8(hu);
+        const unsigned short *uidx = reinterpret_cast<const unsigned short *>(uval + sp_pad((uint32_t)cu));
+        double fusf = 0.0, fufu = 0.0;
+        for (int i = lane; i < cu; i += 32) {
+            const double v = __ldg(uval + i);
+            const int c = __ldg(uidx + i);
+            fu_d[c] = v;
+            fusf = fma(v, s_sumF[c], fusf);
+            fufu = fma(v, v, fufu);
+        }
+        fusf = warp_sum(fusf);
+        fufu = warp_sum(fufu);
+        __syncwarp();
+
+        const bool in_uset = (a.node_mask == nullptr) || (a.node_mask[u] != 0);
+        const bool want_ls = a.do_linesearch && in_uset && deg > 0;
+
+        // ---------------- PRE (:157-169) ----------------
+        double S1 = 0.0;
+        int nchunks = 0, ne_last = 0;
+        for (int cb = 0; cb < deg;) {
+            const int ne = sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, deg - cb), lane, ent_val, ent_idx, poff);
+            double x = 0.0;
+            if (lane < ne) {
+                const int end = poff[lane + 1];
+                for (int i = poff[lane]; i < end; ++i) x = fma(ent_val[i], fu_d[ent_idx[i]], x);
+            }
+            double w;
+            const double t = edge_term<true>(x, ec, w);
+            S1 += (lane < ne) ? t : 0.0;
+            if (want_ls) {
+                for (int e = 0; e < ne; ++e) {
+                    const double we = __shfl_sync(0xffffffffu, w, e);
+                    const int pe = poff[e], pn = poff[e + 1];
+                    for (int i = pe + lane; i < pn; i += 32) {
+                        const int c = ent_idx[i];
+                        g_d[c] = fma(we, ent_val[i], g_d[c]);
+                    }
+                    __syncwarp();
+                }
+            }
+            cb += ne;
+            ne_last = ne;
+            ++nchunks;
+        }
+        S1 = warp_sum(S1);
+        const double llh_u = (S1 - fusf) + fufu;
+        llh_acc += llh_u;
+
+        int jstar = -1;
+        int m = 0;
+        if (want_ls) {
+            // ---- gradient (:168) in place, |g|^2, active components ----
+            double G2 = 0.0;
+            bool hi_lane = false;
+            for (int c0 = 0; c0 < ld; c0 += 32) {
+                const int c = c0 + lane;
+                const bool in = c < ld;
+                const double f = in ? fu_d[c] : 0.0;
+                const double g = in ? (g_d[c] - s_sumF[c]) + f : 0.0;
+                if (in) g_d[c] = g;
+                G2 = fma(g, g, G2);
+                const bool act = in && (f > 0.0 || g > 0.0);
+                const unsigned bal = __ballot_sync(0xffffffffu, act);
+                if (act) {
+                    aidx[m + __popc(bal & lt_mask)] = (unsigned short)c;
+                    hi_lane |= (f + g > max_f);
+                }
+                m += __popc(bal);
+            }
+            G2 = warp_sum(G2);
+            const bool need_hi = __any_sync(0xffffffffu, hi_lane);
+            __syncwarp();
+
+            // ---------------- LS (:172-182) ----------------
+            const int j16 = lane & 15, h = lane >> 4;
+            for (int tg = 0; tg < nsteps && jstar < 0; tg += 16) {
+                const int j = tg + j16;
+                const bool jok = j < nsteps;
+                const double s = s_steps[jok ? j : 0];
+                double sumterms = 0.0;
+                for (int cb = 0; cb < deg;) {
+                    // a node whose neighbours fitted one chunk still has them staged from PRE
+                    const int ne = (nchunks == 1 && tg == 0)
+                                       ? ne_last
+                                       : sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, deg - cb), lane, ent_val, ent_idx, poff);
+#pragma unroll 1
+                    for (int e2 = 0; e2 < ne; e2 += 4) {
+                        const int eA = e2 + h, eB = e2 + 2 + h;
+                        const bool vA = eA < ne, vB = eB < ne;
+                        const int iA = vA ? (int)poff[eA] : 0, nA = vA ? (int)poff[eA + 1] - iA : 0;
+                        const int iB = vB ? (int)poff[eB] : 0, nB = vB ? (int)poff[eB + 1] - iB : 0;
+                        const int nmax = max(nA, nB);
+                        double DA = 0.0, DB = 0.0;
+#pragma unroll 1
+                        for (int k = 0; k < nmax; ++k) {
+                            const bool ka = k < nA, kb = k < nB;
+                            const int ca = ka ? (int)ent_idx[iA + k] : 0, cb2 = kb ? (int)ent_idx[iB + k] : 0;
+                            const double pa = ka ? ent_val[iA + k] : 0.0, pb = kb ? ent_val[iB + k] : 0.0;
+                            const double fa = fu_d[ca], ga = g_d[ca], fb = fu_d[cb2], gb = g_d[cb2];
+                            if (need_hi) {
+                                DA = fma(clamp_step0(fa, s, ga, max_f), pa, DA);
+                                DB = fma(clamp_step0(fb, s, gb, max_f), pb, DB);
+                            } else {
+                                DA = fma(clamp_step0_lo(fa, s, ga), pa, DA);
+                                DB = fma(clamp_step0_lo(fb, s, gb), pb, DB);
+                            }
+                        }
+                        double tA, tB;
+                        edge_term2(DA, DB, ec, tA, tB);
+                        sumterms += vA ? tA : 0.0;
+                        sumterms += vB ? tB : 0.0;
+                    }
+                    __syncwarp();
+                    cb += ne;
+                }
+                sumterms += __shfl_xor_sync(0xffffffffu, sumterms, 16);
+                // - newfu.sfT + newfu.newfu with sfT = (sumF - fu) + newfu   (:176,:180)
+                double oa = 0.0, ob = 0.0;
+                for (int t = h; t < m; t += 2) {
+                    const int c = aidx[t];
+                    const double f = fu_d[c], g = g_d[c];
+                    const double nf = need_hi ? clamp_step0(f, s, g, max_f) : clamp_step0_lo(f, s, g);
+                    const double sf = (s_sumF[c] - f) + nf;
+                    oa = fma(nf, sf, oa);
+                    ob = fma(nf, nf, ob);
+                }
+                oa += __shfl_xor_sync(0xffffffffu, oa, 16);
+                ob += __shfl_xor_sync(0xffffffffu, ob, 16);
+                const double result = (sumterms - oa) + ob;
+                const double rhs = llh_u + (a.alpha * s) * G2;
+                const unsigned pass = __ballot_sync(0xffffffffu, jok && (result >= rhs)) & 0xffffu;
+                if (pass) jstar = tg + __ffs(pass) - 1;   // lowest j == largest step (:182 max)
+            }
+        }
+
+        // ---------------- SWAP (:183-190): the new row goes to the output pool ----------------
+        if (a.do_linesearch) {
+            int cnt_new = 0;
+            if (jstar >= 0) {
+                const double s = s_steps[jstar];
+                for (int t0 = 0; t0 < m; t0 += 32) {
+                    const int t = t0 + lane;
+                    const bool ok = t < m;
+                    const int c = ok ? (int)aidx[t] : 0;
+                    const double f = fu_d[c], g = g_d[c];
+                    const double nr = clamp_step(f, s, g, a.min_f, max_f);
+                    const bool nz = ok && (nr != 0.0);
+                    const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                    if (nz) {
+                        const int p = cnt_new + __popc(bal & lt_mask);
+                        ent_val[p] = nr;
+                        ent_idx[p] = (unsigned short)c;
+                    }
+                    if (ok && f != nr) atomicAdd(s_D + c, f - nr);       // :191-192, sum over accepted nodes of old - new
+                    cnt_new += __popc(bal);
+                }
+                nupd_acc += 1.0;
+            } else {
+                for (int i = lane; i < cu; i += 32) {
+                    ent_val[i] = __ldg(uval + i);
+                    ent_idx[i] = __ldg(uidx + i);
+                }
+                cnt_new = cu;
+            }
+            __syncwarp();
+            const unsigned long long words = sp_words((uint32_t)cnt_new);
+            unsigned long long off = 0;
+            if (lane == 0 && cnt_new > 0) off = atomicAdd(sp.pool_top, words);
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (off + words > sp.pool_cap8) {
+                if (lane == 0) { *sp.overflow = 1; sp.hdr_out[u] = sp_pack(0, 0); }
+            } else {
+                double *ov = sp.pool_out + off;
+                unsigned short *oi = reinterpret_cast<unsigned short *>(ov + sp_pad((uint32_t)cnt_new));
+                for (int i = lane; i < cnt_new; i += 32) {
+                    ov[i] = ent_val[i];
+                    oi[i] = ent_idx[i];
+                }
+                if (lane == 0) sp.hdr_out[u] = sp_pack(off, (uint32_t)cnt_new);
+            }
+        }
+        if (a.accepted != nullptr && lane == 0) a.accepted[u] = (int8_t)jstar;
+
+        // ---- leave the warp's dense vectors at zero for the next node ----
+        __syncwarp();
+        for (int i = lane; i < cu; i += 32) fu_d[__ldg(uidx + i)] = 0.0;
+        if (want_ls)
+            for (int c = lane; c < ld; c += 32) g_d[c] = 0.0;
+        __syncwarp();
+
+        cur = nxt;
+        nxt = nn;
+        pos = pos_n;
+        pos_n = pos_nn;
+        pos_nn = (int64_t)__shfl_sync(0xffffffffu, fetched, 0);
+    }
+
+    // ---------------- block reduction of the partials ----------------
+    __syncthreads();
+    if (a.do_linesearch) {
+        for (int i = threadIdx.x; i < ld; i += kSpThreads) {
+            const double v = s_D[i];
+            if (v != 0.0) atomicAdd(a.partials + i, v);
+        }
+    }
+    __shared__ double s_red[2 * kSpWarps];
+    if (lane == 0) { s_red[wib] = llh_acc; s_red[kSpWarps + wib] = nupd_acc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double l = 0.0, c = 0.0;
+#pragma unroll
+        for (int w = 0; w < kSpWarps; ++w) { l += s_red[w]; c += s_red[kSpWarps + w]; }
+        atomicAdd(a.partials + 2 * ld, l);
+        if (c != 0.0) atomicAdd(a.partials + 2 * ld + 1, c);
+    }
+}
+
+// Dense n x ld rows -> sparse rows (one warp per row; non-zeros in ascending component order).
+__global__ void dense_to_sparse_kernel(const double *F, int64_t n, int ld, uint64_t *hdr, double *pool,
+                                       unsigned long long *pool_top, uint64_t pool_cap8, int32_t *overflow) {
+    const int lane = threadIdx.x & 31;
+    const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= n) return;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const double *row = F + (size_t)u * ld;
+    int cnt = 0;
+    for (int c0 = 0; c0 < ld; c0 += 32) {
+        const int c = c0 + lane;
+        cnt += __popc(__ballot_sync(0xffffffffu, c < ld && row[c] != 0.0));
+    }
+    const unsigned long long words = sp_words((uint32_t)cnt);
+    unsigned long long off = 0;
+    if (lane == 0 && cnt > 0) off = atomicAdd(pool_top, words);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (off + words > pool_cap8) {
+        if (lane == 0) { *overflow = 1; hdr[u] = sp_pack(0, 0); }
+        return;
+    }
+    double *ov = pool + off;
+    unsigned short *oi = reinterpret_cast<unsigned short *>(ov + sp_pad((uint32_t)cnt));
+    int p = 0;
+    for (int c0 = 0; c0 < ld; c0 += 32) {
+        const int c = c0 + lane;
+        const double v = (c < ld) ? row[c] : 0.0;
+        const unsigned bal = __ballot_sync(0xffffffffu, v != 0.0);
+        if (v != 0.0) {
+            const int q = p + __popc(bal & lt_mask);
+            ov[q] = v;
+            oi[q] = (unsigned short)c;
+        }
+        p += __popc(bal);
+    }
+    if (lane == 0) hdr[u] = sp_pack(off, (uint32_t)cnt);
+}
+
+// Sparse rows -> dense n x ld (rows are zeroed here, no separate memset).
+__global__ void sparse_to_dense_kernel(const uint64_t *hdr, const double *pool, int64_t n, int ld, double *F) {
+    const int lane = threadIdx.x & 31;
+    const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= n) return;
+    double *row = F + (size_t)u * ld;
+    for (int c = lane; c < ld; c += 32) row[c] = 0.0;
+    __syncwarp();
+    const uint64_t h = hdr[u];
+    const int cnt = (int)sp_cnt(h);
+    const double *vals = pool + sp_off8(h);
+    const unsigned short *idx = reinterpret_cast<const unsigned short *>(vals + sp_pad((uint32_t)cnt));
+    for (int i = lane; i < cnt; i += 32) row[idx[i]] = vals[i];
+}
+
+}  // namespace bigclam

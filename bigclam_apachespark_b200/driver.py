@@ -79,12 +79,15 @@ class BigClam:
 
     def __init__(self, numCore: int = 36, minCom: int = 1000, maxCom: int = 9000, divCom: int = 100,
                  alpha: float = 0.05, beta: float = 0.1, MaxInter: int = 15, device: int = -1,
-                 time_kernels: bool = False, record_accepted: bool = False, verbose: bool = False):
+                 time_kernels: bool = False, record_accepted: bool = False, verbose: bool = False,
+                 sparse_rows: bool = False):
         self.numCore, self.minCom, self.maxCom, self.divCom = numCore, minCom, maxCom, divCom
         self.alpha, self.beta, self.MaxInter = alpha, beta, MaxInter
         self.MIN_P_, self.MAX_P_, self.MIN_F_, self.MAX_F_ = 0.0001, 0.9999, 0.0, 1000.0   # :40-43
         self.device = device
         self.flags = (_lib.F_TIME_KERNELS if time_kernels else 0) | (_lib.F_RECORD_ACCEPTED if record_accepted else 0)
+        if sparse_rows:       # F as sparse rows on the device (the reference's BSV[Double]); K <= 256, one GPU
+            self.flags |= _lib.F_SPARSE_ROWS
         self.verbose = verbose
         self.K = None
         self.rowptr = self.col = self.ids = None

@@ -54,6 +54,9 @@ typedef struct {
 
 #define BIGCLAM_F_TIME_KERNELS   1   /* record CUDA events around every step-kernel launch */
 #define BIGCLAM_F_RECORD_ACCEPTED 2  /* keep the accepted step index per node (diagnostics/tests) */
+#define BIGCLAM_F_SPARSE_ROWS     4  /* keep F as sparse rows on the device (like the reference's BSV[Double],
+                                        bigclam4-7.scala:97-104): k <= 256, min_f == 0, single GPU.  The C ABI stays
+                                        dense (bigclam_set_F / bigclam_get_F convert on the device). */
 
 /* Fills *p with the reference's constants for a given K. */
 int bigclam_default_params(bigclam_params *p, int32_t k);
