@@ -151,7 +151,11 @@ __device__ __forceinline__ double exp_neg(double x) {
 // 1/d for normal positive d: rcp.approx (2^-23) + two Newton steps.
 __device__ __forceinline__ double rcp_pos(double d) {
     double y;
+#ifdef BIGCLAM_EMU          // host emulation of the kernels (tests/emu): no PTX, same accuracy class of the seed
+    y = (double)(1.0f / (float)d);
+#else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#endif
     double e = fma(-d, y, 1.0);
     y = fma(y, e, y);
     e = fma(-d, y, 1.0);
@@ -251,10 +255,17 @@ __device__ __forceinline__ double clamp_step0_lo(double f, double s, double g) {
 
 // cp.async staging of up to 4 neighbour rows (edges first .. first+3 of the id register `ids`) into the
 // warp's shared-memory row buffer; lane l copies the same 16-byte chunks it later reads back.
+#ifdef BIGCLAM_EMU          // host emulation (tests/emu): the copy happens at once
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+__device__ __forceinline__ void cp_async_wait_all() {}
+#else
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
 template <int C2, int RB>
 __device__ __forceinline__ void stage_rows(double *buf, const double *__restrict__ F, int ld, int ld2, int lane,
                                            int ids, int first, int cnt) {
@@ -271,7 +282,7 @@ __device__ __forceinline__ void stage_rows(double *buf, const double *__restrict
             }
         }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    cp_async_commit();
 }
 
 // Transposed butterfly over RB per-lane partials (RB = 4, 2 or 1): afterwards the lanes of group

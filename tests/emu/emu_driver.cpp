@@ -1,0 +1,122 @@
+// emu_driver.cpp — TEST INFRASTRUCTURE ONLY (see include/cuda_emu.h): runs the kernel source of
+// csrc/bigclam_sparse.cuh / csrc/bigclam_kernels.cuh on the host for tests/test_emu_kernels.py.
+#include <algorithm>
+#include <cstdio>
+#include <numeric>
+
+#include "bigclam_sparse.cuh"        // the transformed copies made by build.sh (includes bigclam_kernels.cuh)
+
+thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+namespace emu {
+thread_local WarpCtx *warp = nullptr;
+thread_local BlockCtx *block = nullptr;
+thread_local int lane = 0;
+unsigned char *g_dyn_smem = nullptr;
+}  // namespace emu
+
+using namespace bigclam;
+
+namespace {
+struct Problem {
+    int64_t n;
+    int32_t k, ld, nsteps;
+    std::vector<NodeMeta> meta;
+    std::vector<double> F, sumF, partials;
+    std::vector<int8_t> accepted;
+    StepArgs a;
+};
+
+// mirrors fill_args / rebuild_order_list of csrc/bigclam_capi.cu
+void setup(Problem &P, int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in, const double *sumF,
+           const uint8_t *mask, int do_linesearch, int max_inter, double alpha, double beta, unsigned *work_counter,
+           unsigned init_positions) {
+    P.n = n;
+    P.k = k;
+    P.ld = (k + 3) & ~3;
+    P.nsteps = max_inter + 1;
+    const int ld = P.ld;
+    P.F.assign((size_t)n * ld, 0.0);
+    for (int64_t u = 0; u < n; ++u) std::copy(F_in + u * k, F_in + (u + 1) * k, P.F.begin() + u * ld);
+    P.sumF.assign(ld, 0.0);
+    std::copy(sumF, sumF + k, P.sumF.begin());
+    P.partials.assign(2 * ld + 2, 0.0);
+    P.accepted.assign(n, -1);
+    std::vector<int32_t> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int32_t x, int32_t y) { return (rowptr[x + 1] - rowptr[x]) > (rowptr[y + 1] - rowptr[y]); });
+    P.meta.resize(n);
+    for (int64_t i = 0; i < n; ++i) P.meta[i] = NodeMeta{order[i], (int32_t)(rowptr[order[i] + 1] - rowptr[order[i]]), rowptr[order[i]]};
+    StepArgs &a = P.a;
+    std::memset(&a, 0, sizeof(a));
+    a.n = n;
+    a.rowptr = rowptr;
+    a.col = col;
+    a.sumF = P.sumF.data();
+    a.k = k;
+    a.ld = ld;
+    a.nsteps = P.nsteps;
+    double s = 1.0;
+    a.steps[0] = s;
+    for (int i = 1; i <= max_inter; ++i) { s *= beta; a.steps[i] = s; }
+    a.alpha = alpha;
+    a.min_p = 0.0001; a.max_p = 0.9999; a.min_f = 0.0; a.max_f = 1000.0;
+    a.x_lo = -std::log(a.max_p) * (1.0 - 1e-12);
+    a.x_hi = -std::log(a.min_p) * (1.0 + 1e-12);
+    a.t_lo = std::log(1.0 - a.max_p);
+    a.t_hi = std::log(1.0 - a.min_p);
+    a.w_lo = 1.0 / (1.0 - a.max_p);
+    a.w_hi = 1.0 / (1.0 - a.min_p);
+    a.meta = P.meta.data();
+    a.order_n = n;
+    a.maxm = std::min<int32_t>(ld, kMaxActiveCap);
+    *work_counter = init_positions;
+    a.work_counter = work_counter;
+    a.node_mask = mask;
+    a.partials = P.partials.data();
+    a.accepted = P.accepted.data();
+    a.do_linesearch = do_linesearch;
+}
+}  // namespace
+
+// One step over sparse rows: dense F_in -> dense_to_sparse_kernel -> sparse_step_kernel -> sparse_to_dense_kernel.
+// partials_out: [D(ld) | unused(ld) | llh | n_updated] as in the library.
+extern "C" int emu_sparse_step(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
+                               const double *sumF, const uint8_t *mask, int do_linesearch, int max_inter, double alpha,
+                               double beta, int grid, double *F_out, double *partials_out, int8_t *accepted_out,
+                               int64_t *pool_words_out) {
+    Problem P;
+    unsigned work = 0;
+    setup(P, n, rowptr, col, k, F_in, sumF, mask, do_linesearch, max_inter, alpha, beta, &work, 3u * (unsigned)grid * kSpWarps);
+    const int ld = P.ld;
+    if (ld > 256) return -1;
+    const uint64_t cap8 = (uint64_t)n * sp_words((uint32_t)ld);
+    std::vector<uint64_t> hdr0(n, 0), hdr1(n, 0);
+    std::vector<double> pool0(cap8 + 8, 0.0), pool1(cap8 + 8, 0.0);
+    unsigned long long top[2] = {0, 0};
+    int32_t overflow = 0;
+    emu::launch(dense_to_sparse_kernel, (unsigned)((n + 7) / 8), 256u, (size_t)0, (const double *)P.F.data(), n, ld, hdr0.data(),
+                pool0.data(), &top[0], cap8, &overflow);
+    SparseArgs sp;
+    sp.hdr_in = hdr0.data();
+    sp.pool_in = pool0.data();
+    sp.hdr_out = hdr1.data();
+    sp.pool_out = pool1.data();
+    sp.pool_top = &top[1];
+    sp.pool_cap8 = cap8;
+    sp.overflow = &overflow;
+    P.a.F_in = P.F.data();
+    P.a.F_out = nullptr;
+    emu::launch(sparse_step_kernel, (unsigned)grid, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
+    std::vector<double> Fo((size_t)n * ld, 0.0);
+    if (do_linesearch)
+        emu::launch(sparse_to_dense_kernel, (unsigned)((n + 7) / 8), 256u, (size_t)0, (const uint64_t *)hdr1.data(),
+                    (const double *)pool1.data(), n, ld, Fo.data());
+    else
+        Fo = P.F;
+    for (int64_t u = 0; u < n; ++u) std::copy(Fo.begin() + u * ld, Fo.begin() + u * ld + k, F_out + u * k);
+    std::copy(P.partials.begin(), P.partials.end(), partials_out);
+    std::copy(P.accepted.begin(), P.accepted.end(), accepted_out);
+    if (pool_words_out) *pool_words_out = (int64_t)top[1];
+    return overflow ? -2 : 0;
+}

@@ -1,0 +1,161 @@
+// cuda_emu.h — TEST INFRASTRUCTURE ONLY.  A minimal SIMT emulation that lets tests/ run the *kernel source* of
+// csrc/*.cuh on the host, one OS thread per CUDA thread, so that kernel logic can be checked against the oracle
+// in a container without a GPU.  It is never linked into libbigclam_b200.so and nothing in the package can
+// reach it: the product has no CPU path.
+//
+//   * a warp = 32 threads sharing a pthread barrier and a 32-slot exchange buffer: __shfl*_sync, __ballot_sync,
+//     __any_sync and __syncwarp are barrier rounds, so a collective reached by only part of a warp (a bug on
+//     the GPU as well) shows up here as a hang -> run under a timeout;
+//   * a block = its warps plus one more barrier (__syncthreads); blocks run one after the other (fine for
+//     kernels without inter-block waits);
+//   * `extern __shared__` / `__shared__` are rewritten by tests/emu/build.sh (dynamic -> emu::dyn_smem(),
+//     static -> function-local static);
+//   * inline PTX is replaced in the kernel headers under #ifdef BIGCLAM_EMU.
+#pragma once
+#include <pthread.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <type_traits>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+extern thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+struct alignas(16) double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+
+namespace emu {
+struct WarpCtx {
+    pthread_barrier_t bar;
+    uint64_t slot[32];
+};
+struct BlockCtx {
+    pthread_barrier_t bar;
+};
+extern thread_local WarpCtx *warp;
+extern thread_local BlockCtx *block;
+extern thread_local int lane;
+extern unsigned char *g_dyn_smem;
+inline unsigned char *dyn_smem() { return g_dyn_smem; }
+inline void wsync() { pthread_barrier_wait(&warp->bar); }
+template <class T>
+inline T exch(T v, int src) {
+    static_assert(sizeof(T) <= 8, "emulated shuffles move at most 8 bytes");
+    uint64_t u = 0;
+    std::memcpy(&u, &v, sizeof(T));
+    warp->slot[lane] = u;
+    wsync();
+    const uint64_t r = warp->slot[src & 31];
+    wsync();
+    T out;
+    std::memcpy(&out, &r, sizeof(T));
+    return out;
+}
+}  // namespace emu
+
+template <class T> inline T __shfl_sync(unsigned, T v, int src, int = 32) { return emu::exch(v, src); }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return emu::exch(v, emu::lane ^ m); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) {
+    const int src = emu::lane - (int)d;
+    return emu::exch(v, src < 0 ? emu::lane : src);
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+    emu::warp->slot[emu::lane] = pred ? 1u : 0u;
+    emu::wsync();
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i) m |= (unsigned)emu::warp->slot[i] << i;
+    emu::wsync();
+    return m;
+}
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::wsync(); }
+inline void __syncthreads() { pthread_barrier_wait(&emu::block->bar); }
+
+inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline double atomicAdd(double *p, double v) {
+    uint64_t *q = reinterpret_cast<uint64_t *>(p);
+    uint64_t old = __atomic_load_n(q, __ATOMIC_SEQ_CST);
+    for (;;) {
+        double d;
+        std::memcpy(&d, &old, 8);
+        d += v;
+        uint64_t nu;
+        std::memcpy(&nu, &d, 8);
+        if (__atomic_compare_exchange_n(q, &old, nu, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+            double r;
+            std::memcpy(&r, &old, 8);
+            return r;
+        }
+    }
+}
+
+template <class T> inline T __ldg(const T *p) { return *p; }
+template <class T> inline T __ldcg(const T *p) { return *p; }
+inline int __double2hiint(double d) { int64_t u; std::memcpy(&u, &d, 8); return (int)(u >> 32); }
+inline int __double2loint(double d) { int64_t u; std::memcpy(&u, &d, 8); return (int)(u & 0xffffffff); }
+inline double __hiloint2double(int hi, int lo) {
+    const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double d;
+    std::memcpy(&d, &u, 8);
+    return d;
+}
+inline double __dadd_rn(double a, double b) { return a + b; }     // build with -ffp-contract=off
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline void __nanosleep(unsigned) {}
+inline void __threadfence() { __sync_synchronize(); }
+using std::fma;
+
+template <class A, class B> inline std::common_type_t<A, B> min(A a, B b) {
+    using T = std::common_type_t<A, B>;
+    return (T)a < (T)b ? (T)a : (T)b;
+}
+template <class A, class B> inline std::common_type_t<A, B> max(A a, B b) {
+    using T = std::common_type_t<A, B>;
+    return (T)a > (T)b ? (T)a : (T)b;
+}
+
+namespace emu {
+// <<<grid, block, smem>>> : blocks one after the other, `block` OS threads each
+template <class K, class... A>
+inline void launch(K kernel, unsigned grid, unsigned block, size_t smem, A... args) {
+    for (unsigned b = 0; b < grid; ++b) {
+        std::vector<unsigned char> sm(smem + 64);
+        g_dyn_smem = reinterpret_cast<unsigned char *>(((uintptr_t)sm.data() + 63) & ~(uintptr_t)63);
+        BlockCtx bc;
+        pthread_barrier_init(&bc.bar, nullptr, block);
+        const unsigned nw = (block + 31) / 32;
+        std::vector<WarpCtx> wc(nw);
+        for (unsigned w = 0; w < nw; ++w) pthread_barrier_init(&wc[w].bar, nullptr, std::min(32u, block - 32 * w));
+        std::vector<std::thread> th;
+        th.reserve(block);
+        for (unsigned t = 0; t < block; ++t)
+            th.emplace_back([=, &bc, &wc]() {
+                threadIdx.x = t;
+                blockIdx.x = b;
+                blockDim.x = block;
+                gridDim.x = grid;
+                lane = (int)(t & 31);
+                warp = &wc[t / 32];
+                emu::block = &bc;
+                kernel(args...);
+            });
+        for (auto &x : th) x.join();
+        for (unsigned w = 0; w < nw; ++w) pthread_barrier_destroy(&wc[w].bar);
+        pthread_barrier_destroy(&bc.bar);
+    }
+}
+}  // namespace emu

@@ -1,0 +1,110 @@
+"""Kernel LOGIC on the CPU: the source of csrc/bigclam_sparse.cuh compiled for the host against the SIMT
+emulation in tests/emu (one OS thread per CUDA thread, warp collectives as barrier rounds) and checked against
+the oracle.  Test infrastructure only — nothing here is reachable from the package, which has no CPU path; the
+`-m gpu` tests remain the parity tests of the compiled sm_100a code."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import random_graph, tiny_graph
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run([os.path.join(HERE, "emu", "build.sh")], check=True)
+    lib = C.CDLL(os.path.join(HERE, "emu", "libemu.so"))
+    lib.emu_sparse_step.restype = C.c_int
+    lib.emu_sparse_step.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.POINTER(C.c_int64)]
+    return lib
+
+
+def sparse_step(lib, rp, col, F, sumF, mask=None, linesearch=True, grid=1):
+    n, k = F.shape
+    ld = (k + 3) & ~3
+    rp = np.ascontiguousarray(rp, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    F = np.ascontiguousarray(F, dtype=np.float64)
+    sumF = np.ascontiguousarray(sumF, dtype=np.float64)
+    Fo = np.empty_like(F)
+    partials = np.zeros(2 * ld + 2)
+    acc = np.empty(n, dtype=np.int8)
+    words = C.c_int64(0)
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+    rc = lib.emu_sparse_step(n, rp.ctypes.data, col.ctypes.data, k, F.ctypes.data, sumF.ctypes.data,
+                             None if m is None else m.ctypes.data, 1 if linesearch else 0, 15, 0.05, 0.1, grid,
+                             Fo.ctypes.data, partials.ctypes.data, acc.ctypes.data, C.byref(words))
+    assert rc == 0
+    D, llh_pre, nupd = partials[:k], partials[2 * ld], int(round(partials[2 * ld + 1]))
+    return Fo, sumF - D if nupd else sumF.copy(), llh_pre, nupd, acc, words.value
+
+
+def check(F, s, llh_pre, nupd, acc, r, oracle_llh_pre, max_flips=0):
+    scale = max(np.abs(r.F).max(), 1e-300)
+    row_err = np.abs(F - r.F).max(axis=1)
+    flipped = row_err > 1e-9 * scale
+    assert int(flipped.sum()) <= max_flips, (int(flipped.sum()), row_err.max())
+    d = (acc != r.accepted) & ~flipped
+    assert (((acc[d] < 0) | (acc[d] >= 12)) & ((r.accepted[d] < 0) | (r.accepted[d] >= 12))).all()
+    assert abs(llh_pre - oracle_llh_pre) <= 1e-10 * abs(oracle_llh_pre)
+    if not flipped.any():
+        assert np.allclose(s, r.sumF, rtol=1e-11, atol=1e-9)
+        if not d.any():
+            assert nupd == r.n_updated
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("k,grid", [(5, 1), (12, 2), (40, 1), (200, 1)])
+def test_sparse_kernel_source_against_oracle(emu, oracle, k, grid):
+    n = 96
+    rp, col = random_graph(n, 5, seed=k, hub=40)
+    rng = np.random.default_rng(k)
+    F = rng.random((n, k)) * (rng.random((n, k)) < min(1.0, 6.0 / k + 0.05))
+    sumF = oracle.colsum(F)
+    P = oracle.make_params(k)
+    for it in range(2):
+        r = oracle.step(rp, col, F, sumF, P)
+        Fo, so, llh_pre, nupd, acc, words = sparse_step(emu, rp, col, F, sumF, grid=grid)
+        check(Fo, so, llh_pre, nupd, acc, r, oracle.llh(rp, col, F, sumF, P))
+        nnz = (Fo != 0).sum(axis=1)
+        assert words == int((((nnz + 3) // 4) * 5).sum())          # the pool holds exactly the padded row blocks
+        F, sumF = r.F, r.sumF
+
+
+@pytest.mark.timeout(600)
+def test_sparse_kernel_source_mask_llh_only_and_isolated(emu, oracle, graphs):
+    rp, col = tiny_graph(graphs)                                 # nodes 10, 11 have no neighbours
+    n, k = len(rp) - 1, 5
+    rng = np.random.default_rng(1)
+    F = rng.random((n, k)) * (rng.random((n, k)) < 0.6)
+    sumF = oracle.colsum(F)
+    P = oracle.make_params(k)
+    mask = np.array([1, 0, 1, 1, 0, 1, 1, 0, 1, 1, 1, 0], dtype=np.uint8)
+    r = oracle.step(rp, col, F, sumF, P, node_mask=mask)
+    Fo, so, llh_pre, nupd, acc, _ = sparse_step(emu, rp, col, F, sumF, mask=mask)
+    check(Fo, so, llh_pre, nupd, acc, r, oracle.llh(rp, col, F, sumF, P))
+    assert np.array_equal(Fo[mask == 0], F[mask == 0]) and np.array_equal(Fo[10:], F[10:])
+    Fo, so, llh_pre, nupd, acc, _ = sparse_step(emu, rp, col, F, sumF, linesearch=False)
+    assert np.array_equal(Fo, F) and nupd == 0
+    assert abs(llh_pre - oracle.llh(rp, col, F, sumF, P)) <= 1e-10 * abs(llh_pre)
+
+
+@pytest.mark.timeout(900)
+def test_sparse_kernel_source_dense_rows_and_chunking(emu, oracle):
+    """Full rows (K = 200 non-zeros: two rows per staged chunk) and a hub whose neighbour list spans chunks."""
+    n, k = 60, 200
+    rp, col = random_graph(n, 4, seed=9, hub=45)
+    rng = np.random.default_rng(9)
+    F = rng.random((n, k)) * 0.1
+    F[::2] *= (rng.random((n // 2, k)) < 0.05)
+    sumF = oracle.colsum(F)
+    P = oracle.make_params(k)
+    r = oracle.step(rp, col, F, sumF, P)
+    Fo, so, llh_pre, nupd, acc, _ = sparse_step(emu, rp, col, F, sumF)
+    check(Fo, so, llh_pre, nupd, acc, r, oracle.llh(rp, col, F, sumF, P), max_flips=1)
