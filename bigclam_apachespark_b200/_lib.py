@@ -85,6 +85,8 @@ SIGNATURES = {
     "bigclam_ipc_export": (C.c_int, [_vp, _vp]),
     "bigclam_ipc_open_peers": (C.c_int, [_vp, _i32, _i32, _vp]),
     "bigclam_mark_all_changed": (C.c_int, [_vp]),
+    "bigclam_ipc_handle_count": (C.c_int, [_vp]),
+    "bigclam_set_pool_region": (C.c_int, [_vp, _i64, _i64]),
     "bigclam_graph_read_edgelist": (C.c_int, [C.c_char_p, _i32, C.POINTER(Graph), C.c_char_p, _i64]),
     "bigclam_graph_free": (None, [C.POINTER(Graph)]),
     "bigclam_extract": (C.c_int, [_vp, _dbl, _vp, _vp]),

@@ -79,6 +79,9 @@ struct bigclam_ctx {
     int sp_grid = 0;
     size_t sp_smem = 0;
     bool dense_valid = true;       // d_F[cur] mirrors the sparse state (set_F; refreshed on demand by ensure_dense)
+    uint64_t region_base8 = 0, region_cap8 = 0;   // this rank's part of every replica's output pool (multi-GPU)
+    uint64_t *peer_hdr[2][7] = {{nullptr}};       // peers' headers / pools (both halves), IPC-mapped
+    double *peer_pool[2][7] = {{nullptr}};
 
     std::string err;
 };
@@ -160,8 +163,11 @@ static void free_ctx(bigclam_ctx *c) {
     cudaFree(c->d_partials); cudaFree(c->d_accepted); cudaFree(c->d_accepted_spec); cudaFree(c->d_mask);
     cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_hub_items); cudaFree(c->d_hub_scratch); cudaFree(c->d_hub_counters); cudaFree(c->d_changed);
     for (int h = 0; h < 2; ++h)
-        for (int r = 0; r < c->n_peers; ++r)
+        for (int r = 0; r < c->n_peers; ++r) {
             if (c->peer_F[h][r]) cudaIpcCloseMemHandle(c->peer_F[h][r]);
+            if (c->peer_hdr[h][r]) cudaIpcCloseMemHandle(c->peer_hdr[h][r]);
+            if (c->peer_pool[h][r]) cudaIpcCloseMemHandle(c->peer_pool[h][r]);
+        }
     cudaFree(c->d_state); cudaFree(c->d_trace);
     cudaFree(c->d_hdr[0]); cudaFree(c->d_hdr[1]); cudaFree(c->d_pool[0]); cudaFree(c->d_pool[1]);
     cudaFree(c->d_pool_top); cudaFree(c->d_overflow);
@@ -395,8 +401,9 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
         ctx->sparse = true;
         ctx->sp_smem = sp_block_smem_bytes(ld);
         int sbps = 0;
-        CUC(cudaFuncSetAttribute(sparse_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
-        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sbps, sparse_step_kernel, kSpThreads, ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(sparse_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(sparse_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sbps, sparse_step_kernel<true>, kSpThreads, ctx->sp_smem));
         if (sbps <= 0) {
             fail(nullptr, BIGCLAM_ECUDA, "bigclam_create: sparse kernel does not fit an SM (smem %zu B)", ctx->sp_smem);
             free_ctx(ctx);
@@ -437,6 +444,8 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     if (ctx->sparse) {
         // worst case: every row full (ld entries) — a step can then never overflow its pool
         ctx->pool_cap8 = (uint64_t)n * sp_words((uint32_t)ld);
+        ctx->region_base8 = 0;
+        ctx->region_cap8 = ctx->pool_cap8;
         for (int b = 0; b < 2; ++b) {
             CUC(cudaMalloc(&ctx->d_hdr[b], sizeof(uint64_t) * (size_t)n));
             CUC(cudaMemset(ctx->d_hdr[b], 0, sizeof(uint64_t) * (size_t)n));
@@ -658,13 +667,20 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
         sp.hdr_out = ctx->d_hdr[out];
         sp.pool_out = ctx->d_pool[out];
         sp.pool_top = ctx->d_pool_top + out;
-        sp.pool_cap8 = ctx->pool_cap8;
+        sp.pool_cap8 = ctx->region_cap8;
+        sp.region_base8 = ctx->region_base8;
         sp.overflow = ctx->d_overflow;
+        sp.n_peers = a.do_linesearch ? ctx->n_peers : 0;
+        for (int r = 0; r < 7; ++r) {
+            sp.peer_hdr[r] = (r < ctx->n_peers) ? ctx->peer_hdr[out][r] : nullptr;
+            sp.peer_pool[r] = (r < ctx->n_peers) ? ctx->peer_pool[out][r] : nullptr;
+        }
         if (a.do_linesearch) {
             CU(cudaMemsetAsync(sp.pool_top, 0, sizeof(unsigned long long), ctx->stream));
             ctx->dense_valid = false;
         }
-        sparse_step_kernel<<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
+        if (sp.n_peers > 0) sparse_step_kernel<true><<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else sparse_step_kernel<false><<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
     } else {
         launch_step(ctx->c2, a, ctx->grid, ctx->smem_bytes, ctx->stream);
     }
@@ -880,7 +896,6 @@ extern "C" int bigclam_get_kernel_time(bigclam_ctx *ctx, double *step_kernel_ms_
 // Node-partitioned pieces.
 extern "C" int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
-    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     if (lo < 0 || hi < lo || hi > ctx->n) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_owned_range: bad range");
     CU(cudaSetDevice(ctx->device));
     std::vector<int64_t> rp((size_t)ctx->n + 1);
@@ -893,7 +908,6 @@ extern "C" int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi)
 
 extern "C" int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
-    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     CU(cudaSetDevice(ctx->device));
     if (int rd = drop_speculation(ctx)) return rd;
     StepArgs a;
@@ -906,7 +920,6 @@ extern "C" int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev) {
 
 extern "C" int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64_t *n_updated_out) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
-    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     CU(cudaSetDevice(ctx->device));
     const bool want = (llh_pre_out != nullptr) || (n_updated_out != nullptr);
     if (want)
@@ -923,7 +936,6 @@ extern "C" int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64
 
 extern "C" int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
-    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     CU(cudaSetDevice(ctx->device));
     if (int rd = drop_speculation(ctx)) return rd;
     CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
@@ -959,12 +971,20 @@ extern "C" int bigclam_device_accepted(bigclam_ctx *ctx, void **accepted_dev) {
 // kernel pushes changed rows straight into the peers' replicas (see StepArgs::peer_out).
 extern "C" int bigclam_ipc_export(bigclam_ctx *ctx, void *handles_out /* 2 x 64 bytes */) {
     if (ctx == nullptr || handles_out == nullptr) return BIGCLAM_EINVAL;
-    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     CU(cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (ctx->sparse) {                       // 4 handles: hdr[0], hdr[1], pool[0], pool[1]
+        cudaIpcMemHandle_t h[4];
+        CU(cudaIpcGetMemHandle(&h[0], ctx->d_hdr[0]));
+        CU(cudaIpcGetMemHandle(&h[1], ctx->d_hdr[1]));
+        CU(cudaIpcGetMemHandle(&h[2], ctx->d_pool[0]));
+        CU(cudaIpcGetMemHandle(&h[3], ctx->d_pool[1]));
+        std::memcpy(handles_out, h, sizeof(h));
+        return BIGCLAM_OK;
+    }
     cudaIpcMemHandle_t h[2];
     CU(cudaIpcGetMemHandle(&h[0], ctx->d_F[0]));
     CU(cudaIpcGetMemHandle(&h[1], ctx->d_F[1]));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     std::memcpy(handles_out, h, sizeof(h));
     return BIGCLAM_OK;
 }
@@ -972,20 +992,30 @@ extern "C" int bigclam_ipc_export(bigclam_ctx *ctx, void *handles_out /* 2 x 64 
 extern "C" int bigclam_ipc_open_peers(bigclam_ctx *ctx, int32_t world, int32_t rank, const void *all_handles /* world x 2 x 64 */) {
     if (ctx == nullptr || all_handles == nullptr || world < 1 || world > 8 || rank < 0 || rank >= world)
         return fail(ctx, BIGCLAM_EINVAL, "bigclam_ipc_open_peers: bad world/rank (at most 8 GPUs)");
-    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     CU(cudaSetDevice(ctx->device));
     const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles);
     for (int half = 0; half < 2; ++half)            // a second call replaces the first mapping
-        for (int r = 0; r < ctx->n_peers; ++r)
+        for (int r = 0; r < ctx->n_peers; ++r) {
             if (ctx->peer_F[half][r]) { cudaIpcCloseMemHandle(ctx->peer_F[half][r]); ctx->peer_F[half][r] = nullptr; }
+            if (ctx->peer_hdr[half][r]) { cudaIpcCloseMemHandle(ctx->peer_hdr[half][r]); ctx->peer_hdr[half][r] = nullptr; }
+            if (ctx->peer_pool[half][r]) { cudaIpcCloseMemHandle(ctx->peer_pool[half][r]); ctx->peer_pool[half][r] = nullptr; }
+        }
     ctx->n_peers = 0;
     int np = 0;
+    const int per = ctx->sparse ? 4 : 2;            // handles per rank (bigclam_ipc_handle_count)
     for (int r = 0; r < world; ++r) {
         if (r == rank) continue;
         for (int half = 0; half < 2; ++half) {
             void *p = nullptr;
-            CU(cudaIpcOpenMemHandle(&p, h[2 * r + half], cudaIpcMemLazyEnablePeerAccess));
-            ctx->peer_F[half][np] = reinterpret_cast<double *>(p);
+            CU(cudaIpcOpenMemHandle(&p, h[per * r + half], cudaIpcMemLazyEnablePeerAccess));
+            if (ctx->sparse) {
+                ctx->peer_hdr[half][np] = reinterpret_cast<uint64_t *>(p);
+                void *q = nullptr;
+                CU(cudaIpcOpenMemHandle(&q, h[per * r + 2 + half], cudaIpcMemLazyEnablePeerAccess));
+                ctx->peer_pool[half][np] = reinterpret_cast<double *>(q);
+            } else {
+                ctx->peer_F[half][np] = reinterpret_cast<double *>(p);
+            }
         }
         ++np;
     }
@@ -1004,6 +1034,25 @@ extern "C" int bigclam_mark_all_changed(bigclam_ctx *ctx) {
     return BIGCLAM_OK;
 }
 
+// Handles per rank that bigclam_ipc_export writes and bigclam_ipc_open_peers expects (64 bytes each).
+extern "C" int bigclam_ipc_handle_count(const bigclam_ctx *ctx) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    return ctx->sparse ? 4 : 2;
+}
+
+// Sparse rows, multi-GPU: the part [base, base + cap) (8-byte words) of every replica's output pool that this
+// rank allocates its owned rows in.  The parts of the ranks must not overlap; cap >= owned nodes * words of a
+// full row can never overflow.
+extern "C" int bigclam_set_pool_region(bigclam_ctx *ctx, int64_t base_words, int64_t cap_words) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (!ctx->sparse) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_pool_region: context without BIGCLAM_F_SPARSE_ROWS");
+    if (base_words < 0 || cap_words < 0 || (uint64_t)base_words + (uint64_t)cap_words > ctx->pool_cap8)
+        return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_pool_region: region outside the pool (%llu words)", (unsigned long long)ctx->pool_cap8);
+    ctx->region_base8 = (uint64_t)base_words;
+    ctx->region_cap8 = (uint64_t)cap_words;
+    return BIGCLAM_OK;
+}
+
 // Sums the CUDA-event timings recorded since the last collection (asynchronous multi-GPU loops).
 extern "C" int bigclam_collect_timing(bigclam_ctx *ctx) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
@@ -1017,7 +1066,6 @@ extern "C" int bigclam_collect_timing(bigclam_ctx *ctx) {
 // the ranks so that every rank gets the same mix of hubs and leaves (used with the peer-store exchange).
 extern "C" int bigclam_set_owned_nodes(bigclam_ctx *ctx, const int32_t *nodes, int64_t count) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
-    if (ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "%s: not available with BIGCLAM_F_SPARSE_ROWS (single GPU, all nodes)", __func__);
     if (count < 0 || count > ctx->n || (count > 0 && nodes == nullptr))
         return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_owned_nodes: bad node list");
     for (int64_t i = 0; i < count; ++i)

@@ -27,8 +27,8 @@
 //   SWAP  the accepted candidate's non-zeros are compacted (ascending) into the staging buffer, a block is
 //         taken from the output pool, the row and its header are written.
 //
-// Limits of this first version: ld <= 256 (K <= 256), MIN_F_ == 0, single GPU (no peer pushes), no
-// block-cooperative hub phase (a hub is walked by one warp in chunks of 32 edges).
+// Limits of this first version: ld <= 256 (K <= 256), MIN_F_ == 0, no block-cooperative hub phase (a hub is
+// walked by one warp in chunks of 32 edges).
 #pragma once
 #include "bigclam_kernels.cuh"
 
@@ -49,9 +49,17 @@ struct SparseArgs {
     const double *pool_in;
     uint64_t *hdr_out;
     double *pool_out;
-    unsigned long long *pool_top;      // words used of pool_out
-    uint64_t pool_cap8;                // capacity of pool_out in words
+    unsigned long long *pool_top;      // words used of this rank's region of pool_out
+    uint64_t pool_cap8;                // capacity of that region in words
+    uint64_t region_base8;             // where the region starts in pool_out (0 on a single GPU)
     int32_t *overflow;                 // set when a row did not fit (the step must be repeated with a larger pool)
+    // node-partitioned multi-GPU: the owners' new rows go to the same offsets of every replica's output pool
+    // (plain stores to IPC-mapped peer memory over NVLink); each rank allocates only inside its own region, so
+    // all replicas end up with the same layout and no remote atomics are needed.  Every owned row is written
+    // (and pushed) every step: the output pool is rebuilt from scratch each step.
+    int32_t n_peers;
+    uint64_t *peer_hdr[7];
+    double *peer_pool[7];
 };
 
 // per-warp shared memory: fu_d[ld] | g_d[ld] | ent_val[E] | ent_idx[E] u16 | aidx[256] u16 | poff[40] u16
@@ -100,6 +108,9 @@ __device__ __noinline__ int sp_stage_chunk(const uint64_t *__restrict__ hdr_in, 
     return ne;
 }
 
+// kPush: multi-GPU launch, the peers' replicas are written too (compile-time so that the single-GPU kernel
+// carries none of that code).
+template <bool kPush>
 __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepArgs a, const SparseArgs sp) {
     if (a.done_flag != nullptr && *a.done_flag != 0) return;
 
@@ -315,19 +326,32 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
             }
             __syncwarp();
             const unsigned long long words = sp_words((uint32_t)cnt_new);
-            unsigned long long off = 0;
-            if (lane == 0 && cnt_new > 0) off = atomicAdd(sp.pool_top, words);
-            off = __shfl_sync(0xffffffffu, off, 0);
-            if (off + words > sp.pool_cap8) {
+            unsigned long long rel = 0;
+            if (lane == 0 && cnt_new > 0) rel = atomicAdd(sp.pool_top, words);
+            rel = __shfl_sync(0xffffffffu, rel, 0);
+            if (rel + words > sp.pool_cap8) {
                 if (lane == 0) { *sp.overflow = 1; sp.hdr_out[u] = sp_pack(0, 0); }
             } else {
+                const unsigned long long off = sp.region_base8 + rel;
+                const uint64_t hnew = sp_pack(off, (uint32_t)cnt_new);
                 double *ov = sp.pool_out + off;
                 unsigned short *oi = reinterpret_cast<unsigned short *>(ov + sp_pad((uint32_t)cnt_new));
                 for (int i = lane; i < cnt_new; i += 32) {
                     ov[i] = ent_val[i];
                     oi[i] = ent_idx[i];
                 }
-                if (lane == 0) sp.hdr_out[u] = sp_pack(off, (uint32_t)cnt_new);
+                if (lane == 0) sp.hdr_out[u] = hnew;
+                if (kPush) {
+                    for (int pr = 0; pr < sp.n_peers; ++pr) {
+                        double *pv = sp.peer_pool[pr] + off;
+                        unsigned short *pi = reinterpret_cast<unsigned short *>(pv + sp_pad((uint32_t)cnt_new));
+                        for (int i = lane; i < cnt_new; i += 32) {
+                            pv[i] = ent_val[i];
+                            pi[i] = ent_idx[i];
+                        }
+                        if (lane == 0) sp.peer_hdr[pr][u] = hnew;
+                    }
+                }
             }
         }
         if (a.accepted != nullptr && lane == 0) a.accepted[u] = (int8_t)jstar;

@@ -158,6 +158,15 @@ int bigclam_rollback(bigclam_ctx *ctx);
 int bigclam_ipc_export(bigclam_ctx *ctx, void *handles_out);
 int bigclam_ipc_open_peers(bigclam_ctx *ctx, int32_t world, int32_t rank, const void *all_handles);
 int bigclam_mark_all_changed(bigclam_ctx *ctx);
+/*
+ * With BIGCLAM_F_SPARSE_ROWS the replicas are (header, pool) pairs: bigclam_ipc_handle_count() handles per rank
+ * (4 instead of 2) travel through bigclam_ipc_export / bigclam_ipc_open_peers, every rank allocates its owned
+ * rows inside its own part of the output pool (bigclam_set_pool_region: disjoint parts, 8-byte words) and the
+ * step kernel writes each owned row to the same offset of every replica — all owned rows, every step (the
+ * output pool is rebuilt per step, so there is no changed-row bookkeeping).
+ */
+int bigclam_ipc_handle_count(const bigclam_ctx *ctx);
+int bigclam_set_pool_region(bigclam_ctx *ctx, int64_t base_words, int64_t cap_words);
 
 /*
  * Edge-list reader with GraphX semantics (GraphLoader.edgeListFile, bigclam4-7.scala:45;

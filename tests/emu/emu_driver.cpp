@@ -107,7 +107,9 @@ extern "C" int emu_sparse_step(int64_t n, const int64_t *rowptr, const int32_t *
     sp.overflow = &overflow;
     P.a.F_in = P.F.data();
     P.a.F_out = nullptr;
-    emu::launch(sparse_step_kernel, (unsigned)grid, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
+    sp.region_base8 = 0;
+    sp.n_peers = 0;
+    emu::launch(sparse_step_kernel<false>, (unsigned)grid, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
     std::vector<double> Fo((size_t)n * ld, 0.0);
     if (do_linesearch)
         emu::launch(sparse_to_dense_kernel, (unsigned)((n + 7) / 8), 256u, (size_t)0, (const uint64_t *)hdr1.data(),
@@ -118,5 +120,107 @@ extern "C" int emu_sparse_step(int64_t n, const int64_t *rowptr, const int32_t *
     std::copy(P.partials.begin(), P.partials.end(), partials_out);
     std::copy(P.accepted.begin(), P.accepted.end(), accepted_out);
     if (pool_words_out) *pool_words_out = (int64_t)top[1];
+    return overflow ? -2 : 0;
+}
+
+// One step of the dense kernels (step_kernel<C2, R, false, false>: no hub phase, no peer pushes), same outputs.
+template <int C2>
+static void run_dense(Problem &P, int grid) {
+    constexpr int R = RowsInFlight<C2>::value;
+    emu::launch(step_kernel<C2, R, false, false>, (unsigned)grid, (unsigned)kBlockThreads, block_smem_bytes(P.ld, P.a.maxm), P.a);
+}
+
+extern "C" int emu_dense_step(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
+                              const double *sumF, const uint8_t *mask, int do_linesearch, int max_inter, double alpha,
+                              double beta, int grid, double *F_out, double *partials_out, int8_t *accepted_out) {
+    Problem P;
+    unsigned work = 0;
+    setup(P, n, rowptr, col, k, F_in, sumF, mask, do_linesearch, max_inter, alpha, beta, &work, 3u * (unsigned)grid * kWarpsPerBlock);
+    const int ld = P.ld;
+    std::vector<double> Fo(P.F);                 // a PRE-only launch leaves F_out alone
+    P.a.F_in = P.F.data();
+    P.a.F_out = Fo.data();
+    const int c2raw = (ld / 2 + 31) / 32;
+    const int c2 = c2raw <= 1 ? 1 : c2raw <= 2 ? 2 : c2raw <= 4 ? 4 : c2raw <= 8 ? 8 : 16;
+    switch (c2) {
+        case 1: run_dense<1>(P, grid); break;
+        case 2: run_dense<2>(P, grid); break;
+        case 4: run_dense<4>(P, grid); break;
+        case 8: run_dense<8>(P, grid); break;
+        default: run_dense<16>(P, grid); break;
+    }
+    for (int64_t u = 0; u < n; ++u) std::copy(Fo.begin() + u * ld, Fo.begin() + u * ld + k, F_out + u * k);
+    std::copy(P.partials.begin(), P.partials.end(), partials_out);
+    std::copy(P.accepted.begin(), P.accepted.end(), accepted_out);
+    return 0;
+}
+
+// Node-partitioned step over sparse rows, `world` ranks emulated one after the other: every rank owns the nodes
+// order[r::world] of the degree-sorted list, allocates in its own region of the output pool and pushes its rows
+// into all replicas (sparse_step_kernel<true>).  Returns every replica's dense view of the new F
+// (F_out: world x n x k) and the summed partials.
+extern "C" int emu_sparse_step_ranks(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
+                                     const double *sumF, int max_inter, double alpha, double beta, int world,
+                                     double *F_out, double *partials_out, int8_t *accepted_out) {
+    if (world < 1 || world > 8) return -1;
+    Problem P0;
+    unsigned work = 0;
+    setup(P0, n, rowptr, col, k, F_in, sumF, nullptr, 1, max_inter, alpha, beta, &work, 3u * kSpWarps);
+    const int ld = P0.ld;
+    if (ld > 256) return -1;
+    const uint64_t cap8 = (uint64_t)n * sp_words((uint32_t)ld);
+    // one input replica is enough here (it is only read); every rank has its own output replica
+    std::vector<uint64_t> hdr_in(n, 0);
+    std::vector<double> pool_in(cap8 + 8, 0.0);
+    unsigned long long top_in = 0;
+    int32_t overflow = 0;
+    emu::launch(dense_to_sparse_kernel, (unsigned)((n + 7) / 8), 256u, (size_t)0, (const double *)P0.F.data(), n, ld, hdr_in.data(),
+                pool_in.data(), &top_in, cap8, &overflow);
+    std::vector<std::vector<uint64_t>> hdr_out(world, std::vector<uint64_t>(n, ~0ull));
+    std::vector<std::vector<double>> pool_out(world, std::vector<double>(cap8 + 8, -7.0));
+    std::vector<double> partials(2 * ld + 2, 0.0);
+    std::vector<int8_t> accepted(n, -5);
+    uint64_t base = 0;
+    for (int r = 0; r < world; ++r) {
+        std::vector<NodeMeta> mine;
+        for (int64_t i = r; i < n; i += world) mine.push_back(P0.meta[i]);        // degree-sorted list dealt round-robin
+        Problem P = P0;
+        P.a.meta = mine.data();
+        P.a.order_n = (int64_t)mine.size();
+        P.a.sumF = P.sumF.data();
+        P.a.partials = P.partials.data();
+        P.a.accepted = accepted.data();
+        unsigned w = 3u * kSpWarps;
+        P.a.work_counter = &w;
+        unsigned long long top = 0;
+        SparseArgs sp;
+        sp.hdr_in = hdr_in.data();
+        sp.pool_in = pool_in.data();
+        sp.hdr_out = hdr_out[r].data();
+        sp.pool_out = pool_out[r].data();
+        sp.pool_top = &top;
+        sp.region_base8 = base;
+        sp.pool_cap8 = (uint64_t)mine.size() * sp_words((uint32_t)ld);
+        base += sp.pool_cap8;
+        sp.overflow = &overflow;
+        sp.n_peers = 0;
+        for (int q = 0; q < world; ++q)
+            if (q != r) {
+                sp.peer_hdr[sp.n_peers] = hdr_out[q].data();
+                sp.peer_pool[sp.n_peers] = pool_out[q].data();
+                ++sp.n_peers;
+            }
+        if (sp.n_peers > 0) emu::launch(sparse_step_kernel<true>, 1u, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
+        else emu::launch(sparse_step_kernel<false>, 1u, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
+        for (size_t i = 0; i < partials.size(); ++i) partials[i] += P.partials[i];          // the all-reduce
+    }
+    for (int r = 0; r < world; ++r) {
+        std::vector<double> Fo((size_t)n * ld, 0.0);
+        emu::launch(sparse_to_dense_kernel, (unsigned)((n + 7) / 8), 256u, (size_t)0, (const uint64_t *)hdr_out[r].data(),
+                    (const double *)pool_out[r].data(), n, ld, Fo.data());
+        for (int64_t u = 0; u < n; ++u) std::copy(Fo.begin() + u * ld, Fo.begin() + u * ld + k, F_out + ((size_t)r * n + u) * k);
+    }
+    std::copy(partials.begin(), partials.end(), partials_out);
+    std::copy(accepted.begin(), accepted.end(), accepted_out);
     return overflow ? -2 : 0;
 }

@@ -22,7 +22,31 @@ def emu():
     lib.emu_sparse_step.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(C.c_int64)]
+    lib.emu_sparse_step_ranks.restype = C.c_int
+    lib.emu_sparse_step_ranks.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.emu_dense_step.restype = C.c_int
+    lib.emu_dense_step.argtypes = lib.emu_sparse_step.argtypes[:-1]
     return lib
+
+
+def dense_step(lib, rp, col, F, sumF, mask=None, linesearch=True, grid=1):
+    n, k = F.shape
+    ld = (k + 3) & ~3
+    rp = np.ascontiguousarray(rp, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    F = np.ascontiguousarray(F, dtype=np.float64)
+    sumF = np.ascontiguousarray(sumF, dtype=np.float64)
+    Fo = np.empty_like(F)
+    partials = np.zeros(2 * ld + 2)
+    acc = np.empty(n, dtype=np.int8)
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+    rc = lib.emu_dense_step(n, rp.ctypes.data, col.ctypes.data, k, F.ctypes.data, sumF.ctypes.data,
+                            None if m is None else m.ctypes.data, 1 if linesearch else 0, 15, 0.05, 0.1, grid,
+                            Fo.ctypes.data, partials.ctypes.data, acc.ctypes.data)
+    assert rc == 0
+    D, llh_pre, nupd = partials[:k], partials[2 * ld], int(round(partials[2 * ld + 1]))
+    return Fo, sumF - D if nupd else sumF.copy(), llh_pre, nupd, acc
 
 
 def sparse_step(lib, rp, col, F, sumF, mask=None, linesearch=True, grid=1):
@@ -108,3 +132,45 @@ def test_sparse_kernel_source_dense_rows_and_chunking(emu, oracle):
     r = oracle.step(rp, col, F, sumF, P)
     Fo, so, llh_pre, nupd, acc, _ = sparse_step(emu, rp, col, F, sumF)
     check(Fo, so, llh_pre, nupd, acc, r, oracle.llh(rp, col, F, sumF, P), max_flips=1)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("k,grid", [(5, 1), (40, 2), (100, 1), (200, 1), (300, 1)])
+def test_dense_kernel_source_against_oracle(emu, oracle, k, grid):
+    """The GPU-validated dense kernels through the same emulation: pins the emulation itself (shuffle, ballot and
+    barrier semantics) as much as the kernel logic (C2 = 1, 1, 2, 4, 8 chunk shapes; dense and pair-list paths)."""
+    n = 80
+    rp, col = random_graph(n, 5, seed=100 + k, hub=40)
+    rng = np.random.default_rng(k)
+    F = rng.random((n, k)) * (rng.random((n, k)) < min(1.0, 6.0 / k + 0.05))
+    sumF = oracle.colsum(F)
+    P = oracle.make_params(k)
+    r = oracle.step(rp, col, F, sumF, P)
+    Fo, so, llh_pre, nupd, acc = dense_step(emu, rp, col, F, sumF, grid=grid)
+    check(Fo, so, llh_pre, nupd, acc, r, oracle.llh(rp, col, F, sumF, P))
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [2, 3])
+def test_sparse_kernel_source_node_partitioned_pushes(emu, oracle, world):
+    """sparse_step_kernel<true>: every rank computes its owned rows and writes them into all replicas' output
+    pools (disjoint regions, identical offsets); afterwards every replica holds the oracle's new F."""
+    n, k = 90, 16
+    rp, col = random_graph(n, 5, seed=21, hub=30)
+    rng = np.random.default_rng(21)
+    F = rng.random((n, k)) * (rng.random((n, k)) < 0.3)
+    sumF = oracle.colsum(F)
+    P = oracle.make_params(k)
+    r = oracle.step(rp, col, F, sumF, P)
+    ld = (k + 3) & ~3
+    Fo = np.empty((world, n, k))
+    partials = np.zeros(2 * ld + 2)
+    acc = np.empty(n, dtype=np.int8)
+    rp64, col32 = np.ascontiguousarray(rp, dtype=np.int64), np.ascontiguousarray(col, dtype=np.int32)
+    rc = emu.emu_sparse_step_ranks(n, rp64.ctypes.data, col32.ctypes.data, k, F.ctypes.data, sumF.ctypes.data, 15, 0.05, 0.1,
+                                   world, Fo.ctypes.data, partials.ctypes.data, acc.ctypes.data)
+    assert rc == 0
+    for w in range(1, world):
+        assert np.array_equal(Fo[0], Fo[w])                       # identical replicas
+    nupd = int(round(partials[2 * ld + 1]))
+    check(Fo[0], sumF - partials[:k] if nupd else sumF, partials[2 * ld], nupd, acc, r, oracle.llh(rp, col, F, sumF, P))
