@@ -6,10 +6,13 @@ here="$(cd "$(dirname "$0")" && pwd)"
 src="$here/../../bigclam_apachespark_b200/csrc"
 gen="$here/_gen"
 mkdir -p "$gen"
+defs=""
 for f in bigclam_kernels.cuh bigclam_sparse.cuh; do
+  test -f "$src/$f" || continue
+  test "$f" = bigclam_sparse.cuh && defs="-DBIGCLAM_EMU_SPARSE"
   sed -e 's/extern __shared__ __align__(16) unsigned char smem_raw\[\];/unsigned char *smem_raw = emu::dyn_smem();/' \
       -e 's/^\( *\)__shared__ /\1static /' "$src/$f" > "$gen/$f"
 done
 CXX=/usr/bin/g++; test -x $CXX || CXX=g++
-$CXX -O1 -g -std=c++20 -ffp-contract=off -DBIGCLAM_EMU -x c++ -I "$here/include" -I "$gen" -I "$here/../../include" \
+$CXX -O1 -g -std=c++20 -ffp-contract=off -DBIGCLAM_EMU $defs -x c++ -I "$here/include" -I "$gen" -I "$here/../../include" \
     -pthread -shared -fPIC -Wno-unknown-pragmas -o "$here/libemu.so" "$here/emu_driver.cpp"

@@ -4,7 +4,11 @@
 #include <cstdio>
 #include <numeric>
 
-#include "bigclam_sparse.cuh"        // the transformed copies made by build.sh (includes bigclam_kernels.cuh)
+#ifdef BIGCLAM_EMU_SPARSE            // the transformed copies made by build.sh
+#include "bigclam_sparse.cuh"        // (includes bigclam_kernels.cuh)
+#else
+#include "bigclam_kernels.cuh"
+#endif
 
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 namespace emu {
@@ -79,6 +83,39 @@ void setup(Problem &P, int64_t n, const int64_t *rowptr, const int32_t *col, int
 }
 }  // namespace
 
+// One step of the dense kernels (step_kernel<C2, R, false, false>: no hub phase, no peer pushes), same outputs.
+template <int C2>
+static void run_dense(Problem &P, int grid) {
+    constexpr int R = RowsInFlight<C2>::value;
+    emu::launch(step_kernel<C2, R, false, false>, (unsigned)grid, (unsigned)kBlockThreads, block_smem_bytes(P.ld, P.a.maxm), P.a);
+}
+
+extern "C" int emu_dense_step(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
+                              const double *sumF, const uint8_t *mask, int do_linesearch, int max_inter, double alpha,
+                              double beta, int grid, double *F_out, double *partials_out, int8_t *accepted_out) {
+    Problem P;
+    unsigned work = 0;
+    setup(P, n, rowptr, col, k, F_in, sumF, mask, do_linesearch, max_inter, alpha, beta, &work, 3u * (unsigned)grid * kWarpsPerBlock);
+    const int ld = P.ld;
+    std::vector<double> Fo(P.F);                 // a PRE-only launch leaves F_out alone
+    P.a.F_in = P.F.data();
+    P.a.F_out = Fo.data();
+    const int c2raw = (ld / 2 + 31) / 32;
+    const int c2 = c2raw <= 1 ? 1 : c2raw <= 2 ? 2 : c2raw <= 4 ? 4 : c2raw <= 8 ? 8 : 16;
+    switch (c2) {
+        case 1: run_dense<1>(P, grid); break;
+        case 2: run_dense<2>(P, grid); break;
+        case 4: run_dense<4>(P, grid); break;
+        case 8: run_dense<8>(P, grid); break;
+        default: run_dense<16>(P, grid); break;
+    }
+    for (int64_t u = 0; u < n; ++u) std::copy(Fo.begin() + u * ld, Fo.begin() + u * ld + k, F_out + u * k);
+    std::copy(P.partials.begin(), P.partials.end(), partials_out);
+    std::copy(P.accepted.begin(), P.accepted.end(), accepted_out);
+    return 0;
+}
+
+#ifdef BIGCLAM_EMU_SPARSE
 // One step over sparse rows: dense F_in -> dense_to_sparse_kernel -> sparse_step_kernel -> sparse_to_dense_kernel.
 // partials_out: [D(ld) | unused(ld) | llh | n_updated] as in the library.
 extern "C" int emu_sparse_step(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
@@ -121,38 +158,6 @@ extern "C" int emu_sparse_step(int64_t n, const int64_t *rowptr, const int32_t *
     std::copy(P.accepted.begin(), P.accepted.end(), accepted_out);
     if (pool_words_out) *pool_words_out = (int64_t)top[1];
     return overflow ? -2 : 0;
-}
-
-// One step of the dense kernels (step_kernel<C2, R, false, false>: no hub phase, no peer pushes), same outputs.
-template <int C2>
-static void run_dense(Problem &P, int grid) {
-    constexpr int R = RowsInFlight<C2>::value;
-    emu::launch(step_kernel<C2, R, false, false>, (unsigned)grid, (unsigned)kBlockThreads, block_smem_bytes(P.ld, P.a.maxm), P.a);
-}
-
-extern "C" int emu_dense_step(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
-                              const double *sumF, const uint8_t *mask, int do_linesearch, int max_inter, double alpha,
-                              double beta, int grid, double *F_out, double *partials_out, int8_t *accepted_out) {
-    Problem P;
-    unsigned work = 0;
-    setup(P, n, rowptr, col, k, F_in, sumF, mask, do_linesearch, max_inter, alpha, beta, &work, 3u * (unsigned)grid * kWarpsPerBlock);
-    const int ld = P.ld;
-    std::vector<double> Fo(P.F);                 // a PRE-only launch leaves F_out alone
-    P.a.F_in = P.F.data();
-    P.a.F_out = Fo.data();
-    const int c2raw = (ld / 2 + 31) / 32;
-    const int c2 = c2raw <= 1 ? 1 : c2raw <= 2 ? 2 : c2raw <= 4 ? 4 : c2raw <= 8 ? 8 : 16;
-    switch (c2) {
-        case 1: run_dense<1>(P, grid); break;
-        case 2: run_dense<2>(P, grid); break;
-        case 4: run_dense<4>(P, grid); break;
-        case 8: run_dense<8>(P, grid); break;
-        default: run_dense<16>(P, grid); break;
-    }
-    for (int64_t u = 0; u < n; ++u) std::copy(Fo.begin() + u * ld, Fo.begin() + u * ld + k, F_out + u * k);
-    std::copy(P.partials.begin(), P.partials.end(), partials_out);
-    std::copy(P.accepted.begin(), P.accepted.end(), accepted_out);
-    return 0;
 }
 
 // Node-partitioned step over sparse rows, `world` ranks emulated one after the other: every rank owns the nodes
@@ -224,3 +229,4 @@ extern "C" int emu_sparse_step_ranks(int64_t n, const int64_t *rowptr, const int
     std::copy(accepted.begin(), accepted.end(), accepted_out);
     return overflow ? -2 : 0;
 }
+#endif  // BIGCLAM_EMU_SPARSE
