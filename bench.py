@@ -160,7 +160,8 @@ def run_single(args):
     torch.cuda.set_device(0)
     rp, col, F0 = load_workload()
     n, nnz = len(rp) - 1, len(col)
-    b = BigClam(device=0, time_kernels=True)
+    sparse = args.layout == "sparse"
+    b = BigClam(device=0, time_kernels=True, sparse_rows=sparse)
     b.set_graph(rp, col).set_K(K)
     stream = torch.cuda.current_stream()
     b.set_stream(stream.cuda_stream)
@@ -193,6 +194,14 @@ def run_single(args):
     tpath = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("step_kernel_dram_bytes_per_launch")
+
+    layout_bytes = None
+    if sparse:
+        # bytes the sparse layout actually has to move per launch (row blocks: 10 B per padded entry + 8 B header):
+        # every neighbour row once per edge, every own row read and written once
+        cnt = (b.F != 0).sum(axis=1)
+        blk = 10 * ((cnt + 3) // 4 * 4) + 8
+        layout_bytes = int((blk[col].sum() + 4 * nnz) + 2 * blk.sum() + 16 * n)
 
     # ---- e2e: per-call C ABI with host buffers ----
     mask = torch.ones(n, dtype=torch.uint8).pin_memory()
@@ -248,8 +257,9 @@ def run_single(args):
                    "l2": "inputs (F 536 MB x2 buffers) larger than L2, no flush", "llh_end": llh_end},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(n_all),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "step_kernel<4>", "kernel_ms": kavg_ms,
-                     "alg_bytes_per_launch": balg, "peak_source": peak_src},
+                     "traffic": None if sparse else traffic, "kernel": "sparse_step_kernel" if sparse else "step_kernel<4>",
+                     "kernel_ms": kavg_ms, "alg_bytes_per_launch": balg, "peak_source": peak_src,
+                     "f_layout": args.layout, "layout_bytes_per_launch": layout_bytes},
         "cpu_baseline": cpu, "reference_init_workload": extra_a,
     }))
     b.close()
@@ -263,6 +273,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-init-a", action="store_true", help="skip the reference-style-init extra workload")
+    ap.add_argument("--layout", default="dense", choices=["dense", "sparse"],
+                    help="device layout of F: dense n x K rows, or sparse rows like the reference's BSV[Double] (K <= 256)")
     ap.add_argument("--graph", default="com-amazon", help="fixture name or rmat:<nodes>:<edges> (default: the headline workload)")
     args = ap.parse_args()
     global _GRAPH, WORKLOAD
@@ -275,6 +287,8 @@ def main():
         args.warmup = min(args.warmup, 1)
         return run_reference(args)
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if args.layout == "sparse":
+            os.environ["BIGCLAM_SPARSE"] = "1"
         from bigclam_apachespark_b200 import dist
         return dist.bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD, K)
     return run_single(args)
