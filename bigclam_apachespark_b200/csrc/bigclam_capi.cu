@@ -249,6 +249,15 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
     const int64_t hub_deg = (4 * max_deg <= 3 * per_warp) ? INT64_MAX
                                                           : std::min<int64_t>(512, std::max<int64_t>(kHubDegree, per_warp / 5));
     if (ctx->c2 <= 4 && !ctx->sparse) while (nh < cnt && meta[(size_t)nh].deg >= hub_deg) ++nh;
+    if (ctx->sparse && ctx->nsteps <= 16) {
+        // sparse rows: a hub is split into kSpHubSeg-edge segments over warps (bigclam_sparse.cuh) when one warp
+        // walking it would take a sizeable part of the launch: from a quarter of a warp's share of the owned
+        // entries upwards, at least 1024 edges (BIGCLAM_SPARSE_HUB_DEG overrides the threshold: tests)
+        const int64_t sp_per_warp = own_nnz / std::max<int64_t>(1, (int64_t)ctx->sp_grid * kSpWarps);
+        int64_t sp_hub_deg = std::max<int64_t>(1024, sp_per_warp / 4);
+        if (const char *ev = std::getenv("BIGCLAM_SPARSE_HUB_DEG")) sp_hub_deg = std::max<int64_t>(1, std::atoll(ev));
+        while (nh < cnt && meta[(size_t)nh].deg >= sp_hub_deg) ++nh;
+    }
     ctx->n_hubs = nh;
     // work items of the hub phase: hubs above kHubSlice edges are split into slices handled by different
     // blocks (phases 1-3), the others are done by one block (phase 0); see hub_phase
@@ -257,10 +266,11 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
         int32_t n_mega = 0;
         for (int32_t i = 0; i < nh; ++i) {
             const int32_t deg = meta[(size_t)i].deg;
-            const int32_t nsl = (deg + kHubSlice - 1) / kHubSlice;
+            const int32_t slice = ctx->sparse ? kSpHubSeg : kHubSlice;
+            const int32_t nsl = (deg + slice - 1) / slice;
             HubItem it{};
             it.hub = i;
-            if (nsl > 1 && ctx->nsteps <= 16) {
+            if ((nsl > 1 || ctx->sparse) && ctx->nsteps <= 16) {
                 it.mslot = n_mega++;
                 it.nslices = nsl;
                 for (int32_t sl = 0; sl < nsl; ++sl) {
@@ -291,9 +301,10 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
         }
         const size_t slots = (size_t)std::max<int32_t>(1, n_mega);
         CU(cudaMalloc(&ctx->d_hub_scratch, sizeof(double) * slots * ((size_t)ctx->ld + 32)));
-        CU(cudaMalloc(&ctx->d_hub_counters, sizeof(unsigned int) * 2 * slots));
+        CU(cudaMalloc(&ctx->d_hub_counters, sizeof(unsigned int) * (2 * slots + 1)));      // + the sparse kernel's item counter
+        CU(cudaMemset(ctx->d_hub_counters, 0, sizeof(unsigned int) * (2 * slots + 1)));
     }
-    const unsigned int init = ctx->sparse ? 3u * (unsigned int)ctx->sp_grid * kSpWarps
+    const unsigned int init = ctx->sparse ? (unsigned int)nh + 3u * (unsigned int)ctx->sp_grid * kSpWarps
                                           : (unsigned int)nh + 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
     ctx->h_work_init = init;
     if (ctx->d_work != nullptr) CU(cudaMemcpy(ctx->d_work + 1, &init, sizeof(unsigned int), cudaMemcpyHostToDevice));
@@ -401,9 +412,14 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
         ctx->sparse = true;
         ctx->sp_smem = sp_block_smem_bytes(ld);
         int sbps = 0;
-        CUC(cudaFuncSetAttribute(sparse_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
-        CUC(cudaFuncSetAttribute(sparse_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
-        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sbps, sparse_step_kernel<true>, kSpThreads, ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(sparse_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(sparse_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(sparse_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(sparse_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        int sb2 = 0;                         // the grid must be resident for every variant (hub items wait for each other)
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sbps, sparse_step_kernel<true, true>, kSpThreads, ctx->sp_smem));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sb2, sparse_step_kernel<false, false>, kSpThreads, ctx->sp_smem));
+        sbps = std::min(sbps, sb2);
         if (sbps <= 0) {
             fail(nullptr, BIGCLAM_ECUDA, "bigclam_create: sparse kernel does not fit an SM (smem %zu B)", ctx->sp_smem);
             free_ctx(ctx);
@@ -652,9 +668,9 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
         }
         CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
     }
-    if (ctx->n_mega > 0) {     // mega-hub scratch and slice counters start every launch at zero
+    if (ctx->n_mega > 0) {     // mega-hub scratch, slice counters (and the sparse kernel's item counter) start every launch at zero
         CU(cudaMemsetAsync(ctx->d_hub_scratch, 0, sizeof(double) * (size_t)ctx->n_mega * ((size_t)ctx->ld + 32), ctx->stream));
-        CU(cudaMemsetAsync(ctx->d_hub_counters, 0, sizeof(unsigned int) * 2 * (size_t)ctx->n_mega, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_hub_counters, 0, sizeof(unsigned int) * (2 * (size_t)ctx->n_mega + 1), ctx->stream));
     }
     // positions 0 .. 3*#warps-1 are pre-assigned statically, the rest is handed out dynamically
     CU(cudaMemcpyAsync(ctx->d_work, ctx->d_work + 1, sizeof(unsigned int), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -679,8 +695,12 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
             CU(cudaMemsetAsync(sp.pool_top, 0, sizeof(unsigned long long), ctx->stream));
             ctx->dense_valid = false;
         }
-        if (sp.n_peers > 0) sparse_step_kernel<true><<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
-        else sparse_step_kernel<false><<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
+        sp.hub_work = ctx->d_hub_counters + 2 * (size_t)std::max<int32_t>(1, ctx->n_mega);
+        const bool hub = a.n_hub_items > 0, push = sp.n_peers > 0;
+        if (hub && push) sparse_step_kernel<true, true><<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else if (hub) sparse_step_kernel<false, true><<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else if (push) sparse_step_kernel<true, false><<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else sparse_step_kernel<false, false><<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
     } else {
         launch_step(ctx->c2, a, ctx->grid, ctx->smem_bytes, ctx->stream);
     }

@@ -27,8 +27,7 @@
 //   SWAP  the accepted candidate's non-zeros are compacted (ascending) into the staging buffer, a block is
 //         taken from the output pool, the row and its header are written.
 //
-// Limits of this first version: ld <= 256 (K <= 256), MIN_F_ == 0, no block-cooperative hub phase (a hub is
-// walked by one warp in chunks of 32 edges).
+// Limits of this version: ld <= 256 (K <= 256), MIN_F_ == 0.
 #pragma once
 #include "bigclam_kernels.cuh"
 
@@ -60,6 +59,7 @@ struct SparseArgs {
     int32_t n_peers;
     uint64_t *peer_hdr[7];
     double *peer_pool[7];
+    unsigned int *hub_work;            // next hub item to hand out (zeroed per launch); items: StepArgs::hub_items
 };
 
 // per-warp shared memory: fu_d[ld] | g_d[ld] | ent_val[E] | ent_idx[E] u16 | aidx[256] u16 | poff[40] u16
@@ -108,9 +108,22 @@ __device__ __noinline__ int sp_stage_chunk(const uint64_t *__restrict__ hdr_in, 
     return ne;
 }
 
-// kPush: multi-GPU launch, the peers' replicas are written too (compile-time so that the single-GPU kernel
-// carries none of that code).
-template <bool kPush>
+// Hubs.  A node whose neighbour list is long enough to dominate a launch when one warp walks it (host: a sizeable
+// fraction of a warp's share of the launch) is split into segments of kSpHubSeg edges that different warps work
+// on; the pieces meet in a global scratch row per hub (same layout as the dense kernels' mega hubs:
+// G[ld] | S1 | ST[16], stride ld + 32 doubles, two counters per hub):
+//   phase 1  PRE of one segment: its share of sum_v w_v fv (atomic adds into G) and of S1;
+//   phase 2  line search of one segment, once all phase-1 segments of the hub are in: the segment's share of the
+//            16 per-trial sums (atomic adds into ST);
+//   phase 3  once per hub, after its phase-2 segments: gradient, active set, Armijo decision, new row.
+// Items are handed out in that order by one counter and every warp holds one item at a time on a grid whose
+// warps are all resident, so a waiting warp only waits for items that are being processed: no deadlock.
+// (G is summed by atomics in arrival order, so a hub's gradient is reproducible only to rounding.)
+constexpr int kSpHubSeg = 256;
+
+// kPush: multi-GPU launch, the peers' replicas are written too; kHub: the launch has split hubs.  Both are
+// compile-time so that the plain single-GPU kernel carries none of that code.
+template <bool kPush, bool kHub>
 __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepArgs a, const SparseArgs sp) {
     if (a.done_flag != nullptr && *a.done_flag != 0) return;
 
@@ -128,8 +141,11 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
     unsigned short *aidx = ent_idx + kSpEntries;
     unsigned short *poff = aidx + kMaxActiveCap;
 
+#pragma unroll 1
     for (int i = threadIdx.x; i < ld; i += kSpThreads) { s_sumF[i] = a.sumF[i]; s_D[i] = 0.0; }
+#pragma unroll 1
     for (int i = threadIdx.x; i < kMaxSteps; i += kSpThreads) s_steps[i] = a.steps[i];
+#pragma unroll 1
     for (int i = lane; i < ld; i += 32) { fu_d[i] = 0.0; g_d[i] = 0.0; }
     __syncthreads();
 
@@ -138,11 +154,279 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
     const int nsteps = a.nsteps;
     const int64_t order_n = a.order_n;
     const unsigned lt_mask = (1u << lane) - 1u;
+    const int j16 = lane & 15, h = lane >> 4;
     double llh_acc = 0.0, nupd_acc = 0.0;
-    const int64_t nwarps = (int64_t)gridDim.x * kSpWarps;
 
-    // positions 0 .. 3*#warps-1 are pre-assigned, the rest is handed out by the work counter two nodes ahead
-    int64_t pos = (int64_t)blockIdx.x * kSpWarps + wib;
+    // ---- pieces shared by the plain node path and the hub phases ----
+    // PRE over the edges [eb, ee) of a node whose fu is in fu_d: returns this lane's share of S1; with `axpy`
+    // the weighted neighbour rows are added into g_d.  `single` = the range fitted one staged chunk (its
+    // entries are still in the buffer, `ne_last` rows).
+    auto pre_range = [&](int64_t e0, int eb, int ee, bool axpy, int &nchunks, int &ne_last) -> double {
+        double S1 = 0.0;
+        nchunks = 0;
+        ne_last = 0;
+        for (int cb = eb; cb < ee;) {
+            const int ne = sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, ee - cb), lane, ent_val, ent_idx, poff);
+            double x = 0.0;
+            if (lane < ne) {
+                const int end = poff[lane + 1];
+                for (int i = poff[lane]; i < end; ++i) x = fma(ent_val[i], fu_d[ent_idx[i]], x);
+            }
+            double w;
+            const double t = edge_term<true>(x, ec, w);
+            S1 += (lane < ne) ? t : 0.0;
+            if (axpy) {
+                for (int e = 0; e < ne; ++e) {
+                    const double we = __shfl_sync(0xffffffffu, w, e);
+                    const int pe = poff[e], pn = poff[e + 1];
+                    for (int i = pe + lane; i < pn; i += 32) {
+                        const int c = ent_idx[i];
+                        g_d[c] = fma(we, ent_val[i], g_d[c]);
+                    }
+                    __syncwarp();
+                }
+            }
+            cb += ne;
+            ne_last = ne;
+            ++nchunks;
+        }
+        return S1;
+    };
+    // g_d (sum of weighted neighbour rows) -> gradient (:168) in place; returns |g|^2, lists the active
+    // components in aidx (m of them) and tells whether any candidate can reach MAX_F_.
+    auto scan_gradient = [&](int &m, bool &need_hi) -> double {
+        double G2 = 0.0;
+        bool hi_lane = false;
+        m = 0;
+        for (int c0 = 0; c0 < ld; c0 += 32) {
+            const int c = c0 + lane;
+            const bool in = c < ld;
+            const double f = in ? fu_d[c] : 0.0;
+            const double g = in ? (g_d[c] - s_sumF[c]) + f : 0.0;
+            if (in) g_d[c] = g;
+            G2 = fma(g, g, G2);
+            const bool act = in && (f > 0.0 || g > 0.0);
+            const unsigned bal = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                aidx[m + __popc(bal & lt_mask)] = (unsigned short)c;
+                hi_lane |= (f + g > max_f);
+            }
+            m += __popc(bal);
+        }
+        G2 = warp_sum(G2);
+        need_hi = __any_sync(0xffffffffu, hi_lane);
+        __syncwarp();
+        return G2;
+    };
+    // Line search over the edges [eb, ee): lane (j, h) returns the sum over its edges of the clamped edge term
+    // for candidate step s; `staged` rows of a single chunk may still be in the buffer from PRE.
+    auto ls_range = [&](int64_t e0, int eb, int ee, double s, bool need_hi, int staged) -> double {
+        double sumterms = 0.0;
+        for (int cb = eb; cb < ee;) {
+            const int ne = (staged > 0) ? staged
+                                        : sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, ee - cb), lane, ent_val, ent_idx, poff);
+#pragma unroll 1
+            for (int e2 = 0; e2 < ne; e2 += 4) {
+                const int eA = e2 + h, eB = e2 + 2 + h;
+                const bool vA = eA < ne, vB = eB < ne;
+                const int iA = vA ? (int)poff[eA] : 0, nA = vA ? (int)poff[eA + 1] - iA : 0;
+                const int iB = vB ? (int)poff[eB] : 0, nB = vB ? (int)poff[eB + 1] - iB : 0;
+                const int nmax = max(nA, nB);
+                double DA = 0.0, DB = 0.0;
+#pragma unroll 1
+                for (int k = 0; k < nmax; ++k) {
+                    const bool ka = k < nA, kb = k < nB;
+                    const int ca = ka ? (int)ent_idx[iA + k] : 0, cb2 = kb ? (int)ent_idx[iB + k] : 0;
+                    const double pa = ka ? ent_val[iA + k] : 0.0, pb = kb ? ent_val[iB + k] : 0.0;
+                    const double fa = fu_d[ca], ga = g_d[ca], fb = fu_d[cb2], gb = g_d[cb2];
+                    if (need_hi) {
+                        DA = fma(clamp_step0(fa, s, ga, max_f), pa, DA);
+                        DB = fma(clamp_step0(fb, s, gb, max_f), pb, DB);
+                    } else {
+                        DA = fma(clamp_step0_lo(fa, s, ga), pa, DA);
+                        DB = fma(clamp_step0_lo(fb, s, gb), pb, DB);
+                    }
+                }
+                double tA, tB;
+                edge_term2(DA, DB, ec, tA, tB);
+                sumterms += vA ? tA : 0.0;
+                sumterms += vB ? tB : 0.0;
+            }
+            __syncwarp();
+            cb += ne;
+        }
+        return sumterms;
+    };
+    // Armijo decision for the 16 candidates tg .. tg+15 given each lane's edge-term sum (already summed over h).
+    auto decide = [&](int tg, double s, bool jok, double sumterms, int m, bool need_hi, double llh_u, double G2) -> int {
+        // - newfu.sfT + newfu.newfu with sfT = (sumF - fu) + newfu   (:176,:180)
+        double oa = 0.0, ob = 0.0;
+        for (int t = h; t < m; t += 2) {
+            const int c = aidx[t];
+            const double f = fu_d[c], g = g_d[c];
+            const double nf = need_hi ? clamp_step0(f, s, g, max_f) : clamp_step0_lo(f, s, g);
+            const double sf = (s_sumF[c] - f) + nf;
+            oa = fma(nf, sf, oa);
+            ob = fma(nf, nf, ob);
+        }
+        oa += __shfl_xor_sync(0xffffffffu, oa, 16);
+        ob += __shfl_xor_sync(0xffffffffu, ob, 16);
+        const double result = (sumterms - oa) + ob;
+        const double rhs = llh_u + (a.alpha * s) * G2;
+        const unsigned pass = __ballot_sync(0xffffffffu, jok && (result >= rhs)) & 0xffffu;
+        return pass ? tg + __ffs(pass) - 1 : -1;          // lowest j == largest step (:182 max)
+    };
+    // SWAP (:183-190): the accepted candidate's non-zeros (or the old row) go to the output pool(s).
+    auto swap_row = [&](int64_t u, int jstar, int m, int cu, const double *uval, const unsigned short *uidx) {
+        int cnt_new = 0;
+        if (jstar >= 0) {
+            const double s = s_steps[jstar];
+            for (int t0 = 0; t0 < m; t0 += 32) {
+                const int t = t0 + lane;
+                const bool ok = t < m;
+                const int c = ok ? (int)aidx[t] : 0;
+                const double f = fu_d[c], g = g_d[c];
+                const double nr = clamp_step(f, s, g, a.min_f, max_f);
+                const bool nz = ok && (nr != 0.0);
+                const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                if (nz) {
+                    const int p = cnt_new + __popc(bal & lt_mask);
+                    ent_val[p] = nr;
+                    ent_idx[p] = (unsigned short)c;
+                }
+                if (ok && f != nr) atomicAdd(s_D + c, f - nr);       // :191-192, sum over accepted nodes of old - new
+                cnt_new += __popc(bal);
+            }
+            nupd_acc += 1.0;
+        } else {
+            for (int i = lane; i < cu; i += 32) {
+                ent_val[i] = __ldg(uval + i);
+                ent_idx[i] = __ldg(uidx + i);
+            }
+            cnt_new = cu;
+        }
+        __syncwarp();
+        const unsigned long long words = sp_words((uint32_t)cnt_new);
+        unsigned long long rel = 0;
+        if (lane == 0 && cnt_new > 0) rel = atomicAdd(sp.pool_top, words);
+        rel = __shfl_sync(0xffffffffu, rel, 0);
+        if (rel + words > sp.pool_cap8) {
+            if (lane == 0) { *sp.overflow = 1; sp.hdr_out[u] = sp_pack(0, 0); }
+        } else {
+            const unsigned long long off = sp.region_base8 + rel;
+            const uint64_t hnew = sp_pack(off, (uint32_t)cnt_new);
+            double *ov = sp.pool_out + off;
+            unsigned short *oi = reinterpret_cast<unsigned short *>(ov + sp_pad((uint32_t)cnt_new));
+            for (int i = lane; i < cnt_new; i += 32) {
+                ov[i] = ent_val[i];
+                oi[i] = ent_idx[i];
+            }
+            if (lane == 0) sp.hdr_out[u] = hnew;
+            if (kPush) {
+                for (int pr = 0; pr < sp.n_peers; ++pr) {
+                    double *pv = sp.peer_pool[pr] + off;
+                    unsigned short *pi = reinterpret_cast<unsigned short *>(pv + sp_pad((uint32_t)cnt_new));
+                    for (int i = lane; i < cnt_new; i += 32) {
+                        pv[i] = ent_val[i];
+                        pi[i] = ent_idx[i];
+                    }
+                    if (lane == 0) sp.peer_hdr[pr][u] = hnew;
+                }
+            }
+        }
+    };
+
+    // ---------------- split hubs (see above), then one warp per node ----------------
+    if constexpr (kHub) {
+        for (;;) {
+            unsigned int it = 0;
+            if (lane == 0) it = atomicAdd(sp.hub_work, 1u);
+            it = __shfl_sync(0xffffffffu, it, 0);
+            if (it >= (unsigned int)a.n_hub_items) break;
+            const HubItem item = a.hub_items[it];
+            const NodeMeta nm = a.meta[item.hub];
+            const int64_t u = nm.u, e0 = nm.e0;
+            const int deg = nm.deg;
+            double *scr = a.hub_scratch + (size_t)item.mslot * (ld + 32);
+            unsigned int *cnt = a.hub_counters + 2 * (size_t)item.mslot;
+            const int sb = item.slice * kSpHubSeg, se = min(deg, sb + kSpHubSeg);
+            const uint64_t hu = __ldg(sp.hdr_in + u);
+            const int cu = (int)sp_cnt(hu);
+            const double *uval = sp.pool_in + sp_off8(hu);
+            const unsigned short *uidx = reinterpret_cast<const unsigned short *>(uval + sp_pad((uint32_t)cu));
+            double fusf = 0.0, fufu = 0.0;
+            for (int i = lane; i < cu; i += 32) {
+                const double v = __ldg(uval + i);
+                const int c = __ldg(uidx + i);
+                fu_d[c] = v;
+                fusf = fma(v, s_sumF[c], fusf);
+                fufu = fma(v, v, fufu);
+            }
+            fusf = warp_sum(fusf);
+            fufu = warp_sum(fufu);
+            __syncwarp();
+            const bool in_uset = (a.node_mask == nullptr) || (a.node_mask[u] != 0);
+            const bool want_ls = a.do_linesearch && in_uset;
+            if (item.phase == 1) {
+                int nch, nel;
+                double S1 = warp_sum(pre_range(e0, sb, se, want_ls, nch, nel));
+                if (want_ls) {
+                    for (int c = lane; c < ld; c += 32) {
+                        const double v = g_d[c];
+                        if (v != 0.0) atomicAdd(scr + c, v);
+                        g_d[c] = 0.0;
+                    }
+                }
+                if (lane == 0) atomicAdd(scr + ld, S1);
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(cnt, 1u);
+            } else {
+                if (lane == 0) {
+                    const unsigned int *c = cnt + (item.phase == 2 ? 0 : 1);
+                    while (*reinterpret_cast<const volatile unsigned int *>(c) < (unsigned int)item.nslices) __nanosleep(200);
+                    __threadfence();
+                }
+                __syncwarp();
+                const double llh_u = (__ldcg(scr + ld) - fusf) + fufu;
+                int m = 0, jstar = -1;
+                bool need_hi = false;
+                double G2 = 0.0;
+                if (want_ls) {
+                    for (int c = lane; c < ld; c += 32) g_d[c] = __ldcg(scr + c);
+                    __syncwarp();
+                    G2 = scan_gradient(m, need_hi);
+                }
+                const double s = s_steps[j16 < nsteps ? j16 : 0];       // hubs are only split when nsteps <= 16
+                if (item.phase == 2) {
+                    if (want_ls) {
+                        double st = ls_range(e0, sb, se, s, need_hi, 0);
+                        st += __shfl_xor_sync(0xffffffffu, st, 16);
+                        if (lane < 16) atomicAdd(scr + ld + 1 + lane, st);
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(cnt + 1, 1u);
+                } else {
+                    if (want_ls) jstar = decide(0, s, j16 < nsteps, __ldcg(scr + ld + 1 + j16), m, need_hi, llh_u, G2);
+                    llh_acc += llh_u;
+                    if (a.do_linesearch) swap_row(u, jstar, m, cu, uval, uidx);
+                    if (a.accepted != nullptr && lane == 0) a.accepted[u] = (int8_t)jstar;
+                }
+                __syncwarp();
+                if (want_ls)
+                    for (int c = lane; c < ld; c += 32) g_d[c] = 0.0;
+            }
+            __syncwarp();
+            for (int i = lane; i < cu; i += 32) fu_d[__ldg(uidx + i)] = 0.0;
+            __syncwarp();
+        }
+    }
+
+    // positions n_hubs .. n_hubs + 3*#warps - 1 are pre-assigned, the rest is handed out by the work counter two
+    // nodes ahead
+    const int64_t nwarps = (int64_t)gridDim.x * kSpWarps;
+    int64_t pos = (kHub ? (int64_t)a.n_hubs : 0) + (int64_t)blockIdx.x * kSpWarps + wib;
     int64_t pos_n = pos + nwarps, pos_nn = pos + 2 * nwarps;
     NodeMeta cur = {0, 0, 0}, nxt = {0, 0, 0};
     if (pos < order_n) cur = a.meta[pos];
@@ -177,183 +461,27 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
         const bool want_ls = a.do_linesearch && in_uset && deg > 0;
 
         // ---------------- PRE (:157-169) ----------------
-        double S1 = 0.0;
-        int nchunks = 0, ne_last = 0;
-        for (int cb = 0; cb < deg;) {
-            const int ne = sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, deg - cb), lane, ent_val, ent_idx, poff);
-            double x = 0.0;
-            if (lane < ne) {
-                const int end = poff[lane + 1];
-                for (int i = poff[lane]; i < end; ++i) x = fma(ent_val[i], fu_d[ent_idx[i]], x);
-            }
-            double w;
-            const double t = edge_term<true>(x, ec, w);
-            S1 += (lane < ne) ? t : 0.0;
-            if (want_ls) {
-                for (int e = 0; e < ne; ++e) {
-                    const double we = __shfl_sync(0xffffffffu, w, e);
-                    const int pe = poff[e], pn = poff[e + 1];
-                    for (int i = pe + lane; i < pn; i += 32) {
-                        const int c = ent_idx[i];
-                        g_d[c] = fma(we, ent_val[i], g_d[c]);
-                    }
-                    __syncwarp();
-                }
-            }
-            cb += ne;
-            ne_last = ne;
-            ++nchunks;
-        }
-        S1 = warp_sum(S1);
+        int nchunks, ne_last;
+        const double S1 = warp_sum(pre_range(e0, 0, deg, want_ls, nchunks, ne_last));
         const double llh_u = (S1 - fusf) + fufu;
         llh_acc += llh_u;
 
-        int jstar = -1;
-        int m = 0;
+        int jstar = -1, m = 0;
         if (want_ls) {
-            // ---- gradient (:168) in place, |g|^2, active components ----
-            double G2 = 0.0;
-            bool hi_lane = false;
-            for (int c0 = 0; c0 < ld; c0 += 32) {
-                const int c = c0 + lane;
-                const bool in = c < ld;
-                const double f = in ? fu_d[c] : 0.0;
-                const double g = in ? (g_d[c] - s_sumF[c]) + f : 0.0;
-                if (in) g_d[c] = g;
-                G2 = fma(g, g, G2);
-                const bool act = in && (f > 0.0 || g > 0.0);
-                const unsigned bal = __ballot_sync(0xffffffffu, act);
-                if (act) {
-                    aidx[m + __popc(bal & lt_mask)] = (unsigned short)c;
-                    hi_lane |= (f + g > max_f);
-                }
-                m += __popc(bal);
-            }
-            G2 = warp_sum(G2);
-            const bool need_hi = __any_sync(0xffffffffu, hi_lane);
-            __syncwarp();
-
+            bool need_hi;
+            const double G2 = scan_gradient(m, need_hi);
             // ---------------- LS (:172-182) ----------------
-            const int j16 = lane & 15, h = lane >> 4;
             for (int tg = 0; tg < nsteps && jstar < 0; tg += 16) {
                 const int j = tg + j16;
                 const bool jok = j < nsteps;
                 const double s = s_steps[jok ? j : 0];
-                double sumterms = 0.0;
-                for (int cb = 0; cb < deg;) {
-                    // a node whose neighbours fitted one chunk still has them staged from PRE
-                    const int ne = (nchunks == 1 && tg == 0)
-                                       ? ne_last
-                                       : sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, deg - cb), lane, ent_val, ent_idx, poff);
-#pragma unroll 1
-                    for (int e2 = 0; e2 < ne; e2 += 4) {
-                        const int eA = e2 + h, eB = e2 + 2 + h;
-                        const bool vA = eA < ne, vB = eB < ne;
-                        const int iA = vA ? (int)poff[eA] : 0, nA = vA ? (int)poff[eA + 1] - iA : 0;
-                        const int iB = vB ? (int)poff[eB] : 0, nB = vB ? (int)poff[eB + 1] - iB : 0;
-                        const int nmax = max(nA, nB);
-                        double DA = 0.0, DB = 0.0;
-#pragma unroll 1
-                        for (int k = 0; k < nmax; ++k) {
-                            const bool ka = k < nA, kb = k < nB;
-                            const int ca = ka ? (int)ent_idx[iA + k] : 0, cb2 = kb ? (int)ent_idx[iB + k] : 0;
-                            const double pa = ka ? ent_val[iA + k] : 0.0, pb = kb ? ent_val[iB + k] : 0.0;
-                            const double fa = fu_d[ca], ga = g_d[ca], fb = fu_d[cb2], gb = g_d[cb2];
-                            if (need_hi) {
-                                DA = fma(clamp_step0(fa, s, ga, max_f), pa, DA);
-                                DB = fma(clamp_step0(fb, s, gb, max_f), pb, DB);
-                            } else {
-                                DA = fma(clamp_step0_lo(fa, s, ga), pa, DA);
-                                DB = fma(clamp_step0_lo(fb, s, gb), pb, DB);
-                            }
-                        }
-                        double tA, tB;
-                        edge_term2(DA, DB, ec, tA, tB);
-                        sumterms += vA ? tA : 0.0;
-                        sumterms += vB ? tB : 0.0;
-                    }
-                    __syncwarp();
-                    cb += ne;
-                }
+                // a node whose neighbours fitted one chunk still has them staged from PRE
+                double sumterms = ls_range(e0, 0, deg, s, need_hi, (nchunks == 1 && tg == 0) ? ne_last : 0);
                 sumterms += __shfl_xor_sync(0xffffffffu, sumterms, 16);
-                // - newfu.sfT + newfu.newfu with sfT = (sumF - fu) + newfu   (:176,:180)
-                double oa = 0.0, ob = 0.0;
-                for (int t = h; t < m; t += 2) {
-                    const int c = aidx[t];
-                    const double f = fu_d[c], g = g_d[c];
-                    const double nf = need_hi ? clamp_step0(f, s, g, max_f) : clamp_step0_lo(f, s, g);
-                    const double sf = (s_sumF[c] - f) + nf;
-                    oa = fma(nf, sf, oa);
-                    ob = fma(nf, nf, ob);
-                }
-                oa += __shfl_xor_sync(0xffffffffu, oa, 16);
-                ob += __shfl_xor_sync(0xffffffffu, ob, 16);
-                const double result = (sumterms - oa) + ob;
-                const double rhs = llh_u + (a.alpha * s) * G2;
-                const unsigned pass = __ballot_sync(0xffffffffu, jok && (result >= rhs)) & 0xffffu;
-                if (pass) jstar = tg + __ffs(pass) - 1;   // lowest j == largest step (:182 max)
+                jstar = decide(tg, s, jok, sumterms, m, need_hi, llh_u, G2);
             }
         }
-
-        // ---------------- SWAP (:183-190): the new row goes to the output pool ----------------
-        if (a.do_linesearch) {
-            int cnt_new = 0;
-            if (jstar >= 0) {
-                const double s = s_steps[jstar];
-                for (int t0 = 0; t0 < m; t0 += 32) {
-                    const int t = t0 + lane;
-                    const bool ok = t < m;
-                    const int c = ok ? (int)aidx[t] : 0;
-                    const double f = fu_d[c], g = g_d[c];
-                    const double nr = clamp_step(f, s, g, a.min_f, max_f);
-                    const bool nz = ok && (nr != 0.0);
-                    const unsigned bal = __ballot_sync(0xffffffffu, nz);
-                    if (nz) {
-                        const int p = cnt_new + __popc(bal & lt_mask);
-                        ent_val[p] = nr;
-                        ent_idx[p] = (unsigned short)c;
-                    }
-                    if (ok && f != nr) atomicAdd(s_D + c, f - nr);       // :191-192, sum over accepted nodes of old - new
-                    cnt_new += __popc(bal);
-                }
-                nupd_acc += 1.0;
-            } else {
-                for (int i = lane; i < cu; i += 32) {
-                    ent_val[i] = __ldg(uval + i);
-                    ent_idx[i] = __ldg(uidx + i);
-                }
-                cnt_new = cu;
-            }
-            __syncwarp();
-            const unsigned long long words = sp_words((uint32_t)cnt_new);
-            unsigned long long rel = 0;
-            if (lane == 0 && cnt_new > 0) rel = atomicAdd(sp.pool_top, words);
-            rel = __shfl_sync(0xffffffffu, rel, 0);
-            if (rel + words > sp.pool_cap8) {
-                if (lane == 0) { *sp.overflow = 1; sp.hdr_out[u] = sp_pack(0, 0); }
-            } else {
-                const unsigned long long off = sp.region_base8 + rel;
-                const uint64_t hnew = sp_pack(off, (uint32_t)cnt_new);
-                double *ov = sp.pool_out + off;
-                unsigned short *oi = reinterpret_cast<unsigned short *>(ov + sp_pad((uint32_t)cnt_new));
-                for (int i = lane; i < cnt_new; i += 32) {
-                    ov[i] = ent_val[i];
-                    oi[i] = ent_idx[i];
-                }
-                if (lane == 0) sp.hdr_out[u] = hnew;
-                if (kPush) {
-                    for (int pr = 0; pr < sp.n_peers; ++pr) {
-                        double *pv = sp.peer_pool[pr] + off;
-                        unsigned short *pi = reinterpret_cast<unsigned short *>(pv + sp_pad((uint32_t)cnt_new));
-                        for (int i = lane; i < cnt_new; i += 32) {
-                            pv[i] = ent_val[i];
-                            pi[i] = ent_idx[i];
-                        }
-                        if (lane == 0) sp.peer_hdr[pr][u] = hnew;
-                    }
-                }
-            }
-        }
+        if (a.do_linesearch) swap_row(u, jstar, m, cu, uval, uidx);
         if (a.accepted != nullptr && lane == 0) a.accepted[u] = (int8_t)jstar;
 
         // ---- leave the warp's dense vectors at zero for the next node ----

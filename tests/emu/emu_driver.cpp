@@ -118,10 +118,12 @@ extern "C" int emu_dense_step(int64_t n, const int64_t *rowptr, const int32_t *c
 #ifdef BIGCLAM_EMU_SPARSE
 // One step over sparse rows: dense F_in -> dense_to_sparse_kernel -> sparse_step_kernel -> sparse_to_dense_kernel.
 // partials_out: [D(ld) | unused(ld) | llh | n_updated] as in the library.
-extern "C" int emu_sparse_step(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
-                               const double *sumF, const uint8_t *mask, int do_linesearch, int max_inter, double alpha,
-                               double beta, int grid, double *F_out, double *partials_out, int8_t *accepted_out,
-                               int64_t *pool_words_out) {
+// hub_deg > 0: nodes of at least that degree are split into kSpHubSeg-edge segments over the warps (grid must be
+// 1 here: the emulation runs blocks one after the other and the hub phases wait for each other).
+static int sparse_step_impl(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
+                            const double *sumF, const uint8_t *mask, int do_linesearch, int max_inter, double alpha,
+                            double beta, int grid, int hub_deg, double *F_out, double *partials_out, int8_t *accepted_out,
+                            int64_t *pool_words_out) {
     Problem P;
     unsigned work = 0;
     setup(P, n, rowptr, col, k, F_in, sumF, mask, do_linesearch, max_inter, alpha, beta, &work, 3u * (unsigned)grid * kSpWarps);
@@ -146,7 +148,42 @@ extern "C" int emu_sparse_step(int64_t n, const int64_t *rowptr, const int32_t *
     P.a.F_out = nullptr;
     sp.region_base8 = 0;
     sp.n_peers = 0;
-    emu::launch(sparse_step_kernel<false>, (unsigned)grid, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
+    // split hubs: same item list as rebuild_order_list (csrc/bigclam_capi.cu)
+    std::vector<HubItem> items;
+    std::vector<double> scratch;
+    std::vector<unsigned int> counters;
+    int nh = 0;
+    if (hub_deg > 0 && grid == 1 && P.nsteps <= 16) {
+        while (nh < n && P.meta[nh].deg >= hub_deg) ++nh;
+        std::vector<HubItem> i1, i2, i3;
+        for (int i = 0; i < nh; ++i) {
+            HubItem it{};
+            it.hub = i;
+            it.mslot = i;
+            it.nslices = (P.meta[i].deg + kSpHubSeg - 1) / kSpHubSeg;
+            for (int sl = 0; sl < it.nslices; ++sl) {
+                it.slice = sl;
+                it.phase = 1; i1.push_back(it);
+                it.phase = 2; i2.push_back(it);
+            }
+            it.slice = 0;
+            it.phase = 3; i3.push_back(it);
+        }
+        items.insert(items.end(), i1.begin(), i1.end());
+        items.insert(items.end(), i2.begin(), i2.end());
+        items.insert(items.end(), i3.begin(), i3.end());
+    }
+    scratch.assign((size_t)std::max(1, nh) * (ld + 32), 0.0);
+    counters.assign(2 * (size_t)std::max(1, nh) + 1, 0u);
+    P.a.n_hubs = nh;
+    P.a.n_hub_items = (int32_t)items.size();
+    P.a.hub_items = items.data();
+    P.a.hub_scratch = scratch.data();
+    P.a.hub_counters = counters.data();
+    sp.hub_work = counters.data() + 2 * (size_t)std::max(1, nh);
+    work = (unsigned)nh + 3u * (unsigned)grid * kSpWarps;
+    if (nh > 0) emu::launch(sparse_step_kernel<false, true>, (unsigned)grid, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
+    else emu::launch(sparse_step_kernel<false, false>, (unsigned)grid, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
     std::vector<double> Fo((size_t)n * ld, 0.0);
     if (do_linesearch)
         emu::launch(sparse_to_dense_kernel, (unsigned)((n + 7) / 8), 256u, (size_t)0, (const uint64_t *)hdr1.data(),
@@ -157,7 +194,23 @@ extern "C" int emu_sparse_step(int64_t n, const int64_t *rowptr, const int32_t *
     std::copy(P.partials.begin(), P.partials.end(), partials_out);
     std::copy(P.accepted.begin(), P.accepted.end(), accepted_out);
     if (pool_words_out) *pool_words_out = (int64_t)top[1];
-    return overflow ? -2 : 0;
+    return overflow ? -2 : (nh > 0 ? 1000 + nh : 0);
+}
+
+extern "C" int emu_sparse_step(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
+                               const double *sumF, const uint8_t *mask, int do_linesearch, int max_inter, double alpha,
+                               double beta, int grid, double *F_out, double *partials_out, int8_t *accepted_out,
+                               int64_t *pool_words_out) {
+    return sparse_step_impl(n, rowptr, col, k, F_in, sumF, mask, do_linesearch, max_inter, alpha, beta, grid, 0, F_out,
+                            partials_out, accepted_out, pool_words_out);
+}
+
+// returns 1000 + number of split hubs on success
+extern "C" int emu_sparse_step_hubs(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
+                                    const double *sumF, const uint8_t *mask, int do_linesearch, int max_inter, double alpha,
+                                    double beta, int hub_deg, double *F_out, double *partials_out, int8_t *accepted_out) {
+    return sparse_step_impl(n, rowptr, col, k, F_in, sumF, mask, do_linesearch, max_inter, alpha, beta, 1, hub_deg, F_out,
+                            partials_out, accepted_out, nullptr);
 }
 
 // Node-partitioned step over sparse rows, `world` ranks emulated one after the other: every rank owns the nodes
@@ -215,8 +268,9 @@ extern "C" int emu_sparse_step_ranks(int64_t n, const int64_t *rowptr, const int
                 sp.peer_pool[sp.n_peers] = pool_out[q].data();
                 ++sp.n_peers;
             }
-        if (sp.n_peers > 0) emu::launch(sparse_step_kernel<true>, 1u, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
-        else emu::launch(sparse_step_kernel<false>, 1u, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
+        sp.hub_work = nullptr;
+        if (sp.n_peers > 0) emu::launch(sparse_step_kernel<true, false>, 1u, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
+        else emu::launch(sparse_step_kernel<false, false>, 1u, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
         for (size_t i = 0; i < partials.size(); ++i) partials[i] += P.partials[i];          // the all-reduce
     }
     for (int r = 0; r < world; ++r) {

@@ -26,6 +26,8 @@ def emu():
     if lib.has_sparse:
         lib.emu_sparse_step.restype = C.c_int
         lib.emu_sparse_step.argtypes = step_args + [C.POINTER(C.c_int64)]
+        lib.emu_sparse_step_hubs.restype = C.c_int
+        lib.emu_sparse_step_hubs.argtypes = step_args
         lib.emu_sparse_step_ranks.restype = C.c_int
         lib.emu_sparse_step_ranks.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int,
                                               C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -180,3 +182,48 @@ def test_sparse_kernel_source_node_partitioned_pushes(emu, oracle, world):
         assert np.array_equal(Fo[0], Fo[w])                       # identical replicas
     nupd = int(round(partials[2 * ld + 1]))
     check(Fo[0], sumF - partials[:k] if nupd else sumF, partials[2 * ld], nupd, acc, r, oracle.llh(rp, col, F, sumF, P))
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("masked,linesearch", [(False, True), (True, True), (False, False)])
+def test_sparse_kernel_source_split_hubs(emu, oracle, masked, linesearch):
+    """Hubs of 700 and 300 edges split into 256-edge segments over the warps (phases 1-3 through the global
+    scratch), the other nodes on the plain path; also with the larger hub outside the uset and PRE-only."""
+    if not emu.has_sparse:
+        pytest.skip("no sparse-row kernel in this tree")
+    from bigclam_apachespark_b200 import graphs as G
+    n, k = 900, 12
+    rng = np.random.default_rng(33)
+    u = np.concatenate([rng.integers(0, n, 1800), np.zeros(700, dtype=np.int64), np.ones(300, dtype=np.int64)])
+    v = np.concatenate([rng.integers(0, n, 1800), rng.choice(np.arange(2, n), 700, replace=False),
+                        rng.choice(np.arange(2, n), 300, replace=False)])
+    keep = u != v
+    lo, hi = np.minimum(u[keep], v[keep]), np.maximum(u[keep], v[keep])
+    key = np.unique(lo * n + hi)
+    rp, col = G.csr_from_undirected(n, key // n, key % n)
+    assert np.diff(rp)[0] >= 700 and np.diff(rp)[1] >= 300
+    F = rng.random((n, k)) * (rng.random((n, k)) < 0.3)
+    sumF = oracle.colsum(F)
+    P = oracle.make_params(k)
+    mask = None
+    if masked:
+        mask = np.ones(n, dtype=np.uint8)
+        mask[0] = 0
+    ld = (k + 3) & ~3
+    Fo = np.empty_like(F)
+    partials = np.zeros(2 * ld + 2)
+    acc = np.empty(n, dtype=np.int8)
+    rp64, col32 = np.ascontiguousarray(rp, dtype=np.int64), np.ascontiguousarray(col, dtype=np.int32)
+    rc = emu.emu_sparse_step_hubs(n, rp64.ctypes.data, col32.ctypes.data, k, F.ctypes.data, sumF.ctypes.data,
+                                  None if mask is None else mask.ctypes.data, 1 if linesearch else 0, 15, 0.05, 0.1, 280,
+                                  Fo.ctypes.data, partials.ctypes.data, acc.ctypes.data)
+    assert rc == 1002                                           # two split hubs
+    llh_pre, nupd = partials[2 * ld], int(round(partials[2 * ld + 1]))
+    assert abs(llh_pre - oracle.llh(rp, col, F, sumF, P)) <= 1e-10 * abs(llh_pre)
+    if not linesearch:
+        assert np.array_equal(Fo, F) and nupd == 0
+        return
+    r = oracle.step(rp, col, F, sumF, P, node_mask=mask)
+    check(Fo, sumF - partials[:k] if nupd else sumF, llh_pre, nupd, acc, r, oracle.llh(rp, col, F, sumF, P))
+    if masked:
+        assert np.array_equal(Fo[0], F[0])

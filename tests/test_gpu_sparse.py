@@ -126,3 +126,39 @@ def test_sparse_mode_limits():
     b.set_graph(rp, col)
     with pytest.raises(_lib.BigclamError):
         b.set_K(300)                                     # K <= 256 in this mode
+
+
+def test_sparse_split_hubs(oracle, monkeypatch):
+    """Hubs split into 256-edge segments over warps (phases 1-3 through the global scratch); the threshold is
+    lowered through the test knob BIGCLAM_SPARSE_HUB_DEG so that a small graph has split hubs."""
+    monkeypatch.setenv("BIGCLAM_SPARSE_HUB_DEG", "200")
+    n, k = 4000, 40
+    rp, col = random_graph(n, 6, seed=17, hub=1500)
+    assert np.diff(rp).max() >= 1500
+    rng = np.random.default_rng(17)
+    F0 = rng.random((n, k)) * (rng.random((n, k)) < 0.2)
+    sumF = oracle.colsum(F0)
+    b = _solver(rp, col, k, F0, sumF)
+    F, s = F0, sumF
+    for it in range(3):
+        llh = b.backtrackingLineSearchs()
+        r = oracle.step(rp, col, F, s, oracle.make_params(k))
+        _check_step(b, r, llh, max_flips=2, where=f"sparse hubs it{it}")
+        F, s = b.F, b.sumF
+    b.close()
+
+
+def test_sparse_rmat_skewed_graph(oracle, graphs):
+    rp, col = graphs.rmat_graph(20000, 200000, seed=42)
+    n, k = len(rp) - 1, 32
+    rng = np.random.default_rng(2)
+    F0 = rng.random((n, k)) * (rng.random((n, k)) < 0.15)
+    sumF = oracle.colsum(F0)
+    b = _solver(rp, col, k, F0, sumF)
+    F, s = F0, sumF
+    for it in range(2):
+        llh = b.backtrackingLineSearchs()
+        r = oracle.step(rp, col, F, s, oracle.make_params(k))
+        _check_step(b, r, llh, max_flips=3, where=f"sparse rmat it{it}")
+        F, s = b.F, b.sumF
+    b.close()
