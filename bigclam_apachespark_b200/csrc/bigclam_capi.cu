@@ -76,7 +76,7 @@ struct bigclam_ctx {
     uint64_t pool_cap8 = 0;
     unsigned long long *d_pool_top = nullptr;   // [2]
     int32_t *d_overflow = nullptr;
-    int sp_grid = 0;
+    int sp_grid = 0, sp_wpb = kSpWarps;
     size_t sp_smem = 0;
     bool dense_valid = true;       // d_F[cur] mirrors the sparse state (set_F; refreshed on demand by ensure_dense)
     uint64_t region_base8 = 0, region_cap8 = 0;   // this rank's part of every replica's output pool (multi-GPU)
@@ -253,7 +253,7 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
         // sparse rows: a hub is split into kSpHubSeg-edge segments over warps (bigclam_sparse.cuh) when one warp
         // walking it would take a sizeable part of the launch: from a quarter of a warp's share of the owned
         // entries upwards, at least 1024 edges (BIGCLAM_SPARSE_HUB_DEG overrides the threshold: tests)
-        const int64_t sp_per_warp = own_nnz / std::max<int64_t>(1, (int64_t)ctx->sp_grid * kSpWarps);
+        const int64_t sp_per_warp = own_nnz / std::max<int64_t>(1, (int64_t)ctx->sp_grid * ctx->sp_wpb);
         int64_t sp_hub_deg = std::max<int64_t>(1024, sp_per_warp / 4);
         if (const char *ev = std::getenv("BIGCLAM_SPARSE_HUB_DEG")) sp_hub_deg = std::max<int64_t>(1, std::atoll(ev));
         while (nh < cnt && meta[(size_t)nh].deg >= sp_hub_deg) ++nh;
@@ -304,7 +304,7 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
         CU(cudaMalloc(&ctx->d_hub_counters, sizeof(unsigned int) * (2 * slots + 1)));      // + the sparse kernel's item counter
         CU(cudaMemset(ctx->d_hub_counters, 0, sizeof(unsigned int) * (2 * slots + 1)));
     }
-    const unsigned int init = ctx->sparse ? (unsigned int)nh + 3u * (unsigned int)ctx->sp_grid * kSpWarps
+    const unsigned int init = ctx->sparse ? (unsigned int)nh + 3u * (unsigned int)ctx->sp_grid * (unsigned int)ctx->sp_wpb
                                           : (unsigned int)nh + 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
     ctx->h_work_init = init;
     if (ctx->d_work != nullptr) CU(cudaMemcpy(ctx->d_work + 1, &init, sizeof(unsigned int), cudaMemcpyHostToDevice));
@@ -404,21 +404,22 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     ctx->grid = ctx->num_sms * bps;
     ctx->h_work_init = 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
     if (params->flags & BIGCLAM_F_SPARSE_ROWS) {
-        if (ld > 256 || params->min_f != 0.0 || 2 * ld > kSpEntries) {
-            fail(nullptr, BIGCLAM_EUNSUPPORTED, "bigclam_create: BIGCLAM_F_SPARSE_ROWS needs k <= 256 and min_f == 0");
+        if (params->min_f != 0.0) {
+            fail(nullptr, BIGCLAM_EUNSUPPORTED, "bigclam_create: BIGCLAM_F_SPARSE_ROWS needs min_f == 0");
             free_ctx(ctx);
             return BIGCLAM_EUNSUPPORTED;
         }
         ctx->sparse = true;
-        ctx->sp_smem = sp_block_smem_bytes(ld);
+        ctx->sp_wpb = sp_warps_per_block(ld);
+        ctx->sp_smem = sp_block_smem_bytes(ld, ctx->sp_wpb);
         int sbps = 0;
         CUC(cudaFuncSetAttribute(sparse_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
         CUC(cudaFuncSetAttribute(sparse_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
         CUC(cudaFuncSetAttribute(sparse_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
         CUC(cudaFuncSetAttribute(sparse_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
         int sb2 = 0;                         // the grid must be resident for every variant (hub items wait for each other)
-        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sbps, sparse_step_kernel<true, true>, kSpThreads, ctx->sp_smem));
-        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sb2, sparse_step_kernel<false, false>, kSpThreads, ctx->sp_smem));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sbps, sparse_step_kernel<true, true>, 32 * ctx->sp_wpb, ctx->sp_smem));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sb2, sparse_step_kernel<false, false>, 32 * ctx->sp_wpb, ctx->sp_smem));
         sbps = std::min(sbps, sb2);
         if (sbps <= 0) {
             fail(nullptr, BIGCLAM_ECUDA, "bigclam_create: sparse kernel does not fit an SM (smem %zu B)", ctx->sp_smem);
@@ -426,7 +427,7 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
             return BIGCLAM_ECUDA;
         }
         ctx->sp_grid = ctx->num_sms * sbps;
-        ctx->h_work_init = 3u * (unsigned int)ctx->sp_grid * kSpWarps;
+        ctx->h_work_init = 3u * (unsigned int)ctx->sp_grid * (unsigned int)ctx->sp_wpb;
     }
 
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -697,10 +698,10 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
         }
         sp.hub_work = ctx->d_hub_counters + 2 * (size_t)std::max<int32_t>(1, ctx->n_mega);
         const bool hub = a.n_hub_items > 0, push = sp.n_peers > 0;
-        if (hub && push) sparse_step_kernel<true, true><<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
-        else if (hub) sparse_step_kernel<false, true><<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
-        else if (push) sparse_step_kernel<true, false><<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
-        else sparse_step_kernel<false, false><<<ctx->sp_grid, kSpThreads, ctx->sp_smem, ctx->stream>>>(a, sp);
+        if (hub && push) sparse_step_kernel<true, true><<<ctx->sp_grid, 32 * ctx->sp_wpb, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else if (hub) sparse_step_kernel<false, true><<<ctx->sp_grid, 32 * ctx->sp_wpb, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else if (push) sparse_step_kernel<true, false><<<ctx->sp_grid, 32 * ctx->sp_wpb, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else sparse_step_kernel<false, false><<<ctx->sp_grid, 32 * ctx->sp_wpb, ctx->sp_smem, ctx->stream>>>(a, sp);
     } else {
         launch_step(ctx->c2, a, ctx->grid, ctx->smem_bytes, ctx->stream);
     }

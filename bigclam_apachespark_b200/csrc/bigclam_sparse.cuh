@@ -33,9 +33,10 @@
 
 namespace bigclam {
 
-constexpr int kSpWarps = 8;
+constexpr int kSpWarps = 8;            // warps per block at most (ld <= 256); wide rows run fewer (sp_warps_per_block)
 constexpr int kSpThreads = kSpWarps * 32;
-constexpr int kSpEntries = 512;        // staged neighbour entries per chunk; >= 2 * ld so that one row always fits
+// staged neighbour entries per chunk: at least one full row always fits
+__host__ __device__ inline int sp_entries(int ld) { return ld > 512 ? ld : 512; }
 
 __host__ __device__ inline uint64_t sp_pack(uint64_t off8, uint32_t cnt) { return (off8 << 24) | (uint64_t)cnt; }
 __host__ __device__ inline uint32_t sp_cnt(uint64_t h) { return (uint32_t)(h & 0xffffffull); }
@@ -62,21 +63,32 @@ struct SparseArgs {
     unsigned int *hub_work;            // next hub item to hand out (zeroed per launch); items: StepArgs::hub_items
 };
 
-// per-warp shared memory: fu_d[ld] | g_d[ld] | ent_val[E] | ent_idx[E] u16 | aidx[256] u16 | poff[40] u16
+// per-warp shared memory: fu_d[ld] | g_d[ld] | ent_val[E] | ent_idx[E] u16 | aidx[max(ld, 256)] u16 | poff[40] u16
 __host__ __device__ inline size_t sp_warp_bytes(int ld) {
-    return sizeof(double) * 2 * (size_t)ld + (size_t)kSpEntries * 10 + 2 * (size_t)kMaxActiveCap + 2 * 40;
+    return sizeof(double) * 2 * (size_t)ld + (size_t)sp_entries(ld) * 10 + 2 * (size_t)(ld > 256 ? ld : 256) + 2 * 40;
 }
-// block: steps[kMaxSteps] | sumF[ld] | D[ld] | kSpWarps x warp area
-__host__ __device__ inline size_t sp_block_smem_bytes(int ld) {
-    return sizeof(double) * (kMaxSteps + 2 * (size_t)ld) + (size_t)kSpWarps * sp_warp_bytes(ld);
+// block: steps[kMaxSteps] | sumF[ld] | D[ld] | wpb x warp area
+__host__ __device__ inline size_t sp_block_smem_bytes(int ld, int wpb) {
+    return sizeof(double) * (kMaxSteps + 2 * (size_t)ld) + (size_t)wpb * sp_warp_bytes(ld);
+}
+// warps per block: as many resident warps per SM as the shared memory (227 KB, 1 KB reserved per block) allows
+inline int sp_warps_per_block(int ld) {
+    int best = 1, best_warps = 0;
+    for (int wpb = kSpWarps; wpb >= 1; wpb >>= 1) {
+        const size_t bytes = sp_block_smem_bytes(ld, wpb) + 1024 + 256;
+        const int blocks = (int)((size_t)233472 / bytes);
+        const int warps = (blocks > 3 ? 3 : blocks) * wpb;         // the kernel is built for at most 3 blocks per SM
+        if (warps > best_warps) { best_warps = warps; best = wpb; }
+    }
+    return best;
 }
 
 // Stages the rows of up to 32 neighbours (ids colp[0 .. cnt32)) of one node into the warp's entry buffer: the
-// longest prefix of them whose entries fit (at least one: a row has at most ld <= kSpEntries / 2 entries).
+// longest prefix of them whose entries fit the `cap` entries of the buffer (at least one: a row has at most ld <= cap).
 // Returns the number ne of staged neighbours; poff[e] .. poff[e + 1] is row e's range in the buffer.
 // (noinline, scalar arguments only: one copy in the code, called from PRE and from the line search.)
 __device__ __noinline__ int sp_stage_chunk(const uint64_t *__restrict__ hdr_in, const double *__restrict__ pool_in,
-                                           const int32_t *__restrict__ colp, int cnt32, int lane, double *ent_val,
+                                           const int32_t *__restrict__ colp, int cnt32, int lane, int cap, double *ent_val,
                                            unsigned short *ent_idx, unsigned short *poff) {
     const int v = (lane < cnt32) ? colp[lane] : 0;
     const uint64_t hv = (lane < cnt32) ? __ldg(hdr_in + v) : 0ull;
@@ -87,7 +99,7 @@ __device__ __noinline__ int sp_stage_chunk(const uint64_t *__restrict__ hdr_in, 
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    const unsigned fit = __ballot_sync(0xffffffffu, (lane < cnt32) && (incl <= kSpEntries));
+    const unsigned fit = __ballot_sync(0xffffffffu, (lane < cnt32) && (incl <= cap));
     const int ne = __popc(fit);                     // incl is monotone: the fitting lanes are 0 .. ne-1
     const int beg = incl - cv;
     if (lane == 0) poff[0] = 0;
@@ -130,6 +142,8 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ld = a.ld;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int wpb = (int)(blockDim.x >> 5), nthreads = (int)blockDim.x;
+    const int ecap = sp_entries(ld);
     double *s_steps = reinterpret_cast<double *>(smem_raw);
     double *s_sumF = s_steps + kMaxSteps;
     double *s_D = s_sumF + ld;
@@ -137,14 +151,14 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
     double *fu_d = reinterpret_cast<double *>(wbase);
     double *g_d = fu_d + ld;
     double *ent_val = g_d + ld;
-    unsigned short *ent_idx = reinterpret_cast<unsigned short *>(ent_val + kSpEntries);
-    unsigned short *aidx = ent_idx + kSpEntries;
-    unsigned short *poff = aidx + kMaxActiveCap;
+    unsigned short *ent_idx = reinterpret_cast<unsigned short *>(ent_val + ecap);
+    unsigned short *aidx = ent_idx + ecap;
+    unsigned short *poff = aidx + (ld > 256 ? ld : 256);
 
 #pragma unroll 1
-    for (int i = threadIdx.x; i < ld; i += kSpThreads) { s_sumF[i] = a.sumF[i]; s_D[i] = 0.0; }
+    for (int i = threadIdx.x; i < ld; i += nthreads) { s_sumF[i] = a.sumF[i]; s_D[i] = 0.0; }
 #pragma unroll 1
-    for (int i = threadIdx.x; i < kMaxSteps; i += kSpThreads) s_steps[i] = a.steps[i];
+    for (int i = threadIdx.x; i < kMaxSteps; i += nthreads) s_steps[i] = a.steps[i];
 #pragma unroll 1
     for (int i = lane; i < ld; i += 32) { fu_d[i] = 0.0; g_d[i] = 0.0; }
     __syncthreads();
@@ -166,7 +180,7 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
         nchunks = 0;
         ne_last = 0;
         for (int cb = eb; cb < ee;) {
-            const int ne = sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, ee - cb), lane, ent_val, ent_idx, poff);
+            const int ne = sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, ee - cb), lane, ecap, ent_val, ent_idx, poff);
             double x = 0.0;
             if (lane < ne) {
                 const int end = poff[lane + 1];
@@ -224,7 +238,7 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
         double sumterms = 0.0;
         for (int cb = eb; cb < ee;) {
             const int ne = (staged > 0) ? staged
-                                        : sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, ee - cb), lane, ent_val, ent_idx, poff);
+                                        : sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, ee - cb), lane, ecap, ent_val, ent_idx, poff);
 #pragma unroll 1
             for (int e2 = 0; e2 < ne; e2 += 4) {
                 const int eA = e2 + h, eB = e2 + 2 + h;
@@ -425,8 +439,8 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
 
     // positions n_hubs .. n_hubs + 3*#warps - 1 are pre-assigned, the rest is handed out by the work counter two
     // nodes ahead
-    const int64_t nwarps = (int64_t)gridDim.x * kSpWarps;
-    int64_t pos = (kHub ? (int64_t)a.n_hubs : 0) + (int64_t)blockIdx.x * kSpWarps + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
+    int64_t pos = (kHub ? (int64_t)a.n_hubs : 0) + (int64_t)blockIdx.x * wpb + wib;
     int64_t pos_n = pos + nwarps, pos_nn = pos + 2 * nwarps;
     NodeMeta cur = {0, 0, 0}, nxt = {0, 0, 0};
     if (pos < order_n) cur = a.meta[pos];
@@ -501,7 +515,7 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
     // ---------------- block reduction of the partials ----------------
     __syncthreads();
     if (a.do_linesearch) {
-        for (int i = threadIdx.x; i < ld; i += kSpThreads) {
+        for (int i = threadIdx.x; i < ld; i += nthreads) {
             const double v = s_D[i];
             if (v != 0.0) atomicAdd(a.partials + i, v);
         }
@@ -512,7 +526,8 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
     if (threadIdx.x == 0) {
         double l = 0.0, c = 0.0;
 #pragma unroll
-        for (int w = 0; w < kSpWarps; ++w) { l += s_red[w]; c += s_red[kSpWarps + w]; }
+        for (int w = 0; w < kSpWarps; ++w)
+            if (w < wpb) { l += s_red[w]; c += s_red[kSpWarps + w]; }
         atomicAdd(a.partials + 2 * ld, l);
         if (c != 0.0) atomicAdd(a.partials + 2 * ld + 1, c);
     }

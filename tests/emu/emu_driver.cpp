@@ -126,9 +126,9 @@ static int sparse_step_impl(int64_t n, const int64_t *rowptr, const int32_t *col
                             int64_t *pool_words_out) {
     Problem P;
     unsigned work = 0;
-    setup(P, n, rowptr, col, k, F_in, sumF, mask, do_linesearch, max_inter, alpha, beta, &work, 3u * (unsigned)grid * kSpWarps);
+    setup(P, n, rowptr, col, k, F_in, sumF, mask, do_linesearch, max_inter, alpha, beta, &work, 3u * (unsigned)grid * (unsigned)sp_warps_per_block((k + 3) & ~3));
     const int ld = P.ld;
-    if (ld > 256) return -1;
+    if (ld > 1024) return -1;
     const uint64_t cap8 = (uint64_t)n * sp_words((uint32_t)ld);
     std::vector<uint64_t> hdr0(n, 0), hdr1(n, 0);
     std::vector<double> pool0(cap8 + 8, 0.0), pool1(cap8 + 8, 0.0);
@@ -181,9 +181,9 @@ static int sparse_step_impl(int64_t n, const int64_t *rowptr, const int32_t *col
     P.a.hub_scratch = scratch.data();
     P.a.hub_counters = counters.data();
     sp.hub_work = counters.data() + 2 * (size_t)std::max(1, nh);
-    work = (unsigned)nh + 3u * (unsigned)grid * kSpWarps;
-    if (nh > 0) emu::launch(sparse_step_kernel<false, true>, (unsigned)grid, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
-    else emu::launch(sparse_step_kernel<false, false>, (unsigned)grid, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
+    work = (unsigned)nh + 3u * (unsigned)grid * (unsigned)sp_warps_per_block((k + 3) & ~3);
+    if (nh > 0) emu::launch(sparse_step_kernel<false, true>, (unsigned)grid, 32u * (unsigned)sp_warps_per_block(ld), sp_block_smem_bytes(ld, sp_warps_per_block(ld)), P.a, sp);
+    else emu::launch(sparse_step_kernel<false, false>, (unsigned)grid, 32u * (unsigned)sp_warps_per_block(ld), sp_block_smem_bytes(ld, sp_warps_per_block(ld)), P.a, sp);
     std::vector<double> Fo((size_t)n * ld, 0.0);
     if (do_linesearch)
         emu::launch(sparse_to_dense_kernel, (unsigned)((n + 7) / 8), 256u, (size_t)0, (const uint64_t *)hdr1.data(),
@@ -223,9 +223,9 @@ extern "C" int emu_sparse_step_ranks(int64_t n, const int64_t *rowptr, const int
     if (world < 1 || world > 8) return -1;
     Problem P0;
     unsigned work = 0;
-    setup(P0, n, rowptr, col, k, F_in, sumF, nullptr, 1, max_inter, alpha, beta, &work, 3u * kSpWarps);
+    setup(P0, n, rowptr, col, k, F_in, sumF, nullptr, 1, max_inter, alpha, beta, &work, 3u * (unsigned)sp_warps_per_block((k + 3) & ~3));
     const int ld = P0.ld;
-    if (ld > 256) return -1;
+    if (ld > 1024) return -1;
     const uint64_t cap8 = (uint64_t)n * sp_words((uint32_t)ld);
     // one input replica is enough here (it is only read); every rank has its own output replica
     std::vector<uint64_t> hdr_in(n, 0);
@@ -248,7 +248,7 @@ extern "C" int emu_sparse_step_ranks(int64_t n, const int64_t *rowptr, const int
         P.a.sumF = P.sumF.data();
         P.a.partials = P.partials.data();
         P.a.accepted = accepted.data();
-        unsigned w = 3u * kSpWarps;
+        unsigned w = 3u * (unsigned)sp_warps_per_block((k + 3) & ~3);
         P.a.work_counter = &w;
         unsigned long long top = 0;
         SparseArgs sp;
@@ -269,8 +269,8 @@ extern "C" int emu_sparse_step_ranks(int64_t n, const int64_t *rowptr, const int
                 ++sp.n_peers;
             }
         sp.hub_work = nullptr;
-        if (sp.n_peers > 0) emu::launch(sparse_step_kernel<true, false>, 1u, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
-        else emu::launch(sparse_step_kernel<false, false>, 1u, (unsigned)kSpThreads, sp_block_smem_bytes(ld), P.a, sp);
+        if (sp.n_peers > 0) emu::launch(sparse_step_kernel<true, false>, 1u, 32u * (unsigned)sp_warps_per_block(ld), sp_block_smem_bytes(ld, sp_warps_per_block(ld)), P.a, sp);
+        else emu::launch(sparse_step_kernel<false, false>, 1u, 32u * (unsigned)sp_warps_per_block(ld), sp_block_smem_bytes(ld, sp_warps_per_block(ld)), P.a, sp);
         for (size_t i = 0; i < partials.size(); ++i) partials[i] += P.partials[i];          // the all-reduce
     }
     for (int r = 0; r < world; ++r) {

@@ -90,7 +90,7 @@ def check(F, s, llh_pre, nupd, acc, r, oracle_llh_pre, max_flips=0):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("k,grid", [(5, 1), (12, 2), (40, 1), (200, 1)])
+@pytest.mark.parametrize("k,grid", [(5, 1), (12, 2), (40, 1), (200, 1), (300, 2), (1000, 1)])
 def test_sparse_kernel_source_against_oracle(emu, oracle, k, grid):
     n = 96
     rp, col = random_graph(n, 5, seed=k, hub=40)

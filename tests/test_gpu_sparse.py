@@ -16,7 +16,7 @@ def _solver(rp, col, K, F0, sumF=None, **kw):
     return b
 
 
-@pytest.mark.parametrize("k", [1, 2, 3, 5, 10, 31, 64, 65, 100, 200, 256])
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 10, 31, 64, 65, 100, 200, 256, 257, 500, 1000])
 def test_sparse_single_step_all_k(oracle, k):
     n = 400
     rp, col = random_graph(n, 6, seed=k, hub=60)
@@ -123,9 +123,10 @@ def test_sparse_mode_limits():
     rp = np.array([0, 1, 2], dtype=np.int64)
     col = np.array([1, 0], dtype=np.int32)
     b = BigClam(sparse_rows=True)
+    b.MIN_F_ = 0.5                                       # the sparse layout presumes MIN_F_ == 0 (zeros are not stored)
     b.set_graph(rp, col)
     with pytest.raises(_lib.BigclamError):
-        b.set_K(300)                                     # K <= 256 in this mode
+        b.set_K(4)
 
 
 def test_sparse_split_hubs(oracle, monkeypatch):
