@@ -86,6 +86,9 @@ SIGNATURES = {
     "bigclam_ipc_open_peers": (C.c_int, [_vp, _i32, _i32, _vp]),
     "bigclam_mark_all_changed": (C.c_int, [_vp]),
     "bigclam_ipc_handle_count": (C.c_int, [_vp]),
+    "bigclam_set_F_csr": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "bigclam_get_F_nnz": (C.c_int, [_vp, _pi64]),
+    "bigclam_get_F_csr": (C.c_int, [_vp, _vp, _vp, _vp]),
     "bigclam_set_pool_region": (C.c_int, [_vp, _i64, _i64]),
     "bigclam_graph_read_edgelist": (C.c_int, [C.c_char_p, _i32, C.POINTER(Graph), C.c_char_p, _i64]),
     "bigclam_graph_free": (None, [C.POINTER(Graph)]),

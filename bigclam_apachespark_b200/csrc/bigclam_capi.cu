@@ -435,8 +435,10 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     const size_t fbytes = sizeof(double) * (size_t)n * (size_t)ld;
     CUC(cudaMalloc(&ctx->d_rowptr, sizeof(int64_t) * ((size_t)n + 1)));
     CUC(cudaMalloc(&ctx->d_col, sizeof(int32_t) * std::max<size_t>(1, (size_t)nnz)));
-    CUC(cudaMalloc(&ctx->d_F[0], fbytes));
-    CUC(cudaMalloc(&ctx->d_F[1], fbytes));
+    if (!ctx->sparse) {            // sparse rows: the dense buffers are only a mirror, allocated on first use (alloc_dense)
+        CUC(cudaMalloc(&ctx->d_F[0], fbytes));
+        CUC(cudaMalloc(&ctx->d_F[1], fbytes));
+    }
     CUC(cudaMalloc(&ctx->d_sumF[0], sizeof(double) * ld));
     CUC(cudaMalloc(&ctx->d_sumF[1], sizeof(double) * ld));
     CUC(cudaMalloc(&ctx->d_partials, sizeof(double) * (2 * (size_t)ld + 2)));
@@ -450,8 +452,10 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     CUC(cudaMallocHost(&ctx->h_pinned, sizeof(double) * (2 * (size_t)ld + 2) + sizeof(RunState) + 64));
     CUC(cudaMemcpy(ctx->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
     if (nnz > 0) CUC(cudaMemcpy(ctx->d_col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
-    CUC(cudaMemset(ctx->d_F[0], 0, fbytes));
-    CUC(cudaMemset(ctx->d_F[1], 0, fbytes));
+    if (!ctx->sparse) {
+        CUC(cudaMemset(ctx->d_F[0], 0, fbytes));
+        CUC(cudaMemset(ctx->d_F[1], 0, fbytes));
+    }
     CUC(cudaMemset(ctx->d_sumF[0], 0, sizeof(double) * ld));
     CUC(cudaMemset(ctx->d_sumF[1], 0, sizeof(double) * ld));
     CUC(cudaMemset(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ld + 2)));
@@ -459,8 +463,16 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     CUC(cudaMemset(ctx->d_done, 0, sizeof(int32_t)));
     CUC(cudaMemset(ctx->d_state, 0, sizeof(RunState)));
     if (ctx->sparse) {
-        // worst case: every row full (ld entries) — a step can then never overflow its pool
+        // worst case: every row full (ld entries) — a step can then never overflow its pool.  When two such
+        // pools do not fit in 80 % of the free memory, each pool gets 40 % of it and a step that runs out reports
+        // BIGCLAM_ENOMEM (its input is untouched).  BIGCLAM_SPARSE_POOL_WORDS overrides the size (tests).
         ctx->pool_cap8 = (uint64_t)n * sp_words((uint32_t)ld);
+        {
+            size_t free_b = 0, total_b = 0;
+            CUC(cudaMemGetInfo(&free_b, &total_b));
+            if ((double)ctx->pool_cap8 * 16.0 > 0.8 * (double)free_b) ctx->pool_cap8 = (uint64_t)(0.4 * (double)free_b / 8.0);
+            if (const char *ev = std::getenv("BIGCLAM_SPARSE_POOL_WORDS")) ctx->pool_cap8 = (uint64_t)std::max<long long>(64, std::atoll(ev));
+        }
         ctx->region_base8 = 0;
         ctx->region_cap8 = ctx->pool_cap8;
         for (int b = 0; b < 2; ++b) {
@@ -520,6 +532,13 @@ static int colsum_current(bigclam_ctx *ctx) {
     return BIGCLAM_OK;
 }
 
+// Sparse mode: the dense n x ld buffers exist only while somebody needs dense rows.
+static int alloc_dense(bigclam_ctx *ctx, int b) {
+    if (ctx->d_F[b] != nullptr) return BIGCLAM_OK;
+    CU(cudaMalloc(&ctx->d_F[b], sizeof(double) * (size_t)ctx->n * (size_t)ctx->ld));
+    return BIGCLAM_OK;
+}
+
 // Sparse mode: rebuild the sparse rows of the current buffer from its dense mirror d_F[cur].
 static int sparse_from_dense(bigclam_ctx *ctx) {
     const int b = ctx->cur;
@@ -535,8 +554,9 @@ static int sparse_from_dense(bigclam_ctx *ctx) {
 
 // Sparse mode: entry points that hand out dense rows refresh the mirror d_F[cur] first.
 static int ensure_dense(bigclam_ctx *ctx) {
-    if (!ctx->sparse || ctx->dense_valid) return BIGCLAM_OK;
+    if (!ctx->sparse || (ctx->dense_valid && ctx->d_F[ctx->cur] != nullptr)) return BIGCLAM_OK;
     const int b = ctx->cur;
+    if (int ra = alloc_dense(ctx, b)) return ra;
     const int wpb = 8;
     sparse_to_dense_kernel<<<(unsigned)((ctx->n + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
         ctx->d_hdr[b], ctx->d_pool[b], ctx->n, ctx->ld, ctx->d_F[b]);
@@ -562,16 +582,129 @@ extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
     CU(cudaSetDevice(ctx->device));
     if (int rd = drop_speculation(ctx)) return rd;
     const int k = ctx->p.k, ld = ctx->ld;
+    if (ctx->sparse) { if (int ra = alloc_dense(ctx, ctx->cur)) return ra; }
     // values must already satisfy the invariant the reference maintains: MIN_F <= F <= MAX_F
     CU(cudaMemsetAsync(ctx->d_F[ctx->cur], 0, sizeof(double) * (size_t)ctx->n * ld, ctx->stream));
     CU(cudaMemcpy2DAsync(ctx->d_F[ctx->cur], sizeof(double) * ld, F, sizeof(double) * k, sizeof(double) * k,
                          (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
     int rc = colsum_current(ctx);
     if (rc != BIGCLAM_OK) return rc;
-    if (ctx->sparse) { rc = sparse_from_dense(ctx); if (rc != BIGCLAM_OK) return rc; }
+    if (ctx->sparse) {
+        rc = sparse_from_dense(ctx);
+        if (rc == BIGCLAM_OK) rc = check_overflow(ctx);        // a pool smaller than the rows: BIGCLAM_ENOMEM
+        if (rc != BIGCLAM_OK) return rc;
+    }
     // with peer replicas every row counts as changed again: the next step publishes all owned rows
     if (ctx->d_changed != nullptr) CU(cudaMemsetAsync(ctx->d_changed, 1, (size_t)ctx->n, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return BIGCLAM_OK;
+}
+
+// F given / returned as CSR rows — the shape of the reference's RDD[(Long, BSV[Double])] (bigclam4-7.scala:97-104).
+// With BIGCLAM_F_SPARSE_ROWS nothing dense is ever materialised (n x K may not fit anywhere); a dense context
+// goes through a dense host image.
+extern "C" int bigclam_set_F_csr(bigclam_ctx *ctx, const int64_t *indptr, const int32_t *indices, const double *values) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (indptr == nullptr || (indptr[ctx->n] > 0 && (indices == nullptr || values == nullptr)))
+        return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_F_csr: NULL argument");
+    const int64_t n = ctx->n;
+    const int32_t k = ctx->p.k, ld = ctx->ld;
+    if (!ctx->sparse) {
+        std::vector<double> dense((size_t)n * k, 0.0);
+        for (int64_t u = 0; u < n; ++u)
+            for (int64_t i = indptr[u]; i < indptr[u + 1]; ++i) {
+                if (indices[i] < 0 || indices[i] >= k) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_F_csr: index out of range in row %lld", (long long)u);
+                dense[(size_t)u * k + indices[i]] = values[i];
+            }
+        return bigclam_set_F(ctx, dense.data());
+    }
+    CU(cudaSetDevice(ctx->device));
+    if (int rd = drop_speculation(ctx)) return rd;
+    uint64_t need = 0;
+    for (int64_t u = 0; u < n; ++u) {
+        uint32_t cnt = 0;
+        for (int64_t i = indptr[u]; i < indptr[u + 1]; ++i) cnt += (values[i] != 0.0);
+        need += sp_words(cnt);
+    }
+    if (need > ctx->pool_cap8) return fail(ctx, BIGCLAM_ENOMEM, "bigclam_set_F_csr: rows need %llu pool words, %llu available", (unsigned long long)need, (unsigned long long)ctx->pool_cap8);
+    std::vector<uint64_t> hdr((size_t)n);
+    std::vector<double> pool((size_t)need + 1), colsum((size_t)ld, 0.0);
+    const int64_t used = sp_host_pack(n, k, ld, indptr, indices, values, hdr.data(), pool.data(), need, colsum.data());
+    if (used < 0) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_F_csr: index outside [0, k) or more than ld entries in a row");
+    const int b = ctx->cur;
+    const unsigned long long top = (unsigned long long)used;
+    CU(cudaMemcpyAsync(ctx->d_hdr[b], hdr.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (used > 0) CU(cudaMemcpyAsync(ctx->d_pool[b], pool.data(), sizeof(double) * (size_t)used, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_pool_top + b, &top, sizeof(top), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_sumF[b], colsum.data(), sizeof(double) * (size_t)ld, cudaMemcpyHostToDevice, ctx->stream));   // :105-106
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->dense_valid = false;
+    return BIGCLAM_OK;
+}
+
+// Downloads the sparse state (sparse context) or the dense F (dense context) for the two getters below.
+static int fetch_rows_host(bigclam_ctx *ctx, std::vector<uint64_t> &hdr, std::vector<double> &pool, std::vector<double> &dense) {
+    const int64_t n = ctx->n;
+    if (ctx->sparse) {
+        const int b = ctx->cur;
+        hdr.resize((size_t)n);
+        CU(cudaMemcpyAsync(hdr.data(), ctx->d_hdr[b], sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        uint64_t extent = 0;
+        for (int64_t u = 0; u < n; ++u)
+            if (sp_cnt(hdr[u]) > 0) extent = std::max<uint64_t>(extent, sp_off8(hdr[u]) + sp_words(sp_cnt(hdr[u])));
+        pool.resize((size_t)extent + 1);
+        if (extent > 0) CU(cudaMemcpyAsync(pool.data(), ctx->d_pool[b], sizeof(double) * (size_t)extent, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return BIGCLAM_OK;
+    }
+    dense.resize((size_t)n * ctx->p.k);
+    return bigclam_get_F(ctx, dense.data());
+}
+
+extern "C" int bigclam_get_F_nnz(bigclam_ctx *ctx, int64_t *nnz_out) {
+    if (ctx == nullptr || nnz_out == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> hdr;
+    std::vector<double> pool, dense;
+    if (ctx->sparse) {                       // the headers are enough
+        hdr.resize((size_t)ctx->n);
+        CU(cudaMemcpyAsync(hdr.data(), ctx->d_hdr[ctx->cur], sizeof(uint64_t) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        *nnz_out = sp_host_nnz(ctx->n, hdr.data());
+        return BIGCLAM_OK;
+    }
+    if (int rf = fetch_rows_host(ctx, hdr, pool, dense)) return rf;
+    int64_t t = 0;
+    for (double v : dense) t += (v != 0.0);
+    *nnz_out = t;
+    return BIGCLAM_OK;
+}
+
+// indptr_out: n + 1; indices_out / values_out: bigclam_get_F_nnz() entries (ascending indices inside a row).
+extern "C" int bigclam_get_F_csr(bigclam_ctx *ctx, int64_t *indptr_out, int32_t *indices_out, double *values_out) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (indptr_out == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_get_F_csr: indptr_out is NULL");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> hdr;
+    std::vector<double> pool, dense;
+    if (int rf = fetch_rows_host(ctx, hdr, pool, dense)) return rf;
+    if (ctx->sparse) {
+        if (sp_host_nnz(ctx->n, hdr.data()) > 0 && (indices_out == nullptr || values_out == nullptr))
+            return fail(ctx, BIGCLAM_EINVAL, "bigclam_get_F_csr: NULL output");
+        sp_host_unpack(ctx->n, hdr.data(), pool.data(), indptr_out, indices_out, values_out);
+        return BIGCLAM_OK;
+    }
+    int64_t t = 0;
+    const int k = ctx->p.k;
+    for (int64_t u = 0; u < ctx->n; ++u) {
+        indptr_out[u] = t;
+        for (int c = 0; c < k; ++c) {
+            const double v = dense[(size_t)u * k + c];
+            if (v != 0.0) { indices_out[t] = c; values_out[t] = v; ++t; }
+        }
+    }
+    indptr_out[ctx->n] = t;
     return BIGCLAM_OK;
 }
 
@@ -677,7 +810,7 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
     CU(cudaMemcpyAsync(ctx->d_work, ctx->d_work + 1, sizeof(unsigned int), cudaMemcpyDeviceToDevice, ctx->stream));
     if (ctx->sparse) {
         // reads hdr/pool of the current buffer, writes the other one (its bump allocator starts at zero)
-        const int in = (a.F_in == ctx->d_F[0]) ? 0 : 1, out = in ^ 1;
+        const int in = ctx->cur, out = in ^ 1;
         SparseArgs sp;
         sp.hdr_in = ctx->d_hdr[in];
         sp.pool_in = ctx->d_pool[in];

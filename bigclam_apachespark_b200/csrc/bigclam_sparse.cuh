@@ -571,6 +571,61 @@ __global__ void dense_to_sparse_kernel(const double *F, int64_t n, int ld, uint6
     if (lane == 0) hdr[u] = sp_pack(off, (uint32_t)cnt);
 }
 
+// Host side of the layout: rows given as CSR (indptr, ascending-or-not indices, values; explicit zeros are dropped)
+// -> header + pool image, and back.  Used by bigclam_set_F_csr / bigclam_get_F_csr (and by the emulation tests).
+// Returns the number of 8-byte words used, or -1 for an index outside [0, k) / a row longer than ld.
+inline int64_t sp_host_pack(int64_t n, int32_t k, int32_t ld, const int64_t *indptr, const int32_t *indices, const double *values,
+                            uint64_t *hdr, double *pool, uint64_t pool_cap8, double *colsum /* k, optional */) {
+    uint64_t top = 0;
+    if (colsum != nullptr)
+        for (int32_t c = 0; c < k; ++c) colsum[c] = 0.0;
+    for (int64_t u = 0; u < n; ++u) {
+        uint32_t cnt = 0;
+        for (int64_t i = indptr[u]; i < indptr[u + 1]; ++i) {
+            if (indices[i] < 0 || indices[i] >= k) return -1;
+            if (values[i] != 0.0) ++cnt;
+        }
+        if (cnt > (uint32_t)ld) return -1;
+        const uint64_t words = sp_words(cnt);
+        if (top + words > pool_cap8) return -2;
+        double *ov = pool + top;
+        unsigned short *oi = reinterpret_cast<unsigned short *>(ov + sp_pad(cnt));
+        uint32_t q = 0;
+        for (int64_t i = indptr[u]; i < indptr[u + 1]; ++i) {
+            if (values[i] == 0.0) continue;
+            // insertion keeps the indices ascending (rows arrive sorted in practice: one comparison per entry)
+            uint32_t p = q;
+            while (p > 0 && oi[p - 1] > (unsigned short)indices[i]) { oi[p] = oi[p - 1]; ov[p] = ov[p - 1]; --p; }
+            oi[p] = (unsigned short)indices[i];
+            ov[p] = values[i];
+            ++q;
+            if (colsum != nullptr) colsum[indices[i]] += values[i];
+        }
+        for (uint32_t z = cnt; z < sp_pad(cnt); ++z) { ov[z] = 0.0; oi[z] = 0; }
+        hdr[u] = sp_pack(cnt ? top : 0, cnt);
+        top += words;
+    }
+    return (int64_t)top;
+}
+
+inline int64_t sp_host_nnz(int64_t n, const uint64_t *hdr) {
+    int64_t t = 0;
+    for (int64_t u = 0; u < n; ++u) t += sp_cnt(hdr[u]);
+    return t;
+}
+
+inline void sp_host_unpack(int64_t n, const uint64_t *hdr, const double *pool, int64_t *indptr, int32_t *indices, double *values) {
+    int64_t t = 0;
+    for (int64_t u = 0; u < n; ++u) {
+        indptr[u] = t;
+        const uint32_t cnt = sp_cnt(hdr[u]);
+        const double *ov = pool + sp_off8(hdr[u]);
+        const unsigned short *oi = reinterpret_cast<const unsigned short *>(ov + sp_pad(cnt));
+        for (uint32_t i = 0; i < cnt; ++i) { indices[t] = oi[i]; values[t] = ov[i]; ++t; }
+    }
+    indptr[n] = t;
+}
+
 // Sparse rows -> dense n x ld (rows are zeroed here, no separate memset).
 __global__ void sparse_to_dense_kernel(const uint64_t *hdr, const double *pool, int64_t n, int ld, double *F) {
     const int lane = threadIdx.x & 31;

@@ -128,8 +128,38 @@ class BigClam:
         self._ctx = ctx
         return self
 
+    def set_F_csr(self, indptr, indices, values, K=None, sumF=None):
+        """F <- CSR rows (the reference's RDD[(Long, BSV[Double])], :97-104); sumF <- column sums unless given.
+        With sparse_rows=True no dense n x K image is built anywhere."""
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        if K is not None and (self._ctx is None or int(K) != self.K):
+            self.set_K(int(K))
+        if len(indptr) != self.n + 1 or len(indices) != indptr[-1] or len(values) != indptr[-1]:
+            raise ValueError("CSR arrays do not describe n rows")
+        check(_lib.load().bigclam_set_F_csr(self._need(), indptr.ctypes.data, indices.ctypes.data, values.ctypes.data), self._ctx)
+        if sumF is not None:
+            sumF = np.ascontiguousarray(sumF, dtype=np.float64)
+            check(_lib.load().bigclam_set_sumF(self._ctx, sumF.ctypes.data), self._ctx)
+        return self
+
+    def F_csr(self):
+        """Current F as (indptr, indices, values): ascending indices inside a row, no stored zeros."""
+        lib = _lib.load()
+        nnz = C.c_int64()
+        check(lib.bigclam_get_F_nnz(self._need(), C.byref(nnz)), self._ctx)
+        indptr = np.empty(self.n + 1, dtype=np.int64)
+        indices = np.empty(max(nnz.value, 1), dtype=np.int32)
+        values = np.empty(max(nnz.value, 1), dtype=np.float64)
+        check(lib.bigclam_get_F_csr(self._ctx, indptr.ctypes.data, indices.ctypes.data, values.ctypes.data), self._ctx)
+        return indptr, indices[:nnz.value], values[:nnz.value]
+
     def set_F(self, F, sumF=None):
         """F <- n x K (the result of initNeighborComF); sumF <- column sums unless given."""
+        if hasattr(F, "tocsr"):                 # scipy.sparse matrix
+            m = F.tocsr()
+            return self.set_F_csr(m.indptr, m.indices, m.data, K=m.shape[1], sumF=sumF)
         F = np.ascontiguousarray(F, dtype=np.float64)
         if self._ctx is None or F.shape[1] != self.K:
             self.set_K(F.shape[1])

@@ -166,6 +166,15 @@ int bigclam_mark_all_changed(bigclam_ctx *ctx);
  * output pool is rebuilt per step, so there is no changed-row bookkeeping).
  */
 int bigclam_ipc_handle_count(const bigclam_ctx *ctx);
+/*
+ * F as CSR rows, the shape of the reference's RDD[(Long, BSV[Double])] (bigclam4-7.scala:97-104): indptr[n + 1],
+ * indices (component of each entry, any order inside a row), values.  sumF becomes the column sums (:105-106).
+ * With BIGCLAM_F_SPARSE_ROWS no dense n x K image is ever built.  bigclam_get_F_nnz sizes the output of
+ * bigclam_get_F_csr (ascending indices inside a row, explicit zeros never stored).
+ */
+int bigclam_set_F_csr(bigclam_ctx *ctx, const int64_t *indptr, const int32_t *indices, const double *values);
+int bigclam_get_F_nnz(bigclam_ctx *ctx, int64_t *nnz_out);
+int bigclam_get_F_csr(bigclam_ctx *ctx, int64_t *indptr_out, int32_t *indices_out, double *values_out);
 int bigclam_set_pool_region(bigclam_ctx *ctx, int64_t base_words, int64_t cap_words);
 
 /*

@@ -283,4 +283,23 @@ extern "C" int emu_sparse_step_ranks(int64_t n, const int64_t *rowptr, const int
     std::copy(accepted.begin(), accepted.end(), accepted_out);
     return overflow ? -2 : 0;
 }
+
+// Host packer of the sparse layout (bigclam_set_F_csr) -> sparse_to_dense_kernel -> dense, and unpack again.
+extern "C" int64_t emu_pack_roundtrip(int64_t n, int32_t k, const int64_t *indptr, const int32_t *indices, const double *values,
+                                      double *F_out, double *colsum_out, int64_t *indptr_out, int32_t *indices_out,
+                                      double *values_out) {
+    const int ld = (k + 3) & ~3;
+    const uint64_t cap8 = (uint64_t)n * sp_words((uint32_t)ld);
+    std::vector<uint64_t> hdr(n);
+    std::vector<double> pool(cap8 + 8, -3.0), colsum(ld, 0.0);
+    const int64_t used = sp_host_pack(n, k, ld, indptr, indices, values, hdr.data(), pool.data(), cap8, colsum.data());
+    if (used < 0) return used;
+    std::vector<double> Fo((size_t)n * ld, 0.0);
+    emu::launch(sparse_to_dense_kernel, (unsigned)((n + 7) / 8), 256u, (size_t)0, (const uint64_t *)hdr.data(), (const double *)pool.data(),
+                n, ld, Fo.data());
+    for (int64_t u = 0; u < n; ++u) std::copy(Fo.begin() + u * ld, Fo.begin() + u * ld + k, F_out + u * k);
+    std::copy(colsum.begin(), colsum.begin() + k, colsum_out);
+    sp_host_unpack(n, hdr.data(), pool.data(), indptr_out, indices_out, values_out);
+    return used;
+}
 #endif  // BIGCLAM_EMU_SPARSE

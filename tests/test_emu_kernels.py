@@ -26,6 +26,8 @@ def emu():
     if lib.has_sparse:
         lib.emu_sparse_step.restype = C.c_int
         lib.emu_sparse_step.argtypes = step_args + [C.POINTER(C.c_int64)]
+        lib.emu_pack_roundtrip.restype = C.c_int64
+        lib.emu_pack_roundtrip.argtypes = [C.c_int64, C.c_int32] + [C.c_void_p] * 8
         lib.emu_sparse_step_hubs.restype = C.c_int
         lib.emu_sparse_step_hubs.argtypes = step_args
         lib.emu_sparse_step_ranks.restype = C.c_int
@@ -227,3 +229,42 @@ def test_sparse_kernel_source_split_hubs(emu, oracle, masked, linesearch):
     check(Fo, sumF - partials[:k] if nupd else sumF, llh_pre, nupd, acc, r, oracle.llh(rp, col, F, sumF, P))
     if masked:
         assert np.array_equal(Fo[0], F[0])
+
+
+def test_sparse_host_packer_roundtrip(emu):
+    """sp_host_pack (bigclam_set_F_csr) -> device layout -> sparse_to_dense_kernel, and sp_host_unpack
+    (bigclam_get_F_csr): unsorted input rows, explicit zeros dropped, empty rows."""
+    if not emu.has_sparse:
+        pytest.skip("no sparse-row kernel in this tree")
+    rng = np.random.default_rng(4)
+    n, k = 300, 37
+    F = rng.random((n, k)) * (rng.random((n, k)) < 0.15)
+    F[5] = 0.0
+    F[6] = rng.random(k) + 0.1                                   # a full row
+    indptr, indices, values = [0], [], []
+    for u in range(n):
+        nz = np.nonzero(F[u])[0]
+        if u % 7 == 0 and k - len(nz) > 2:                       # sprinkle explicit zeros
+            nz = np.concatenate([nz, np.setdiff1d(np.arange(k), nz)[:2]])
+        nz = rng.permutation(nz)                                 # unsorted inside the row
+        indices.extend(nz.tolist())
+        values.extend(F[u, nz].tolist())
+        indptr.append(len(indices))
+    indptr = np.array(indptr, dtype=np.int64)
+    indices = np.array(indices, dtype=np.int32)
+    values = np.array(values, dtype=np.float64)
+    Fo, cs = np.empty((n, k)), np.empty(k)
+    ip2, ix2, vl2 = np.empty(n + 1, dtype=np.int64), np.empty(len(indices), dtype=np.int32), np.empty(len(indices))
+    used = emu.emu_pack_roundtrip(n, k, indptr.ctypes.data, indices.ctypes.data, values.ctypes.data, Fo.ctypes.data,
+                                  cs.ctypes.data, ip2.ctypes.data, ix2.ctypes.data, vl2.ctypes.data)
+    nnz_rows = (F != 0).sum(axis=1)
+    assert used == int((((nnz_rows + 3) // 4) * 5).sum())
+    assert np.array_equal(Fo, F)
+    assert np.allclose(cs, F.sum(axis=0), rtol=1e-13)
+    assert ip2[-1] == int(nnz_rows.sum()) and np.array_equal(np.diff(ip2), nnz_rows)
+    G = np.zeros_like(F)
+    for u in range(n):
+        sl = slice(ip2[u], ip2[u + 1])
+        assert (np.diff(ix2[sl]) > 0).all()
+        G[u, ix2[sl]] = vl2[sl]
+    assert np.array_equal(G, F)

@@ -163,3 +163,43 @@ def test_sparse_rmat_skewed_graph(oracle, graphs):
         _check_step(b, r, llh, max_flips=3, where=f"sparse rmat it{it}")
         F, s = b.F, b.sumF
     b.close()
+
+
+@pytest.mark.parametrize("sparse", [True, False])
+def test_csr_entry_points(oracle, sparse):
+    """bigclam_set_F_csr / bigclam_get_F_nnz / bigclam_get_F_csr: the reference's RDD[(Long, BSV[Double])] shape."""
+    import scipy.sparse as sps
+    from bigclam_apachespark_b200 import BigClam
+    n, k = 700, 50
+    rp, col = random_graph(n, 6, seed=8)
+    rng = np.random.default_rng(8)
+    F0 = rng.random((n, k)) * (rng.random((n, k)) < 0.1)
+    b = BigClam(record_accepted=True, sparse_rows=sparse)
+    b.set_graph(rp, col).set_K(k)
+    b.set_F(sps.csr_matrix(F0))
+    assert np.array_equal(b.F, F0)
+    assert np.allclose(b.sumF, F0.sum(axis=0), rtol=1e-13)
+    llh = b.backtrackingLineSearchs()
+    r = oracle.step(rp, col, F0, oracle.colsum(F0), oracle.make_params(k))
+    _check_step(b, r, llh, where="csr")
+    ip, ix, vl = b.F_csr()
+    F1 = b.F
+    assert ip[-1] == (F1 != 0).sum()
+    G = np.zeros_like(F1)
+    for u in range(n):
+        G[u, ix[ip[u]:ip[u + 1]]] = vl[ip[u]:ip[u + 1]]
+    assert np.array_equal(G, F1)
+    b.close()
+
+
+def test_sparse_pool_exhaustion_is_reported(monkeypatch):
+    from bigclam_apachespark_b200 import BigClam, _lib
+    monkeypatch.setenv("BIGCLAM_SPARSE_POOL_WORDS", "2000")
+    n, k = 600, 40
+    rp, col = random_graph(n, 6, seed=2)
+    rng = np.random.default_rng(2)
+    b = BigClam(sparse_rows=True)
+    b.set_graph(rp, col).set_K(k)
+    with pytest.raises(_lib.BigclamError):
+        b.set_F(rng.random((n, k)))                      # 600 full rows do not fit 2000 words
+    b.close()
