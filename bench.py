@@ -47,6 +47,11 @@ def load_workload():
     else:
         rp, col, _ = G.load_npz_graph(_GRAPH)
     n = len(rp) - 1
+    if n * K > (1 << 31):
+        # n x K does not exist densely at this size: CSR rows (same distribution), needs --layout sparse
+        import scipy.sparse as sps
+        ip, ix, vl = G.synthetic_F0_csr(n, K, seed=1234, density=0.05)
+        return rp, col, sps.csr_matrix((vl, ix, ip), shape=(n, K))
     F0 = G.synthetic_F0(n, K, seed=1234, density=0.05)
     return rp, col, F0
 
@@ -222,7 +227,7 @@ def run_single(args):
 
     # ---- workload A of SURVEY §8d: the reference's own init (conductance seeds, 0/1 indicator columns) ----
     extra_a = None
-    if not args.no_init_a:
+    if not args.no_init_a and not hasattr(F0, "tocsr"):
         t0 = time.perf_counter()
         b.initNeighborComF(K)
         init_s = time.perf_counter() - t0
@@ -242,7 +247,7 @@ def run_single(args):
 
     # ---- CPU baseline beside it (bounded: 2 faithful steps after 1 warm-up) ----
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and not hasattr(F0, "tocsr"):
         sec, cores = time_oracle(rp, col, F0, 2, 1)
         cpu = {"value": nnz / sec, "unit": "edges/s", "cores": cores, "kind": "port",
                "sample": "2 full steps of the same workload (all 16 candidates per node) after 1 warm-up; CPU restatement of the reference, not Spark",
@@ -273,13 +278,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-init-a", action="store_true", help="skip the reference-style-init extra workload")
+    ap.add_argument("--k", type=int, default=200, help="number of communities (default: the headline K = 200)")
     ap.add_argument("--layout", default="dense", choices=["dense", "sparse"],
-                    help="device layout of F: dense n x K rows, or sparse rows like the reference's BSV[Double] (K <= 256)")
+                    help="device layout of F: dense n x K rows, or sparse rows like the reference's BSV[Double]")
     ap.add_argument("--graph", default="com-amazon", help="fixture name or rmat:<nodes>:<edges> (default: the headline workload)")
     args = ap.parse_args()
-    global _GRAPH, WORKLOAD
+    global _GRAPH, WORKLOAD, K
     _GRAPH = args.graph
-    if _GRAPH != "com-amazon":
+    K = args.k
+    if _GRAPH != "com-amazon" or K != 200:
         WORKLOAD = f"{_GRAPH} K={K}, synthetic F0 (p=0.05 U[0,1), seed 1234), fp64"
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
