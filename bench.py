@@ -204,7 +204,7 @@ def run_single(args):
     if sparse:
         # bytes the sparse layout actually has to move per launch (row blocks: 10 B per padded entry + 8 B header):
         # every neighbour row once per edge, every own row read and written once
-        cnt = (b.F != 0).sum(axis=1)
+        cnt = np.diff(b.F_csr()[0])
         blk = 10 * ((cnt + 3) // 4 * 4) + 8
         layout_bytes = int((blk[col].sum() + 4 * nnz) + 2 * blk.sum() + 16 * n)
 
