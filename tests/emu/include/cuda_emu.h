@@ -17,6 +17,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <thread>
 #include <type_traits>
 #include <vector>
@@ -29,7 +32,11 @@
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 
-struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+using emu_dim3 = dim3;
 extern thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 struct alignas(16) double2 { double x, y; };
@@ -131,7 +138,8 @@ template <class A, class B> inline std::common_type_t<A, B> max(A a, B b) {
 namespace emu {
 // <<<grid, block, smem>>> : blocks one after the other, `block` OS threads each
 template <class K, class... A>
-inline void launch(K kernel, unsigned grid, unsigned block, size_t smem, A... args) {
+inline void launch(K kernel, dim3 grid3, unsigned block, size_t smem, A... args) {
+    const unsigned grid = grid3.x * grid3.y;
     for (unsigned b = 0; b < grid; ++b) {
         std::vector<unsigned char> sm(smem + 64);
         g_dyn_smem = reinterpret_cast<unsigned char *>(((uintptr_t)sm.data() + 63) & ~(uintptr_t)63);
@@ -145,9 +153,11 @@ inline void launch(K kernel, unsigned grid, unsigned block, size_t smem, A... ar
         for (unsigned t = 0; t < block; ++t)
             th.emplace_back([=, &bc, &wc]() {
                 threadIdx.x = t;
-                blockIdx.x = b;
+                blockIdx.x = b % grid3.x;
+                blockIdx.y = b / grid3.x;
                 blockDim.x = block;
-                gridDim.x = grid;
+                gridDim.x = grid3.x;
+                gridDim.y = grid3.y;
                 lane = (int)(t & 31);
                 warp = &wc[t / 32];
                 emu::block = &bc;
@@ -159,3 +169,54 @@ inline void launch(K kernel, unsigned grid, unsigned block, size_t smem, A... ar
     }
 }
 }  // namespace emu
+
+// ---------------------------------------------------------------------------------------------------------------
+// BIGCLAM_EMU_HOST: a synchronous stand-in for the part of the CUDA runtime csrc/bigclam_capi.cu uses, so that the
+// HOST LOGIC of the C API (speculation, buffer flips, device-side loop bookkeeping, sparse-row plumbing) can be
+// driven by the existing `-m gpu` tests on a machine without a GPU (tools only; see tests/emu/build_hostemu.sh).
+// "Device" memory is host memory, streams and events are no-ops / wall clocks, one SM, kernels run on launch.
+#ifdef BIGCLAM_EMU_HOST
+typedef int cudaError_t;
+constexpr cudaError_t cudaSuccess = 0;
+typedef void *cudaStream_t;
+struct emu_event { std::chrono::steady_clock::time_point t; };
+typedef emu_event *cudaEvent_t;
+struct cudaIpcMemHandle_t { char reserved[64]; };
+struct cudaDeviceProp { int major = 10, minor = 0, multiProcessorCount = 1; };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyHostToHost };
+enum { cudaStreamNonBlocking = 1, cudaIpcMemLazyEnablePeerAccess = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+inline const char *cudaGetErrorString(cudaError_t) { return "emulated runtime error"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { *p = cudaDeviceProp(); return cudaSuccess; }
+template <class K> inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
+template <class K> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *b, K, int, size_t) { *b = 2; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+template <class T> inline cudaError_t cudaMalloc(T **p, size_t bytes) { *p = static_cast<T *>(std::malloc(bytes ? bytes : 1)); return *p ? cudaSuccess : 2; }
+template <class T> inline cudaError_t cudaMallocHost(T **p, size_t bytes) { return cudaMalloc(p, bytes); }
+inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(d, s, n, k); }
+inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < h; ++r) std::memmove(static_cast<char *>(d) + r * dp, static_cast<const char *>(s) + r * sp, w);
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemset(void *d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { return cudaMemset(d, v, n); }
+inline cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = (size_t)8 << 30; return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event(); return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    return cudaSuccess;
+}
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { std::memset(h, 0, sizeof(*h)); std::memcpy(h, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+#endif  // BIGCLAM_EMU_HOST
