@@ -63,9 +63,10 @@ struct SparseArgs {
     unsigned int *hub_work;            // next hub item to hand out (zeroed per launch); items: StepArgs::hub_items
 };
 
-// per-warp shared memory: fu_d[ld] | g_d[ld] | ent_val[E] | ent_idx[E] u16 | aidx[max(ld, 256)] u16 | poff[40] u16
+// per-warp shared memory: fu_d[ld] | g_d[ld] | ent_val[E] | ent_idx[E] u16 | aidx[max(ld, 256)] u16 | poff[40] u16 |
+//                         cbal[32] u32 | ccum[32] u16 (+ pad)   (ballots / running counts of the entry compaction)
 __host__ __device__ inline size_t sp_warp_bytes(int ld) {
-    return sizeof(double) * 2 * (size_t)ld + (size_t)sp_entries(ld) * 10 + 2 * (size_t)(ld > 256 ? ld : 256) + 2 * 40;
+    return sizeof(double) * 2 * (size_t)ld + (size_t)sp_entries(ld) * 10 + 2 * (size_t)(ld > 256 ? ld : 256) + 2 * 40 + 4 * 32 + 2 * 32;
 }
 // block: steps[kMaxSteps] | sumF[ld] | D[ld] | wpb x warp area
 __host__ __device__ inline size_t sp_block_smem_bytes(int ld, int wpb) {
@@ -154,6 +155,8 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
     unsigned short *ent_idx = reinterpret_cast<unsigned short *>(ent_val + ecap);
     unsigned short *aidx = ent_idx + ecap;
     unsigned short *poff = aidx + (ld > 256 ? ld : 256);
+    unsigned int *cbal = reinterpret_cast<unsigned int *>(poff + 40);
+    unsigned short *ccum = reinterpret_cast<unsigned short *>(cbal + 32);
 
 #pragma unroll 1
     for (int i = threadIdx.x; i < ld; i += nthreads) { s_sumF[i] = a.sumF[i]; s_D[i] = 0.0; }
@@ -232,6 +235,39 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
         __syncwarp();
         return G2;
     };
+    // The staged entries of `ne` rows shrink, in place, to those on ACTIVE components (fu > 0 or grad > 0): only
+    // they can contribute to a candidate's dot (an inactive component clamps to 0), and a neighbour row typically
+    // keeps ~3 of its ~9 entries.  Order inside a row is kept, poff is rewritten.
+    auto compact_active = [&](int ne) {
+        const int T = poff[ne];
+        int total = 0;
+        for (int base = 0; base < T; base += 32) {
+            const int j = base + lane;
+            const bool in = j < T;
+            const int c = in ? (int)ent_idx[j] : 0;
+            const double v = in ? ent_val[j] : 0.0;
+            const bool act = in && (fu_d[c] > 0.0 || g_d[c] > 0.0);
+            const unsigned bal = __ballot_sync(0xffffffffu, act);
+            if (lane == 0) { cbal[base >> 5] = bal; ccum[base >> 5] = (unsigned short)total; }
+            __syncwarp();                       // this block's reads are done; writes land at or below them
+            if (act) {
+                const int p = total + __popc(bal & lt_mask);
+                ent_idx[p] = (unsigned short)c;
+                ent_val[p] = v;
+            }
+            total += __popc(bal);
+        }
+        __syncwarp();
+        int newp = 0;
+        if (lane < ne) {
+            const int p = poff[lane];
+            newp = (p >= T) ? total : (int)ccum[p >> 5] + __popc(cbal[p >> 5] & ((1u << (p & 31)) - 1u));
+        }
+        __syncwarp();
+        if (lane < ne) poff[lane] = (unsigned short)newp;
+        if (lane == 0) poff[ne] = (unsigned short)total;
+        __syncwarp();
+    };
     // Line search over the edges [eb, ee): lane (j, h) returns the sum over its edges of the clamped edge term
     // for candidate step s; `staged` rows of a single chunk may still be in the buffer from PRE.
     auto ls_range = [&](int64_t e0, int eb, int ee, double s, bool need_hi, int staged) -> double {
@@ -239,6 +275,7 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
         for (int cb = eb; cb < ee;) {
             const int ne = (staged > 0) ? staged
                                         : sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, ee - cb), lane, ecap, ent_val, ent_idx, poff);
+            compact_active(ne);
 #pragma unroll 1
             for (int e2 = 0; e2 < ne; e2 += 4) {
                 const int eA = e2 + h, eB = e2 + 2 + h;
