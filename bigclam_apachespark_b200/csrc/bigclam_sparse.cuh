@@ -33,6 +33,20 @@
 
 namespace bigclam {
 
+// Build-time knobs for A/B runs (tools/build_variant.sh <name> -DBIGCLAM_SP_BLOCKS=2 -DBIGCLAM_SP_PREFETCH=1):
+//   BIGCLAM_SP_BLOCKS    blocks per SM the kernel is compiled for: 2 (default) = 16 warps/SM, ~120 registers, no
+//                        spills; 3 = 24 warps/SM at 80 registers with 72-112 bytes of spills (the dense kernel's
+//                        128-register builds lost 40 % to far fewer spilled bytes: to be measured, not assumed);
+//   BIGCLAM_SP_PREFETCH  load the next node's header, neighbour ids, neighbour headers and own entries one node
+//                        ahead (two dependent round trips less per node, ~16 more live registers).
+#ifndef BIGCLAM_SP_BLOCKS
+#define BIGCLAM_SP_BLOCKS 2
+#endif
+#ifndef BIGCLAM_SP_PREFETCH
+#define BIGCLAM_SP_PREFETCH 0
+#endif
+constexpr int kSpBlocksPerSM = BIGCLAM_SP_BLOCKS;
+constexpr bool kSpPrefetch = BIGCLAM_SP_PREFETCH != 0;
 constexpr int kSpWarps = 8;            // warps per block at most (ld <= 256); wide rows run fewer (sp_warps_per_block)
 constexpr int kSpThreads = kSpWarps * 32;
 // staged neighbour entries per chunk: at least one full row always fits
@@ -78,7 +92,7 @@ inline int sp_warps_per_block(int ld) {
     for (int wpb = kSpWarps; wpb >= 1; wpb >>= 1) {
         const size_t bytes = sp_block_smem_bytes(ld, wpb) + 1024 + 256;
         const int blocks = (int)((size_t)233472 / bytes);
-        const int warps = (blocks > 3 ? 3 : blocks) * wpb;         // the kernel is built for at most 3 blocks per SM
+        const int warps = (blocks > kSpBlocksPerSM ? kSpBlocksPerSM : blocks) * wpb;         // the kernel is built for that many blocks per SM
         if (warps > best_warps) { best_warps = warps; best = wpb; }
     }
     return best;
@@ -90,9 +104,14 @@ inline int sp_warps_per_block(int ld) {
 // (noinline, scalar arguments only: one copy in the code, called from PRE and from the line search.)
 __device__ __noinline__ int sp_stage_chunk(const uint64_t *__restrict__ hdr_in, const double *__restrict__ pool_in,
                                            const int32_t *__restrict__ colp, int cnt32, int lane, int cap, double *ent_val,
-                                           unsigned short *ent_idx, unsigned short *poff) {
-    const int v = (lane < cnt32) ? colp[lane] : 0;
-    const uint64_t hv = (lane < cnt32) ? __ldg(hdr_in + v) : 0ull;
+                                           unsigned short *ent_idx, unsigned short *poff, int use_pre = 0,
+                                           unsigned long long pre_hv = 0ull) {
+    // use_pre: the caller already holds this chunk's row headers (loaded one node ahead)
+    uint64_t hv = pre_hv;
+    if (!use_pre) {
+        const int v = (lane < cnt32) ? colp[lane] : 0;
+        hv = (lane < cnt32) ? __ldg(hdr_in + v) : 0ull;
+    }
     const int cv = (int)sp_cnt(hv);
     int incl = cv;
 #pragma unroll
@@ -137,7 +156,7 @@ constexpr int kSpHubSeg = 256;
 // kPush: multi-GPU launch, the peers' replicas are written too; kHub: the launch has split hubs.  Both are
 // compile-time so that the plain single-GPU kernel carries none of that code.
 template <bool kPush, bool kHub>
-__global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepArgs a, const SparseArgs sp) {
+__global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel(const StepArgs a, const SparseArgs sp) {
     if (a.done_flag != nullptr && *a.done_flag != 0) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -178,12 +197,14 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
     // PRE over the edges [eb, ee) of a node whose fu is in fu_d: returns this lane's share of S1; with `axpy`
     // the weighted neighbour rows are added into g_d.  `single` = the range fitted one staged chunk (its
     // entries are still in the buffer, `ne_last` rows).
-    auto pre_range = [&](int64_t e0, int eb, int ee, bool axpy, int &nchunks, int &ne_last) -> double {
+    auto pre_range = [&](int64_t e0, int eb, int ee, bool axpy, int &nchunks, int &ne_last, int use_pre = 0,
+                         unsigned long long pre_hv = 0ull) -> double {
         double S1 = 0.0;
         nchunks = 0;
         ne_last = 0;
         for (int cb = eb; cb < ee;) {
-            const int ne = sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, ee - cb), lane, ecap, ent_val, ent_idx, poff);
+            const int ne = sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, ee - cb), lane, ecap, ent_val, ent_idx, poff,
+                                          (use_pre && cb == eb) ? 1 : 0, pre_hv);
             double x = 0.0;
             if (lane < ne) {
                 const int end = poff[lane + 1];
@@ -482,6 +503,22 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
     NodeMeta cur = {0, 0, 0}, nxt = {0, 0, 0};
     if (pos < order_n) cur = a.meta[pos];
     if (pos_n < order_n) nxt = a.meta[pos_n];
+    // kSpPrefetch: what the current node needs first is loaded while the previous one is processed — its header
+    // (c_hu), its first 32 entries (lane i holds entry i), the headers of its first 32 neighbours (c_hv)
+    unsigned long long c_hu = 0ull, c_hv = 0ull;
+    double c_val = 0.0;
+    int c_idx = 0;
+    if (kSpPrefetch && pos < order_n) {
+        c_hu = __ldg(sp.hdr_in + cur.u);
+        const int v0 = (lane < min(32, cur.deg)) ? a.col[cur.e0 + lane] : 0;
+        c_hv = (lane < min(32, cur.deg)) ? __ldg(sp.hdr_in + v0) : 0ull;
+        const int cu0 = (int)sp_cnt(c_hu);
+        const double *uv0 = sp.pool_in + sp_off8(c_hu);
+        if (lane < cu0) {
+            c_val = __ldg(uv0 + lane);
+            c_idx = __ldg(reinterpret_cast<const unsigned short *>(uv0 + sp_pad((uint32_t)cu0)) + lane);
+        }
+    }
 
     while (pos < order_n) {
         const int64_t u = cur.u, e0 = cur.e0;
@@ -490,16 +527,26 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
         if (pos_nn < order_n) nn = a.meta[pos_nn];
         unsigned int fetched = 0;
         if (lane == 0) fetched = atomicAdd(a.work_counter, 1u);
+        // stage 1 of the prefetch for the next node: header and neighbour ids
+        const bool has_next = pos_n < order_n;
+        unsigned long long n_hu = 0ull, n_hv = 0ull;
+        int n_v = 0, n_idx = 0;
+        double n_val = 0.0;
+        if (kSpPrefetch && has_next) {
+            n_hu = __ldg(sp.hdr_in + nxt.u);
+            n_v = (lane < min(32, nxt.deg)) ? a.col[nxt.e0 + lane] : 0;
+        }
 
         // ---- own row: scatter into fu_d ----
-        const uint64_t hu = __ldg(sp.hdr_in + u);
+        const uint64_t hu = kSpPrefetch ? (uint64_t)c_hu : __ldg(sp.hdr_in + u);
         const int cu = (int)sp_cnt(hu);
         const double *uval = sp.pool_in + sp_off8(hu);
         const unsigned short *uidx = reinterpret_cast<const unsigned short *>(uval + sp_pad((uint32_t)cu));
         double fusf = 0.0, fufu = 0.0;
         for (int i = lane; i < cu; i += 32) {
-            const double v = __ldg(uval + i);
-            const int c = __ldg(uidx + i);
+            const bool first = kSpPrefetch && i < 32;
+            const double v = first ? c_val : __ldg(uval + i);
+            const int c = first ? c_idx : (int)__ldg(uidx + i);
             fu_d[c] = v;
             fusf = fma(v, s_sumF[c], fusf);
             fufu = fma(v, v, fufu);
@@ -513,9 +560,19 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
 
         // ---------------- PRE (:157-169) ----------------
         int nchunks, ne_last;
-        const double S1 = warp_sum(pre_range(e0, 0, deg, want_ls, nchunks, ne_last));
+        const double S1 = warp_sum(pre_range(e0, 0, deg, want_ls, nchunks, ne_last, kSpPrefetch ? 1 : 0, c_hv));
         const double llh_u = (S1 - fusf) + fufu;
         llh_acc += llh_u;
+        // stage 2 of the prefetch: the next node's first entries and its neighbours' headers (stage 1 has landed)
+        if (kSpPrefetch && has_next) {
+            n_hv = (lane < min(32, nxt.deg)) ? __ldg(sp.hdr_in + n_v) : 0ull;
+            const int cun = (int)sp_cnt(n_hu);
+            const double *uvn = sp.pool_in + sp_off8(n_hu);
+            if (lane < cun) {
+                n_val = __ldg(uvn + lane);
+                n_idx = __ldg(reinterpret_cast<const unsigned short *>(uvn + sp_pad((uint32_t)cun)) + lane);
+            }
+        }
 
         int jstar = -1, m = 0;
         if (want_ls) {
@@ -547,6 +604,7 @@ __global__ void __launch_bounds__(kSpThreads, 3) sparse_step_kernel(const StepAr
         pos = pos_n;
         pos_n = pos_nn;
         pos_nn = (int64_t)__shfl_sync(0xffffffffu, fetched, 0);
+        if (kSpPrefetch) { c_hu = n_hu; c_hv = n_hv; c_val = n_val; c_idx = n_idx; }
     }
 
     // ---------------- block reduction of the partials ----------------

@@ -14,5 +14,5 @@ for f in bigclam_kernels.cuh bigclam_sparse.cuh; do
       -e 's/^\( *\)__shared__ /\1static /' "$src/$f" > "$gen/$f"
 done
 CXX=/usr/bin/g++; test -x $CXX || CXX=g++
-$CXX -O1 -g -std=c++20 -ffp-contract=off -DBIGCLAM_EMU $defs -x c++ -I "$here/include" -I "$gen" -I "$here/../../include" \
-    -pthread -shared -fPIC -Wno-unknown-pragmas -o "$here/libemu.so" "$here/emu_driver.cpp"
+$CXX -O1 -g -std=c++20 -ffp-contract=off -DBIGCLAM_EMU $defs $EMU_DEFS -x c++ -I "$here/include" -I "$gen" -I "$here/../../include" \
+    -pthread -shared -fPIC -Wno-unknown-pragmas -o "$here/${EMU_OUT:-libemu.so}" "$here/emu_driver.cpp"

@@ -14,10 +14,17 @@ from conftest import random_graph, tiny_graph
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module")
-def emu():
-    subprocess.run([os.path.join(HERE, "emu", "build.sh")], check=True)
-    lib = C.CDLL(os.path.join(HERE, "emu", "libemu.so"))
+# "prefetch": the sparse kernel built with its one-node-ahead prefetch (BIGCLAM_SP_PREFETCH=1, see bigclam_sparse.cuh)
+@pytest.fixture(scope="module", params=["default", "prefetch"])
+def emu(request):
+    has_sparse_src = os.path.exists(os.path.join(HERE, "..", "bigclam_apachespark_b200", "csrc", "bigclam_sparse.cuh"))
+    if request.param == "prefetch" and not has_sparse_src:
+        pytest.skip("no sparse-row kernel in this tree")
+    out = "libemu.so" if request.param == "default" else "libemu_prefetch.so"
+    env = dict(os.environ, EMU_OUT=out, EMU_DEFS="" if request.param == "default" else "-DBIGCLAM_SP_PREFETCH=1")
+    subprocess.run([os.path.join(HERE, "emu", "build.sh")], check=True, env=env)
+    lib = C.CDLL(os.path.join(HERE, "emu", out))
+    lib.variant = request.param
     step_args = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                  C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.emu_dense_step.restype = C.c_int
@@ -147,6 +154,8 @@ def test_sparse_kernel_source_dense_rows_and_chunking(emu, oracle):
 def test_dense_kernel_source_against_oracle(emu, oracle, k, grid):
     """The GPU-validated dense kernels through the same emulation: pins the emulation itself (shuffle, ballot and
     barrier semantics) as much as the kernel logic (C2 = 1, 1, 2, 4, 8 chunk shapes; dense and pair-list paths)."""
+    if emu.variant != "default":
+        pytest.skip("dense kernels do not depend on the sparse build knobs")
     n = 80
     rp, col = random_graph(n, 5, seed=100 + k, hub=40)
     rng = np.random.default_rng(k)
