@@ -885,6 +885,7 @@ __device__ __noinline__ void hub_phase(const HubArgs ha, const EdgeConst ec, con
         if (wib == 0) {
             double *orow = ha.F_out + (size_t)u * ld;
             const bool push = (ha.n_peers > 0) && ha.do_linesearch && ((jstar >= 0) || (ha.changed[u] != 0));
+            __syncwarp();      // every lane has read the flag before lane 0 rewrites it below
             if (ha.do_linesearch) {
                 const double s = (jstar >= 0) ? s_steps[jstar] : 0.0;
 #pragma unroll
@@ -1216,7 +1217,9 @@ __global__ void __launch_bounds__(kBlockThreads, (C2 <= 4) ? 2 : 1) step_kernel(
         }
         if (kPush && a.n_peers > 0 && a.do_linesearch) {
             // multi-GPU launches only (compile-time flag)
-            if ((jstar >= 0) || (a.changed[u] != 0)) {
+            const bool push_row = (jstar >= 0) || (a.changed[u] != 0);
+            __syncwarp();      // every lane has read the flag before lane 0 rewrites it below
+            if (push_row) {
                 for (int pr = 0; pr < a.n_peers; ++pr) {
                     double *prow = a.peer_out[pr] + (size_t)u * ld;
 #pragma unroll
