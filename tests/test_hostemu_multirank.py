@@ -15,13 +15,15 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("BIGCLAM_HOSTEMU") != "1", reason="host-emulation build only")]
 
 
+@pytest.mark.parametrize("hub", [40, 150])          # 150: the owner of the hub runs the hub phase (dense) / split hubs (sparse)
 @pytest.mark.parametrize("sparse", [False, True])
-def test_two_ranks_through_the_c_abi(oracle, sparse):
+def test_two_ranks_through_the_c_abi(oracle, sparse, hub, monkeypatch):
+    monkeypatch.setenv("BIGCLAM_SPARSE_HUB_DEG", "100")
     from bigclam_apachespark_b200 import BigClam, _lib
     from bigclam_apachespark_b200.dist import deal_by_degree
     lib = _lib.load()
     world, n, k = 2, 160, 12
-    rp, col = random_graph(n, 5, seed=31, hub=40)
+    rp, col = random_graph(n, 5, seed=31, hub=hub)
     rng = np.random.default_rng(31)
     F0 = rng.random((n, k)) * (rng.random((n, k)) < 0.3)
     sumF = oracle.colsum(F0)
