@@ -14,7 +14,8 @@ if os.environ.get("BIGCLAM_HOSTEMU") == "1":
     # machine without a GPU — the ctypes binding is pointed at the host-emulation build for this pytest run only
     import subprocess
 
-    subprocess.run([os.path.join(REPO, "tests", "emu", "build_hostemu.sh")], check=True)
+    if os.environ.get("BIGCLAM_HOSTEMU_NOBUILD") != "1":
+        subprocess.run([os.path.join(REPO, "tests", "emu", "build_hostemu.sh")], check=True)
     from bigclam_apachespark_b200 import _lib as _L
 
     _L.LIB_PATH = os.path.join(REPO, "tests", "emu", "libbigclam_hostemu.so")

@@ -28,6 +28,6 @@ unsigned char *g_dyn_smem = nullptr;
 }
 EOT
 CXX=/usr/bin/g++; test -x $CXX || CXX=g++
-$CXX -O1 -g -std=c++20 -ffp-contract=off -DBIGCLAM_EMU -DBIGCLAM_EMU_HOST -I "$here/include" -I "$gen" -I "$here/../../include" \
+$CXX -O1 -g -std=c++20 -ffp-contract=off -DBIGCLAM_EMU -DBIGCLAM_EMU_HOST $EMU_DEFS -I "$here/include" -I "$gen" -I "$here/../../include" \
     -pthread -shared -fPIC -Wno-unknown-pragmas -o "$here/libbigclam_hostemu.so" \
     "$gen/bigclam_capi_emu.cpp" "$gen/emu_globals.cpp" "$src/edgelist.cpp" "$src/initf.cpp"
