@@ -90,9 +90,19 @@ static void run_dense(Problem &P, int grid) {
     emu::launch(step_kernel<C2, R, false, false>, (unsigned)grid, (unsigned)kBlockThreads, block_smem_bytes(P.ld, P.a.maxm), P.a);
 }
 
-extern "C" int emu_dense_step(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
-                              const double *sumF, const uint8_t *mask, int do_linesearch, int max_inter, double alpha,
-                              double beta, int grid, double *F_out, double *partials_out, int8_t *accepted_out) {
+// hub phase (step_kernel<C2, R, true, false>, one block: the emulation runs blocks one after the other and the
+// phases of a multi-block hub wait for each other)
+template <int C2>
+static void run_dense_hubs(Problem &P) {
+    constexpr int R = RowsInFlight<C2>::value;
+    emu::launch(step_kernel<C2, R, true, false>, 1u, (unsigned)kBlockThreads, block_smem_bytes(P.ld, P.a.maxm), P.a);
+}
+
+// hub_deg > 0 (grid 1, K <= 256): nodes of at least that degree go through the block-cooperative hub phase, those
+// above kHubSlice edges as multi-phase "mega" hubs — the item list of rebuild_order_list (csrc/bigclam_capi.cu).
+static int dense_step_impl(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
+                           const double *sumF, const uint8_t *mask, int do_linesearch, int max_inter, double alpha,
+                           double beta, int grid, int hub_deg, double *F_out, double *partials_out, int8_t *accepted_out) {
     Problem P;
     unsigned work = 0;
     setup(P, n, rowptr, col, k, F_in, sumF, mask, do_linesearch, max_inter, alpha, beta, &work, 3u * (unsigned)grid * kWarpsPerBlock);
@@ -102,6 +112,51 @@ extern "C" int emu_dense_step(int64_t n, const int64_t *rowptr, const int32_t *c
     P.a.F_out = Fo.data();
     const int c2raw = (ld / 2 + 31) / 32;
     const int c2 = c2raw <= 1 ? 1 : c2raw <= 2 ? 2 : c2raw <= 4 ? 4 : c2raw <= 8 ? 8 : 16;
+    std::vector<HubItem> items;
+    std::vector<double> scratch(ld + 32, 0.0);
+    std::vector<unsigned int> counters(2, 0u);
+    int nh = 0;
+    if (hub_deg > 0 && grid == 1 && c2 <= 4 && P.nsteps <= 16) {
+        while (nh < n && P.meta[nh].deg >= hub_deg) ++nh;
+        std::vector<HubItem> i1, i0, i2, i3;
+        int n_mega = 0;
+        for (int i = 0; i < nh; ++i) {
+            HubItem it{};
+            it.hub = i;
+            const int nsl = (P.meta[i].deg + kHubSlice - 1) / kHubSlice;
+            if (nsl > 1) {
+                it.mslot = n_mega++;
+                it.nslices = nsl;
+                for (int sl = 0; sl < nsl; ++sl) {
+                    it.slice = sl;
+                    it.phase = 1; i1.push_back(it);
+                    it.phase = 2; i2.push_back(it);
+                }
+                it.slice = 0;
+                it.phase = 3; i3.push_back(it);
+            } else {
+                it.phase = 0; it.nslices = 1; it.mslot = 0;
+                i0.push_back(it);
+            }
+        }
+        items.insert(items.end(), i1.begin(), i1.end());
+        items.insert(items.end(), i0.begin(), i0.end());
+        items.insert(items.end(), i2.begin(), i2.end());
+        items.insert(items.end(), i3.begin(), i3.end());
+        scratch.assign((size_t)std::max(1, n_mega) * (ld + 32), 0.0);
+        counters.assign(2 * (size_t)std::max(1, n_mega), 0u);
+        P.a.n_hubs = nh;
+        P.a.n_hub_items = (int32_t)items.size();
+        P.a.hub_items = items.data();
+        P.a.hub_scratch = scratch.data();
+        P.a.hub_counters = counters.data();
+        work = (unsigned)nh + 3u * kWarpsPerBlock;
+        switch (c2) {
+            case 1: run_dense_hubs<1>(P); break;
+            case 2: run_dense_hubs<2>(P); break;
+            default: run_dense_hubs<4>(P); break;
+        }
+    } else
     switch (c2) {
         case 1: run_dense<1>(P, grid); break;
         case 2: run_dense<2>(P, grid); break;
@@ -112,7 +167,22 @@ extern "C" int emu_dense_step(int64_t n, const int64_t *rowptr, const int32_t *c
     for (int64_t u = 0; u < n; ++u) std::copy(Fo.begin() + u * ld, Fo.begin() + u * ld + k, F_out + u * k);
     std::copy(P.partials.begin(), P.partials.end(), partials_out);
     std::copy(P.accepted.begin(), P.accepted.end(), accepted_out);
-    return 0;
+    return nh > 0 ? 1000 + nh : 0;
+}
+
+extern "C" int emu_dense_step(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
+                              const double *sumF, const uint8_t *mask, int do_linesearch, int max_inter, double alpha,
+                              double beta, int grid, double *F_out, double *partials_out, int8_t *accepted_out) {
+    return dense_step_impl(n, rowptr, col, k, F_in, sumF, mask, do_linesearch, max_inter, alpha, beta, grid, 0, F_out,
+                           partials_out, accepted_out);
+}
+
+// returns 1000 + number of hub nodes on success
+extern "C" int emu_dense_step_hubs(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k, const double *F_in,
+                                   const double *sumF, const uint8_t *mask, int do_linesearch, int max_inter, double alpha,
+                                   double beta, int hub_deg, double *F_out, double *partials_out, int8_t *accepted_out) {
+    return dense_step_impl(n, rowptr, col, k, F_in, sumF, mask, do_linesearch, max_inter, alpha, beta, 1, hub_deg, F_out,
+                           partials_out, accepted_out);
 }
 
 #ifdef BIGCLAM_EMU_SPARSE

@@ -29,6 +29,8 @@ def emu(request):
                  C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.emu_dense_step.restype = C.c_int
     lib.emu_dense_step.argtypes = step_args
+    lib.emu_dense_step_hubs.restype = C.c_int
+    lib.emu_dense_step_hubs.argtypes = step_args
     lib.has_sparse = hasattr(lib, "emu_sparse_step")          # csrc/bigclam_sparse.cuh present in this tree
     if lib.has_sparse:
         lib.emu_sparse_step.restype = C.c_int
@@ -277,3 +279,36 @@ def test_sparse_host_packer_roundtrip(emu):
         assert (np.diff(ix2[sl]) > 0).all()
         G[u, ix2[sl]] = vl2[sl]
     assert np.array_equal(G, F)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("k", [12, 200])
+def test_dense_kernel_source_hub_phase(emu, oracle, k):
+    """step_kernel<C2,R,true,false>: a 700-edge hub as a multi-phase "mega" hub (two 384-edge slices through the
+    global scratch), a 300-edge hub done by the whole block (phase 0), the other nodes one warp each."""
+    if emu.variant != "default":
+        pytest.skip("dense kernels do not depend on the sparse build knobs")
+    from bigclam_apachespark_b200 import graphs as G
+    n = 900
+    rng = np.random.default_rng(44)
+    u = np.concatenate([rng.integers(0, n, 1500), np.zeros(700, dtype=np.int64), np.ones(300, dtype=np.int64)])
+    v = np.concatenate([rng.integers(0, n, 1500), rng.choice(np.arange(2, n), 700, replace=False),
+                        rng.choice(np.arange(2, n), 300, replace=False)])
+    keep = u != v
+    lo, hi = np.minimum(u[keep], v[keep]), np.maximum(u[keep], v[keep])
+    key = np.unique(lo * n + hi)
+    rp, col = G.csr_from_undirected(n, key // n, key % n)
+    F = rng.random((n, k)) * (rng.random((n, k)) < min(1.0, 4.0 / k + 0.05))
+    sumF = oracle.colsum(F)
+    P = oracle.make_params(k)
+    ld = (k + 3) & ~3
+    Fo = np.empty_like(F)
+    partials = np.zeros(2 * ld + 2)
+    acc = np.empty(n, dtype=np.int8)
+    rp64, col32 = np.ascontiguousarray(rp, dtype=np.int64), np.ascontiguousarray(col, dtype=np.int32)
+    rc = emu.emu_dense_step_hubs(n, rp64.ctypes.data, col32.ctypes.data, k, F.ctypes.data, sumF.ctypes.data, None, 1, 15,
+                                 0.05, 0.1, 280, Fo.ctypes.data, partials.ctypes.data, acc.ctypes.data)
+    assert rc == 1002
+    r = oracle.step(rp, col, F, sumF, P)
+    nupd = int(round(partials[2 * ld + 1]))
+    check(Fo, sumF - partials[:k] if nupd else sumF, partials[2 * ld], nupd, acc, r, oracle.llh(rp, col, F, sumF, P), max_flips=1)
