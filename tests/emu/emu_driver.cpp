@@ -15,6 +15,7 @@ namespace emu {
 thread_local WarpCtx *warp = nullptr;
 thread_local BlockCtx *block = nullptr;
 thread_local int lane = 0;
+thread_local int xpar = 0;
 unsigned char *g_dyn_smem = nullptr;
 }  // namespace emu
 

@@ -45,7 +45,7 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 namespace emu {
 struct WarpCtx {
     pthread_barrier_t bar;
-    uint64_t slot[32];
+    uint64_t slot[2][32];          // two exchange buffers used alternately: one barrier round per collective
 };
 struct BlockCtx {
     pthread_barrier_t bar;
@@ -53,6 +53,7 @@ struct BlockCtx {
 extern thread_local WarpCtx *warp;
 extern thread_local BlockCtx *block;
 extern thread_local int lane;
+extern thread_local int xpar;      // which exchange buffer this lane's next collective uses (same on all lanes of a warp)
 extern unsigned char *g_dyn_smem;
 inline unsigned char *dyn_smem() { return g_dyn_smem; }
 inline void wsync() { pthread_barrier_wait(&warp->bar); }
@@ -61,10 +62,12 @@ inline T exch(T v, int src) {
     static_assert(sizeof(T) <= 8, "emulated shuffles move at most 8 bytes");
     uint64_t u = 0;
     std::memcpy(&u, &v, sizeof(T));
-    warp->slot[lane] = u;
+    // the next collective writes the other buffer, and the one after that can only start once every lane has
+    // passed the next barrier, i.e. has finished reading this one: no second barrier needed
+    const int p = (xpar ^= 1);
+    warp->slot[p][lane] = u;
     wsync();
-    const uint64_t r = warp->slot[src & 31];
-    wsync();
+    const uint64_t r = warp->slot[p][src & 31];
     T out;
     std::memcpy(&out, &r, sizeof(T));
     return out;
@@ -78,11 +81,11 @@ template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) 
     return emu::exch(v, src < 0 ? emu::lane : src);
 }
 inline unsigned __ballot_sync(unsigned, int pred) {
-    emu::warp->slot[emu::lane] = pred ? 1u : 0u;
+    const int p = (emu::xpar ^= 1);
+    emu::warp->slot[p][emu::lane] = pred ? 1u : 0u;
     emu::wsync();
     unsigned m = 0;
-    for (int i = 0; i < 32; ++i) m |= (unsigned)emu::warp->slot[i] << i;
-    emu::wsync();
+    for (int i = 0; i < 32; ++i) m |= (unsigned)emu::warp->slot[p][i] << i;
     return m;
 }
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
@@ -159,6 +162,7 @@ inline void launch(K kernel, dim3 grid3, unsigned block, size_t smem, A... args)
                 gridDim.x = grid3.x;
                 gridDim.y = grid3.y;
                 lane = (int)(t & 31);
+                xpar = 0;
                 warp = &wc[t / 32];
                 emu::block = &bc;
                 kernel(args...);
