@@ -152,10 +152,10 @@ def test_sparse_kernel_source_dense_rows_and_chunking(emu, oracle):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("k,grid", [(5, 1), (40, 2), (100, 1), (200, 1), (300, 1)])
+@pytest.mark.parametrize("k,grid", [(5, 1), (40, 2), (100, 1), (200, 1), (300, 1), (600, 1)])
 def test_dense_kernel_source_against_oracle(emu, oracle, k, grid):
     """The GPU-validated dense kernels through the same emulation: pins the emulation itself (shuffle, ballot and
-    barrier semantics) as much as the kernel logic (C2 = 1, 1, 2, 4, 8 chunk shapes; dense and pair-list paths)."""
+    barrier semantics) as much as the kernel logic (C2 = 1, 1, 2, 4, 8, 16 chunk shapes; dense and pair-list paths)."""
     if emu.variant != "default":
         pytest.skip("dense kernels do not depend on the sparse build knobs")
     n = 80
