@@ -121,19 +121,29 @@ __device__ __noinline__ int sp_stage_chunk(const uint64_t *__restrict__ hdr_in, 
     }
     const unsigned fit = __ballot_sync(0xffffffffu, (lane < cnt32) && (incl <= cap));
     const int ne = __popc(fit);                     // incl is monotone: the fitting lanes are 0 .. ne-1
-    const int beg = incl - cv;
     if (lane == 0) poff[0] = 0;
     if (lane < ne) poff[lane + 1] = (unsigned short)incl;
-#pragma unroll 2
-    for (int e = 0; e < ne; ++e) {
-        const uint64_t he = __shfl_sync(0xffffffffu, hv, e);
-        const int pe = __shfl_sync(0xffffffffu, beg, e);
-        const int ce = (int)sp_cnt(he);
-        const double *vals = pool_in + sp_off8(he);
-        const unsigned short *idxp = reinterpret_cast<const unsigned short *>(vals + sp_pad((uint32_t)ce));
-        for (int i = lane; i < ce; i += 32) {
-            ent_val[pe + i] = __ldg(vals + i);
-            ent_idx[pe + i] = __ldg(idxp + i);
+    __syncwarp();
+    // the T entries of the ne rows, 32 at a time, one per lane: all loads of a round are in flight together
+    // (the rows are ~9 entries long: going row by row would serialise a round trip per row)
+    const int T = (ne > 0) ? __shfl_sync(0xffffffffu, incl, ne - 1) : 0;
+    for (int base = 0; base < T; base += 32) {
+        const int j = base + lane;
+        int lo = 0, hi = ne;                                   // row of entry j: the largest e with poff[e] <= j
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const int mid = (lo + hi) >> 1;
+            const bool le = (int)poff[mid] <= j;
+            if (hi - lo > 1) { if (le) lo = mid; else hi = mid; }
+        }
+        const uint64_t he = __shfl_sync(0xffffffffu, hv, lo);
+        if (j < T) {
+            const int ce = (int)sp_cnt(he);
+            const double *vals = pool_in + sp_off8(he);
+            const unsigned short *idxp = reinterpret_cast<const unsigned short *>(vals + sp_pad((uint32_t)ce));
+            const int i = j - (int)poff[lo];
+            ent_val[j] = __ldg(vals + i);
+            ent_idx[j] = __ldg(idxp + i);
         }
     }
     __syncwarp();
