@@ -77,14 +77,17 @@ struct SparseArgs {
     unsigned int *hub_work;            // next hub item to hand out (zeroed per launch); items: StepArgs::hub_items
 };
 
-// per-warp shared memory: fu_d[ld] | g_d[ld] | ent_val[E] | ent_idx[E] u16 | aidx[max(ld, 256)] u16 | poff[40] u16 |
+// The dense per-warp / per-block vectors are padded to a multiple of 32 components (zeros: a padding component has
+// fu = sumF = 0, hence gradient 0, never active), so that the loops over components need no bounds checks.
+__host__ __device__ inline int sp_ldp(int ld) { return (ld + 31) & ~31; }
+// per-warp shared memory: fu_d[ldp] | g_d[ldp] | ent_val[E] | ent_idx[E] u16 | aidx[max(ld, 256)] u16 | poff[40] u16 |
 //                         cbal[32] u32 | ccum[32] u16 (+ pad)   (ballots / running counts of the entry compaction)
 __host__ __device__ inline size_t sp_warp_bytes(int ld) {
-    return sizeof(double) * 2 * (size_t)ld + (size_t)sp_entries(ld) * 10 + 2 * (size_t)(ld > 256 ? ld : 256) + 2 * 40 + 4 * 32 + 2 * 32;
+    return sizeof(double) * 2 * (size_t)sp_ldp(ld) + (size_t)sp_entries(ld) * 10 + 2 * (size_t)(ld > 256 ? ld : 256) + 2 * 40 + 4 * 32 + 2 * 32;
 }
-// block: steps[kMaxSteps] | sumF[ld] | D[ld] | wpb x warp area
+// block: steps[kMaxSteps] | sumF[ldp] | D[ldp] | wpb x warp area
 __host__ __device__ inline size_t sp_block_smem_bytes(int ld, int wpb) {
-    return sizeof(double) * (kMaxSteps + 2 * (size_t)ld) + (size_t)wpb * sp_warp_bytes(ld);
+    return sizeof(double) * (kMaxSteps + 2 * (size_t)sp_ldp(ld)) + (size_t)wpb * sp_warp_bytes(ld);
 }
 // warps per block: as many resident warps per SM as the shared memory (227 KB, 1 KB reserved per block) allows
 inline int sp_warps_per_block(int ld) {
@@ -174,13 +177,14 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int wpb = (int)(blockDim.x >> 5), nthreads = (int)blockDim.x;
     const int ecap = sp_entries(ld);
+    const int ldp = sp_ldp(ld);
     double *s_steps = reinterpret_cast<double *>(smem_raw);
     double *s_sumF = s_steps + kMaxSteps;
-    double *s_D = s_sumF + ld;
-    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_D + ld) + (size_t)wib * sp_warp_bytes(ld);
+    double *s_D = s_sumF + ldp;
+    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_D + ldp) + (size_t)wib * sp_warp_bytes(ld);
     double *fu_d = reinterpret_cast<double *>(wbase);
-    double *g_d = fu_d + ld;
-    double *ent_val = g_d + ld;
+    double *g_d = fu_d + ldp;
+    double *ent_val = g_d + ldp;
     unsigned short *ent_idx = reinterpret_cast<unsigned short *>(ent_val + ecap);
     unsigned short *aidx = ent_idx + ecap;
     unsigned short *poff = aidx + (ld > 256 ? ld : 256);
@@ -188,11 +192,11 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
     unsigned short *ccum = reinterpret_cast<unsigned short *>(cbal + 32);
 
 #pragma unroll 1
-    for (int i = threadIdx.x; i < ld; i += nthreads) { s_sumF[i] = a.sumF[i]; s_D[i] = 0.0; }
+    for (int i = threadIdx.x; i < ldp; i += nthreads) { s_sumF[i] = (i < ld) ? a.sumF[i] : 0.0; s_D[i] = 0.0; }
 #pragma unroll 1
     for (int i = threadIdx.x; i < kMaxSteps; i += nthreads) s_steps[i] = a.steps[i];
 #pragma unroll 1
-    for (int i = lane; i < ld; i += 32) { fu_d[i] = 0.0; g_d[i] = 0.0; }
+    for (int i = lane; i < ldp; i += 32) { fu_d[i] = 0.0; g_d[i] = 0.0; }
     __syncthreads();
 
     const EdgeConst ec = {a.x_lo, a.x_hi, a.t_lo, a.t_hi, a.w_lo, a.w_hi};
@@ -246,14 +250,13 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
         double G2 = 0.0;
         bool hi_lane = false;
         m = 0;
-        for (int c0 = 0; c0 < ld; c0 += 32) {
+        for (int c0 = 0; c0 < ldp; c0 += 32) {          // (padding components: f = g = 0, inactive)
             const int c = c0 + lane;
-            const bool in = c < ld;
-            const double f = in ? fu_d[c] : 0.0;
-            const double g = in ? (g_d[c] - s_sumF[c]) + f : 0.0;
-            if (in) g_d[c] = g;
+            const double f = fu_d[c];
+            const double g = (g_d[c] - s_sumF[c]) + f;
+            g_d[c] = g;
             G2 = fma(g, g, G2);
-            const bool act = in && (f > 0.0 || g > 0.0);
+            const bool act = (f > 0.0 || g > 0.0);
             const unsigned bal = __ballot_sync(0xffffffffu, act);
             if (act) {
                 aidx[m + __popc(bal & lt_mask)] = (unsigned short)c;
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
                 bool need_hi = false;
                 double G2 = 0.0;
                 if (want_ls) {
-                    for (int c = lane; c < ld; c += 32) g_d[c] = __ldcg(scr + c);
+                    for (int c = lane; c < ldp; c += 32) g_d[c] = (c < ld) ? __ldcg(scr + c) : 0.0;
                     __syncwarp();
                     G2 = scan_gradient(m, need_hi);
                 }
@@ -497,7 +500,7 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
                 }
                 __syncwarp();
                 if (want_ls)
-                    for (int c = lane; c < ld; c += 32) g_d[c] = 0.0;
+                    for (int c = lane; c < ldp; c += 32) g_d[c] = 0.0;
             }
             __syncwarp();
             for (int i = lane; i < cu; i += 32) fu_d[__ldg(uidx + i)] = 0.0;
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
         __syncwarp();
         for (int i = lane; i < cu; i += 32) fu_d[__ldg(uidx + i)] = 0.0;
         if (want_ls)
-            for (int c = lane; c < ld; c += 32) g_d[c] = 0.0;
+            for (int c = lane; c < ldp; c += 32) g_d[c] = 0.0;
         __syncwarp();
 
         cur = nxt;
