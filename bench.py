@@ -47,6 +47,11 @@ def load_workload():
     else:
         rp, col, _ = G.load_npz_graph(_GRAPH)
     n = len(rp) - 1
+    if n * K > (1 << 31):
+        # n x K does not exist densely at this size: CSR rows (same distribution), needs --layout sparse
+        import scipy.sparse as sps
+        ip, ix, vl = G.synthetic_F0_csr(n, K, seed=1234, density=0.05)
+        return rp, col, sps.csr_matrix((vl, ix, ip), shape=(n, K))
     F0 = G.synthetic_F0(n, K, seed=1234, density=0.05)
     return rp, col, F0
 
@@ -160,7 +165,8 @@ def run_single(args):
     torch.cuda.set_device(0)
     rp, col, F0 = load_workload()
     n, nnz = len(rp) - 1, len(col)
-    b = BigClam(device=0, time_kernels=True)
+    sparse = args.layout == "sparse"
+    b = BigClam(device=0, time_kernels=True, sparse_rows=sparse)
     b.set_graph(rp, col).set_K(K)
     stream = torch.cuda.current_stream()
     b.set_stream(stream.cuda_stream)
@@ -194,6 +200,14 @@ def run_single(args):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("step_kernel_dram_bytes_per_launch")
 
+    layout_bytes = None
+    if sparse:
+        # bytes the sparse layout actually has to move per launch (row blocks: 10 B per padded entry + 8 B header):
+        # every neighbour row once per edge, every own row read and written once
+        cnt = np.diff(b.F_csr()[0])
+        blk = 10 * ((cnt + 3) // 4 * 4) + 8
+        layout_bytes = int((blk[col].sum() + 4 * nnz) + 2 * blk.sum() + 16 * n)
+
     # ---- e2e: per-call C ABI with host buffers ----
     mask = torch.ones(n, dtype=torch.uint8).pin_memory()
     llh = C.c_double(); nupd = C.c_int64()
@@ -213,7 +227,7 @@ def run_single(args):
 
     # ---- workload A of SURVEY §8d: the reference's own init (conductance seeds, 0/1 indicator columns) ----
     extra_a = None
-    if not args.no_init_a:
+    if not args.no_init_a and not hasattr(F0, "tocsr"):
         t0 = time.perf_counter()
         b.initNeighborComF(K)
         init_s = time.perf_counter() - t0
@@ -233,7 +247,7 @@ def run_single(args):
 
     # ---- CPU baseline beside it (bounded: 2 faithful steps after 1 warm-up) ----
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and not hasattr(F0, "tocsr"):
         sec, cores = time_oracle(rp, col, F0, 2, 1)
         cpu = {"value": nnz / sec, "unit": "edges/s", "cores": cores, "kind": "port",
                "sample": "2 full steps of the same workload (all 16 candidates per node) after 1 warm-up; CPU restatement of the reference, not Spark",
@@ -248,8 +262,9 @@ def run_single(args):
                    "l2": "inputs (F 536 MB x2 buffers) larger than L2, no flush", "llh_end": llh_end},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(n_all),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "step_kernel<4>", "kernel_ms": kavg_ms,
-                     "alg_bytes_per_launch": balg, "peak_source": peak_src},
+                     "traffic": None if sparse else traffic, "kernel": "sparse_step_kernel" if sparse else "step_kernel<4>",
+                     "kernel_ms": kavg_ms, "alg_bytes_per_launch": balg, "peak_source": peak_src,
+                     "f_layout": args.layout, "layout_bytes_per_launch": layout_bytes},
         "cpu_baseline": cpu, "reference_init_workload": extra_a,
     }))
     b.close()
@@ -263,11 +278,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-init-a", action="store_true", help="skip the reference-style-init extra workload")
+    ap.add_argument("--k", type=int, default=200, help="number of communities (default: the headline K = 200)")
+    ap.add_argument("--layout", default="dense", choices=["dense", "sparse"],
+                    help="device layout of F: dense n x K rows, or sparse rows like the reference's BSV[Double]")
     ap.add_argument("--graph", default="com-amazon", help="fixture name or rmat:<nodes>:<edges> (default: the headline workload)")
     args = ap.parse_args()
-    global _GRAPH, WORKLOAD
+    global _GRAPH, WORKLOAD, K
     _GRAPH = args.graph
-    if _GRAPH != "com-amazon":
+    K = args.k
+    if _GRAPH != "com-amazon" or K != 200:
         WORKLOAD = f"{_GRAPH} K={K}, synthetic F0 (p=0.05 U[0,1), seed 1234), fp64"
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -275,6 +294,8 @@ def main():
         args.warmup = min(args.warmup, 1)
         return run_reference(args)
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if args.layout == "sparse":
+            os.environ["BIGCLAM_SPARSE"] = "1"
         from bigclam_apachespark_b200 import dist
         return dist.bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD, K)
     return run_single(args)

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libbigclam_b200.so")
 OK, EINVAL, ECUDA, ENOMEM, EIO, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 F_TIME_KERNELS = 1
 F_RECORD_ACCEPTED = 2
+F_SPARSE_ROWS = 4
 
 
 class Params(C.Structure):
@@ -84,6 +85,11 @@ SIGNATURES = {
     "bigclam_ipc_export": (C.c_int, [_vp, _vp]),
     "bigclam_ipc_open_peers": (C.c_int, [_vp, _i32, _i32, _vp]),
     "bigclam_mark_all_changed": (C.c_int, [_vp]),
+    "bigclam_ipc_handle_count": (C.c_int, [_vp]),
+    "bigclam_set_F_csr": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "bigclam_get_F_nnz": (C.c_int, [_vp, _pi64]),
+    "bigclam_get_F_csr": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "bigclam_set_pool_region": (C.c_int, [_vp, _i64, _i64]),
     "bigclam_graph_read_edgelist": (C.c_int, [C.c_char_p, _i32, C.POINTER(Graph), C.c_char_p, _i64]),
     "bigclam_graph_free": (None, [C.POINTER(Graph)]),
     "bigclam_extract": (C.c_int, [_vp, _dbl, _vp, _vp]),

@@ -2,6 +2,7 @@
 // No CPU fallback: every compute entry point launches CUDA kernels or fails.
 #include "../../include/bigclam_b200.h"
 #include "bigclam_kernels.cuh"
+#include "bigclam_sparse.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -46,7 +47,7 @@ struct bigclam_ctx {
     int8_t *d_accepted_spec = nullptr;   // written by a speculative step (bigclam_step), swapped in at commit
     bool spec_valid = false;        // the next step has already been computed speculatively (see bigclam_step)
     bool spec_null_mask = true;
-    uint64_t spec_mask_hash = 0;
+    std::vector<uint8_t> spec_mask;    // the uset the speculative step was computed with (exact comparison)
     uint8_t *d_mask = nullptr;
     int32_t *d_done = nullptr;
     unsigned int *d_work = nullptr;
@@ -68,10 +69,24 @@ struct bigclam_ctx {
 
     unsigned int h_work_init = 0;
 
+    // sparse rows of F (BIGCLAM_F_SPARSE_ROWS, bigclam_sparse.cuh): header + pool per F buffer
+    bool sparse = false;
+    uint64_t *d_hdr[2] = {nullptr, nullptr};
+    double *d_pool[2] = {nullptr, nullptr};
+    uint64_t pool_cap8 = 0;
+    unsigned long long *d_pool_top = nullptr;   // [2]
+    int32_t *d_overflow = nullptr;
+    int sp_grid = 0, sp_wpb = kSpWarps;
+    size_t sp_smem = 0;
+    bool dense_valid = true;       // d_F[cur] mirrors the sparse state (set_F; refreshed on demand by ensure_dense)
+    uint64_t region_base8 = 0, region_cap8 = 0;   // this rank's part of every replica's output pool (multi-GPU)
+    uint64_t *peer_hdr[2][7] = {{nullptr}};       // peers' headers / pools (both halves), IPC-mapped
+    double *peer_pool[2][7] = {{nullptr}};
+
     std::string err;
 };
 
-static std::string g_create_err;
+static thread_local std::string g_create_err;   // bigclam_create failures (no context yet), per calling thread
 
 static int fail(bigclam_ctx *c, int code, const char *fmt, ...) {
     char buf[512];
@@ -90,6 +105,17 @@ static int fail(bigclam_ctx *c, int code, const char *fmt, ...) {
             return fail(ctx, BIGCLAM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
                         __FILE__, __LINE__);                                                      \
     } while (0)
+
+// A speculative step (bigclam_step) left its partial sums in d_partials: forget both.
+static int drop_speculation(bigclam_ctx *ctx) {
+    if (!ctx->spec_valid) return BIGCLAM_OK;
+    ctx->spec_valid = false;
+    CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
+    return BIGCLAM_OK;
+}
+
+static int ensure_dense(bigclam_ctx *ctx);
+static int check_overflow(bigclam_ctx *ctx);
 
 extern "C" const char *bigclam_version(void) { return "bigclam_b200 0.1 (sm_100a)"; }
 
@@ -136,7 +162,15 @@ static void free_ctx(bigclam_ctx *c) {
     cudaFree(c->d_sumF[0]); cudaFree(c->d_sumF[1]);
     cudaFree(c->d_partials); cudaFree(c->d_accepted); cudaFree(c->d_accepted_spec); cudaFree(c->d_mask);
     cudaFree(c->d_done); cudaFree(c->d_work); cudaFree(c->d_hub_items); cudaFree(c->d_hub_scratch); cudaFree(c->d_hub_counters); cudaFree(c->d_changed);
-    for (int h = 0; h < 2; ++h) for (int r = 0; r < c->n_peers; ++r) if (c->peer_F[h][r]) cudaIpcCloseMemHandle(c->peer_F[h][r]); cudaFree(c->d_state); cudaFree(c->d_trace);
+    for (int h = 0; h < 2; ++h)
+        for (int r = 0; r < c->n_peers; ++r) {
+            if (c->peer_F[h][r]) cudaIpcCloseMemHandle(c->peer_F[h][r]);
+            if (c->peer_hdr[h][r]) cudaIpcCloseMemHandle(c->peer_hdr[h][r]);
+            if (c->peer_pool[h][r]) cudaIpcCloseMemHandle(c->peer_pool[h][r]);
+        }
+    cudaFree(c->d_state); cudaFree(c->d_trace);
+    cudaFree(c->d_hdr[0]); cudaFree(c->d_hdr[1]); cudaFree(c->d_pool[0]); cudaFree(c->d_pool[1]);
+    cudaFree(c->d_pool_top); cudaFree(c->d_overflow);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -214,7 +248,16 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
     const int64_t max_deg = (cnt > 0) ? meta[0].deg : 0;
     const int64_t hub_deg = (4 * max_deg <= 3 * per_warp) ? INT64_MAX
                                                           : std::min<int64_t>(512, std::max<int64_t>(kHubDegree, per_warp / 5));
-    if (ctx->c2 <= 4) while (nh < cnt && meta[(size_t)nh].deg >= hub_deg) ++nh;
+    if (ctx->c2 <= 4 && !ctx->sparse) while (nh < cnt && meta[(size_t)nh].deg >= hub_deg) ++nh;
+    if (ctx->sparse && ctx->nsteps <= 16) {
+        // sparse rows: a hub is split into kSpHubSeg-edge segments over warps (bigclam_sparse.cuh) when one warp
+        // walking it would take a sizeable part of the launch: from a quarter of a warp's share of the owned
+        // entries upwards, at least 1024 edges (BIGCLAM_SPARSE_HUB_DEG overrides the threshold: tests)
+        const int64_t sp_per_warp = own_nnz / std::max<int64_t>(1, (int64_t)ctx->sp_grid * ctx->sp_wpb);
+        int64_t sp_hub_deg = std::max<int64_t>(1024, sp_per_warp / 4);
+        if (const char *ev = std::getenv("BIGCLAM_SPARSE_HUB_DEG")) sp_hub_deg = std::max<int64_t>(1, std::atoll(ev));
+        while (nh < cnt && meta[(size_t)nh].deg >= sp_hub_deg) ++nh;
+    }
     ctx->n_hubs = nh;
     // work items of the hub phase: hubs above kHubSlice edges are split into slices handled by different
     // blocks (phases 1-3), the others are done by one block (phase 0); see hub_phase
@@ -223,10 +266,11 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
         int32_t n_mega = 0;
         for (int32_t i = 0; i < nh; ++i) {
             const int32_t deg = meta[(size_t)i].deg;
-            const int32_t nsl = (deg + kHubSlice - 1) / kHubSlice;
+            const int32_t slice = ctx->sparse ? kSpHubSeg : kHubSlice;
+            const int32_t nsl = (deg + slice - 1) / slice;
             HubItem it{};
             it.hub = i;
-            if (nsl > 1 && ctx->nsteps <= 16) {
+            if ((nsl > 1 || ctx->sparse) && ctx->nsteps <= 16) {
                 it.mslot = n_mega++;
                 it.nslices = nsl;
                 for (int32_t sl = 0; sl < nsl; ++sl) {
@@ -257,9 +301,11 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
         }
         const size_t slots = (size_t)std::max<int32_t>(1, n_mega);
         CU(cudaMalloc(&ctx->d_hub_scratch, sizeof(double) * slots * ((size_t)ctx->ld + 32)));
-        CU(cudaMalloc(&ctx->d_hub_counters, sizeof(unsigned int) * 2 * slots));
+        CU(cudaMalloc(&ctx->d_hub_counters, sizeof(unsigned int) * (2 * slots + 1)));      // + the sparse kernel's item counter
+        CU(cudaMemset(ctx->d_hub_counters, 0, sizeof(unsigned int) * (2 * slots + 1)));
     }
-    const unsigned int init = (unsigned int)nh + 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
+    const unsigned int init = ctx->sparse ? (unsigned int)nh + 3u * (unsigned int)ctx->sp_grid * (unsigned int)ctx->sp_wpb
+                                          : (unsigned int)nh + 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
     ctx->h_work_init = init;
     if (ctx->d_work != nullptr) CU(cudaMemcpy(ctx->d_work + 1, &init, sizeof(unsigned int), cudaMemcpyHostToDevice));
     return BIGCLAM_OK;
@@ -357,14 +403,42 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     }
     ctx->grid = ctx->num_sms * bps;
     ctx->h_work_init = 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
+    if (params->flags & BIGCLAM_F_SPARSE_ROWS) {
+        if (params->min_f != 0.0) {
+            fail(nullptr, BIGCLAM_EUNSUPPORTED, "bigclam_create: BIGCLAM_F_SPARSE_ROWS needs min_f == 0");
+            free_ctx(ctx);
+            return BIGCLAM_EUNSUPPORTED;
+        }
+        ctx->sparse = true;
+        ctx->sp_wpb = sp_warps_per_block(ld);
+        ctx->sp_smem = sp_block_smem_bytes(ld, ctx->sp_wpb);
+        int sbps = 0;
+        CUC(cudaFuncSetAttribute(sparse_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(sparse_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(sparse_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(sparse_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        int sb2 = 0;                         // the grid must be resident for every variant (hub items wait for each other)
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sbps, sparse_step_kernel<true, true>, 32 * ctx->sp_wpb, ctx->sp_smem));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sb2, sparse_step_kernel<false, false>, 32 * ctx->sp_wpb, ctx->sp_smem));
+        sbps = std::min(sbps, sb2);
+        if (sbps <= 0) {
+            fail(nullptr, BIGCLAM_ECUDA, "bigclam_create: sparse kernel does not fit an SM (smem %zu B)", ctx->sp_smem);
+            free_ctx(ctx);
+            return BIGCLAM_ECUDA;
+        }
+        ctx->sp_grid = ctx->num_sms * sbps;
+        ctx->h_work_init = 3u * (unsigned int)ctx->sp_grid * (unsigned int)ctx->sp_wpb;
+    }
 
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
     const size_t fbytes = sizeof(double) * (size_t)n * (size_t)ld;
     CUC(cudaMalloc(&ctx->d_rowptr, sizeof(int64_t) * ((size_t)n + 1)));
     CUC(cudaMalloc(&ctx->d_col, sizeof(int32_t) * std::max<size_t>(1, (size_t)nnz)));
-    CUC(cudaMalloc(&ctx->d_F[0], fbytes));
-    CUC(cudaMalloc(&ctx->d_F[1], fbytes));
+    if (!ctx->sparse) {            // sparse rows: the dense buffers are only a mirror, allocated on first use (alloc_dense)
+        CUC(cudaMalloc(&ctx->d_F[0], fbytes));
+        CUC(cudaMalloc(&ctx->d_F[1], fbytes));
+    }
     CUC(cudaMalloc(&ctx->d_sumF[0], sizeof(double) * ld));
     CUC(cudaMalloc(&ctx->d_sumF[1], sizeof(double) * ld));
     CUC(cudaMalloc(&ctx->d_partials, sizeof(double) * (2 * (size_t)ld + 2)));
@@ -378,14 +452,39 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
     CUC(cudaMallocHost(&ctx->h_pinned, sizeof(double) * (2 * (size_t)ld + 2) + sizeof(RunState) + 64));
     CUC(cudaMemcpy(ctx->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
     if (nnz > 0) CUC(cudaMemcpy(ctx->d_col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
-    CUC(cudaMemset(ctx->d_F[0], 0, fbytes));
-    CUC(cudaMemset(ctx->d_F[1], 0, fbytes));
+    if (!ctx->sparse) {
+        CUC(cudaMemset(ctx->d_F[0], 0, fbytes));
+        CUC(cudaMemset(ctx->d_F[1], 0, fbytes));
+    }
     CUC(cudaMemset(ctx->d_sumF[0], 0, sizeof(double) * ld));
     CUC(cudaMemset(ctx->d_sumF[1], 0, sizeof(double) * ld));
     CUC(cudaMemset(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ld + 2)));
     CUC(cudaMemset(ctx->d_accepted, 0xff, (size_t)n));
     CUC(cudaMemset(ctx->d_done, 0, sizeof(int32_t)));
     CUC(cudaMemset(ctx->d_state, 0, sizeof(RunState)));
+    if (ctx->sparse) {
+        // worst case: every row full (ld entries) — a step can then never overflow its pool.  When two such
+        // pools do not fit in 80 % of the free memory, each pool gets 40 % of it and a step that runs out reports
+        // BIGCLAM_ENOMEM (its input is untouched).  BIGCLAM_SPARSE_POOL_WORDS overrides the size (tests).
+        ctx->pool_cap8 = (uint64_t)n * sp_words((uint32_t)ld);
+        {
+            size_t free_b = 0, total_b = 0;
+            CUC(cudaMemGetInfo(&free_b, &total_b));
+            if ((double)ctx->pool_cap8 * 16.0 > 0.8 * (double)free_b) ctx->pool_cap8 = (uint64_t)(0.4 * (double)free_b / 8.0);
+            if (const char *ev = std::getenv("BIGCLAM_SPARSE_POOL_WORDS")) ctx->pool_cap8 = (uint64_t)std::max<long long>(64, std::atoll(ev));
+        }
+        ctx->region_base8 = 0;
+        ctx->region_cap8 = ctx->pool_cap8;
+        for (int b = 0; b < 2; ++b) {
+            CUC(cudaMalloc(&ctx->d_hdr[b], sizeof(uint64_t) * (size_t)n));
+            CUC(cudaMemset(ctx->d_hdr[b], 0, sizeof(uint64_t) * (size_t)n));
+            CUC(cudaMalloc(&ctx->d_pool[b], sizeof(double) * (size_t)ctx->pool_cap8));
+        }
+        CUC(cudaMalloc(&ctx->d_pool_top, 2 * sizeof(unsigned long long)));
+        CUC(cudaMemset(ctx->d_pool_top, 0, 2 * sizeof(unsigned long long)));
+        CUC(cudaMalloc(&ctx->d_overflow, sizeof(int32_t)));
+        CUC(cudaMemset(ctx->d_overflow, 0, sizeof(int32_t)));
+    }
 #undef CUC
     {
         std::vector<int64_t> rp(rowptr, rowptr + n + 1);
@@ -408,6 +507,10 @@ extern "C" int bigclam_set_stream(bigclam_ctx *ctx, void *cuda_stream) {
 
 extern "C" int bigclam_device_state(bigclam_ctx *ctx, void **F_dev, void **F_next_dev, void **sumF_dev, int64_t *ld) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (ctx->sparse) {                       // the dense buffers are only a mirror here: refresh it
+        CU(cudaSetDevice(ctx->device));
+        if (int re = ensure_dense(ctx)) return re;
+    }
     if (F_dev) *F_dev = ctx->d_F[ctx->cur];
     if (F_next_dev) *F_next_dev = ctx->d_F[ctx->cur ^ 1];
     if (sumF_dev) *sumF_dev = ctx->d_sumF[ctx->cur];
@@ -422,35 +525,194 @@ static int colsum_current(bigclam_ctx *ctx) {
     dim3 grid((ctx->ld + 31) / 32, nchunks);
     colsum_partial_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_F[ctx->cur], ctx->n, ctx->ld, part);
     colsum_final_kernel<<<(ctx->ld + 127) / 128, 128, 0, ctx->stream>>>(part, nchunks, ctx->ld, ctx->d_sumF[ctx->cur]);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(part);
+    if (e != cudaSuccess) return fail(ctx, BIGCLAM_ECUDA, "column sums of F: %s", cudaGetErrorString(e));
+    return BIGCLAM_OK;
+}
+
+// Sparse mode: the dense n x ld buffers exist only while somebody needs dense rows.
+static int alloc_dense(bigclam_ctx *ctx, int b) {
+    if (ctx->d_F[b] != nullptr) return BIGCLAM_OK;
+    CU(cudaMalloc(&ctx->d_F[b], sizeof(double) * (size_t)ctx->n * (size_t)ctx->ld));
+    return BIGCLAM_OK;
+}
+
+// Sparse mode: rebuild the sparse rows of the current buffer from its dense mirror d_F[cur].
+static int sparse_from_dense(bigclam_ctx *ctx) {
+    const int b = ctx->cur;
+    CU(cudaMemsetAsync(ctx->d_pool_top + b, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_overflow, 0, sizeof(int32_t), ctx->stream));
+    const int wpb = 8;
+    dense_to_sparse_kernel<<<(unsigned)((ctx->n + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+        ctx->d_F[b], ctx->n, ctx->ld, ctx->d_hdr[b], ctx->d_pool[b], ctx->d_pool_top + b, ctx->pool_cap8, ctx->d_overflow);
     CU(cudaGetLastError());
+    ctx->dense_valid = true;
+    return BIGCLAM_OK;
+}
+
+// Sparse mode: entry points that hand out dense rows refresh the mirror d_F[cur] first.
+static int ensure_dense(bigclam_ctx *ctx) {
+    if (!ctx->sparse || (ctx->dense_valid && ctx->d_F[ctx->cur] != nullptr)) return BIGCLAM_OK;
+    const int b = ctx->cur;
+    if (int ra = alloc_dense(ctx, b)) return ra;
+    const int wpb = 8;
+    sparse_to_dense_kernel<<<(unsigned)((ctx->n + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+        ctx->d_hdr[b], ctx->d_pool[b], ctx->n, ctx->ld, ctx->d_F[b]);
+    CU(cudaGetLastError());
+    ctx->dense_valid = true;
+    return BIGCLAM_OK;
+}
+
+// Sparse mode: a step that ran out of pool space left garbage rows; report it (cannot happen with the
+// worst-case pool bigclam_create allocates, kept as a guard for smaller pools).
+static int check_overflow(bigclam_ctx *ctx) {
+    if (!ctx->sparse) return BIGCLAM_OK;
+    int32_t ov = 0;
+    CU(cudaMemcpyAsync(&ov, ctx->d_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaFree(part));
+    if (ov) return fail(ctx, BIGCLAM_ENOMEM, "sparse row pool exhausted");
     return BIGCLAM_OK;
 }
 
 extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
-    ctx->spec_valid = false;
     if (F == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_F: F is NULL");
     CU(cudaSetDevice(ctx->device));
+    if (int rd = drop_speculation(ctx)) return rd;
     const int k = ctx->p.k, ld = ctx->ld;
+    if (ctx->sparse) { if (int ra = alloc_dense(ctx, ctx->cur)) return ra; }
     // values must already satisfy the invariant the reference maintains: MIN_F <= F <= MAX_F
     CU(cudaMemsetAsync(ctx->d_F[ctx->cur], 0, sizeof(double) * (size_t)ctx->n * ld, ctx->stream));
     CU(cudaMemcpy2DAsync(ctx->d_F[ctx->cur], sizeof(double) * ld, F, sizeof(double) * k, sizeof(double) * k,
                          (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
     int rc = colsum_current(ctx);
     if (rc != BIGCLAM_OK) return rc;
+    if (ctx->sparse) {
+        rc = sparse_from_dense(ctx);
+        if (rc == BIGCLAM_OK) rc = check_overflow(ctx);        // a pool smaller than the rows: BIGCLAM_ENOMEM
+        if (rc != BIGCLAM_OK) return rc;
+    }
     // with peer replicas every row counts as changed again: the next step publishes all owned rows
     if (ctx->d_changed != nullptr) CU(cudaMemsetAsync(ctx->d_changed, 1, (size_t)ctx->n, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return BIGCLAM_OK;
 }
 
+// F given / returned as CSR rows — the shape of the reference's RDD[(Long, BSV[Double])] (bigclam4-7.scala:97-104).
+// With BIGCLAM_F_SPARSE_ROWS nothing dense is ever materialised (n x K may not fit anywhere); a dense context
+// goes through a dense host image.
+extern "C" int bigclam_set_F_csr(bigclam_ctx *ctx, const int64_t *indptr, const int32_t *indices, const double *values) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (indptr == nullptr || (indptr[ctx->n] > 0 && (indices == nullptr || values == nullptr)))
+        return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_F_csr: NULL argument");
+    const int64_t n = ctx->n;
+    const int32_t k = ctx->p.k, ld = ctx->ld;
+    if (!ctx->sparse) {
+        std::vector<double> dense((size_t)n * k, 0.0);
+        for (int64_t u = 0; u < n; ++u)
+            for (int64_t i = indptr[u]; i < indptr[u + 1]; ++i) {
+                if (indices[i] < 0 || indices[i] >= k) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_F_csr: index out of range in row %lld", (long long)u);
+                dense[(size_t)u * k + indices[i]] = values[i];
+            }
+        return bigclam_set_F(ctx, dense.data());
+    }
+    CU(cudaSetDevice(ctx->device));
+    if (int rd = drop_speculation(ctx)) return rd;
+    uint64_t need = 0;
+    for (int64_t u = 0; u < n; ++u) {
+        uint32_t cnt = 0;
+        for (int64_t i = indptr[u]; i < indptr[u + 1]; ++i) cnt += (values[i] != 0.0);
+        need += sp_words(cnt);
+    }
+    if (need > ctx->pool_cap8) return fail(ctx, BIGCLAM_ENOMEM, "bigclam_set_F_csr: rows need %llu pool words, %llu available", (unsigned long long)need, (unsigned long long)ctx->pool_cap8);
+    std::vector<uint64_t> hdr((size_t)n);
+    std::vector<double> pool((size_t)need + 1), colsum((size_t)ld, 0.0);
+    const int64_t used = sp_host_pack(n, k, ld, indptr, indices, values, hdr.data(), pool.data(), need, colsum.data());
+    if (used < 0) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_F_csr: index outside [0, k) or more than ld entries in a row");
+    const int b = ctx->cur;
+    const unsigned long long top = (unsigned long long)used;
+    CU(cudaMemcpyAsync(ctx->d_hdr[b], hdr.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (used > 0) CU(cudaMemcpyAsync(ctx->d_pool[b], pool.data(), sizeof(double) * (size_t)used, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_pool_top + b, &top, sizeof(top), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_sumF[b], colsum.data(), sizeof(double) * (size_t)ld, cudaMemcpyHostToDevice, ctx->stream));   // :105-106
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->dense_valid = false;
+    return BIGCLAM_OK;
+}
+
+// Downloads the sparse state (sparse context) or the dense F (dense context) for the two getters below.
+static int fetch_rows_host(bigclam_ctx *ctx, std::vector<uint64_t> &hdr, std::vector<double> &pool, std::vector<double> &dense) {
+    const int64_t n = ctx->n;
+    if (ctx->sparse) {
+        const int b = ctx->cur;
+        hdr.resize((size_t)n);
+        CU(cudaMemcpyAsync(hdr.data(), ctx->d_hdr[b], sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        uint64_t extent = 0;
+        for (int64_t u = 0; u < n; ++u)
+            if (sp_cnt(hdr[u]) > 0) extent = std::max<uint64_t>(extent, sp_off8(hdr[u]) + sp_words(sp_cnt(hdr[u])));
+        pool.resize((size_t)extent + 1);
+        if (extent > 0) CU(cudaMemcpyAsync(pool.data(), ctx->d_pool[b], sizeof(double) * (size_t)extent, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return BIGCLAM_OK;
+    }
+    dense.resize((size_t)n * ctx->p.k);
+    return bigclam_get_F(ctx, dense.data());
+}
+
+extern "C" int bigclam_get_F_nnz(bigclam_ctx *ctx, int64_t *nnz_out) {
+    if (ctx == nullptr || nnz_out == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> hdr;
+    std::vector<double> pool, dense;
+    if (ctx->sparse) {                       // the headers are enough
+        hdr.resize((size_t)ctx->n);
+        CU(cudaMemcpyAsync(hdr.data(), ctx->d_hdr[ctx->cur], sizeof(uint64_t) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        *nnz_out = sp_host_nnz(ctx->n, hdr.data());
+        return BIGCLAM_OK;
+    }
+    if (int rf = fetch_rows_host(ctx, hdr, pool, dense)) return rf;
+    int64_t t = 0;
+    for (double v : dense) t += (v != 0.0);
+    *nnz_out = t;
+    return BIGCLAM_OK;
+}
+
+// indptr_out: n + 1; indices_out / values_out: bigclam_get_F_nnz() entries (ascending indices inside a row).
+extern "C" int bigclam_get_F_csr(bigclam_ctx *ctx, int64_t *indptr_out, int32_t *indices_out, double *values_out) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (indptr_out == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_get_F_csr: indptr_out is NULL");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> hdr;
+    std::vector<double> pool, dense;
+    if (int rf = fetch_rows_host(ctx, hdr, pool, dense)) return rf;
+    if (ctx->sparse) {
+        if (sp_host_nnz(ctx->n, hdr.data()) > 0 && (indices_out == nullptr || values_out == nullptr))
+            return fail(ctx, BIGCLAM_EINVAL, "bigclam_get_F_csr: NULL output");
+        sp_host_unpack(ctx->n, hdr.data(), pool.data(), indptr_out, indices_out, values_out);
+        return BIGCLAM_OK;
+    }
+    int64_t t = 0;
+    const int k = ctx->p.k;
+    for (int64_t u = 0; u < ctx->n; ++u) {
+        indptr_out[u] = t;
+        for (int c = 0; c < k; ++c) {
+            const double v = dense[(size_t)u * k + c];
+            if (v != 0.0) { indices_out[t] = c; values_out[t] = v; ++t; }
+        }
+    }
+    indptr_out[ctx->n] = t;
+    return BIGCLAM_OK;
+}
+
 extern "C" int bigclam_set_sumF(bigclam_ctx *ctx, const double *sumF) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
-    ctx->spec_valid = false;
     if (sumF == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_sumF: sumF is NULL");
     CU(cudaSetDevice(ctx->device));
+    if (int rd = drop_speculation(ctx)) return rd;
     CU(cudaMemsetAsync(ctx->d_sumF[ctx->cur], 0, sizeof(double) * ctx->ld, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_sumF[ctx->cur], sumF, sizeof(double) * ctx->p.k, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -461,6 +723,7 @@ extern "C" int bigclam_get_F(bigclam_ctx *ctx, double *F_out) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     if (F_out == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_get_F: F_out is NULL");
     CU(cudaSetDevice(ctx->device));
+    if (int re = ensure_dense(ctx)) return re;
     const int k = ctx->p.k, ld = ctx->ld;
     CU(cudaMemcpy2DAsync(F_out, sizeof(double) * k, ctx->d_F[ctx->cur], sizeof(double) * ld, sizeof(double) * k,
                          (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -539,13 +802,42 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
         }
         CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
     }
-    if (ctx->n_mega > 0) {     // mega-hub scratch and slice counters start every launch at zero
+    if (ctx->n_mega > 0) {     // mega-hub scratch, slice counters (and the sparse kernel's item counter) start every launch at zero
         CU(cudaMemsetAsync(ctx->d_hub_scratch, 0, sizeof(double) * (size_t)ctx->n_mega * ((size_t)ctx->ld + 32), ctx->stream));
-        CU(cudaMemsetAsync(ctx->d_hub_counters, 0, sizeof(unsigned int) * 2 * (size_t)ctx->n_mega, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_hub_counters, 0, sizeof(unsigned int) * (2 * (size_t)ctx->n_mega + 1), ctx->stream));
     }
     // positions 0 .. 3*#warps-1 are pre-assigned statically, the rest is handed out dynamically
     CU(cudaMemcpyAsync(ctx->d_work, ctx->d_work + 1, sizeof(unsigned int), cudaMemcpyDeviceToDevice, ctx->stream));
-    launch_step(ctx->c2, a, ctx->grid, ctx->smem_bytes, ctx->stream);
+    if (ctx->sparse) {
+        // reads hdr/pool of the current buffer, writes the other one (its bump allocator starts at zero)
+        const int in = ctx->cur, out = in ^ 1;
+        SparseArgs sp;
+        sp.hdr_in = ctx->d_hdr[in];
+        sp.pool_in = ctx->d_pool[in];
+        sp.hdr_out = ctx->d_hdr[out];
+        sp.pool_out = ctx->d_pool[out];
+        sp.pool_top = ctx->d_pool_top + out;
+        sp.pool_cap8 = ctx->region_cap8;
+        sp.region_base8 = ctx->region_base8;
+        sp.overflow = ctx->d_overflow;
+        sp.n_peers = a.do_linesearch ? ctx->n_peers : 0;
+        for (int r = 0; r < 7; ++r) {
+            sp.peer_hdr[r] = (r < ctx->n_peers) ? ctx->peer_hdr[out][r] : nullptr;
+            sp.peer_pool[r] = (r < ctx->n_peers) ? ctx->peer_pool[out][r] : nullptr;
+        }
+        if (a.do_linesearch) {
+            CU(cudaMemsetAsync(sp.pool_top, 0, sizeof(unsigned long long), ctx->stream));
+            ctx->dense_valid = false;
+        }
+        sp.hub_work = ctx->d_hub_counters + 2 * (size_t)std::max<int32_t>(1, ctx->n_mega);
+        const bool hub = a.n_hub_items > 0, push = sp.n_peers > 0;
+        if (hub && push) sparse_step_kernel<true, true><<<ctx->sp_grid, 32 * ctx->sp_wpb, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else if (hub) sparse_step_kernel<false, true><<<ctx->sp_grid, 32 * ctx->sp_wpb, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else if (push) sparse_step_kernel<true, false><<<ctx->sp_grid, 32 * ctx->sp_wpb, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else sparse_step_kernel<false, false><<<ctx->sp_grid, 32 * ctx->sp_wpb, ctx->sp_smem, ctx->stream>>>(a, sp);
+    } else {
+        launch_step(ctx->c2, a, ctx->grid, ctx->smem_bytes, ctx->stream);
+    }
     CU(cudaGetLastError());
     if (timing) {
         CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
@@ -617,18 +909,6 @@ extern "C" int bigclam_loglikelihood(bigclam_ctx *ctx, double *llh_out) {
     return BIGCLAM_OK;
 }
 
-static uint64_t mask_hash(const uint8_t *m, int64_t n) {
-    uint64_t h = 1469598103934665603ULL;
-    int64_t i = 0;
-    for (; i + 8 <= n; i += 8) {
-        uint64_t v;
-        std::memcpy(&v, m + i, 8);
-        h = (h ^ v) * 1099511628211ULL;
-    }
-    for (; i < n; ++i) h = (h ^ m[i]) * 1099511628211ULL;
-    return h;
-}
-
 // One call of backtrackingLineSearchs.  The LLH it has to return is the PRE sum of the NEXT call, so
 // instead of a separate LLH pass the next call's whole step kernel is launched speculatively (same uset):
 // its PRE delivers this call's LLH, and when the next call arrives with the same uset its result is simply
@@ -638,8 +918,9 @@ extern "C" int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *
     CU(cudaSetDevice(ctx->device));
     const bool speculate = (ctx->n_peers == 0);         // peers' replicas must never see uncommitted rows
     const bool null_mask = (node_mask == nullptr);
-    const uint64_t hash = null_mask ? 0 : mask_hash(node_mask, ctx->n);
-    const bool hit = speculate && ctx->spec_valid && ctx->spec_null_mask == null_mask && ctx->spec_mask_hash == hash;
+    const bool hit = speculate && ctx->spec_valid && ctx->spec_null_mask == null_mask &&
+                     (null_mask || (ctx->spec_mask.size() == (size_t)ctx->n &&
+                                    std::memcmp(ctx->spec_mask.data(), node_mask, (size_t)ctx->n) == 0));
     int rc;
     StepArgs a;
     const uint8_t *d_mask = null_mask ? nullptr : ctx->d_mask;
@@ -662,6 +943,7 @@ extern "C" int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *
     rc = launch_finish(ctx, 0, 0, 0.0, true, false);
     if (rc) return rc;
     ctx->cur ^= 1;
+    ctx->dense_valid = false;
     std::swap(ctx->d_accepted, ctx->d_accepted_spec);
     CU(cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_state, sizeof(RunState), cudaMemcpyDeviceToHost, ctx->stream));
     if (speculate) {
@@ -671,7 +953,7 @@ extern "C" int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *
         if (rc) return rc;
         ctx->spec_valid = true;
         ctx->spec_null_mask = null_mask;
-        ctx->spec_mask_hash = hash;
+        if (!null_mask && !hit) ctx->spec_mask.assign(node_mask, node_mask + ctx->n);   // on a hit it is already equal
     } else {
         fill_args(ctx, a, false, nullptr, false);          // LLH with new F, new sumF (:196-219)
         rc = timed_launch(ctx, a, false);
@@ -679,6 +961,7 @@ extern "C" int bigclam_step(bigclam_ctx *ctx, const uint8_t *node_mask, double *
     }
     CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials + 2 * ctx->ld, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (int ro = check_overflow(ctx)) return ro;
     if (llh_out) *llh_out = ctx->h_pinned[0];
     if (n_updated_out) *n_updated_out = reinterpret_cast<RunState *>(ctx->h_pinned + 8)->n_updated;
     return collect_timing(ctx);
@@ -742,6 +1025,8 @@ extern "C" int bigclam_run(bigclam_ctx *ctx, int32_t variant, double rel_tol, in
         CU(cudaStreamSynchronize(ctx->stream));
     }
     ctx->cur = (start_cur + (int)(calls & 1)) & 1;
+    ctx->dense_valid = false;
+    if (int ro = check_overflow(ctx)) return ro;
     if (llh_out) *llh_out = hst->ret_llh;
     if (calls_out) *calls_out = calls;
     if (llh_trace != nullptr && trace_cap > 0) {
@@ -771,14 +1056,14 @@ extern "C" int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi)
     CU(cudaMemcpy(rp.data(), ctx->d_rowptr, sizeof(int64_t) * rp.size(), cudaMemcpyDeviceToHost));
     ctx->lo = lo;
     ctx->hi = hi;
-    ctx->spec_valid = false;
+    if (int rd = drop_speculation(ctx)) return rd;
     return rebuild_order(ctx, rp);
 }
 
 extern "C" int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    if (ctx->spec_valid) { int rr = reset_run_state(ctx); if (rr) return rr; }   // drop a speculative bigclam_step
+    if (int rd = drop_speculation(ctx)) return rd;
     StepArgs a;
     fill_args(ctx, a, true, nullptr, false);
     int rc = timed_launch(ctx, a, true);
@@ -806,7 +1091,7 @@ extern "C" int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64
 extern "C" int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    if (ctx->spec_valid) { int rr = reset_run_state(ctx); if (rr) return rr; }   // drop a speculative bigclam_step
+    if (int rd = drop_speculation(ctx)) return rd;
     CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
     StepArgs a;
     fill_args(ctx, a, false, nullptr, false);
@@ -818,8 +1103,10 @@ extern "C" int bigclam_llh_local(bigclam_ctx *ctx, void **partials_dev) {
 
 extern "C" int bigclam_rollback(bigclam_ctx *ctx) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
-    ctx->spec_valid = false;
+    CU(cudaSetDevice(ctx->device));
+    if (int rd = drop_speculation(ctx)) return rd;
     ctx->cur ^= 1;
+    ctx->dense_valid = false;
     return BIGCLAM_OK;
 }
 
@@ -839,10 +1126,19 @@ extern "C" int bigclam_device_accepted(bigclam_ctx *ctx, void **accepted_dev) {
 extern "C" int bigclam_ipc_export(bigclam_ctx *ctx, void *handles_out /* 2 x 64 bytes */) {
     if (ctx == nullptr || handles_out == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (ctx->sparse) {                       // 4 handles: hdr[0], hdr[1], pool[0], pool[1]
+        cudaIpcMemHandle_t h[4];
+        CU(cudaIpcGetMemHandle(&h[0], ctx->d_hdr[0]));
+        CU(cudaIpcGetMemHandle(&h[1], ctx->d_hdr[1]));
+        CU(cudaIpcGetMemHandle(&h[2], ctx->d_pool[0]));
+        CU(cudaIpcGetMemHandle(&h[3], ctx->d_pool[1]));
+        std::memcpy(handles_out, h, sizeof(h));
+        return BIGCLAM_OK;
+    }
     cudaIpcMemHandle_t h[2];
     CU(cudaIpcGetMemHandle(&h[0], ctx->d_F[0]));
     CU(cudaIpcGetMemHandle(&h[1], ctx->d_F[1]));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     std::memcpy(handles_out, h, sizeof(h));
     return BIGCLAM_OK;
 }
@@ -852,13 +1148,28 @@ extern "C" int bigclam_ipc_open_peers(bigclam_ctx *ctx, int32_t world, int32_t r
         return fail(ctx, BIGCLAM_EINVAL, "bigclam_ipc_open_peers: bad world/rank (at most 8 GPUs)");
     CU(cudaSetDevice(ctx->device));
     const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles);
+    for (int half = 0; half < 2; ++half)            // a second call replaces the first mapping
+        for (int r = 0; r < ctx->n_peers; ++r) {
+            if (ctx->peer_F[half][r]) { cudaIpcCloseMemHandle(ctx->peer_F[half][r]); ctx->peer_F[half][r] = nullptr; }
+            if (ctx->peer_hdr[half][r]) { cudaIpcCloseMemHandle(ctx->peer_hdr[half][r]); ctx->peer_hdr[half][r] = nullptr; }
+            if (ctx->peer_pool[half][r]) { cudaIpcCloseMemHandle(ctx->peer_pool[half][r]); ctx->peer_pool[half][r] = nullptr; }
+        }
+    ctx->n_peers = 0;
     int np = 0;
+    const int per = ctx->sparse ? 4 : 2;            // handles per rank (bigclam_ipc_handle_count)
     for (int r = 0; r < world; ++r) {
         if (r == rank) continue;
         for (int half = 0; half < 2; ++half) {
             void *p = nullptr;
-            CU(cudaIpcOpenMemHandle(&p, h[2 * r + half], cudaIpcMemLazyEnablePeerAccess));
-            ctx->peer_F[half][np] = reinterpret_cast<double *>(p);
+            CU(cudaIpcOpenMemHandle(&p, h[per * r + half], cudaIpcMemLazyEnablePeerAccess));
+            if (ctx->sparse) {
+                ctx->peer_hdr[half][np] = reinterpret_cast<uint64_t *>(p);
+                void *q = nullptr;
+                CU(cudaIpcOpenMemHandle(&q, h[per * r + 2 + half], cudaIpcMemLazyEnablePeerAccess));
+                ctx->peer_pool[half][np] = reinterpret_cast<double *>(q);
+            } else {
+                ctx->peer_F[half][np] = reinterpret_cast<double *>(p);
+            }
         }
         ++np;
     }
@@ -874,6 +1185,25 @@ extern "C" int bigclam_mark_all_changed(bigclam_ctx *ctx) {
     if (ctx->d_changed == nullptr) return BIGCLAM_OK;
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemsetAsync(ctx->d_changed, 1, (size_t)ctx->n, ctx->stream));
+    return BIGCLAM_OK;
+}
+
+// Handles per rank that bigclam_ipc_export writes and bigclam_ipc_open_peers expects (64 bytes each).
+extern "C" int bigclam_ipc_handle_count(const bigclam_ctx *ctx) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    return ctx->sparse ? 4 : 2;
+}
+
+// Sparse rows, multi-GPU: the part [base, base + cap) (8-byte words) of every replica's output pool that this
+// rank allocates its owned rows in.  The parts of the ranks must not overlap; cap >= owned nodes * words of a
+// full row can never overflow.
+extern "C" int bigclam_set_pool_region(bigclam_ctx *ctx, int64_t base_words, int64_t cap_words) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    if (!ctx->sparse) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_pool_region: context without BIGCLAM_F_SPARSE_ROWS");
+    if (base_words < 0 || cap_words < 0 || (uint64_t)base_words + (uint64_t)cap_words > ctx->pool_cap8)
+        return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_pool_region: region outside the pool (%llu words)", (unsigned long long)ctx->pool_cap8);
+    ctx->region_base8 = (uint64_t)base_words;
+    ctx->region_cap8 = (uint64_t)cap_words;
     return BIGCLAM_OK;
 }
 
@@ -900,7 +1230,7 @@ extern "C" int bigclam_set_owned_nodes(bigclam_ctx *ctx, const int32_t *nodes, i
     std::vector<int32_t> order(nodes, nodes + count);
     ctx->lo = 0;
     ctx->hi = ctx->n;
-    ctx->spec_valid = false;
+    if (int rd = drop_speculation(ctx)) return rd;
     return rebuild_order_list(ctx, rp, order);
 }
 
@@ -909,14 +1239,17 @@ extern "C" int bigclam_extract(bigclam_ctx *ctx, double delta, uint8_t *member_o
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     if (member_out == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_extract: member_out is NULL");
     CU(cudaSetDevice(ctx->device));
+    if (int re = ensure_dense(ctx)) return re;
     const int k = ctx->p.k;
     uint8_t *d_member = nullptr;
     double *d_fmax = nullptr;
-    CU(cudaMalloc(&d_member, (size_t)ctx->n * k));
-    CU(cudaMalloc(&d_fmax, sizeof(double) * (size_t)ctx->n));
+    cudaError_t e = cudaMalloc(&d_member, (size_t)ctx->n * k);
+    if (e == cudaSuccess) e = cudaMalloc(&d_fmax, sizeof(double) * (size_t)ctx->n);
     const int wpb = 8;
-    extract_kernel<<<(unsigned)((ctx->n + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(ctx->d_F[ctx->cur], ctx->n, k, ctx->ld, delta, d_member, d_fmax);
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        extract_kernel<<<(unsigned)((ctx->n + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(ctx->d_F[ctx->cur], ctx->n, k, ctx->ld, delta, d_member, d_fmax);
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(member_out, d_member, (size_t)ctx->n * k, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && fmax_out != nullptr) e = cudaMemcpyAsync(fmax_out, d_fmax, sizeof(double) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -64,7 +64,9 @@ def deal_by_degree(rowptr: np.ndarray, rank: int, world: int) -> np.ndarray:
 class CudaEngine:
     """The C-ABI context of one rank (libbigclam_b200.so) behind the engine interface."""
 
-    def __init__(self, solver, lo: int, hi: int, nodes=None):
+    def __init__(self, solver, lo: int, hi: int, nodes=None, owned_counts=None, rank: int = 0):
+        """owned_counts (sparse rows only): the number of owned nodes of every rank, so that each rank can place
+        its part of the output pool behind the parts of the lower ranks (bigclam_set_pool_region)."""
         import torch
         from . import _lib
         self.torch = torch
@@ -72,11 +74,17 @@ class CudaEngine:
         self.check = _lib.check
         self.s = solver
         self.ctx = solver._need()
+        self.sparse = bool(solver.flags & _lib.F_SPARSE_ROWS)
         if nodes is None:
             self.check(self.lib.bigclam_set_owned_range(self.ctx, lo, hi), self.ctx)
         else:
             nodes = np.ascontiguousarray(nodes, dtype=np.int32)
             self.check(self.lib.bigclam_set_owned_nodes(self.ctx, nodes.ctypes.data, len(nodes)), self.ctx)
+        if self.sparse and owned_counts is not None:
+            ld = (solver.K + 3) & ~3
+            row_words = ld * 5 // 4                       # sp_words(ld): a full row, values + uint16 indices
+            base = int(sum(owned_counts[:rank])) * row_words
+            self.check(self.lib.bigclam_set_pool_region(self.ctx, base, int(owned_counts[rank]) * row_words), self.ctx)
         self.lo, self.hi = int(lo), int(hi)
         self._views = {}
         self.n, self.k = solver.n, solver.K
@@ -127,12 +135,13 @@ class CudaEngine:
         """Exchange the CUDA IPC handles of the F double buffers and map every peer's replica, so that
         the step kernel can push changed rows straight into them over NVLink (exchange="p2p")."""
         torch = self.torch
-        mine = (C.c_ubyte * 128)()
+        nbytes = 64 * int(self.lib.bigclam_ipc_handle_count(self.ctx))        # 2 handles (dense F) or 4 (sparse rows)
+        mine = (C.c_ubyte * nbytes)()
         self.check(self.lib.bigclam_ipc_export(self.ctx, mine), self.ctx)
         t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).cuda()
-        allh = torch.empty(world * 128, dtype=torch.uint8, device="cuda")
+        allh = torch.empty(world * nbytes, dtype=torch.uint8, device="cuda")
         dist.all_gather_into_tensor(allh, t)
-        buf = (C.c_ubyte * (world * 128)).from_buffer_copy(allh.cpu().numpy().tobytes())
+        buf = (C.c_ubyte * (world * nbytes)).from_buffer_copy(allh.cpu().numpy().tobytes())
         self.check(self.lib.bigclam_ipc_open_peers(self.ctx, world, rank, buf), self.ctx)
 
     def mark_all_changed(self):
@@ -164,6 +173,8 @@ class DistBigClam:
         if exchange == "delta":
             import torch
             self.torch = torch
+        if getattr(engine, "sparse", False) and exchange != "p2p":
+            raise ValueError("sparse rows travel through the fused peer stores only (exchange='p2p')")
         if exchange == "p2p":
             engine.open_peers(self.dist, rank, world)
 
@@ -294,7 +305,8 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rp, col, F0 = load_workload()
     n, nnz = len(rp) - 1, len(col)
-    b = BigClam(device=local, time_kernels=True, record_accepted=True)
+    sparse = os.environ.get("BIGCLAM_SPARSE", "0") == "1"
+    b = BigClam(device=local, time_kernels=True, record_accepted=True, sparse_rows=sparse)
     b.set_graph(rp, col).set_K(K)
     stream = torch.cuda.current_stream()
     b.set_stream(stream.cuda_stream)
@@ -302,7 +314,8 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     bounds = partition_by_nnz(rp, world)
     exchange = os.environ.get("BIGCLAM_EXCHANGE", "p2p")
     nodes = deal_by_degree(rp, rank, world) if exchange == "p2p" else None
-    eng = CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1]), nodes=nodes)
+    counts = [len(range(r, n, world)) for r in range(world)] if exchange == "p2p" else None     # |order[r::world]|
+    eng = CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1]), nodes=nodes, owned_counts=counts, rank=rank)
     d = DistBigClam(eng, rp, rank, world, bounds, exchange=exchange)
 
     for _ in range(args.warmup):

@@ -79,12 +79,15 @@ class BigClam:
 
     def __init__(self, numCore: int = 36, minCom: int = 1000, maxCom: int = 9000, divCom: int = 100,
                  alpha: float = 0.05, beta: float = 0.1, MaxInter: int = 15, device: int = -1,
-                 time_kernels: bool = False, record_accepted: bool = False, verbose: bool = False):
+                 time_kernels: bool = False, record_accepted: bool = False, verbose: bool = False,
+                 sparse_rows: bool = False):
         self.numCore, self.minCom, self.maxCom, self.divCom = numCore, minCom, maxCom, divCom
         self.alpha, self.beta, self.MaxInter = alpha, beta, MaxInter
         self.MIN_P_, self.MAX_P_, self.MIN_F_, self.MAX_F_ = 0.0001, 0.9999, 0.0, 1000.0   # :40-43
         self.device = device
         self.flags = (_lib.F_TIME_KERNELS if time_kernels else 0) | (_lib.F_RECORD_ACCEPTED if record_accepted else 0)
+        if sparse_rows:       # F as sparse rows on the device (the reference's BSV[Double]); K <= 256, one GPU
+            self.flags |= _lib.F_SPARSE_ROWS
         self.verbose = verbose
         self.K = None
         self.rowptr = self.col = self.ids = None
@@ -125,8 +128,38 @@ class BigClam:
         self._ctx = ctx
         return self
 
+    def set_F_csr(self, indptr, indices, values, K=None, sumF=None):
+        """F <- CSR rows (the reference's RDD[(Long, BSV[Double])], :97-104); sumF <- column sums unless given.
+        With sparse_rows=True no dense n x K image is built anywhere."""
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        if K is not None and (self._ctx is None or int(K) != self.K):
+            self.set_K(int(K))
+        if len(indptr) != self.n + 1 or len(indices) != indptr[-1] or len(values) != indptr[-1]:
+            raise ValueError("CSR arrays do not describe n rows")
+        check(_lib.load().bigclam_set_F_csr(self._need(), indptr.ctypes.data, indices.ctypes.data, values.ctypes.data), self._ctx)
+        if sumF is not None:
+            sumF = np.ascontiguousarray(sumF, dtype=np.float64)
+            check(_lib.load().bigclam_set_sumF(self._ctx, sumF.ctypes.data), self._ctx)
+        return self
+
+    def F_csr(self):
+        """Current F as (indptr, indices, values): ascending indices inside a row, no stored zeros."""
+        lib = _lib.load()
+        nnz = C.c_int64()
+        check(lib.bigclam_get_F_nnz(self._need(), C.byref(nnz)), self._ctx)
+        indptr = np.empty(self.n + 1, dtype=np.int64)
+        indices = np.empty(max(nnz.value, 1), dtype=np.int32)
+        values = np.empty(max(nnz.value, 1), dtype=np.float64)
+        check(lib.bigclam_get_F_csr(self._ctx, indptr.ctypes.data, indices.ctypes.data, values.ctypes.data), self._ctx)
+        return indptr, indices[:nnz.value], values[:nnz.value]
+
     def set_F(self, F, sumF=None):
         """F <- n x K (the result of initNeighborComF); sumF <- column sums unless given."""
+        if hasattr(F, "tocsr"):                 # scipy.sparse matrix
+            m = F.tocsr()
+            return self.set_F_csr(m.indptr, m.indices, m.data, K=m.shape[1], sumF=sumF)
         F = np.ascontiguousarray(F, dtype=np.float64)
         if self._ctx is None or F.shape[1] != self.K:
             self.set_K(F.shape[1])

@@ -60,6 +60,38 @@ def synthetic_F0(n: int, k: int, seed: int = 1234, density: float = 0.05) -> np.
     return F
 
 
+def synthetic_F0_csr(n: int, k: int, seed: int = 1234, density: float = 0.05, chunk: int = 1 << 20):
+    """Same distribution as synthetic_F0 (each entry non-zero with probability `density`, values U[0,1)) as CSR
+    rows (indptr, indices, values), generated in row chunks so that n x k never has to exist densely
+    (R-MAT 10M x K=1000).  Not entry-for-entry the same matrix as synthetic_F0(seed)."""
+    rng = np.random.default_rng(seed)
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    idx_parts, val_parts = [], []
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        cnt = rng.binomial(k, density, size=m)
+        total = int(cnt.sum())
+        # distinct components per row: draw, then sort keys of (row, random) and take the first cnt of a permutation
+        row = np.repeat(np.arange(m, dtype=np.int64), cnt)
+        comp = np.empty(total, dtype=np.int32)
+        # rejection-free: for every row a random permutation prefix via argsort of random keys per chunk of rows
+        # would need m x k memory; instead draw with replacement and repair duplicates (rare at low density)
+        comp[:] = rng.integers(0, k, size=total)
+        key = row * k + comp
+        _, first = np.unique(key, return_index=True)
+        keep = np.zeros(total, dtype=bool)
+        keep[first] = True
+        row, comp = row[keep], comp[keep]
+        order = np.lexsort((comp, row))
+        row, comp = row[order], comp[order]
+        idx_parts.append(comp)
+        val_parts.append(rng.random(len(comp)))
+        indptr[lo + 1:lo + m + 1] = np.bincount(row, minlength=m)
+    np.cumsum(indptr, out=indptr)
+    return indptr, np.concatenate(idx_parts) if idx_parts else np.zeros(0, np.int32), \
+        np.concatenate(val_parts) if val_parts else np.zeros(0)
+
+
 def rmat_graph(scale_n: int, n_edges: int, a=0.57, b=0.19, c=0.19, seed: int = 42, permute: bool = True):
     """R-MAT (a,b,c,d) edge generator -> simple undirected CSR over n = scale_n nodes
     (n need not be a power of two: endpoints are drawn in the next power of two and rejected

@@ -54,6 +54,9 @@ typedef struct {
 
 #define BIGCLAM_F_TIME_KERNELS   1   /* record CUDA events around every step-kernel launch */
 #define BIGCLAM_F_RECORD_ACCEPTED 2  /* keep the accepted step index per node (diagnostics/tests) */
+#define BIGCLAM_F_SPARSE_ROWS     4  /* keep F as sparse rows on the device (like the reference's BSV[Double],
+                                        bigclam4-7.scala:97-104): k <= 256, min_f == 0, single GPU.  The C ABI stays
+                                        dense (bigclam_set_F / bigclam_get_F convert on the device). */
 
 /* Fills *p with the reference's constants for a given K. */
 int bigclam_default_params(bigclam_params *p, int32_t k);
@@ -155,6 +158,24 @@ int bigclam_rollback(bigclam_ctx *ctx);
 int bigclam_ipc_export(bigclam_ctx *ctx, void *handles_out);
 int bigclam_ipc_open_peers(bigclam_ctx *ctx, int32_t world, int32_t rank, const void *all_handles);
 int bigclam_mark_all_changed(bigclam_ctx *ctx);
+/*
+ * With BIGCLAM_F_SPARSE_ROWS the replicas are (header, pool) pairs: bigclam_ipc_handle_count() handles per rank
+ * (4 instead of 2) travel through bigclam_ipc_export / bigclam_ipc_open_peers, every rank allocates its owned
+ * rows inside its own part of the output pool (bigclam_set_pool_region: disjoint parts, 8-byte words) and the
+ * step kernel writes each owned row to the same offset of every replica — all owned rows, every step (the
+ * output pool is rebuilt per step, so there is no changed-row bookkeeping).
+ */
+int bigclam_ipc_handle_count(const bigclam_ctx *ctx);
+/*
+ * F as CSR rows, the shape of the reference's RDD[(Long, BSV[Double])] (bigclam4-7.scala:97-104): indptr[n + 1],
+ * indices (component of each entry, any order inside a row), values.  sumF becomes the column sums (:105-106).
+ * With BIGCLAM_F_SPARSE_ROWS no dense n x K image is ever built.  bigclam_get_F_nnz sizes the output of
+ * bigclam_get_F_csr (ascending indices inside a row, explicit zeros never stored).
+ */
+int bigclam_set_F_csr(bigclam_ctx *ctx, const int64_t *indptr, const int32_t *indices, const double *values);
+int bigclam_get_F_nnz(bigclam_ctx *ctx, int64_t *nnz_out);
+int bigclam_get_F_csr(bigclam_ctx *ctx, int64_t *indptr_out, int32_t *indices_out, double *values_out);
+int bigclam_set_pool_region(bigclam_ctx *ctx, int64_t base_words, int64_t cap_words);
 
 /*
  * Edge-list reader with GraphX semantics (GraphLoader.edgeListFile, bigclam4-7.scala:45;

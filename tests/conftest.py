@@ -9,6 +9,18 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 
+if os.environ.get("BIGCLAM_HOSTEMU") == "1":
+    # development aid (tests/emu/build_hostemu.sh): drive the HOST LOGIC of the C API with the `-m gpu` tests on a
+    # machine without a GPU — the ctypes binding is pointed at the host-emulation build for this pytest run only
+    import subprocess
+
+    if os.environ.get("BIGCLAM_HOSTEMU_NOBUILD") != "1":
+        subprocess.run([os.path.join(REPO, "tests", "emu", "build_hostemu.sh")], check=True)
+    from bigclam_apachespark_b200 import _lib as _L
+
+    _L.LIB_PATH = os.path.join(REPO, "tests", "emu", "libbigclam_hostemu.so")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

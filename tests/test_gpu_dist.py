@@ -27,13 +27,18 @@ def _worker(rank, world, port, exchange, out):
     rng = np.random.default_rng(5)
     F0 = rng.random((n, k)) * (rng.random((n, k)) < 0.2)
     sumF = O.colsum(F0)
-    b = BigClam(device=rank, record_accepted=True)
+    sparse = exchange == "p2p-sparse"          # sparse rows of F, pushed by the step kernel (regions of the pools)
+    if sparse:
+        exchange = "p2p"
+    b = BigClam(device=rank, record_accepted=True, sparse_rows=sparse)
     b.set_graph(rp, col).set_K(k)
     b.set_stream(torch.cuda.current_stream().cuda_stream)
     b.set_F(F0, sumF=sumF)
     bounds = partition_by_nnz(rp, world)
     nodes = deal_by_degree(rp, rank, world) if exchange == "p2p" else None
-    d = DistBigClam(CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1]), nodes=nodes), rp, rank, world, bounds, exchange=exchange)
+    counts = [len(range(r, n, world)) for r in range(world)]
+    d = DistBigClam(CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1]), nodes=nodes, owned_counts=counts, rank=rank),
+                    rp, rank, world, bounds, exchange=exchange)
     llhs = [d.backtrackingLineSearchs() for _ in range(3)]
     F3, s3 = b.F, b.sumF
     b.set_F(F0, sumF=sumF)
@@ -48,7 +53,7 @@ def _worker(rank, world, port, exchange, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "delta", "full"])
+@pytest.mark.parametrize("exchange", ["p2p", "delta", "full", "p2p-sparse"])
 def test_two_gpu_partitioned_equals_oracle(tmp_path, oracle, exchange):
     import torch
     import torch.multiprocessing as mp

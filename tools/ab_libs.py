@@ -24,10 +24,12 @@ print(f"oracle step: {time.time() - t0:.2f} s, llh {ref.llh:.12e}", flush=True)
 scale = np.abs(ref.F).max()
 
 for v in sys.argv[1:]:
+    sparse = v.endswith(":sparse")            # e.g. "product:sparse": the library's sparse-row mode
+    v = v.split(":")[0]
     _lib._lib = None
     _lib.LIB_PATH = os.path.join(ROOT, "tools", "ab", f"lib_{v}.so") if v != "product" else os.path.join(ROOT, "bigclam_apachespark_b200", "libbigclam_b200.so")
     try:
-        b = BigClam(device=0, time_kernels=True, record_accepted=True)
+        b = BigClam(device=0, time_kernels=True, record_accepted=True, sparse_rows=sparse)
         b.set_graph(rp, col).set_K(K).set_F(F0, sumF=sumF)
         llh = b.backtrackingLineSearchs()
         F = b.F
@@ -36,7 +38,7 @@ for v in sys.argv[1:]:
         par = (f"1-step: rows>1e-12 {int((row_err > 1e-12).sum())} max {row_err.max():.2e} "
                f"llh_rel {abs(llh - ref.llh) / abs(ref.llh):.1e} idx_diff {int((acc != ref.accepted).sum())}")
         b.close()
-        b = BigClam(device=0, time_kernels=True)
+        b = BigClam(device=0, time_kernels=True, sparse_rows=sparse)
         b.set_graph(rp, col).set_K(K).set_F(F0, sumF=sumF)
         b._run(4, 0.0, 10)
         res = []
@@ -44,7 +46,7 @@ for v in sys.argv[1:]:
             b._run(4, 0.0, 40)
             ms, nk, _ = b.kernel_time()
             res.append(ms / max(nk, 1))
-        print(f"== {v}: kernel {res[0]:.4f} / {res[1]:.4f} ms  llh@90 {b.last_trace[-1]:.12e}  {par}", flush=True)
+        print(f"== {v}{':sparse' if sparse else ''}: kernel {res[0]:.4f} / {res[1]:.4f} ms  llh@90 {b.last_trace[-1]:.12e}  {par}", flush=True)
         b.close()
     except Exception as e:  # noqa: BLE001
         print(f"== {v}: FAILED {e!r}", flush=True)

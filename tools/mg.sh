@@ -1,7 +1,7 @@
 #!/bin/bash
-# tools/mg.sh N [exchange] [steps]: run the N-GPU bench and print the key numbers
+# tools/mg.sh N [exchange] [steps] [layout]: run the N-GPU bench and print the key numbers (layout: dense | sparse)
 N=$1; EX=${2:-p2p}
-BIGCLAM_EXCHANGE=$EX python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps ${3:-50} --warmup 5 > /tmp/mg_$N.log 2>&1
+BIGCLAM_EXCHANGE=$EX python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps ${3:-50} --warmup 5 --layout ${4:-dense} > /tmp/mg_$N.log 2>&1
 python - <<PY
 import json
 line=[l for l in open('/tmp/mg_$N.log') if l.startswith('{"metric')]

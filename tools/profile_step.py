@@ -18,7 +18,7 @@ if name.startswith("rmat:"):          # rmat:<nodes>:<edges>
 else:
     rp, col, _ = G.load_npz_graph(name)
 n = len(rp) - 1
-b = BigClam(device=0, time_kernels=True)
+b = BigClam(device=0, time_kernels=True, sparse_rows=os.environ.get("BIGCLAM_AB_SPARSE") == "1")
 b.set_graph(rp, col).set_K(K).set_F(G.synthetic_F0(n, K, seed=1234, density=0.05))
 b._run(4, 0.0, W)
 b._run(4, 0.0, S)
