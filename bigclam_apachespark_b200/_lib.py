@@ -72,6 +72,7 @@ SIGNATURES = {
     "bigclam_run": (C.c_int, [_vp, _i32, _dbl, _i64, _pd, _pi64, _vp, _i64]),
     "bigclam_get_accepted": (C.c_int, [_vp, _vp]),
     "bigclam_get_kernel_time": (C.c_int, [_vp, _pd, _pi64, _pi64]),
+    "bigclam_get_tile_stats": (C.c_int, [_vp, _pi64, _pi64, _pi64, _pi64, _pi64]),
     "bigclam_set_stream": (C.c_int, [_vp, _vp]),
     "bigclam_device_state": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _pi64]),
     "bigclam_device_accepted": (C.c_int, [_vp, C.POINTER(_vp)]),
@@ -123,3 +124,9 @@ def check(rc: int, ctx=None):
     if rc != OK:
         msg = load().bigclam_last_error(ctx)
         raise BigclamError(rc, msg.decode() if msg else "unknown error")
+
+
+def sparse_node_words(ld: int) -> int:
+    """Worst-case 8-byte words one node can take in a sparse-row output pool: a full row block and a full delta
+    block (csrc/bigclam_sparse.cuh: sp_words(ld) each) — the unit bigclam_set_pool_region is sized in."""
+    return 2 * (((ld + 1) & ~1) + ((ld + 7) & ~7) // 4)

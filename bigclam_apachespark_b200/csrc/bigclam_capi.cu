@@ -3,6 +3,7 @@
 #include "../../include/bigclam_b200.h"
 #include "bigclam_kernels.cuh"
 #include "bigclam_sparse.cuh"
+#include "bigclam_tile.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -82,6 +83,30 @@ struct bigclam_ctx {
     uint64_t region_base8 = 0, region_cap8 = 0;   // this rank's part of every replica's output pool (multi-GPU)
     uint64_t *peer_hdr[2][7] = {{nullptr}};       // peers' headers / pools (both halves), IPC-mapped
     double *peer_pool[2][7] = {{nullptr}};
+    // per-node results of a launch and the fixed-order reduction behind it (bigclam_tile.cuh)
+    double *d_node_llh = nullptr;
+    unsigned short *d_dcnt = nullptr;
+    double *d_block_part = nullptr;
+    unsigned int *d_ticket = nullptr;
+    int red_grid = 0;
+    // tiles of small nodes (bigclam_tile.cuh) and the nodes of the general path in front of them
+    TileMeta *d_tiles = nullptr;
+    int32_t *d_tcol = nullptr;
+    int32_t ntiles = 0, n_gen = 0;
+    int32_t tile_edges = kTlMaxEdges;             // edge budget of a tile (0: no tiles), see retile()
+    unsigned int *d_stats = nullptr;              // [tiles on the tile path, tiles that fell back], BIGCLAM_F_TIME_KERNELS only
+    // fused collective of the node-partitioned path (reduce_kernel publishes, xreduce_kernel adds up): this rank's
+    // exchange buffer [2 halves][world][ld + 2] and flags [world], and every rank's (peer memory, incl. our own)
+    int x_world = 0, x_rank = 0;
+    unsigned long long x_seq = 0;                 // collectives issued so far (same count on every rank)
+    double *d_xbuf = nullptr;
+    unsigned long long *d_xflags = nullptr;
+    double *x_peer_buf[8] = {nullptr};
+    unsigned long long *x_peer_flags[8] = {nullptr};
+    bool x_ipc = false;                           // peers' buffers came through CUDA IPC (closed on destroy)
+    std::vector<int64_t> h_rowptr;                // host copy of the CSR row pointers (order / tile rebuilds)
+    std::vector<int32_t> h_col;
+    std::vector<int32_t> h_owned;                 // owned nodes (processing order is derived from it)
 
     std::string err;
 };
@@ -171,6 +196,15 @@ static void free_ctx(bigclam_ctx *c) {
     cudaFree(c->d_state); cudaFree(c->d_trace);
     cudaFree(c->d_hdr[0]); cudaFree(c->d_hdr[1]); cudaFree(c->d_pool[0]); cudaFree(c->d_pool[1]);
     cudaFree(c->d_pool_top); cudaFree(c->d_overflow);
+    cudaFree(c->d_node_llh); cudaFree(c->d_dcnt); cudaFree(c->d_block_part); cudaFree(c->d_ticket);
+    cudaFree(c->d_tiles); cudaFree(c->d_tcol); cudaFree(c->d_stats);
+    if (c->x_ipc)
+        for (int r = 0; r < c->x_world; ++r)
+            if (r != c->x_rank) {
+                if (c->x_peer_buf[r]) cudaIpcCloseMemHandle(c->x_peer_buf[r]);
+                if (c->x_peer_flags[r]) cudaIpcCloseMemHandle(c->x_peer_flags[r]);
+            }
+    cudaFree(c->d_xbuf); cudaFree(c->d_xflags);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -216,11 +250,103 @@ static void launch_step(int c2, const StepArgs &a, int grid, size_t smem, cudaSt
     }
 }
 
+// Sparse rows: hub items, the nodes of the general path and the tiles of small nodes (bigclam_tile.cuh) for the
+// processing order `meta` (degree descending).  Needs the host copy of col (ctx->h_col).
+static int rebuild_sparse_lists(bigclam_ctx *ctx, const std::vector<NodeMeta> &meta) {
+    const int64_t cnt = (int64_t)meta.size();
+    int64_t own_nnz = 0;
+    for (int64_t i = 0; i < cnt; ++i) own_nnz += meta[(size_t)i].deg;
+    // a hub is split into kSpHubSeg-edge segments over warps when one warp walking it would take a sizeable
+    // part of the launch: from a quarter of a warp's share of the owned entries upwards, at least 1024 edges
+    // (BIGCLAM_SPARSE_HUB_DEG overrides the threshold: tests)
+    int32_t nh = 0;
+    if (ctx->nsteps <= 16) {
+        const int64_t sp_per_warp = own_nnz / std::max<int64_t>(1, (int64_t)ctx->sp_grid * ctx->sp_wpb);
+        int64_t sp_hub_deg = std::max<int64_t>(1024, sp_per_warp / 4);
+        if (const char *ev = std::getenv("BIGCLAM_SPARSE_HUB_DEG")) sp_hub_deg = std::max<int64_t>(1, std::atoll(ev));
+        while (nh < cnt && meta[(size_t)nh].deg >= sp_hub_deg) ++nh;
+    }
+    ctx->n_hubs = nh;
+    {
+        std::vector<HubItem> i1, i2, i3;
+        int32_t slots = 0;
+        for (int32_t i = 0; i < nh; ++i) {
+            const int32_t deg = meta[(size_t)i].deg;
+            HubItem it{};
+            it.hub = i;
+            it.nslices = (deg + kSpHubSeg - 1) / kSpHubSeg;
+            it.mslot = slots;                           // first scratch slot of the hub: nslices + 1 slots
+            slots += it.nslices + 1;
+            for (int32_t sl = 0; sl < it.nslices; ++sl) {
+                it.slice = sl;
+                it.phase = 1; i1.push_back(it);
+                it.phase = 2; i2.push_back(it);
+            }
+            it.slice = 0;
+            it.phase = 3; i3.push_back(it);
+        }
+        std::vector<HubItem> items;
+        items.insert(items.end(), i1.begin(), i1.end());
+        items.insert(items.end(), i2.begin(), i2.end());
+        items.insert(items.end(), i3.begin(), i3.end());
+        cudaFree(ctx->d_hub_items); ctx->d_hub_items = nullptr;
+        cudaFree(ctx->d_hub_scratch); ctx->d_hub_scratch = nullptr;
+        cudaFree(ctx->d_hub_counters); ctx->d_hub_counters = nullptr;
+        ctx->n_hub_items = (int32_t)items.size();
+        ctx->n_mega = nh;
+        if (!items.empty()) {
+            CU(cudaMalloc(&ctx->d_hub_items, sizeof(HubItem) * items.size()));
+            CU(cudaMemcpy(ctx->d_hub_items, items.data(), sizeof(HubItem) * items.size(), cudaMemcpyHostToDevice));
+        }
+        CU(cudaMalloc(&ctx->d_hub_scratch, sizeof(double) * (size_t)std::max<int32_t>(1, slots) * sp_hub_stride(ctx->ld)));
+        CU(cudaMalloc(&ctx->d_hub_counters, sizeof(unsigned int) * (2 * (size_t)std::max<int32_t>(1, nh) + 1)));   // + the item counter
+        CU(cudaMemset(ctx->d_hub_counters, 0, sizeof(unsigned int) * (2 * (size_t)std::max<int32_t>(1, nh) + 1)));
+    }
+    // after the hubs: nodes above the tile budget go one per warp (general path), the rest in tiles of up to
+    // kTlMaxNodes consecutive nodes with at most tile_edges edges
+    const int32_t budget = (ctx->nsteps <= 16) ? ctx->tile_edges : 0;
+    int64_t pos = nh;
+    while (pos < cnt && (budget <= 0 || meta[(size_t)pos].deg > budget)) ++pos;
+    ctx->n_gen = (int32_t)(pos - nh);
+    std::vector<TileMeta> tiles;
+    std::vector<int32_t> tcol;
+    while (pos < cnt) {
+        TileMeta t{};
+        t.pos0 = (int32_t)pos;
+        t.ecol0 = (int32_t)tcol.size();
+        while (pos < cnt && t.nn < kTlMaxNodes && t.ne + meta[(size_t)pos].deg <= budget) {
+            const NodeMeta &m = meta[(size_t)pos];
+            for (int32_t e = 0; e < m.deg; ++e) tcol.push_back(ctx->h_col[(size_t)(m.e0 + e)] | (int32_t)((uint32_t)t.nn << 28));
+            t.ne += m.deg;
+            ++t.nn;
+            ++pos;
+        }
+        tiles.push_back(t);
+    }
+    ctx->ntiles = (int32_t)tiles.size();
+    cudaFree(ctx->d_tiles); ctx->d_tiles = nullptr;
+    cudaFree(ctx->d_tcol); ctx->d_tcol = nullptr;
+    if (!tiles.empty()) {
+        CU(cudaMalloc(&ctx->d_tiles, sizeof(TileMeta) * tiles.size()));
+        CU(cudaMemcpy(ctx->d_tiles, tiles.data(), sizeof(TileMeta) * tiles.size(), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&ctx->d_tcol, sizeof(int32_t) * std::max<size_t>(1, tcol.size())));
+        if (!tcol.empty()) CU(cudaMemcpy(ctx->d_tcol, tcol.data(), sizeof(int32_t) * tcol.size(), cudaMemcpyHostToDevice));
+    }
+    // the reduction walks the processing order with a fixed grid
+    ctx->red_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, (cnt + 255) / 256));
+    cudaFree(ctx->d_block_part); ctx->d_block_part = nullptr;
+    CU(cudaMalloc(&ctx->d_block_part, sizeof(double) * (size_t)ctx->red_grid * ((size_t)ctx->ld + 2)));
+    ctx->h_work_init = 0;                                  // every item of the sparse kernel is handed out dynamically
+    if (ctx->d_work != nullptr) CU(cudaMemcpy(ctx->d_work + 1, &ctx->h_work_init, sizeof(unsigned int), cudaMemcpyHostToDevice));
+    return BIGCLAM_OK;
+}
+
 static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowptr_host, std::vector<int32_t> &order) {
     // Processing order over the owned nodes: degree descending (hubs first so the tail of the
     // launch is made of cheap nodes), ties by id; packed as NodeMeta so one 16-byte load gives a
     // warp everything it needs to start a node.
     const int64_t cnt = (int64_t)order.size();
+    ctx->h_owned = order;
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
         return (rowptr_host[a + 1] - rowptr_host[a]) > (rowptr_host[b + 1] - rowptr_host[b]);
     });
@@ -234,6 +360,7 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
     if (ctx->d_meta == nullptr) CU(cudaMalloc(&ctx->d_meta, sizeof(NodeMeta) * std::max<size_t>(1, (size_t)ctx->n)));
     if (cnt > 0) CU(cudaMemcpy(ctx->d_meta, meta.data(), sizeof(NodeMeta) * (size_t)cnt, cudaMemcpyHostToDevice));
     ctx->order_n = cnt;
+    if (ctx->sparse) return rebuild_sparse_lists(ctx, meta);
     // hubs (block-cooperative phase): only the C2 <= 4 kernels have the staging buffers the phase uses
     int32_t nh = 0;
     // a node is worth sharing among a block's warps when its serial chain (~ its degree) is a sizeable
@@ -248,16 +375,7 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
     const int64_t max_deg = (cnt > 0) ? meta[0].deg : 0;
     const int64_t hub_deg = (4 * max_deg <= 3 * per_warp) ? INT64_MAX
                                                           : std::min<int64_t>(512, std::max<int64_t>(kHubDegree, per_warp / 5));
-    if (ctx->c2 <= 4 && !ctx->sparse) while (nh < cnt && meta[(size_t)nh].deg >= hub_deg) ++nh;
-    if (ctx->sparse && ctx->nsteps <= 16) {
-        // sparse rows: a hub is split into kSpHubSeg-edge segments over warps (bigclam_sparse.cuh) when one warp
-        // walking it would take a sizeable part of the launch: from a quarter of a warp's share of the owned
-        // entries upwards, at least 1024 edges (BIGCLAM_SPARSE_HUB_DEG overrides the threshold: tests)
-        const int64_t sp_per_warp = own_nnz / std::max<int64_t>(1, (int64_t)ctx->sp_grid * ctx->sp_wpb);
-        int64_t sp_hub_deg = std::max<int64_t>(1024, sp_per_warp / 4);
-        if (const char *ev = std::getenv("BIGCLAM_SPARSE_HUB_DEG")) sp_hub_deg = std::max<int64_t>(1, std::atoll(ev));
-        while (nh < cnt && meta[(size_t)nh].deg >= sp_hub_deg) ++nh;
-    }
+    if (ctx->c2 <= 4) while (nh < cnt && meta[(size_t)nh].deg >= hub_deg) ++nh;
     ctx->n_hubs = nh;
     // work items of the hub phase: hubs above kHubSlice edges are split into slices handled by different
     // blocks (phases 1-3), the others are done by one block (phase 0); see hub_phase
@@ -266,11 +384,10 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
         int32_t n_mega = 0;
         for (int32_t i = 0; i < nh; ++i) {
             const int32_t deg = meta[(size_t)i].deg;
-            const int32_t slice = ctx->sparse ? kSpHubSeg : kHubSlice;
-            const int32_t nsl = (deg + slice - 1) / slice;
+            const int32_t nsl = (deg + kHubSlice - 1) / kHubSlice;
             HubItem it{};
             it.hub = i;
-            if ((nsl > 1 || ctx->sparse) && ctx->nsteps <= 16) {
+            if (nsl > 1 && ctx->nsteps <= 16) {
                 it.mslot = n_mega++;
                 it.nslices = nsl;
                 for (int32_t sl = 0; sl < nsl; ++sl) {
@@ -301,11 +418,10 @@ static int rebuild_order_list(bigclam_ctx *ctx, const std::vector<int64_t> &rowp
         }
         const size_t slots = (size_t)std::max<int32_t>(1, n_mega);
         CU(cudaMalloc(&ctx->d_hub_scratch, sizeof(double) * slots * ((size_t)ctx->ld + 32)));
-        CU(cudaMalloc(&ctx->d_hub_counters, sizeof(unsigned int) * (2 * slots + 1)));      // + the sparse kernel's item counter
+        CU(cudaMalloc(&ctx->d_hub_counters, sizeof(unsigned int) * (2 * slots + 1)));
         CU(cudaMemset(ctx->d_hub_counters, 0, sizeof(unsigned int) * (2 * slots + 1)));
     }
-    const unsigned int init = ctx->sparse ? (unsigned int)nh + 3u * (unsigned int)ctx->sp_grid * (unsigned int)ctx->sp_wpb
-                                          : (unsigned int)nh + 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
+    const unsigned int init = (unsigned int)nh + 3u * (unsigned int)ctx->grid * kWarpsPerBlock;
     ctx->h_work_init = init;
     if (ctx->d_work != nullptr) CU(cudaMemcpy(ctx->d_work + 1, &init, sizeof(unsigned int), cudaMemcpyHostToDevice));
     return BIGCLAM_OK;
@@ -409,25 +525,33 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
             free_ctx(ctx);
             return BIGCLAM_EUNSUPPORTED;
         }
+        if (n >= ((int64_t)1 << 28)) {
+            fail(nullptr, BIGCLAM_EUNSUPPORTED, "bigclam_create: BIGCLAM_F_SPARSE_ROWS supports n < 2^28 nodes");
+            free_ctx(ctx);
+            return BIGCLAM_EUNSUPPORTED;
+        }
         ctx->sparse = true;
-        ctx->sp_wpb = sp_warps_per_block(ld);
-        ctx->sp_smem = sp_block_smem_bytes(ld, ctx->sp_wpb);
+        ctx->sp_wpb = tl_warps_per_block(ld);
+        ctx->sp_smem = tl_block_smem_bytes(ld, ctx->sp_wpb);
         int sbps = 0;
-        CUC(cudaFuncSetAttribute(sparse_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
-        CUC(cudaFuncSetAttribute(sparse_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
-        CUC(cudaFuncSetAttribute(sparse_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
-        CUC(cudaFuncSetAttribute(sparse_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(tile_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(tile_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(tile_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(tile_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
+        CUC(cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kRedWarps * (size_t)sp_ldp(ld))));
         int sb2 = 0;                         // the grid must be resident for every variant (hub items wait for each other)
-        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sbps, sparse_step_kernel<true, true>, 32 * ctx->sp_wpb, ctx->sp_smem));
-        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sb2, sparse_step_kernel<false, false>, 32 * ctx->sp_wpb, ctx->sp_smem));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sbps, tile_step_kernel<true, true>, 32 * ctx->sp_wpb, ctx->sp_smem));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sb2, tile_step_kernel<false, false>, 32 * ctx->sp_wpb, ctx->sp_smem));
         sbps = std::min(sbps, sb2);
         if (sbps <= 0) {
             fail(nullptr, BIGCLAM_ECUDA, "bigclam_create: sparse kernel does not fit an SM (smem %zu B)", ctx->sp_smem);
             free_ctx(ctx);
             return BIGCLAM_ECUDA;
         }
+        sbps = std::min(sbps, kTlBlocksPerSM);
         ctx->sp_grid = ctx->num_sms * sbps;
-        ctx->h_work_init = 3u * (unsigned int)ctx->sp_grid * (unsigned int)ctx->sp_wpb;
+        ctx->h_work_init = 0;
+        if (const char *ev = std::getenv("BIGCLAM_TILE_EDGES")) ctx->tile_edges = std::max(0, std::min(kTlMaxEdges, std::atoi(ev)));
     }
 
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -466,7 +590,7 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
         // worst case: every row full (ld entries) — a step can then never overflow its pool.  When two such
         // pools do not fit in 80 % of the free memory, each pool gets 40 % of it and a step that runs out reports
         // BIGCLAM_ENOMEM (its input is untouched).  BIGCLAM_SPARSE_POOL_WORDS overrides the size (tests).
-        ctx->pool_cap8 = (uint64_t)n * sp_words((uint32_t)ld);
+        ctx->pool_cap8 = (uint64_t)n * 2 * sp_words((uint32_t)ld);        // a full row and a full delta block per node
         {
             size_t free_b = 0, total_b = 0;
             CUC(cudaMemGetInfo(&free_b, &total_b));
@@ -484,10 +608,20 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
         CUC(cudaMemset(ctx->d_pool_top, 0, 2 * sizeof(unsigned long long)));
         CUC(cudaMalloc(&ctx->d_overflow, sizeof(int32_t)));
         CUC(cudaMemset(ctx->d_overflow, 0, sizeof(int32_t)));
+        CUC(cudaMalloc(&ctx->d_node_llh, sizeof(double) * (size_t)n));
+        CUC(cudaMemset(ctx->d_node_llh, 0, sizeof(double) * (size_t)n));
+        CUC(cudaMalloc(&ctx->d_dcnt, sizeof(unsigned short) * (size_t)n));
+        CUC(cudaMemset(ctx->d_dcnt, 0, sizeof(unsigned short) * (size_t)n));
+        CUC(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
+        CUC(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
+        CUC(cudaMalloc(&ctx->d_stats, 2 * sizeof(unsigned int)));
+        CUC(cudaMemset(ctx->d_stats, 0, 2 * sizeof(unsigned int)));
+        ctx->h_col.assign(col, col + nnz);
     }
 #undef CUC
+    ctx->h_rowptr.assign(rowptr, rowptr + n + 1);
     {
-        std::vector<int64_t> rp(rowptr, rowptr + n + 1);
+        const std::vector<int64_t> &rp = ctx->h_rowptr;
         int rc = rebuild_order(ctx, rp);
         if (rc != BIGCLAM_OK) { g_create_err = ctx->err; free_ctx(ctx); return rc; }
     }
@@ -576,6 +710,27 @@ static int check_overflow(bigclam_ctx *ctx) {
     return BIGCLAM_OK;
 }
 
+// Sparse rows: the edge budget of a tile follows the rows' average size (the rows of a tile are staged in
+// kTlStage16 16-byte chunks of shared memory); called when F is set.  BIGCLAM_TILE_EDGES pins it instead.
+static int retile(bigclam_ctx *ctx, uint64_t words_used) {
+    if (!ctx->sparse || std::getenv("BIGCLAM_TILE_EDGES") != nullptr) return BIGCLAM_OK;
+    std::vector<uint64_t> hdr((size_t)ctx->n);
+    CU(cudaMemcpy(hdr.data(), ctx->d_hdr[ctx->cur], sizeof(uint64_t) * (size_t)ctx->n, cudaMemcpyDeviceToHost));
+    const double nn = (double)std::max<int64_t>(1, ctx->n);
+    const double avg_cnt = std::max(1.0, (double)sp_host_nnz(ctx->n, hdr.data()) / nn);
+    const double avg16 = std::max(1.0, (double)words_used / 2.0 / nn);
+    // the rows of a tile (its edges' and its nodes' own) must fit the staging chunks, their entries the slots
+    // (worst case: no two of them on the same component), with 10 % to spare
+    const double rows = std::min((double)kTlStage16 / (1.1 * avg16), (double)kTlSlots / (1.1 * avg_cnt));
+    int budget = (int)rows - kTlMaxNodes;
+    budget = std::max(0, std::min(kTlMaxEdges, budget));
+    if (budget < 6) budget = 0;
+    if (budget == ctx->tile_edges) return BIGCLAM_OK;
+    ctx->tile_edges = budget;
+    std::vector<int32_t> order = ctx->h_owned;
+    return rebuild_order_list(ctx, ctx->h_rowptr, order);
+}
+
 extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     if (F == nullptr) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_F: F is NULL");
@@ -593,6 +748,9 @@ extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
         rc = sparse_from_dense(ctx);
         if (rc == BIGCLAM_OK) rc = check_overflow(ctx);        // a pool smaller than the rows: BIGCLAM_ENOMEM
         if (rc != BIGCLAM_OK) return rc;
+        unsigned long long used = 0;
+        CU(cudaMemcpy(&used, ctx->d_pool_top + ctx->cur, sizeof(used), cudaMemcpyDeviceToHost));
+        if (int rt = retile(ctx, used)) return rt;
     }
     // with peer replicas every row counts as changed again: the next step publishes all owned rows
     if (ctx->d_changed != nullptr) CU(cudaMemsetAsync(ctx->d_changed, 1, (size_t)ctx->n, ctx->stream));
@@ -639,6 +797,7 @@ extern "C" int bigclam_set_F_csr(bigclam_ctx *ctx, const int64_t *indptr, const 
     CU(cudaMemcpyAsync(ctx->d_sumF[b], colsum.data(), sizeof(double) * (size_t)ld, cudaMemcpyHostToDevice, ctx->stream));   // :105-106
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->dense_valid = false;
+    if (int rt = retile(ctx, (uint64_t)used)) return rt;
     return BIGCLAM_OK;
 }
 
@@ -803,7 +962,8 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
         CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
     }
     if (ctx->n_mega > 0) {     // mega-hub scratch, slice counters (and the sparse kernel's item counter) start every launch at zero
-        CU(cudaMemsetAsync(ctx->d_hub_scratch, 0, sizeof(double) * (size_t)ctx->n_mega * ((size_t)ctx->ld + 32), ctx->stream));
+        if (!ctx->sparse)      // (the sparse kernel writes every scratch slot before it is read)
+            CU(cudaMemsetAsync(ctx->d_hub_scratch, 0, sizeof(double) * (size_t)ctx->n_mega * ((size_t)ctx->ld + 32), ctx->stream));
         CU(cudaMemsetAsync(ctx->d_hub_counters, 0, sizeof(unsigned int) * (2 * (size_t)ctx->n_mega + 1), ctx->stream));
     }
     // positions 0 .. 3*#warps-1 are pre-assigned statically, the rest is handed out dynamically
@@ -811,7 +971,7 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
     if (ctx->sparse) {
         // reads hdr/pool of the current buffer, writes the other one (its bump allocator starts at zero)
         const int in = ctx->cur, out = in ^ 1;
-        SparseArgs sp;
+        SparseArgs sp{};
         sp.hdr_in = ctx->d_hdr[in];
         sp.pool_in = ctx->d_pool[in];
         sp.hdr_out = ctx->d_hdr[out];
@@ -830,11 +990,56 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
             ctx->dense_valid = false;
         }
         sp.hub_work = ctx->d_hub_counters + 2 * (size_t)std::max<int32_t>(1, ctx->n_mega);
+        sp.node_llh = ctx->d_node_llh;
+        sp.dcnt = ctx->d_dcnt;
+        sp.accepted = (a.accepted != nullptr) ? a.accepted : ctx->d_accepted;
+        sp.n_gen = ctx->n_gen;
+        sp.ntiles = ctx->ntiles;
+        sp.tiles = ctx->d_tiles;
+        sp.tcol = ctx->d_tcol;
+        sp.stats = (ctx->p.flags & BIGCLAM_F_TIME_KERNELS) ? ctx->d_stats : nullptr;
         const bool hub = a.n_hub_items > 0, push = sp.n_peers > 0;
-        if (hub && push) sparse_step_kernel<true, true><<<ctx->sp_grid, 32 * ctx->sp_wpb, ctx->sp_smem, ctx->stream>>>(a, sp);
-        else if (hub) sparse_step_kernel<false, true><<<ctx->sp_grid, 32 * ctx->sp_wpb, ctx->sp_smem, ctx->stream>>>(a, sp);
-        else if (push) sparse_step_kernel<true, false><<<ctx->sp_grid, 32 * ctx->sp_wpb, ctx->sp_smem, ctx->stream>>>(a, sp);
-        else sparse_step_kernel<false, false><<<ctx->sp_grid, 32 * ctx->sp_wpb, ctx->sp_smem, ctx->stream>>>(a, sp);
+        const int threads = 32 * ctx->sp_wpb;
+        if (hub && push) tile_step_kernel<true, true><<<ctx->sp_grid, threads, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else if (hub) tile_step_kernel<false, true><<<ctx->sp_grid, threads, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else if (push) tile_step_kernel<true, false><<<ctx->sp_grid, threads, ctx->sp_smem, ctx->stream>>>(a, sp);
+        else tile_step_kernel<false, false><<<ctx->sp_grid, threads, ctx->sp_smem, ctx->stream>>>(a, sp);
+        CU(cudaGetLastError());
+        if (timing) {
+            CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
+            ctx->ev_used += 2;
+        }
+        // the sums over the nodes, in a fixed order (no floating-point atomics): partials = [D | - | llh | n_updated]
+        ReduceArgs r{};
+        r.world = 0;
+        if (ctx->x_world > 1) {              // publish this rank's sums to every rank (fused collective)
+            const unsigned long long seq = ++ctx->x_seq;
+            const size_t half = (size_t)(seq & 1ull) * (size_t)ctx->x_world * ((size_t)ctx->ld + 2);
+            r.world = ctx->x_world;
+            r.seq = seq;
+            for (int q = 0; q < ctx->x_world; ++q) {
+                r.xslot[q] = ctx->x_peer_buf[q] + half + (size_t)ctx->x_rank * ((size_t)ctx->ld + 2);
+                r.xflag[q] = ctx->x_peer_flags[q] + ctx->x_rank;
+            }
+        }
+        r.meta = ctx->d_meta;
+        r.order_n = ctx->order_n;
+        r.hdr_out = sp.hdr_out;
+        r.pool_out = sp.pool_out;
+        r.node_llh = ctx->d_node_llh;
+        r.dcnt = ctx->d_dcnt;
+        r.accepted = sp.accepted;
+        r.ld = ctx->ld;
+        r.do_linesearch = a.do_linesearch;
+        r.block_part = ctx->d_block_part;
+        r.ticket = ctx->d_ticket;
+        r.partials = ctx->d_partials;
+        r.done_flag = a.done_flag;
+        reduce_kernel<<<ctx->red_grid, kRedWarps * 32, sizeof(double) * kRedWarps * (size_t)sp_ldp(ctx->ld), ctx->stream>>>(r);
+        CU(cudaGetLastError());
+        if (is_step) ++ctx->last_step_launches;
+        ctx->last_all_launches += 2;
+        return BIGCLAM_OK;
     } else {
         launch_step(ctx->c2, a, ctx->grid, ctx->smem_bytes, ctx->stream);
     }
@@ -857,6 +1062,24 @@ static int collect_timing(bigclam_ctx *ctx) {
         ctx->last_step_ms += ms;
     }
     ctx->ev_used = 0;
+    return BIGCLAM_OK;
+}
+
+// Node-partitioned launches: every rank's sums of the most recent reduce_kernel -> partials (all ranks: same bits).
+static int launch_xreduce(bigclam_ctx *ctx, bool use_done) {
+    if (ctx->x_world <= 1) return BIGCLAM_OK;
+    XReduceArgs x{};
+    const unsigned long long seq = ctx->x_seq;
+    x.xbuf = ctx->d_xbuf + (size_t)(seq & 1ull) * (size_t)ctx->x_world * ((size_t)ctx->ld + 2);
+    x.flags = ctx->d_xflags;
+    x.seq = seq;
+    x.world = ctx->x_world;
+    x.ld = ctx->ld;
+    x.partials = ctx->d_partials;
+    x.done_flag = use_done ? ctx->d_done : nullptr;
+    xreduce_kernel<<<1, 256, 0, ctx->stream>>>(x);
+    CU(cudaGetLastError());
+    ++ctx->last_all_launches;
     return BIGCLAM_OK;
 }
 
@@ -1046,14 +1269,31 @@ extern "C" int bigclam_get_kernel_time(bigclam_ctx *ctx, double *step_kernel_ms_
     return BIGCLAM_OK;
 }
 
+extern "C" int bigclam_get_tile_stats(bigclam_ctx *ctx, int64_t *tiles_done, int64_t *tiles_fallback, int64_t *n_tiles,
+                                      int64_t *n_general_nodes, int64_t *n_split_hubs) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    unsigned int st[2] = {0u, 0u};
+    if (ctx->sparse && ctx->d_stats != nullptr) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpy(st, ctx->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+        CU(cudaMemset(ctx->d_stats, 0, sizeof(st)));
+    }
+    if (tiles_done) *tiles_done = st[0];
+    if (tiles_fallback) *tiles_fallback = st[1];
+    if (n_tiles) *n_tiles = ctx->sparse ? ctx->ntiles : 0;
+    if (n_general_nodes) *n_general_nodes = ctx->sparse ? ctx->n_gen : 0;
+    if (n_split_hubs) *n_split_hubs = ctx->sparse ? ctx->n_hubs : 0;
+    return BIGCLAM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Node-partitioned pieces.
 extern "C" int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     if (lo < 0 || hi < lo || hi > ctx->n) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_owned_range: bad range");
     CU(cudaSetDevice(ctx->device));
-    std::vector<int64_t> rp((size_t)ctx->n + 1);
-    CU(cudaMemcpy(rp.data(), ctx->d_rowptr, sizeof(int64_t) * rp.size(), cudaMemcpyDeviceToHost));
+    const std::vector<int64_t> &rp = ctx->h_rowptr;
     ctx->lo = lo;
     ctx->hi = hi;
     if (int rd = drop_speculation(ctx)) return rd;
@@ -1076,6 +1316,7 @@ extern "C" int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
     const bool want = (llh_pre_out != nullptr) || (n_updated_out != nullptr);
+    if (int rx = launch_xreduce(ctx, false)) return rx;      // (with the fused collective: every rank's sums first)
     if (want)
         CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials + 2 * ctx->ld, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     int rc = launch_finish(ctx, 0, 0, 0.0, true, false);
@@ -1225,8 +1466,7 @@ extern "C" int bigclam_set_owned_nodes(bigclam_ctx *ctx, const int32_t *nodes, i
     for (int64_t i = 0; i < count; ++i)
         if (nodes[i] < 0 || nodes[i] >= ctx->n) return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_owned_nodes: node out of range");
     CU(cudaSetDevice(ctx->device));
-    std::vector<int64_t> rp((size_t)ctx->n + 1);
-    CU(cudaMemcpy(rp.data(), ctx->d_rowptr, sizeof(int64_t) * rp.size(), cudaMemcpyDeviceToHost));
+    const std::vector<int64_t> &rp = ctx->h_rowptr;
     std::vector<int32_t> order(nodes, nodes + count);
     ctx->lo = 0;
     ctx->hi = ctx->n;
@@ -1258,3 +1498,376 @@ extern "C" int bigclam_extract(bigclam_ctx *ctx, double delta, uint8_t *member_o
     if (e != cudaSuccess) return fail(ctx, BIGCLAM_ECUDA, "bigclam_extract: %s", cudaGetErrorString(e));
     return BIGCLAM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Fused collective of the node-partitioned path: exchange buffers (see bigclam_ctx::x_*).
+static int xchg_alloc(bigclam_ctx *ctx, int32_t world, int32_t rank) {
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(ctx, BIGCLAM_EINVAL, "exchange buffers: bad world/rank (at most 8 GPUs)");
+    if (!ctx->sparse) return fail(ctx, BIGCLAM_EUNSUPPORTED, "the fused collective needs BIGCLAM_F_SPARSE_ROWS");
+    CU(cudaSetDevice(ctx->device));
+    cudaFree(ctx->d_xbuf); ctx->d_xbuf = nullptr;
+    cudaFree(ctx->d_xflags); ctx->d_xflags = nullptr;
+    const size_t nb = sizeof(double) * 2 * (size_t)world * ((size_t)ctx->ld + 2);
+    CU(cudaMalloc(&ctx->d_xbuf, nb));
+    CU(cudaMemset(ctx->d_xbuf, 0, nb));
+    CU(cudaMalloc(&ctx->d_xflags, sizeof(unsigned long long) * 8));
+    CU(cudaMemset(ctx->d_xflags, 0, sizeof(unsigned long long) * 8));
+    ctx->x_world = world;
+    ctx->x_rank = rank;
+    ctx->x_seq = 0;
+    for (int r = 0; r < 8; ++r) { ctx->x_peer_buf[r] = nullptr; ctx->x_peer_flags[r] = nullptr; }
+    ctx->x_peer_buf[rank] = ctx->d_xbuf;
+    ctx->x_peer_flags[rank] = ctx->d_xflags;
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_xchg_export(bigclam_ctx *ctx, int32_t world, int32_t rank, void *handles_out /* 2 x 64 bytes */) {
+    if (ctx == nullptr || handles_out == nullptr) return BIGCLAM_EINVAL;
+    if (int rc = xchg_alloc(ctx, world, rank)) return rc;
+    cudaIpcMemHandle_t h[2];
+    CU(cudaIpcGetMemHandle(&h[0], ctx->d_xbuf));
+    CU(cudaIpcGetMemHandle(&h[1], ctx->d_xflags));
+    std::memcpy(handles_out, h, sizeof(h));
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_xchg_open_peers(bigclam_ctx *ctx, const void *all_handles /* world x 2 x 64 bytes, rank order */) {
+    if (ctx == nullptr || all_handles == nullptr) return BIGCLAM_EINVAL;
+    if (ctx->x_world < 1) return fail(ctx, BIGCLAM_EINVAL, "bigclam_xchg_open_peers: call bigclam_xchg_export first");
+    CU(cudaSetDevice(ctx->device));
+    const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles);
+    for (int r = 0; r < ctx->x_world; ++r) {
+        if (r == ctx->x_rank) continue;
+        void *p = nullptr, *q = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h[2 * r], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&q, h[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+        ctx->x_peer_buf[r] = reinterpret_cast<double *>(p);
+        ctx->x_peer_flags[r] = reinterpret_cast<unsigned long long *>(q);
+    }
+    ctx->x_ipc = true;
+    return BIGCLAM_OK;
+}
+
+// After bigclam_llh_local: the all-rank sum of the PRE block's llh_u (fused collective), synchronous.
+extern "C" int bigclam_llh_finish_local(bigclam_ctx *ctx, double *llh_out) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    if (int rx = launch_xreduce(ctx, false)) return rx;
+    CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials + 2 * ctx->ld, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (llh_out) *llh_out = ctx->h_pinned[0];
+    return BIGCLAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// All the GPUs of one box behind ONE handle, for a single-threaded caller (the JVM driver of INTEGRATION.md): one
+// context per device, nodes dealt over the ranks by degree, every rank's new rows stored into all replicas by the
+// step kernel (peer memory over NVLink), the sums combined by the fused collective above.  No NCCL, no Python.
+struct bigclam_multi {
+    int world = 0;
+    std::vector<bigclam_ctx *> r;
+    int64_t n = 0;
+    int32_t k = 0, ld = 0;
+    std::string err;
+};
+static thread_local std::string g_multi_err;
+
+static int mfail(bigclam_multi *m, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (m != nullptr) m->err = buf; else g_multi_err = buf;
+    return code;
+}
+static int mfail_from(bigclam_multi *m, int code, bigclam_ctx *c) { return mfail(m, code, "%s", bigclam_last_error(c)); }
+
+extern "C" const char *bigclam_multi_last_error(const bigclam_multi *m) { return m != nullptr ? m->err.c_str() : g_multi_err.c_str(); }
+
+extern "C" void bigclam_multi_destroy(bigclam_multi *m) {
+    if (m == nullptr) return;
+    for (bigclam_ctx *c : m->r) {
+        if (c == nullptr) continue;
+        for (int h = 0; h < 2; ++h)
+            for (int q = 0; q < 7; ++q) { c->peer_hdr[h][q] = nullptr; c->peer_pool[h][q] = nullptr; }   // direct pointers, not IPC mappings
+        c->n_peers = 0;
+        free_ctx(c);
+    }
+    delete m;
+}
+
+extern "C" int bigclam_multi_create(bigclam_multi **out, int64_t n, const int64_t *rowptr, const int32_t *col,
+                                    const bigclam_params *params, int32_t world, const int32_t *devices) {
+    if (out == nullptr) return mfail(nullptr, BIGCLAM_EINVAL, "bigclam_multi_create: out is NULL");
+    *out = nullptr;
+    if (params == nullptr || world < 1 || world > 8) return mfail(nullptr, BIGCLAM_EINVAL, "bigclam_multi_create: world must be 1..8");
+    bigclam_multi *m = new (std::nothrow) bigclam_multi();
+    if (m == nullptr) return mfail(nullptr, BIGCLAM_ENOMEM, "bigclam_multi_create: out of host memory");
+    m->world = world;
+    m->n = n;
+    m->k = params->k;
+    m->ld = (params->k + 3) & ~3;
+    m->r.assign((size_t)world, nullptr);
+#define MFAIL(code, ...)                             \
+    do {                                             \
+        mfail(nullptr, code, __VA_ARGS__);           \
+        bigclam_multi_destroy(m);                    \
+        return code;                                 \
+    } while (0)
+    for (int i = 0; i < world; ++i) {
+        bigclam_params p = *params;
+        p.device = devices != nullptr ? devices[i] : i;
+        p.flags |= BIGCLAM_F_SPARSE_ROWS;
+        int rc = bigclam_create(&m->r[(size_t)i], n, rowptr, col, &p);
+        if (rc != BIGCLAM_OK) MFAIL(rc, "bigclam_multi_create: device %d: %s", p.device, bigclam_last_error(nullptr));
+    }
+    if (world > 1) {
+        // peer access both ways (already enabled is fine)
+        for (int i = 0; i < world; ++i)
+            for (int j = 0; j < world; ++j) {
+                if (i == j || m->r[(size_t)i]->device == m->r[(size_t)j]->device) continue;
+                if (cudaSetDevice(m->r[(size_t)i]->device) != cudaSuccess) MFAIL(BIGCLAM_ECUDA, "bigclam_multi_create: cudaSetDevice failed");
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, m->r[(size_t)i]->device, m->r[(size_t)j]->device);
+                if (!can) MFAIL(BIGCLAM_EUNSUPPORTED, "bigclam_multi_create: device %d cannot access device %d", m->r[(size_t)i]->device, m->r[(size_t)j]->device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(m->r[(size_t)j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) MFAIL(BIGCLAM_ECUDA, "bigclam_multi_create: cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+                (void)cudaGetLastError();
+            }
+        // owned nodes: the degree-sorted node list dealt round-robin; pool regions in proportion to the owned counts
+        std::vector<int32_t> order((size_t)n);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return (rowptr[a + 1] - rowptr[a]) > (rowptr[b + 1] - rowptr[b]); });
+        uint64_t cap = m->r[0]->pool_cap8;
+        for (int i = 1; i < world; ++i) cap = std::min(cap, m->r[(size_t)i]->pool_cap8);
+        uint64_t base = 0;
+        for (int i = 0; i < world; ++i) {
+            bigclam_ctx *c = m->r[(size_t)i];
+            std::vector<int32_t> mine;
+            for (int64_t q = i; q < n; q += world) mine.push_back(order[(size_t)q]);
+            int rc = bigclam_set_owned_nodes(c, mine.data(), (int64_t)mine.size());
+            if (rc != BIGCLAM_OK) MFAIL(rc, "bigclam_multi_create: %s", bigclam_last_error(c));
+            uint64_t share = (uint64_t)((double)cap * (double)mine.size() / (double)n) & ~(uint64_t)1;
+            if (i == world - 1) share = (cap - base) & ~(uint64_t)1;
+            rc = bigclam_set_pool_region(c, (int64_t)base, (int64_t)share);
+            if (rc != BIGCLAM_OK) MFAIL(rc, "bigclam_multi_create: %s", bigclam_last_error(c));
+            base += share;
+            rc = xchg_alloc(c, world, i);
+            if (rc != BIGCLAM_OK) MFAIL(rc, "bigclam_multi_create: %s", bigclam_last_error(c));
+        }
+        for (int i = 0; i < world; ++i) {
+            bigclam_ctx *c = m->r[(size_t)i];
+            int np = 0;
+            for (int j = 0; j < world; ++j) {
+                bigclam_ctx *o = m->r[(size_t)j];
+                c->x_peer_buf[j] = o->d_xbuf;
+                c->x_peer_flags[j] = o->d_xflags;
+                if (j == i) continue;
+                for (int h = 0; h < 2; ++h) { c->peer_hdr[h][np] = o->d_hdr[h]; c->peer_pool[h][np] = o->d_pool[h]; }
+                ++np;
+            }
+            c->n_peers = np;
+        }
+    }
+#undef MFAIL
+    *out = m;
+    return BIGCLAM_OK;
+}
+
+#define MCALL(expr, c)                                           \
+    do {                                                         \
+        int rc__ = (expr);                                       \
+        if (rc__ != BIGCLAM_OK) return mfail_from(m, rc__, c);   \
+    } while (0)
+
+extern "C" int bigclam_multi_set_F(bigclam_multi *m, const double *F) {
+    if (m == nullptr) return BIGCLAM_EINVAL;
+    for (bigclam_ctx *c : m->r) MCALL(bigclam_set_F(c, F), c);
+    return BIGCLAM_OK;
+}
+extern "C" int bigclam_multi_set_F_csr(bigclam_multi *m, const int64_t *indptr, const int32_t *indices, const double *values) {
+    if (m == nullptr) return BIGCLAM_EINVAL;
+    for (bigclam_ctx *c : m->r) MCALL(bigclam_set_F_csr(c, indptr, indices, values), c);
+    return BIGCLAM_OK;
+}
+extern "C" int bigclam_multi_set_sumF(bigclam_multi *m, const double *sumF) {
+    if (m == nullptr) return BIGCLAM_EINVAL;
+    for (bigclam_ctx *c : m->r) MCALL(bigclam_set_sumF(c, sumF), c);
+    return BIGCLAM_OK;
+}
+extern "C" int bigclam_multi_get_F(bigclam_multi *m, int32_t rank, double *F_out) {
+    if (m == nullptr || rank < 0 || rank >= m->world) return BIGCLAM_EINVAL;
+    MCALL(bigclam_get_F(m->r[(size_t)rank], F_out), m->r[(size_t)rank]);
+    return BIGCLAM_OK;
+}
+extern "C" int bigclam_multi_get_sumF(bigclam_multi *m, int32_t rank, double *sumF_out) {
+    if (m == nullptr || rank < 0 || rank >= m->world) return BIGCLAM_EINVAL;
+    MCALL(bigclam_get_sumF(m->r[(size_t)rank], sumF_out), m->r[(size_t)rank]);
+    return BIGCLAM_OK;
+}
+extern "C" int bigclam_multi_get_F_nnz(bigclam_multi *m, int64_t *nnz_out) {
+    if (m == nullptr) return BIGCLAM_EINVAL;
+    MCALL(bigclam_get_F_nnz(m->r[0], nnz_out), m->r[0]);
+    return BIGCLAM_OK;
+}
+extern "C" int bigclam_multi_get_F_csr(bigclam_multi *m, int64_t *indptr_out, int32_t *indices_out, double *values_out) {
+    if (m == nullptr) return BIGCLAM_EINVAL;
+    MCALL(bigclam_get_F_csr(m->r[0], indptr_out, indices_out, values_out), m->r[0]);
+    return BIGCLAM_OK;
+}
+
+// One kernel round over all ranks: every rank's step (or PRE-only) kernel and reduction first, then every rank's
+// combine + finish — a rank's combine waits on device flags for the other ranks' reductions, so nothing of the
+// second half may be queued in front of another rank's first half.
+static int multi_round(bigclam_multi *m, bool linesearch, const uint8_t *host_mask, bool use_done, long long kernel_index,
+                       int variant, double rel_tol, bool apply, bool llh_is_final) {
+    for (bigclam_ctx *c : m->r) {
+        if (cudaSetDevice(c->device) != cudaSuccess) return mfail(m, BIGCLAM_ECUDA, "cudaSetDevice(%d) failed", c->device);
+        const uint8_t *d_mask = nullptr;
+        if (host_mask != nullptr) {
+            if (cudaMemcpyAsync(c->d_mask, host_mask, (size_t)c->n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+                return mfail(m, BIGCLAM_ECUDA, "uset upload failed");
+            d_mask = c->d_mask;
+        }
+        StepArgs a;
+        fill_args(c, a, linesearch, d_mask, use_done);
+        MCALL(timed_launch(c, a, linesearch), c);
+    }
+    for (bigclam_ctx *c : m->r) {
+        if (cudaSetDevice(c->device) != cudaSuccess) return mfail(m, BIGCLAM_ECUDA, "cudaSetDevice(%d) failed", c->device);
+        MCALL(launch_xreduce(c, use_done), c);
+        MCALL(launch_finish(c, kernel_index, variant, rel_tol, apply, llh_is_final), c);
+    }
+    return BIGCLAM_OK;
+}
+
+static int multi_sync(bigclam_multi *m) {
+    for (bigclam_ctx *c : m->r) {
+        if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
+            return mfail(m, BIGCLAM_ECUDA, "device %d: %s", c->device, cudaGetErrorString(cudaGetLastError()));
+        if (int ro = check_overflow(c)) return mfail_from(m, ro, c);
+    }
+    return BIGCLAM_OK;
+}
+
+// PRE-only round; the all-rank LLH lands in every rank's partials (finish with apply = 0 leaves the state alone)
+static int multi_llh(bigclam_multi *m, double *llh_out) {
+    for (bigclam_ctx *c : m->r) {
+        if (cudaSetDevice(c->device) != cudaSuccess) return mfail(m, BIGCLAM_ECUDA, "cudaSetDevice(%d) failed", c->device);
+        StepArgs a;
+        fill_args(c, a, false, nullptr, false);
+        MCALL(timed_launch(c, a, false), c);
+    }
+    for (bigclam_ctx *c : m->r) {
+        if (cudaSetDevice(c->device) != cudaSuccess) return mfail(m, BIGCLAM_ECUDA, "cudaSetDevice(%d) failed", c->device);
+        MCALL(launch_xreduce(c, false), c);
+    }
+    bigclam_ctx *c0 = m->r[0];
+    if (cudaSetDevice(c0->device) != cudaSuccess) return mfail(m, BIGCLAM_ECUDA, "cudaSetDevice failed");
+    if (cudaMemcpyAsync(c0->h_pinned, c0->d_partials + 2 * c0->ld, sizeof(double), cudaMemcpyDeviceToHost, c0->stream) != cudaSuccess)
+        return mfail(m, BIGCLAM_ECUDA, "LLH download failed");
+    if (int rs = multi_sync(m)) return rs;
+    if (llh_out) *llh_out = c0->h_pinned[0];
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_multi_loglikelihood(bigclam_multi *m, double *llh_out) {
+    if (m == nullptr) return BIGCLAM_EINVAL;
+    for (bigclam_ctx *c : m->r) { if (cudaSetDevice(c->device) == cudaSuccess) { int rc = reset_run_state(c); if (rc) return mfail_from(m, rc, c); } }
+    return multi_llh(m, llh_out);
+}
+
+// backtrackingLineSearchs(uset) over all GPUs: one step round, then a PRE-only round for the LLH it returns.
+extern "C" int bigclam_multi_step(bigclam_multi *m, const uint8_t *node_mask, double *llh_out, int64_t *n_updated_out) {
+    if (m == nullptr) return BIGCLAM_EINVAL;
+    for (bigclam_ctx *c : m->r) { if (cudaSetDevice(c->device) == cudaSuccess) { int rc = reset_run_state(c); if (rc) return mfail_from(m, rc, c); } }
+    if (int rr = multi_round(m, true, node_mask, false, 0, 0, 0.0, true, false)) return rr;
+    for (bigclam_ctx *c : m->r) { c->cur ^= 1; c->dense_valid = false; }
+    bigclam_ctx *c0 = m->r[0];
+    cudaSetDevice(c0->device);
+    if (cudaMemcpyAsync(c0->h_pinned + 8, c0->d_state, sizeof(RunState), cudaMemcpyDeviceToHost, c0->stream) != cudaSuccess)
+        return mfail(m, BIGCLAM_ECUDA, "state download failed");
+    double llh = 0.0;
+    if (int rl = multi_llh(m, &llh)) return rl;
+    if (llh_out) *llh_out = llh;
+    if (n_updated_out) *n_updated_out = reinterpret_cast<RunState *>(c0->h_pinned + 8)->n_updated;
+    for (bigclam_ctx *c : m->r) { cudaSetDevice(c->device); collect_timing(c); }
+    return BIGCLAM_OK;
+}
+
+// The outer loop (bigclam_run) over all GPUs: same device-side bookkeeping on every rank (they all see the same sums).
+extern "C" int bigclam_multi_run(bigclam_multi *m, int32_t variant, double rel_tol, int64_t max_outer, double *llh_out,
+                                 int64_t *calls_out, double *llh_trace, int64_t trace_cap) {
+    if (m == nullptr) return BIGCLAM_EINVAL;
+    if (variant != 2 && variant != 3 && variant != 4) return mfail(m, BIGCLAM_EINVAL, "bigclam_multi_run: variant must be 2, 3 or 4");
+    if (max_outer < 0 || trace_cap < 0) return mfail(m, BIGCLAM_EINVAL, "bigclam_multi_run: negative max_outer/trace_cap");
+    bigclam_ctx *c0 = m->r[0];
+    for (bigclam_ctx *c : m->r) {
+        if (cudaSetDevice(c->device) != cudaSuccess) return mfail(m, BIGCLAM_ECUDA, "cudaSetDevice failed");
+        int rc = reset_run_state(c);
+        if (rc) return mfail_from(m, rc, c);
+        c->trace_cap = 0;
+    }
+    cudaSetDevice(c0->device);
+    if (llh_trace != nullptr && trace_cap > 0) {
+        cudaFree(c0->d_trace);
+        c0->d_trace = nullptr;
+        if (cudaMalloc(&c0->d_trace, sizeof(double) * (size_t)trace_cap) != cudaSuccess) return mfail(m, BIGCLAM_ENOMEM, "trace buffer");
+        c0->trace_cap = trace_cap;
+    }
+    RunState *hst = reinterpret_cast<RunState *>(c0->h_pinned + 8);
+    const int start_cur = c0->cur;
+    const int64_t batch = 8;
+    int64_t cdone = 0;
+    bool done = false;
+    while (!done) {
+        int64_t todo = batch;
+        if (max_outer > 0) todo = std::min<int64_t>(batch, max_outer - cdone);
+        for (int64_t i = 0; i < todo; ++i) {
+            ++cdone;
+            for (bigclam_ctx *c : m->r) c->cur = (start_cur + (int)((cdone - 1) & 1)) & 1;
+            if (int rr = multi_round(m, true, nullptr, true, cdone, variant, rel_tol, true, false)) return rr;
+        }
+        cudaSetDevice(c0->device);
+        if (cudaMemcpyAsync(hst, c0->d_state, sizeof(RunState), cudaMemcpyDeviceToHost, c0->stream) != cudaSuccess) return mfail(m, BIGCLAM_ECUDA, "state download failed");
+        if (int rs = multi_sync(m)) return rs;
+        if (hst->done) { done = true; break; }
+        if (max_outer > 0 && cdone >= max_outer) break;
+    }
+    int64_t calls;
+    if (done) {
+        calls = hst->conv_call;
+    } else {
+        calls = cdone;
+        for (bigclam_ctx *c : m->r) c->cur = (start_cur + (int)(cdone & 1)) & 1;
+        if (int rr = multi_round(m, false, nullptr, false, cdone, variant, rel_tol, false, true)) return rr;
+        cudaSetDevice(c0->device);
+        if (cudaMemcpyAsync(hst, c0->d_state, sizeof(RunState), cudaMemcpyDeviceToHost, c0->stream) != cudaSuccess) return mfail(m, BIGCLAM_ECUDA, "state download failed");
+        if (int rs = multi_sync(m)) return rs;
+    }
+    for (bigclam_ctx *c : m->r) { c->cur = (start_cur + (int)(calls & 1)) & 1; c->dense_valid = false; }
+    if (llh_out) *llh_out = hst->ret_llh;
+    if (calls_out) *calls_out = calls;
+    if (llh_trace != nullptr && trace_cap > 0) {
+        const int64_t cnt = std::min<int64_t>(calls, trace_cap);
+        cudaSetDevice(c0->device);
+        if (cnt > 0 && cudaMemcpy(llh_trace, c0->d_trace, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return mfail(m, BIGCLAM_ECUDA, "trace download failed");
+    }
+    for (bigclam_ctx *c : m->r) { cudaSetDevice(c->device); collect_timing(c); }
+    return BIGCLAM_OK;
+}
+
+// Step-kernel time of the most recent bigclam_multi_step / bigclam_multi_run: the slowest rank's sum (BIGCLAM_F_TIME_KERNELS).
+extern "C" int bigclam_multi_get_kernel_time(bigclam_multi *m, double *max_rank_ms_sum, int64_t *step_kernel_launches) {
+    if (m == nullptr) return BIGCLAM_EINVAL;
+    double mx = 0.0;
+    for (bigclam_ctx *c : m->r) mx = std::max(mx, c->last_step_ms);
+    if (max_rank_ms_sum) *max_rank_ms_sum = mx;
+    if (step_kernel_launches) *step_kernel_launches = m->r[0]->last_step_launches;
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_multi_world(const bigclam_multi *m) { return m != nullptr ? m->world : BIGCLAM_EINVAL; }
+#undef MCALL

@@ -1,62 +1,69 @@
-// bigclam_sparse.cuh — the same step (codes/bigclam4-7.scala:152-223) over SPARSE rows of F.
+// bigclam_sparse.cuh — the step (codes/bigclam4-7.scala:152-223) over SPARSE rows of F: layout, the general
+// one-warp-per-node path (any degree, any row length, K <= 1024) and the split-hub phases.  The tile path for
+// small nodes and the kernels themselves are in bigclam_tile.cuh.
 //
 // Why: the reference keeps F as Breeze sparse vectors (`BSV[Double]`, bigclam4-7.scala:97-104) because the rows
 // ARE sparse: on the bench workload (com-amazon, K = 200) a row holds ~9 non-zeros of 200 through the whole
-// run and ~17 components are "active" in a line search.  The dense kernel (bigclam_kernels.cuh) moves and
-// multiplies 95 % zeros.  Here a row is (count, ascending component indices, values) in a per-step pool, every
-// neighbour row is read once per step (~120 bytes instead of 1.6 KB), and all per-edge work is proportional
-// to the row's non-zeros.
+// run and ~17 components are "active" in a line search.  A row is (count, ascending component indices, values)
+// in a per-step pool, every neighbour row is read once per step (~112 bytes instead of 1.6 KB), and all
+// per-edge work is proportional to the row's non-zeros.
 //
 // Layout (per F buffer; double-buffered like the dense F):
 //   hdr[u]      uint64: (offset in 8-byte words << 24) | count
-//   pool        row block at `offset`: pad4(count) doubles, then pad4(count) uint16 indices (ascending)
-//   pool_top    bump allocator of the OUTPUT pool (words), zeroed before every step; a warp takes its new
-//               row's block with one atomicAdd.  The input pool is only read (Jacobi), so a step whose pool
-//               overflowed can simply be repeated with a larger pool.
+//   pool        row block at `offset` (16-byte aligned, a multiple of 16 bytes — one bulk copy moves it):
+//               vpad(count) doubles, then ipad(count) uint16 indices (ascending);  vpad = count rounded up to 2,
+//               ipad = count rounded up to 8.  A node whose step was accepted is followed by its DELTA block in
+//               the same format: the non-zero (old - new) components (:191-192), dcnt[u] of them.
+//   pool_top    bump allocator of the OUTPUT pool (words), zeroed before every step.  The input pool is only
+//               read (Jacobi), so a step whose pool overflowed can simply be repeated with a larger pool.
 //
-// Per node (one warp), with fu scattered into a dense shared-memory vector fu_d[ld]:
+// Per-node results (no floating-point atomics anywhere: the sums over nodes are taken afterwards, in a fixed
+// order, by reduce_kernel — bit-identical from run to run):
+//   node_llh[u]  llh_u of the PRE block (:168)          accepted[u]  accepted step index, -1 = row kept
+//   dcnt[u]      entries of the delta block
+//
+// General path, per node (one warp), with fu scattered into a dense shared-memory vector fu_d[ld]:
 //   PRE   the entries of up to 32 neighbour rows are staged in shared memory; lane e walks row e:
-//         x_e = sum_i val_i * fu_d[idx_i] (no reduction: the dot lands in the lane that evaluates exp/log for
-//         that edge, 32 edges per call); the gradient sum g_d[idx] += w_e * val goes neighbour by neighbour
-//         (indices are unique inside a row: no conflicts, fixed order);
+//         x_e = sum_i val_i * fu_d[idx_i]; the gradient sum g_d[idx] += w_e * val goes neighbour by neighbour;
 //   scan  one pass over the ld components turns g_d into the gradient (:168), sums |g|^2 and lists the
 //         active components (fu > 0 or g > 0);
 //   LS    lane (trial j, edge parity h) walks the staged entries of its edges:
 //         D = sum_i clamp(fu_d[idx_i] + s_j * g_d[idx_i]) * val_i — an inactive component clamps to 0 and adds
-//         exactly nothing, so no pair list / intersection is needed; two edges per lane in flight;
+//         exactly nothing; two edges per lane in flight;
 //   SWAP  the accepted candidate's non-zeros are compacted (ascending) into the staging buffer, a block is
-//         taken from the output pool, the row and its header are written.
+//         taken from the output pool, the row, its delta block and its header are written.
 //
-// Limits of this version: ld <= 256 (K <= 256), MIN_F_ == 0.
+// Limits: ld <= 1024, MIN_F_ == 0.
 #pragma once
 #include "bigclam_kernels.cuh"
 
 namespace bigclam {
 
-// Build-time knobs for A/B runs (tools/build_variant.sh <name> -DBIGCLAM_SP_BLOCKS=2 -DBIGCLAM_SP_PREFETCH=1):
-//   BIGCLAM_SP_BLOCKS    blocks per SM the kernel is compiled for: 2 (default) = 16 warps/SM, ~120 registers, no
-//                        spills; 3 = 24 warps/SM at 80 registers with 72-112 bytes of spills (the dense kernel's
-//                        128-register builds lost 40 % to far fewer spilled bytes: to be measured, not assumed);
-//   BIGCLAM_SP_PREFETCH  load the next node's header, neighbour ids, neighbour headers and own entries one node
-//                        ahead (two dependent round trips less per node, ~16 more live registers).
-#ifndef BIGCLAM_SP_BLOCKS
-#define BIGCLAM_SP_BLOCKS 2
-#endif
-#ifndef BIGCLAM_SP_PREFETCH
-#define BIGCLAM_SP_PREFETCH 0
-#endif
-constexpr int kSpBlocksPerSM = BIGCLAM_SP_BLOCKS;
-constexpr bool kSpPrefetch = BIGCLAM_SP_PREFETCH != 0;
-constexpr int kSpWarps = 8;            // warps per block at most (ld <= 256); wide rows run fewer (sp_warps_per_block)
+constexpr int kSpBlocksPerSM = 2;
+constexpr int kSpWarps = 8;            // warps per block at most; wide rows run fewer (sp_warps_per_block)
 constexpr int kSpThreads = kSpWarps * 32;
-// staged neighbour entries per chunk: at least one full row always fits
+// staged neighbour entries per chunk of the general path: at least one full row always fits
 __host__ __device__ inline int sp_entries(int ld) { return ld > 512 ? ld : 512; }
 
 __host__ __device__ inline uint64_t sp_pack(uint64_t off8, uint32_t cnt) { return (off8 << 24) | (uint64_t)cnt; }
 __host__ __device__ inline uint32_t sp_cnt(uint64_t h) { return (uint32_t)(h & 0xffffffull); }
 __host__ __device__ inline uint64_t sp_off8(uint64_t h) { return h >> 24; }
-__host__ __device__ inline uint32_t sp_pad(uint32_t cnt) { return (cnt + 3u) & ~3u; }
-__host__ __device__ inline uint64_t sp_words(uint32_t cnt) { return (uint64_t)sp_pad(cnt) * 5u / 4u; }   // 8-byte words of a row block
+__host__ __device__ inline uint32_t sp_vpad(uint32_t cnt) { return (cnt + 1u) & ~1u; }
+__host__ __device__ inline uint32_t sp_ipad(uint32_t cnt) { return (cnt + 7u) & ~7u; }
+__host__ __device__ inline uint64_t sp_words(uint32_t cnt) { return (uint64_t)sp_vpad(cnt) + sp_ipad(cnt) / 4u; }   // 8-byte words of a block
+__host__ __device__ inline const unsigned short *sp_idx(const double *vals, uint32_t cnt) {
+    return reinterpret_cast<const unsigned short *>(vals + sp_vpad(cnt));
+}
+__host__ __device__ inline unsigned short *sp_idx(double *vals, uint32_t cnt) {
+    return reinterpret_cast<unsigned short *>(vals + sp_vpad(cnt));
+}
+
+struct TileMeta {   // a group of consecutive small nodes of the processing order handled together by one warp
+    int32_t pos0;   // first position (index into StepArgs::meta)
+    int32_t ecol0;  // first entry of the tile in SparseArgs::tcol
+    int32_t nn;     // nodes (<= kTlMaxNodes)
+    int32_t ne;     // edges (<= kTlMaxEdges)
+};
 
 struct SparseArgs {
     const uint64_t *hdr_in;
@@ -67,170 +74,155 @@ struct SparseArgs {
     uint64_t pool_cap8;                // capacity of that region in words
     uint64_t region_base8;             // where the region starts in pool_out (0 on a single GPU)
     int32_t *overflow;                 // set when a row did not fit (the step must be repeated with a larger pool)
+    // per-node results (see the header comment)
+    double *node_llh;
+    unsigned short *dcnt;
+    int8_t *accepted;                  // always written by a line-search launch
     // node-partitioned multi-GPU: the owners' new rows go to the same offsets of every replica's output pool
     // (plain stores to IPC-mapped peer memory over NVLink); each rank allocates only inside its own region, so
-    // all replicas end up with the same layout and no remote atomics are needed.  Every owned row is written
-    // (and pushed) every step: the output pool is rebuilt from scratch each step.
+    // all replicas end up with the same layout and no remote atomics are needed.
     int32_t n_peers;
     uint64_t *peer_hdr[7];
     double *peer_pool[7];
     unsigned int *hub_work;            // next hub item to hand out (zeroed per launch); items: StepArgs::hub_items
+    // work list after the hubs: n_gen nodes for the general path (positions n_hubs ..), then the tiles
+    int32_t n_gen;
+    int32_t ntiles;
+    const TileMeta *tiles;
+    const int32_t *tcol;               // per tile edge: neighbour id | (node index within the tile << 28)
+    unsigned int *stats;               // optional [tiles done on the tile path, tiles that fell back]
 };
 
-// The dense per-warp / per-block vectors are padded to a multiple of 32 components (zeros: a padding component has
+// The dense per-warp vectors are padded to a multiple of 32 components (zeros: a padding component has
 // fu = sumF = 0, hence gradient 0, never active), so that the loops over components need no bounds checks.
 __host__ __device__ inline int sp_ldp(int ld) { return (ld + 31) & ~31; }
-// per-warp shared memory: fu_d[ldp] | g_d[ldp] | ent_val[E] | ent_idx[E] u16 | aidx[max(ld, 256)] u16 | poff[40] u16 |
-//                         cbal[32] u32 | ccum[32] u16 (+ pad)   (ballots / running counts of the entry compaction)
-__host__ __device__ inline size_t sp_warp_bytes(int ld) {
+// general path, per-warp shared memory:
+//   fu_d[ldp] | g_d[ldp] | ent_val[E] | ent_idx[E] u16 | aidx[max(ld, 256)] u16 | poff[40] u16 | cbal[32] u32 | ccum[32] u16
+__host__ __device__ inline size_t sp_gen_warp_bytes(int ld) {
     return sizeof(double) * 2 * (size_t)sp_ldp(ld) + (size_t)sp_entries(ld) * 10 + 2 * (size_t)(ld > 256 ? ld : 256) + 2 * 40 + 4 * 32 + 2 * 32;
 }
-// block: steps[kMaxSteps] | sumF[ldp] | D[ldp] | wpb x warp area
-__host__ __device__ inline size_t sp_block_smem_bytes(int ld, int wpb) {
-    return sizeof(double) * (kMaxSteps + 2 * (size_t)sp_ldp(ld)) + (size_t)wpb * sp_warp_bytes(ld);
-}
-// warps per block: as many resident warps per SM as the shared memory (227 KB, 1 KB reserved per block) allows
-inline int sp_warps_per_block(int ld) {
-    int best = 1, best_warps = 0;
-    for (int wpb = kSpWarps; wpb >= 1; wpb >>= 1) {
-        const size_t bytes = sp_block_smem_bytes(ld, wpb) + 1024 + 256;
-        const int blocks = (int)((size_t)233472 / bytes);
-        const int warps = (blocks > kSpBlocksPerSM ? kSpBlocksPerSM : blocks) * wpb;         // the kernel is built for that many blocks per SM
-        if (warps > best_warps) { best_warps = warps; best = wpb; }
-    }
-    return best;
-}
 
-// Stages the rows of up to 32 neighbours (ids colp[0 .. cnt32)) of one node into the warp's entry buffer: the
-// longest prefix of them whose entries fit the `cap` entries of the buffer (at least one: a row has at most ld <= cap).
-// Returns the number ne of staged neighbours; poff[e] .. poff[e + 1] is row e's range in the buffer.
-// (noinline, scalar arguments only: one copy in the code, called from PRE and from the line search.)
-__device__ __noinline__ int sp_stage_chunk(const uint64_t *__restrict__ hdr_in, const double *__restrict__ pool_in,
-                                           const int32_t *__restrict__ colp, int cnt32, int lane, int cap, double *ent_val,
-                                           unsigned short *ent_idx, unsigned short *poff, int use_pre = 0,
-                                           unsigned long long pre_hv = 0ull) {
-    // use_pre: the caller already holds this chunk's row headers (loaded one node ahead)
-    uint64_t hv = pre_hv;
-    if (!use_pre) {
-        const int v = (lane < cnt32) ? colp[lane] : 0;
-        hv = (lane < cnt32) ? __ldg(hdr_in + v) : 0ull;
-    }
-    const int cv = (int)sp_cnt(hv);
-    int incl = cv;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    const unsigned fit = __ballot_sync(0xffffffffu, (lane < cnt32) && (incl <= cap));
-    const int ne = __popc(fit);                     // incl is monotone: the fitting lanes are 0 .. ne-1
-    if (lane == 0) poff[0] = 0;
-    if (lane < ne) poff[lane + 1] = (unsigned short)incl;
-    __syncwarp();
-    // the T entries of the ne rows, 32 at a time, one per lane: all loads of a round are in flight together
-    // (the rows are ~9 entries long: going row by row would serialise a round trip per row)
-    const int T = (ne > 0) ? __shfl_sync(0xffffffffu, incl, ne - 1) : 0;
-    for (int base = 0; base < T; base += 32) {
-        const int j = base + lane;
-        int lo = 0, hi = ne;                                   // row of entry j: the largest e with poff[e] <= j
-#pragma unroll
-        for (int s = 0; s < 5; ++s) {
-            const int mid = (lo + hi) >> 1;
-            const bool le = (int)poff[mid] <= j;
-            if (hi - lo > 1) { if (le) lo = mid; else hi = mid; }
-        }
-        const uint64_t he = __shfl_sync(0xffffffffu, hv, lo);
-        if (j < T) {
-            const int ce = (int)sp_cnt(he);
-            const double *vals = pool_in + sp_off8(he);
-            const unsigned short *idxp = reinterpret_cast<const unsigned short *>(vals + sp_pad((uint32_t)ce));
-            const int i = j - (int)poff[lo];
-            ent_val[j] = __ldg(vals + i);
-            ent_idx[j] = __ldg(idxp + i);
-        }
-    }
-    __syncwarp();
-    return ne;
-}
-
-// Hubs.  A node whose neighbour list is long enough to dominate a launch when one warp walks it (host: a sizeable
-// fraction of a warp's share of the launch) is split into segments of kSpHubSeg edges that different warps work
-// on; the pieces meet in a global scratch row per hub (same layout as the dense kernels' mega hubs:
-// G[ld] | S1 | ST[16], stride ld + 32 doubles, two counters per hub):
-//   phase 1  PRE of one segment: its share of sum_v w_v fv (atomic adds into G) and of S1;
-//   phase 2  line search of one segment, once all phase-1 segments of the hub are in: the segment's share of the
-//            16 per-trial sums (atomic adds into ST);
+// Split hubs.  A node whose neighbour list is long enough to dominate a launch when one warp walks it is split
+// into segments of kSpHubSeg edges that different warps work on; the pieces meet in a global scratch row per
+// hub (G[ld] | S1 | ST[16], stride ld + 32 doubles, two counters per hub):
+//   phase 1  PRE of one segment: its share of sum_v w_v fv and of S1 into the segment's own slot of the scratch
+//            (no atomics: the hub's warps add the slots up in slot order, so the result is reproducible);
+//   phase 2  line search of one segment, once all phase-1 segments of the hub are in;
 //   phase 3  once per hub, after its phase-2 segments: gradient, active set, Armijo decision, new row.
 // Items are handed out in that order by one counter and every warp holds one item at a time on a grid whose
 // warps are all resident, so a waiting warp only waits for items that are being processed: no deadlock.
-// (G is summed by atomics in arrival order, so a hub's gradient is reproducible only to rounding.)
 constexpr int kSpHubSeg = 256;
+// scratch of one hub: (nslices + 1) x (ld + 32) doubles: slice sl holds  G_sl[ld] | S1_sl | ST_sl[16], the last
+// slot the sums over the slices (G | S1)
+__host__ __device__ inline size_t sp_hub_stride(int ld) { return (size_t)ld + 32; }
 
-// kPush: multi-GPU launch, the peers' replicas are written too; kHub: the launch has split hubs.  Both are
-// compile-time so that the plain single-GPU kernel carries none of that code.
-template <bool kPush, bool kHub>
-__global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel(const StepArgs a, const SparseArgs sp) {
-    if (a.done_flag != nullptr && *a.done_flag != 0) return;
+// ---------------------------------------------------------------------------------------------------------------
+// The general path: everything one warp needs to process one node (or one hub item).
+struct SpGen {
+    // launch-wide
+    const StepArgs *a;
+    const SparseArgs *sp;
+    const double *s_steps;
+    const double *s_sumF;
+    EdgeConst ec;
+    // per warp
+    double *fu_d, *g_d, *ent_val;
+    unsigned short *ent_idx, *aidx, *poff, *ccum;
+    unsigned int *cbal;
+    int lane, ld, ldp, ecap;
+    unsigned lt_mask;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int ld = a.ld;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int wpb = (int)(blockDim.x >> 5), nthreads = (int)blockDim.x;
-    const int ecap = sp_entries(ld);
-    const int ldp = sp_ldp(ld);
-    double *s_steps = reinterpret_cast<double *>(smem_raw);
-    double *s_sumF = s_steps + kMaxSteps;
-    double *s_D = s_sumF + ldp;
-    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_D + ldp) + (size_t)wib * sp_warp_bytes(ld);
-    double *fu_d = reinterpret_cast<double *>(wbase);
-    double *g_d = fu_d + ldp;
-    double *ent_val = g_d + ldp;
-    unsigned short *ent_idx = reinterpret_cast<unsigned short *>(ent_val + ecap);
-    unsigned short *aidx = ent_idx + ecap;
-    unsigned short *poff = aidx + (ld > 256 ? ld : 256);
-    unsigned int *cbal = reinterpret_cast<unsigned int *>(poff + 40);
-    unsigned short *ccum = reinterpret_cast<unsigned short *>(cbal + 32);
-
+    __device__ __forceinline__ void carve(unsigned char *wbase, int ld_, int lane_) {
+        ld = ld_;
+        ldp = sp_ldp(ld_);
+        ecap = sp_entries(ld_);
+        lane = lane_;
+        lt_mask = (1u << lane_) - 1u;
+        fu_d = reinterpret_cast<double *>(wbase);
+        g_d = fu_d + ldp;
+        ent_val = g_d + ldp;
+        ent_idx = reinterpret_cast<unsigned short *>(ent_val + ecap);
+        aidx = ent_idx + ecap;
+        poff = aidx + (ld > 256 ? ld : 256);
+        cbal = reinterpret_cast<unsigned int *>(poff + 40);
+        ccum = reinterpret_cast<unsigned short *>(cbal + 32);
+    }
+    // the tile path uses the same bytes: the dense vectors must be zero whenever the general path starts
+    __device__ __forceinline__ void clear_dense() {
 #pragma unroll 1
-    for (int i = threadIdx.x; i < ldp; i += nthreads) { s_sumF[i] = (i < ld) ? a.sumF[i] : 0.0; s_D[i] = 0.0; }
-#pragma unroll 1
-    for (int i = threadIdx.x; i < kMaxSteps; i += nthreads) s_steps[i] = a.steps[i];
-#pragma unroll 1
-    for (int i = lane; i < ldp; i += 32) { fu_d[i] = 0.0; g_d[i] = 0.0; }
-    __syncthreads();
+        for (int i = lane; i < ldp; i += 32) { fu_d[i] = 0.0; g_d[i] = 0.0; }
+        __syncwarp();
+    }
 
-    const EdgeConst ec = {a.x_lo, a.x_hi, a.t_lo, a.t_hi, a.w_lo, a.w_hi};
-    const double max_f = a.max_f;
-    const int nsteps = a.nsteps;
-    const int64_t order_n = a.order_n;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const int j16 = lane & 15, h = lane >> 4;
-    double llh_acc = 0.0, nupd_acc = 0.0;
+    // Stages the rows of up to 32 neighbours (ids colp[0 .. cnt32), the low 28 bits when `tagged`) of one node
+    // into the entry buffer: the longest prefix of them whose entries fit (at least one: a row has at most
+    // ld <= ecap entries).  Returns the number ne of staged neighbours; poff[e] .. poff[e + 1] is row e's range.
+    __device__ __forceinline__ int stage_chunk(const int32_t *__restrict__ colp, int cnt32) {
+        const uint64_t *__restrict__ hdr_in = sp->hdr_in;
+        const double *__restrict__ pool_in = sp->pool_in;
+        const int v = (lane < cnt32) ? (colp[lane] & 0x0fffffff) : 0;
+        const uint64_t hv = (lane < cnt32) ? __ldg(hdr_in + v) : 0ull;
+        const int cv = (int)sp_cnt(hv);
+        int incl = cv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const unsigned fit = __ballot_sync(0xffffffffu, (lane < cnt32) && (incl <= ecap));
+        const int ne = __popc(fit);                     // incl is monotone: the fitting lanes are 0 .. ne-1
+        if (lane == 0) poff[0] = 0;
+        if (lane < ne) poff[lane + 1] = (unsigned short)incl;
+        __syncwarp();
+        // the T entries of the ne rows, 32 at a time, one per lane: all loads of a round are in flight together
+        const int T = (ne > 0) ? __shfl_sync(0xffffffffu, incl, ne - 1) : 0;
+#pragma unroll 1
+        for (int base = 0; base < T; base += 32) {
+            const int j = base + lane;
+            int lo = 0, hi = ne;                                   // row of entry j: the largest e with poff[e] <= j
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                const int mid = (lo + hi) >> 1;
+                const bool le = (int)poff[mid] <= j;
+                if (hi - lo > 1) { if (le) lo = mid; else hi = mid; }
+            }
+            const uint64_t he = __shfl_sync(0xffffffffu, hv, lo);
+            if (j < T) {
+                const int ce = (int)sp_cnt(he);
+                const double *vals = pool_in + sp_off8(he);
+                const int i = j - (int)poff[lo];
+                ent_val[j] = __ldg(vals + i);
+                ent_idx[j] = __ldg(sp_idx(vals, (uint32_t)ce) + i);
+            }
+        }
+        __syncwarp();
+        return ne;
+    }
 
-    // ---- pieces shared by the plain node path and the hub phases ----
-    // PRE over the edges [eb, ee) of a node whose fu is in fu_d: returns this lane's share of S1; with `axpy`
-    // the weighted neighbour rows are added into g_d.  `single` = the range fitted one staged chunk (its
-    // entries are still in the buffer, `ne_last` rows).
-    auto pre_range = [&](int64_t e0, int eb, int ee, bool axpy, int &nchunks, int &ne_last, int use_pre = 0,
-                         unsigned long long pre_hv = 0ull) -> double {
+    // PRE over the edges [eb, ee) of a node whose fu is in fu_d: returns this lane's share of S1 (lane e holds the
+    // terms of the chunks' e-th rows); with `axpy` the weighted neighbour rows are added into g_d.
+    __device__ __forceinline__ double pre_range(const int32_t *colbase, int eb, int ee, bool axpy, int &nchunks, int &ne_last) {
         double S1 = 0.0;
         nchunks = 0;
         ne_last = 0;
+#pragma unroll 1
         for (int cb = eb; cb < ee;) {
-            const int ne = sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, ee - cb), lane, ecap, ent_val, ent_idx, poff,
-                                          (use_pre && cb == eb) ? 1 : 0, pre_hv);
+            const int ne = stage_chunk(colbase + cb, min(32, ee - cb));
             double x = 0.0;
             if (lane < ne) {
                 const int end = poff[lane + 1];
+#pragma unroll 1
                 for (int i = poff[lane]; i < end; ++i) x = fma(ent_val[i], fu_d[ent_idx[i]], x);
             }
             double w;
             const double t = edge_term<true>(x, ec, w);
             S1 += (lane < ne) ? t : 0.0;
             if (axpy) {
+#pragma unroll 1
                 for (int e = 0; e < ne; ++e) {
                     const double we = __shfl_sync(0xffffffffu, w, e);
                     const int pe = poff[e], pn = poff[e + 1];
+#pragma unroll 1
                     for (int i = pe + lane; i < pn; i += 32) {
                         const int c = ent_idx[i];
                         g_d[c] = fma(we, ent_val[i], g_d[c]);
@@ -243,13 +235,15 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
             ++nchunks;
         }
         return S1;
-    };
+    }
     // g_d (sum of weighted neighbour rows) -> gradient (:168) in place; returns |g|^2, lists the active
     // components in aidx (m of them) and tells whether any candidate can reach MAX_F_.
-    auto scan_gradient = [&](int &m, bool &need_hi) -> double {
+    __device__ __forceinline__ double scan_gradient(int &m, bool &need_hi) {
         double G2 = 0.0;
         bool hi_lane = false;
         m = 0;
+        const double max_f = a->max_f;
+#pragma unroll 1
         for (int c0 = 0; c0 < ldp; c0 += 32) {          // (padding components: f = g = 0, inactive)
             const int c = c0 + lane;
             const double f = fu_d[c];
@@ -268,13 +262,13 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
         need_hi = __any_sync(0xffffffffu, hi_lane);
         __syncwarp();
         return G2;
-    };
+    }
     // The staged entries of `ne` rows shrink, in place, to those on ACTIVE components (fu > 0 or grad > 0): only
-    // they can contribute to a candidate's dot (an inactive component clamps to 0), and a neighbour row typically
-    // keeps ~3 of its ~9 entries.  Order inside a row is kept, poff is rewritten.
-    auto compact_active = [&](int ne) {
+    // they can contribute to a candidate's dot.  Order inside a row is kept, poff is rewritten.
+    __device__ __forceinline__ void compact_active(int ne) {
         const int T = poff[ne];
         int total = 0;
+#pragma unroll 1
         for (int base = 0; base < T; base += 32) {
             const int j = base + lane;
             const bool in = j < T;
@@ -301,14 +295,16 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
         if (lane < ne) poff[lane] = (unsigned short)newp;
         if (lane == 0) poff[ne] = (unsigned short)total;
         __syncwarp();
-    };
+    }
     // Line search over the edges [eb, ee): lane (j, h) returns the sum over its edges of the clamped edge term
     // for candidate step s; `staged` rows of a single chunk may still be in the buffer from PRE.
-    auto ls_range = [&](int64_t e0, int eb, int ee, double s, bool need_hi, int staged) -> double {
+    __device__ __forceinline__ double ls_range(const int32_t *colbase, int eb, int ee, double s, bool need_hi, int staged) {
+        const int h = lane >> 4;
+        const double max_f = a->max_f;
         double sumterms = 0.0;
+#pragma unroll 1
         for (int cb = eb; cb < ee;) {
-            const int ne = (staged > 0) ? staged
-                                        : sp_stage_chunk(sp.hdr_in, sp.pool_in, a.col + e0 + cb, min(32, ee - cb), lane, ecap, ent_val, ent_idx, poff);
+            const int ne = (staged > 0) ? staged : stage_chunk(colbase + cb, min(32, ee - cb));
             compact_active(ne);
 #pragma unroll 1
             for (int e2 = 0; e2 < ne; e2 += 4) {
@@ -341,11 +337,14 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
             cb += ne;
         }
         return sumterms;
-    };
+    }
     // Armijo decision for the 16 candidates tg .. tg+15 given each lane's edge-term sum (already summed over h).
-    auto decide = [&](int tg, double s, bool jok, double sumterms, int m, bool need_hi, double llh_u, double G2) -> int {
+    __device__ __forceinline__ int decide(int tg, double s, bool jok, double sumterms, int m, bool need_hi, double llh_u, double G2) {
+        const int h = lane >> 4;
+        const double max_f = a->max_f;
         // - newfu.sfT + newfu.newfu with sfT = (sumF - fu) + newfu   (:176,:180)
         double oa = 0.0, ob = 0.0;
+#pragma unroll 1
         for (int t = h; t < m; t += 2) {
             const int c = aidx[t];
             const double f = fu_d[c], g = g_d[c];
@@ -357,21 +356,26 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
         oa += __shfl_xor_sync(0xffffffffu, oa, 16);
         ob += __shfl_xor_sync(0xffffffffu, ob, 16);
         const double result = (sumterms - oa) + ob;
-        const double rhs = llh_u + (a.alpha * s) * G2;
+        const double rhs = llh_u + (a->alpha * s) * G2;
         const unsigned pass = __ballot_sync(0xffffffffu, jok && (result >= rhs)) & 0xffffu;
         return pass ? tg + __ffs(pass) - 1 : -1;          // lowest j == largest step (:182 max)
-    };
-    // SWAP (:183-190): the accepted candidate's non-zeros (or the old row) go to the output pool(s).
-    auto swap_row = [&](int64_t u, int jstar, int m, int cu, const double *uval, const unsigned short *uidx) {
-        int cnt_new = 0;
+    }
+    // SWAP (:183-190): the accepted candidate's non-zeros (or the old row) go to the output pool(s), followed by
+    // the delta block (old - new, :191-192) of an accepted node.
+    template <bool kPush>
+    __device__ __forceinline__ void swap_row(int64_t u, int jstar, int m, int cu, const double *uval, const unsigned short *uidx) {
+        const double max_f = a->max_f;
+        int cnt_new = 0, nd = 0;
+        double s = 0.0;
         if (jstar >= 0) {
-            const double s = s_steps[jstar];
+            s = s_steps[jstar];
+#pragma unroll 1
             for (int t0 = 0; t0 < m; t0 += 32) {
                 const int t = t0 + lane;
                 const bool ok = t < m;
                 const int c = ok ? (int)aidx[t] : 0;
                 const double f = fu_d[c], g = g_d[c];
-                const double nr = clamp_step(f, s, g, a.min_f, max_f);
+                const double nr = clamp_step(f, s, g, a->min_f, max_f);
                 const bool nz = ok && (nr != 0.0);
                 const unsigned bal = __ballot_sync(0xffffffffu, nz);
                 if (nz) {
@@ -379,11 +383,11 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
                     ent_val[p] = nr;
                     ent_idx[p] = (unsigned short)c;
                 }
-                if (ok && f != nr) atomicAdd(s_D + c, f - nr);       // :191-192, sum over accepted nodes of old - new
                 cnt_new += __popc(bal);
+                nd += __popc(__ballot_sync(0xffffffffu, ok && (f != nr)));
             }
-            nupd_acc += 1.0;
         } else {
+#pragma unroll 1
             for (int i = lane; i < cu; i += 32) {
                 ent_val[i] = __ldg(uval + i);
                 ent_idx[i] = __ldg(uidx + i);
@@ -391,175 +395,69 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
             cnt_new = cu;
         }
         __syncwarp();
-        const unsigned long long words = sp_words((uint32_t)cnt_new);
+        const unsigned long long wrow = sp_words((uint32_t)cnt_new);
+        const unsigned long long words = wrow + (nd > 0 ? sp_words((uint32_t)nd) : 0ull);
         unsigned long long rel = 0;
-        if (lane == 0 && cnt_new > 0) rel = atomicAdd(sp.pool_top, words);
+        if (lane == 0 && words > 0) rel = atomicAdd(sp->pool_top, words);
         rel = __shfl_sync(0xffffffffu, rel, 0);
-        if (rel + words > sp.pool_cap8) {
-            if (lane == 0) { *sp.overflow = 1; sp.hdr_out[u] = sp_pack(0, 0); }
-        } else {
-            const unsigned long long off = sp.region_base8 + rel;
-            const uint64_t hnew = sp_pack(off, (uint32_t)cnt_new);
-            double *ov = sp.pool_out + off;
-            unsigned short *oi = reinterpret_cast<unsigned short *>(ov + sp_pad((uint32_t)cnt_new));
-            for (int i = lane; i < cnt_new; i += 32) {
-                ov[i] = ent_val[i];
-                oi[i] = ent_idx[i];
-            }
-            if (lane == 0) sp.hdr_out[u] = hnew;
-            if (kPush) {
-                for (int pr = 0; pr < sp.n_peers; ++pr) {
-                    double *pv = sp.peer_pool[pr] + off;
-                    unsigned short *pi = reinterpret_cast<unsigned short *>(pv + sp_pad((uint32_t)cnt_new));
-                    for (int i = lane; i < cnt_new; i += 32) {
-                        pv[i] = ent_val[i];
-                        pi[i] = ent_idx[i];
-                    }
-                    if (lane == 0) sp.peer_hdr[pr][u] = hnew;
+        if (rel + words > sp->pool_cap8) {
+            if (lane == 0) { *sp->overflow = 1; sp->hdr_out[u] = sp_pack(0, 0); sp->dcnt[u] = 0; }
+            return;
+        }
+        const unsigned long long off = sp->region_base8 + rel;
+        const uint64_t hnew = sp_pack(off, (uint32_t)cnt_new);
+        double *ov = sp->pool_out + off;
+        unsigned short *oi = sp_idx(ov, (uint32_t)cnt_new);
+#pragma unroll 1
+        for (int i = lane; i < cnt_new; i += 32) {
+            ov[i] = ent_val[i];
+            oi[i] = ent_idx[i];
+        }
+        if (lane == 0) { sp->hdr_out[u] = hnew; sp->dcnt[u] = (unsigned short)nd; }
+        if (kPush) {
+#pragma unroll 1
+            for (int pr = 0; pr < sp->n_peers; ++pr) {
+                double *pv = sp->peer_pool[pr] + off;
+                unsigned short *pi = sp_idx(pv, (uint32_t)cnt_new);
+#pragma unroll 1
+                for (int i = lane; i < cnt_new; i += 32) {
+                    pv[i] = ent_val[i];
+                    pi[i] = ent_idx[i];
                 }
+                if (lane == 0) sp->peer_hdr[pr][u] = hnew;
             }
         }
-    };
-
-    // ---------------- split hubs (see above), then one warp per node ----------------
-    if constexpr (kHub) {
-        for (;;) {
-            unsigned int it = 0;
-            if (lane == 0) it = atomicAdd(sp.hub_work, 1u);
-            it = __shfl_sync(0xffffffffu, it, 0);
-            if (it >= (unsigned int)a.n_hub_items) break;
-            const HubItem item = a.hub_items[it];
-            const NodeMeta nm = a.meta[item.hub];
-            const int64_t u = nm.u, e0 = nm.e0;
-            const int deg = nm.deg;
-            double *scr = a.hub_scratch + (size_t)item.mslot * (ld + 32);
-            unsigned int *cnt = a.hub_counters + 2 * (size_t)item.mslot;
-            const int sb = item.slice * kSpHubSeg, se = min(deg, sb + kSpHubSeg);
-            const uint64_t hu = __ldg(sp.hdr_in + u);
-            const int cu = (int)sp_cnt(hu);
-            const double *uval = sp.pool_in + sp_off8(hu);
-            const unsigned short *uidx = reinterpret_cast<const unsigned short *>(uval + sp_pad((uint32_t)cu));
-            double fusf = 0.0, fufu = 0.0;
-            for (int i = lane; i < cu; i += 32) {
-                const double v = __ldg(uval + i);
-                const int c = __ldg(uidx + i);
-                fu_d[c] = v;
-                fusf = fma(v, s_sumF[c], fusf);
-                fufu = fma(v, v, fufu);
+        if (nd > 0) {                                    // delta block (local only: the owner reduces it)
+            double *dv = ov + wrow;
+            unsigned short *di = sp_idx(dv, (uint32_t)nd);
+            int q = 0;
+#pragma unroll 1
+            for (int t0 = 0; t0 < m; t0 += 32) {
+                const int t = t0 + lane;
+                const bool ok = t < m;
+                const int c = ok ? (int)aidx[t] : 0;
+                const double f = fu_d[c], g = g_d[c];
+                const double nr = clamp_step(f, s, g, a->min_f, max_f);
+                const bool ch = ok && (f != nr);
+                const unsigned bal = __ballot_sync(0xffffffffu, ch);
+                if (ch) {
+                    const int p = q + __popc(bal & lt_mask);
+                    dv[p] = f - nr;
+                    di[p] = (unsigned short)c;
+                }
+                q += __popc(bal);
             }
-            fusf = warp_sum(fusf);
-            fufu = warp_sum(fufu);
-            __syncwarp();
-            const bool in_uset = (a.node_mask == nullptr) || (a.node_mask[u] != 0);
-            const bool want_ls = a.do_linesearch && in_uset;
-            if (item.phase == 1) {
-                int nch, nel;
-                double S1 = warp_sum(pre_range(e0, sb, se, want_ls, nch, nel));
-                if (want_ls) {
-                    for (int c = lane; c < ld; c += 32) {
-                        const double v = g_d[c];
-                        if (v != 0.0) atomicAdd(scr + c, v);
-                        g_d[c] = 0.0;
-                    }
-                }
-                if (lane == 0) atomicAdd(scr + ld, S1);
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) atomicAdd(cnt, 1u);
-            } else {
-                if (lane == 0) {
-                    const unsigned int *c = cnt + (item.phase == 2 ? 0 : 1);
-                    while (*reinterpret_cast<const volatile unsigned int *>(c) < (unsigned int)item.nslices) __nanosleep(200);
-                    __threadfence();
-                }
-                __syncwarp();
-                const double llh_u = (__ldcg(scr + ld) - fusf) + fufu;
-                int m = 0, jstar = -1;
-                bool need_hi = false;
-                double G2 = 0.0;
-                if (want_ls) {
-                    for (int c = lane; c < ldp; c += 32) g_d[c] = (c < ld) ? __ldcg(scr + c) : 0.0;
-                    __syncwarp();
-                    G2 = scan_gradient(m, need_hi);
-                }
-                const double s = s_steps[j16 < nsteps ? j16 : 0];       // hubs are only split when nsteps <= 16
-                if (item.phase == 2) {
-                    if (want_ls) {
-                        double st = ls_range(e0, sb, se, s, need_hi, 0);
-                        st += __shfl_xor_sync(0xffffffffu, st, 16);
-                        if (lane < 16) atomicAdd(scr + ld + 1 + lane, st);
-                    }
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) atomicAdd(cnt + 1, 1u);
-                } else {
-                    if (want_ls) jstar = decide(0, s, j16 < nsteps, __ldcg(scr + ld + 1 + j16), m, need_hi, llh_u, G2);
-                    llh_acc += llh_u;
-                    if (a.do_linesearch) swap_row(u, jstar, m, cu, uval, uidx);
-                    if (a.accepted != nullptr && lane == 0) a.accepted[u] = (int8_t)jstar;
-                }
-                __syncwarp();
-                if (want_ls)
-                    for (int c = lane; c < ldp; c += 32) g_d[c] = 0.0;
-            }
-            __syncwarp();
-            for (int i = lane; i < cu; i += 32) fu_d[__ldg(uidx + i)] = 0.0;
-            __syncwarp();
         }
     }
 
-    // positions n_hubs .. n_hubs + 3*#warps - 1 are pre-assigned, the rest is handed out by the work counter two
-    // nodes ahead
-    const int64_t nwarps = (int64_t)gridDim.x * wpb;
-    int64_t pos = (kHub ? (int64_t)a.n_hubs : 0) + (int64_t)blockIdx.x * wpb + wib;
-    int64_t pos_n = pos + nwarps, pos_nn = pos + 2 * nwarps;
-    NodeMeta cur = {0, 0, 0}, nxt = {0, 0, 0};
-    if (pos < order_n) cur = a.meta[pos];
-    if (pos_n < order_n) nxt = a.meta[pos_n];
-    // kSpPrefetch: what the current node needs first is loaded while the previous one is processed — its header
-    // (c_hu), its first 32 entries (lane i holds entry i), the headers of its first 32 neighbours (c_hv)
-    unsigned long long c_hu = 0ull, c_hv = 0ull;
-    double c_val = 0.0;
-    int c_idx = 0;
-    if (kSpPrefetch && pos < order_n) {
-        c_hu = __ldg(sp.hdr_in + cur.u);
-        const int v0 = (lane < min(32, cur.deg)) ? a.col[cur.e0 + lane] : 0;
-        c_hv = (lane < min(32, cur.deg)) ? __ldg(sp.hdr_in + v0) : 0ull;
-        const int cu0 = (int)sp_cnt(c_hu);
-        const double *uv0 = sp.pool_in + sp_off8(c_hu);
-        if (lane < cu0) {
-            c_val = __ldg(uv0 + lane);
-            c_idx = __ldg(reinterpret_cast<const unsigned short *>(uv0 + sp_pad((uint32_t)cu0)) + lane);
-        }
-    }
-
-    while (pos < order_n) {
-        const int64_t u = cur.u, e0 = cur.e0;
-        const int deg = cur.deg;
-        NodeMeta nn = {0, 0, 0};
-        if (pos_nn < order_n) nn = a.meta[pos_nn];
-        unsigned int fetched = 0;
-        if (lane == 0) fetched = atomicAdd(a.work_counter, 1u);
-        // stage 1 of the prefetch for the next node: header and neighbour ids
-        const bool has_next = pos_n < order_n;
-        unsigned long long n_hu = 0ull, n_hv = 0ull;
-        int n_v = 0, n_idx = 0;
-        double n_val = 0.0;
-        if (kSpPrefetch && has_next) {
-            n_hu = __ldg(sp.hdr_in + nxt.u);
-            n_v = (lane < min(32, nxt.deg)) ? a.col[nxt.e0 + lane] : 0;
-        }
-
-        // ---- own row: scatter into fu_d ----
-        const uint64_t hu = kSpPrefetch ? (uint64_t)c_hu : __ldg(sp.hdr_in + u);
-        const int cu = (int)sp_cnt(hu);
-        const double *uval = sp.pool_in + sp_off8(hu);
-        const unsigned short *uidx = reinterpret_cast<const unsigned short *>(uval + sp_pad((uint32_t)cu));
-        double fusf = 0.0, fufu = 0.0;
+    // own row -> fu_d; returns fu.sumF and fu.fu through the references
+    __device__ __forceinline__ void scatter_own(int cu, const double *uval, const unsigned short *uidx, double &fusf, double &fufu) {
+        fusf = 0.0;
+        fufu = 0.0;
+#pragma unroll 1
         for (int i = lane; i < cu; i += 32) {
-            const bool first = kSpPrefetch && i < 32;
-            const double v = first ? c_val : __ldg(uval + i);
-            const int c = first ? c_idx : (int)__ldg(uidx + i);
+            const double v = __ldg(uval + i);
+            const int c = __ldg(uidx + i);
             fu_d[c] = v;
             fusf = fma(v, s_sumF[c], fusf);
             fufu = fma(v, v, fufu);
@@ -567,79 +465,168 @@ __global__ void __launch_bounds__(kSpThreads, kSpBlocksPerSM) sparse_step_kernel
         fusf = warp_sum(fusf);
         fufu = warp_sum(fufu);
         __syncwarp();
+    }
 
-        const bool in_uset = (a.node_mask == nullptr) || (a.node_mask[u] != 0);
-        const bool want_ls = a.do_linesearch && in_uset && deg > 0;
+    // One node, start to finish.  colp: the node's neighbour list (ids in the low 28 bits when it comes from tcol).
+    template <bool kPush>
+    __device__ __forceinline__ void node(int64_t u, int deg, const int32_t *colp) {
+        const uint64_t hu = __ldg(sp->hdr_in + u);
+        const int cu = (int)sp_cnt(hu);
+        const double *uval = sp->pool_in + sp_off8(hu);
+        const unsigned short *uidx = sp_idx(uval, (uint32_t)cu);
+        double fusf, fufu;
+        scatter_own(cu, uval, uidx, fusf, fufu);
+        const bool in_uset = (a->node_mask == nullptr) || (a->node_mask[u] != 0);
+        const bool want_ls = a->do_linesearch && in_uset && deg > 0;
+        const int nsteps = a->nsteps;
+        const int j16 = lane & 15;
 
         // ---------------- PRE (:157-169) ----------------
         int nchunks, ne_last;
-        const double S1 = warp_sum(pre_range(e0, 0, deg, want_ls, nchunks, ne_last, kSpPrefetch ? 1 : 0, c_hv));
+        const double S1 = warp_sum(pre_range(colp, 0, deg, want_ls, nchunks, ne_last));
         const double llh_u = (S1 - fusf) + fufu;
-        llh_acc += llh_u;
-        // stage 2 of the prefetch: the next node's first entries and its neighbours' headers (stage 1 has landed)
-        if (kSpPrefetch && has_next) {
-            n_hv = (lane < min(32, nxt.deg)) ? __ldg(sp.hdr_in + n_v) : 0ull;
-            const int cun = (int)sp_cnt(n_hu);
-            const double *uvn = sp.pool_in + sp_off8(n_hu);
-            if (lane < cun) {
-                n_val = __ldg(uvn + lane);
-                n_idx = __ldg(reinterpret_cast<const unsigned short *>(uvn + sp_pad((uint32_t)cun)) + lane);
-            }
-        }
-
         int jstar = -1, m = 0;
         if (want_ls) {
             bool need_hi;
             const double G2 = scan_gradient(m, need_hi);
             // ---------------- LS (:172-182) ----------------
+#pragma unroll 1
             for (int tg = 0; tg < nsteps && jstar < 0; tg += 16) {
                 const int j = tg + j16;
                 const bool jok = j < nsteps;
                 const double s = s_steps[jok ? j : 0];
                 // a node whose neighbours fitted one chunk still has them staged from PRE
-                double sumterms = ls_range(e0, 0, deg, s, need_hi, (nchunks == 1 && tg == 0) ? ne_last : 0);
+                double sumterms = ls_range(colp, 0, deg, s, need_hi, (nchunks == 1 && tg == 0) ? ne_last : 0);
                 sumterms += __shfl_xor_sync(0xffffffffu, sumterms, 16);
                 jstar = decide(tg, s, jok, sumterms, m, need_hi, llh_u, G2);
             }
         }
-        if (a.do_linesearch) swap_row(u, jstar, m, cu, uval, uidx);
-        if (a.accepted != nullptr && lane == 0) a.accepted[u] = (int8_t)jstar;
-
-        // ---- leave the warp's dense vectors at zero for the next node ----
+        if (lane == 0) sp->node_llh[u] = llh_u;
+        if (a->do_linesearch) {
+            swap_row<kPush>(u, jstar, m, cu, uval, uidx);
+            if (lane == 0) sp->accepted[u] = (int8_t)jstar;
+        }
+        // ---- leave the dense vectors at zero for the next node ----
         __syncwarp();
+#pragma unroll 1
         for (int i = lane; i < cu; i += 32) fu_d[__ldg(uidx + i)] = 0.0;
         if (want_ls)
+#pragma unroll 1
             for (int c = lane; c < ldp; c += 32) g_d[c] = 0.0;
         __syncwarp();
-
-        cur = nxt;
-        nxt = nn;
-        pos = pos_n;
-        pos_n = pos_nn;
-        pos_nn = (int64_t)__shfl_sync(0xffffffffu, fetched, 0);
-        if (kSpPrefetch) { c_hu = n_hu; c_hv = n_hv; c_val = n_val; c_idx = n_idx; }
     }
 
-    // ---------------- block reduction of the partials ----------------
-    __syncthreads();
-    if (a.do_linesearch) {
-        for (int i = threadIdx.x; i < ld; i += nthreads) {
-            const double v = s_D[i];
-            if (v != 0.0) atomicAdd(a.partials + i, v);
+    // One item of a split hub (see above).
+    template <bool kPush>
+    __device__ __forceinline__ void hub_item(const HubItem item) {
+        const NodeMeta nm = a->meta[item.hub];
+        const int64_t u = nm.u, e0 = nm.e0;
+        const int deg = nm.deg;
+        const size_t hstride = sp_hub_stride(ld);
+        double *scr0 = a->hub_scratch + (size_t)item.mslot * hstride;            // mslot: first scratch slot of the hub
+        unsigned int *cnt = a->hub_counters + 2 * (size_t)item.hub;
+        const int sb = item.slice * kSpHubSeg, se = min(deg, sb + kSpHubSeg);
+        const uint64_t hu = __ldg(sp->hdr_in + u);
+        const int cu = (int)sp_cnt(hu);
+        const double *uval = sp->pool_in + sp_off8(hu);
+        const unsigned short *uidx = sp_idx(uval, (uint32_t)cu);
+        double fusf, fufu;
+        scatter_own(cu, uval, uidx, fusf, fufu);
+        const bool in_uset = (a->node_mask == nullptr) || (a->node_mask[u] != 0);
+        const bool want_ls = a->do_linesearch && in_uset;
+        const int j16 = lane & 15;
+        const int32_t *colp = a->col + e0;
+        double *tot = scr0 + (size_t)item.nslices * hstride;                      // the hub's combined slot
+        if (item.phase == 1) {
+            int nch, nel;
+            const double S1 = warp_sum(pre_range(colp, sb, se, want_ls, nch, nel));
+            double *scr = scr0 + (size_t)item.slice * hstride;
+            if (want_ls) {
+#pragma unroll 1
+                for (int c = lane; c < ld; c += 32) { scr[c] = g_d[c]; g_d[c] = 0.0; }
+            }
+            if (lane == 0) scr[ld] = S1;
+            __threadfence();
+            __syncwarp();
+            unsigned int old = 0;
+            if (lane == 0) old = atomicAdd(cnt, 1u);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == (unsigned int)item.nslices - 1u) {
+                // the last segment to arrive adds the slots up, in slot order: whichever warp does it, the sums
+                // are the same bits
+                __threadfence();
+                if (want_ls) {
+#pragma unroll 1
+                    for (int c = lane; c < ld; c += 32) {
+                        double v = 0.0;
+#pragma unroll 1
+                        for (int sl = 0; sl < item.nslices; ++sl) v += __ldcg(scr0 + (size_t)sl * hstride + c);
+                        tot[c] = v;
+                    }
+                }
+                if (lane == 0) {
+                    double v = 0.0;
+#pragma unroll 1
+                    for (int sl = 0; sl < item.nslices; ++sl) v += __ldcg(scr0 + (size_t)sl * hstride + ld);
+                    tot[ld] = v;
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(cnt, 1u);
+            }
+        } else {
+            if (lane == 0) {
+                const unsigned int *c = cnt + (item.phase == 2 ? 0 : 1);
+                const unsigned int target = (unsigned int)item.nslices + (item.phase == 2 ? 1u : 0u);
+                while (*reinterpret_cast<const volatile unsigned int *>(c) < target) __nanosleep(200);
+                __threadfence();
+            }
+            __syncwarp();
+            const double llh_u = (__ldcg(tot + ld) - fusf) + fufu;
+            int m = 0, jstar = -1;
+            bool need_hi = false;
+            double G2 = 0.0;
+            if (want_ls) {
+#pragma unroll 1
+                for (int c = lane; c < ldp; c += 32) g_d[c] = (c < ld) ? __ldcg(tot + c) : 0.0;
+                __syncwarp();
+                G2 = scan_gradient(m, need_hi);
+            }
+            const int nsteps = a->nsteps;
+            const double s = s_steps[j16 < nsteps ? j16 : 0];       // hubs are only split when nsteps <= 16
+            if (item.phase == 2) {
+                if (want_ls) {
+                    double st = ls_range(colp, sb, se, s, need_hi, 0);
+                    st += __shfl_xor_sync(0xffffffffu, st, 16);
+                    if (lane < 16) scr0[(size_t)item.slice * hstride + ld + 1 + lane] = st;
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(cnt + 1, 1u);
+            } else {
+                if (want_ls) {
+                    double st = 0.0;
+#pragma unroll 1
+                    for (int sl = 0; sl < item.nslices; ++sl) st += __ldcg(scr0 + (size_t)sl * hstride + ld + 1 + j16);
+                    jstar = decide(0, s, j16 < nsteps, st, m, need_hi, llh_u, G2);
+                }
+                if (lane == 0) sp->node_llh[u] = llh_u;
+                if (a->do_linesearch) {
+                    swap_row<kPush>(u, jstar, m, cu, uval, uidx);
+                    if (lane == 0) sp->accepted[u] = (int8_t)jstar;
+                }
+            }
+            __syncwarp();
+            if (want_ls)
+#pragma unroll 1
+                for (int c = lane; c < ldp; c += 32) g_d[c] = 0.0;
         }
+        __syncwarp();
+#pragma unroll 1
+        for (int i = lane; i < cu; i += 32) fu_d[__ldg(uidx + i)] = 0.0;
+        __syncwarp();
     }
-    __shared__ double s_red[2 * kSpWarps];
-    if (lane == 0) { s_red[wib] = llh_acc; s_red[kSpWarps + wib] = nupd_acc; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double l = 0.0, c = 0.0;
-#pragma unroll
-        for (int w = 0; w < kSpWarps; ++w)
-            if (w < wpb) { l += s_red[w]; c += s_red[kSpWarps + w]; }
-        atomicAdd(a.partials + 2 * ld, l);
-        if (c != 0.0) atomicAdd(a.partials + 2 * ld + 1, c);
-    }
-}
+};
 
 // Dense n x ld rows -> sparse rows (one warp per row; non-zeros in ascending component order).
 __global__ void dense_to_sparse_kernel(const double *F, int64_t n, int ld, uint64_t *hdr, double *pool,
@@ -663,7 +650,7 @@ __global__ void dense_to_sparse_kernel(const double *F, int64_t n, int ld, uint6
         return;
     }
     double *ov = pool + off;
-    unsigned short *oi = reinterpret_cast<unsigned short *>(ov + sp_pad((uint32_t)cnt));
+    unsigned short *oi = sp_idx(ov, (uint32_t)cnt);
     int p = 0;
     for (int c0 = 0; c0 < ld; c0 += 32) {
         const int c = c0 + lane;
@@ -697,7 +684,8 @@ inline int64_t sp_host_pack(int64_t n, int32_t k, int32_t ld, const int64_t *ind
         const uint64_t words = sp_words(cnt);
         if (top + words > pool_cap8) return -2;
         double *ov = pool + top;
-        unsigned short *oi = reinterpret_cast<unsigned short *>(ov + sp_pad(cnt));
+        unsigned short *oi = sp_idx(ov, cnt);
+        for (uint64_t z = 0; z < words; ++z) ov[z] = 0.0;
         uint32_t q = 0;
         for (int64_t i = indptr[u]; i < indptr[u + 1]; ++i) {
             if (values[i] == 0.0) continue;
@@ -709,7 +697,6 @@ inline int64_t sp_host_pack(int64_t n, int32_t k, int32_t ld, const int64_t *ind
             ++q;
             if (colsum != nullptr) colsum[indices[i]] += values[i];
         }
-        for (uint32_t z = cnt; z < sp_pad(cnt); ++z) { ov[z] = 0.0; oi[z] = 0; }
         hdr[u] = sp_pack(cnt ? top : 0, cnt);
         top += words;
     }
@@ -728,7 +715,7 @@ inline void sp_host_unpack(int64_t n, const uint64_t *hdr, const double *pool, i
         indptr[u] = t;
         const uint32_t cnt = sp_cnt(hdr[u]);
         const double *ov = pool + sp_off8(hdr[u]);
-        const unsigned short *oi = reinterpret_cast<const unsigned short *>(ov + sp_pad(cnt));
+        const unsigned short *oi = sp_idx(ov, cnt);
         for (uint32_t i = 0; i < cnt; ++i) { indices[t] = oi[i]; values[t] = ov[i]; ++t; }
     }
     indptr[n] = t;
@@ -745,7 +732,7 @@ __global__ void sparse_to_dense_kernel(const uint64_t *hdr, const double *pool, 
     const uint64_t h = hdr[u];
     const int cnt = (int)sp_cnt(h);
     const double *vals = pool + sp_off8(h);
-    const unsigned short *idx = reinterpret_cast<const unsigned short *>(vals + sp_pad((uint32_t)cnt));
+    const unsigned short *idx = sp_idx(vals, (uint32_t)cnt);
     for (int i = lane; i < cnt; i += 32) row[idx[i]] = vals[i];
 }
 

@@ -1,0 +1,896 @@
+// bigclam_tile.cuh — the sparse-row step kernel: small nodes in TILES, the rest on the general path, and the
+// deterministic reduction that follows every launch.
+//
+// Why tiles: com-amazon has a mean degree of 5.5 and rows of ~10 non-zeros — a warp that owns ONE such node
+// spends most of its issue slots with 5 of 32 lanes busy (the one-warp-per-node kernels execute 2,900 warp
+// instructions per node, see profiles/r2_sparse_warp_per_node_ncu.txt).  A tile is a run of up to 8 consecutive
+// nodes of the degree-sorted processing order with at most 32 edges in total, handled by one warp; every phase
+// maps its work items flat onto the 32 lanes:
+//   stage   one bulk copy (cp.async.bulk.shared::cluster.global + mbarrier) per neighbour row and per own row;
+//   PRE     lane = edge: x_e = fu . fv_e with fu looked up through the node's bitmask of non-zero components
+//           (rank = popcount below the bit), exp/log once for 32 edges of up to 8 nodes;
+//   slots   the components a node touches (its own and its neighbours' non-zeros) get consecutive slots in
+//           ascending component order (bitmask + prefix popcounts): slot s holds (fu_c, grad_c);
+//   axpy    lane groups of 32/nn lanes per node add w_e * fv_e into the slots, edge by edge (CSR order);
+//   LS      lane = (edge parity, trial): dots over the ACTIVE entries only; (edge, trial) pairs whose x is
+//           outside (x_lo, x_hi) are constants after the clamp (:166), the others are compacted and exp/log runs
+//           on full warps of them (about half of the 16 x deg pairs on the bench workload);
+//   decide  lane = (node, trial); swap: rows written by the node's lane group, one pool allocation per tile.
+// A tile whose rows or touched components do not fit the warp's shared memory is processed node by node on the
+// general path (SpGen) by the same warp; nodes above 32 edges always are.
+#pragma once
+#include "bigclam_sparse.cuh"
+
+namespace bigclam {
+
+constexpr int kTlMaxNodes = 8;
+constexpr int kTlMaxEdges = 32;
+#ifndef BIGCLAM_TL_STAGE16          // row staging buffer of a tile, in 16-byte chunks (neighbour rows + own rows)
+#define BIGCLAM_TL_STAGE16 320
+#endif
+#ifndef BIGCLAM_TL_SLOTS            // touched components of all nodes of a tile
+#define BIGCLAM_TL_SLOTS 256
+#endif
+#ifndef BIGCLAM_TL_BULK             // 1: cp.async.bulk + mbarrier; 0: each lane copies its rows with 16-byte loads
+#define BIGCLAM_TL_BULK 1
+#endif
+#ifndef BIGCLAM_TL_ILP2             // 1: the exp/log pass of the line search evaluates two pairs per lane (two independent chains)
+#define BIGCLAM_TL_ILP2 0
+#endif
+#ifndef BIGCLAM_TL_WARPS
+#define BIGCLAM_TL_WARPS 8
+#endif
+#ifndef BIGCLAM_TL_BLOCKS
+#define BIGCLAM_TL_BLOCKS 2
+#endif
+constexpr int kTlStage16 = BIGCLAM_TL_STAGE16;
+constexpr int kTlSlots = BIGCLAM_TL_SLOTS;
+constexpr int kTlWarps = BIGCLAM_TL_WARPS;
+constexpr int kTlBlocksPerSM = BIGCLAM_TL_BLOCKS;
+constexpr int kTlThreads = kTlWarps * 32;
+
+// per-warp shared memory of the tile path (W = ldp / 32 mask words per node)
+__host__ __device__ inline size_t tl_warp_bytes(int ld) {
+    const size_t W = (size_t)sp_ldp(ld) / 32;
+    size_t b = 16 * (size_t)kTlStage16;                 // stage
+    b += 16 * (size_t)kTlSlots;                         // fg
+    b += 8 * 256;                                       // xs
+    b += 8 * 32 + 8 * 8 + 8 * 8;                        // we, n_llh, n_G2
+    b += 4 * 2 * kTlMaxNodes * W + 4 * kTlMaxNodes;     // tmask, fmask, n_u
+    b += 2 * 2 * (size_t)kTlSlots;                      // slot_c, alist
+    b += 2 * 2 * kTlMaxNodes * W;                       // pref_t, pref_f
+    b += 2 * (40 + 40 + 12 + 12 + 8 + 8);               // e_soff, e_cnt, n_es, n_sb, n_m, n_tot
+    b += 32 + 256 + 8 + 8;                              // e_acnt, plist, n_js, n_want
+    return (b + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t tl_region_bytes(int ld) {
+    const size_t t = tl_warp_bytes(ld), g = (sp_gen_warp_bytes(ld) + 15) & ~(size_t)15;
+    return t > g ? t : g;
+}
+// block: steps[kMaxSteps] | sumF[ldp] | mbar[kTlWarps] | wpb x warp region
+__host__ __device__ inline size_t tl_block_smem_bytes(int ld, int wpb) {
+    return sizeof(double) * (kMaxSteps + (size_t)sp_ldp(ld) + kTlWarps) + (size_t)wpb * tl_region_bytes(ld);
+}
+// warps per block: as many resident warps per SM as the shared memory (227 KB, 1 KB reserved per block) allows
+inline int tl_warps_per_block(int ld) {
+    int best = 1, best_warps = 0;
+    for (int wpb = kTlWarps; wpb >= 1; wpb >>= 1) {
+        const size_t bytes = tl_block_smem_bytes(ld, wpb) + 1024 + 256;
+        const int blocks = (int)((size_t)233472 / bytes);
+        const int warps = (blocks > kTlBlocksPerSM ? kTlBlocksPerSM : blocks) * wpb;
+        if (warps > best_warps) { best_warps = warps; best = wpb; }
+    }
+    return best;
+}
+
+// ---- mbarrier / bulk-copy primitives (host emulation: the copy happens at once) ----
+#if defined(BIGCLAM_EMU)
+__device__ __forceinline__ void mbar_init(unsigned long long *) {}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *, unsigned) {}
+__device__ __forceinline__ void mbar_wait(unsigned long long *, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void fence_proxy_async() {}
+#else
+__device__ __forceinline__ void mbar_init(unsigned long long *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
+struct TlWarp {
+    const StepArgs *a;
+    const SparseArgs *sp;
+    const double *s_steps;
+    const double *s_sumF;
+    double S2_all;                   // sum_c sumF_c^2 (fixed order)
+    EdgeConst ec;
+    unsigned char *stage;
+    double2 *fg;
+    double *xs, *we, *n_llh, *n_G2;
+    unsigned long long *mbar;
+    unsigned int *tmask, *fmask;
+    int *n_u;
+    unsigned short *slot_c, *alist, *pref_t, *pref_f, *e_soff, *e_cnt, *n_es, *n_sb, *n_m, *n_tot;
+    unsigned char *e_acnt, *plist, *n_want;
+    signed char *n_js;
+    int lane, ld, W;
+    unsigned parity;
+
+    __device__ __forceinline__ void carve(unsigned char *p, int ld_, int lane_) {
+        ld = ld_;
+        lane = lane_;
+        W = sp_ldp(ld_) / 32;
+        parity = 0;
+        stage = p;                                 p += 16 * (size_t)kTlStage16;
+        fg = reinterpret_cast<double2 *>(p);       p += 16 * (size_t)kTlSlots;
+        xs = reinterpret_cast<double *>(p);        p += 8 * 256;
+        we = reinterpret_cast<double *>(p);        p += 8 * 32;
+        n_llh = reinterpret_cast<double *>(p);     p += 8 * 8;
+        n_G2 = reinterpret_cast<double *>(p);      p += 8 * 8;
+        tmask = reinterpret_cast<unsigned int *>(p);      p += 4 * (size_t)kTlMaxNodes * W;
+        fmask = reinterpret_cast<unsigned int *>(p);      p += 4 * (size_t)kTlMaxNodes * W;
+        n_u = reinterpret_cast<int *>(p);                 p += 4 * kTlMaxNodes;
+        slot_c = reinterpret_cast<unsigned short *>(p);   p += 2 * (size_t)kTlSlots;
+        alist = reinterpret_cast<unsigned short *>(p);    p += 2 * (size_t)kTlSlots;
+        pref_t = reinterpret_cast<unsigned short *>(p);   p += 2 * (size_t)kTlMaxNodes * W;
+        pref_f = reinterpret_cast<unsigned short *>(p);   p += 2 * (size_t)kTlMaxNodes * W;
+        e_soff = reinterpret_cast<unsigned short *>(p);   p += 2 * 40;
+        e_cnt = reinterpret_cast<unsigned short *>(p);    p += 2 * 40;
+        n_es = reinterpret_cast<unsigned short *>(p);     p += 2 * 12;
+        n_sb = reinterpret_cast<unsigned short *>(p);     p += 2 * 12;
+        n_m = reinterpret_cast<unsigned short *>(p);      p += 2 * 8;
+        n_tot = reinterpret_cast<unsigned short *>(p);    p += 2 * 8;
+        e_acnt = p;                                       p += 32;
+        plist = p;                                        p += 256;
+        n_js = reinterpret_cast<signed char *>(p);        p += 8;
+        n_want = p;
+    }
+
+    // inclusive scan over the lanes of a group of gs lanes (sub = lane within the group)
+    __device__ __forceinline__ int group_scan(int v, int gs, int sub) const {
+        for (int o = 1; o < gs; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (sub >= o) v += t;
+        }
+        return v;
+    }
+    __device__ __forceinline__ double group_sum(double v, int gs) const {
+        for (int o = 16; o > 0; o >>= 1)
+            if (o < gs) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+
+    // One tile.  Returns false (nothing written) when the tile does not fit the warp's buffers.
+    template <bool kPush>
+    __device__ __forceinline__ bool run(const TileMeta tm) {
+        const int nn = tm.nn, ne = tm.ne;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        const uint64_t *__restrict__ hdr_in = sp->hdr_in;
+        const double *__restrict__ pool_in = sp->pool_in;
+        const bool do_ls = a->do_linesearch != 0;
+        const int nsteps = a->nsteps;
+        const double max_f = a->max_f;
+
+        // ---------------- A. metadata, row headers, staging ----------------
+        int ni = 0;
+        uint64_t hv = 0ull, hu = 0ull;
+        NodeMeta nm = {0, 0, 0};
+        if (lane < ne) {
+            const int t = sp->tcol[tm.ecol0 + lane];
+            ni = (int)((unsigned)t >> 28);
+            hv = __ldg(hdr_in + (t & 0x0fffffff));
+        }
+        if (lane < nn) {
+            nm = a->meta[tm.pos0 + lane];
+            hu = __ldg(hdr_in + nm.u);
+        }
+        const int ce = (int)sp_cnt(hv), cu = (int)sp_cnt(hu);
+        const int qe = (int)(sp_words((uint32_t)ce) >> 1), qu = (int)(sp_words((uint32_t)cu) >> 1);     // 16-byte chunks
+        int incl_e = qe, incl_u = qu, incl_d = nm.deg, maxdeg = nm.deg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t1 = __shfl_up_sync(0xffffffffu, incl_e, o);
+            const int t2 = __shfl_up_sync(0xffffffffu, incl_u, o);
+            const int t3 = __shfl_up_sync(0xffffffffu, incl_d, o);
+            const int t4 = __shfl_xor_sync(0xffffffffu, maxdeg, o);
+            if (lane >= o) { incl_e += t1; incl_u += t2; incl_d += t3; }
+            maxdeg = max(maxdeg, t4);
+        }
+        const int total_e = __shfl_sync(0xffffffffu, incl_e, 31);
+        const int total16 = total_e + __shfl_sync(0xffffffffu, incl_u, 31);
+        if (total16 > kTlStage16) return false;
+        const int soff_e = incl_e - qe, soff_u = total_e + incl_u - qu;
+        if (lane < ne) { e_soff[lane] = (unsigned short)soff_e; e_cnt[lane] = (unsigned short)ce; }
+        if (lane < nn) {
+            e_soff[32 + lane] = (unsigned short)soff_u;
+            e_cnt[32 + lane] = (unsigned short)cu;
+            n_u[lane] = nm.u;
+            n_es[lane] = (unsigned short)(incl_d - nm.deg);
+            if (lane == nn - 1) n_es[nn] = (unsigned short)incl_d;
+            const bool in_uset = (a->node_mask == nullptr) || (a->node_mask[nm.u] != 0);
+            n_want[lane] = (unsigned char)(do_ls && in_uset && nm.deg > 0);
+        }
+#pragma unroll 1
+        for (int i = lane; i < nn * W; i += 32) { tmask[i] = 0u; fmask[i] = 0u; }
+#if BIGCLAM_TL_BULK
+        if (total16 > 0) {
+            fence_proxy_async();                         // this warp's earlier accesses to the stage come first
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(mbar, 16u * (unsigned)total16);
+            __syncwarp();
+            if (qe > 0) bulk_g2s(stage + 16 * (size_t)soff_e, pool_in + sp_off8(hv), 16u * (unsigned)qe, mbar);
+            if (qu > 0) bulk_g2s(stage + 16 * (size_t)soff_u, pool_in + sp_off8(hu), 16u * (unsigned)qu, mbar);
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
+        }
+#else
+        {
+            const uint4 *se = reinterpret_cast<const uint4 *>(pool_in + sp_off8(hv));
+            uint4 *de = reinterpret_cast<uint4 *>(stage) + soff_e;
+#pragma unroll 1
+            for (int q = 0; q < qe; ++q) de[q] = __ldg(se + q);
+            const uint4 *su = reinterpret_cast<const uint4 *>(pool_in + sp_off8(hu));
+            uint4 *du = reinterpret_cast<uint4 *>(stage) + soff_u;
+#pragma unroll 1
+            for (int q = 0; q < qu; ++q) du[q] = __ldg(su + q);
+        }
+#endif
+        __syncwarp();
+
+        // ---------------- B. own rows: masks of the non-zero components, fu.sumF, fu.fu ----------------
+        const int lgs = nn <= 1 ? 5 : nn <= 2 ? 4 : nn <= 4 ? 3 : 2;          // lanes per node: 32 / pow2(nn)
+        const int gs = 1 << lgs;
+        const int g = lane >> lgs, sub = lane & (gs - 1);
+        const bool gv = g < nn;
+        const unsigned gmask = gs == 32 ? 0xffffffffu : ((1u << gs) - 1u);
+        const int gW = g * W;
+        const int cu_g = gv ? (int)e_cnt[32 + g] : 0;
+        double *ov = reinterpret_cast<double *>(stage + 16 * (size_t)(gv ? e_soff[32 + g] : 0));
+        const unsigned short *oi = sp_idx(ov, (uint32_t)cu_g);
+        double fusf = 0.0, fufu = 0.0;
+#pragma unroll 1
+        for (int i = sub; i < cu_g; i += gs) {
+            const int c = oi[i];
+            const double val = ov[i];
+            atomicOr(fmask + gW + (c >> 5), 1u << (c & 31));
+            fusf = fma(val, s_sumF[c], fusf);
+            fufu = fma(val, val, fufu);
+        }
+        fusf = group_sum(fusf, gs);
+        fufu = group_sum(fufu, gs);
+        __syncwarp();
+        {
+            int carry = 0;
+#pragma unroll 1
+            for (int w0 = 0; w0 < W; w0 += gs) {
+                const int w = w0 + sub;
+                const bool ok = gv && w < W;
+                const unsigned mk = ok ? fmask[gW + w] : 0u;
+                const int pc = __popc(mk);
+                const int incl = group_scan(pc, gs, sub);
+                if (ok) { pref_f[gW + w] = (unsigned short)(carry + incl - pc); tmask[gW + w] = mk; }
+                carry += __shfl_sync(0xffffffffu, incl, (g << lgs) + gs - 1);
+            }
+        }
+        __syncwarp();
+
+        // ---------------- C. PRE dots (:162-165), lane = edge ----------------
+        double *rv = reinterpret_cast<double *>(stage + 16 * (size_t)soff_e);
+        unsigned short *ri = sp_idx(rv, (uint32_t)ce);
+        double x = 0.0;
+        if (lane < ne) {
+            const unsigned int *fm = fmask + ni * W;
+            unsigned int *tmk = tmask + ni * W;
+            const unsigned short *pf = pref_f + ni * W;
+            const double *ove = reinterpret_cast<const double *>(stage + 16 * (size_t)e_soff[32 + ni]);
+#pragma unroll 1
+            for (int i = 0; i < ce; ++i) {
+                const int c = ri[i];
+                const int w = c >> 5;
+                const unsigned bit = 1u << (c & 31);
+                atomicOr(tmk + w, bit);
+                const unsigned fmw = fm[w];
+                if (fmw & bit) x = fma(rv[i], ove[pf[w] + __popc(fmw & (bit - 1u))], x);
+            }
+        }
+        // ---------------- D. edge terms (:166-167), llh_u (:168) ----------------
+        double wgt;
+        const double term = edge_term<true>(x, ec, wgt);
+        xs[lane] = term;
+        we[lane] = wgt;
+        __syncwarp();
+        const int es_g = gv ? (int)n_es[g] : 0;
+        const int deg_g = gv ? (int)n_es[g + 1] - es_g : 0;
+        double llh_g = 0.0;
+        {
+            double S1 = 0.0;
+#pragma unroll 1
+            for (int e = es_g; e < es_g + deg_g; ++e) S1 += xs[e];            // CSR order, like the reference's fold
+            llh_g = (S1 - fusf) + fufu;
+        }
+        if (!do_ls) {
+            if (gv && sub == 0) sp->node_llh[n_u[g]] = llh_g;
+            __syncwarp();
+            return true;
+        }
+        if (gv && sub == 0) n_llh[g] = llh_g;
+
+        // ---------------- E. slots of the touched components ----------------
+        int tot_g = 0;
+        {
+            int carry = 0;
+#pragma unroll 1
+            for (int w0 = 0; w0 < W; w0 += gs) {
+                const int w = w0 + sub;
+                const bool ok = gv && w < W;
+                const int pc = ok ? __popc(tmask[gW + w]) : 0;
+                const int incl = group_scan(pc, gs, sub);
+                if (ok) pref_t[gW + w] = (unsigned short)(carry + incl - pc);
+                carry += __shfl_sync(0xffffffffu, incl, (g << lgs) + gs - 1);
+            }
+            tot_g = gv ? carry : 0;
+        }
+        int base_g = 0, total_slots = 0, maxtot = 0;
+#pragma unroll 1
+        for (int q = 0; q < nn; ++q) {
+            const int t = __shfl_sync(0xffffffffu, tot_g, q << lgs);
+            if (q < g) base_g += t;
+            total_slots += t;
+            maxtot = max(maxtot, t);
+        }
+        if (total_slots > kTlSlots) return false;
+        if (gv && sub == 0) { n_sb[g] = (unsigned short)base_g; n_tot[g] = (unsigned short)tot_g; }
+#pragma unroll 1
+        for (int i = lane; i < total_slots; i += 32) fg[i] = make_double2(0.0, 0.0);
+        __syncwarp();
+        // ---------------- F. own row -> slots ----------------
+#pragma unroll 1
+        for (int i = sub; i < cu_g; i += gs) {
+            const int c = oi[i];
+            const int w = c >> 5;
+            const unsigned bit = 1u << (c & 31);
+            const int slot = base_g + pref_t[gW + w] + __popc(tmask[gW + w] & (bit - 1u));
+            fg[slot].x = ov[i];
+            slot_c[slot] = (unsigned short)c;
+        }
+        __syncwarp();
+        // ---------------- G. sum_v fv / (1 - p) (:167-168), edge by edge in CSR order; entries -> slot ids ----------------
+#pragma unroll 1
+        for (int r = 0; r < maxdeg; ++r) {
+            if (r < deg_g) {
+                const int e = es_g + r;
+                const double wv = we[e];
+                const int cn = e_cnt[e];
+                double *vv = reinterpret_cast<double *>(stage + 16 * (size_t)e_soff[e]);
+                unsigned short *vi = sp_idx(vv, (uint32_t)cn);
+#pragma unroll 1
+                for (int i = sub; i < cn; i += gs) {
+                    const int c = vi[i];
+                    const int w = c >> 5;
+                    const unsigned bit = 1u << (c & 31);
+                    const int slot = base_g + pref_t[gW + w] + __popc(tmask[gW + w] & (bit - 1u));
+                    fg[slot].y = fma(wv, vv[i], fg[slot].y);
+                    slot_c[slot] = (unsigned short)c;
+                    vi[i] = (unsigned short)slot;
+                }
+            }
+            __syncwarp();
+        }
+        // ---------------- H. gradient (:168), |g|^2, active components ----------------
+        int m_g = 0;
+        bool hi_lane = false;
+        {
+            double G2 = 0.0, SF2 = 0.0;
+#pragma unroll 1
+            for (int k0 = 0; k0 < maxtot; k0 += gs) {
+                const int k = k0 + sub;
+                const bool ok = k < tot_g;
+                const int slot = base_g + k;
+                bool act = false;
+                if (ok) {
+                    const double2 v = fg[slot];
+                    const double sf = s_sumF[slot_c[slot]];
+                    const double gr = (v.y - sf) + v.x;
+                    fg[slot].y = gr;
+                    G2 = fma(gr, gr, G2);
+                    SF2 = fma(sf, sf, SF2);
+                    act = (v.x > 0.0 || gr > 0.0);
+                    hi_lane |= act && (v.x + gr > max_f);
+                }
+                const unsigned gb = (__ballot_sync(0xffffffffu, act) >> (g << lgs)) & gmask;
+                if (act) alist[base_g + m_g + __popc(gb & ((1u << sub) - 1u))] = (unsigned short)slot;
+                m_g += __popc(gb);
+            }
+            G2 = group_sum(G2, gs);
+            SF2 = group_sum(SF2, gs);
+            // an untouched component has fu = 0 and gradient -sumF_c: its square is part of S2_all
+            if (gv && sub == 0) { n_G2[g] = (S2_all - SF2) + G2; n_m[g] = (unsigned short)m_g; }
+        }
+        int maxm = m_g;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxm = max(maxm, __shfl_xor_sync(0xffffffffu, maxm, o));
+        // no candidate of any node of the tile can reach MAX_F_ (the largest step is 1): the upper clamp is dropped
+        const bool need_hi = __any_sync(0xffffffffu, hi_lane);
+        __syncwarp();
+        // ---------------- I. neighbour rows shrink to their entries on active components ----------------
+        if (lane < ne) {
+            int p = 0;
+#pragma unroll 1
+            for (int i = 0; i < ce; ++i) {
+                const int slot = ri[i];
+                const double2 v = fg[slot];
+                if (v.x > 0.0 || v.y > 0.0) {
+                    rv[p] = rv[i];
+                    ri[p] = (unsigned short)slot;
+                    ++p;
+                }
+            }
+            e_acnt[lane] = (unsigned char)p;
+        }
+        __syncwarp();
+        // ---------------- J. line search (:172-180): 16 candidates x edges, 16 edges at a time ----------------
+        const int h = lane >> 4, j = lane & 15;
+        const double s = s_steps[j < nsteps ? j : 0];
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+        for (int hb = 0; hb < ne; hb += 16) {
+            int np = 0;
+#pragma unroll 1
+            for (int r = 0; r < 8; ++r) {
+                if (hb + 2 * r >= ne) break;
+                const int e = hb + 2 * r + h;
+                const bool valid = e < ne;
+                double D = 0.0;
+                if (valid) {
+                    const int ac = e_acnt[e];
+                    const double *vv = reinterpret_cast<const double *>(stage + 16 * (size_t)e_soff[e]);
+                    const unsigned short *vi = sp_idx(vv, (uint32_t)e_cnt[e]);
+                    if (!need_hi) {
+#pragma unroll 1
+                        for (int k = 0; k < ac; ++k) {
+                            const double2 v = fg[vi[k]];
+                            D = fma(clamp_step0_lo(v.x, s, v.y), vv[k], D);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int k = 0; k < ac; ++k) {
+                            const double2 v = fg[vi[k]];
+                            D = fma(clamp_step0(v.x, s, v.y, max_f), vv[k], D);
+                        }
+                    }
+                }
+                const bool low = D <= ec.x_lo;
+                const bool inr = valid && !low && (D < ec.x_hi);
+                const int pid = (2 * r + h) * 16 + j;
+                if (valid) xs[pid] = inr ? D : (low ? ec.t_lo : ec.t_hi) + D;
+                const unsigned bal = __ballot_sync(0xffffffffu, inr);
+                if (inr) plist[np + __popc(bal & lt_mask)] = (unsigned char)pid;
+                np += __popc(bal);
+            }
+            __syncwarp();
+#pragma unroll 1
+#if BIGCLAM_TL_ILP2
+            for (int b = 0; b < np; b += 64) {          // exp/log on full warps of the pairs that need it, two per lane
+                const int k1 = b + lane, k2 = b + 32 + lane;
+                const bool ok1 = k1 < np, ok2 = k2 < np;
+                const int pid1 = ok1 ? (int)plist[k1] : 0, pid2 = ok2 ? (int)plist[k2] : 0;
+                const double x1 = ok1 ? xs[pid1] : 1.0, x2 = ok2 ? xs[pid2] : 1.0;
+                const double o1 = 1.0 - exp_neg(x1), o2 = 1.0 - exp_neg(x2);
+                const double t1 = log_pos(o1) + x1, t2 = log_pos(o2) + x2;
+                if (ok1) xs[pid1] = t1;
+                if (ok2) xs[pid2] = t2;
+            }
+#else
+            for (int b = 0; b < np; b += 32) {          // exp/log on full warps of the pairs that need it
+                const int k = b + lane;
+                const bool ok = k < np;
+                const int pid = ok ? (int)plist[k] : 0;
+                const double xv = ok ? xs[pid] : 1.0;
+                const double omp = 1.0 - exp_neg(xv);
+                const double t = log_pos(omp) + xv;
+                if (ok) xs[pid] = t;
+            }
+#endif
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {               // lane = (node 2q + h, trial j): its edges of this half, in order
+                const int node = 2 * q + h;
+                if (node < nn) {
+                    const int e_lo = max((int)n_es[node], hb), e_hi = min((int)n_es[node + 1], hb + 16);
+#pragma unroll 1
+                    for (int e = e_lo; e < e_hi; ++e) acc[q] += xs[(e - hb) * 16 + j];
+                }
+            }
+            __syncwarp();
+        }
+        // ---------------- K. Armijo test (:181), largest passing step (:182) ----------------
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int node = 2 * q + h;
+            const bool nv = node < nn;
+            double oa = 0.0, ob = 0.0;
+            if (nv) {
+                const int mb = n_sb[node], mm = n_m[node];
+#pragma unroll 1
+                for (int t = 0; t < mm; ++t) {
+                    const int slot = alist[mb + t];
+                    const double2 v = fg[slot];
+                    const double nf = need_hi ? clamp_step0(v.x, s, v.y, max_f) : clamp_step0_lo(v.x, s, v.y);
+                    const double sf = (s_sumF[slot_c[slot]] - v.x) + nf;          // sfT = (sumF - fu) + newfu   (:176)
+                    oa = fma(nf, sf, oa);
+                    ob = fma(nf, nf, ob);
+                }
+            }
+            bool pass = false;
+            if (nv) {
+                const double result = (acc[q] - oa) + ob;
+                const double rhs = n_llh[node] + (a->alpha * s) * n_G2[node];
+                pass = (j < nsteps) && (n_want[node] != 0) && (result >= rhs);
+            }
+            const unsigned mine = (__ballot_sync(0xffffffffu, pass) >> (16 * h)) & 0xffffu;
+            if (nv && j == 0) n_js[node] = (signed char)(mine ? __ffs(mine) - 1 : -1);
+        }
+        __syncwarp();
+        // ---------------- L. new rows (:183-190) and delta blocks (:191-192) ----------------
+        const int js = gv ? (int)n_js[g] : -1;
+        const double sstar = s_steps[js >= 0 ? js : 0];
+        int nz = 0, nd = 0;
+#pragma unroll 1
+        for (int t0 = 0; t0 < maxm; t0 += gs) {
+            const int t = t0 + sub;
+            bool isnz = false, ch = false;
+            if (js >= 0 && t < m_g) {
+                const double2 v = fg[alist[base_g + t]];
+                const double nr = clamp_step(v.x, sstar, v.y, a->min_f, max_f);
+                isnz = nr != 0.0;
+                ch = v.x != nr;
+            }
+            nz += __popc((__ballot_sync(0xffffffffu, isnz) >> (g << lgs)) & gmask);
+            nd += __popc((__ballot_sync(0xffffffffu, ch) >> (g << lgs)) & gmask);
+        }
+        if (js < 0) { nz = cu_g; nd = 0; }
+        const int wrow = gv ? (int)sp_words((uint32_t)nz) : 0;
+        const int words_g = gv ? wrow + (nd > 0 ? (int)sp_words((uint32_t)nd) : 0) : 0;
+        int woff = 0, wtotal = 0;
+#pragma unroll 1
+        for (int q = 0; q < nn; ++q) {
+            const int t = __shfl_sync(0xffffffffu, words_g, q << lgs);
+            if (q < g) woff += t;
+            wtotal += t;
+        }
+        unsigned long long rel = 0;
+        if (lane == 0 && wtotal > 0) rel = atomicAdd(sp->pool_top, (unsigned long long)wtotal);
+        rel = __shfl_sync(0xffffffffu, rel, 0);
+        if (rel + (unsigned long long)wtotal > sp->pool_cap8) {
+            if (gv && sub == 0) { *sp->overflow = 1; sp->hdr_out[n_u[g]] = sp_pack(0, 0); sp->dcnt[n_u[g]] = 0; }
+            __syncwarp();
+            return true;
+        }
+        const unsigned long long off = sp->region_base8 + rel + (unsigned long long)woff;
+        double *outv = sp->pool_out + off;
+        {
+            // accepted nodes: the candidate's non-zeros, ascending, and the delta block right behind the row
+            unsigned short *outi = sp_idx(outv, (uint32_t)nz);
+            double *dv = outv + wrow;
+            unsigned short *di = sp_idx(dv, (uint32_t)nd);
+            int pz = 0, pd = 0;
+#pragma unroll 1
+            for (int t0 = 0; t0 < maxm; t0 += gs) {
+                const int t = t0 + sub;
+                bool isnz = false, ch = false;
+                double nr = 0.0, f = 0.0;
+                int c = 0;
+                if (js >= 0 && t < m_g) {
+                    const int slot = alist[base_g + t];
+                    const double2 v = fg[slot];
+                    c = slot_c[slot];
+                    f = v.x;
+                    nr = clamp_step(f, sstar, v.y, a->min_f, max_f);
+                    isnz = nr != 0.0;
+                    ch = f != nr;
+                }
+                const unsigned bz = (__ballot_sync(0xffffffffu, isnz) >> (g << lgs)) & gmask;
+                const unsigned bd = (__ballot_sync(0xffffffffu, ch) >> (g << lgs)) & gmask;
+                const unsigned below = (1u << sub) - 1u;
+                if (isnz) {
+                    const int p = pz + __popc(bz & below);
+                    outv[p] = nr;
+                    outi[p] = (unsigned short)c;
+                    if (kPush)
+#pragma unroll 1
+                        for (int pr = 0; pr < sp->n_peers; ++pr) {
+                            double *pv = sp->peer_pool[pr] + off;
+                            pv[p] = nr;
+                            sp_idx(pv, (uint32_t)nz)[p] = (unsigned short)c;
+                        }
+                }
+                if (ch) {
+                    const int p = pd + __popc(bd & below);
+                    dv[p] = f - nr;
+                    di[p] = (unsigned short)c;
+                }
+                pz += __popc(bz);
+                pd += __popc(bd);
+            }
+        }
+        if (gv && js < 0) {
+            // row kept: block copy of the staged own row
+            const uint4 *src = reinterpret_cast<const uint4 *>(ov);
+            uint4 *dst = reinterpret_cast<uint4 *>(outv);
+            const int q16 = wrow >> 1;
+#pragma unroll 1
+            for (int q = sub; q < q16; q += gs) {
+                const uint4 blk = src[q];
+                dst[q] = blk;
+                if (kPush)
+#pragma unroll 1
+                    for (int pr = 0; pr < sp->n_peers; ++pr) reinterpret_cast<uint4 *>(sp->peer_pool[pr] + off)[q] = blk;
+            }
+        }
+        if (gv && sub == 0) {
+            const int64_t u = n_u[g];
+            const uint64_t hnew = sp_pack(off, (uint32_t)nz);
+            sp->hdr_out[u] = hnew;
+            sp->dcnt[u] = (unsigned short)nd;
+            sp->accepted[u] = (int8_t)js;
+            sp->node_llh[u] = llh_g;
+            if (kPush)
+#pragma unroll 1
+                for (int pr = 0; pr < sp->n_peers; ++pr) sp->peer_hdr[pr][u] = hnew;
+        }
+        __syncwarp();
+        return true;
+    }
+};
+
+// kPush: multi-GPU launch, the peers' replicas are written too; kHub: the launch has split hubs.  Both are
+// compile-time so that the plain single-GPU kernel carries none of that code.
+template <bool kPush, bool kHub>
+__global__ void __launch_bounds__(kTlThreads, kTlBlocksPerSM) tile_step_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ SparseArgs sp) {
+    if (a.done_flag != nullptr && *a.done_flag != 0) return;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ld = a.ld;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nthreads = (int)blockDim.x;
+    const int ldp = sp_ldp(ld);
+    double *s_steps = reinterpret_cast<double *>(smem_raw);
+    double *s_sumF = s_steps + kMaxSteps;
+    unsigned long long *s_mbar = reinterpret_cast<unsigned long long *>(s_sumF + ldp);
+    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_mbar + kTlWarps) + (size_t)wib * tl_region_bytes(ld);
+
+#pragma unroll 1
+    for (int i = threadIdx.x; i < ldp; i += nthreads) s_sumF[i] = (i < ld) ? a.sumF[i] : 0.0;
+#pragma unroll 1
+    for (int i = threadIdx.x; i < kMaxSteps; i += nthreads) s_steps[i] = a.steps[i];
+    __syncthreads();
+    // S2_all = sum_c sumF_c^2 in a fixed order (every warp computes the same bits)
+    double S2 = 0.0;
+    for (int c = lane; c < ldp; c += 32) S2 = fma(s_sumF[c], s_sumF[c], S2);
+    S2 = warp_sum(S2);
+
+    SpGen G;
+    G.a = &a;
+    G.sp = &sp;
+    G.s_steps = s_steps;
+    G.s_sumF = s_sumF;
+    G.ec = {a.x_lo, a.x_hi, a.t_lo, a.t_hi, a.w_lo, a.w_hi};
+    G.carve(wbase, ld, lane);
+    TlWarp T;
+    T.a = &a;
+    T.sp = &sp;
+    T.s_steps = s_steps;
+    T.s_sumF = s_sumF;
+    T.S2_all = S2;
+    T.ec = G.ec;
+    T.carve(wbase, ld, lane);
+    T.mbar = s_mbar + wib;
+    if (lane == 0) mbar_init(T.mbar);
+    G.clear_dense();
+    bool dense_clean = true;      // the two paths share the warp's region: the general path needs its dense vectors zeroed
+    __syncwarp();
+
+    if constexpr (kHub) {
+        for (;;) {
+            unsigned int it = 0;
+            if (lane == 0) it = atomicAdd(sp.hub_work, 1u);
+            it = __shfl_sync(0xffffffffu, it, 0);
+            if (it >= (unsigned int)a.n_hub_items) break;
+            G.template hub_item<kPush>(a.hub_items[it]);
+        }
+    }
+
+    const unsigned int n_items = (unsigned int)sp.n_gen + (unsigned int)sp.ntiles;
+    unsigned int item = 0;
+    if (lane == 0) item = atomicAdd(a.work_counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    while (item < n_items) {
+        unsigned int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(a.work_counter, 1u);
+        // nodes for the general path: the item itself, or the nodes of a tile that did not fit (one call site)
+        int gen_cnt = 1;
+        int64_t gen_pos = (int64_t)a.n_hubs + item;
+        const int32_t *gen_col = nullptr;
+        if (item >= (unsigned int)sp.n_gen) {
+            const TileMeta tm = sp.tiles[item - (unsigned int)sp.n_gen];
+            dense_clean = false;
+            const bool done = T.template run<kPush>(tm);
+            if (sp.stats != nullptr && lane == 0) atomicAdd(sp.stats + (done ? 0 : 1), 1u);
+            gen_cnt = done ? 0 : tm.nn;
+            gen_pos = tm.pos0;
+            gen_col = sp.tcol + tm.ecol0;           // the tile's entries of tcol are its nodes' neighbour lists (tagged ids)
+        }
+#pragma unroll 1
+        for (int i = 0; i < gen_cnt; ++i) {
+            const NodeMeta nm = a.meta[gen_pos + i];
+            if (!dense_clean) { G.clear_dense(); dense_clean = true; }
+            G.template node<kPush>(nm.u, nm.deg, gen_col != nullptr ? gen_col : a.col + nm.e0);
+            if (gen_col != nullptr) gen_col += nm.deg;
+        }
+        item = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The sums over nodes, in a fixed order: partials = [D(ld) = sum over accepted nodes of (old - new) | unused(ld) |
+// sum_u llh_u | number of accepted nodes].  Warp w of the grid owns a contiguous range of the processing order and
+// walks it front to back (delta blocks land in a per-warp dense vector, entries of one node never collide), the
+// warps of a block are added in warp order, the blocks in block order by the last block to finish.  No
+// floating-point atomics: two runs give the same bits.
+struct ReduceArgs {
+    const NodeMeta *meta;
+    int64_t order_n;
+    const uint64_t *hdr_out;
+    const double *pool_out;
+    const double *node_llh;
+    const unsigned short *dcnt;
+    const int8_t *accepted;
+    int32_t ld;
+    int32_t do_linesearch;
+    double *block_part;       // gridDim.x x (ld + 2)
+    unsigned int *ticket;
+    double *partials;         // 2 * ld + 2
+    const int32_t *done_flag;
+    // node-partitioned multi-GPU (fused collective, no NCCL on the data path): the last block also stores this
+    // rank's sums into its slot of every rank's exchange buffer (peer memory over NVLink) and then raises its
+    // flag there to `seq`; xreduce_kernel on every rank adds the slots up in rank order once all flags are up.
+    int32_t world;
+    double *xslot[8];                    // this rank's slot (ld + 2 doubles) in rank p's buffer, p = 0 .. world-1
+    unsigned long long *xflag[8];        // this rank's flag in rank p's flag array
+    unsigned long long seq;
+};
+constexpr int kRedWarps = 8;
+
+__global__ void __launch_bounds__(kRedWarps * 32) reduce_kernel(const ReduceArgs r) {
+    if (r.done_flag != nullptr && *r.done_flag != 0) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ld = r.ld, ldp = sp_ldp(ld);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *Dw = reinterpret_cast<double *>(smem_raw) + (size_t)wib * ldp;
+    __shared__ double s_llh[kRedWarps];
+    __shared__ unsigned int s_nupd[kRedWarps];
+    __shared__ unsigned int s_last;
+    for (int c = lane; c < ldp; c += 32) Dw[c] = 0.0;
+    __syncwarp();
+    const int64_t nwarps = (int64_t)gridDim.x * kRedWarps;
+    const int64_t chunk = (r.order_n + nwarps - 1) / nwarps;
+    const int64_t gw = (int64_t)blockIdx.x * kRedWarps + wib;
+    const int64_t lo = min(r.order_n, gw * chunk), hi = min(r.order_n, lo + chunk);
+    double llh = 0.0;
+    unsigned int nupd = 0;
+    for (int64_t p0 = lo; p0 < hi; p0 += 32) {
+        const int64_t p = p0 + lane;
+        const bool ok = p < hi;
+        const int32_t u = ok ? r.meta[p].u : 0;
+        if (ok) llh += r.node_llh[u];
+        const bool acc = ok && r.do_linesearch && r.accepted[u] >= 0;
+        uint64_t h = 0;
+        int dc = 0;
+        if (acc) { h = r.hdr_out[u]; dc = r.dcnt[u]; }
+        unsigned bal = __ballot_sync(0xffffffffu, acc);
+        nupd += __popc(bal);
+        while (bal) {
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1u;
+            const uint64_t hs = __shfl_sync(0xffffffffu, h, src);
+            const int d = __shfl_sync(0xffffffffu, dc, src);
+            const double *dv = r.pool_out + sp_off8(hs) + sp_words(sp_cnt(hs));
+            const unsigned short *di = sp_idx(dv, (uint32_t)d);
+            for (int i = lane; i < d; i += 32) Dw[di[i]] += dv[i];
+            __syncwarp();
+        }
+    }
+    llh = warp_sum(llh);
+    if (lane == 0) { s_llh[wib] = llh; s_nupd[wib] = nupd; }
+    __syncthreads();
+    const double *D0 = reinterpret_cast<const double *>(smem_raw);
+    double *mine = r.block_part + (size_t)blockIdx.x * (ld + 2);
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+        double v = 0.0;
+        for (int w = 0; w < kRedWarps; ++w) v += D0[(size_t)w * ldp + c];
+        mine[c] = v;
+    }
+    if (threadIdx.x == 0) {
+        double l = 0.0;
+        unsigned int nu = 0;
+        for (int w = 0; w < kRedWarps; ++w) { l += s_llh[w]; nu += s_nupd[w]; }
+        mine[ld] = l;
+        mine[ld + 1] = (double)nu;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(r.ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < ld + 2; c += blockDim.x) {
+        double v = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) v += __ldcg(r.block_part + (size_t)b * (ld + 2) + c);
+        if (c < ld) r.partials[c] = v;
+        else r.partials[2 * ld + (c - ld)] = v;
+        for (int p = 0; p < r.world; ++p) r.xslot[p][c] = v;
+    }
+    if (threadIdx.x == 0) *r.ticket = 0u;
+    if (r.world > 0) {
+        // the step kernel's rows went to the peers before this kernel started; the slots above follow; only then
+        // the flags (system-scope fence in between)
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < r.world) {
+            *reinterpret_cast<volatile unsigned long long *>(r.xflag[threadIdx.x]) = r.seq;
+            __threadfence_system();
+        }
+    }
+}
+
+// Multi-GPU: waits until every rank's sums of this step have arrived (flags >= seq), then adds the slots up in rank
+// order — every rank gets the same bits — into the partials the finish kernel reads.  One block.
+struct XReduceArgs {
+    const double *xbuf;                        // world x (ld + 2), this step's half of the local exchange buffer
+    const unsigned long long *flags;           // world flags (local memory, written by the peers)
+    unsigned long long seq;
+    int32_t world, ld;
+    double *partials;
+    const int32_t *done_flag;
+};
+__global__ void xreduce_kernel(const XReduceArgs x) {
+    if (x.done_flag != nullptr && *x.done_flag != 0) return;
+    if ((int)threadIdx.x < x.world) {
+        const volatile unsigned long long *f = x.flags + threadIdx.x;
+        while (*f < x.seq) __nanosleep(100);
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int ld = x.ld;
+    for (int c = threadIdx.x; c < ld + 2; c += blockDim.x) {
+        double v = 0.0;
+        for (int p = 0; p < x.world; ++p) v += __ldcg(x.xbuf + (size_t)p * (ld + 2) + c);
+        if (c < ld) x.partials[c] = v;
+        else x.partials[2 * ld + (c - ld)] = v;
+    }
+}
+
+}  // namespace bigclam

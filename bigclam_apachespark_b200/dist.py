@@ -82,7 +82,7 @@ class CudaEngine:
             self.check(self.lib.bigclam_set_owned_nodes(self.ctx, nodes.ctypes.data, len(nodes)), self.ctx)
         if self.sparse and owned_counts is not None:
             ld = (solver.K + 3) & ~3
-            row_words = ld * 5 // 4                       # sp_words(ld): a full row, values + uint16 indices
+            row_words = _lib.sparse_node_words(ld)        # a full row block + a full delta block per owned node
             base = int(sum(owned_counts[:rank])) * row_words
             self.check(self.lib.bigclam_set_pool_region(self.ctx, base, int(owned_counts[rank]) * row_words), self.ctx)
         self.lo, self.hi = int(lo), int(hi)

@@ -121,6 +121,13 @@ int bigclam_get_kernel_time(bigclam_ctx *ctx, double *step_kernel_ms_sum, int64_
 
 /* Interop with the host framework's plumbing (torch streams / NCCL buffers): use an existing
  * cudaStream_t, and expose device pointers of the current F (n x ld doubles, ld = row pitch) and sumF. */
+/* Sparse rows (BIGCLAM_F_SPARSE_ROWS + BIGCLAM_F_TIME_KERNELS): how the small nodes were processed since the
+ * context was created / the counters were last read — tiles done on the tile path, tiles that did not fit the
+ * warp's shared memory and went node by node through the general path; the tile layout of the current order
+ * (tiles, nodes on the general path, split hubs).  Reading resets the two counters. */
+int bigclam_get_tile_stats(bigclam_ctx *ctx, int64_t *tiles_done, int64_t *tiles_fallback, int64_t *n_tiles,
+                           int64_t *n_general_nodes, int64_t *n_split_hubs);
+
 int bigclam_set_stream(bigclam_ctx *ctx, void *cuda_stream);
 int bigclam_device_state(bigclam_ctx *ctx, void **F_dev, void **F_next_dev, void **sumF_dev, int64_t *ld);
 /* Device pointer of the per-node accepted-step index (int8, n entries; BIGCLAM_F_RECORD_ACCEPTED):

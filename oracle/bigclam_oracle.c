@@ -104,6 +104,12 @@ static double pre_node(const int64_t *rowptr, const int32_t *col, int64_t u,
     return (s1 - fusfT) + fufuT;
 }
 
+/* test hook: when set, ls_trial also stores result - (llh_u + arm) here (oracle_armijo_margins, single-threaded) */
+static double *g_margin_out = NULL;
+#ifdef _OPENMP
+#pragma omp threadprivate(g_margin_out)
+#endif
+
 /* One candidate of the LS block, bigclam4-7.scala:173-181.  newfu (k) is written. */
 static int ls_trial(const int64_t *rowptr, const int32_t *col, int64_t u,
                     const double *F, const double *sumF, const oracle_params *p,
@@ -130,7 +136,38 @@ static int ls_trial(const int64_t *rowptr, const int32_t *col, int64_t u,
     double as = p->alpha * s;
     double arm = 0.0;
     for (int i = 0; i < k; ++i) arm += (as * grad[i]) * grad[i];
+    if (g_margin_out) *g_margin_out = result - (llh_u + arm);
     return result >= (llh_u + arm);
+}
+
+/* Test helper (SURVEY 8c property iv): for `count` nodes, the Armijo margins  llh'(s_j) - (llh_u + alpha s_j |g|^2)
+ * of all candidates (bigclam4-7.scala:181) as this restatement computes them, and llh_u.  A node whose accepted
+ * index differs between two implementations is a genuine tie only if the margin at the first index where they
+ * disagree is at rounding level. */
+void oracle_armijo_margins(int64_t n, const int64_t *rowptr, const int32_t *col, const oracle_params *p,
+                           const double *F, const double *sumF, const int64_t *nodes, int64_t count,
+                           double *margins_out /* count x (max_inter+1) */, double *llh_u_out /* count */) {
+    (void)n;
+    const int k = p->k;
+    const int nsteps = p->max_inter + 1;
+    double *steps = (double *)malloc(sizeof(double) * (size_t)nsteps);
+    oracle_step_sizes(p->beta, p->max_inter, steps);
+    double *grad = (double *)malloc(sizeof(double) * (size_t)k * 3);
+    double *newfu = grad + k, *sfT = grad + 2 * (size_t)k;
+    for (int64_t i = 0; i < count; ++i) {
+        const int64_t u = nodes[i];
+        const double llh_u = pre_node(rowptr, col, u, F, sumF, p, grad);
+        llh_u_out[i] = llh_u;
+        for (int j = 0; j < nsteps; ++j) {
+            double m = 0.0;
+            g_margin_out = &m;
+            (void)ls_trial(rowptr, col, u, F, sumF, p, grad, llh_u, steps[j], newfu, sfT);
+            g_margin_out = NULL;
+            margins_out[i * nsteps + j] = m;
+        }
+    }
+    free(grad);
+    free(steps);
 }
 
 /* per-node LLH term of the LLH block, bigclam4-7.scala:196-219 (== loglikelihood(),

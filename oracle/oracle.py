@@ -41,12 +41,33 @@ def make_params(k, alpha=0.05, beta=0.1, max_inter=15, min_p=0.0001, max_p=0.999
     return OracleParams(int(k), int(max_inter), alpha, beta, min_p, max_p, min_f, max_f)
 
 
+def _cpu_tag() -> str:
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force: bool = False) -> str:
-    """Compile liboracle.so from the C restatement (gcc + OpenMP); returns its path."""
+    """Compile liboracle.so from the C restatement (gcc + OpenMP, -O3 -march=native); returns its path.  The
+    library is rebuilt when the source is newer or when it was built for another CPU model (it travels with the
+    repository snapshot to the GPU box, whose host CPU may differ)."""
     src = os.path.join(_HERE, "bigclam_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
-                       stdout=subprocess.DEVNULL)
+    tag_path = os.path.join(_HERE, "liboracle.host")
+    tag = _cpu_tag()
+    try:
+        with open(tag_path) as fh:
+            same_cpu = fh.read().strip() == tag
+    except OSError:
+        same_cpu = False
+    if force or not same_cpu or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, stdout=subprocess.DEVNULL)
+        with open(tag_path, "w") as fh:
+            fh.write(tag + "\n")
     return _LIB_PATH
 
 
@@ -56,8 +77,7 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
+        build()
         L = C.CDLL(_LIB_PATH)
         dp = C.POINTER(C.c_double)
         L.oracle_step_sizes.argtypes = [C.c_double, C.c_int32, dp]
@@ -76,6 +96,9 @@ def lib() -> C.CDLL:
                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_int64,
                                  dp, C.c_void_p, C.c_int64]
         L.oracle_run.restype = C.c_int64
+        L.oracle_armijo_margins.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(OracleParams), C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.oracle_armijo_margins.restype = None
         L.oracle_num_threads.restype = C.c_int32
         _lib = L
     return _lib
@@ -157,6 +180,17 @@ def run(rowptr, col, F, sumF, params: OracleParams, variant=4, rel_tol=1e-4, max
     calls = lib().oracle_run(n, _p(rowptr), _p(col), C.byref(params), _p(F2), _p(s2), variant,
                              rel_tol, max_outer, C.byref(out), _p(trace), trace_cap)
     return F2, s2, out.value, calls, trace[:min(calls, trace_cap)]
+
+
+def armijo_margins(rowptr, col, F, sumF, params: OracleParams, nodes):
+    """Margins llh'(s_j) - (llh_u + alpha s_j |g|^2) of every candidate for the given nodes, and their llh_u."""
+    n = _chk(rowptr, col, F, params.k)
+    nodes = np.ascontiguousarray(nodes, dtype=np.int64)
+    m = np.empty((len(nodes), params.max_inter + 1), dtype=np.float64)
+    lu = np.empty(len(nodes), dtype=np.float64)
+    sumF = np.ascontiguousarray(sumF, dtype=np.float64)
+    lib().oracle_armijo_margins(n, _p(rowptr), _p(col), C.byref(params), _p(F), _p(sumF), _p(nodes), len(nodes), _p(m), _p(lu))
+    return m, lu
 
 
 def num_threads() -> int:

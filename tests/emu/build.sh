@@ -7,9 +7,9 @@ src="$here/../../bigclam_apachespark_b200/csrc"
 gen="$here/_gen"
 mkdir -p "$gen"
 defs=""
-for f in bigclam_kernels.cuh bigclam_sparse.cuh; do
+# (the sparse-row kernels are exercised through the host build of the whole C API: build_hostemu.sh)
+for f in bigclam_kernels.cuh; do
   test -f "$src/$f" || continue
-  test "$f" = bigclam_sparse.cuh && defs="-DBIGCLAM_EMU_SPARSE"
   sed -e 's/extern __shared__ __align__(16) unsigned char smem_raw\[\];/unsigned char *smem_raw = emu::dyn_smem();/' \
       -e 's/^\( *\)__shared__ /\1static /' "$src/$f" > "$gen/$f"
 done

@@ -11,7 +11,7 @@ src="$here/../../bigclam_apachespark_b200/csrc"
 gen="$here/_gen"
 mkdir -p "$gen"
 defs=""
-for f in bigclam_kernels.cuh bigclam_sparse.cuh; do
+for f in bigclam_kernels.cuh bigclam_sparse.cuh bigclam_tile.cuh; do
   test -f "$src/$f" || continue
   sed -e 's/extern __shared__ __align__(16) unsigned char smem_raw\[\];/unsigned char *smem_raw = emu::dyn_smem();/' \
       -e 's/^\( *\)__shared__ /\1static /' "$src/$f" > "$gen/$f"

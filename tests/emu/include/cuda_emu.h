@@ -30,6 +30,7 @@
 #define __forceinline__ inline
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __align__(n) alignas(n)
 
 struct dim3 {
@@ -92,7 +93,9 @@ inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::wsync(); }
 inline void __syncthreads() { pthread_barrier_wait(&emu::block->bar); }
 
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline double atomicAdd(double *p, double v) {
     uint64_t *q = reinterpret_cast<uint64_t *>(p);
@@ -127,6 +130,7 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline void __nanosleep(unsigned) {}
 inline void __threadfence() { __sync_synchronize(); }
+inline void __threadfence_system() { __sync_synchronize(); }
 using std::fma;
 
 template <class A, class B> inline std::common_type_t<A, B> min(A a, B b) {

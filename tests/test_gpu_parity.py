@@ -25,11 +25,15 @@ def _solver(rp, col, K, F0, sumF=None, **kw):
     return b
 
 
-def _check_step(b, r, llh, max_flips=0, where="", max_idx_diff=0.02):
-    """Rows must agree tightly; a "flip" is a row that does not (an Armijo decision that went the
-    other way).  A differing accepted index alone is not a flip: at s ~ 1e-13..1e-15 the slope term
-    alpha*s*|g|^2 is below one ulp of llh_u, the test degenerates to `llh' >= llh_u` and its outcome is
-    rounding noise in the reference too — the row then moves by <= 1e-13*|g|, far inside tolerance."""
+TIE_TOL = 1e-9          # a differing Armijo decision must be a tie: |llh'(s) - rhs| <= TIE_TOL * max(|llh_u|, 1)
+
+
+def _check_step(b, r, llh, max_flips=0, where="", max_idx_diff=0.02, inputs=None):
+    """Rows must agree tightly; a "flip" is a row that does not (an Armijo decision that went the other way).
+    Every node whose accepted index differs from the oracle's — flipped row or not — must be a GENUINE TIE
+    (SURVEY 8c property iv): at the first candidate where the two decision sequences part, the oracle's own
+    Armijo margin llh'(s) - (llh_u + alpha s |g|^2) is at rounding level, and the step the GPU accepted passes
+    the oracle's test up to that noise.  `inputs` = (rowptr, col, F_in, sumF_in, params) of the step."""
     F = b.F
     acc = b.accepted()
     scale = max(np.abs(r.F).max(), 1e-300)
@@ -38,10 +42,23 @@ def _check_step(b, r, llh, max_flips=0, where="", max_idx_diff=0.02):
     flips = int(flipped.sum())
     assert flips <= max_flips, f"{where}: {flips} rows differ (max err {row_err.max():.3e}, scale {scale:.3e})"
     idx_diff = acc != r.accepted
+    assert not (flipped & ~idx_diff).any(), f"{where}: rows differ although the accepted step is the same"
     if idx_diff.any():
-        # index disagreements are only tolerated at noise-level step sizes (index >= 12 or -1)
-        a, o = acc[idx_diff & ~flipped], r.accepted[idx_diff & ~flipped]
-        assert ((a < 0) | (a >= 12)).all() and ((o < 0) | (o >= 12)).all(), (where, a, o)
+        assert inputs is not None, f"{where}: accepted indices differ and no inputs were given to prove the ties"
+        from oracle import oracle as O
+        rp_, col_, F_in, sumF_in, params = inputs
+        nodes = np.nonzero(idx_diff)[0]
+        margins, llh_u = O.armijo_margins(rp_, col_, np.ascontiguousarray(F_in), sumF_in, params, nodes)
+        nsteps = margins.shape[1]
+        for i, u in enumerate(nodes):
+            a, o = int(acc[u]), int(r.accepted[u])
+            a1, o1 = (a if a >= 0 else nsteps), (o if o >= 0 else nsteps)
+            j0 = min(a1, o1)
+            tol = TIE_TOL * max(abs(llh_u[i]), 1.0)
+            assert abs(margins[i, j0]) <= tol, (f"{where}: node {u} gpu idx {a} oracle idx {o}: margin "
+                                                f"{margins[i, j0]:.3e} at candidate {j0} is not a tie (tol {tol:.1e})")
+            if a >= 0:
+                assert margins[i, a] >= -tol, f"{where}: node {u}: accepted candidate {a} fails the oracle's Armijo test"
     assert idx_diff.mean() <= max_idx_diff, where
     if flips == 0:
         assert np.allclose(b.sumF, r.sumF, rtol=1e-11, atol=1e-9), where
@@ -67,7 +84,7 @@ def test_single_step_all_k(oracle, k):
     b = _solver(rp, col, k, F0, sumF)
     llh = b.backtrackingLineSearchs()
     r = oracle.step(rp, col, F0, sumF, oracle.make_params(k))
-    _check_step(b, r, llh, where=f"k={k}")
+    _check_step(b, r, llh, where=f"k={k}", inputs=(rp, col, F0, sumF, oracle.make_params(k)))
     b.close()
 
 
@@ -82,7 +99,7 @@ def test_dense_rows_take_dense_path(oracle):
     b = _solver(rp, col, k, F0, sumF)
     llh = b.backtrackingLineSearchs()
     r = oracle.step(rp, col, F0, sumF, oracle.make_params(k))
-    _check_step(b, r, llh, where="dense")
+    _check_step(b, r, llh, where="dense", inputs=(rp, col, F0, sumF, oracle.make_params(k)))
     b.close()
 
 
@@ -112,7 +129,7 @@ def test_facebook_k10_multi_step_against_golden_and_oracle(oracle, golden, graph
     for it in range(6):
         llh = b.backtrackingLineSearchs()
         r = oracle.step(rp, col, F, sumF, P)
-        total_flips += _check_step(b, r, llh, max_flips=2, where=f"facebook it{it}")
+        total_flips += _check_step(b, r, llh, max_flips=2, where=f"facebook it{it}", inputs=(rp, col, F, sumF, P))
         if it < 3 and total_flips == 0:
             assert abs(llh - golden[f"facebook_llh_{it}"]) <= 1e-10 * abs(golden[f"facebook_llh_{it}"])
             assert (b.accepted() == golden[f"facebook_accepted_{it}"]).mean() > 0.99
@@ -133,7 +150,7 @@ def test_uset_mask(oracle):
     b = _solver(rp, col, k, F0, sumF)
     llh = b.backtrackingLineSearchs(uset=uset)
     r = oracle.step(rp, col, F0, sumF, oracle.make_params(k), node_mask=mask)
-    _check_step(b, r, llh, where="mask")
+    _check_step(b, r, llh, where="mask", inputs=(rp, col, F0, sumF, oracle.make_params(k)))
     assert np.array_equal(b.F[mask == 0], F0[mask == 0])
     b.close()
 
@@ -155,7 +172,7 @@ def test_multiplicity_kept_and_clamp_at_max_f(oracle):
     for it in range(8):
         llh = b.backtrackingLineSearchs()
         r = oracle.step(rp2, col2, F, sumF, P)
-        _check_step(b, r, llh, max_flips=1, where=f"dup it{it}", max_idx_diff=0.25)   # rows pinned at MAX_F_: nf == fu, pure noise decisions
+        _check_step(b, r, llh, max_flips=1, where=f"dup it{it}", max_idx_diff=0.25, inputs=(rp2, col2, F, sumF, P))   # rows pinned at MAX_F_: nf == fu, pure noise decisions
         F, sumF = b.F, b.sumF
         hit_max |= bool((F == 1000.0).any())
     b.close()
@@ -171,7 +188,7 @@ def test_sumF_injection_and_drift(oracle):
     b = _solver(rp, col, k, F0, sumF)
     llh = b.backtrackingLineSearchs()
     r = oracle.step(rp, col, F0, sumF, oracle.make_params(k))
-    _check_step(b, r, llh, where="drift")
+    _check_step(b, r, llh, where="drift", inputs=(rp, col, F0, sumF, oracle.make_params(k)))
     # and without injection the library's own column sums match the exact ones
     b2 = _solver(rp, col, k, F0)
     assert np.allclose(b2.sumF, oracle.colsum(F0), rtol=1e-13)
@@ -232,7 +249,7 @@ def test_email_enron_k50_one_step(oracle, graphs):
     b = _solver(rp, col, K, F0, sumF)
     llh = b.backtrackingLineSearchs()
     r = oracle.step(rp, col, F0, sumF, oracle.make_params(K))
-    _check_step(b, r, llh, max_flips=3, where="enron")
+    _check_step(b, r, llh, max_flips=3, where="enron", inputs=(rp, col, F0, sumF, oracle.make_params(K)))
     b.close()
 
 
@@ -250,7 +267,7 @@ def test_com_amazon_k200_steps_and_properties(oracle, graphs):
     for it in range(2):
         llh = b.backtrackingLineSearchs()
         r = oracle.step(rp, col, F, s, P)
-        _check_step(b, r, llh, max_flips=5, where=f"amazon it{it}")
+        _check_step(b, r, llh, max_flips=5, where=f"amazon it{it}", inputs=(rp, col, F, s, P))
         F, s = b.F, b.sumF
     # property (iii): incremental sumF stays within 1e-9 of the true column sums
     b._run(4, 0.0, 10)
@@ -276,7 +293,7 @@ def test_reference_style_init_then_steps(oracle, graphs):
     for it in range(4):
         llh = b.backtrackingLineSearchs()
         r = oracle.step(rp, col, F, sumF, P)
-        _check_step(b, r, llh, max_flips=2, where=f"ref-init it{it}", max_idx_diff=0.05)
+        _check_step(b, r, llh, max_flips=2, where=f"ref-init it{it}", max_idx_diff=0.05, inputs=(rp, col, F, sumF, P))
         F, sumF = b.F, b.sumF
     b.close()
 
@@ -309,7 +326,7 @@ def test_rmat_skewed_graph(oracle, graphs):
     for it in range(3):
         llh = b.backtrackingLineSearchs()
         r = oracle.step(rp, col, F, s, P)
-        _check_step(b, r, llh, max_flips=2, where=f"rmat it{it}", max_idx_diff=0.05)
+        _check_step(b, r, llh, max_flips=2, where=f"rmat it{it}", max_idx_diff=0.05, inputs=(rp, col, F, s, P))
         F, s = b.F, b.sumF
     b.close()
 
@@ -329,7 +346,7 @@ def test_mega_hub_split_over_blocks(oracle, graphs):
     for it in range(4):
         llh = b.backtrackingLineSearchs()
         r = oracle.step(rp, col, F, s, P)
-        _check_step(b, r, llh, max_flips=2, where=f"mega it{it}", max_idx_diff=0.05)
+        _check_step(b, r, llh, max_flips=2, where=f"mega it{it}", max_idx_diff=0.05, inputs=(rp, col, F, s, P))
         F, s = b.F, b.sumF
     # the device-side loop uses the same kernels
     b.set_F(F0, sumF=sumF)
@@ -355,7 +372,7 @@ def test_step_speculation_is_invisible(oracle):
         uset = None if mk is None else np.flatnonzero(mk)
         llh = b.backtrackingLineSearchs(uset=uset)
         r = oracle.step(rp, col, F, s, P, node_mask=None if mk is None else mk.astype(np.uint8))
-        _check_step(b, r, llh, max_flips=1, where=f"spec it{it}", max_idx_diff=0.05)
+        _check_step(b, r, llh, max_flips=1, where=f"spec it{it}", max_idx_diff=0.05, inputs=(rp, col, F, s, P))
         if it == 1:
             assert abs(b.loglikelihood() - llh) <= 1e-12 * abs(llh)      # drops the speculation, state unchanged
         F, s = b.F, b.sumF
@@ -363,7 +380,7 @@ def test_step_speculation_is_invisible(oracle):
     b.set_F(F0, sumF=sumF)
     llh = b.backtrackingLineSearchs()
     r = oracle.step(rp, col, F0, sumF, P)
-    _check_step(b, r, llh, max_flips=1, where="spec after set_F")
+    _check_step(b, r, llh, max_flips=1, where="spec after set_F", inputs=(rp, col, F0, sumF, P))
     # the device loop after speculative single steps
     b._run(4, 1e-4, 5)
     Fo, so, llho, callso, tro = oracle.run(rp, col, r.F, r.sumF, P, variant=4, max_outer=5)

@@ -27,7 +27,7 @@ def test_sparse_single_step_all_k(oracle, k):
     assert np.array_equal(b.F, F0)                      # dense -> sparse -> dense round trip
     llh = b.backtrackingLineSearchs()
     r = oracle.step(rp, col, F0, sumF, oracle.make_params(k))
-    _check_step(b, r, llh, where=f"sparse k={k}")
+    _check_step(b, r, llh, where=f"sparse k={k}", inputs=(rp, col, F0, sumF, oracle.make_params(k)))
     b.close()
 
 
@@ -44,7 +44,7 @@ def test_sparse_dense_rows_and_long_neighbour_lists(oracle):
     for it in range(3):
         llh = b.backtrackingLineSearchs()
         r = oracle.step(rp, col, F, s, oracle.make_params(k))
-        _check_step(b, r, llh, max_flips=2, where=f"sparse dense-rows it{it}")
+        _check_step(b, r, llh, max_flips=2, where=f"sparse dense-rows it{it}", inputs=(rp, col, F, s, oracle.make_params(k)))
         F, s = b.F, b.sumF
     b.close()
 
@@ -72,7 +72,7 @@ def test_sparse_uset_mask_and_loglikelihood(oracle):
     mask = (rng.random(n) < 0.5).astype(np.uint8)
     llh = b.backtrackingLineSearchs(np.nonzero(mask)[0])
     r = oracle.step(rp, col, F0, sumF, oracle.make_params(k), node_mask=mask)
-    _check_step(b, r, llh, where="sparse uset")
+    _check_step(b, r, llh, where="sparse uset", inputs=(rp, col, F0, sumF, oracle.make_params(k)))
     assert np.array_equal(b.F[mask == 0], F0[mask == 0])
     b.close()
 
@@ -109,7 +109,7 @@ def test_sparse_com_amazon_k200(oracle, graphs):
     for it in range(2):
         llh = b.backtrackingLineSearchs()
         r = oracle.step(rp, col, F, s, P)
-        _check_step(b, r, llh, max_flips=5, where=f"sparse amazon it{it}")
+        _check_step(b, r, llh, max_flips=5, where=f"sparse amazon it{it}", inputs=(rp, col, F, s, P))
         F, s = b.F, b.sumF
     b._run(4, 0.0, 10)
     Fg, sg = b.F, b.sumF
@@ -144,7 +144,7 @@ def test_sparse_split_hubs(oracle, monkeypatch):
     for it in range(3):
         llh = b.backtrackingLineSearchs()
         r = oracle.step(rp, col, F, s, oracle.make_params(k))
-        _check_step(b, r, llh, max_flips=2, where=f"sparse hubs it{it}")
+        _check_step(b, r, llh, max_flips=2, where=f"sparse hubs it{it}", inputs=(rp, col, F, s, oracle.make_params(k)))
         F, s = b.F, b.sumF
     b.close()
 
@@ -160,7 +160,7 @@ def test_sparse_rmat_skewed_graph(oracle, graphs):
     for it in range(2):
         llh = b.backtrackingLineSearchs()
         r = oracle.step(rp, col, F, s, oracle.make_params(k))
-        _check_step(b, r, llh, max_flips=3, where=f"sparse rmat it{it}")
+        _check_step(b, r, llh, max_flips=3, where=f"sparse rmat it{it}", inputs=(rp, col, F, s, oracle.make_params(k)))
         F, s = b.F, b.sumF
     b.close()
 
@@ -181,7 +181,7 @@ def test_csr_entry_points(oracle, sparse):
     assert np.allclose(b.sumF, F0.sum(axis=0), rtol=1e-13)
     llh = b.backtrackingLineSearchs()
     r = oracle.step(rp, col, F0, oracle.colsum(F0), oracle.make_params(k))
-    _check_step(b, r, llh, where="csr")
+    _check_step(b, r, llh, where="csr", inputs=(rp, col, F0, oracle.colsum(F0), oracle.make_params(k)))
     ip, ix, vl = b.F_csr()
     F1 = b.F
     assert ip[-1] == (F1 != 0).sum()

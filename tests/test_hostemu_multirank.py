@@ -36,7 +36,7 @@ def test_two_ranks_through_the_c_abi(oracle, sparse, hub, monkeypatch):
         _lib.check(lib.bigclam_set_owned_nodes(b._ctx, nodes.ctypes.data, len(nodes)), b._ctx)
         if sparse:
             counts = [len(range(q, n, world)) for q in range(world)]
-            row_words = ld * 5 // 4
+            row_words = _lib.sparse_node_words(ld)
             _lib.check(lib.bigclam_set_pool_region(b._ctx, sum(counts[:r]) * row_words, counts[r] * row_words), b._ctx)
         ranks.append(b)
     per = 64 * lib.bigclam_ipc_handle_count(ranks[0]._ctx)

@@ -1,0 +1,29 @@
+"""Kernel LOGIC of the sparse-row engine on the CPU (no GPU in this container): a selection of the `-m gpu` tests of
+tests/test_gpu_sparse.py is run, in a child pytest, against the HOST-EMULATION build of the whole C API
+(tests/emu/build_hostemu.sh: csrc/bigclam_capi.cu + the kernel sources compiled for the host against the SIMT
+emulation of tests/emu/include/cuda_emu.h — one OS thread per CUDA thread, warp collectives as barrier rounds, so a
+collective reached by part of a warp hangs instead of passing).  The tile path, the general path, split hubs, the
+fixed-order reduction, the pool / CSR entry points and the device-side loop bookkeeping all run here against the
+oracle.  Test infrastructure only: the product library has no CPU path and the `-m gpu` tests on the B200 remain
+the parity tests of the compiled sm_100a code."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SELECTION = ("golden_tiny or uset_mask or csr_entry or pool_exhaustion or split_hubs or mode_limits or "
+             "(all_k and (k1- or 3 or 31 or 65))")
+
+
+@pytest.mark.timeout(1500)
+def test_sparse_engine_under_host_emulation():
+    env = dict(os.environ, BIGCLAM_HOSTEMU="1")
+    env.pop("BIGCLAM_HOSTEMU_NOBUILD", None)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(REPO, "tests", "test_gpu_sparse.py"), "-m", "gpu", "-q", "-x",
+                        "-k", SELECTION, "-p", "no:cacheprovider"], cwd=REPO, env=env, capture_output=True, text=True, timeout=1400)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout, tail

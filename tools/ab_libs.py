@@ -46,7 +46,18 @@ for v in sys.argv[1:]:
             b._run(4, 0.0, 40)
             ms, nk, _ = b.kernel_time()
             res.append(ms / max(nk, 1))
-        print(f"== {v}{':sparse' if sparse else ''}: kernel {res[0]:.4f} / {res[1]:.4f} ms  llh@90 {b.last_trace[-1]:.12e}  {par}", flush=True)
+        st = b.tile_stats() if sparse else {}
+        llh90 = b.last_trace[-1]
         b.close()
+        # determinism: the same 6 steps on two fresh contexts must give the same bits
+        bits = []
+        for _ in range(2):
+            b = BigClam(device=0, sparse_rows=sparse)
+            b.set_graph(rp, col).set_K(K).set_F(F0, sumF=sumF)
+            b._run(4, 0.0, 6)
+            bits.append((b.last_trace[-1], b.F.tobytes(), b.sumF.tobytes()))
+            b.close()
+        det = bits[0] == bits[1]
+        print(f"== {v}{':sparse' if sparse else ''}: kernel {res[0]:.4f} / {res[1]:.4f} ms  llh@90 {llh90:.12e}  {par}  bit-identical reruns {det}  {st}", flush=True)
     except Exception as e:  # noqa: BLE001
         print(f"== {v}: FAILED {e!r}", flush=True)
