@@ -3,13 +3,21 @@
 com-amazon K=200".
 
 A step = one call of the hot path (backtrackingLineSearchs, codes/bigclam4-7.scala:152-223: PRE +
-16-candidate line search + row swap + sumF update + LLH) over the whole graph.  Workload: the
-com-amazon topology (SNAP, 334,863 nodes / 925,872 edges, committed as tests/golden/graphs/
-com-amazon.npz) with K=200 and the synthetic F0 of BASELINE.md (U[0,1) with probability 0.05,
-seed 1234), fp64.  F is 536 MB (> the 126 MB L2), so no L2 flush is needed between steps.
+16-candidate line search + row swap + sumF update + LLH) over the whole graph.  Default workload
+(`--config amazon200`, BASELINE config 3): the com-amazon topology (SNAP, 334,863 nodes / 925,872
+edges, package data bigclam_apachespark_b200/data/graphs/com-amazon.npz) with K=200 and the synthetic
+F0 of BASELINE.md (U[0,1) with probability 0.05, seed 1234), fp64.  The other BASELINE configs are
+`--config enron50 | amazon500 | rmat` (or --graph / --k).
 
-  value   directed neighbour-list entries processed per second, F resident in HBM, K steps run by
-          the device-side loop (bigclam_run), timed with CUDA events on the launching stream
+F lives on the device as SPARSE ROWS (the reference's own layout, RDD[(Long, BSV[Double])],
+bigclam4-7.scala:97-104); `--layout dense` selects the round-1 dense n x K kernels.  The roofline
+is reported against SURVEY §8(d)'s DENSE-model algorithmic bytes (nnz*(K*8+4) + N*(2*K*8+8) + K*8);
+`layout_bytes_per_launch` is what the sparse layout really has to move and `traffic` the DRAM bytes
+of one launch measured in this run by a side process under ncu (never inside the timed region).
+The working set of the sparse layout is ~80 MB: it is L2-resident on purpose, nothing is flushed.
+
+  value   directed neighbour-list entries processed per second (= 2 x undirected edges), F resident
+          in HBM, K steps run by the device-side loop (bigclam_run), CUDA events on the launching stream
   e2e     the same metric through per-call bigclam_step() with host buffers (uset mask H2D from
           pinned memory, LLH/n_updated D2H every step)
   roofline  algorithmic bytes of one step kernel / its average duration (CUDA events in the library)
@@ -30,30 +38,43 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-WORKLOAD = "com-amazon K=200, synthetic F0 (p=0.05 U[0,1), seed 1234), fp64"
-K = 200
+CONFIGS = {
+    "enron50": dict(graph="email-enron", k=50, note="BASELINE config 2 (Email-Enron, reciprocal lines deduplicated)"),
+    "amazon200": dict(graph="com-amazon", k=200, note="BASELINE config 3 (headline)"),
+    "amazon500": dict(graph="com-amazon", k=500, note="BASELINE config 4"),
+    "rmat": dict(graph="rmat:10000000:100000000", k=1000, note="BASELINE config 5 (R-MAT 10M nodes / 100M edges)"),
+}
 
 
-_GRAPH = "com-amazon"
+def workload_name(graph, k):
+    return f"{graph} K={k}, synthetic F0 (p=0.05 U[0,1), seed 1234), fp64"
 
 
-def load_workload():
-    """Default: the com-amazon topology fixture.  `--graph rmat:<nodes>:<edges>` generates BASELINE config 5's
-    R-MAT family instead ((a,b,c,d) = (.57,.19,.19,.05), seed 42) — not the headline workload."""
+def load_graph(graph):
     from bigclam_apachespark_b200 import graphs as G
-    if _GRAPH.startswith("rmat:"):
-        _, nn, mm = _GRAPH.split(":")
-        rp, col = G.rmat_graph(int(nn), int(mm), seed=42)
-    else:
-        rp, col, _ = G.load_npz_graph(_GRAPH)
+    if graph.startswith("rmat:"):
+        _, nn, mm = graph.split(":")
+        return G.rmat_graph(int(nn), int(mm), seed=42)
+    rp, col, _ = G.load_npz_graph(graph)
+    return rp, col
+
+
+def load_workload(graph, k):
+    """(rowptr, col, F0): F0 dense when n x K fits comfortably, else a scipy CSR matrix (same distribution)."""
+    from bigclam_apachespark_b200 import graphs as G
+    rp, col = load_graph(graph)
     n = len(rp) - 1
-    if n * K > (1 << 31):
-        # n x K does not exist densely at this size: CSR rows (same distribution), needs --layout sparse
+    if n * k > (1 << 29):
         import scipy.sparse as sps
-        ip, ix, vl = G.synthetic_F0_csr(n, K, seed=1234, density=0.05)
-        return rp, col, sps.csr_matrix((vl, ix, ip), shape=(n, K))
-    F0 = G.synthetic_F0(n, K, seed=1234, density=0.05)
-    return rp, col, F0
+        ip, ix, vl = G.synthetic_F0_csr(n, k, seed=1234, density=0.05)
+        return rp, col, sps.csr_matrix((vl, ix, ip), shape=(n, k))
+    return rp, col, G.synthetic_F0(n, k, seed=1234, density=0.05)
+
+
+def base_config(graph, k, n, nnz, layout):
+    """The same keys in both arms (GPU and reference)."""
+    return {"workload": workload_name(graph, k), "graph": graph, "k": int(k), "n": int(n), "nnz_directed": int(nnz),
+            "edges_undirected": int(nnz // 2), "f0": "synthetic p=0.05 U[0,1) seed 1234", "f_layout": layout}
 
 
 def alg_bytes(n, nnz, k, s=8):
@@ -120,50 +141,131 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def time_oracle(rp, col, F0, steps, warmup):
-    """Faithful CPU restatement (all 16 candidates per node, like the reference); all host threads."""
+# ------------------------------------------------------------------------------------------------
+# CPU restatement of the reference (oracle/): the cpu_baseline leg and the --impl reference arm
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def load_oracle_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to its children: the oracle must see the box's cores anyway (libgomp reads
+    the variable when the library is loaded)."""
+    os.environ["OMP_NUM_THREADS"] = str(host_cores())
+    os.environ.pop("OMP_THREAD_LIMIT", None)
     from oracle import oracle as O
     O.build()
-    P = O.make_params(K)
+    return O
+
+
+def time_oracle(rp, col, F0, k, steps, warmup, budget_s=200.0):
+    """Faithful CPU restatement (all 16 candidates per node, like the reference); all host threads.  A step is the
+    whole graph when the run fits the time budget; otherwise a fixed sample of the nodes (uset) per step, with the
+    metric counted over the sample's neighbour-list entries.  Returns (edges per second, cores, sample text)."""
+    O = load_oracle_all_cores()
+    P = O.make_params(k)
+    if hasattr(F0, "toarray"):
+        raise RuntimeError("the CPU restatement needs a dense F0")
+    n = len(rp) - 1
+    deg = np.diff(rp)
     F, s = F0, O.colsum(F0)
+    t0 = time.perf_counter()
+    r = O.step(rp, col, F, s, P, early_exit=False)           # probe: one full step (also the first warm-up step)
+    probe = time.perf_counter() - t0
+    F, s = r.F, r.sumF
+    total_steps = steps + max(warmup, 1)
+    mask, frac, sample = None, 1.0, f"{steps} full steps of the workload (all 16 candidates per node), {max(warmup, 1)} warm-up"
+    if probe * total_steps > budget_s:
+        frac = max(budget_s / (probe * total_steps), 1.0 / 64.0)
+        rng = np.random.default_rng(99)
+        mask = (rng.random(n) < frac).astype(np.uint8)
+        sample = (f"{steps} steps over a fixed {100 * mask.mean():.1f} % node sample (uset, {int(deg[mask != 0].sum())} neighbour-list entries; "
+                  f"all 16 candidates per node; the LLH pass after each step still covers the whole graph), {max(warmup, 1)} warm-up; "
+                  f"one full step took {probe:.2f} s")
+    edges = int(deg.sum()) if mask is None else int(deg[mask != 0].sum())
     times = []
-    for i in range(warmup + steps):
+    for i in range(total_steps - 1):
         t0 = time.perf_counter()
-        r = O.step(rp, col, F, s, P, early_exit=False)
+        r = O.step(rp, col, F, s, P, node_mask=mask, early_exit=False)
         dt = time.perf_counter() - t0
-        if i >= warmup:
+        if i >= max(warmup, 1) - 1:
             times.append(dt)
         F, s = r.F, r.sumF
-    return float(np.mean(times)), O.num_threads()
+    sec = float(np.mean(times)) if times else probe
+    return edges / sec, O.num_threads(), sample, sec
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rp, col, F0 = load_workload()
+    rp, col, F0 = load_workload(args.graph, args.k)
     n, nnz = len(rp) - 1, len(col)
-    sec, cores = time_oracle(rp, col, F0, args.steps, args.warmup)
-    val = nnz / sec
-    sample = f"{args.steps} full steps of the workload (all 16 candidates per node), {args.warmup} warm-up"
+    val, cores, sample, sec = time_oracle(rp, col, F0, args.k, args.steps, args.warmup)
     print(json.dumps({
         "impl": "reference", "metric": "edges/sec in F-gradient step", "value": val, "unit": "edges/s",
+        "unit_note": "directed neighbour-list entries per second (2 per undirected edge)",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "iters_per_sec": 1.0 / sec, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "com-amazon topology (SNAP fixture) + synthetic F0",
-        "config": {"workload": WORKLOAD, "n": n, "nnz_directed": nnz, "k": K,
-                   "note": "CPU restatement of the reference (oracle/, C + OpenMP), NOT Spark: no JVM in the image"},
+        "dtype": "f64", "data": "SNAP topology (package data) or generated R-MAT + synthetic F0",
+        "config": base_config(args.graph, args.k, n, nnz, args.layout),
+        "note": "CPU restatement of the reference (oracle/, C + OpenMP, -O3 -march=native), NOT Spark: no JVM in the image. PARITY UNPINNED.",
         "cpu_baseline": {"value": val, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+# ------------------------------------------------------------------------------------------------
+def measure_traffic(args, kernel_regex):
+    """DRAM bytes of ONE launch of the step kernel, measured now by a side process under ncu (same workload, same
+    library); None when ncu is not available.  Never overlaps the timed region."""
+    if args.no_traffic:
+        return None, "skipped (--no-traffic)"
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", f"regex:{kernel_regex}",
+           "--launch-skip", "4", "--launch-count", "1", "--csv", sys.executable, os.path.join(REPO, "tools", "profile_step.py"),
+           str(args.k), "5", "2", args.graph]
+    env = dict(os.environ, BIGCLAM_AB_SPARSE="1" if args.layout == "sparse" else "0")
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env).stdout
+    except Exception as exc:                # noqa: BLE001
+        return None, f"ncu failed: {exc!r}"
+    tot = 0.0
+    seen = 0
+    for line in out.splitlines():
+        if "dram__bytes_" in line:
+            parts = [p.strip('"') for p in line.split('","')]
+            try:
+                v = float(parts[-1].replace(",", ""))
+                unit = parts[-2].lower()
+            except ValueError:
+                continue
+            mult = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, None)
+            if mult is None:
+                continue
+            tot += v * mult
+            seen += 1
+    if seen < 2:
+        return None, "ncu gave no dram__bytes rows"
+    return int(tot), "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu side process in this run"
+
+
+def sparse_layout_bytes(indptr, rp, col):
+    """Bytes the sparse layout has to move per launch: every neighbour's row block once per edge (+ its 8-byte header
+    and the 4-byte neighbour id), every own row block read once and written once (+ header each way)."""
+    cnt = np.diff(indptr)
+    blk = 8 * ((cnt + 1) // 2 * 2) + 2 * ((cnt + 7) // 8 * 8)
+    return int(blk[col].sum() + 12 * len(col) + 2 * blk.sum() + 16 * (len(rp) - 1))
+
+
 def run_single(args):
     import torch
-    from bigclam_apachespark_b200 import BigClam
+    from bigclam_apachespark_b200 import BigClam, _lib
 
     torch.cuda.set_device(0)
-    rp, col, F0 = load_workload()
+    K = args.k
+    rp, col, F0 = load_workload(args.graph, K)
     n, nnz = len(rp) - 1, len(col)
     sparse = args.layout == "sparse"
     b = BigClam(device=0, time_kernels=True, sparse_rows=sparse)
@@ -174,6 +276,8 @@ def run_single(args):
 
     # ---- value: device-resident loop ----
     b._run(4, 0.0, args.warmup)                      # W untimed warm-up steps
+    if sparse:
+        b.tile_stats()                               # reset the counters
     sampler = ClockSampler(0)
     sampler.start()
     torch.cuda.synchronize()
@@ -189,29 +293,19 @@ def run_single(args):
     ms_per_step = total_ms / args.steps
     value = nnz / (ms_per_step * 1e-3)
     llh_end = float(b.last_trace[-1])
+    tiles = b.tile_stats() if sparse else None
 
-    # ---- roofline of the dominant kernel (step_kernel) ----
+    # ---- roofline of the dominant kernel ----
     peak, peak_src = hbm_peak()
     balg = alg_bytes(n, nnz, K)
     kavg_ms = kern_ms / max(n_step_kernels, 1)
     achieved = balg / (kavg_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(REPO, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("step_kernel_dram_bytes_per_launch")
-
-    layout_bytes = None
-    if sparse:
-        # bytes the sparse layout actually has to move per launch (row blocks: 10 B per padded entry + 8 B header):
-        # every neighbour row once per edge, every own row read and written once
-        cnt = np.diff(b.F_csr()[0])
-        blk = 10 * ((cnt + 3) // 4 * 4) + 8
-        layout_bytes = int((blk[col].sum() + 4 * nnz) + 2 * blk.sum() + 16 * n)
+    kernel = "tile_step_kernel" if sparse else "step_kernel"
+    layout_bytes = sparse_layout_bytes(b.F_csr()[0], rp, col) if sparse else balg
 
     # ---- e2e: per-call C ABI with host buffers ----
     mask = torch.ones(n, dtype=torch.uint8).pin_memory()
     llh = C.c_double(); nupd = C.c_int64()
-    from bigclam_apachespark_b200 import _lib
     lib = _lib.load()
     for _ in range(3):
         _lib.check(lib.bigclam_step(b._ctx, mask.data_ptr(), C.byref(llh), C.byref(nupd)), b._ctx)
@@ -227,7 +321,7 @@ def run_single(args):
 
     # ---- workload A of SURVEY §8d: the reference's own init (conductance seeds, 0/1 indicator columns) ----
     extra_a = None
-    if not args.no_init_a and not hasattr(F0, "tocsr"):
+    if not args.no_init_a and not hasattr(F0, "tocsr") and n <= 2_000_000:
         t0 = time.perf_counter()
         b.initNeighborComF(K)
         init_s = time.perf_counter() - t0
@@ -240,34 +334,43 @@ def run_single(args):
         torch.cuda.synchronize()
         ms_a = ea.elapsed_time(eb) / args.steps
         kms_a, nk_a, _ = b.kernel_time()
-        extra_a = {"workload": "com-amazon K=200, F0 = initNeighborComF(200) (bigclam4-7.scala:81-108: 0/1 indicator columns of the 200 best-conductance seeds)",
+        extra_a = {"workload": f"{args.graph} K={K}, F0 = initNeighborComF({K}) (bigclam4-7.scala:81-108: 0/1 indicator columns of the best-conductance seeds)",
                    "value": nnz / (ms_a * 1e-3), "unit": "edges/s", "ms_per_step": ms_a, "step_kernel_ms": kms_a / max(nk_a, 1),
-                   "roofline_frac": balg / (kms_a / max(nk_a, 1) * 1e-3) / 1e9 / peak, "host_init_seconds": init_s,
+                   "roofline_frac": balg / (kms_a / max(nk_a, 1) * 1e-3) / 1e9 / peak, "init_seconds": init_s,
                    "llh_end": float(b.last_trace[-1])}
+    b.close()
 
-    # ---- CPU baseline beside it (bounded: 2 faithful steps after 1 warm-up) ----
+    # ---- DRAM traffic of one launch, measured now (side process under ncu) ----
+    traffic, traffic_src = measure_traffic(args, kernel)
+
+    # ---- CPU baseline beside it (bounded: 5 faithful steps after 1 warm-up) ----
     cpu = None
     if not args.no_cpu and not hasattr(F0, "tocsr"):
-        sec, cores = time_oracle(rp, col, F0, 2, 1)
-        cpu = {"value": nnz / sec, "unit": "edges/s", "cores": cores, "kind": "port",
-               "sample": "2 full steps of the same workload (all 16 candidates per node) after 1 warm-up; CPU restatement of the reference, not Spark",
-               "ms_per_step": sec * 1e3}
+        val, cores, sample, sec = time_oracle(rp, col, F0, K, 5, 1, budget_s=45.0)
+        cpu = {"value": val, "unit": "edges/s", "cores": cores, "kind": "port",
+               "sample": sample + "; CPU restatement of the reference (oracle/, -O3 -march=native), not Spark", "ms_per_step": sec * 1e3}
 
+    cfg = base_config(args.graph, K, n, nnz, args.layout)
     print(json.dumps({
-        "metric": "edges/sec in F-gradient step", "value": value, "unit": "edges/s", "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "metric": "edges/sec in F-gradient step", "value": value, "unit": "edges/s",
+        "unit_note": "directed neighbour-list entries per second (2 per undirected edge)", "value_undirected_edges_per_s": value / 2,
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "iters_per_sec": 1e3 / ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "com-amazon topology (SNAP fixture) + synthetic F0",
-        "config": {"workload": WORKLOAD, "n": n, "nnz_directed": nnz, "k": K, "parallelism": "1 GPU",
-                   "l2": "inputs (F 536 MB x2 buffers) larger than L2, no flush", "llh_end": llh_end},
+        "vs_baseline": None, "dtype": "f64", "data": "SNAP topology (package data) or generated R-MAT + synthetic F0",
+        "config": cfg, "parallelism": "1 GPU",
+        "l2": ("sparse rows: working set ~2 x %.0f MB, L2-resident by design, no flush" % (layout_bytes / 4e6)) if sparse
+              else "inputs (F, 2 buffers) larger than L2, no flush",
+        "llh_end": llh_end, "parity": "PARITY UNPINNED: checked against oracle/ (CPU restatement), not against outputs of the reference",
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(n_all),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None if sparse else traffic, "kernel": "sparse_step_kernel" if sparse else "step_kernel<4>",
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel,
                      "kernel_ms": kavg_ms, "alg_bytes_per_launch": balg, "peak_source": peak_src,
-                     "f_layout": args.layout, "layout_bytes_per_launch": layout_bytes},
+                     "f_layout": args.layout, "layout_bytes_per_launch": layout_bytes,
+                     "layout_frac": layout_bytes / (kavg_ms * 1e-3) / 1e9 / peak,
+                     "note": "achieved/frac use SURVEY 8(d)'s dense-model algorithmic bytes; layout_bytes_per_launch is what the sparse rows move, traffic what DRAM saw (the rest is L2)",
+                     "tiles": tiles},
         "cpu_baseline": cpu, "reference_init_workload": extra_a,
     }))
-    b.close()
 
 
 def main():
@@ -276,28 +379,24 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="amazon200", choices=sorted(CONFIGS), help="BASELINE.json config (default: the headline)")
+    ap.add_argument("--k", type=int, default=None, help="number of communities (overrides --config)")
+    ap.add_argument("--graph", default=None, help="fixture name or rmat:<nodes>:<edges> (overrides --config)")
+    ap.add_argument("--layout", default="sparse", choices=["dense", "sparse"],
+                    help="device layout of F: sparse rows like the reference's BSV[Double] (default), or dense n x K rows")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-init-a", action="store_true", help="skip the reference-style-init extra workload")
-    ap.add_argument("--k", type=int, default=200, help="number of communities (default: the headline K = 200)")
-    ap.add_argument("--layout", default="dense", choices=["dense", "sparse"],
-                    help="device layout of F: dense n x K rows, or sparse rows like the reference's BSV[Double]")
-    ap.add_argument("--graph", default="com-amazon", help="fixture name or rmat:<nodes>:<edges> (default: the headline workload)")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu side process that measures DRAM traffic")
     args = ap.parse_args()
-    global _GRAPH, WORKLOAD, K
-    _GRAPH = args.graph
-    K = args.k
-    if _GRAPH != "com-amazon" or K != 200:
-        WORKLOAD = f"{_GRAPH} K={K}, synthetic F0 (p=0.05 U[0,1), seed 1234), fp64"
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    cfg = CONFIGS[args.config]
+    args.graph = args.graph or cfg["graph"]
+    args.k = args.k or cfg["k"]
     if args.impl == "reference":
-        args.steps = min(args.steps, 20)     # bounded: each step is ~1-4 s of all-core CPU work
-        args.warmup = min(args.warmup, 1)
         return run_reference(args)
+    args.warmup = max(args.warmup, 3)
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        if args.layout == "sparse":
-            os.environ["BIGCLAM_SPARSE"] = "1"
         from bigclam_apachespark_b200 import dist
-        return dist.bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD, K)
+        return dist.bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, base_config)
     return run_single(args)
 
 

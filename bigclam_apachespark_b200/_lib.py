@@ -78,6 +78,7 @@ SIGNATURES = {
     "bigclam_device_accepted": (C.c_int, [_vp, C.POINTER(_vp)]),
     "bigclam_set_owned_nodes": (C.c_int, [_vp, _vp, _i64]),
     "bigclam_set_owned_range": (C.c_int, [_vp, _i64, _i64]),
+    "bigclam_set_uset": (C.c_int, [_vp, _vp]),
     "bigclam_step_local": (C.c_int, [_vp, C.POINTER(_vp)]),
     "bigclam_finish_local": (C.c_int, [_vp, _pd, _pi64]),
     "bigclam_collect_timing": (C.c_int, [_vp]),
@@ -87,6 +88,24 @@ SIGNATURES = {
     "bigclam_ipc_open_peers": (C.c_int, [_vp, _i32, _i32, _vp]),
     "bigclam_mark_all_changed": (C.c_int, [_vp]),
     "bigclam_ipc_handle_count": (C.c_int, [_vp]),
+    "bigclam_xchg_export": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "bigclam_xchg_open_peers": (C.c_int, [_vp, _vp]),
+    "bigclam_llh_finish_local": (C.c_int, [_vp, _pd]),
+    "bigclam_multi_create": (C.c_int, [C.POINTER(_vp), _i64, _vp, _vp, C.POINTER(Params), _i32, _vp]),
+    "bigclam_multi_destroy": (None, [_vp]),
+    "bigclam_multi_last_error": (C.c_char_p, [_vp]),
+    "bigclam_multi_world": (C.c_int, [_vp]),
+    "bigclam_multi_set_F": (C.c_int, [_vp, _vp]),
+    "bigclam_multi_set_F_csr": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "bigclam_multi_set_sumF": (C.c_int, [_vp, _vp]),
+    "bigclam_multi_get_F": (C.c_int, [_vp, _i32, _vp]),
+    "bigclam_multi_get_sumF": (C.c_int, [_vp, _i32, _vp]),
+    "bigclam_multi_get_F_nnz": (C.c_int, [_vp, _pi64]),
+    "bigclam_multi_get_F_csr": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "bigclam_multi_step": (C.c_int, [_vp, _vp, _pd, _pi64]),
+    "bigclam_multi_loglikelihood": (C.c_int, [_vp, _pd]),
+    "bigclam_multi_run": (C.c_int, [_vp, _i32, _dbl, _i64, _pd, _pi64, _vp, _i64]),
+    "bigclam_multi_get_kernel_time": (C.c_int, [_vp, _pd, _pi64]),
     "bigclam_set_F_csr": (C.c_int, [_vp, _vp, _vp, _vp]),
     "bigclam_get_F_nnz": (C.c_int, [_vp, _pi64]),
     "bigclam_get_F_csr": (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -94,6 +94,7 @@ struct bigclam_ctx {
     int32_t *d_tcol = nullptr;
     int32_t ntiles = 0, n_gen = 0;
     int32_t tile_edges = kTlMaxEdges;             // edge budget of a tile (0: no tiles), see retile()
+    int32_t tile_nodes = kTlMaxNodes;             // node budget of a tile
     unsigned int *d_stats = nullptr;              // [tiles on the tile path, tiles that fell back], BIGCLAM_F_TIME_KERNELS only
     // fused collective of the node-partitioned path (reduce_kernel publishes, xreduce_kernel adds up): this rank's
     // exchange buffer [2 halves][world][ld + 2] and flags [world], and every rank's (peer memory, incl. our own)
@@ -104,6 +105,7 @@ struct bigclam_ctx {
     double *x_peer_buf[8] = {nullptr};
     unsigned long long *x_peer_flags[8] = {nullptr};
     bool x_ipc = false;                           // peers' buffers came through CUDA IPC (closed on destroy)
+    bool local_mask = false;                      // bigclam_set_uset: the node-partitioned step kernels honour d_mask
     std::vector<int64_t> h_rowptr;                // host copy of the CSR row pointers (order / tile rebuilds)
     std::vector<int32_t> h_col;
     std::vector<int32_t> h_owned;                 // owned nodes (processing order is derived from it)
@@ -314,7 +316,7 @@ static int rebuild_sparse_lists(bigclam_ctx *ctx, const std::vector<NodeMeta> &m
         TileMeta t{};
         t.pos0 = (int32_t)pos;
         t.ecol0 = (int32_t)tcol.size();
-        while (pos < cnt && t.nn < kTlMaxNodes && t.ne + meta[(size_t)pos].deg <= budget) {
+        while (pos < cnt && t.nn < ctx->tile_nodes && t.ne + meta[(size_t)pos].deg <= budget) {
             const NodeMeta &m = meta[(size_t)pos];
             for (int32_t e = 0; e < m.deg; ++e) tcol.push_back(ctx->h_col[(size_t)(m.e0 + e)] | (int32_t)((uint32_t)t.nn << 28));
             t.ne += m.deg;
@@ -548,7 +550,7 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
             free_ctx(ctx);
             return BIGCLAM_ECUDA;
         }
-        sbps = std::min(sbps, kTlBlocksPerSM);
+        sbps = std::min(sbps, tl_blocks_that_fit(ld, ctx->sp_wpb));
         ctx->sp_grid = ctx->num_sms * sbps;
         ctx->h_work_init = 0;
         if (const char *ev = std::getenv("BIGCLAM_TILE_EDGES")) ctx->tile_edges = std::max(0, std::min(kTlMaxEdges, std::atoi(ev)));
@@ -719,13 +721,14 @@ static int retile(bigclam_ctx *ctx, uint64_t words_used) {
     const double nn = (double)std::max<int64_t>(1, ctx->n);
     const double avg_cnt = std::max(1.0, (double)sp_host_nnz(ctx->n, hdr.data()) / nn);
     const double avg16 = std::max(1.0, (double)words_used / 2.0 / nn);
-    // the rows of a tile (its edges' and its nodes' own) must fit the staging chunks, their entries the slots
-    // (worst case: no two of them on the same component), with 10 % to spare
-    const double rows = std::min((double)kTlStage16 / (1.1 * avg16), (double)kTlSlots / (1.1 * avg_cnt));
-    int budget = (int)rows - kTlMaxNodes;
-    budget = std::max(0, std::min(kTlMaxEdges, budget));
-    if (budget < 6) budget = 0;
-    if (budget == ctx->tile_edges) return BIGCLAM_OK;
+    // the neighbour rows of a tile must fit the staging chunks, its nodes' own rows theirs, and all their entries
+    // the slots (worst case: no two of them on the same component) — with 10-15 % to spare
+    int nodes = std::max(0, std::min(kTlMaxNodes, (int)((double)kTlOwn16 / (1.15 * avg16))));
+    const double rows = std::min((double)kTlStage16 / (1.1 * avg16), (double)kTlSlots / (1.1 * avg_cnt) - nodes);
+    int budget = std::max(0, std::min(kTlMaxEdges, (int)rows));
+    if (budget < 6 || nodes < 2) budget = 0;
+    if (budget == ctx->tile_edges && nodes == ctx->tile_nodes) return BIGCLAM_OK;
+    ctx->tile_nodes = std::max(1, nodes);
     ctx->tile_edges = budget;
     std::vector<int32_t> order = ctx->h_owned;
     return rebuild_order_list(ctx, ctx->h_rowptr, order);
@@ -1300,12 +1303,21 @@ extern "C" int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi)
     return rebuild_order(ctx, rp);
 }
 
+// uset of the following bigclam_step_local calls (n bytes from host memory, copied asynchronously; NULL = all vertices)
+extern "C" int bigclam_set_uset(bigclam_ctx *ctx, const uint8_t *node_mask) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    ctx->local_mask = node_mask != nullptr;
+    if (node_mask != nullptr) CU(cudaMemcpyAsync(ctx->d_mask, node_mask, (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    return BIGCLAM_OK;
+}
+
 extern "C" int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
     if (int rd = drop_speculation(ctx)) return rd;
     StepArgs a;
-    fill_args(ctx, a, true, nullptr, false);
+    fill_args(ctx, a, true, ctx->local_mask ? ctx->d_mask : nullptr, false);
     int rc = timed_launch(ctx, a, true);
     if (rc) return rc;
     if (partials_dev) *partials_dev = ctx->d_partials;

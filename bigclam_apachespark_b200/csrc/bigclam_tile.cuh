@@ -25,42 +25,74 @@ namespace bigclam {
 
 constexpr int kTlMaxNodes = 8;
 constexpr int kTlMaxEdges = 32;
-#ifndef BIGCLAM_TL_STAGE16          // row staging buffer of a tile, in 16-byte chunks (neighbour rows + own rows)
-#define BIGCLAM_TL_STAGE16 320
+#ifndef BIGCLAM_TL_STAGE16          // neighbour-row staging buffer of a tile, in 16-byte chunks (>= 256: it becomes xs[512])
+#define BIGCLAM_TL_STAGE16 288
 #endif
-#ifndef BIGCLAM_TL_SLOTS            // touched components of all nodes of a tile
-#define BIGCLAM_TL_SLOTS 256
+#ifndef BIGCLAM_TL_OWN16            // own-row staging buffer, in 16-byte chunks
+#define BIGCLAM_TL_OWN16 80
+#endif
+#ifndef BIGCLAM_TL_SLOTS            // touched components of all nodes of a tile (>= 1.5 * BIGCLAM_TL_ACT)
+#define BIGCLAM_TL_SLOTS 384
+#endif
+#ifndef BIGCLAM_TL_ACT              // active components of all nodes of a tile
+#define BIGCLAM_TL_ACT 160
+#endif
+#ifndef BIGCLAM_TL_ENT              // neighbour entries on active components (>= 128: the pair list lives there later)
+#define BIGCLAM_TL_ENT 224
+#endif
+#ifndef BIGCLAM_TL_EROW             // neighbour entries of a tile (flat entry -> row map)
+#define BIGCLAM_TL_EROW 416
 #endif
 #ifndef BIGCLAM_TL_BULK             // 1: cp.async.bulk + mbarrier; 0: each lane copies its rows with 16-byte loads
 #define BIGCLAM_TL_BULK 1
 #endif
 #ifndef BIGCLAM_TL_ILP2             // 1: the exp/log pass of the line search evaluates two pairs per lane (two independent chains)
-#define BIGCLAM_TL_ILP2 0
+#define BIGCLAM_TL_ILP2 1
 #endif
+#ifndef BIGCLAM_TL_UF               // unroll factor of the flat (lane-strided, uniform) loops over entries / slots / pairs
+#define BIGCLAM_TL_UF 1
+#endif
+#ifndef BIGCLAM_TL_UJ               // unroll factor of the merged dot / decide loops
+#define BIGCLAM_TL_UJ 1
+#endif
+#define BIGCLAM_PRAGMA(x) _Pragma(#x)
+#define BIGCLAM_UNROLL(n) BIGCLAM_PRAGMA(unroll n)
 #ifndef BIGCLAM_TL_WARPS
-#define BIGCLAM_TL_WARPS 8
+#define BIGCLAM_TL_WARPS 6
 #endif
 #ifndef BIGCLAM_TL_BLOCKS
 #define BIGCLAM_TL_BLOCKS 2
 #endif
 constexpr int kTlStage16 = BIGCLAM_TL_STAGE16;
+constexpr int kTlOwn16 = BIGCLAM_TL_OWN16;
 constexpr int kTlSlots = BIGCLAM_TL_SLOTS;
+constexpr int kTlAct = BIGCLAM_TL_ACT;
+constexpr int kTlEnt = BIGCLAM_TL_ENT;
+constexpr int kTlErow = BIGCLAM_TL_EROW;
 constexpr int kTlWarps = BIGCLAM_TL_WARPS;
 constexpr int kTlBlocksPerSM = BIGCLAM_TL_BLOCKS;
 constexpr int kTlThreads = kTlWarps * 32;
+static_assert(kTlStage16 >= 256, "the neighbour staging buffer doubles as xs[32 edges][16 trials]");
+static_assert(2 * kTlSlots >= 3 * kTlAct, "fg must hold (f, g) and sumF - f of the active components after compaction");
+static_assert(kTlEnt >= 128 && kTlEnt <= 256, "entry lists: the pair list (512 uint16) overlays ent_val; edge ids are bytes");
+static_assert(kTlAct <= 255, "active-component ids of the entry lists are bytes");
 
 // per-warp shared memory of the tile path (W = ldp / 32 mask words per node)
 __host__ __device__ inline size_t tl_warp_bytes(int ld) {
     const size_t W = (size_t)sp_ldp(ld) / 32;
-    size_t b = 16 * (size_t)kTlStage16;                 // stage
-    b += 16 * (size_t)kTlSlots;                         // fg
-    b += 8 * 256;                                       // xs
+    size_t b = 16 * (size_t)kTlStage16;                 // stageN (later xs)
+    b += 16 * (size_t)kTlOwn16;                         // stageO
+    b += 16 * (size_t)kTlSlots;                         // fg (later fa | asfm)
+    b += 8 * (size_t)kTlEnt;                            // ent_val (later plist)
     b += 8 * 32 + 8 * 8 + 8 * 8;                        // we, n_llh, n_G2
     b += 4 * 2 * kTlMaxNodes * W + 4 * kTlMaxNodes;     // tmask, fmask, n_u
-    b += 2 * 2 * (size_t)kTlSlots;                      // slot_c, alist
+    b += 4 * (size_t)kTlAct;                            // lcnt
+    b += 2 * 2 * (size_t)kTlSlots;                      // slot_c (later ac), amap
+    b += 2 * ((size_t)kTlAct + 2);                      // loff
     b += 2 * 2 * kTlMaxNodes * W;                       // pref_t, pref_f
-    b += 2 * (40 + 40 + 12 + 12 + 8 + 8);               // e_soff, e_cnt, n_es, n_sb, n_m, n_tot
-    b += 32 + 256 + 8 + 8;                              // e_acnt, plist, n_js, n_want
+    b += 2 * (40 + 40 + 12 + 12 + 12 + 8 + 8);          // e_soff, e_cnt, n_es, n_sb, n_ab, n_m, n_tot
+    b += 2 * (size_t)kTlEnt + 8 + 8;                    // ent_e, ent_a, n_js, n_want
+    b += (size_t)kTlErow + 2 * 34 + 32;                 // erow, epos, e_ni
     return (b + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t tl_region_bytes(int ld) {
@@ -71,13 +103,19 @@ __host__ __device__ inline size_t tl_region_bytes(int ld) {
 __host__ __device__ inline size_t tl_block_smem_bytes(int ld, int wpb) {
     return sizeof(double) * (kMaxSteps + (size_t)sp_ldp(ld) + kTlWarps) + (size_t)wpb * tl_region_bytes(ld);
 }
-// warps per block: as many resident warps per SM as the shared memory (227 KB, 1 KB reserved per block) allows
+// warps per block: as many resident warps per SM as the shared memory (227 KB, 1 KB reserved per block) allows, in
+// at most kTlMaxBlocks blocks (wide rows run more blocks of fewer warps)
+constexpr int kTlMaxBlocks = 4;
+inline int tl_blocks_that_fit(int ld, int wpb) {
+    const size_t bytes = tl_block_smem_bytes(ld, wpb) + 1024 + 256;
+    const int blocks = (int)((size_t)233472 / bytes);
+    const int cap = (wpb == kTlWarps) ? kTlBlocksPerSM : kTlMaxBlocks;      // the full-size block is built for kTlBlocksPerSM
+    return blocks > cap ? cap : blocks;
+}
 inline int tl_warps_per_block(int ld) {
     int best = 1, best_warps = 0;
-    for (int wpb = kTlWarps; wpb >= 1; wpb >>= 1) {
-        const size_t bytes = tl_block_smem_bytes(ld, wpb) + 1024 + 256;
-        const int blocks = (int)((size_t)233472 / bytes);
-        const int warps = (blocks > kTlBlocksPerSM ? kTlBlocksPerSM : blocks) * wpb;
+    for (int wpb = kTlWarps; wpb >= 1; --wpb) {
+        const int warps = tl_blocks_that_fit(ld, wpb) * wpb;
         if (warps > best_warps) { best_warps = warps; best = wpb; }
     }
     return best;
@@ -127,14 +165,15 @@ struct TlWarp {
     const double *s_sumF;
     double S2_all;                   // sum_c sumF_c^2 (fixed order)
     EdgeConst ec;
-    unsigned char *stage;
+    unsigned char *stageN, *stageO;
     double2 *fg;
-    double *xs, *we, *n_llh, *n_G2;
+    double *xs, *ent_val, *we, *n_llh, *n_G2;
     unsigned long long *mbar;
-    unsigned int *tmask, *fmask;
+    unsigned int *tmask, *fmask, *lcnt;
     int *n_u;
-    unsigned short *slot_c, *alist, *pref_t, *pref_f, *e_soff, *e_cnt, *n_es, *n_sb, *n_m, *n_tot;
-    unsigned char *e_acnt, *plist, *n_want;
+    unsigned short *slot_c, *amap, *loff, *plist, *pref_t, *pref_f, *e_soff, *e_cnt, *n_es, *n_sb, *n_ab, *n_m, *n_tot;
+    unsigned char *ent_e, *ent_a, *erow, *e_ni, *n_want;
+    unsigned short *epos;
     signed char *n_js;
     int lane, ld, W;
     unsigned parity;
@@ -144,33 +183,43 @@ struct TlWarp {
         lane = lane_;
         W = sp_ldp(ld_) / 32;
         parity = 0;
-        stage = p;                                 p += 16 * (size_t)kTlStage16;
-        fg = reinterpret_cast<double2 *>(p);       p += 16 * (size_t)kTlSlots;
-        xs = reinterpret_cast<double *>(p);        p += 8 * 256;
-        we = reinterpret_cast<double *>(p);        p += 8 * 32;
-        n_llh = reinterpret_cast<double *>(p);     p += 8 * 8;
-        n_G2 = reinterpret_cast<double *>(p);      p += 8 * 8;
+        stageN = p;                                       p += 16 * (size_t)kTlStage16;
+        xs = reinterpret_cast<double *>(stageN);          // (after the rows have been turned into per-component lists)
+        stageO = p;                                       p += 16 * (size_t)kTlOwn16;
+        fg = reinterpret_cast<double2 *>(p);              p += 16 * (size_t)kTlSlots;
+        ent_val = reinterpret_cast<double *>(p);          p += 8 * (size_t)kTlEnt;
+        plist = reinterpret_cast<unsigned short *>(ent_val);   // (after the merged dot / decide loop)
+        we = reinterpret_cast<double *>(p);               p += 8 * 32;
+        n_llh = reinterpret_cast<double *>(p);            p += 8 * 8;
+        n_G2 = reinterpret_cast<double *>(p);             p += 8 * 8;
         tmask = reinterpret_cast<unsigned int *>(p);      p += 4 * (size_t)kTlMaxNodes * W;
         fmask = reinterpret_cast<unsigned int *>(p);      p += 4 * (size_t)kTlMaxNodes * W;
         n_u = reinterpret_cast<int *>(p);                 p += 4 * kTlMaxNodes;
+        lcnt = reinterpret_cast<unsigned int *>(p);       p += 4 * (size_t)kTlAct;
         slot_c = reinterpret_cast<unsigned short *>(p);   p += 2 * (size_t)kTlSlots;
-        alist = reinterpret_cast<unsigned short *>(p);    p += 2 * (size_t)kTlSlots;
+        amap = reinterpret_cast<unsigned short *>(p);     p += 2 * (size_t)kTlSlots;
+        loff = reinterpret_cast<unsigned short *>(p);     p += 2 * ((size_t)kTlAct + 2);
         pref_t = reinterpret_cast<unsigned short *>(p);   p += 2 * (size_t)kTlMaxNodes * W;
         pref_f = reinterpret_cast<unsigned short *>(p);   p += 2 * (size_t)kTlMaxNodes * W;
         e_soff = reinterpret_cast<unsigned short *>(p);   p += 2 * 40;
         e_cnt = reinterpret_cast<unsigned short *>(p);    p += 2 * 40;
         n_es = reinterpret_cast<unsigned short *>(p);     p += 2 * 12;
         n_sb = reinterpret_cast<unsigned short *>(p);     p += 2 * 12;
+        n_ab = reinterpret_cast<unsigned short *>(p);     p += 2 * 12;
         n_m = reinterpret_cast<unsigned short *>(p);      p += 2 * 8;
         n_tot = reinterpret_cast<unsigned short *>(p);    p += 2 * 8;
-        e_acnt = p;                                       p += 32;
-        plist = p;                                        p += 256;
+        epos = reinterpret_cast<unsigned short *>(p);     p += 2 * 34;
+        ent_e = p;                                        p += (size_t)kTlEnt;
+        ent_a = p;                                        p += (size_t)kTlEnt;
+        erow = p;                                         p += (size_t)kTlErow;
+        e_ni = p;                                         p += 32;
         n_js = reinterpret_cast<signed char *>(p);        p += 8;
         n_want = p;
     }
 
     // inclusive scan over the lanes of a group of gs lanes (sub = lane within the group)
     __device__ __forceinline__ int group_scan(int v, int gs, int sub) const {
+#pragma unroll 1
         for (int o = 1; o < gs; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, v, o);
             if (sub >= o) v += t;
@@ -178,6 +227,7 @@ struct TlWarp {
         return v;
     }
     __device__ __forceinline__ double group_sum(double v, int gs) const {
+#pragma unroll
         for (int o = 16; o > 0; o >>= 1)
             if (o < gs) v += __shfl_xor_sync(0xffffffffu, v, o);
         return v;
@@ -209,21 +259,30 @@ struct TlWarp {
         }
         const int ce = (int)sp_cnt(hv), cu = (int)sp_cnt(hu);
         const int qe = (int)(sp_words((uint32_t)ce) >> 1), qu = (int)(sp_words((uint32_t)cu) >> 1);     // 16-byte chunks
-        int incl_e = qe, incl_u = qu, incl_d = nm.deg, maxdeg = nm.deg;
+        // one scan for four counts: chunks of the neighbour rows (bits 0-11) and of the own rows (12-21), degrees (22-31
+        // would overflow: separate), entries of the neighbour rows
+        int incl_q = qe | (qu << 16), incl_d = nm.deg | (ce << 16), maxdeg = nm.deg;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t1 = __shfl_up_sync(0xffffffffu, incl_e, o);
-            const int t2 = __shfl_up_sync(0xffffffffu, incl_u, o);
+            const int t1 = __shfl_up_sync(0xffffffffu, incl_q, o);
             const int t3 = __shfl_up_sync(0xffffffffu, incl_d, o);
             const int t4 = __shfl_xor_sync(0xffffffffu, maxdeg, o);
-            if (lane >= o) { incl_e += t1; incl_u += t2; incl_d += t3; }
+            if (lane >= o) { incl_q += t1; incl_d += t3; }
             maxdeg = max(maxdeg, t4);
         }
-        const int total_e = __shfl_sync(0xffffffffu, incl_e, 31);
-        const int total16 = total_e + __shfl_sync(0xffffffffu, incl_u, 31);
-        if (total16 > kTlStage16) return false;
-        const int soff_e = incl_e - qe, soff_u = total_e + incl_u - qu;
-        if (lane < ne) { e_soff[lane] = (unsigned short)soff_e; e_cnt[lane] = (unsigned short)ce; }
+        const int incl_e = incl_q & 0xffff, incl_u = incl_q >> 16, incl_c = incl_d >> 16;
+        incl_d &= 0xffff;
+        const int total_q = __shfl_sync(0xffffffffu, incl_q, 31);
+        const int total_e = total_q & 0xffff, total_u = total_q >> 16;
+        const int T = __shfl_sync(0xffffffffu, incl_c, 31);                 // neighbour entries of the tile
+        if (total_e > kTlStage16 || total_u > kTlOwn16 || T > kTlErow) return false;
+        const int soff_e = incl_e - qe, soff_u = incl_u - qu;
+        if (lane < ne) {
+            e_soff[lane] = (unsigned short)soff_e;
+            e_cnt[lane] = (unsigned short)ce;
+            epos[lane] = (unsigned short)(incl_c - ce);
+            e_ni[lane] = (unsigned char)ni;
+        }
         if (lane < nn) {
             e_soff[32 + lane] = (unsigned short)soff_u;
             e_cnt[32 + lane] = (unsigned short)cu;
@@ -236,24 +295,24 @@ struct TlWarp {
 #pragma unroll 1
         for (int i = lane; i < nn * W; i += 32) { tmask[i] = 0u; fmask[i] = 0u; }
 #if BIGCLAM_TL_BULK
-        if (total16 > 0) {
-            fence_proxy_async();                         // this warp's earlier accesses to the stage come first
+        if (total_e + total_u > 0) {
+            fence_proxy_async();                         // this warp's earlier accesses to the buffers come first
             __syncwarp();
-            if (lane == 0) mbar_expect_tx(mbar, 16u * (unsigned)total16);
+            if (lane == 0) mbar_expect_tx(mbar, 16u * (unsigned)(total_e + total_u));
             __syncwarp();
-            if (qe > 0) bulk_g2s(stage + 16 * (size_t)soff_e, pool_in + sp_off8(hv), 16u * (unsigned)qe, mbar);
-            if (qu > 0) bulk_g2s(stage + 16 * (size_t)soff_u, pool_in + sp_off8(hu), 16u * (unsigned)qu, mbar);
+            if (qe > 0) bulk_g2s(stageN + 16 * (size_t)soff_e, pool_in + sp_off8(hv), 16u * (unsigned)qe, mbar);
+            if (qu > 0) bulk_g2s(stageO + 16 * (size_t)soff_u, pool_in + sp_off8(hu), 16u * (unsigned)qu, mbar);
             mbar_wait(mbar, parity);
             parity ^= 1u;
         }
 #else
         {
             const uint4 *se = reinterpret_cast<const uint4 *>(pool_in + sp_off8(hv));
-            uint4 *de = reinterpret_cast<uint4 *>(stage) + soff_e;
+            uint4 *de = reinterpret_cast<uint4 *>(stageN) + soff_e;
 #pragma unroll 1
             for (int q = 0; q < qe; ++q) de[q] = __ldg(se + q);
             const uint4 *su = reinterpret_cast<const uint4 *>(pool_in + sp_off8(hu));
-            uint4 *du = reinterpret_cast<uint4 *>(stage) + soff_u;
+            uint4 *du = reinterpret_cast<uint4 *>(stageO) + soff_u;
 #pragma unroll 1
             for (int q = 0; q < qu; ++q) du[q] = __ldg(su + q);
         }
@@ -266,10 +325,12 @@ struct TlWarp {
         const int g = lane >> lgs, sub = lane & (gs - 1);
         const bool gv = g < nn;
         const unsigned gmask = gs == 32 ? 0xffffffffu : ((1u << gs) - 1u);
+        const unsigned below = (1u << sub) - 1u;
+        const int gsh = g << lgs;
         const int gW = g * W;
         const int cu_g = gv ? (int)e_cnt[32 + g] : 0;
-        double *ov = reinterpret_cast<double *>(stage + 16 * (size_t)(gv ? e_soff[32 + g] : 0));
-        const unsigned short *oi = sp_idx(ov, (uint32_t)cu_g);
+        double *ov = reinterpret_cast<double *>(stageO + 16 * (size_t)(gv ? e_soff[32 + g] : 0));
+        unsigned short *oi = sp_idx(ov, (uint32_t)cu_g);
         double fusf = 0.0, fufu = 0.0;
 #pragma unroll 1
         for (int i = sub; i < cu_g; i += gs) {
@@ -282,63 +343,28 @@ struct TlWarp {
         fusf = group_sum(fusf, gs);
         fufu = group_sum(fufu, gs);
         __syncwarp();
-        {
-            int carry = 0;
 #pragma unroll 1
-            for (int w0 = 0; w0 < W; w0 += gs) {
-                const int w = w0 + sub;
-                const bool ok = gv && w < W;
-                const unsigned mk = ok ? fmask[gW + w] : 0u;
-                const int pc = __popc(mk);
-                const int incl = group_scan(pc, gs, sub);
-                if (ok) { pref_f[gW + w] = (unsigned short)(carry + incl - pc); tmask[gW + w] = mk; }
-                carry += __shfl_sync(0xffffffffu, incl, (g << lgs) + gs - 1);
-            }
-        }
+        for (int i = lane; i < nn * W; i += 32) tmask[i] = fmask[i];
         __syncwarp();
-
-        // ---------------- C. PRE dots (:162-165), lane = edge ----------------
-        double *rv = reinterpret_cast<double *>(stage + 16 * (size_t)soff_e);
+        // ---------------- C1. components the neighbours' rows touch ----------------
+        double *rv = reinterpret_cast<double *>(stageN + 16 * (size_t)soff_e);
         unsigned short *ri = sp_idx(rv, (uint32_t)ce);
-        double x = 0.0;
         if (lane < ne) {
-            const unsigned int *fm = fmask + ni * W;
-            unsigned int *tmk = tmask + ni * W;
-            const unsigned short *pf = pref_f + ni * W;
-            const double *ove = reinterpret_cast<const double *>(stage + 16 * (size_t)e_soff[32 + ni]);
+            unsigned char *er = erow + (incl_c - ce);
 #pragma unroll 1
-            for (int i = 0; i < ce; ++i) {
-                const int c = ri[i];
-                const int w = c >> 5;
-                const unsigned bit = 1u << (c & 31);
-                atomicOr(tmk + w, bit);
-                const unsigned fmw = fm[w];
-                if (fmw & bit) x = fma(rv[i], ove[pf[w] + __popc(fmw & (bit - 1u))], x);
-            }
+            for (int i = 0; i < ce; ++i) er[i] = (unsigned char)lane;         // flat entry -> row
         }
-        // ---------------- D. edge terms (:166-167), llh_u (:168) ----------------
-        double wgt;
-        const double term = edge_term<true>(x, ec, wgt);
-        xs[lane] = term;
-        we[lane] = wgt;
         __syncwarp();
-        const int es_g = gv ? (int)n_es[g] : 0;
-        const int deg_g = gv ? (int)n_es[g + 1] - es_g : 0;
-        double llh_g = 0.0;
-        {
-            double S1 = 0.0;
-#pragma unroll 1
-            for (int e = es_g; e < es_g + deg_g; ++e) S1 += xs[e];            // CSR order, like the reference's fold
-            llh_g = (S1 - fusf) + fufu;
+        // (from here on the loops over the neighbours' entries are FLAT: entry t of the tile = entry t - epos[row] of row erow[t])
+BIGCLAM_UNROLL(BIGCLAM_TL_UF)
+        for (int t = lane; t < T; t += 32) {
+            const int row = erow[t];
+            const double *vv = reinterpret_cast<const double *>(stageN + 16 * (size_t)e_soff[row]);
+            const int c = sp_idx(vv, (uint32_t)e_cnt[row])[t - (int)epos[row]];
+            atomicOr(tmask + (int)e_ni[row] * W + (c >> 5), 1u << (c & 31));
         }
-        if (!do_ls) {
-            if (gv && sub == 0) sp->node_llh[n_u[g]] = llh_g;
-            __syncwarp();
-            return true;
-        }
-        if (gv && sub == 0) n_llh[g] = llh_g;
-
-        // ---------------- E. slots of the touched components ----------------
+        __syncwarp();
+        // ---------------- E. slots of the touched components (ascending component order per node) ----------------
         int tot_g = 0;
         {
             int carry = 0;
@@ -349,24 +375,23 @@ struct TlWarp {
                 const int pc = ok ? __popc(tmask[gW + w]) : 0;
                 const int incl = group_scan(pc, gs, sub);
                 if (ok) pref_t[gW + w] = (unsigned short)(carry + incl - pc);
-                carry += __shfl_sync(0xffffffffu, incl, (g << lgs) + gs - 1);
+                carry += __shfl_sync(0xffffffffu, incl, gsh + gs - 1);
             }
             tot_g = gv ? carry : 0;
         }
-        int base_g = 0, total_slots = 0, maxtot = 0;
+        int base_g = 0, total_slots = 0;
 #pragma unroll 1
         for (int q = 0; q < nn; ++q) {
             const int t = __shfl_sync(0xffffffffu, tot_g, q << lgs);
             if (q < g) base_g += t;
             total_slots += t;
-            maxtot = max(maxtot, t);
         }
         if (total_slots > kTlSlots) return false;
         if (gv && sub == 0) { n_sb[g] = (unsigned short)base_g; n_tot[g] = (unsigned short)tot_g; }
 #pragma unroll 1
         for (int i = lane; i < total_slots; i += 32) fg[i] = make_double2(0.0, 0.0);
         __syncwarp();
-        // ---------------- F. own row -> slots ----------------
+        // ---------------- C2. every entry learns its slot (kept in place of the component index) ----------------
 #pragma unroll 1
         for (int i = sub; i < cu_g; i += gs) {
             const int c = oi[i];
@@ -376,25 +401,62 @@ struct TlWarp {
             fg[slot].x = ov[i];
             slot_c[slot] = (unsigned short)c;
         }
+BIGCLAM_UNROLL(BIGCLAM_TL_UF)
+        for (int t = lane; t < T; t += 32) {
+            const int row = erow[t];
+            double *vv = reinterpret_cast<double *>(stageN + 16 * (size_t)e_soff[row]);
+            unsigned short *pc = sp_idx(vv, (uint32_t)e_cnt[row]) + (t - (int)epos[row]);
+            const int c = *pc;
+            const int node = e_ni[row];
+            const int w = c >> 5;
+            const unsigned bit = 1u << (c & 31);
+            const int slot = (int)n_sb[node] + pref_t[node * W + w] + __popc(tmask[node * W + w] & (bit - 1u));
+            slot_c[slot] = (unsigned short)c;
+            *pc = (unsigned short)slot;
+        }
         __syncwarp();
-        // ---------------- G. sum_v fv / (1 - p) (:167-168), edge by edge in CSR order; entries -> slot ids ----------------
+        // ---------------- C3. PRE dots (:162-165), lane = edge ----------------
+        double x = 0.0;
+        if (lane < ne) {
+#pragma unroll 1
+            for (int i = 0; i < ce; ++i) x = fma(rv[i], fg[ri[i]].x, x);
+        }
+        // ---------------- D. edge terms (:166-167), llh_u (:168) ----------------
+        double wgt;
+        const double term = edge_term<true>(x, ec, wgt);
+        we[lane] = wgt;
+        const int es_g = gv ? (int)n_es[g] : 0;
+        const int deg_g = gv ? (int)n_es[g + 1] - es_g : 0;
+        double llh_g = 0.0;
+        {
+            double S1 = 0.0;
+#pragma unroll 1
+            for (int r = 0; r < maxdeg; ++r) {            // CSR order, like the reference's fold
+                const double t = __shfl_sync(0xffffffffu, term, (es_g + r) & 31);
+                if (r < deg_g) S1 += t;
+            }
+            llh_g = (S1 - fusf) + fufu;
+        }
+        if (!do_ls) {
+            if (gv && sub == 0) sp->node_llh[n_u[g]] = llh_g;
+            __syncwarp();
+            return true;
+        }
+        if (gv && sub == 0) n_llh[g] = llh_g;
+        __syncwarp();
+        // ---------------- G. sum_v fv / (1 - p) (:167-168), edge by edge in CSR order ----------------
 #pragma unroll 1
         for (int r = 0; r < maxdeg; ++r) {
             if (r < deg_g) {
                 const int e = es_g + r;
                 const double wv = we[e];
                 const int cn = e_cnt[e];
-                double *vv = reinterpret_cast<double *>(stage + 16 * (size_t)e_soff[e]);
-                unsigned short *vi = sp_idx(vv, (uint32_t)cn);
+                const double *vv = reinterpret_cast<const double *>(stageN + 16 * (size_t)e_soff[e]);
+                const unsigned short *vi = sp_idx(vv, (uint32_t)cn);
 #pragma unroll 1
                 for (int i = sub; i < cn; i += gs) {
-                    const int c = vi[i];
-                    const int w = c >> 5;
-                    const unsigned bit = 1u << (c & 31);
-                    const int slot = base_g + pref_t[gW + w] + __popc(tmask[gW + w] & (bit - 1u));
+                    const int slot = vi[i];
                     fg[slot].y = fma(wv, vv[i], fg[slot].y);
-                    slot_c[slot] = (unsigned short)c;
-                    vi[i] = (unsigned short)slot;
                 }
             }
             __syncwarp();
@@ -404,13 +466,15 @@ struct TlWarp {
         bool hi_lane = false;
         {
             double G2 = 0.0, SF2 = 0.0;
+            int maxtot = tot_g;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxtot = max(maxtot, __shfl_xor_sync(0xffffffffu, maxtot, o));
 #pragma unroll 1
             for (int k0 = 0; k0 < maxtot; k0 += gs) {
                 const int k = k0 + sub;
-                const bool ok = k < tot_g;
-                const int slot = base_g + k;
                 bool act = false;
-                if (ok) {
+                if (k < tot_g) {
+                    const int slot = base_g + k;
                     const double2 v = fg[slot];
                     const double sf = s_sumF[slot_c[slot]];
                     const double gr = (v.y - sf) + v.x;
@@ -420,133 +484,185 @@ struct TlWarp {
                     act = (v.x > 0.0 || gr > 0.0);
                     hi_lane |= act && (v.x + gr > max_f);
                 }
-                const unsigned gb = (__ballot_sync(0xffffffffu, act) >> (g << lgs)) & gmask;
-                if (act) alist[base_g + m_g + __popc(gb & ((1u << sub) - 1u))] = (unsigned short)slot;
-                m_g += __popc(gb);
+                m_g += __popc((__ballot_sync(0xffffffffu, act) >> gsh) & gmask);
             }
             G2 = group_sum(G2, gs);
             SF2 = group_sum(SF2, gs);
             // an untouched component has fu = 0 and gradient -sumF_c: its square is part of S2_all
-            if (gv && sub == 0) { n_G2[g] = (S2_all - SF2) + G2; n_m[g] = (unsigned short)m_g; }
+            if (gv && sub == 0) n_G2[g] = (S2_all - SF2) + G2;
         }
-        int maxm = m_g;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxm = max(maxm, __shfl_xor_sync(0xffffffffu, maxm, o));
+        if (!gv) m_g = 0;
+        int ab_g = 0, maxm = 0;
+#pragma unroll 1
+        for (int q = 0; q < nn; ++q) {
+            const int t = __shfl_sync(0xffffffffu, m_g, q << lgs);
+            if (q < g) ab_g += t;
+            maxm = max(maxm, t);
+        }
+        if (gv && sub == 0) { n_ab[g] = (unsigned short)ab_g; n_m[g] = (unsigned short)m_g; }
         // no candidate of any node of the tile can reach MAX_F_ (the largest step is 1): the upper clamp is dropped
         const bool need_hi = __any_sync(0xffffffffu, hi_lane);
         __syncwarp();
-        // ---------------- I. neighbour rows shrink to their entries on active components ----------------
-        if (lane < ne) {
-            int p = 0;
+        // the active components move to the front, in slot order: fg[a] = (fu_c, grad_c), slot_c[a] = c; amap: slot -> a
+        int A = 0;
 #pragma unroll 1
-            for (int i = 0; i < ce; ++i) {
-                const int slot = ri[i];
-                const double2 v = fg[slot];
-                if (v.x > 0.0 || v.y > 0.0) {
-                    rv[p] = rv[i];
-                    ri[p] = (unsigned short)slot;
-                    ++p;
-                }
-            }
-            e_acnt[lane] = (unsigned char)p;
+        for (int p0 = 0; p0 < total_slots; p0 += 32) {
+            const int p = p0 + lane;
+            const bool ok = p < total_slots;
+            double2 v = make_double2(0.0, 0.0);
+            int c = 0;
+            if (ok) { v = fg[p]; c = slot_c[p]; }
+            const bool act = ok && (v.x > 0.0 || v.y > 0.0);
+            const unsigned bal = __ballot_sync(0xffffffffu, act);
+            __syncwarp();                        // every lane has read its slot; the writes land at or below them
+            const int an = A + __popc(bal & lt_mask);
+            if (act && an < kTlSlots) { fg[an] = v; slot_c[an] = (unsigned short)c; }
+            if (ok) amap[p] = act ? (unsigned short)an : (unsigned short)0xffffu;
+            A += __popc(bal);
+            __syncwarp();
+        }
+        if (A > kTlAct) return false;
+        double *asfm = reinterpret_cast<double *>(fg + kTlAct);            // sumF_c - fu_c of the active components
+#pragma unroll 1
+        for (int t = lane; t < A; t += 32) { asfm[t] = s_sumF[slot_c[t]] - fg[t].x; lcnt[t] = 0u; }
+        __syncwarp();
+        // ---------------- I. the neighbours' entries on active components, listed per component ----------------
+BIGCLAM_UNROLL(BIGCLAM_TL_UF)
+        for (int t = lane; t < T; t += 32) {
+            const int row = erow[t];
+            const double *vv = reinterpret_cast<const double *>(stageN + 16 * (size_t)e_soff[row]);
+            const unsigned an = amap[sp_idx(vv, (uint32_t)e_cnt[row])[t - (int)epos[row]]];
+            if (an != 0xffffu) atomicAdd(lcnt + an, 1u);
         }
         __syncwarp();
-        // ---------------- J. line search (:172-180): 16 candidates x edges, 16 edges at a time ----------------
+        int TE = 0;
+#pragma unroll 1
+        for (int t0 = 0; t0 < A; t0 += 32) {
+            const int t = t0 + lane;
+            const int c = (t < A) ? (int)lcnt[t] : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (t < A) { loff[t] = (unsigned short)(TE + incl - c); lcnt[t] = (unsigned int)(TE + incl - c); }
+            TE += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (TE > kTlEnt) return false;
+        if (lane == 0) loff[A] = (unsigned short)TE;
+        __syncwarp();
+BIGCLAM_UNROLL(BIGCLAM_TL_UF)
+        for (int t = lane; t < T; t += 32) {
+            const int row = erow[t];
+            const double *vv = reinterpret_cast<const double *>(stageN + 16 * (size_t)e_soff[row]);
+            const int i = t - (int)epos[row];
+            const unsigned an = amap[sp_idx(vv, (uint32_t)e_cnt[row])[i]];
+            if (an != 0xffffu) {
+                const unsigned q = atomicAdd(lcnt + an, 1u);
+                ent_val[q] = vv[i];
+                ent_e[q] = (unsigned char)row;
+                ent_a[q] = (unsigned char)an;
+            }
+        }
+        __syncwarp();
+        // ---------------- J. line search (:172-180), lane = (node 2q + h, trial j) ----------------
+        // One loop over the node's active components gives, per candidate: newfu.sfT and newfu.newfu (:176,:180) and,
+        // through the components' entry lists, newfu.fv of every edge (xs[edge][trial], component order ascending).
         const int h = lane >> 4, j = lane & 15;
         const double s = s_steps[j < nsteps ? j : 0];
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 1
-        for (int hb = 0; hb < ne; hb += 16) {
-            int np = 0;
-#pragma unroll 1
-            for (int r = 0; r < 8; ++r) {
-                if (hb + 2 * r >= ne) break;
-                const int e = hb + 2 * r + h;
-                const bool valid = e < ne;
-                double D = 0.0;
-                if (valid) {
-                    const int ac = e_acnt[e];
-                    const double *vv = reinterpret_cast<const double *>(stage + 16 * (size_t)e_soff[e]);
-                    const unsigned short *vi = sp_idx(vv, (uint32_t)e_cnt[e]);
-                    if (!need_hi) {
-#pragma unroll 1
-                        for (int k = 0; k < ac; ++k) {
-                            const double2 v = fg[vi[k]];
-                            D = fma(clamp_step0_lo(v.x, s, v.y), vv[k], D);
-                        }
-                    } else {
-#pragma unroll 1
-                        for (int k = 0; k < ac; ++k) {
-                            const double2 v = fg[vi[k]];
-                            D = fma(clamp_step0(v.x, s, v.y, max_f), vv[k], D);
-                        }
-                    }
-                }
-                const bool low = D <= ec.x_lo;
-                const bool inr = valid && !low && (D < ec.x_hi);
-                const int pid = (2 * r + h) * 16 + j;
-                if (valid) xs[pid] = inr ? D : (low ? ec.t_lo : ec.t_hi) + D;
-                const unsigned bal = __ballot_sync(0xffffffffu, inr);
-                if (inr) plist[np + __popc(bal & lt_mask)] = (unsigned char)pid;
-                np += __popc(bal);
-            }
-            __syncwarp();
-#pragma unroll 1
-#if BIGCLAM_TL_ILP2
-            for (int b = 0; b < np; b += 64) {          // exp/log on full warps of the pairs that need it, two per lane
-                const int k1 = b + lane, k2 = b + 32 + lane;
-                const bool ok1 = k1 < np, ok2 = k2 < np;
-                const int pid1 = ok1 ? (int)plist[k1] : 0, pid2 = ok2 ? (int)plist[k2] : 0;
-                const double x1 = ok1 ? xs[pid1] : 1.0, x2 = ok2 ? xs[pid2] : 1.0;
-                const double o1 = 1.0 - exp_neg(x1), o2 = 1.0 - exp_neg(x2);
-                const double t1 = log_pos(o1) + x1, t2 = log_pos(o2) + x2;
-                if (ok1) xs[pid1] = t1;
-                if (ok2) xs[pid2] = t2;
-            }
-#else
-            for (int b = 0; b < np; b += 32) {          // exp/log on full warps of the pairs that need it
-                const int k = b + lane;
-                const bool ok = k < np;
-                const int pid = ok ? (int)plist[k] : 0;
-                const double xv = ok ? xs[pid] : 1.0;
-                const double omp = 1.0 - exp_neg(xv);
-                const double t = log_pos(omp) + xv;
-                if (ok) xs[pid] = t;
-            }
-#endif
-            __syncwarp();
+BIGCLAM_UNROLL(BIGCLAM_TL_UF)
+        for (int p = lane; p < ne * 16; p += 32) xs[p] = 0.0;             // (the staged rows are not needed any more)
+        __syncwarp();
+        double oa[4], ob[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {               // lane = (node 2q + h, trial j): its edges of this half, in order
-                const int node = 2 * q + h;
-                if (node < nn) {
-                    const int e_lo = max((int)n_es[node], hb), e_hi = min((int)n_es[node + 1], hb + 16);
-#pragma unroll 1
-                    for (int e = e_lo; e < e_hi; ++e) acc[q] += xs[(e - hb) * 16 + j];
-                }
+        for (int q = 0; q < 4; ++q) {
+            if (2 * q >= nn) { oa[q] = 0.0; ob[q] = 0.0; continue; }          // (warp-uniform)
+            const int node = 2 * q + h;
+            const bool nv = node < nn;
+            const int t0 = nv ? (int)n_ab[node] : 0, mm = nv ? (int)n_m[node] : 0;
+            const int q0 = nv ? (int)loff[t0] : 0, nq = nv ? (int)loff[t0 + mm] - q0 : 0;
+            // the two half-warps (two nodes) walk in lockstep: common trip counts, predicated bodies
+            const int mmax = max(mm, __shfl_xor_sync(0xffffffffu, mm, 16));
+            const int qmax = max(nq, __shfl_xor_sync(0xffffffffu, nq, 16));
+            double a1 = 0.0, b1 = 0.0;
+BIGCLAM_UNROLL(BIGCLAM_TL_UJ)
+            for (int t = 0; t < mmax; ++t) {
+                const bool ok = t < mm;
+                const int ti = t0 + (ok ? t : 0);
+                const double2 v = fg[ti];
+                const double nf = need_hi ? clamp_step0(v.x, s, v.y, max_f) : clamp_step0_lo(v.x, s, v.y);
+                const double sf = asfm[ti] + nf;                        // sfT = (sumF - fu) + newfu   (:176)
+                a1 = ok ? fma(nf, sf, a1) : a1;
+                b1 = ok ? fma(nf, nf, b1) : b1;
             }
-            __syncwarp();
+BIGCLAM_UNROLL(BIGCLAM_TL_UJ)
+            for (int k = 0; k < qmax; ++k) {
+                const bool ok = k < nq;
+                const int qq = q0 + (ok ? k : 0);
+                const double2 v = fg[ent_a[qq]];
+                const double nf = need_hi ? clamp_step0(v.x, s, v.y, max_f) : clamp_step0_lo(v.x, s, v.y);
+                double *cell = xs + (int)ent_e[qq] * 16 + j;
+                const double cur = *cell;
+                if (ok) *cell = fma(nf, ent_val[qq], cur);
+            }
+            oa[q] = a1;
+            ob[q] = b1;
         }
+        __syncwarp();
+        // pairs whose x is outside (x_lo, x_hi) are constants after the clamp (:166); the others are listed and exp/log
+        // runs on full warps of them
+        int np = 0;
+BIGCLAM_UNROLL(BIGCLAM_TL_UF)
+        for (int p0 = 0; p0 < ne * 16; p0 += 32) {
+            const int p = p0 + lane;                       // ne * 16 is a multiple of 16: p < ne * 16 for whole half-warps
+            const bool valid = p < ne * 16;
+            const double D = valid ? xs[p] : 0.0;
+            const bool low = D <= ec.x_lo;
+            const bool inr = valid && !low && (D < ec.x_hi);
+            if (valid && !inr) xs[p] = (low ? ec.t_lo : ec.t_hi) + D;
+            const unsigned bal = __ballot_sync(0xffffffffu, inr);
+            if (inr) plist[np + __popc(bal & lt_mask)] = (unsigned short)p;
+            np += __popc(bal);
+        }
+        __syncwarp();
+#if BIGCLAM_TL_ILP2
+#pragma unroll 1
+        for (int b = 0; b < np; b += 64) {
+            const int k1 = b + lane, k2 = b + 32 + lane;
+            const bool ok1 = k1 < np, ok2 = k2 < np;
+            const int pid1 = ok1 ? (int)plist[k1] : 0, pid2 = ok2 ? (int)plist[k2] : 0;
+            const double x1 = ok1 ? xs[pid1] : 1.0, x2 = ok2 ? xs[pid2] : 1.0;
+            const double o1 = 1.0 - exp_neg(x1), o2 = 1.0 - exp_neg(x2);
+            const double t1 = log_pos(o1) + x1, t2 = log_pos(o2) + x2;
+            if (ok1) xs[pid1] = t1;
+            if (ok2) xs[pid2] = t2;
+        }
+#else
+#pragma unroll 1
+        for (int b = 0; b < np; b += 32) {
+            const int k = b + lane;
+            const bool ok = k < np;
+            const int pid = ok ? (int)plist[k] : 0;
+            const double xv = ok ? xs[pid] : 1.0;
+            const double omp = 1.0 - exp_neg(xv);
+            const double t = log_pos(omp) + xv;
+            if (ok) xs[pid] = t;
+        }
+#endif
+        __syncwarp();
         // ---------------- K. Armijo test (:181), largest passing step (:182) ----------------
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int node = 2 * q + h;
             const bool nv = node < nn;
-            double oa = 0.0, ob = 0.0;
-            if (nv) {
-                const int mb = n_sb[node], mm = n_m[node];
-#pragma unroll 1
-                for (int t = 0; t < mm; ++t) {
-                    const int slot = alist[mb + t];
-                    const double2 v = fg[slot];
-                    const double nf = need_hi ? clamp_step0(v.x, s, v.y, max_f) : clamp_step0_lo(v.x, s, v.y);
-                    const double sf = (s_sumF[slot_c[slot]] - v.x) + nf;          // sfT = (sumF - fu) + newfu   (:176)
-                    oa = fma(nf, sf, oa);
-                    ob = fma(nf, nf, ob);
-                }
-            }
             bool pass = false;
             if (nv) {
-                const double result = (acc[q] - oa) + ob;
+                double acc = 0.0;
+                const int e1 = n_es[node + 1];
+#pragma unroll 1
+                for (int e = n_es[node]; e < e1; ++e) acc += xs[e * 16 + j];          // the node's edges, in CSR order
+                const double result = (acc - oa[q]) + ob[q];
                 const double rhs = n_llh[node] + (a->alpha * s) * n_G2[node];
                 pass = (j < nsteps) && (n_want[node] != 0) && (result >= rhs);
             }
@@ -563,13 +679,13 @@ struct TlWarp {
             const int t = t0 + sub;
             bool isnz = false, ch = false;
             if (js >= 0 && t < m_g) {
-                const double2 v = fg[alist[base_g + t]];
+                const double2 v = fg[ab_g + t];
                 const double nr = clamp_step(v.x, sstar, v.y, a->min_f, max_f);
                 isnz = nr != 0.0;
                 ch = v.x != nr;
             }
-            nz += __popc((__ballot_sync(0xffffffffu, isnz) >> (g << lgs)) & gmask);
-            nd += __popc((__ballot_sync(0xffffffffu, ch) >> (g << lgs)) & gmask);
+            nz += __popc((__ballot_sync(0xffffffffu, isnz) >> gsh) & gmask);
+            nd += __popc((__ballot_sync(0xffffffffu, ch) >> gsh) & gmask);
         }
         if (js < 0) { nz = cu_g; nd = 0; }
         const int wrow = gv ? (int)sp_words((uint32_t)nz) : 0;
@@ -604,23 +720,20 @@ struct TlWarp {
                 double nr = 0.0, f = 0.0;
                 int c = 0;
                 if (js >= 0 && t < m_g) {
-                    const int slot = alist[base_g + t];
-                    const double2 v = fg[slot];
-                    c = slot_c[slot];
+                    const double2 v = fg[ab_g + t];
+                    c = slot_c[ab_g + t];
                     f = v.x;
                     nr = clamp_step(f, sstar, v.y, a->min_f, max_f);
                     isnz = nr != 0.0;
                     ch = f != nr;
                 }
-                const unsigned bz = (__ballot_sync(0xffffffffu, isnz) >> (g << lgs)) & gmask;
-                const unsigned bd = (__ballot_sync(0xffffffffu, ch) >> (g << lgs)) & gmask;
-                const unsigned below = (1u << sub) - 1u;
+                const unsigned bz = (__ballot_sync(0xffffffffu, isnz) >> gsh) & gmask;
+                const unsigned bd = (__ballot_sync(0xffffffffu, ch) >> gsh) & gmask;
                 if (isnz) {
                     const int p = pz + __popc(bz & below);
                     outv[p] = nr;
                     outi[p] = (unsigned short)c;
                     if (kPush)
-#pragma unroll 1
                         for (int pr = 0; pr < sp->n_peers; ++pr) {
                             double *pv = sp->peer_pool[pr] + off;
                             pv[p] = nr;
@@ -646,7 +759,6 @@ struct TlWarp {
                 const uint4 blk = src[q];
                 dst[q] = blk;
                 if (kPush)
-#pragma unroll 1
                     for (int pr = 0; pr < sp->n_peers; ++pr) reinterpret_cast<uint4 *>(sp->peer_pool[pr] + off)[q] = blk;
             }
         }
@@ -658,7 +770,6 @@ struct TlWarp {
             sp->accepted[u] = (int8_t)js;
             sp->node_llh[u] = llh_g;
             if (kPush)
-#pragma unroll 1
                 for (int pr = 0; pr < sp->n_peers; ++pr) sp->peer_hdr[pr][u] = hnew;
         }
         __syncwarp();

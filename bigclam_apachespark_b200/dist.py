@@ -144,6 +144,28 @@ class CudaEngine:
         buf = (C.c_ubyte * (world * nbytes)).from_buffer_copy(allh.cpu().numpy().tobytes())
         self.check(self.lib.bigclam_ipc_open_peers(self.ctx, world, rank, buf), self.ctx)
 
+    def open_xchg(self, dist, rank: int, world: int):
+        """Fused collective (sparse rows): exchange buffers of every rank mapped through CUDA IPC; afterwards
+        step_local publishes this rank's sums to all ranks and finish_local / llh_finish add them up on the device
+        (rank order: the same bits everywhere) — no all-reduce by the host framework on the data path."""
+        torch = self.torch
+        mine = (C.c_ubyte * 128)()
+        self.check(self.lib.bigclam_xchg_export(self.ctx, world, rank, mine), self.ctx)
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).cuda()
+        allh = torch.empty(world * 128, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh, t)
+        buf = (C.c_ubyte * (world * 128)).from_buffer_copy(allh.cpu().numpy().tobytes())
+        self.check(self.lib.bigclam_xchg_open_peers(self.ctx, buf), self.ctx)
+        self.fused = True
+
+    def llh_finish(self) -> float:
+        v = C.c_double()
+        self.check(self.lib.bigclam_llh_finish_local(self.ctx, C.byref(v)), self.ctx)
+        return v.value
+
+    def set_uset(self, mask_ptr):
+        self.check(self.lib.bigclam_set_uset(self.ctx, mask_ptr), self.ctx)
+
     def mark_all_changed(self):
         self.check(self.lib.bigclam_mark_all_changed(self.ctx), self.ctx)
 
@@ -177,6 +199,9 @@ class DistBigClam:
             raise ValueError("sparse rows travel through the fused peer stores only (exchange='p2p')")
         if exchange == "p2p":
             engine.open_peers(self.dist, rank, world)
+            if getattr(engine, "sparse", False) and world > 1 and os.environ.get("BIGCLAM_NCCL_ALLREDUCE", "0") != "1":
+                engine.open_xchg(self.dist, rank, world)          # fused collective instead of the NCCL all-reduce
+        self.fused = bool(getattr(engine, "fused", False))
 
     @property
     def owned(self):
@@ -236,7 +261,8 @@ class DistBigClam:
         call (== the LLH the previous call returns, the fused identity) and n_updated; with
         sync=False nothing is read back and the host does not wait (None, None)."""
         part = self.e.step_local()
-        self.dist.all_reduce(part)                      # sum over ranks (:191-192, :219)
+        if not self.fused:
+            self.dist.all_reduce(part)                  # sum over ranks (:191-192, :219); fused: done by finish_local
         if self.exchange != "p2p":
             F_cur, F_next, _ = self.e.state()
             self._exchange_rows(F_cur, F_next)
@@ -246,6 +272,8 @@ class DistBigClam:
 
     def loglikelihood(self) -> float:
         part = self.e.llh_local()
+        if self.fused:
+            return self.e.llh_finish()
         self.dist.all_reduce(part)
         return float(part[2 * self.e.ld].item())
 
@@ -289,8 +317,10 @@ class DistBigClam:
 
 
 # ------------------------------------------------------------------------------------------------
-def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD, K):
-    """bench.py for N > 1: launched by torchrun, one rank per GPU, NCCL."""
+def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, base_config):
+    """bench.py for N > 1: launched by torchrun, one rank per GPU; torch.distributed (NCCL) is the plumbing (rendezvous,
+    IPC-handle all-gather, timing reductions), the data path is the step kernel's NVLink row stores plus the fused
+    collective (bigclam_xchg_*)."""
     import json
 
     import torch
@@ -303,9 +333,10 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rp, col, F0 = load_workload()
+    K = args.k
+    rp, col, F0 = load_workload(args.graph, K)
     n, nnz = len(rp) - 1, len(col)
-    sparse = os.environ.get("BIGCLAM_SPARSE", "0") == "1"
+    sparse = args.layout == "sparse"
     b = BigClam(device=local, time_kernels=True, record_accepted=True, sparse_rows=sparse)
     b.set_graph(rp, col).set_K(K)
     stream = torch.cuda.current_stream()
@@ -329,11 +360,12 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     e0.record(stream)
     launches = 0
     sync = d.exchange != "p2p"       # the NCCL delta exchange sizes its buffers on the host
+    per_step = 4 if d.fused else 3   # step kernel, reduction, (combine,) finish
     for _ in range(args.steps):
         d.step_nollh(sync=sync)
-        launches += 2
+        launches += per_step
     llh_end = d.loglikelihood()              # the LLH of the last call (tail pass, inside the timed region)
-    launches += 1
+    launches += 3
     e1.record(stream)
     dist.barrier()
     torch.cuda.synchronize()
@@ -342,17 +374,21 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     kms, nk, _ = eng.collect_timing()        # step-kernel events of the timed (asynchronous) region
-    # e2e: the reference-facing call (one full backtrackingLineSearchs per step, LLH read back by the host)
+    # e2e: the reference-facing call with host buffers (uset mask H2D from pinned memory, one full
+    # backtrackingLineSearchs per step, LLH and n_updated read back by the host)
     n_e2e = min(args.steps, 20)
+    mask = torch.ones(n, dtype=torch.uint8).pin_memory()
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
+        eng.set_uset(mask.data_ptr())
         d.backtrackingLineSearchs()
     torch.cuda.synchronize()
     te = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_e2e], device="cuda", dtype=torch.float64)
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
+    eng.set_uset(None)
     per_rank = torch.zeros(world, device="cuda", dtype=torch.float64)
     per_rank[rank] = kms / max(nk, 1)
     dist.all_reduce(per_rank)
@@ -362,23 +398,28 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, WORKLOAD,
     ms_per_step = total_ms / args.steps
     if rank == 0:
         peak, peak_src = hbm_peak()
+        value = nnz / (ms_per_step * 1e-3)
         print(json.dumps({
-            "metric": "edges/sec in F-gradient step", "value": nnz / (ms_per_step * 1e-3), "unit": "edges/s",
+            "metric": "edges/sec in F-gradient step", "value": value, "unit": "edges/s",
+            "unit_note": "directed neighbour-list entries per second (2 per undirected edge)", "value_undirected_edges_per_s": value / 2,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "iters_per_sec": 1e3 / ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "com-amazon topology (SNAP fixture) + synthetic F0",
-            "config": {"workload": WORKLOAD, "n": n, "nnz_directed": nnz, "k": K,
-                       "parallelism": f"node-partitioned x{world} ({'degree-sorted nodes dealt round-robin' if exchange == 'p2p' else 'nnz-balanced contiguous ranges'}), "
-                                      f"F replicated, all-reduce of [sum(old-new), llh, n_updated] + {d.exchange} row exchange per step",
-                       "l2": "inputs larger than L2, no flush", "llh_end": llh_end},
-            "clocks": clocks, "gpu_launches": launches,
+            "vs_baseline": None, "dtype": "f64", "data": "SNAP topology (package data) or generated R-MAT + synthetic F0",
+            "config": base_config(args.graph, K, n, nnz, args.layout),
+            "parallelism": f"node-partitioned x{world} ({'degree-sorted nodes dealt round-robin' if exchange == 'p2p' else 'nnz-balanced contiguous ranges'}), "
+                           f"F replicated, rows pushed into the peers' replicas by the step kernel (NVLink), sums [sum(old-new), llh, n_updated] by "
+                           f"{'the fused device-side collective (peer stores + flags)' if d.fused else 'an NCCL all-reduce'}",
+            "l2": "sparse rows: working set L2-resident by design, no flush" if sparse else "inputs larger than L2, no flush",
+            "llh_end": llh_end, "clocks": clocks, "gpu_launches": launches,
             "rank_step_kernel_ms": [round(float(x), 4) for x in per_rank.tolist()],
             "roofline": {"bound": "hbm", "achieved": alg_bytes(own_n, own_nnz, K) / (float(per_rank[0]) * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": alg_bytes(own_n, own_nnz, K) / (float(per_rank[0]) * 1e-3) / 1e9 / peak,
-                         "traffic": None, "kernel": "step_kernel<4,4> on rank 0 (owned rows only, incl. NVLink pushes)", "peak_source": peak_src},
-            "e2e": {"value": nnz / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 32 * world,
-                    "ms_per_step": e2e_ms, "note": "DistBigClam.backtrackingLineSearchs(): step kernel + all-reduce + sumF + separate LLH pass + all-reduce, "
-                                                   "LLH and n_updated read back by every rank each step; F replicas stay resident"},
+                         "traffic": None, "kernel": "step kernel of rank 0 (owned rows only, incl. NVLink pushes)", "peak_source": peak_src,
+                         "f_layout": args.layout},
+            "e2e": {"value": nnz / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(n) * world, "d2h_bytes_per_step": 16 * world,
+                    "ms_per_step": e2e_ms, "note": "per step and rank: bigclam_set_uset (mask H2D from pinned memory) + DistBigClam.backtrackingLineSearchs(): "
+                                                   "step kernel + reduction + collective + sumF + separate LLH pass + collective; LLH and n_updated read back "
+                                                   "by every rank each step; F replicas stay resident"},
             "cpu_baseline": None,
         }))
     dist.destroy_process_group()

@@ -80,7 +80,7 @@ class BigClam:
     def __init__(self, numCore: int = 36, minCom: int = 1000, maxCom: int = 9000, divCom: int = 100,
                  alpha: float = 0.05, beta: float = 0.1, MaxInter: int = 15, device: int = -1,
                  time_kernels: bool = False, record_accepted: bool = False, verbose: bool = False,
-                 sparse_rows: bool = False):
+                 sparse_rows: bool = False, numGPUs: int = 1, devices=None):
         self.numCore, self.minCom, self.maxCom, self.divCom = numCore, minCom, maxCom, divCom
         self.alpha, self.beta, self.MaxInter = alpha, beta, MaxInter
         self.MIN_P_, self.MAX_P_, self.MIN_F_, self.MAX_F_ = 0.0001, 0.9999, 0.0, 1000.0   # :40-43
@@ -93,6 +93,13 @@ class BigClam:
         self.rowptr = self.col = self.ids = None
         self._ctx = None
         self._F0 = None
+        # numGPUs > 1: all GPUs of the box behind one handle (bigclam_multi_*, sparse rows, fused NVLink collective) —
+        # the role `numCore` plays in the script (:14); devices: CUDA ordinals, default 0 .. numGPUs-1
+        self.numGPUs = int(numGPUs)
+        self.devices = None if devices is None else [int(d) for d in devices]
+        self._multi = None
+        if self.numGPUs > 1:
+            self.flags |= _lib.F_SPARSE_ROWS
 
     # ---- graph (collectNeighbor / Neightborbc, :50-51) ----
     def load_edge_list(self, path: str, multiplicity: str = "dedup"):
@@ -124,9 +131,23 @@ class BigClam:
         p.min_p, p.max_p, p.min_f, p.max_f = self.MIN_P_, self.MAX_P_, self.MIN_F_, self.MAX_F_
         p.device, p.flags = self.device, self.flags
         ctx = C.c_void_p()
+        if self.numGPUs > 1:
+            devs = None
+            if self.devices is not None:
+                devs = (C.c_int32 * self.numGPUs)(*self.devices[:self.numGPUs])
+            rc = lib.bigclam_multi_create(C.byref(ctx), self.n, self.rowptr.ctypes.data, self.col.ctypes.data, C.byref(p),
+                                          self.numGPUs, devs)
+            if rc != _lib.OK:
+                raise _lib.BigclamError(rc, (lib.bigclam_multi_last_error(None) or b"").decode())
+            self._multi = ctx
+            return self
         check(lib.bigclam_create(C.byref(ctx), self.n, self.rowptr.ctypes.data, self.col.ctypes.data, C.byref(p)))
         self._ctx = ctx
         return self
+
+    def _mcheck(self, rc):
+        if rc != _lib.OK:
+            raise _lib.BigclamError(rc, (_lib.load().bigclam_multi_last_error(self._multi) or b"").decode())
 
     def set_F_csr(self, indptr, indices, values, K=None, sumF=None):
         """F <- CSR rows (the reference's RDD[(Long, BSV[Double])], :97-104); sumF <- column sums unless given.
@@ -138,6 +159,12 @@ class BigClam:
             self.set_K(int(K))
         if len(indptr) != self.n + 1 or len(indices) != indptr[-1] or len(values) != indptr[-1]:
             raise ValueError("CSR arrays do not describe n rows")
+        if self._multi is not None:
+            self._mcheck(_lib.load().bigclam_multi_set_F_csr(self._multi, indptr.ctypes.data, indices.ctypes.data, values.ctypes.data))
+            if sumF is not None:
+                sumF = np.ascontiguousarray(sumF, dtype=np.float64)
+                self._mcheck(_lib.load().bigclam_multi_set_sumF(self._multi, sumF.ctypes.data))
+            return self
         check(_lib.load().bigclam_set_F_csr(self._need(), indptr.ctypes.data, indices.ctypes.data, values.ctypes.data), self._ctx)
         if sumF is not None:
             sumF = np.ascontiguousarray(sumF, dtype=np.float64)
@@ -148,11 +175,17 @@ class BigClam:
         """Current F as (indptr, indices, values): ascending indices inside a row, no stored zeros."""
         lib = _lib.load()
         nnz = C.c_int64()
-        check(lib.bigclam_get_F_nnz(self._need(), C.byref(nnz)), self._ctx)
+        if self._multi is not None:
+            self._mcheck(lib.bigclam_multi_get_F_nnz(self._multi, C.byref(nnz)))
+        else:
+            check(lib.bigclam_get_F_nnz(self._need(), C.byref(nnz)), self._ctx)
         indptr = np.empty(self.n + 1, dtype=np.int64)
         indices = np.empty(max(nnz.value, 1), dtype=np.int32)
         values = np.empty(max(nnz.value, 1), dtype=np.float64)
-        check(lib.bigclam_get_F_csr(self._ctx, indptr.ctypes.data, indices.ctypes.data, values.ctypes.data), self._ctx)
+        if self._multi is not None:
+            self._mcheck(lib.bigclam_multi_get_F_csr(self._multi, indptr.ctypes.data, indices.ctypes.data, values.ctypes.data))
+        else:
+            check(lib.bigclam_get_F_csr(self._ctx, indptr.ctypes.data, indices.ctypes.data, values.ctypes.data), self._ctx)
         return indptr, indices[:nnz.value], values[:nnz.value]
 
     def set_F(self, F, sumF=None):
@@ -161,24 +194,45 @@ class BigClam:
             m = F.tocsr()
             return self.set_F_csr(m.indptr, m.indices, m.data, K=m.shape[1], sumF=sumF)
         F = np.ascontiguousarray(F, dtype=np.float64)
-        if self._ctx is None or F.shape[1] != self.K:
+        if (self._ctx is None and self._multi is None) or F.shape[1] != self.K:
             self.set_K(F.shape[1])
         if F.shape != (self.n, self.K):
             raise ValueError(f"F must be {self.n} x {self.K}")
+        if self._multi is not None:
+            self._mcheck(_lib.load().bigclam_multi_set_F(self._multi, F.ctypes.data))
+            if sumF is not None:
+                sumF = np.ascontiguousarray(sumF, dtype=np.float64)
+                self._mcheck(_lib.load().bigclam_multi_set_sumF(self._multi, sumF.ctypes.data))
+            return self
         check(_lib.load().bigclam_set_F(self._ctx, F.ctypes.data), self._ctx)
         if sumF is not None:
             sumF = np.ascontiguousarray(sumF, dtype=np.float64)
             check(_lib.load().bigclam_set_sumF(self._ctx, sumF.ctypes.data), self._ctx)
         return self
 
+    def replica_F(self, rank: int = 0) -> np.ndarray:
+        """numGPUs > 1: the F replica of one rank (all replicas are identical after every call)."""
+        out = np.empty((self.n, self.K), dtype=np.float64)
+        self._mcheck(_lib.load().bigclam_multi_get_F(self._multi, int(rank), out.ctypes.data))
+        return out
+
+    def replica_sumF(self, rank: int = 0) -> np.ndarray:
+        out = np.empty(self.K, dtype=np.float64)
+        self._mcheck(_lib.load().bigclam_multi_get_sumF(self._multi, int(rank), out.ctypes.data))
+        return out
+
     @property
     def F(self) -> np.ndarray:
+        if self._multi is not None:
+            return self.replica_F(0)
         out = np.empty((self.n, self.K), dtype=np.float64)
         check(_lib.load().bigclam_get_F(self._need(), out.ctypes.data), self._ctx)
         return out
 
     @property
     def sumF(self) -> np.ndarray:
+        if self._multi is not None:
+            return self.replica_sumF(0)
         out = np.empty(self.K, dtype=np.float64)
         check(_lib.load().bigclam_get_sumF(self._need(), out.ctypes.data), self._ctx)
         return out
@@ -222,22 +276,32 @@ class BigClam:
             mask_ptr = mask.ctypes.data
         llh = C.c_double()
         nupd = C.c_int64()
-        check(_lib.load().bigclam_step(self._need(), mask_ptr, C.byref(llh), C.byref(nupd)), self._ctx)
+        if self._multi is not None:
+            self._mcheck(_lib.load().bigclam_multi_step(self._multi, mask_ptr, C.byref(llh), C.byref(nupd)))
+        else:
+            check(_lib.load().bigclam_step(self._need(), mask_ptr, C.byref(llh), C.byref(nupd)), self._ctx)
         self.last_n_updated = nupd.value
         return llh.value
 
     def loglikelihood(self) -> float:
         """bigclamv3-7.scala:106-120 / Bigclamv2.scala:187-200."""
         llh = C.c_double()
-        check(_lib.load().bigclam_loglikelihood(self._need(), C.byref(llh)), self._ctx)
+        if self._multi is not None:
+            self._mcheck(_lib.load().bigclam_multi_loglikelihood(self._multi, C.byref(llh)))
+        else:
+            check(_lib.load().bigclam_loglikelihood(self._need(), C.byref(llh)), self._ctx)
         return llh.value
 
     def _run(self, variant: int, rel_tol: float, max_outer: int, trace_cap: int = 65536):
         trace = np.full(trace_cap, np.nan)
         llh = C.c_double()
         calls = C.c_int64()
-        check(_lib.load().bigclam_run(self._need(), variant, rel_tol, max_outer, C.byref(llh), C.byref(calls),
-                                      trace.ctypes.data, trace_cap), self._ctx)
+        if self._multi is not None:
+            self._mcheck(_lib.load().bigclam_multi_run(self._multi, variant, rel_tol, max_outer, C.byref(llh), C.byref(calls),
+                                                       trace.ctypes.data, trace_cap))
+        else:
+            check(_lib.load().bigclam_run(self._need(), variant, rel_tol, max_outer, C.byref(llh), C.byref(calls),
+                                          trace.ctypes.data, trace_cap), self._ctx)
         self.last_calls = calls.value
         self.last_trace = trace[:min(calls.value, trace_cap)]
         return llh.value
@@ -295,6 +359,9 @@ class BigClam:
         ms = C.c_double()
         nstep = C.c_int64()
         nall = C.c_int64()
+        if self._multi is not None:          # slowest rank's sum of step-kernel times
+            self._mcheck(_lib.load().bigclam_multi_get_kernel_time(self._multi, C.byref(ms), C.byref(nstep)))
+            return ms.value, nstep.value, nstep.value
         check(_lib.load().bigclam_get_kernel_time(self._need(), C.byref(ms), C.byref(nstep), C.byref(nall)), self._ctx)
         return ms.value, nstep.value, nall.value
 
@@ -322,6 +389,9 @@ class BigClam:
         if self._ctx is not None:
             _lib.load().bigclam_destroy(self._ctx)
             self._ctx = None
+        if getattr(self, "_multi", None) is not None:
+            _lib.load().bigclam_multi_destroy(self._multi)
+            self._multi = None
 
     def close(self):
         self._free()

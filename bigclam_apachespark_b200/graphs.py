@@ -9,8 +9,9 @@ import os
 
 import numpy as np
 
-_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FIXTURE_DIR = os.path.join(_REPO, "tests", "golden", "graphs")
+# package data: the SNAP topologies the reference ships, as compact .npz (written by tests/golden/make_fixtures.py);
+# BIGCLAM_GRAPH_DIR points somewhere else
+FIXTURE_DIR = os.environ.get("BIGCLAM_GRAPH_DIR", os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "graphs"))
 
 
 def csr_from_undirected(n: int, u: np.ndarray, v: np.ndarray):

@@ -55,8 +55,9 @@ typedef struct {
 #define BIGCLAM_F_TIME_KERNELS   1   /* record CUDA events around every step-kernel launch */
 #define BIGCLAM_F_RECORD_ACCEPTED 2  /* keep the accepted step index per node (diagnostics/tests) */
 #define BIGCLAM_F_SPARSE_ROWS     4  /* keep F as sparse rows on the device (like the reference's BSV[Double],
-                                        bigclam4-7.scala:97-104): k <= 256, min_f == 0, single GPU.  The C ABI stays
-                                        dense (bigclam_set_F / bigclam_get_F convert on the device). */
+                                        bigclam4-7.scala:97-104): k <= 1024, min_f == 0, n < 2^28.  The dense entry
+                                        points still work (bigclam_set_F / bigclam_get_F convert on the device);
+                                        bigclam_set_F_csr / bigclam_get_F_csr never build a dense image. */
 
 /* Fills *p with the reference's constants for a given K. */
 int bigclam_default_params(bigclam_params *p, int32_t k);
@@ -144,6 +145,7 @@ int bigclam_device_accepted(bigclam_ctx *ctx, void **accepted_dev);
  */
 int bigclam_set_owned_range(bigclam_ctx *ctx, int64_t lo, int64_t hi);
 int bigclam_set_owned_nodes(bigclam_ctx *ctx, const int32_t *nodes, int64_t count);   /* arbitrary owned set */
+int bigclam_set_uset(bigclam_ctx *ctx, const uint8_t *node_mask);   /* uset of the following bigclam_step_local calls (NULL = all) */
 int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev /* 2*ld+2 doubles */);
 int bigclam_finish_local(bigclam_ctx *ctx, double *llh_pre_out, int64_t *n_updated_out);  /* both NULL: asynchronous, no host sync */
 int bigclam_collect_timing(bigclam_ctx *ctx);   /* sync + sum the kernel timings recorded since the last collection */
@@ -173,6 +175,45 @@ int bigclam_mark_all_changed(bigclam_ctx *ctx);
  * output pool is rebuilt per step, so there is no changed-row bookkeeping).
  */
 int bigclam_ipc_handle_count(const bigclam_ctx *ctx);
+/*
+ * Fused collective of the node-partitioned path (sparse rows): instead of an all-reduce by the host framework, the
+ * reduction kernel behind every step kernel stores this rank's sums [sum(old-new) | llh | n_updated] into its slot
+ * of every rank's exchange buffer (peer memory over NVLink) and raises a flag there; bigclam_finish_local /
+ * bigclam_llh_finish_local then wait for all flags on the device and add the slots up in rank order (every rank
+ * gets the same bits).  bigclam_xchg_export allocates the buffers and writes their 2 CUDA IPC handles (2 x 64
+ * bytes); the caller all-gathers them and passes all of them (world x 2 x 64 bytes, rank order) to
+ * bigclam_xchg_open_peers.  Replaces the driver-side reduce of bigclam4-7.scala:191-192 and :219.
+ */
+int bigclam_xchg_export(bigclam_ctx *ctx, int32_t world, int32_t rank, void *handles_out);
+int bigclam_xchg_open_peers(bigclam_ctx *ctx, const void *all_handles);
+int bigclam_llh_finish_local(bigclam_ctx *ctx, double *llh_out);
+
+/*
+ * All the GPUs of one box behind ONE handle, driven by one host thread — what a JVM/JNI caller uses:
+ * one context per device (sparse rows), nodes dealt over the ranks by degree, each rank's new rows stored straight
+ * into every replica by the step kernel, sums combined by the fused collective above.  No NCCL, no Python.
+ * devices: `world` CUDA ordinals, NULL = 0 .. world-1.  The entry points mirror the single-GPU ones
+ * (same reference lines); rank selects the replica a getter reads (they are identical).
+ */
+typedef struct bigclam_multi bigclam_multi;
+int  bigclam_multi_create(bigclam_multi **out, int64_t n, const int64_t *rowptr, const int32_t *col,
+                          const bigclam_params *params, int32_t world, const int32_t *devices);
+void bigclam_multi_destroy(bigclam_multi *m);
+const char *bigclam_multi_last_error(const bigclam_multi *m);     /* m may be NULL: last create error */
+int  bigclam_multi_world(const bigclam_multi *m);
+int  bigclam_multi_set_F(bigclam_multi *m, const double *F);
+int  bigclam_multi_set_F_csr(bigclam_multi *m, const int64_t *indptr, const int32_t *indices, const double *values);
+int  bigclam_multi_set_sumF(bigclam_multi *m, const double *sumF);
+int  bigclam_multi_get_F(bigclam_multi *m, int32_t rank, double *F_out);
+int  bigclam_multi_get_sumF(bigclam_multi *m, int32_t rank, double *sumF_out);
+int  bigclam_multi_get_F_nnz(bigclam_multi *m, int64_t *nnz_out);
+int  bigclam_multi_get_F_csr(bigclam_multi *m, int64_t *indptr_out, int32_t *indices_out, double *values_out);
+int  bigclam_multi_step(bigclam_multi *m, const uint8_t *node_mask, double *llh_out, int64_t *n_updated_out);
+int  bigclam_multi_loglikelihood(bigclam_multi *m, double *llh_out);
+int  bigclam_multi_run(bigclam_multi *m, int32_t variant, double rel_tol, int64_t max_outer, double *llh_out,
+                       int64_t *calls_out, double *llh_trace, int64_t trace_cap);
+int  bigclam_multi_get_kernel_time(bigclam_multi *m, double *max_rank_ms_sum, int64_t *step_kernel_launches);
+
 /*
  * F as CSR rows, the shape of the reference's RDD[(Long, BSV[Double])] (bigclam4-7.scala:97-104): indptr[n + 1],
  * indices (component of each entry, any order inside a row), values.  sumF becomes the column sums (:105-106).

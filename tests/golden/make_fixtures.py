@@ -25,7 +25,7 @@ def graphs():
     for src, name in [("facebook_combined.txt", "facebook_combined"), ("Email-Enron.txt", "email-enron"),
                       ("com-amazon.ungraph.txt", "com-amazon")]:
         (rp, col), ids = O.read_edge_list(os.path.join(REF_DATA, src), "dedup")
-        out = os.path.join(HERE, "graphs", name + ".npz")
+        out = os.path.join(G.FIXTURE_DIR, name + ".npz")
         G.save_npz_graph(out, rp, col, ids)
         rp2, col2, ids2 = G.load_npz_graph(out)
         assert np.array_equal(rp, rp2) and np.array_equal(col, col2) and np.array_equal(ids, ids2)
@@ -76,7 +76,7 @@ def ground_truth():
         xs = np.sort(np.array([idmap[int(t)] for t in line.split() if int(t) in idmap], dtype=np.int64))
         sizes.append(len(xs))
         deltas.append(np.diff(xs, prepend=0))
-    out = os.path.join(HERE, "graphs", "com-amazon.cmty.npz")
+    out = os.path.join(G.FIXTURE_DIR, "com-amazon.cmty.npz")
     np.savez_compressed(out, sizes=np.array(sizes, dtype=np.int32), deltas=np.concatenate(deltas).astype(np.int32))
     print("com-amazon.cmty", len(sizes), os.path.getsize(out))
 

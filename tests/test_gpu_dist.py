@@ -27,8 +27,10 @@ def _worker(rank, world, port, exchange, out):
     rng = np.random.default_rng(5)
     F0 = rng.random((n, k)) * (rng.random((n, k)) < 0.2)
     sumF = O.colsum(F0)
-    sparse = exchange == "p2p-sparse"          # sparse rows of F, pushed by the step kernel (regions of the pools)
+    sparse = exchange.startswith("p2p-sparse")  # sparse rows of F, pushed by the step kernel (regions of the pools)
     if sparse:
+        # default: the fused device-side collective (bigclam_xchg_*); "-nccl": the all-reduce goes through NCCL instead
+        os.environ["BIGCLAM_NCCL_ALLREDUCE"] = "1" if exchange.endswith("-nccl") else "0"
         exchange = "p2p"
     b = BigClam(device=rank, record_accepted=True, sparse_rows=sparse)
     b.set_graph(rp, col).set_K(k)
@@ -53,7 +55,7 @@ def _worker(rank, world, port, exchange, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "delta", "full", "p2p-sparse"])
+@pytest.mark.parametrize("exchange", ["p2p", "delta", "full", "p2p-sparse", "p2p-sparse-nccl"])
 def test_two_gpu_partitioned_equals_oracle(tmp_path, oracle, exchange):
     import torch
     import torch.multiprocessing as mp
