@@ -54,7 +54,7 @@ def load_graph(graph):
     from bigclam_apachespark_b200 import graphs as G
     if graph.startswith("rmat:"):
         _, nn, mm = graph.split(":")
-        return G.rmat_graph(int(nn), int(mm), seed=42)
+        return (G.rmat_graph_fast if int(mm) >= 20_000_000 else G.rmat_graph)(int(nn), int(mm), seed=42)
     rp, col, _ = G.load_npz_graph(graph)
     return rp, col
 
@@ -66,7 +66,8 @@ def load_workload(graph, k):
     n = len(rp) - 1
     if n * k > (1 << 29):
         import scipy.sparse as sps
-        ip, ix, vl = G.synthetic_F0_csr(n, k, seed=1234, density=0.05)
+        gen = G.synthetic_F0_csr_stratified if n * k > (1 << 32) else G.synthetic_F0_csr
+        ip, ix, vl = gen(n, k, seed=1234, density=0.05)
         return rp, col, sps.csr_matrix((vl, ix, ip), shape=(n, k))
     return rp, col, G.synthetic_F0(n, k, seed=1234, density=0.05)
 

@@ -73,6 +73,7 @@ SIGNATURES = {
     "bigclam_get_accepted": (C.c_int, [_vp, _vp]),
     "bigclam_get_kernel_time": (C.c_int, [_vp, _pd, _pi64, _pi64]),
     "bigclam_get_tile_stats": (C.c_int, [_vp, _pi64, _pi64, _pi64, _pi64, _pi64]),
+    "bigclam_retile": (C.c_int, [_vp]),
     "bigclam_set_stream": (C.c_int, [_vp, _vp]),
     "bigclam_device_state": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _pi64]),
     "bigclam_device_accepted": (C.c_int, [_vp, C.POINTER(_vp)]),
@@ -114,6 +115,7 @@ SIGNATURES = {
     "bigclam_graph_free": (None, [C.POINTER(Graph)]),
     "bigclam_extract": (C.c_int, [_vp, _dbl, _vp, _vp]),
     "bigclam_conductance_seeds": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _pi64]),
+    "bigclam_conductance_seeds_gpu": (C.c_int, [_i64, _vp, _vp, _i32, _vp, _vp, _pi64]),
     "bigclam_init_neighbor_com_F": (C.c_int, [_i64, _vp, _vp, _i32, _vp, _i64, _i32, C.c_uint64, _vp]),
     "bigclam_device_count": (C.c_int, []),
     "bigclam_version": (C.c_char_p, []),

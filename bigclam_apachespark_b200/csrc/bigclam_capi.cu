@@ -95,6 +95,7 @@ struct bigclam_ctx {
     int32_t ntiles = 0, n_gen = 0;
     int32_t tile_edges = kTlMaxEdges;             // edge budget of a tile (0: no tiles), see retile()
     int32_t tile_nodes = kTlMaxNodes;             // node budget of a tile
+    double tile_avg16 = 1.0;                      // average row size (16-byte chunks) the tiles were cut for
     unsigned int *d_stats = nullptr;              // [tiles on the tile path, tiles that fell back], BIGCLAM_F_TIME_KERNELS only
     // fused collective of the node-partitioned path (reduce_kernel publishes, xreduce_kernel adds up): this rank's
     // exchange buffer [2 halves][world][ld + 2] and flags [world], and every rank's (peer memory, incl. our own)
@@ -259,12 +260,13 @@ static int rebuild_sparse_lists(bigclam_ctx *ctx, const std::vector<NodeMeta> &m
     int64_t own_nnz = 0;
     for (int64_t i = 0; i < cnt; ++i) own_nnz += meta[(size_t)i].deg;
     // a hub is split into kSpHubSeg-edge segments over warps when one warp walking it would take a sizeable
-    // part of the launch: from a quarter of a warp's share of the owned entries upwards, at least 1024 edges
+    // part of the launch: from an eighth of a warp's share of the owned entries upwards, at least 2 segments' worth
+    // of edges (a 1,383-edge node of Email-Enron walked by one warp WAS the launch: 1.3 ms for 367 K entries)
     // (BIGCLAM_SPARSE_HUB_DEG overrides the threshold: tests)
     int32_t nh = 0;
     if (ctx->nsteps <= 16) {
         const int64_t sp_per_warp = own_nnz / std::max<int64_t>(1, (int64_t)ctx->sp_grid * ctx->sp_wpb);
-        int64_t sp_hub_deg = std::max<int64_t>(1024, sp_per_warp / 4);
+        int64_t sp_hub_deg = std::max<int64_t>(2 * kSpHubSeg, sp_per_warp / 8);
         if (const char *ev = std::getenv("BIGCLAM_SPARSE_HUB_DEG")) sp_hub_deg = std::max<int64_t>(1, std::atoll(ev));
         while (nh < cnt && meta[(size_t)nh].deg >= sp_hub_deg) ++nh;
     }
@@ -335,7 +337,7 @@ static int rebuild_sparse_lists(bigclam_ctx *ctx, const std::vector<NodeMeta> &m
         if (!tcol.empty()) CU(cudaMemcpy(ctx->d_tcol, tcol.data(), sizeof(int32_t) * tcol.size(), cudaMemcpyHostToDevice));
     }
     // the reduction walks the processing order with a fixed grid
-    ctx->red_grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, (cnt + 255) / 256));
+    ctx->red_grid = (int)std::max<int64_t>(1, std::min<int64_t>(2 * (int64_t)ctx->num_sms, (cnt + 32 * kRedWarps - 1) / (32 * kRedWarps)));
     cudaFree(ctx->d_block_part); ctx->d_block_part = nullptr;
     CU(cudaMalloc(&ctx->d_block_part, sizeof(double) * (size_t)ctx->red_grid * ((size_t)ctx->ld + 2)));
     ctx->h_work_init = 0;                                  // every item of the sparse kernel is handed out dynamically
@@ -721,6 +723,7 @@ static int retile(bigclam_ctx *ctx, uint64_t words_used) {
     const double nn = (double)std::max<int64_t>(1, ctx->n);
     const double avg_cnt = std::max(1.0, (double)sp_host_nnz(ctx->n, hdr.data()) / nn);
     const double avg16 = std::max(1.0, (double)words_used / 2.0 / nn);
+    ctx->tile_avg16 = avg16;
     // the neighbour rows of a tile must fit the staging chunks, its nodes' own rows theirs, and all their entries
     // the slots (worst case: no two of them on the same component) — with 10-15 % to spare
     int nodes = std::max(0, std::min(kTlMaxNodes, (int)((double)kTlOwn16 / (1.15 * avg16))));
@@ -732,6 +735,27 @@ static int retile(bigclam_ctx *ctx, uint64_t words_used) {
     ctx->tile_edges = budget;
     std::vector<int32_t> order = ctx->h_owned;
     return rebuild_order_list(ctx, ctx->h_rowptr, order);
+}
+
+// The rows change size while the solver runs (they fill up on small-K problems): when the tiles were cut for rows
+// of a very different size, cut them again.  Call at a point where the stream is idle.
+static int maybe_retile(bigclam_ctx *ctx) {
+    if (!ctx->sparse || std::getenv("BIGCLAM_TILE_EDGES") != nullptr) return BIGCLAM_OK;
+    unsigned long long used = 0;
+    CU(cudaMemcpy(&used, ctx->d_pool_top + ctx->cur, sizeof(used), cudaMemcpyDeviceToHost));
+    if (used == 0) return BIGCLAM_OK;
+    const double avg16 = std::max(1.0, (double)used / 2.0 / (double)std::max<int64_t>(1, ctx->order_n));   // (this rank's rows; deltas included: conservative)
+    const double ratio = avg16 / std::max(1.0, ctx->tile_avg16);
+    if (ratio < 1.3 && ratio > 0.6) return BIGCLAM_OK;
+    if (ctx->n_peers > 0) return BIGCLAM_OK;     // (replicated pools: pool_top only counts the owned region; the caller retiles through set_F)
+    return retile(ctx, used);
+}
+
+extern "C" int bigclam_retile(bigclam_ctx *ctx) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return maybe_retile(ctx);
 }
 
 extern "C" int bigclam_set_F(bigclam_ctx *ctx, const double *F) {
@@ -1235,6 +1259,13 @@ extern "C" int bigclam_run(bigclam_ctx *ctx, int32_t variant, double rel_tol, in
         CU(cudaStreamSynchronize(ctx->stream));
         if (hst->done) { done = true; break; }
         if (max_outer > 0 && c >= max_outer) break;
+        {   // the stream is idle: a good moment to re-cut the tiles when the rows have changed size a lot
+            const int keep = ctx->cur;
+            ctx->cur = (start_cur + (int)(c & 1)) & 1;            // S_c, the current state
+            const int rt = maybe_retile(ctx);
+            ctx->cur = keep;
+            if (rt) return rt;
+        }
     }
     int64_t calls;
     if (done) {
@@ -1316,6 +1347,9 @@ extern "C" int bigclam_step_local(bigclam_ctx *ctx, void **partials_dev) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
     if (int rd = drop_speculation(ctx)) return rd;
+    // dense kernels accumulate their sums into d_partials: whatever an earlier call left there must not be counted
+    // (the sparse engine's reduction overwrites them)
+    if (!ctx->sparse) CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
     StepArgs a;
     fill_args(ctx, a, true, ctx->local_mask ? ctx->d_mask : nullptr, false);
     int rc = timed_launch(ctx, a, true);

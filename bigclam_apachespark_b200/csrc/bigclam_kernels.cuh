@@ -1299,7 +1299,9 @@ __global__ void finish_kernel(const FinishArgs f) {
     const int ld = f.ld;
     if (threadIdx.x == 0) {
         RunState *st = f.st;
-        int done = st->done;
+        // a plain apply (kernel_index == 0: bigclam_step, bigclam_finish_local) is not part of a device-side loop: a
+        // `done` left behind by an earlier converged bigclam_run must not turn it into a no-op
+        int done = (f.kernel_index > 0) ? st->done : 0;
         if (!done && f.kernel_index > 0) {
             // partials.llh == LLH(state before kernel c) == LLH returned by call c-1
             const double L = f.partials[2 * ld];

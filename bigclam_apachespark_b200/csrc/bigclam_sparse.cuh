@@ -111,7 +111,7 @@ __host__ __device__ inline size_t sp_gen_warp_bytes(int ld) {
 //   phase 3  once per hub, after its phase-2 segments: gradient, active set, Armijo decision, new row.
 // Items are handed out in that order by one counter and every warp holds one item at a time on a grid whose
 // warps are all resident, so a waiting warp only waits for items that are being processed: no deadlock.
-constexpr int kSpHubSeg = 256;
+constexpr int kSpHubSeg = 96;
 // scratch of one hub: (nslices + 1) x (ld + 32) doubles: slice sl holds  G_sl[ld] | S1_sl | ST_sl[16], the last
 // slot the sums over the slices (G | S1)
 __host__ __device__ inline size_t sp_hub_stride(int ld) { return (size_t)ld + 32; }

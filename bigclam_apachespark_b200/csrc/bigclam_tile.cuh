@@ -893,7 +893,7 @@ struct ReduceArgs {
     unsigned long long *xflag[8];        // this rank's flag in rank p's flag array
     unsigned long long seq;
 };
-constexpr int kRedWarps = 8;
+constexpr int kRedWarps = 16;
 
 __global__ void __launch_bounds__(kRedWarps * 32) reduce_kernel(const ReduceArgs r) {
     if (r.done_flag != nullptr && *r.done_flag != 0) return;

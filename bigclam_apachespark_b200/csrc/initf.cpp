@@ -27,6 +27,35 @@
 #include <numeric>
 #include <vector>
 
+// Candidates (:70): (min-id neighbour, its conductance) per node, or (x, 10.0) without neighbours; de-duplicated by
+// id (reduceByKey keeps the minimum), sorted by conductance ascending, ties by id.  Shared by the host and the GPU
+// path (csrc/initf_gpu.cu).  A conductance can be negative as coded (vol_T < 0 on multigraph input): candidates
+// are tracked by a flag, not by the sign of the key.
+void bigclam_select_seeds_internal(int64_t n, const int64_t *rowptr, const int32_t *col, const double *cond,
+                                   int32_t *seeds_out, int64_t *n_seeds_out) {
+    std::vector<double> key((size_t)n, 0.0);
+    std::vector<char> is_cand((size_t)n, 0);
+    auto offer = [&](int64_t v, double c) {
+        if (!is_cand[(size_t)v] || c < key[(size_t)v]) key[(size_t)v] = c;
+        is_cand[(size_t)v] = 1;
+    };
+    for (int64_t x = 0; x < n; ++x) {
+        if (rowptr[x + 1] > rowptr[x]) {
+            int32_t v = col[rowptr[x]];
+            for (int64_t e = rowptr[x] + 1; e < rowptr[x + 1]; ++e) v = std::min(v, col[e]);
+            offer(v, cond[(size_t)v]);
+        } else {
+            offer(x, 10.0);
+        }
+    }
+    std::vector<int32_t> cand;
+    for (int64_t v = 0; v < n; ++v)
+        if (is_cand[(size_t)v]) cand.push_back((int32_t)v);
+    std::stable_sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) { return key[(size_t)a] < key[(size_t)b]; });
+    std::memcpy(seeds_out, cand.data(), sizeof(int32_t) * cand.size());
+    *n_seeds_out = (int64_t)cand.size();
+}
+
 extern "C" int bigclam_conductance_seeds(int64_t n, const int64_t *rowptr, const int32_t *col,
                                          double *conductance_out /* n, optional */,
                                          int32_t *seeds_out /* n */, int64_t *n_seeds_out) {
@@ -54,24 +83,7 @@ extern "C" int bigclam_conductance_seeds(int64_t n, const int64_t *rowptr, const
     }
     if (conductance_out != nullptr) std::memcpy(conductance_out, cond.data(), sizeof(double) * (size_t)n);
 
-    // candidates (:70): (min-id neighbour, its conductance) per node, or (x, 10.0) without neighbours
-    std::vector<double> key((size_t)n, -1.0);        // -1 == not a candidate
-    for (int64_t x = 0; x < n; ++x) {
-        if (rowptr[x + 1] > rowptr[x]) {
-            int32_t v = col[rowptr[x]];
-            for (int64_t e = rowptr[x] + 1; e < rowptr[x + 1]; ++e) v = std::min(v, col[e]);
-            const double c = cond[(size_t)v];
-            key[(size_t)v] = (key[(size_t)v] < 0) ? c : std::min(key[(size_t)v], c);
-        } else {
-            key[(size_t)x] = (key[(size_t)x] < 0) ? 10.0 : std::min(key[(size_t)x], 10.0);
-        }
-    }
-    std::vector<int32_t> cand;
-    for (int64_t v = 0; v < n; ++v)
-        if (key[(size_t)v] >= 0) cand.push_back((int32_t)v);
-    std::stable_sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) { return key[(size_t)a] < key[(size_t)b]; });
-    std::memcpy(seeds_out, cand.data(), sizeof(int32_t) * cand.size());
-    *n_seeds_out = (int64_t)cand.size();
+    bigclam_select_seeds_internal(n, rowptr, col, cond.data(), seeds_out, n_seeds_out);
     return BIGCLAM_OK;
 }
 

@@ -238,14 +238,21 @@ class BigClam:
         return out
 
     # ---- init of F (conductanceLocalMin + initNeighborComF, bigclam4-7.scala:58-108) ----
-    def conductanceLocalMin(self):
-        """Ranked seed candidates (dense vertex indices) and the conductance of every vertex."""
+    def conductanceLocalMin(self, on_gpu=None):
+        """Ranked seed candidates (dense vertex indices) and the conductance of every vertex.  on_gpu: True = the
+        CUDA kernel (csrc/initf_gpu.cu), False = the host path, None = the GPU when there is one."""
         lib = _lib.load()
         cond = np.empty(self.n, dtype=np.float64)
         seeds = np.empty(self.n, dtype=np.int32)
         cnt = C.c_int64()
-        rc = lib.bigclam_conductance_seeds(self.n, self.rowptr.ctypes.data, self.col.ctypes.data, cond.ctypes.data,
-                                           seeds.ctypes.data, C.byref(cnt))
+        if on_gpu is None:
+            on_gpu = lib.bigclam_device_count() > 0
+        if on_gpu:
+            rc = lib.bigclam_conductance_seeds_gpu(self.n, self.rowptr.ctypes.data, self.col.ctypes.data, self.device,
+                                                   cond.ctypes.data, seeds.ctypes.data, C.byref(cnt))
+        else:
+            rc = lib.bigclam_conductance_seeds(self.n, self.rowptr.ctypes.data, self.col.ctypes.data, cond.ctypes.data,
+                                               seeds.ctypes.data, C.byref(cnt))
         if rc != _lib.OK:
             raise _lib.BigclamError(rc, "bigclam_conductance_seeds failed")
         self.Sbc = seeds[:cnt.value].copy()             # `Sbc` of the script (:75), reused for every K

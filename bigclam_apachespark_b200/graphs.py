@@ -93,6 +93,68 @@ def synthetic_F0_csr(n: int, k: int, seed: int = 1234, density: float = 0.05, ch
         np.concatenate(val_parts) if val_parts else np.zeros(0)
 
 
+def synthetic_F0_csr_stratified(n: int, k: int, seed: int = 1234, density: float = 0.05, chunk: int = 1 << 21):
+    """CSR rows with exactly round(k * density) non-zeros each, one per stride of 1/density components (a uniformly
+    random component inside every stride, values U[0,1)): distinct and ascending by construction, so no sort and no
+    de-duplication — the generator for sizes where n x k must never exist densely and the i.i.d. variant
+    (synthetic_F0_csr) would spend minutes sorting (R-MAT 10M x K=1000: 5e8 entries).  Same marginals per component
+    as synthetic_F0 (each component non-zero with probability `density`); the row lengths are constant instead of
+    binomial."""
+    rng = np.random.default_rng(seed)
+    stride = max(1, int(round(1.0 / density)))
+    per_row = max(1, k // stride)
+    indptr = np.arange(n + 1, dtype=np.int64) * per_row
+    indices = np.empty(n * per_row, dtype=np.int32)
+    values = np.empty(n * per_row, dtype=np.float64)
+    base = (np.arange(per_row, dtype=np.int32) * stride)[None, :]
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        off = rng.integers(0, stride, size=(m, per_row), dtype=np.int32)
+        indices[lo * per_row:(lo + m) * per_row] = np.minimum(base + off, k - 1).reshape(-1)
+        values[lo * per_row:(lo + m) * per_row] = rng.random(m * per_row)
+    return indptr, indices, values
+
+
+def rmat_graph_fast(scale_n: int, n_edges: int, a=0.57, b=0.19, c=0.19, seed: int = 42, permute: bool = True):
+    """Same R-MAT family as rmat_graph with 16-bit random draws per level and a single key sort (about 10x faster at
+    1e8 edges); not edge-for-edge the same graph as rmat_graph(seed)."""
+    rng = np.random.default_rng(seed)
+    bits = int(np.ceil(np.log2(max(scale_n, 2))))
+    ta, tb, tc = int(a * 65536), int((a + b) * 65536), int((a + b + c) * 65536)
+    keys = np.zeros(0, dtype=np.int64)
+    need = n_edges
+    while need > 0:
+        m = int(need * 1.25) + 1024
+        u = np.zeros(m, dtype=np.int64)
+        v = np.zeros(m, dtype=np.int64)
+        for _ in range(bits):
+            r = rng.integers(0, 65536, size=m, dtype=np.uint16)
+            right = ((r >= ta) & (r < tb)) | (r >= tc)              # quadrants b, d: column bit set
+            down = r >= tb                                          # quadrants c, d: row bit set
+            u = (u << 1) | down
+            v = (v << 1) | right
+        ok = (u < scale_n) & (v < scale_n) & (u != v)
+        lo = np.minimum(u[ok], v[ok])
+        hi = np.maximum(u[ok], v[ok])
+        keys = np.unique(np.concatenate([keys, lo * scale_n + hi]))
+        need = n_edges - len(keys)
+    if len(keys) > n_edges:
+        keys = keys[rng.permutation(len(keys))[:n_edges]]
+    u, v = keys // scale_n, keys % scale_n
+    if permute:
+        perm = rng.permutation(scale_n)
+        u, v = perm[u], perm[v]
+    # symmetric CSR by one sort of the directed keys
+    a_ = np.concatenate([u, v])
+    b_ = np.concatenate([v, u])
+    key = a_ * scale_n + b_
+    key.sort()
+    a_ = key // scale_n
+    rowptr = np.zeros(scale_n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(a_, minlength=scale_n), out=rowptr[1:])
+    return rowptr, (key % scale_n).astype(np.int32)
+
+
 def rmat_graph(scale_n: int, n_edges: int, a=0.57, b=0.19, c=0.19, seed: int = 42, permute: bool = True):
     """R-MAT (a,b,c,d) edge generator -> simple undirected CSR over n = scale_n nodes
     (n need not be a power of two: endpoints are drawn in the next power of two and rejected

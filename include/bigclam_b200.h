@@ -129,6 +129,10 @@ int bigclam_get_kernel_time(bigclam_ctx *ctx, double *step_kernel_ms_sum, int64_
 int bigclam_get_tile_stats(bigclam_ctx *ctx, int64_t *tiles_done, int64_t *tiles_fallback, int64_t *n_tiles,
                            int64_t *n_general_nodes, int64_t *n_split_hubs);
 
+/* Sparse rows: re-cut the tiles of small nodes for the current average row size (rows grow or shrink while the solver
+ * runs; bigclam_run does this by itself between its batches, bigclam_set_F* always).  Synchronises the stream. */
+int bigclam_retile(bigclam_ctx *ctx);
+
 int bigclam_set_stream(bigclam_ctx *ctx, void *cuda_stream);
 int bigclam_device_state(bigclam_ctx *ctx, void **F_dev, void **F_next_dev, void **sumF_dev, int64_t *ld);
 /* Device pointer of the per-node accepted-step index (int8, n entries; BIGCLAM_F_RECORD_ACCEPTED):
@@ -268,6 +272,10 @@ int bigclam_extract(bigclam_ctx *ctx, double delta, uint8_t *member_out, double 
  */
 int bigclam_conductance_seeds(int64_t n, const int64_t *rowptr, const int32_t *col, double *conductance_out,
                               int32_t *seeds_out, int64_t *n_seeds_out);
+/* The same ranking with the ego-net conductances computed on the GPU (one warp per node, csrc/initf_gpu.cu); device:
+ * CUDA ordinal, -1 = current.  Fails without a CUDA device (BIGCLAM_ECUDA): bigclam_conductance_seeds is the host path. */
+int bigclam_conductance_seeds_gpu(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t device,
+                                  double *conductance_out, int32_t *seeds_out, int64_t *n_seeds_out);
 int bigclam_init_neighbor_com_F(int64_t n, const int64_t *rowptr, const int32_t *col, int32_t k,
                                 const int32_t *ranked_seeds, int64_t n_ranked, int32_t include_self,
                                 uint64_t pad_seed, double *F_out);

@@ -17,6 +17,7 @@ for f in bigclam_kernels.cuh bigclam_sparse.cuh bigclam_tile.cuh; do
       -e 's/^\( *\)__shared__ /\1static /' "$src/$f" > "$gen/$f"
 done
 python3 "$here/rewrite_launches.py" "$src/bigclam_capi.cu" | sed -e 's#"../../include/bigclam_b200.h"#"bigclam_b200.h"#' > "$gen/bigclam_capi_emu.cpp"
+python3 "$here/rewrite_launches.py" "$src/initf_gpu.cu" | sed -e 's#"../../include/bigclam_b200.h"#"bigclam_b200.h"#' > "$gen/initf_gpu_emu.cpp"
 cat > "$gen/emu_globals.cpp" <<'EOT'
 #include "cuda_emu.h"
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -31,4 +32,4 @@ EOT
 CXX=/usr/bin/g++; test -x $CXX || CXX=g++
 $CXX -O1 -g -std=c++20 -ffp-contract=off -DBIGCLAM_EMU -DBIGCLAM_EMU_HOST $EMU_DEFS -I "$here/include" -I "$gen" -I "$here/../../include" \
     -pthread -shared -fPIC -Wno-unknown-pragmas -o "$here/libbigclam_hostemu.so" \
-    "$gen/bigclam_capi_emu.cpp" "$gen/emu_globals.cpp" "$src/edgelist.cpp" "$src/initf.cpp"
+    "$gen/bigclam_capi_emu.cpp" "$gen/initf_gpu_emu.cpp" "$gen/emu_globals.cpp" "$src/edgelist.cpp" "$src/initf.cpp"

@@ -299,8 +299,11 @@ def test_reference_style_init_then_steps(oracle, graphs):
 
 
 def test_k_sweep_driver(oracle):
-    """The K sweep of bigclam4-7.scala:244-266 on a small graph: stops at the first K with < 0.1 % LLH gain."""
+    """The K sweep of bigclam4-7.scala:244-266 on a small graph against an ORACLE-DRIVEN sweep: the same K grid, the
+    same reference-style F0 per K (NumPy twin of initNeighborComF), SGDFindC by the CPU restatement, the same stop rule
+    (`1 - LLH_K / LLH_prev < 0.001`, LLHKold starting at 0.0 as coded)."""
     from bigclam_apachespark_b200 import BigClam
+    from oracle import numpy_twin as T
     rp, col = random_graph(400, 6, seed=3, hub=30)
     b = BigClam(minCom=4, maxCom=16, divCom=4)
     b.set_graph(rp, col)
@@ -309,6 +312,23 @@ def test_k_sweep_driver(oracle):
     assert len(hist) >= 2 and [k for k, _ in hist] == b.Kset()[:len(hist)]
     if KforC:
         assert KforC == hist[-1][0] and (1 - hist[-1][1] / hist[-2][1]) < 0.001
+    # the oracle's sweep
+    ranked, _ = T.conductance_local_min(rp, col)
+    assert np.array_equal(b.Sbc, ranked)
+    LLHKold, K_o, hist_o = 0.0, 0, []
+    for K in b.Kset():
+        F0 = T.init_neighbor_com_F(rp, col, K, ranked)                       # (K <= number of candidates: no random padding)
+        _, _, llh, calls, _ = oracle.run(rp, col, F0, oracle.colsum(F0), oracle.make_params(K), variant=4, rel_tol=1e-4, max_outer=30)
+        hist_o.append((K, llh))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            gain = 1.0 - np.float64(llh) / np.float64(LLHKold)
+        if gain < 0.001:
+            K_o = K
+            break
+        LLHKold = llh
+    assert KforC == K_o and len(hist) == len(hist_o)
+    for (k1, l1), (k2, l2) in zip(hist, hist_o):
+        assert k1 == k2 and abs(l1 - l2) <= 1e-8 * abs(l2), (k1, l1, l2)
     b.close()
 
 

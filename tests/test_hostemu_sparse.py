@@ -18,12 +18,34 @@ SELECTION = ("golden_tiny or uset_mask or csr_entry or pool_exhaustion or split_
              "(all_k and (k1- or 3 or 31 or 65))")
 
 
-@pytest.mark.timeout(1500)
-def test_sparse_engine_under_host_emulation():
+def _child(test_file, selection, nobuild):
     env = dict(os.environ, BIGCLAM_HOSTEMU="1")
-    env.pop("BIGCLAM_HOSTEMU_NOBUILD", None)
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(REPO, "tests", "test_gpu_sparse.py"), "-m", "gpu", "-q", "-x",
-                        "-k", SELECTION, "-p", "no:cacheprovider"], cwd=REPO, env=env, capture_output=True, text=True, timeout=1400)
+    if nobuild:
+        env["BIGCLAM_HOSTEMU_NOBUILD"] = "1"
+    else:
+        env.pop("BIGCLAM_HOSTEMU_NOBUILD", None)
+    cmd = [sys.executable, "-m", "pytest", os.path.join(REPO, "tests", test_file), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
+    if selection:
+        cmd += ["-k", selection]
+    r = subprocess.run(cmd, cwd=REPO, env=env, capture_output=True, text=True, timeout=1400)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+@pytest.mark.timeout(1500)
+def test_sparse_engine_under_host_emulation():
+    _child("test_gpu_sparse.py", SELECTION, nobuild=False)
+
+
+@pytest.mark.timeout(1500)
+def test_multi_gpu_c_abi_under_host_emulation():
+    """bigclam_multi_* on 2 and 3 emulated devices: node deal, pool regions, peer pushes, the fused collective (publish,
+    flags, rank-ordered sums), the device-side loop on every rank — against the oracle, replicas bit-identical."""
+    _child("test_gpu_multi.py", None, nobuild=True)
+    _child("test_hostemu_multirank.py", None, nobuild=True)
+
+
+@pytest.mark.timeout(600)
+def test_conductance_kernel_under_host_emulation():
+    _child("test_gpu_init.py", "twin and (80 or 300) or unsorted", nobuild=True)

@@ -10,7 +10,7 @@ def _seeds(rp, col):
     from bigclam_apachespark_b200 import BigClam
     b = BigClam()
     b.set_graph(rp, col)
-    return b, b.conductanceLocalMin()
+    return b, b.conductanceLocalMin(on_gpu=False)
 
 
 @pytest.mark.parametrize("seed,n,deg,hub", [(1, 80, 4, 10), (2, 300, 6, 40), (3, 500, 3, 0)])
@@ -65,3 +65,27 @@ def test_facebook_seeds_and_colsums(graphs):
                                                    0, C.c_uint64(1), F.ctypes.data) == 0
     S = np.sort(seeds[:K])
     assert np.array_equal(F.sum(axis=0), np.diff(rp)[S].astype(float))
+
+
+def test_negative_conductance_on_multigraph_is_still_a_candidate():
+    """vol_T = sigma - vol_S - 2 cut goes negative on multigraph input (every neighbour listed several times): as coded
+    (:64-67) the conductance is then negative and the node ranks FIRST.  Candidates are tracked by a flag, not by the
+    sign of the key."""
+    from oracle import numpy_twin as T
+    from bigclam_apachespark_b200 import graphs as G
+    # a small clique whose edges are all listed three times, plus a path hanging off it
+    u = np.array([0, 0, 0, 1, 1, 2] * 3 + [3, 4, 5])
+    v = np.array([1, 2, 3, 2, 3, 3] * 3 + [4, 5, 6])
+    a = np.concatenate([u, v]); b_ = np.concatenate([v, u])
+    order = np.lexsort((b_, a))
+    a, b_ = a[order], b_[order]
+    n = 7
+    rp = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(a, minlength=n), out=rp[1:])
+    col = b_.astype(np.int32)
+    ranked, cond = T.conductance_local_min(rp, col)
+    assert (cond < 0).any(), "the construction must produce a negative conductance"
+    b, seeds = _seeds(rp, col)
+    assert np.array_equal(b.conductance, cond)
+    assert np.array_equal(seeds, ranked)
+    assert cond[seeds[0]] == cond[ranked].min()
