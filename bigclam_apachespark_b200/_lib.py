@@ -111,6 +111,7 @@ SIGNATURES = {
     "bigclam_get_F_nnz": (C.c_int, [_vp, _pi64]),
     "bigclam_get_F_csr": (C.c_int, [_vp, _vp, _vp, _vp]),
     "bigclam_set_pool_region": (C.c_int, [_vp, _i64, _i64]),
+    "bigclam_get_pool_capacity": (C.c_int, [_vp, _pi64]),
     "bigclam_graph_read_edgelist": (C.c_int, [C.c_char_p, _i32, C.POINTER(Graph), C.c_char_p, _i64]),
     "bigclam_graph_free": (None, [C.POINTER(Graph)]),
     "bigclam_extract": (C.c_int, [_vp, _dbl, _vp, _vp]),

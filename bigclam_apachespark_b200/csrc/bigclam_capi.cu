@@ -96,6 +96,8 @@ struct bigclam_ctx {
     int32_t tile_edges = kTlMaxEdges;             // edge budget of a tile (0: no tiles), see retile()
     int32_t tile_nodes = kTlMaxNodes;             // node budget of a tile
     double tile_avg16 = 1.0;                      // average row size (16-byte chunks) the tiles were cut for
+    unsigned int stats_seen[2] = {0u, 0u};        // d_stats at the last look (maybe_retile)
+    unsigned int stats_read[2] = {0u, 0u};        // d_stats at the last bigclam_get_tile_stats
     unsigned int *d_stats = nullptr;              // [tiles on the tile path, tiles that fell back], BIGCLAM_F_TIME_KERNELS only
     // fused collective of the node-partitioned path (reduce_kernel publishes, xreduce_kernel adds up): this rank's
     // exchange buffer [2 halves][world][ld + 2] and flags [world], and every rank's (peer memory, incl. our own)
@@ -741,6 +743,23 @@ static int retile(bigclam_ctx *ctx, uint64_t words_used) {
 // of a very different size, cut them again.  Call at a point where the stream is idle.
 static int maybe_retile(bigclam_ctx *ctx) {
     if (!ctx->sparse || std::getenv("BIGCLAM_TILE_EDGES") != nullptr) return BIGCLAM_OK;
+    // (1) tiles that keep falling back to the general path (too many active components / entries for the warp's
+    //     buffers: small K, rows filling up) are cut smaller: the fallback costs three times the tile path
+    unsigned int st[2] = {0u, 0u};
+    CU(cudaMemcpy(st, ctx->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+    const unsigned int done = st[0] - ctx->stats_seen[0], fb = st[1] - ctx->stats_seen[1];
+    ctx->stats_seen[0] = st[0];
+    ctx->stats_seen[1] = st[1];
+    if (ctx->tile_edges > 0 && done + fb > 0 && (double)fb > 0.2 * (double)(done + fb)) {
+        const int edges = std::max(6, (ctx->tile_edges * 5) / 8), nodes = std::max(2, (ctx->tile_nodes * 5 + 7) / 8);
+        if (edges != ctx->tile_edges || nodes != ctx->tile_nodes) {
+            ctx->tile_edges = edges;
+            ctx->tile_nodes = nodes;
+            std::vector<int32_t> order = ctx->h_owned;
+            return rebuild_order_list(ctx, ctx->h_rowptr, order);
+        }
+    }
+    // (2) rows of a very different size than the tiles were cut for
     unsigned long long used = 0;
     CU(cudaMemcpy(&used, ctx->d_pool_top + ctx->cur, sizeof(used), cudaMemcpyDeviceToHost));
     if (used == 0) return BIGCLAM_OK;
@@ -1024,7 +1043,7 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
         sp.ntiles = ctx->ntiles;
         sp.tiles = ctx->d_tiles;
         sp.tcol = ctx->d_tcol;
-        sp.stats = (ctx->p.flags & BIGCLAM_F_TIME_KERNELS) ? ctx->d_stats : nullptr;
+        sp.stats = ctx->d_stats;
         const bool hub = a.n_hub_items > 0, push = sp.n_peers > 0;
         const int threads = 32 * ctx->sp_wpb;
         if (hub && push) tile_step_kernel<true, true><<<ctx->sp_grid, threads, ctx->sp_smem, ctx->stream>>>(a, sp);
@@ -1311,10 +1330,11 @@ extern "C" int bigclam_get_tile_stats(bigclam_ctx *ctx, int64_t *tiles_done, int
         CU(cudaSetDevice(ctx->device));
         CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaMemcpy(st, ctx->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
-        CU(cudaMemset(ctx->d_stats, 0, sizeof(st)));
     }
-    if (tiles_done) *tiles_done = st[0];
-    if (tiles_fallback) *tiles_fallback = st[1];
+    if (tiles_done) *tiles_done = (int64_t)(st[0] - ctx->stats_read[0]);
+    if (tiles_fallback) *tiles_fallback = (int64_t)(st[1] - ctx->stats_read[1]);
+    ctx->stats_read[0] = st[0];
+    ctx->stats_read[1] = st[1];
     if (n_tiles) *n_tiles = ctx->sparse ? ctx->ntiles : 0;
     if (n_general_nodes) *n_general_nodes = ctx->sparse ? ctx->n_gen : 0;
     if (n_split_hubs) *n_split_hubs = ctx->sparse ? ctx->n_hubs : 0;
@@ -1491,6 +1511,14 @@ extern "C" int bigclam_set_pool_region(bigclam_ctx *ctx, int64_t base_words, int
         return fail(ctx, BIGCLAM_EINVAL, "bigclam_set_pool_region: region outside the pool (%llu words)", (unsigned long long)ctx->pool_cap8);
     ctx->region_base8 = (uint64_t)base_words;
     ctx->region_cap8 = (uint64_t)cap_words;
+    return BIGCLAM_OK;
+}
+
+// Sparse rows: capacity of each row pool in 8-byte words (the regions of bigclam_set_pool_region partition it).
+extern "C" int bigclam_get_pool_capacity(bigclam_ctx *ctx, int64_t *words_out) {
+    if (ctx == nullptr || words_out == nullptr) return BIGCLAM_EINVAL;
+    if (!ctx->sparse) return fail(ctx, BIGCLAM_EINVAL, "bigclam_get_pool_capacity: context without BIGCLAM_F_SPARSE_ROWS");
+    *words_out = (int64_t)ctx->pool_cap8;
     return BIGCLAM_OK;
 }
 

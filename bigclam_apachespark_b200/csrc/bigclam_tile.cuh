@@ -72,7 +72,7 @@ constexpr int kTlErow = BIGCLAM_TL_EROW;
 constexpr int kTlWarps = BIGCLAM_TL_WARPS;
 constexpr int kTlBlocksPerSM = BIGCLAM_TL_BLOCKS;
 constexpr int kTlThreads = kTlWarps * 32;
-static_assert(kTlStage16 >= 256, "the neighbour staging buffer doubles as xs[32 edges][16 trials]");
+static_assert(kTlStage16 >= 264, "the neighbour staging buffer doubles as xs[32 edges + 1 scratch row][16 trials]");
 static_assert(2 * kTlSlots >= 3 * kTlAct, "fg must hold (f, g) and sumF - f of the active components after compaction");
 static_assert(kTlEnt >= 128 && kTlEnt <= 256, "entry lists: the pair list (512 uint16) overlays ent_val; edge ids are bytes");
 static_assert(kTlAct <= 255, "active-component ids of the entry lists are bytes");
@@ -521,10 +521,13 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
             A += __popc(bal);
             __syncwarp();
         }
-        if (A > kTlAct) return false;
+        if (A > kTlAct - 1) return false;                      // (one spare: the padding component below)
         double *asfm = reinterpret_cast<double *>(fg + kTlAct);            // sumF_c - fu_c of the active components
 #pragma unroll 1
         for (int t = lane; t < A; t += 32) { asfm[t] = s_sumF[slot_c[t]] - fg[t].x; lcnt[t] = 0u; }
+        // padding component A: fu = grad = 0, so every candidate is 0 there and adds exactly nothing — the lockstep loops
+        // of the line search read it instead of predicating their bodies
+        if (lane == 0) { fg[A] = make_double2(0.0, 0.0); asfm[A] = 0.0; }
         __syncwarp();
         // ---------------- I. the neighbours' entries on active components, listed per component ----------------
 BIGCLAM_UNROLL(BIGCLAM_TL_UF)
@@ -549,8 +552,13 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
             if (t < A) { loff[t] = (unsigned short)(TE + incl - c); lcnt[t] = (unsigned int)(TE + incl - c); }
             TE += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (TE > kTlEnt) return false;
-        if (lane == 0) loff[A] = (unsigned short)TE;
+        if (TE > kTlEnt - 1) return false;
+        if (lane == 0) {
+            loff[A] = (unsigned short)TE;
+            ent_val[TE] = 0.0;                 // padding entry: component A, a scratch cell behind the 32 edges' cells
+            ent_e[TE] = 32;
+            ent_a[TE] = (unsigned char)A;
+        }
         __syncwarp();
 BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         for (int t = lane; t < T; t += 32) {
@@ -573,6 +581,7 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         const double s = s_steps[j < nsteps ? j : 0];
 BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         for (int p = lane; p < ne * 16; p += 32) xs[p] = 0.0;             // (the staged rows are not needed any more)
+        if (lane < 16) xs[32 * 16 + lane] = 0.0;                          // scratch row of the padding entry
         __syncwarp();
         double oa[4], ob[4];
 #pragma unroll
@@ -588,23 +597,20 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
             double a1 = 0.0, b1 = 0.0;
 BIGCLAM_UNROLL(BIGCLAM_TL_UJ)
             for (int t = 0; t < mmax; ++t) {
-                const bool ok = t < mm;
-                const int ti = t0 + (ok ? t : 0);
+                const int ti = (t < mm) ? t0 + t : A;                   // (A: the padding component, adds +0.0)
                 const double2 v = fg[ti];
                 const double nf = need_hi ? clamp_step0(v.x, s, v.y, max_f) : clamp_step0_lo(v.x, s, v.y);
                 const double sf = asfm[ti] + nf;                        // sfT = (sumF - fu) + newfu   (:176)
-                a1 = ok ? fma(nf, sf, a1) : a1;
-                b1 = ok ? fma(nf, nf, b1) : b1;
+                a1 = fma(nf, sf, a1);
+                b1 = fma(nf, nf, b1);
             }
 BIGCLAM_UNROLL(BIGCLAM_TL_UJ)
             for (int k = 0; k < qmax; ++k) {
-                const bool ok = k < nq;
-                const int qq = q0 + (ok ? k : 0);
+                const int qq = (k < nq) ? q0 + k : TE;                  // (TE: the padding entry, scratch cell, value 0)
                 const double2 v = fg[ent_a[qq]];
                 const double nf = need_hi ? clamp_step0(v.x, s, v.y, max_f) : clamp_step0_lo(v.x, s, v.y);
                 double *cell = xs + (int)ent_e[qq] * 16 + j;
-                const double cur = *cell;
-                if (ok) *cell = fma(nf, ent_val[qq], cur);
+                *cell = fma(nf, ent_val[qq], *cell);
             }
             oa[q] = a1;
             ob[q] = b1;

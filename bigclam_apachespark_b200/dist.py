@@ -64,7 +64,7 @@ def deal_by_degree(rowptr: np.ndarray, rank: int, world: int) -> np.ndarray:
 class CudaEngine:
     """The C-ABI context of one rank (libbigclam_b200.so) behind the engine interface."""
 
-    def __init__(self, solver, lo: int, hi: int, nodes=None, owned_counts=None, rank: int = 0):
+    def __init__(self, solver, lo: int, hi: int, nodes=None, owned_counts=None, rank: int = 0, pool_words=None):
         """owned_counts (sparse rows only): the number of owned nodes of every rank, so that each rank can place
         its part of the output pool behind the parts of the lower ranks (bigclam_set_pool_region)."""
         import torch
@@ -83,8 +83,19 @@ class CudaEngine:
         if self.sparse and owned_counts is not None:
             ld = (solver.K + 3) & ~3
             row_words = _lib.sparse_node_words(ld)        # a full row block + a full delta block per owned node
-            base = int(sum(owned_counts[:rank])) * row_words
-            self.check(self.lib.bigclam_set_pool_region(self.ctx, base, int(owned_counts[rank]) * row_words), self.ctx)
+            cap = C.c_int64()
+            self.check(self.lib.bigclam_get_pool_capacity(self.ctx, C.byref(cap)), self.ctx)
+            cap_words = cap.value
+            if pool_words is not None:
+                cap_words = min(cap_words, int(pool_words))       # the smallest pool of all ranks (caller's all-reduce)
+            total = int(sum(owned_counts))
+            if total * row_words <= cap_words:                    # worst case fits: a region can never overflow
+                base = int(sum(owned_counts[:rank])) * row_words
+                size = int(owned_counts[rank]) * row_words
+            else:                                                 # shares in proportion to the owned nodes (overflow is reported)
+                starts = [(cap_words * int(sum(owned_counts[:r])) // total) & ~1 for r in range(len(owned_counts) + 1)]
+                base, size = starts[rank], starts[rank + 1] - starts[rank]
+            self.check(self.lib.bigclam_set_pool_region(self.ctx, base, size), self.ctx)
         self.lo, self.hi = int(lo), int(hi)
         self._views = {}
         self.n, self.k = solver.n, solver.K
@@ -346,7 +357,15 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, base_conf
     exchange = os.environ.get("BIGCLAM_EXCHANGE", "p2p")
     nodes = deal_by_degree(rp, rank, world) if exchange == "p2p" else None
     counts = [len(range(r, n, world)) for r in range(world)] if exchange == "p2p" else None     # |order[r::world]|
-    eng = CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1]), nodes=nodes, owned_counts=counts, rank=rank)
+    pool_words = None
+    if sparse:
+        from . import _lib
+        cap = C.c_int64()
+        _lib.check(_lib.load().bigclam_get_pool_capacity(b._need(), C.byref(cap)), b._ctx)
+        t_cap = torch.tensor([cap.value], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t_cap, op=dist.ReduceOp.MIN)
+        pool_words = int(t_cap.item())
+    eng = CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1]), nodes=nodes, owned_counts=counts, rank=rank, pool_words=pool_words)
     d = DistBigClam(eng, rp, rank, world, bounds, exchange=exchange)
 
     for _ in range(args.warmup):

@@ -372,6 +372,12 @@ class BigClam:
         check(_lib.load().bigclam_get_kernel_time(self._need(), C.byref(ms), C.byref(nstep), C.byref(nall)), self._ctx)
         return ms.value, nstep.value, nall.value
 
+    def retile(self):
+        """Sparse rows: re-cut the tiles of small nodes for the rows' current size / the observed fallback rate
+        (bigclam_run does this between its batches of 8 calls)."""
+        if self._multi is None:
+            check(_lib.load().bigclam_retile(self._need()), self._ctx)
+
     def tile_stats(self):
         """Sparse rows + time_kernels: dict(tiles_done, tiles_fallback, n_tiles, n_general_nodes, n_split_hubs)."""
         v = [C.c_int64() for _ in range(5)]

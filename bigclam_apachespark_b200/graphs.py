@@ -155,6 +155,72 @@ def rmat_graph_fast(scale_n: int, n_edges: int, a=0.57, b=0.19, c=0.19, seed: in
     return rowptr, (key % scale_n).astype(np.int32)
 
 
+def rmat_graph_torch(scale_n: int, n_edges: int, a=0.57, b=0.19, c=0.19, seed: int = 42, permute: bool = True, device="cuda"):
+    """The same R-MAT family generated with torch on a CUDA device (seconds instead of minutes at 1e8 edges): benchmark
+    plumbing only.  Deterministic for a given (seed, torch build, GPU model) — every rank of a multi-GPU run builds the
+    identical graph on its own device; not edge-for-edge the NumPy generators' graph."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    bits = int(np.ceil(np.log2(max(scale_n, 2))))
+    keys = torch.zeros(0, dtype=torch.int64, device=device)
+    need = n_edges
+    while need > 0:
+        m = int(need * 1.25) + 1024
+        u = torch.zeros(m, dtype=torch.int64, device=device)
+        v = torch.zeros(m, dtype=torch.int64, device=device)
+        for _ in range(bits):
+            r = torch.rand(m, generator=g, device=device, dtype=torch.float32)
+            right = ((r >= a) & (r < a + b)) | (r >= a + b + c)
+            down = r >= a + b
+            u = (u << 1) | down.to(torch.int64)
+            v = (v << 1) | right.to(torch.int64)
+        ok = (u < scale_n) & (v < scale_n) & (u != v)
+        lo = torch.minimum(u[ok], v[ok])
+        hi = torch.maximum(u[ok], v[ok])
+        keys = torch.unique(torch.cat([keys, lo * scale_n + hi]))
+        need = n_edges - keys.numel()
+        del u, v, r, ok, lo, hi
+    if keys.numel() > n_edges:
+        keys = keys[torch.randperm(keys.numel(), generator=g, device=device)[:n_edges]]
+    u, v = keys // scale_n, keys % scale_n
+    if permute:
+        perm = torch.randperm(scale_n, generator=g, device=device)
+        u, v = perm[u], perm[v]
+    key = torch.cat([u * scale_n + v, v * scale_n + u])
+    del u, v, keys
+    key, _ = torch.sort(key)
+    rows = key // scale_n
+    rowptr = torch.zeros(scale_n + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=scale_n), 0)
+    col = (key % scale_n).to(torch.int32)
+    out = rowptr.cpu().numpy(), col.cpu().numpy()
+    del key, rows, rowptr, col
+    torch.cuda.empty_cache()
+    return out
+
+
+def synthetic_F0_csr_stratified_torch(n: int, k: int, seed: int = 1234, density: float = 0.05, device="cuda"):
+    """synthetic_F0_csr_stratified generated on a CUDA device (benchmark plumbing; same construction, torch's RNG)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    stride = max(1, int(round(1.0 / density)))
+    per_row = max(1, k // stride)
+    indptr = np.arange(n + 1, dtype=np.int64) * per_row
+    indices = np.empty(n * per_row, dtype=np.int32)
+    values = np.empty(n * per_row, dtype=np.float64)
+    base = (torch.arange(per_row, dtype=torch.int32, device=device) * stride)[None, :]
+    chunk = 1 << 21
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        off = torch.randint(0, stride, (m, per_row), generator=g, device=device, dtype=torch.int32)
+        indices[lo * per_row:(lo + m) * per_row] = torch.clamp(base + off, max=k - 1).reshape(-1).cpu().numpy()
+        values[lo * per_row:(lo + m) * per_row] = torch.rand(m * per_row, generator=g, device=device, dtype=torch.float64).cpu().numpy()
+    torch.cuda.empty_cache()
+    return indptr, indices, values
+
+
 def rmat_graph(scale_n: int, n_edges: int, a=0.57, b=0.19, c=0.19, seed: int = 42, permute: bool = True):
     """R-MAT (a,b,c,d) edge generator -> simple undirected CSR over n = scale_n nodes
     (n need not be a power of two: endpoints are drawn in the next power of two and rejected

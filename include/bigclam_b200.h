@@ -122,10 +122,10 @@ int bigclam_get_kernel_time(bigclam_ctx *ctx, double *step_kernel_ms_sum, int64_
 
 /* Interop with the host framework's plumbing (torch streams / NCCL buffers): use an existing
  * cudaStream_t, and expose device pointers of the current F (n x ld doubles, ld = row pitch) and sumF. */
-/* Sparse rows (BIGCLAM_F_SPARSE_ROWS + BIGCLAM_F_TIME_KERNELS): how the small nodes were processed since the
+/* Sparse rows (BIGCLAM_F_SPARSE_ROWS): how the small nodes were processed since the
  * context was created / the counters were last read — tiles done on the tile path, tiles that did not fit the
  * warp's shared memory and went node by node through the general path; the tile layout of the current order
- * (tiles, nodes on the general path, split hubs).  Reading resets the two counters. */
+ * (tiles, nodes on the general path, split hubs).  The two counters count from the previous read. */
 int bigclam_get_tile_stats(bigclam_ctx *ctx, int64_t *tiles_done, int64_t *tiles_fallback, int64_t *n_tiles,
                            int64_t *n_general_nodes, int64_t *n_split_hubs);
 
@@ -228,6 +228,7 @@ int bigclam_set_F_csr(bigclam_ctx *ctx, const int64_t *indptr, const int32_t *in
 int bigclam_get_F_nnz(bigclam_ctx *ctx, int64_t *nnz_out);
 int bigclam_get_F_csr(bigclam_ctx *ctx, int64_t *indptr_out, int32_t *indices_out, double *values_out);
 int bigclam_set_pool_region(bigclam_ctx *ctx, int64_t base_words, int64_t cap_words);
+int bigclam_get_pool_capacity(bigclam_ctx *ctx, int64_t *words_out);   /* words of each row pool (what the regions partition) */
 
 /*
  * Edge-list reader with GraphX semantics (GraphLoader.edgeListFile, bigclam4-7.scala:45;
