@@ -109,6 +109,8 @@ struct bigclam_ctx {
     unsigned long long *x_peer_flags[8] = {nullptr};
     bool x_ipc = false;                           // peers' buffers came through CUDA IPC (closed on destroy)
     bool local_mask = false;                      // bigclam_set_uset: the node-partitioned step kernels honour d_mask
+    bool work_clean = false;                      // the previous launch's reduction has reset the work counter
+    bool top_clean[2] = {false, false};           // ... and zeroed this pool's bump allocator
     std::vector<int64_t> h_rowptr;                // host copy of the CSR row pointers (order / tile rebuilds)
     std::vector<int32_t> h_col;
     std::vector<int32_t> h_owned;                 // owned nodes (processing order is derived from it)
@@ -135,6 +137,14 @@ static int fail(bigclam_ctx *c, int code, const char *fmt, ...) {
             return fail(ctx, BIGCLAM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
                         __FILE__, __LINE__);                                                      \
     } while (0)
+
+// The reduction behind a sparse step kernel resets the work counter and the next output pool's allocator on the
+// device; whenever the host changes the state behind its back (or a loop may have ended on no-op kernels) the next
+// launch does it with memory operations again.
+static void invalidate_resets(bigclam_ctx *ctx) {
+    ctx->work_clean = false;
+    ctx->top_clean[0] = ctx->top_clean[1] = false;
+}
 
 // A speculative step (bigclam_step) left its partial sums in d_partials: forget both.
 static int drop_speculation(bigclam_ctx *ctx) {
@@ -342,6 +352,7 @@ static int rebuild_sparse_lists(bigclam_ctx *ctx, const std::vector<NodeMeta> &m
     ctx->red_grid = (int)std::max<int64_t>(1, std::min<int64_t>(2 * (int64_t)ctx->num_sms, (cnt + 32 * kRedWarps - 1) / (32 * kRedWarps)));
     cudaFree(ctx->d_block_part); ctx->d_block_part = nullptr;
     CU(cudaMalloc(&ctx->d_block_part, sizeof(double) * (size_t)ctx->red_grid * ((size_t)ctx->ld + 2)));
+    invalidate_resets(ctx);
     ctx->h_work_init = 0;                                  // every item of the sparse kernel is handed out dynamically
     if (ctx->d_work != nullptr) CU(cudaMemcpy(ctx->d_work + 1, &ctx->h_work_init, sizeof(unsigned int), cudaMemcpyHostToDevice));
     return BIGCLAM_OK;
@@ -682,6 +693,7 @@ static int alloc_dense(bigclam_ctx *ctx, int b) {
 // Sparse mode: rebuild the sparse rows of the current buffer from its dense mirror d_F[cur].
 static int sparse_from_dense(bigclam_ctx *ctx) {
     const int b = ctx->cur;
+    invalidate_resets(ctx);
     CU(cudaMemsetAsync(ctx->d_pool_top + b, 0, sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_overflow, 0, sizeof(int32_t), ctx->stream));
     const int wpb = 8;
@@ -824,6 +836,7 @@ extern "C" int bigclam_set_F_csr(bigclam_ctx *ctx, const int64_t *indptr, const 
     }
     CU(cudaSetDevice(ctx->device));
     if (int rd = drop_speculation(ctx)) return rd;
+    invalidate_resets(ctx);
     uint64_t need = 0;
     for (int64_t u = 0; u < n; ++u) {
         uint32_t cnt = 0;
@@ -1013,7 +1026,9 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
         CU(cudaMemsetAsync(ctx->d_hub_counters, 0, sizeof(unsigned int) * (2 * (size_t)ctx->n_mega + 1), ctx->stream));
     }
     // positions 0 .. 3*#warps-1 are pre-assigned statically, the rest is handed out dynamically
-    CU(cudaMemcpyAsync(ctx->d_work, ctx->d_work + 1, sizeof(unsigned int), cudaMemcpyDeviceToDevice, ctx->stream));
+    // (sparse engine: the previous launch's reduce_kernel has usually done this already)
+    if (!(ctx->sparse && ctx->work_clean))
+        CU(cudaMemcpyAsync(ctx->d_work, ctx->d_work + 1, sizeof(unsigned int), cudaMemcpyDeviceToDevice, ctx->stream));
     if (ctx->sparse) {
         // reads hdr/pool of the current buffer, writes the other one (its bump allocator starts at zero)
         const int in = ctx->cur, out = in ^ 1;
@@ -1032,7 +1047,8 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
             sp.peer_pool[r] = (r < ctx->n_peers) ? ctx->peer_pool[out][r] : nullptr;
         }
         if (a.do_linesearch) {
-            CU(cudaMemsetAsync(sp.pool_top, 0, sizeof(unsigned long long), ctx->stream));
+            if (!ctx->top_clean[out]) CU(cudaMemsetAsync(sp.pool_top, 0, sizeof(unsigned long long), ctx->stream));
+            ctx->top_clean[out] = false;
             ctx->dense_valid = false;
         }
         sp.hub_work = ctx->d_hub_counters + 2 * (size_t)std::max<int32_t>(1, ctx->n_mega);
@@ -1081,6 +1097,15 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
         r.ticket = ctx->d_ticket;
         r.partials = ctx->d_partials;
         r.done_flag = a.done_flag;
+        r.work_counter = ctx->d_work;
+        r.work_init = ctx->h_work_init;
+        // the input pool of a step is the output pool of the next one: its allocator can be zeroed now.  Not under a
+        // Not for a PRE-only launch (the state stays where it is).
+        // (under a done flag the kernels of a converged loop are no-ops and skip this: the loops invalidate the host's
+        // bookkeeping when they end, see invalidate_resets)
+        r.pool_top_in = a.do_linesearch ? ctx->d_pool_top + in : nullptr;
+        ctx->work_clean = true;
+        if (a.do_linesearch) ctx->top_clean[in] = true;
         reduce_kernel<<<ctx->red_grid, kRedWarps * 32, sizeof(double) * kRedWarps * (size_t)sp_ldp(ctx->ld), ctx->stream>>>(r);
         CU(cudaGetLastError());
         if (is_step) ++ctx->last_step_launches;
@@ -1153,6 +1178,7 @@ static int launch_finish(bigclam_ctx *ctx, long long kernel_index, int variant, 
 
 static int reset_run_state(bigclam_ctx *ctx) {
     ctx->spec_valid = false;
+    invalidate_resets(ctx);
     CU(cudaMemsetAsync(ctx->d_done, 0, sizeof(int32_t), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_state, 0, sizeof(RunState), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_partials, 0, sizeof(double) * (2 * (size_t)ctx->ld + 2), ctx->stream));
@@ -1302,6 +1328,7 @@ extern "C" int bigclam_run(bigclam_ctx *ctx, int32_t variant, double rel_tol, in
     }
     ctx->cur = (start_cur + (int)(calls & 1)) & 1;
     ctx->dense_valid = false;
+    invalidate_resets(ctx);
     if (int ro = check_overflow(ctx)) return ro;
     if (llh_out) *llh_out = hst->ret_llh;
     if (calls_out) *calls_out = calls;
@@ -1412,6 +1439,7 @@ extern "C" int bigclam_rollback(bigclam_ctx *ctx) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
     CU(cudaSetDevice(ctx->device));
     if (int rd = drop_speculation(ctx)) return rd;
+    invalidate_resets(ctx);
     ctx->cur ^= 1;
     ctx->dense_valid = false;
     return BIGCLAM_OK;
@@ -1920,7 +1948,7 @@ extern "C" int bigclam_multi_run(bigclam_multi *m, int32_t variant, double rel_t
         if (cudaMemcpyAsync(hst, c0->d_state, sizeof(RunState), cudaMemcpyDeviceToHost, c0->stream) != cudaSuccess) return mfail(m, BIGCLAM_ECUDA, "state download failed");
         if (int rs = multi_sync(m)) return rs;
     }
-    for (bigclam_ctx *c : m->r) { c->cur = (start_cur + (int)(calls & 1)) & 1; c->dense_valid = false; }
+    for (bigclam_ctx *c : m->r) { c->cur = (start_cur + (int)(calls & 1)) & 1; c->dense_valid = false; invalidate_resets(c); }
     if (llh_out) *llh_out = hst->ret_llh;
     if (calls_out) *calls_out = calls;
     if (llh_trace != nullptr && trace_cap > 0) {

@@ -891,6 +891,9 @@ struct ReduceArgs {
     unsigned int *ticket;
     double *partials;         // 2 * ld + 2
     const int32_t *done_flag;
+    unsigned int *work_counter;          // reset to work_init for the next launch (no separate memcpy node per step)
+    unsigned int work_init;
+    unsigned long long *pool_top_in;     // zeroed: this step's input pool is the next step's output pool
     // node-partitioned multi-GPU (fused collective, no NCCL on the data path): the last block also stores this
     // rank's sums into its slot of every rank's exchange buffer (peer memory over NVLink) and then raises its
     // flag there to `seq`; xreduce_kernel on every rank adds the slots up in rank order once all flags are up.
@@ -963,12 +966,28 @@ __global__ void __launch_bounds__(kRedWarps * 32) reduce_kernel(const ReduceArgs
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // block partials in block order, four independent running sums per component (blocks b, b+1, b+2, b+3 of every
+    // group of four) added up in a fixed association: the same bits from run to run, and four loads in flight
     for (int c = threadIdx.x; c < ld + 2; c += blockDim.x) {
-        double v = 0.0;
-        for (unsigned int b = 0; b < gridDim.x; ++b) v += __ldcg(r.block_part + (size_t)b * (ld + 2) + c);
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        const unsigned int nb = gridDim.x;
+        unsigned int b = 0;
+        for (; b + 4 <= nb; b += 4) {
+            v0 += __ldcg(r.block_part + (size_t)(b + 0) * (ld + 2) + c);
+            v1 += __ldcg(r.block_part + (size_t)(b + 1) * (ld + 2) + c);
+            v2 += __ldcg(r.block_part + (size_t)(b + 2) * (ld + 2) + c);
+            v3 += __ldcg(r.block_part + (size_t)(b + 3) * (ld + 2) + c);
+        }
+        for (; b < nb; ++b) v0 += __ldcg(r.block_part + (size_t)b * (ld + 2) + c);
+        const double v = (v0 + v1) + (v2 + v3);
         if (c < ld) r.partials[c] = v;
         else r.partials[2 * ld + (c - ld)] = v;
         for (int p = 0; p < r.world; ++p) r.xslot[p][c] = v;
+    }
+    // the next launch starts from a fresh work counter, and the buffer this step read becomes the next output pool
+    if (threadIdx.x == 0) {
+        if (r.work_counter != nullptr) *r.work_counter = r.work_init;
+        if (r.pool_top_in != nullptr) *r.pool_top_in = 0ull;
     }
     if (threadIdx.x == 0) *r.ticket = 0u;
     if (r.world > 0) {

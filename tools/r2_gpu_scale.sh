@@ -7,9 +7,9 @@ N=${1:-8}
 run() {   # name, extra bench args
   local name=$1; shift
   if [ "$N" = "1" ]; then
-    timeout 1500 python bench.py --no-cpu --no-init-a --no-traffic "$@" > gpurun_out/r2g_${name}_n$N.json 2> gpurun_out/r2g_${name}_n$N.err
+    timeout ${TMO:-300} python bench.py --no-cpu --no-init-a --no-traffic "$@" > gpurun_out/r2g_${name}_n$N.json 2> gpurun_out/r2g_${name}_n$N.err
   else
-    timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N "$@" > gpurun_out/r2g_${name}_n$N.json 2> gpurun_out/r2g_${name}_n$N.err
+    timeout ${TMO:-300} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N "$@" > gpurun_out/r2g_${name}_n$N.json 2> gpurun_out/r2g_${name}_n$N.err
   fi
   python - <<PY
 import json
@@ -21,11 +21,13 @@ except Exception as e:
 PY
 }
 nvidia-smi -L | wc -l
+echo "== smoke"; timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 if [ "$N" != "1" ]; then
-  echo "== bigclam_multi_* tests"; timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q > gpurun_out/r2g_pytest_multi_n$N.log 2>&1; tail -2 gpurun_out/r2g_pytest_multi_n$N.log
+  echo "== bigclam_multi_* tests"; timeout 240 python -m pytest tests/test_gpu_multi.py -m gpu -q -x > gpurun_out/r2g_pytest_multi_n$N.log 2>&1; tail -2 gpurun_out/r2g_pytest_multi_n$N.log
 fi
-run amazon200 --steps 50 --warmup 5
-run amazon500 --config amazon500 --steps 30 --warmup 5
+TMO=240 run amazon200 --steps 50 --warmup 5
 if [ "${2:-}" = "rmat" ]; then
-  run rmat --config rmat --steps 5 --warmup 3
+  TMO=540 run rmat --config rmat --steps 5 --warmup 3
+else
+  TMO=240 run amazon500 --config amazon500 --steps 30 --warmup 5
 fi
