@@ -290,7 +290,8 @@ static int rebuild_sparse_lists(bigclam_ctx *ctx, const std::vector<NodeMeta> &m
             const int32_t deg = meta[(size_t)i].deg;
             HubItem it{};
             it.hub = i;
-            it.nslices = (deg + kSpHubSeg - 1) / kSpHubSeg;
+            it.seg = std::max(kSpHubSeg, (deg + kSpHubMaxSlices - 1) / kSpHubMaxSlices);
+            it.nslices = (deg + it.seg - 1) / it.seg;
             it.mslot = slots;                           // first scratch slot of the hub: nslices + 1 slots
             slots += it.nslices + 1;
             for (int32_t sl = 0; sl < it.nslices; ++sl) {
@@ -658,7 +659,9 @@ extern "C" int bigclam_set_stream(bigclam_ctx *ctx, void *cuda_stream) {
 
 extern "C" int bigclam_device_state(bigclam_ctx *ctx, void **F_dev, void **F_next_dev, void **sumF_dev, int64_t *ld) {
     if (ctx == nullptr) return BIGCLAM_EINVAL;
-    if (ctx->sparse) {                       // the dense buffers are only a mirror here: refresh it
+    if (ctx->sparse && (F_dev != nullptr || F_next_dev != nullptr)) {
+        // the dense buffers are only a mirror here: build / refresh it — only when the caller asks for dense rows
+        // (n x K may not fit anywhere: R-MAT 10M x 1000)
         CU(cudaSetDevice(ctx->device));
         if (int re = ensure_dense(ctx)) return re;
     }
@@ -1737,20 +1740,32 @@ extern "C" int bigclam_multi_create(bigclam_multi **out, int64_t n, const int64_
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) MFAIL(BIGCLAM_ECUDA, "bigclam_multi_create: cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
                 (void)cudaGetLastError();
             }
-        // owned nodes: the degree-sorted node list dealt round-robin; pool regions in proportion to the owned counts
+        // owned nodes: the degree-sorted node list dealt to the least loaded rank (load = neighbour-list entries + 1 per
+        // node, ties to the lowest rank): equal work even when a few hubs hold a sizeable part of the edges; pool
+        // regions in proportion to the owned counts
         std::vector<int32_t> order((size_t)n);
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return (rowptr[a + 1] - rowptr[a]) > (rowptr[b + 1] - rowptr[b]); });
+        std::vector<std::vector<int32_t>> mine((size_t)world);
+        {
+            std::vector<int64_t> load((size_t)world, 0);
+            for (int64_t q = 0; q < n; ++q) {
+                int best = 0;
+                for (int i = 1; i < world; ++i)
+                    if (load[(size_t)i] < load[(size_t)best]) best = i;
+                const int32_t u = order[(size_t)q];
+                mine[(size_t)best].push_back(u);
+                load[(size_t)best] += (rowptr[u + 1] - rowptr[u]) + 1;
+            }
+        }
         uint64_t cap = m->r[0]->pool_cap8;
         for (int i = 1; i < world; ++i) cap = std::min(cap, m->r[(size_t)i]->pool_cap8);
         uint64_t base = 0;
         for (int i = 0; i < world; ++i) {
             bigclam_ctx *c = m->r[(size_t)i];
-            std::vector<int32_t> mine;
-            for (int64_t q = i; q < n; q += world) mine.push_back(order[(size_t)q]);
-            int rc = bigclam_set_owned_nodes(c, mine.data(), (int64_t)mine.size());
+            int rc = bigclam_set_owned_nodes(c, mine[(size_t)i].data(), (int64_t)mine[(size_t)i].size());
             if (rc != BIGCLAM_OK) MFAIL(rc, "bigclam_multi_create: %s", bigclam_last_error(c));
-            uint64_t share = (uint64_t)((double)cap * (double)mine.size() / (double)n) & ~(uint64_t)1;
+            uint64_t share = (uint64_t)((double)cap * (double)mine[(size_t)i].size() / (double)n) & ~(uint64_t)1;
             if (i == world - 1) share = (cap - base) & ~(uint64_t)1;
             rc = bigclam_set_pool_region(c, (int64_t)base, (int64_t)share);
             if (rc != BIGCLAM_OK) MFAIL(rc, "bigclam_multi_create: %s", bigclam_last_error(c));

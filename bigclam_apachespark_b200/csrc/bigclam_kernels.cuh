@@ -581,7 +581,8 @@ struct HubItem {
     int32_t phase;
     int32_t mslot;    // scratch / counter slot of the mega hub (0 for phase-0 hubs)
     int32_t nslices;
-    int32_t pad[3];
+    int32_t seg;      // edges per slice (sparse engine: kSpHubSeg, more for very large hubs)
+    int32_t pad[2];
 };
 
 struct HubArgs {

@@ -112,6 +112,7 @@ __host__ __device__ inline size_t sp_gen_warp_bytes(int ld) {
 // Items are handed out in that order by one counter and every warp holds one item at a time on a grid whose
 // warps are all resident, so a waiting warp only waits for items that are being processed: no deadlock.
 constexpr int kSpHubSeg = 96;
+constexpr int kSpHubMaxSlices = 192;      // very large hubs get longer segments: the slot sums are taken by one warp per hub
 // scratch of one hub: (nslices + 1) x (ld + 32) doubles: slice sl holds  G_sl[ld] | S1_sl | ST_sl[16], the last
 // slot the sums over the slices (G | S1)
 __host__ __device__ inline size_t sp_hub_stride(int ld) { return (size_t)ld + 32; }
@@ -525,7 +526,7 @@ struct SpGen {
         const size_t hstride = sp_hub_stride(ld);
         double *scr0 = a->hub_scratch + (size_t)item.mslot * hstride;            // mslot: first scratch slot of the hub
         unsigned int *cnt = a->hub_counters + 2 * (size_t)item.hub;
-        const int sb = item.slice * kSpHubSeg, se = min(deg, sb + kSpHubSeg);
+        const int sb = item.slice * item.seg, se = min(deg, sb + item.seg);
         const uint64_t hu = __ldg(sp->hdr_in + u);
         const int cu = (int)sp_cnt(hu);
         const double *uval = sp->pool_in + sp_off8(hu);

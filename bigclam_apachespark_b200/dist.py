@@ -52,13 +52,34 @@ class _DevMemI8:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "|i1", "data": (int(ptr), False), "version": 3}
 
 
-def deal_by_degree(rowptr: np.ndarray, rank: int, world: int) -> np.ndarray:
-    """Owned node set of `rank` when the degree-sorted node list is dealt round-robin over the ranks:
-    every rank gets the same mix of hubs and leaves (used with the peer-store exchange, which does not
-    need contiguous ranges)."""
-    deg = np.diff(rowptr)
+def deal_all_by_degree(rowptr: np.ndarray, world: int):
+    """Owned node sets of all ranks: the degree-sorted node list dealt to the least loaded rank (load = neighbour-list
+    entries + 1 per node, ties to the lowest rank) — the same rule as bigclam_multi_create.  The few thousand largest
+    nodes go one by one (a hub can hold a sizeable part of a rank's edges); the long tail of similar degrees is dealt
+    in snake order, which keeps the loads level.  Every rank gets the same mix of hubs and leaves."""
+    deg = np.diff(rowptr).astype(np.int64)
     order = np.argsort(-deg, kind="stable")
-    return np.sort(order[rank::world]).astype(np.int32)
+    n = len(order)
+    head = min(n, 4096 * world)
+    owner = np.empty(n, dtype=np.int32)
+    load = np.zeros(world, dtype=np.int64)
+    for q in range(head):
+        r = int(np.argmin(load))
+        owner[q] = r
+        load[r] += deg[order[q]] + 1
+    if head < n:
+        # snake deal of the tail, starting with the currently least loaded ranks
+        ranks = np.argsort(load, kind="stable").astype(np.int32)
+        k = np.arange(n - head)
+        pos = k % (2 * world)
+        pos = np.where(pos < world, pos, 2 * world - 1 - pos)
+        owner[head:] = ranks[pos]
+    return [np.sort(order[owner == r]).astype(np.int32) for r in range(world)]
+
+
+def deal_by_degree(rowptr: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Owned node set of `rank` (see deal_all_by_degree)."""
+    return deal_all_by_degree(rowptr, world)[rank]
 
 
 class CudaEngine:
@@ -99,8 +120,7 @@ class CudaEngine:
         self.lo, self.hi = int(lo), int(hi)
         self._views = {}
         self.n, self.k = solver.n, solver.K
-        _, _, _, ld = solver.device_state()
-        self.ld = ld
+        self.ld = (solver.K + 3) & ~3            # row pitch of the dense layout == length of the partial-sum vectors' D part
 
     def _view(self, ptr, count):
         return self.torch.as_tensor(_DevMem(ptr, count), device="cuda")
@@ -355,8 +375,9 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, base_conf
     b.set_F(F0)
     bounds = partition_by_nnz(rp, world)
     exchange = os.environ.get("BIGCLAM_EXCHANGE", "p2p")
-    nodes = deal_by_degree(rp, rank, world) if exchange == "p2p" else None
-    counts = [len(range(r, n, world)) for r in range(world)] if exchange == "p2p" else None     # |order[r::world]|
+    deal = deal_all_by_degree(rp, world) if exchange == "p2p" else None
+    nodes = deal[rank] if deal is not None else None
+    counts = [len(x) for x in deal] if deal is not None else None
     pool_words = None
     if sparse:
         from . import _lib
@@ -411,7 +432,7 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, base_conf
     per_rank = torch.zeros(world, device="cuda", dtype=torch.float64)
     per_rank[rank] = kms / max(nk, 1)
     dist.all_reduce(per_rank)
-    own0 = deal_by_degree(rp, 0, world) if exchange == "p2p" else np.arange(bounds[0], bounds[1])
+    own0 = deal[0] if deal is not None else np.arange(bounds[0], bounds[1])
     own_nnz = int(np.diff(rp)[own0].sum())
     own_n = len(own0)
     ms_per_step = total_ms / args.steps

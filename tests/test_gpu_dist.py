@@ -20,7 +20,7 @@ def _worker(rank, world, port, exchange, out):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from bigclam_apachespark_b200 import BigClam
-    from bigclam_apachespark_b200.dist import CudaEngine, DistBigClam, deal_by_degree, partition_by_nnz
+    from bigclam_apachespark_b200.dist import CudaEngine, DistBigClam, deal_all_by_degree, partition_by_nnz
     from oracle import oracle as O
     n, k = 3000, 40
     rp, col = random_graph(n, 8, seed=5, hub=300)
@@ -37,8 +37,9 @@ def _worker(rank, world, port, exchange, out):
     b.set_stream(torch.cuda.current_stream().cuda_stream)
     b.set_F(F0, sumF=sumF)
     bounds = partition_by_nnz(rp, world)
-    nodes = deal_by_degree(rp, rank, world) if exchange == "p2p" else None
-    counts = [len(range(r, n, world)) for r in range(world)]
+    deal = deal_all_by_degree(rp, world)
+    nodes = deal[rank] if exchange == "p2p" else None
+    counts = [len(x) for x in deal]
     d = DistBigClam(CudaEngine(b, int(bounds[rank]), int(bounds[rank + 1]), nodes=nodes, owned_counts=counts, rank=rank),
                     rp, rank, world, bounds, exchange=exchange)
     llhs = [d.backtrackingLineSearchs() for _ in range(3)]

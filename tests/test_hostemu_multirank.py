@@ -20,7 +20,7 @@ pytestmark = [pytest.mark.gpu,
 def test_two_ranks_through_the_c_abi(oracle, sparse, hub, monkeypatch):
     monkeypatch.setenv("BIGCLAM_SPARSE_HUB_DEG", "100")
     from bigclam_apachespark_b200 import BigClam, _lib
-    from bigclam_apachespark_b200.dist import deal_by_degree
+    from bigclam_apachespark_b200.dist import deal_all_by_degree
     lib = _lib.load()
     world, n, k = 2, 160, 12
     rp, col = random_graph(n, 5, seed=31, hub=hub)
@@ -32,10 +32,11 @@ def test_two_ranks_through_the_c_abi(oracle, sparse, hub, monkeypatch):
     for r in range(world):
         b = BigClam(record_accepted=True, sparse_rows=sparse)
         b.set_graph(rp, col).set_K(k).set_F(F0, sumF=sumF)
-        nodes = deal_by_degree(rp, r, world)
+        deal = deal_all_by_degree(rp, world)
+        nodes = deal[r]
         _lib.check(lib.bigclam_set_owned_nodes(b._ctx, nodes.ctypes.data, len(nodes)), b._ctx)
         if sparse:
-            counts = [len(range(q, n, world)) for q in range(world)]
+            counts = [len(x) for x in deal]
             row_words = _lib.sparse_node_words(ld)
             _lib.check(lib.bigclam_set_pool_region(b._ctx, sum(counts[:r]) * row_words, counts[r] * row_words), b._ctx)
         ranks.append(b)

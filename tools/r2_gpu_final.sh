@@ -1,0 +1,11 @@
+#!/bin/bash
+# Final single-GPU evidence of the round: GPU test suite, the default bench line, the reference arm, the ncu launch
+# list of the bench command and one full ncu capture of the step kernel.  Logs under gpurun_out/r2z_*.
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+echo "== GPU test suite"; timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2z_pytest_gpu.log 2>&1; tail -3 gpurun_out/r2z_pytest_gpu.log
+echo "== bench (default)"; timeout 900 python bench.py > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err; tail -c 300 gpurun_out/r2z_bench.json; tail -2 gpurun_out/r2z_bench.err
+echo "== bench --impl reference"; timeout 600 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/r2z_bench_reference.json 2> gpurun_out/r2z_bench_reference.err; tail -c 400 gpurun_out/r2z_bench_reference.json
+echo "== ncu launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2z_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-init-a --no-traffic > gpurun_out/r2z_launches_bench.log 2>&1; grep -c tile_step_kernel gpurun_out/r2z_launches.csv
+echo "== ncu --set full of the step kernel"; BIGCLAM_AB_SPARSE=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:tile_step_kernel --launch-skip 6 --launch-count 1 -f -o gpurun_out/r2z_prof_tile python tools/profile_step.py 200 8 2 > gpurun_out/r2z_ncu.log 2>&1; tail -2 gpurun_out/r2z_ncu.log

@@ -21,6 +21,16 @@ except Exception as e:
 PY
 }
 nvidia-smi -L | wc -l
+if [ "${2:-}" = "rmatonly" ]; then
+  TMO=540 run rmat --config rmat --steps 5 --warmup 3
+  exit 0
+fi
+if [ "${2:-}" = "final8" ]; then
+  TMO=540 run rmat --config rmat --steps 5 --warmup 3
+  TMO=240 run amazon500 --config amazon500 --steps 30 --warmup 5
+  TMO=240 run amazon200 --steps 50 --warmup 5
+  exit 0
+fi
 echo "== smoke"; timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 if [ "$N" != "1" ]; then
   echo "== bigclam_multi_* tests"; timeout 240 python -m pytest tests/test_gpu_multi.py -m gpu -q -x > gpurun_out/r2g_pytest_multi_n$N.log 2>&1; tail -2 gpurun_out/r2g_pytest_multi_n$N.log
