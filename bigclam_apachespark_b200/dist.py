@@ -446,7 +446,7 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, base_conf
             "iters_per_sec": 1e3 / ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "SNAP topology (package data) or generated R-MAT + synthetic F0",
             "config": base_config(args.graph, K, n, nnz, args.layout),
-            "parallelism": f"node-partitioned x{world} ({'degree-sorted nodes dealt round-robin' if exchange == 'p2p' else 'nnz-balanced contiguous ranges'}), "
+            "parallelism": f"node-partitioned x{world} ({'degree-sorted nodes dealt to the least loaded rank' if exchange == 'p2p' else 'nnz-balanced contiguous ranges'}), "
                            f"F replicated, rows pushed into the peers' replicas by the step kernel (NVLink), sums [sum(old-new), llh, n_updated] by "
                            f"{'the fused device-side collective (peer stores + flags)' if d.fused else 'an NCCL all-reduce'}",
             "l2": "sparse rows: working set L2-resident by design, no flush" if sparse else "inputs larger than L2, no flush",

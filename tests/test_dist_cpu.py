@@ -139,3 +139,19 @@ def test_partition_by_nnz_balance(graphs):
         assert len(b) == world + 1 and b[0] == 0 and b[-1] == len(rp) - 1
         w = np.diff(rp[b]) + np.diff(b)
         assert w.max() <= 1.02 * w.mean() + 600
+
+
+def test_deal_all_by_degree_balances_edges_and_covers_every_node():
+    """The owned-node rule of the node-partitioned path (dist.deal_all_by_degree == bigclam_multi_create): every node
+    exactly once, neighbour-list entries per rank level even on a skewed graph."""
+    from bigclam_apachespark_b200 import graphs as G
+    from bigclam_apachespark_b200.dist import deal_all_by_degree
+    rp, col = G.rmat_graph(20000, 150000, seed=7)
+    deg = np.diff(rp)
+    for world in (2, 3, 8):
+        deal = deal_all_by_degree(rp, world)
+        allv = np.concatenate(deal)
+        assert len(allv) == len(deg) and len(np.unique(allv)) == len(deg)
+        loads = np.array([deg[x].sum() for x in deal])
+        assert loads.max() - loads.min() <= max(deg.max(), 0.002 * loads.mean())
+        assert max(len(x) for x in deal) - min(len(x) for x in deal) <= 0.02 * len(deg) / world + 4

@@ -203,3 +203,41 @@ def test_sparse_pool_exhaustion_is_reported(monkeypatch):
     with pytest.raises(_lib.BigclamError):
         b.set_F(rng.random((n, k)))                      # 600 full rows do not fit 2000 words
     b.close()
+
+
+def test_sparse_reruns_are_bit_identical(oracle):
+    """No floating-point atomics on the sparse path: per-node results + fixed-order reduction.  Two fresh contexts give
+    the same bits (LLH trace, F, sumF) — with dynamic work distribution, split hubs and tiles that fall back."""
+    rp, col = random_graph(3000, 7, seed=17, hub=400)
+    k = 60
+    rng = np.random.default_rng(17)
+    F0 = rng.random((3000, k)) * (rng.random((3000, k)) < 0.15)
+    sumF = oracle.colsum(F0)
+    out = []
+    for _ in range(2):
+        b = _solver(rp, col, k, F0, sumF)
+        llh = b._run(4, 0.0, 7)
+        out.append((llh, b.last_trace.tobytes(), b.F.tobytes(), b.sumF.tobytes()))
+        b.close()
+    assert out[0] == out[1]
+
+
+def test_sparse_tiles_are_recut_when_rows_fill_up(oracle):
+    """Small K: the rows fill up while the solver runs and the tiles cut for the sparse F0 start to fall back; between its
+    batches bigclam_run re-cuts them (smaller tiles / tiles off) — results unchanged."""
+    n, k = 4000, 24
+    rp, col = random_graph(n, 10, seed=23)
+    rng = np.random.default_rng(23)
+    F0 = rng.random((n, k)) * (rng.random((n, k)) < 0.1)
+    sumF = oracle.colsum(F0)
+    b = _solver(rp, col, k, F0, sumF, time_kernels=True)
+    t0 = b.tile_stats()
+    llh = b._run(4, 0.0, 24)
+    t1 = b.tile_stats()
+    Fo, so, llh_o, calls_o, _ = oracle.run(rp, col, F0, sumF, oracle.make_params(k), variant=4, rel_tol=0.0, max_outer=24)
+    assert b.last_calls == calls_o == 24
+    assert abs(llh - llh_o) <= 1e-9 * abs(llh_o)
+    assert np.abs(b.F - Fo).max() <= 1e-7 * max(np.abs(Fo).max(), 1e-300)
+    assert t0["n_tiles"] > 0
+    print("tiles before / after:", t0, t1)
+    b.close()
