@@ -16,6 +16,7 @@ OK, EINVAL, ECUDA, ENOMEM, EIO, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 F_TIME_KERNELS = 1
 F_RECORD_ACCEPTED = 2
 F_SPARSE_ROWS = 4
+F_LS_EXHAUSTIVE = 8
 
 
 class Params(C.Structure):
@@ -73,6 +74,7 @@ SIGNATURES = {
     "bigclam_get_accepted": (C.c_int, [_vp, _vp]),
     "bigclam_get_kernel_time": (C.c_int, [_vp, _pd, _pi64, _pi64]),
     "bigclam_get_tile_stats": (C.c_int, [_vp, _pi64, _pi64, _pi64, _pi64, _pi64]),
+    "bigclam_get_ls_stats": (C.c_int, [_vp, _pi64, _pi64]),
     "bigclam_retile": (C.c_int, [_vp]),
     "bigclam_set_stream": (C.c_int, [_vp, _vp]),
     "bigclam_device_state": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _pi64]),

@@ -98,7 +98,9 @@ struct bigclam_ctx {
     double tile_avg16 = 1.0;                      // average row size (16-byte chunks) the tiles were cut for
     unsigned int stats_seen[2] = {0u, 0u};        // d_stats at the last look (maybe_retile)
     unsigned int stats_read[2] = {0u, 0u};        // d_stats at the last bigclam_get_tile_stats
-    unsigned int *d_stats = nullptr;              // [tiles on the tile path, tiles that fell back], BIGCLAM_F_TIME_KERNELS only
+    unsigned int *d_stats = nullptr;              // [tiles on the tile path, tiles that fell back, nodes line-searched, nodes that asked for it]
+    unsigned int ls_read[2] = {0u, 0u};           // d_stats[2..3] at the last bigclam_get_ls_stats
+    bool ls_exhaustive = false;                   // BIGCLAM_F_LS_EXHAUSTIVE (or the environment variable BIGCLAM_LS_EXHAUSTIVE=1)
     // fused collective of the node-partitioned path (reduce_kernel publishes, xreduce_kernel adds up): this rank's
     // exchange buffer [2 halves][world][ld + 2] and flags [world], and every rank's (peer memory, incl. our own)
     int x_world = 0, x_rank = 0;
@@ -569,6 +571,8 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
         sbps = std::min(sbps, tl_blocks_that_fit(ld, ctx->sp_wpb));
         ctx->sp_grid = ctx->num_sms * sbps;
         ctx->h_work_init = 0;
+        ctx->ls_exhaustive = (params->flags & BIGCLAM_F_LS_EXHAUSTIVE) != 0;
+        if (const char *ev = std::getenv("BIGCLAM_LS_EXHAUSTIVE")) ctx->ls_exhaustive = std::atoi(ev) != 0;
         if (const char *ev = std::getenv("BIGCLAM_TILE_EDGES")) ctx->tile_edges = std::max(0, std::min(kTlMaxEdges, std::atoi(ev)));
     }
 
@@ -632,8 +636,8 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
         CUC(cudaMemset(ctx->d_dcnt, 0, sizeof(unsigned short) * (size_t)n));
         CUC(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
         CUC(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
-        CUC(cudaMalloc(&ctx->d_stats, 2 * sizeof(unsigned int)));
-        CUC(cudaMemset(ctx->d_stats, 0, 2 * sizeof(unsigned int)));
+        CUC(cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned int)));
+        CUC(cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned int)));
         ctx->h_col.assign(col, col + nnz);
     }
 #undef CUC
@@ -1063,6 +1067,11 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
         sp.tiles = ctx->d_tiles;
         sp.tcol = ctx->d_tcol;
         sp.stats = ctx->d_stats;
+        // line search by bounds (bigclam_tile.cuh, H2): needs the reference's clamps in their usual order
+        sp.ls_prune = (ctx->ls_exhaustive || !(ctx->p.min_f == 0.0 && ctx->p.min_p > 0.0 && ctx->p.min_p < ctx->p.max_p && ctx->p.max_p < 1.0 && ctx->p.alpha > 0.0)) ? 0 : 1;
+        sp.pr_xlo = std::nextafterf((float)a.x_lo, 0.0f);
+        sp.pr_kinv = std::nextafterf((float)(1.0 / (1.0 - ctx->p.max_p)), INFINITY) * 1.000001f;
+        sp.pr_cap = std::nextafterf((float)(a.t_hi - a.t_lo), INFINITY) * 1.000001f;
         const bool hub = a.n_hub_items > 0, push = sp.n_peers > 0;
         const int threads = 32 * ctx->sp_wpb;
         if (hub && push) tile_step_kernel<true, true><<<ctx->sp_grid, threads, ctx->sp_smem, ctx->stream>>>(a, sp);
@@ -1349,6 +1358,21 @@ extern "C" int bigclam_get_kernel_time(bigclam_ctx *ctx, double *step_kernel_ms_
     if (step_kernel_ms_sum) *step_kernel_ms_sum = ctx->last_step_ms;
     if (step_kernel_launches) *step_kernel_launches = ctx->last_step_launches;
     if (all_kernel_launches) *all_kernel_launches = ctx->last_all_launches;
+    return BIGCLAM_OK;
+}
+
+extern "C" int bigclam_get_ls_stats(bigclam_ctx *ctx, int64_t *nodes_asked, int64_t *nodes_searched) {
+    if (ctx == nullptr) return BIGCLAM_EINVAL;
+    unsigned int st[4] = {0u, 0u, 0u, 0u};
+    if (ctx->sparse && ctx->d_stats != nullptr) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpy(st, ctx->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+    }
+    if (nodes_searched) *nodes_searched = (int64_t)(st[2] - ctx->ls_read[0]);
+    if (nodes_asked) *nodes_asked = (int64_t)(st[3] - ctx->ls_read[1]);
+    ctx->ls_read[0] = st[2];
+    ctx->ls_read[1] = st[3];
     return BIGCLAM_OK;
 }
 

@@ -90,7 +90,10 @@ struct SparseArgs {
     int32_t ntiles;
     const TileMeta *tiles;
     const int32_t *tcol;               // per tile edge: neighbour id | (node index within the tile << 28)
-    unsigned int *stats;               // optional [tiles done on the tile path, tiles that fell back]
+    unsigned int *stats;               // optional [tiles done on the tile path, tiles that fell back, nodes line-searched, nodes that asked for it]
+    // line search by bounds (bigclam_tile.cuh, H2): 0 = every candidate of every node is evaluated (BIGCLAM_F_LS_EXHAUSTIVE)
+    int32_t ls_prune;
+    float pr_xlo, pr_kinv, pr_cap;     // x_lo rounded down, 1 / (1 - MAX_P_) and S_hi - S_lo rounded up
 };
 
 // The dense per-warp vectors are padded to a multiple of 32 components (zeros: a padding component has

@@ -76,6 +76,7 @@ static_assert(kTlStage16 >= 264, "the neighbour staging buffer doubles as xs[32 
 static_assert(2 * kTlSlots >= 3 * kTlAct, "fg must hold (f, g) and sumF - f of the active components after compaction");
 static_assert(kTlEnt >= 128 && kTlEnt <= 256, "entry lists: the pair list (512 uint16) overlays ent_val; edge ids are bytes");
 static_assert(kTlAct <= 255, "active-component ids of the entry lists are bytes");
+static_assert(16 * kTlSlots >= 24 * kTlAct + 2 * 16 * kTlMaxEdges, "fg also holds sumF - f of the active components and the pair list of a line-search round");
 
 // per-warp shared memory of the tile path (W = ldp / 32 mask words per node)
 __host__ __device__ inline size_t tl_warp_bytes(int ld) {
@@ -83,7 +84,7 @@ __host__ __device__ inline size_t tl_warp_bytes(int ld) {
     size_t b = 16 * (size_t)kTlStage16;                 // stageN (later xs)
     b += 16 * (size_t)kTlOwn16;                         // stageO
     b += 16 * (size_t)kTlSlots;                         // fg (later fa | asfm)
-    b += 8 * (size_t)kTlEnt;                            // ent_val (later plist)
+    b += 8 * (size_t)kTlEnt;                            // ent_val
     b += 8 * 32 + 8 * 8 + 8 * 8;                        // we, n_llh, n_G2
     b += 4 * 2 * kTlMaxNodes * W + 4 * kTlMaxNodes;     // tmask, fmask, n_u
     b += 4 * (size_t)kTlAct;                            // lcnt
@@ -93,6 +94,7 @@ __host__ __device__ inline size_t tl_warp_bytes(int ld) {
     b += 2 * (40 + 40 + 12 + 12 + 12 + 8 + 8);          // e_soff, e_cnt, n_es, n_sb, n_ab, n_m, n_tot
     b += 2 * (size_t)kTlEnt + 8 + 8;                    // ent_e, ent_a, n_js, n_want
     b += (size_t)kTlErow + 2 * 34 + 32;                 // erow, epos, e_ni
+    b += 2 * 8 + 8;                                     // n_sv, n_sl (line search by bounds)
     return (b + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t tl_region_bytes(int ld) {
@@ -101,7 +103,7 @@ __host__ __device__ inline size_t tl_region_bytes(int ld) {
 }
 // block: steps[kMaxSteps] | sumF[ldp] | mbar[kTlWarps] | wpb x warp region
 __host__ __device__ inline size_t tl_block_smem_bytes(int ld, int wpb) {
-    return sizeof(double) * (kMaxSteps + (size_t)sp_ldp(ld) + kTlWarps) + (size_t)wpb * tl_region_bytes(ld);
+    return sizeof(double) * (kMaxSteps + (size_t)sp_ldp(ld) + kTlWarps + 8) + (size_t)wpb * tl_region_bytes(ld);
 }
 // warps per block: as many resident warps per SM as the shared memory (227 KB, 1 KB reserved per block) allows, in
 // at most kTlMaxBlocks blocks (wide rows run more blocks of fewer warps)
@@ -163,11 +165,15 @@ struct TlWarp {
     const SparseArgs *sp;
     const double *s_steps;
     const double *s_sumF;
+    const float *s_lns;              // upper bounds of ln(step size) (line search by bounds)
     double S2_all;                   // sum_c sumF_c^2 (fixed order)
     EdgeConst ec;
     unsigned char *stageN, *stageO;
     double2 *fg;
     double *xs, *ent_val, *we, *n_llh, *n_G2;
+    unsigned short *n_sv;
+    unsigned char *n_sl;
+    int last_ns, last_nw;            // nodes of the last tile that were line-searched / that wanted a line search
     unsigned long long *mbar;
     unsigned int *tmask, *fmask, *lcnt;
     int *n_u;
@@ -186,9 +192,10 @@ struct TlWarp {
         stageN = p;                                       p += 16 * (size_t)kTlStage16;
         xs = reinterpret_cast<double *>(stageN);          // (after the rows have been turned into per-component lists)
         stageO = p;                                       p += 16 * (size_t)kTlOwn16;
-        fg = reinterpret_cast<double2 *>(p);              p += 16 * (size_t)kTlSlots;
+        fg = reinterpret_cast<double2 *>(p);
+        plist = reinterpret_cast<unsigned short *>(p + 24 * (size_t)kTlAct);   // (behind fa | asfm, after the compaction of the active components)
+        p += 16 * (size_t)kTlSlots;
         ent_val = reinterpret_cast<double *>(p);          p += 8 * (size_t)kTlEnt;
-        plist = reinterpret_cast<unsigned short *>(ent_val);   // (after the merged dot / decide loop)
         we = reinterpret_cast<double *>(p);               p += 8 * 32;
         n_llh = reinterpret_cast<double *>(p);            p += 8 * 8;
         n_G2 = reinterpret_cast<double *>(p);             p += 8 * 8;
@@ -214,7 +221,11 @@ struct TlWarp {
         erow = p;                                         p += (size_t)kTlErow;
         e_ni = p;                                         p += 32;
         n_js = reinterpret_cast<signed char *>(p);        p += 8;
-        n_want = p;
+        n_want = p;                                       p += 8;
+        n_sl = p;                                         p += 8;
+        n_sv = reinterpret_cast<unsigned short *>(p);
+        last_ns = 0;
+        last_nw = 0;
     }
 
     // inclusive scan over the lanes of a group of gs lanes (sub = lane within the group)
@@ -226,7 +237,8 @@ struct TlWarp {
         }
         return v;
     }
-    __device__ __forceinline__ double group_sum(double v, int gs) const {
+    template <class T>
+    __device__ __forceinline__ T group_sum(T v, int gs) const {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
             if (o < gs) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -282,6 +294,7 @@ struct TlWarp {
             e_cnt[lane] = (unsigned short)ce;
             epos[lane] = (unsigned short)(incl_c - ce);
             e_ni[lane] = (unsigned char)ni;
+            if (lane == 0) epos[ne] = (unsigned short)T;
         }
         if (lane < nn) {
             e_soff[32 + lane] = (unsigned short)soff_u;
@@ -425,6 +438,18 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         double wgt;
         const double term = edge_term<true>(x, ec, wgt);
         we[lane] = wgt;
+        // [bounds, see H2] an edge that is NOT clamped at MAX_P_ is bounded by its tangent (the clamped edge term is
+        // concave from x_lo on) plus what the two clamps can add to it: below x_lo the term stops falling with the
+        // tangent (at most S_lo - tangent(0)); above x_hi the coded slope w - 1 is not the slope of the flat term
+        const bool prune_on = sp->ls_prune != 0;
+        const bool e_low = x <= ec.x_lo;
+        const float xf = (lane < ne) ? __double2float_ru(x) : 0.0f;
+        float violf = 0.0f;
+        if (prune_on && !e_low && lane < ne) {
+            const double m = wgt - 1.0;
+            const double v = (x < ec.x_hi) ? fma(m, x, ec.t_lo - (term - x)) : m * (x - ec.x_hi);
+            violf = (v > 0.0) ? __double2float_ru(v) * 1.000001f : 0.0f;
+        }
         const int es_g = gv ? (int)n_es[g] : 0;
         const int deg_g = gv ? (int)n_es[g + 1] - es_g : 0;
         double llh_g = 0.0;
@@ -464,6 +489,10 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         // ---------------- H. gradient (:168), |g|^2, active components ----------------
         int m_g = 0;
         bool hi_lane = false;
+        double G2n = 0.0, G2p = 0.0;     // [bounds] |g|^2 over the active components with g < 0 / g > 0
+        float r3 = 0.0f, r4 = 0.0f;      // [bounds] R3 >= sum fu_c |gt_c|; magnitudes behind the rounding allowance
+        float gmx = 0.0f;                // [bounds] largest positive gradient component
+        double G2node = 0.0;             // |g|^2 of the node (all K components)
         {
             double G2 = 0.0, SF2 = 0.0;
             int maxtot = tot_g;
@@ -483,13 +512,35 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
                     SF2 = fma(sf, sf, SF2);
                     act = (v.x > 0.0 || gr > 0.0);
                     hi_lane |= act && (v.x + gr > max_f);
+                    if (act && prune_on) {
+                        const float ga = __double2float_ru(fabs(gr)), ff = __double2float_ru(v.x);
+                        r3 = fmaf(ff, fmaf(2.0f, ga, __double2float_ru(fabs(sf))) + 3.0f * ff, r3);
+                        if (gr > 0.0) {
+                            G2p = fma(gr, gr, G2p);
+                            gmx = fmaxf(gmx, ga);
+                        } else {
+                            G2n = fma(gr, gr, G2n);
+                        }
+                    }
                 }
                 m_g += __popc((__ballot_sync(0xffffffffu, act) >> gsh) & gmask);
             }
             G2 = group_sum(G2, gs);
             SF2 = group_sum(SF2, gs);
+            if (prune_on) {
+                G2n = group_sum(G2n, gs);
+                G2p = group_sum(G2p, gs);
+                r3 = group_sum(r3, gs);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    if (o < gs) gmx = fmaxf(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
+                // sum_act |g_c| (2|g_c| + sumF_c + 3 fu_c) <= 2 |g|^2 + |g| sqrt(2 sum sumF_c^2 + 18 fu.fu) over the touched components
+                const float g2f = __double2float_ru(G2);
+                r4 = fmaf(2.0f, g2f, sqrtf(g2f) * sqrtf(fmaf(2.0f, __double2float_ru(SF2), 18.0f * __double2float_ru(fufu))) * 1.0001f);
+            }
             // an untouched component has fu = 0 and gradient -sumF_c: its square is part of S2_all
-            if (gv && sub == 0) n_G2[g] = (S2_all - SF2) + G2;
+            G2node = (S2_all - SF2) + G2;
+            if (gv && sub == 0) n_G2[g] = G2node;
         }
         if (!gv) m_g = 0;
         int ab_g = 0, maxm = 0;
@@ -503,6 +554,18 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         // no candidate of any node of the tile can reach MAX_F_ (the largest step is 1): the upper clamp is dropped
         const bool need_hi = __any_sync(0xffffffffu, hi_lane);
         __syncwarp();
+        // [bounds, see H2] of the edges that are clamped flat: Dp_e = sum_c max(g_c, 0) fv_c and En_e = sum_{c active} min(g_c, 0) fv_c
+        // (a component with g_c < 0 is active iff fu_c > 0)
+        double Dp = 0.0, En = 0.0;
+        if (prune_on && e_low && lane < ne) {
+#pragma unroll 1
+            for (int i = 0; i < ce; ++i) {
+                const double2 v = fg[ri[i]];
+                const double val = rv[i];
+                Dp = fma(val, v.y > 0.0 ? v.y : 0.0, Dp);
+                En = fma(val, (v.y < 0.0 && v.x > 0.0) ? v.y : 0.0, En);
+            }
+        }
         // the active components move to the front, in slot order: fg[a] = (fu_c, grad_c), slot_c[a] = c; amap: slot -> a
         int A = 0;
 #pragma unroll 1
@@ -524,156 +587,297 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         if (A > kTlAct - 1) return false;                      // (one spare: the padding component below)
         double *asfm = reinterpret_cast<double *>(fg + kTlAct);            // sumF_c - fu_c of the active components
 #pragma unroll 1
-        for (int t = lane; t < A; t += 32) { asfm[t] = s_sumF[slot_c[t]] - fg[t].x; lcnt[t] = 0u; }
+        for (int t = lane; t < A; t += 32) asfm[t] = s_sumF[slot_c[t]] - fg[t].x;
         // padding component A: fu = grad = 0, so every candidate is 0 there and adds exactly nothing — the lockstep loops
         // of the line search read it instead of predicating their bodies
         if (lane == 0) { fg[A] = make_double2(0.0, 0.0); asfm[A] = 0.0; }
         __syncwarp();
-        // ---------------- I. the neighbours' entries on active components, listed per component ----------------
-BIGCLAM_UNROLL(BIGCLAM_TL_UF)
-        for (int t = lane; t < T; t += 32) {
-            const int row = erow[t];
-            const double *vv = reinterpret_cast<const double *>(stageN + 16 * (size_t)e_soff[row]);
-            const unsigned an = amap[sp_idx(vv, (uint32_t)e_cnt[row])[t - (int)epos[row]]];
-            if (an != 0xffffu) atomicAdd(lcnt + an, 1u);
+        // ---------------- H2. bounds: which (node, candidate) pairs can pass the Armijo test at all ----------------
+        // Most candidates can be PROVEN to fail (:181) from what the PRE block already has.  Write the node's objective
+        // as phi(nf) = sum_v T(nf.fv) - nf.(sumF - fu), T(x) = S(x) + x, S(x) = log(1 - clamp(exp(-x))) (:166,:179): S is
+        // the constant S_lo up to x_lo (clamp at MAX_P_), concave and increasing up to x_hi, constant from there.  With
+        // D = nf - fu, D_c = min(max(s g_c, -fu_c), MAX_F_ - fu_c) (:110-113, MIN_F_ = 0) and fv >= 0:
+        //   * an edge with x_v >  x_lo:  S(x') - S(x_v) <= (w_v - 1) (x' - x_v) + viol_v               (tangent, see D.)
+        //   * an edge with x_v <= x_lo:  S(x') - S(x_v) <= H(x_v + s Dp_v),  Dp_v = sum_c max(g_c, 0) fv_c >= (x' - x_v) / s,
+        //                                H(y) = S(y) - S_lo <= min(log(y / (1 - MAX_P_)), cap), and 0 for y <= x_lo
+        //   * the linear part and the tangents add up to sum_c D_c gt_c, gt_c = g_c - (w_lo - 1) sum_{v low} fv_c: the coded
+        //     gradient (:168) minus the slope it books for edges that are clamped flat; gt_c <= g_c, |gt_c| <= 2|g_c| + sumF_c
+        //       g_c < 0:  D_c gt_c = min(s |g_c|, fu_c) |gt_c|      -> in total <= min(s Qn, R3),
+        //                 Qn = sum_{g<0} g_c^2 - (w_lo - 1) sum_{v low} En_v,  En_v = sum_{g_c<0} g_c fv_c,  R3 >= sum fu_c |gt_c|
+        //       g_c > 0:  D_c in [kappa s g_c, s g_c], kappa = min(1, (MAX_F_ - max fu) / (s max g))
+        //                 -> in total <= s (Qp - kappa Mp),  Qp = sum_{g>0} g_c^2,  Mp = (w_lo - 1) sum_{v low} Dp_v
+        // Hence  phi(nf_j) - phi(fu) <= min(s_j Qn, R3) + s_j (Qp - kappa_j Mp) + V + sum_{v low} H(x_v + s_j Dp_v),  V = sum viol_v.
+        // A pair (node, j) whose bound stays below alpha s_j |g|^2 by more than the rounding allowance — 1e-13 of the
+        // magnitudes that enter the candidate's sums (c0 + s c1: above the worst-case rounding error of either
+        // evaluation for the <= 32 edges and <= 160 components of a tile node) plus 1e-9 relative — cannot pass and is not
+        // evaluated; a node without a surviving pair keeps its row.  Everything else is evaluated exactly as before:
+        // the results are the same bits as those of the exhaustive search (BIGCLAM_F_LS_EXHAUSTIVE, tests/test_gpu_prune.py).
+        // Mapping: lane = edge for the per-edge terms, then the lanes of a node's group share its candidates.
+        const bool prune = prune_on;
+        float2 *we2 = reinterpret_cast<float2 *>(we);          // (the weights w_e are not needed any more)
+        if (prune) {
+            float lnthr = 3.0e38f, Lp = 0.0f;                  // H_e(s) = 0 up to ln s = lnthr, <= min(cap, ln s + Lp) beyond
+            if (Dp > 0.0) {
+                const float Df = __double2float_ru(Dp) * 1.000001f;
+                const float sthr = (sp->pr_xlo - xf) / Df * 0.99999f;           // x + s Dp stays below x_lo up to here
+                if (sthr > 0.0f) {
+                    const float t1 = __log2f(sthr), t2 = __log2f(sp->pr_kinv * (Df + xf / sthr));
+                    lnthr = t1 * 0.69314718f - fmaf(1.0e-6f, fabsf(t1), 1.0e-4f);
+                    Lp = t2 * 0.69314718f + fmaf(1.0e-6f, fabsf(t2), 1.0e-4f);
+                } else {
+                    lnthr = -3.0e38f;                                           // (always at the cap)
+                    Lp = 3.0e38f;
+                }
+            }
+            we2[lane] = make_float2(lnthr, Lp);
         }
-        __syncwarp();
-        int TE = 0;
+        unsigned svbits = 0u;
+        {
+            const bool want_g = gv && (n_want[gv ? g : 0] != 0);
+            const int jn = nsteps < 16 ? nsteps : 16;
+            if (prune) {
+                double sDp = 0.0, sEn = 0.0;
+                float sV = 0.0f;
 #pragma unroll 1
-        for (int t0 = 0; t0 < A; t0 += 32) {
-            const int t = t0 + lane;
-            const int c = (t < A) ? (int)lcnt[t] : 0;
-            int incl = c;
+                for (int r = 0; r < maxdeg; ++r) {
+                    const int src = (es_g + r) & 31;
+                    const double tD = __shfl_sync(0xffffffffu, Dp, src);
+                    const double tE = __shfl_sync(0xffffffffu, En, src);
+                    const float tV = __shfl_sync(0xffffffffu, violf, src);
+                    if (r < deg_g) { sDp += tD; sEn += tE; sV += tV; }
+                }
+                __syncwarp();                                                   // (we2 is complete)
+                if (want_g) {
+                    const double Mp = (ec.w_lo - 1.0) * sDp, Qn = G2n - (ec.w_lo - 1.0) * sEn;
+                    const float cap_f = sp->pr_cap;
+                    const float fuf = __double2float_ru(fabs(fusf)), fff = __double2float_ru(fufu);
+                    const float base = fmaf(2.0f * cap_f, (float)deg_g, __double2float_ru(fabs(llh_g))) + 2.0f * (fuf + fff) + r3;
+                    const float c0 = fmaf(1.0e-13f, base, sV) * 1.0001f;
+                    const float c1 = 1.0e-13f * fmaf(2.0f, r4, __double2float_ru(sDp)) * 1.0001f;
+                    const double R3 = (double)(r3 * 1.0001f);
+                    const float fmx = sqrtf(fff) * 1.000001f;                   // >= every fu_c
+                    const float kap0 = (gmx > 0.0f) ? __fdividef(fmaxf(__double2float_rd(max_f) - fmx, 0.0f), gmx) * 0.9999f : 3.0e38f;
+                    // this lane's candidates: sub, sub + gs, sub + 2 gs, sub + 3 gs (gs >= 4); the edge terms of all four in one walk
+                    float lns[4], Hs[4];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (t < A) { loff[t] = (unsigned short)(TE + incl - c); lcnt[t] = (unsigned int)(TE + incl - c); }
-            TE += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (TE > kTlEnt - 1) return false;
-        if (lane == 0) {
-            loff[A] = (unsigned short)TE;
-            ent_val[TE] = 0.0;                 // padding entry: component A, a scratch cell behind the 32 edges' cells
-            ent_e[TE] = 32;
-            ent_a[TE] = (unsigned char)A;
-        }
-        __syncwarp();
-BIGCLAM_UNROLL(BIGCLAM_TL_UF)
-        for (int t = lane; t < T; t += 32) {
-            const int row = erow[t];
-            const double *vv = reinterpret_cast<const double *>(stageN + 16 * (size_t)e_soff[row]);
-            const int i = t - (int)epos[row];
-            const unsigned an = amap[sp_idx(vv, (uint32_t)e_cnt[row])[i]];
-            if (an != 0xffffu) {
-                const unsigned q = atomicAdd(lcnt + an, 1u);
-                ent_val[q] = vv[i];
-                ent_e[q] = (unsigned char)row;
-                ent_a[q] = (unsigned char)an;
-            }
-        }
-        __syncwarp();
-        // ---------------- J. line search (:172-180), lane = (node 2q + h, trial j) ----------------
-        // One loop over the node's active components gives, per candidate: newfu.sfT and newfu.newfu (:176,:180) and,
-        // through the components' entry lists, newfu.fv of every edge (xs[edge][trial], component order ascending).
-        const int h = lane >> 4, j = lane & 15;
-        const double s = s_steps[j < nsteps ? j : 0];
-BIGCLAM_UNROLL(BIGCLAM_TL_UF)
-        for (int p = lane; p < ne * 16; p += 32) xs[p] = 0.0;             // (the staged rows are not needed any more)
-        if (lane < 16) xs[32 * 16 + lane] = 0.0;                          // scratch row of the padding entry
-        __syncwarp();
-        double oa[4], ob[4];
+                    for (int k = 0; k < 4; ++k) {
+                        const int jj = sub + k * gs;
+                        lns[k] = (jj < jn) ? s_lns[jj] : -3.0e38f;
+                        Hs[k] = 0.0f;
+                    }
+#pragma unroll 1
+                    for (int r = 0; r < deg_g; ++r) {
+                        const float2 tl = we2[es_g + r];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (2 * q >= nn) { oa[q] = 0.0; ob[q] = 0.0; continue; }          // (warp-uniform)
-            const int node = 2 * q + h;
-            const bool nv = node < nn;
-            const int t0 = nv ? (int)n_ab[node] : 0, mm = nv ? (int)n_m[node] : 0;
-            const int q0 = nv ? (int)loff[t0] : 0, nq = nv ? (int)loff[t0 + mm] - q0 : 0;
-            // the two half-warps (two nodes) walk in lockstep: common trip counts, predicated bodies
-            const int mmax = max(mm, __shfl_xor_sync(0xffffffffu, mm, 16));
-            const int qmax = max(nq, __shfl_xor_sync(0xffffffffu, nq, 16));
-            double a1 = 0.0, b1 = 0.0;
-BIGCLAM_UNROLL(BIGCLAM_TL_UJ)
-            for (int t = 0; t < mmax; ++t) {
-                const int ti = (t < mm) ? t0 + t : A;                   // (A: the padding component, adds +0.0)
-                const double2 v = fg[ti];
-                const double nf = need_hi ? clamp_step0(v.x, s, v.y, max_f) : clamp_step0_lo(v.x, s, v.y);
-                const double sf = asfm[ti] + nf;                        // sfT = (sumF - fu) + newfu   (:176)
-                a1 = fma(nf, sf, a1);
-                b1 = fma(nf, nf, b1);
+                        for (int k = 0; k < 4; ++k)
+                            if (lns[k] > tl.x) Hs[k] += fminf(cap_f, fmaxf(lns[k] + tl.y, 0.0f));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int jj = sub + k * gs;
+                        if (jj < jn) {
+                            const double sj = s_steps[jj];
+                            const float sfu = __double2float_ru(sj);
+                            const float kap = fminf(1.0f, __fdividef(kap0, sfu) * 0.9999f);
+                            const double negp = fmin(sj * Qn, R3);
+                            const double bound = negp + sj * (G2p - (double)kap * Mp) + (double)(fmaf(Hs[k], 1.00001f, c0) + sfu * c1);
+                            const double rhs = (a->alpha * sj) * G2node;
+                            if (!(bound < rhs * (1.0 - 1.0e-9))) svbits |= 1u << jj;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    if (o < gs) svbits |= __shfl_xor_sync(0xffffffffu, svbits, o);
+            } else if (want_g) {
+                svbits = (1u << jn) - 1u;
             }
-BIGCLAM_UNROLL(BIGCLAM_TL_UJ)
-            for (int k = 0; k < qmax; ++k) {
-                const int qq = (k < nq) ? q0 + k : TE;                  // (TE: the padding entry, scratch cell, value 0)
-                const double2 v = fg[ent_a[qq]];
-                const double nf = need_hi ? clamp_step0(v.x, s, v.y, max_f) : clamp_step0_lo(v.x, s, v.y);
-                double *cell = xs + (int)ent_e[qq] * 16 + j;
-                *cell = fma(nf, ent_val[qq], *cell);
-            }
-            oa[q] = a1;
-            ob[q] = b1;
+            if (gv && sub == 0) n_sv[g] = (unsigned short)svbits;
         }
         __syncwarp();
-        // pairs whose x is outside (x_lo, x_hi) are constants after the clamp (:166); the others are listed and exp/log
-        // runs on full warps of them
-        int np = 0;
+        // the nodes that are line-searched at all, in tile order
+        const unsigned svmask = __ballot_sync(0xffffffffu, lane < nn && n_sv[lane < nn ? lane : 0] != 0);
+        const int ns = __popc(svmask);
+        last_ns = ns;
+        last_nw = __popc(__ballot_sync(0xffffffffu, lane < nn && n_want[lane < nn ? lane : 0] != 0));
+        if (lane < nn) {
+            n_js[lane] = -1;
+            if ((svmask >> lane) & 1u) n_sl[__popc(svmask & lt_mask)] = (unsigned char)lane;
+        }
+        __syncwarp();
+        if (ns > 0) {
+            // ---------------- I. the neighbours' entries on active components, listed per component ----------------
+            // (only for the nodes that are line-searched: flat loops over runs of consecutive such nodes — their edges,
+            // entries and active components are contiguous)
+            unsigned rem = svmask;
+#pragma unroll 1
+            while (rem) {
+                const int na = __ffs(rem) - 1, len = __ffs(~(rem >> na)) - 1;
+                rem &= ~(((1u << len) - 1u) << na);
+                const int ahi = (int)n_ab[na + len - 1] + (int)n_m[na + len - 1];
+#pragma unroll 1
+                for (int t = (int)n_ab[na] + lane; t < ahi; t += 32) lcnt[t] = 0u;
+            }
+            __syncwarp();
+            rem = svmask;
+#pragma unroll 1
+            while (rem) {
+                const int na = __ffs(rem) - 1, len = __ffs(~(rem >> na)) - 1;
+                rem &= ~(((1u << len) - 1u) << na);
+                const int thi = epos[n_es[na + len]];
 BIGCLAM_UNROLL(BIGCLAM_TL_UF)
-        for (int p0 = 0; p0 < ne * 16; p0 += 32) {
-            const int p = p0 + lane;                       // ne * 16 is a multiple of 16: p < ne * 16 for whole half-warps
-            const bool valid = p < ne * 16;
-            const double D = valid ? xs[p] : 0.0;
-            const bool low = D <= ec.x_lo;
-            const bool inr = valid && !low && (D < ec.x_hi);
-            if (valid && !inr) xs[p] = (low ? ec.t_lo : ec.t_hi) + D;
-            const unsigned bal = __ballot_sync(0xffffffffu, inr);
-            if (inr) plist[np + __popc(bal & lt_mask)] = (unsigned short)p;
-            np += __popc(bal);
-        }
-        __syncwarp();
+                for (int t = (int)epos[n_es[na]] + lane; t < thi; t += 32) {
+                    const int row = erow[t];
+                    const double *vv = reinterpret_cast<const double *>(stageN + 16 * (size_t)e_soff[row]);
+                    const unsigned an = amap[sp_idx(vv, (uint32_t)e_cnt[row])[t - (int)epos[row]]];
+                    if (an != 0xffffu) atomicAdd(lcnt + an, 1u);
+                }
+            }
+            __syncwarp();
+            int TE = 0;
+            rem = svmask;
+#pragma unroll 1
+            while (rem) {
+                const int na = __ffs(rem) - 1, len = __ffs(~(rem >> na)) - 1;
+                rem &= ~(((1u << len) - 1u) << na);
+                const int ahi = (int)n_ab[na + len - 1] + (int)n_m[na + len - 1];
+#pragma unroll 1
+                for (int t0 = n_ab[na]; t0 < ahi; t0 += 32) {
+                    const int t = t0 + lane;
+                    const int c = (t < ahi) ? (int)lcnt[t] : 0;
+                    int incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    if (t < ahi) { loff[t] = (unsigned short)(TE + incl - c); lcnt[t] = (unsigned int)(TE + incl - c); }
+                    TE += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) loff[ahi] = (unsigned short)TE;          // end of the run's last list (a following run starts there or later)
+            }
+            if (TE > kTlEnt - 1) return false;
+            if (lane == 0) {
+                ent_val[TE] = 0.0;                 // padding entry: component A, a scratch cell behind the 32 edges' cells
+                ent_e[TE] = 32;
+                ent_a[TE] = (unsigned char)A;
+            }
+            __syncwarp();
+            rem = svmask;
+#pragma unroll 1
+            while (rem) {
+                const int na = __ffs(rem) - 1, len = __ffs(~(rem >> na)) - 1;
+                rem &= ~(((1u << len) - 1u) << na);
+                const int thi = epos[n_es[na + len]];
+BIGCLAM_UNROLL(BIGCLAM_TL_UF)
+                for (int t = (int)epos[n_es[na]] + lane; t < thi; t += 32) {
+                    const int row = erow[t];
+                    const double *vv = reinterpret_cast<const double *>(stageN + 16 * (size_t)e_soff[row]);
+                    const int i = t - (int)epos[row];
+                    const unsigned an = amap[sp_idx(vv, (uint32_t)e_cnt[row])[i]];
+                    if (an != 0xffffu) {
+                        const unsigned q = atomicAdd(lcnt + an, 1u);
+                        ent_val[q] = vv[i];
+                        ent_e[q] = (unsigned char)row;
+                        ent_a[q] = (unsigned char)an;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---------------- J. line search (:172-180), two line-searched nodes at a time: lane = (node, trial j) ----------------
+            // One loop over the node's active components gives, per candidate: newfu.sfT and newfu.newfu (:176,:180) and,
+            // through the components' entry lists, newfu.fv of every edge (xs[edge][trial], component order ascending).
+            const int h = lane >> 4, j = lane & 15;
+            const double s = s_steps[j < nsteps ? j : 0];
+            if (lane < 16) xs[32 * 16 + lane] = 0.0;                          // scratch row of the padding entry (the staged rows are not needed any more)
+            __syncwarp();
+#pragma unroll 1
+            for (int k0 = 0; k0 < ns; k0 += 2) {
+                const bool nv = k0 + h < ns;
+                const int node = nv ? (int)n_sl[k0 + h] : 0;
+                const bool mine = nv && (((unsigned)n_sv[node] >> j) & 1u);     // (a pair that cannot pass is not evaluated)
+                const int e0 = nv ? (int)n_es[node] : 0, dn = nv ? (int)n_es[node + 1] - e0 : 0;
+                const int t0 = nv ? (int)n_ab[node] : 0, mm = nv ? (int)n_m[node] : 0;
+                const int q0 = nv ? (int)loff[t0] : 0, nq = nv ? (int)loff[t0 + mm] - q0 : 0;
+#pragma unroll 1
+                for (int r = 0; r < dn; ++r) xs[(e0 + r) * 16 + j] = 0.0;       // (each cell belongs to one lane)
+                // the two half-warps (two nodes) walk in lockstep: common trip counts, padded with a component / an entry that add nothing
+                const int mmax = max(mm, __shfl_xor_sync(0xffffffffu, mm, 16));
+                const int qmax = max(nq, __shfl_xor_sync(0xffffffffu, nq, 16));
+                const int dmax = max(dn, __shfl_xor_sync(0xffffffffu, dn, 16));
+                double a1 = 0.0, b1 = 0.0;
+BIGCLAM_UNROLL(BIGCLAM_TL_UJ)
+                for (int t = 0; t < mmax; ++t) {
+                    const int ti = (t < mm) ? t0 + t : A;                   // (A: the padding component, adds +0.0)
+                    const double2 v = fg[ti];
+                    const double nf = need_hi ? clamp_step0(v.x, s, v.y, max_f) : clamp_step0_lo(v.x, s, v.y);
+                    const double sf = asfm[ti] + nf;                        // sfT = (sumF - fu) + newfu   (:176)
+                    a1 = fma(nf, sf, a1);
+                    b1 = fma(nf, nf, b1);
+                }
+BIGCLAM_UNROLL(BIGCLAM_TL_UJ)
+                for (int k = 0; k < qmax; ++k) {
+                    const int qq = (k < nq) ? q0 + k : TE;                  // (TE: the padding entry, scratch cell, value 0)
+                    const double2 v = fg[ent_a[qq]];
+                    const double nf = need_hi ? clamp_step0(v.x, s, v.y, max_f) : clamp_step0_lo(v.x, s, v.y);
+                    double *cell = xs + (int)ent_e[qq] * 16 + j;
+                    *cell = fma(nf, ent_val[qq], *cell);
+                }
+                // pairs whose x is outside (x_lo, x_hi) are constants after the clamp (:166); the others are listed and exp/log
+                // runs on full warps of them
+                int np = 0;
+#pragma unroll 1
+                for (int r = 0; r < dmax; ++r) {
+                    const int p = (e0 + r) * 16 + j;
+                    const bool valid = mine && r < dn;
+                    const double D = valid ? xs[p] : 0.0;
+                    const bool low = D <= ec.x_lo;
+                    const bool inr = valid && !low && (D < ec.x_hi);
+                    if (valid && !inr) xs[p] = (low ? ec.t_lo : ec.t_hi) + D;
+                    const unsigned bal = __ballot_sync(0xffffffffu, inr);
+                    if (inr) plist[np + __popc(bal & lt_mask)] = (unsigned short)p;
+                    np += __popc(bal);
+                }
+                __syncwarp();
 #if BIGCLAM_TL_ILP2
 #pragma unroll 1
-        for (int b = 0; b < np; b += 64) {
-            const int k1 = b + lane, k2 = b + 32 + lane;
-            const bool ok1 = k1 < np, ok2 = k2 < np;
-            const int pid1 = ok1 ? (int)plist[k1] : 0, pid2 = ok2 ? (int)plist[k2] : 0;
-            const double x1 = ok1 ? xs[pid1] : 1.0, x2 = ok2 ? xs[pid2] : 1.0;
-            const double o1 = 1.0 - exp_neg(x1), o2 = 1.0 - exp_neg(x2);
-            const double t1 = log_pos(o1) + x1, t2 = log_pos(o2) + x2;
-            if (ok1) xs[pid1] = t1;
-            if (ok2) xs[pid2] = t2;
-        }
+                for (int b = 0; b < np; b += 64) {
+                    const int k1 = b + lane, k2 = b + 32 + lane;
+                    const bool ok1 = k1 < np, ok2 = k2 < np;
+                    const int pid1 = ok1 ? (int)plist[k1] : 0, pid2 = ok2 ? (int)plist[k2] : 0;
+                    const double x1 = ok1 ? xs[pid1] : 1.0, x2 = ok2 ? xs[pid2] : 1.0;
+                    const double o1 = 1.0 - exp_neg(x1), o2 = 1.0 - exp_neg(x2);
+                    const double t1 = log_pos(o1) + x1, t2 = log_pos(o2) + x2;
+                    if (ok1) xs[pid1] = t1;
+                    if (ok2) xs[pid2] = t2;
+                }
 #else
 #pragma unroll 1
-        for (int b = 0; b < np; b += 32) {
-            const int k = b + lane;
-            const bool ok = k < np;
-            const int pid = ok ? (int)plist[k] : 0;
-            const double xv = ok ? xs[pid] : 1.0;
-            const double omp = 1.0 - exp_neg(xv);
-            const double t = log_pos(omp) + xv;
-            if (ok) xs[pid] = t;
-        }
+                for (int b = 0; b < np; b += 32) {
+                    const int k = b + lane;
+                    const bool ok = k < np;
+                    const int pid = ok ? (int)plist[k] : 0;
+                    const double xv = ok ? xs[pid] : 1.0;
+                    const double omp = 1.0 - exp_neg(xv);
+                    const double t = log_pos(omp) + xv;
+                    if (ok) xs[pid] = t;
+                }
 #endif
-        __syncwarp();
-        // ---------------- K. Armijo test (:181), largest passing step (:182) ----------------
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int node = 2 * q + h;
-            const bool nv = node < nn;
-            bool pass = false;
-            if (nv) {
-                double acc = 0.0;
-                const int e1 = n_es[node + 1];
+                __syncwarp();
+                // ---------------- K. Armijo test (:181), largest passing step (:182) ----------------
+                bool pass = false;
+                if (mine) {
+                    double acc = 0.0;
 #pragma unroll 1
-                for (int e = n_es[node]; e < e1; ++e) acc += xs[e * 16 + j];          // the node's edges, in CSR order
-                const double result = (acc - oa[q]) + ob[q];
-                const double rhs = n_llh[node] + (a->alpha * s) * n_G2[node];
-                pass = (j < nsteps) && (n_want[node] != 0) && (result >= rhs);
+                    for (int r = 0; r < dn; ++r) acc += xs[(e0 + r) * 16 + j];          // the node's edges, in CSR order
+                    const double result = (acc - a1) + b1;
+                    const double rhs = n_llh[node] + (a->alpha * s) * n_G2[node];
+                    pass = result >= rhs;
+                }
+                const unsigned won = (__ballot_sync(0xffffffffu, pass) >> (16 * h)) & 0xffffu;
+                if (nv && j == 0) n_js[node] = (signed char)(won ? __ffs(won) - 1 : -1);
+                __syncwarp();
             }
-            const unsigned mine = (__ballot_sync(0xffffffffu, pass) >> (16 * h)) & 0xffffu;
-            if (nv && j == 0) n_js[node] = (signed char)(mine ? __ffs(mine) - 1 : -1);
         }
         __syncwarp();
         // ---------------- L. new rows (:183-190) and delta blocks (:191-192) ----------------
@@ -797,12 +1001,18 @@ __global__ void __launch_bounds__(kTlThreads, kTlBlocksPerSM) tile_step_kernel(c
     double *s_steps = reinterpret_cast<double *>(smem_raw);
     double *s_sumF = s_steps + kMaxSteps;
     unsigned long long *s_mbar = reinterpret_cast<unsigned long long *>(s_sumF + ldp);
-    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_mbar + kTlWarps) + (size_t)wib * tl_region_bytes(ld);
+    float *s_lns = reinterpret_cast<float *>(s_mbar + kTlWarps);          // 16 floats
+    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_mbar + kTlWarps + 8) + (size_t)wib * tl_region_bytes(ld);
 
 #pragma unroll 1
     for (int i = threadIdx.x; i < ldp; i += nthreads) s_sumF[i] = (i < ld) ? a.sumF[i] : 0.0;
 #pragma unroll 1
     for (int i = threadIdx.x; i < kMaxSteps; i += nthreads) s_steps[i] = a.steps[i];
+    if (threadIdx.x < 16) {
+        const float sfu = __double2float_ru(a.steps[threadIdx.x]);
+        const float t = (sfu > 0.0f) ? __log2f(sfu) : -3.0e38f;
+        s_lns[threadIdx.x] = (sfu > 0.0f) ? t * 0.69314718f + fmaf(1.0e-6f, fabsf(t), 1.0e-4f) : -3.0e38f;
+    }
     __syncthreads();
     // S2_all = sum_c sumF_c^2 in a fixed order (every warp computes the same bits)
     double S2 = 0.0;
@@ -821,6 +1031,7 @@ __global__ void __launch_bounds__(kTlThreads, kTlBlocksPerSM) tile_step_kernel(c
     T.sp = &sp;
     T.s_steps = s_steps;
     T.s_sumF = s_sumF;
+    T.s_lns = s_lns;
     T.S2_all = S2;
     T.ec = G.ec;
     T.carve(wbase, ld, lane);
@@ -855,7 +1066,10 @@ __global__ void __launch_bounds__(kTlThreads, kTlBlocksPerSM) tile_step_kernel(c
             const TileMeta tm = sp.tiles[item - (unsigned int)sp.n_gen];
             dense_clean = false;
             const bool done = T.template run<kPush>(tm);
-            if (sp.stats != nullptr && lane == 0) atomicAdd(sp.stats + (done ? 0 : 1), 1u);
+            if (sp.stats != nullptr && lane == 0) {
+                atomicAdd(sp.stats + (done ? 0 : 1), 1u);
+                if (done && a.do_linesearch) { atomicAdd(sp.stats + 2, (unsigned)T.last_ns); atomicAdd(sp.stats + 3, (unsigned)T.last_nw); }
+            }
             gen_cnt = done ? 0 : tm.nn;
             gen_pos = tm.pos0;
             gen_col = sp.tcol + tm.ecol0;           // the tile's entries of tcol are its nodes' neighbour lists (tagged ids)

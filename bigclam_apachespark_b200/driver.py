@@ -80,7 +80,7 @@ class BigClam:
     def __init__(self, numCore: int = 36, minCom: int = 1000, maxCom: int = 9000, divCom: int = 100,
                  alpha: float = 0.05, beta: float = 0.1, MaxInter: int = 15, device: int = -1,
                  time_kernels: bool = False, record_accepted: bool = False, verbose: bool = False,
-                 sparse_rows: bool = False, numGPUs: int = 1, devices=None):
+                 sparse_rows: bool = False, numGPUs: int = 1, devices=None, exhaustive_linesearch: bool = False):
         self.numCore, self.minCom, self.maxCom, self.divCom = numCore, minCom, maxCom, divCom
         self.alpha, self.beta, self.MaxInter = alpha, beta, MaxInter
         self.MIN_P_, self.MAX_P_, self.MIN_F_, self.MAX_F_ = 0.0001, 0.9999, 0.0, 1000.0   # :40-43
@@ -88,6 +88,8 @@ class BigClam:
         self.flags = (_lib.F_TIME_KERNELS if time_kernels else 0) | (_lib.F_RECORD_ACCEPTED if record_accepted else 0)
         if sparse_rows:       # F as sparse rows on the device (the reference's BSV[Double]); K <= 256, one GPU
             self.flags |= _lib.F_SPARSE_ROWS
+        if exhaustive_linesearch:     # evaluate every candidate of every node (no bounds), like the reference's cartesian (:172-181)
+            self.flags |= _lib.F_LS_EXHAUSTIVE
         self.verbose = verbose
         self.K = None
         self.rowptr = self.col = self.ids = None
@@ -383,6 +385,13 @@ class BigClam:
         v = [C.c_int64() for _ in range(5)]
         check(_lib.load().bigclam_get_tile_stats(self._need(), *[C.byref(x) for x in v]), self._ctx)
         return dict(zip(("tiles_done", "tiles_fallback", "n_tiles", "n_general_nodes", "n_split_hubs"), (x.value for x in v)))
+
+    def ls_stats(self):
+        """Sparse rows: dict(nodes_asked, nodes_searched) of the tile path since the previous read — how many of the
+        nodes that asked for a line search had a candidate the bounds could not exclude."""
+        a, b = C.c_int64(), C.c_int64()
+        check(_lib.load().bigclam_get_ls_stats(self._need(), C.byref(a), C.byref(b)), self._ctx)
+        return {"nodes_asked": a.value, "nodes_searched": b.value}
 
     def set_stream(self, cuda_stream: int):
         check(_lib.load().bigclam_set_stream(self._need(), C.c_void_p(cuda_stream)), self._ctx)

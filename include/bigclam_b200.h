@@ -59,6 +59,11 @@ typedef struct {
                                         points still work (bigclam_set_F / bigclam_get_F convert on the device);
                                         bigclam_set_F_csr / bigclam_get_F_csr never build a dense image. */
 
+#define BIGCLAM_F_LS_EXHAUSTIVE   8  /* sparse rows: evaluate all max_inter+1 candidates of every node like the reference
+                                        does (bigclam4-7.scala:172-181).  Default: a candidate that a bound on the node's
+                                        objective proves unable to pass the Armijo test (:181) is not evaluated — same
+                                        accepted steps, same rows, same LLH bits (tests/test_gpu_prune.py). */
+
 /* Fills *p with the reference's constants for a given K. */
 int bigclam_default_params(bigclam_params *p, int32_t k);
 
@@ -128,6 +133,10 @@ int bigclam_get_kernel_time(bigclam_ctx *ctx, double *step_kernel_ms_sum, int64_
  * (tiles, nodes on the general path, split hubs).  The two counters count from the previous read. */
 int bigclam_get_tile_stats(bigclam_ctx *ctx, int64_t *tiles_done, int64_t *tiles_fallback, int64_t *n_tiles,
                            int64_t *n_general_nodes, int64_t *n_split_hubs);
+
+/* Sparse rows, line search by bounds: of the tile-path nodes that asked for a line search since the previous read, how many
+ * had at least one candidate that the bounds could not exclude (and were therefore evaluated). */
+int bigclam_get_ls_stats(bigclam_ctx *ctx, int64_t *nodes_asked, int64_t *nodes_searched);
 
 /* Sparse rows: re-cut the tiles of small nodes for the current average row size (rows grow or shrink while the solver
  * runs; bigclam_run does this by itself between its batches, bigclam_set_F* always).  Synchronises the stream. */

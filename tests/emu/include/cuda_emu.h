@@ -42,6 +42,20 @@ extern thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 struct alignas(16) double2 { double x, y; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
+struct alignas(8) float2 { float x, y; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline float __double2float_ru(double d) {
+    float f = (float)d;
+    if ((double)f < d) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+inline float __log2f(float v) { return std::log2(v); }
+inline float __fdividef(float a, float b) { return a / b; }
+inline float __double2float_rd(double d) {
+    float f = (float)d;
+    if ((double)f > d) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
 
 namespace emu {
 struct WarpCtx {
