@@ -444,11 +444,16 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         const bool prune_on = sp->ls_prune != 0;
         const bool e_low = x <= ec.x_lo;
         const float xf = (lane < ne) ? __double2float_ru(x) : 0.0f;
-        float violf = 0.0f;
+        float violf = 0.0f;              // above x_hi: a constant of the node's bound
+        float vnear = 0.0f;              // in range, next to x_lo: only for candidates that can bring x' below x_lo (see H2)
         if (prune_on && !e_low && lane < ne) {
             const double m = wgt - 1.0;
-            const double v = (x < ec.x_hi) ? fma(m, x, ec.t_lo - (term - x)) : m * (x - ec.x_hi);
-            violf = (v > 0.0) ? __double2float_ru(v) * 1.000001f : 0.0f;
+            if (x < ec.x_hi) {
+                const double v = fma(m, x, ec.t_lo - (term - x));
+                vnear = (v > 0.0) ? __double2float_ru(v) * 1.000001f : 0.0f;
+            } else {
+                violf = __double2float_ru(m * (x - ec.x_hi)) * 1.000001f;
+            }
         }
         const int es_g = gv ? (int)n_es[g] : 0;
         const int deg_g = gv ? (int)n_es[g + 1] - es_g : 0;
@@ -491,7 +496,7 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         bool hi_lane = false;
         double G2n = 0.0, G2p = 0.0;     // [bounds] |g|^2 over the active components with g < 0 / g > 0
         float r3 = 0.0f, r4 = 0.0f;      // [bounds] R3 >= sum fu_c |gt_c|; magnitudes behind the rounding allowance
-        float gmx = 0.0f;                // [bounds] largest positive gradient component
+        float gmx = 0.0f, g1p = 0.0f;    // [bounds] largest positive gradient component, sum of the positive ones
         double G2node = 0.0;             // |g|^2 of the node (all K components)
         {
             double G2 = 0.0, SF2 = 0.0;
@@ -518,6 +523,7 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
                         if (gr > 0.0) {
                             G2p = fma(gr, gr, G2p);
                             gmx = fmaxf(gmx, ga);
+                            g1p += ga;
                         } else {
                             G2n = fma(gr, gr, G2n);
                         }
@@ -531,6 +537,7 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
                 G2n = group_sum(G2n, gs);
                 G2p = group_sum(G2p, gs);
                 r3 = group_sum(r3, gs);
+                g1p = group_sum(g1p, gs);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
                     if (o < gs) gmx = fmaxf(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
@@ -557,7 +564,7 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         // [bounds, see H2] of the edges that are clamped flat: Dp_e = sum_c max(g_c, 0) fv_c and En_e = sum_{c active} min(g_c, 0) fv_c
         // (a component with g_c < 0 is active iff fu_c > 0)
         double Dp = 0.0, En = 0.0;
-        if (prune_on && e_low && lane < ne) {
+        if (prune_on && (e_low || vnear > 0.0f) && lane < ne) {
 #pragma unroll 1
             for (int i = 0; i < ce; ++i) {
                 const double2 v = fg[ri[i]];
@@ -604,12 +611,15 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         //     gradient (:168) minus the slope it books for edges that are clamped flat; gt_c <= g_c, |gt_c| <= 2|g_c| + sumF_c
         //       g_c < 0:  D_c gt_c = min(s |g_c|, fu_c) |gt_c|      -> in total <= min(s Qn, R3),
         //                 Qn = sum_{g<0} g_c^2 - (w_lo - 1) sum_{v low} En_v,  En_v = sum_{g_c<0} g_c fv_c,  R3 >= sum fu_c |gt_c|
-        //       g_c > 0:  D_c in [kappa s g_c, s g_c], kappa = min(1, (MAX_F_ - max fu) / (s max g))
-        //                 -> in total <= s (Qp - kappa Mp),  Qp = sum_{g>0} g_c^2,  Mp = (w_lo - 1) sum_{v low} Dp_v
-        // Hence  phi(nf_j) - phi(fu) <= min(s_j Qn, R3) + s_j (Qp - kappa_j Mp) + V + sum_{v low} H(x_v + s_j Dp_v),  V = sum viol_v.
-        // A pair (node, j) whose bound stays below alpha s_j |g|^2 by more than the rounding allowance — 1e-13 of the
-        // magnitudes that enter the candidate's sums (c0 + s c1: above the worst-case rounding error of either
-        // evaluation for the <= 32 edges and <= 160 components of a tile node) plus 1e-9 relative — cannot pass and is not
+        //       g_c > 0:  D_c in [kappa s g_c, min(s g_c, MAX_F_)], kappa = min(1, (MAX_F_ - max fu) / (s max g))
+        //                 -> in total <= min(s Qp, MAX_F_ G1) - kappa s Mp,  Qp = sum_{g>0} g_c^2,  G1 = sum_{g>0} g_c,
+        //                    Mp = (w_lo - 1) sum_{v low} Dp_v
+        // Hence  phi(nf_j) - phi(fu) <= min(s_j Qn, R3) + min(s_j Qp, MAX_F_ G1) - kappa_j s_j Mp + V_j + sum_{v low} H(x_v + s_j Dp_v),
+        // V_j = the viol_v of the edges above x_hi and of those edges next to x_lo that candidate j can bring below it
+        // (x_v + s_j En_v < x_lo).
+        // A pair (node, j) whose bound stays below alpha s_j |g|^2 by more than the rounding allowance — twice the worst-case
+        // rounding error of a sum of 4 deg + 3 m + 16 operations on the magnitudes that enter the candidate's sums
+        // (c0 + s c1) plus 1e-9 relative — cannot pass and is not
         // evaluated; a node without a surviving pair keeps its row.  Everything else is evaluated exactly as before:
         // the results are the same bits as those of the exhaustive search (BIGCLAM_F_LS_EXHAUSTIVE, tests/test_gpu_prune.py).
         // Mapping: lane = edge for the per-edge terms, then the lanes of a node's group share its candidates.
@@ -617,7 +627,20 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         float2 *we2 = reinterpret_cast<float2 *>(we);          // (the weights w_e are not needed any more)
         if (prune) {
             float lnthr = 3.0e38f, Lp = 0.0f;                  // H_e(s) = 0 up to ln s = lnthr, <= min(cap, ln s + Lp) beyond
-            if (Dp > 0.0) {
+            if (vnear > 0.0f) {
+                // an edge in range next to x_lo: its tangent only fails for x' < x_lo, and x' >= x + s En: from ln s = lnthr on
+                // the candidate is charged viol (kept as Lp = -1000 - viol)
+                if (En < 0.0) {
+                    const float sthr = __double2float_rd((x - ec.x_lo) / (-En)) * 0.99999f;
+                    if (sthr > 0.0f) {
+                        const float t1 = __log2f(sthr);
+                        lnthr = t1 * 0.69314718f - fmaf(1.0e-6f, fabsf(t1), 1.0e-4f);
+                    } else {
+                        lnthr = -3.0e38f;
+                    }
+                    Lp = -1000.0f - vnear;
+                }
+            } else if (Dp > 0.0) {
                 const float Df = __double2float_ru(Dp) * 1.000001f;
                 const float sthr = (sp->pr_xlo - xf) / Df * 0.99999f;           // x + s Dp stays below x_lo up to here
                 if (sthr > 0.0f) {
@@ -630,6 +653,7 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
                 }
             }
             we2[lane] = make_float2(lnthr, Lp);
+            if (!e_low) { Dp = 0.0; En = 0.0; }                // (the node's sums below are over the flat edges only)
         }
         unsigned svbits = 0u;
         {
@@ -652,8 +676,19 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
                     const float cap_f = sp->pr_cap;
                     const float fuf = __double2float_ru(fabs(fusf)), fff = __double2float_ru(fufu);
                     const float base = fmaf(2.0f * cap_f, (float)deg_g, __double2float_ru(fabs(llh_g))) + 2.0f * (fuf + fff) + r3;
-                    const float c0 = fmaf(1.0e-13f, base, sV) * 1.0001f;
-                    const float c1 = 1.0e-13f * fmaf(2.0f, r4, __double2float_ru(sDp)) * 1.0001f;
+                    // rounding allowance: twice the worst case of a sum of (4 deg + 3 m + 16) rounded operations on these magnitudes
+#ifdef BIGCLAM_PR_OLDNOPS
+                    const float nops = 1.0e-13f;
+#else
+                    const float nops = 2.3e-16f * (float)(4 * deg_g + 3 * m_g + 16);
+#endif
+                    const float c0 = fmaf(nops, base, sV) * 1.0001f;
+                    const float c1 = nops * fmaf(2.0f, r4, __double2float_ru(sDp)) * 1.0001f;
+#ifdef BIGCLAM_PR_NOG1
+                    const double G1 = 1.0e300;
+#else
+                    const double G1 = (double)(__double2float_ru(max_f) * g1p * 1.0001f);   // >= sum_{g>0} min(s g_c, MAX_F_) g_c
+#endif
                     const double R3 = (double)(r3 * 1.0001f);
                     const float fmx = sqrtf(fff) * 1.000001f;                   // >= every fu_c
                     const float kap0 = (gmx > 0.0f) ? __fdividef(fmaxf(__double2float_rd(max_f) - fmx, 0.0f), gmx) * 0.9999f : 3.0e38f;
@@ -668,9 +703,11 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
 #pragma unroll 1
                     for (int r = 0; r < deg_g; ++r) {
                         const float2 tl = we2[es_g + r];
+                        const bool isv = tl.y < -500.0f;
+                        const float vv = -1000.0f - tl.y;
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (lns[k] > tl.x) Hs[k] += fminf(cap_f, fmaxf(lns[k] + tl.y, 0.0f));
+                            if (lns[k] > tl.x) Hs[k] += isv ? vv : fminf(cap_f, fmaxf(lns[k] + tl.y, 0.0f));
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -680,7 +717,7 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
                             const float sfu = __double2float_ru(sj);
                             const float kap = fminf(1.0f, __fdividef(kap0, sfu) * 0.9999f);
                             const double negp = fmin(sj * Qn, R3);
-                            const double bound = negp + sj * (G2p - (double)kap * Mp) + (double)(fmaf(Hs[k], 1.00001f, c0) + sfu * c1);
+                            const double bound = negp + fmin(sj * G2p, G1) - sj * ((double)kap * Mp) + (double)(fmaf(Hs[k], 1.00001f, c0) + sfu * c1);
                             const double rhs = (a->alpha * sj) * G2node;
                             if (!(bound < rhs * (1.0 - 1.0e-9))) svbits |= 1u << jj;
                         }
