@@ -91,7 +91,8 @@ struct SparseArgs {
     const TileMeta *tiles;
     const int32_t *tcol;               // per tile edge: neighbour id | (node index within the tile << 28)
     unsigned int *stats;               // optional [tiles done on the tile path, tiles that fell back, nodes line-searched, nodes that asked for it]
-    // line search by bounds (bigclam_tile.cuh, H2): 0 = every candidate of every node is evaluated (BIGCLAM_F_LS_EXHAUSTIVE)
+    // line search by bounds (bigclam_tile.cuh, H2): 0 = every candidate of every node is evaluated (BIGCLAM_F_LS_EXHAUSTIVE),
+    // 1 = bounds on the tile path only, 2 = on the general path too
     int32_t ls_prune;
     float pr_xlo, pr_kinv, pr_cap;     // x_lo rounded down, 1 / (1 - MAX_P_) and S_hi - S_lo rounded up
 };
@@ -121,6 +122,51 @@ constexpr int kSpHubMaxSlices = 192;      // very large hubs get longer segments
 __host__ __device__ inline size_t sp_hub_stride(int ld) { return (size_t)ld + 32; }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Line search by bounds (derivation: bigclam_tile.cuh, phase H2): the per-node terms of the bound
+//   phi(nf_j) - phi(fu) <= min(s Qn, R3) + min(s Qp, G1) - kappa s Mp + c0 + s c1 + Hs_j
+// and the test that excludes candidate j.  Shared by the tile path and the general path.
+struct LsBound {
+    double Qn, Qp, Mp, G1, R3;
+    float c0, c1, kap0;
+    __device__ __forceinline__ bool cannot_pass(double sj, float Hs, double alpha, double G2node) const {
+        const float sfu = __double2float_ru(sj);
+        const float kap = fminf(1.0f, __fdividef(kap0, sfu) * 0.9999f);
+        const double bound = fmin(sj * Qn, R3) + fmin(sj * Qp, G1) - sj * ((double)kap * Mp) + (double)(fmaf(Hs, 1.00001f, c0) + sfu * c1);
+        return bound < (alpha * sj) * G2node * (1.0 - 1.0e-9);
+    }
+};
+// One edge's share Hs of candidate ln(s) = lns given the edge's code (lnthr, Lp): 0 up to lnthr; beyond it
+// min(cap, lns + Lp) for an edge that is clamped flat, or the constant -1000 - Lp (an edge next to x_lo, Lp < -500).
+__device__ __forceinline__ float ls_edge_share(float lns, float lnthr, float Lp, float cap) {
+    if (!(lns > lnthr)) return 0.0f;
+    return (Lp < -500.0f) ? (-1000.0f - Lp) : fminf(cap, fmaxf(lns + Lp, 0.0f));
+}
+// The code of an edge that is clamped flat (x <= x_lo): Dp = sum_c max(g_c, 0) fv_c > 0.
+__device__ __forceinline__ void ls_code_flat(float xf, double Dp, float xlo_f, float kinv_f, float &lnthr, float &Lp) {
+    const float Df = __double2float_ru(Dp) * 1.000001f;
+    const float sthr = (xlo_f - xf) / Df * 0.99999f;                    // x + s Dp stays below x_lo up to here
+    if (sthr > 0.0f) {
+        const float t1 = __log2f(sthr), t2 = __log2f(kinv_f * (Df + xf / sthr));
+        lnthr = t1 * 0.69314718f - fmaf(1.0e-6f, fabsf(t1), 1.0e-4f);
+        Lp = t2 * 0.69314718f + fmaf(1.0e-6f, fabsf(t2), 1.0e-4f);
+    } else {
+        lnthr = -3.0e38f;                                               // (always at the cap)
+        Lp = 3.0e38f;
+    }
+}
+// The code of an edge in range next to x_lo with violation `vnear`: charged from x + s En < x_lo on (En < 0).
+__device__ __forceinline__ void ls_code_near(double x, double x_lo, double En, float vnear, float &lnthr, float &Lp) {
+    const float sthr = __double2float_rd((x - x_lo) / (-En)) * 0.99999f;
+    if (sthr > 0.0f) {
+        const float t1 = __log2f(sthr);
+        lnthr = t1 * 0.69314718f - fmaf(1.0e-6f, fabsf(t1), 1.0e-4f);
+    } else {
+        lnthr = -3.0e38f;
+    }
+    Lp = -1000.0f - vnear;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // The general path: everything one warp needs to process one node (or one hub item).
 struct SpGen {
     // launch-wide
@@ -128,6 +174,7 @@ struct SpGen {
     const SparseArgs *sp;
     const double *s_steps;
     const double *s_sumF;
+    const float *s_lns;              // upper bounds of ln(step size), 16 values (line search by bounds)
     EdgeConst ec;
     // per warp
     double *fu_d, *g_d, *ent_val;
@@ -343,7 +390,7 @@ struct SpGen {
         return sumterms;
     }
     // Armijo decision for the 16 candidates tg .. tg+15 given each lane's edge-term sum (already summed over h).
-    __device__ __forceinline__ int decide(int tg, double s, bool jok, double sumterms, int m, bool need_hi, double llh_u, double G2) {
+    __device__ __forceinline__ int decide(int tg, double s, bool jok, double sumterms, int m, bool need_hi, double llh_u, double G2, unsigned surv = 0xffffu) {
         const int h = lane >> 4;
         const double max_f = a->max_f;
         // - newfu.sfT + newfu.newfu with sfT = (sumF - fu) + newfu   (:176,:180)
@@ -361,7 +408,7 @@ struct SpGen {
         ob += __shfl_xor_sync(0xffffffffu, ob, 16);
         const double result = (sumterms - oa) + ob;
         const double rhs = llh_u + (a->alpha * s) * G2;
-        const unsigned pass = __ballot_sync(0xffffffffu, jok && (result >= rhs)) & 0xffffu;
+        const unsigned pass = __ballot_sync(0xffffffffu, jok && (result >= rhs)) & 0xffffu & surv;
         return pass ? tg + __ffs(pass) - 1 : -1;          // lowest j == largest step (:182 max)
     }
     // SWAP (:183-190): the accepted candidate's non-zeros (or the old row) go to the output pool(s), followed by
@@ -471,6 +518,104 @@ struct SpGen {
         __syncwarp();
     }
 
+    // Line search by bounds for a node on the general path (gradient in g_d, m active components in aidx): the mask of
+    // the candidates 0 .. 15 that the bound cannot exclude.  `staged`: rows of the node's only chunk that are still
+    // staged from PRE (0: the chunks are staged again).  Next to x_lo the violation is taken at its cap (w_lo - 1) x.
+    __device__ __forceinline__ unsigned bound_mask(const int32_t *colp, int deg, int m, double G2node, double llh_u, double fusf, double fufu, int staged) {
+        const int nsteps = a->nsteps;
+        const int j = lane & 15, h = lane >> 4;
+        // active components: |g|^2 split by sign, R3, G1, max g, sum sumF^2
+        float g2n = 0.0f, g2p = 0.0f, r3 = 0.0f, g1p = 0.0f, gmx = 0.0f, sf2 = 0.0f;
+#pragma unroll 1
+        for (int t = lane; t < m; t += 32) {
+            const int c = aidx[t];
+            const double f = fu_d[c], g = g_d[c];
+            const float ga = __double2float_ru(fabs(g)), ff = __double2float_ru(f), sff = __double2float_ru(fabs(s_sumF[c]));
+            r3 = fmaf(ff, fmaf(2.0f, ga, sff) + 3.0f * ff, r3);
+            sf2 = fmaf(sff, sff, sf2);
+            if (g > 0.0) {
+                g2p = fmaf(ga, ga, g2p);
+                g1p += ga;
+                gmx = fmaxf(gmx, ga);
+            } else {
+                g2n = fmaf(ga, ga, g2n);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            g2n += __shfl_xor_sync(0xffffffffu, g2n, o);
+            g2p += __shfl_xor_sync(0xffffffffu, g2p, o);
+            r3 += __shfl_xor_sync(0xffffffffu, r3, o);
+            g1p += __shfl_xor_sync(0xffffffffu, g1p, o);
+            sf2 += __shfl_xor_sync(0xffffffffu, sf2, o);
+            gmx = fmaxf(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
+        }
+        // edges, chunk by chunk: x, Dp, En per edge (lane = edge), then every candidate lane (j, h) collects its share
+        const float lns = (j < nsteps) ? s_lns[j] : -3.0e38f;
+        const float cap_f = sp->pr_cap;
+        double sDp = 0.0, sEn = 0.0;
+        float sV = 0.0f, Hs = 0.0f;
+#pragma unroll 1
+        for (int cb = 0; cb < deg;) {
+            const int ne = (staged > 0) ? staged : stage_chunk(colp + cb, min(32, deg - cb));
+            double x = 0.0, Dp = 0.0, En = 0.0;
+            if (lane < ne) {
+                const int end = poff[lane + 1];
+#pragma unroll 1
+                for (int i = poff[lane]; i < end; ++i) {
+                    const int c = ent_idx[i];
+                    const double v = ent_val[i], f = fu_d[c], g = g_d[c];
+                    x = fma(v, f, x);
+                    Dp = fma(v, g > 0.0 ? g : 0.0, Dp);
+                    En = fma(v, (g < 0.0 && f > 0.0) ? g : 0.0, En);
+                }
+            }
+            float lnthr = 3.0e38f, Lp = 0.0f, violf = 0.0f;
+            if (lane < ne) {
+                if (x <= ec.x_lo) {
+                    if (Dp > 0.0) ls_code_flat(__double2float_ru(x), Dp, sp->pr_xlo, sp->pr_kinv, lnthr, Lp);
+                } else {
+                    if (x >= ec.x_hi) violf = __double2float_ru((ec.w_hi - 1.0) * (x - ec.x_hi)) * 1.000001f;
+                    else if (x < 4.0 * ec.x_lo && En < 0.0)             // (beyond e * x_lo the tangent never fails)
+                        ls_code_near(x, ec.x_lo, En, __double2float_ru((ec.w_lo - 1.0) * x) * 1.000001f, lnthr, Lp);
+                    Dp = 0.0;
+                    En = 0.0;
+                }
+            }
+            sDp += Dp;
+            sEn += En;
+            sV += violf;
+#pragma unroll 1
+            for (int r0 = 0; r0 < ne; r0 += 2) {                     // (the two half-warps take alternate edges)
+                const int r = r0 + h;
+                const float tx = __shfl_sync(0xffffffffu, lnthr, r & 31), ty = __shfl_sync(0xffffffffu, Lp, r & 31);
+                if (r < ne) Hs += ls_edge_share(lns, tx, ty, cap_f);
+            }
+            cb += ne;
+        }
+        sDp = warp_sum(sDp);
+        sEn = warp_sum(sEn);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sV += __shfl_xor_sync(0xffffffffu, sV, o);
+        Hs += __shfl_xor_sync(0xffffffffu, Hs, 16);
+        LsBound B;
+        const double m_lo = ec.w_lo - 1.0;
+        B.Qn = (double)(g2n * 1.000001f) - m_lo * sEn;
+        B.Qp = (double)(g2p * 1.000001f);
+        B.Mp = m_lo * sDp;
+        B.G1 = (double)(__double2float_ru(a->max_f) * g1p * 1.0001f);
+        B.R3 = (double)(r3 * 1.0001f);
+        const float fuf = __double2float_ru(fabs(fusf)), fff = __double2float_ru(fufu), g2f = __double2float_ru(G2node);
+        const float r4 = fmaf(2.0f, g2f, sqrtf(g2f) * sqrtf(fmaf(2.0f, sf2, 18.0f * fff)) * 1.0001f);
+        const float base = fmaf(2.0f * cap_f, (float)deg, __double2float_ru(fabs(llh_u))) + 2.0f * (fuf + fff) + r3;
+        const float nops = 2.3e-16f * (float)(4 * deg + 3 * m + 16);
+        B.c0 = fmaf(nops, base, sV) * 1.0001f;
+        B.c1 = nops * fmaf(2.0f, r4, __double2float_ru(sDp)) * 1.0001f;
+        B.kap0 = (gmx > 0.0f) ? __fdividef(fmaxf(__double2float_rd(a->max_f) - sqrtf(fff) * 1.000001f, 0.0f), gmx) * 0.9999f : 3.0e38f;
+        const bool keep = (j < nsteps) && !B.cannot_pass(s_steps[j < nsteps ? j : 0], Hs, a->alpha, G2node);
+        return __ballot_sync(0xffffffffu, keep) & 0xffffu;
+    }
+
     // One node, start to finish.  colp: the node's neighbour list (ids in the low 28 bits when it comes from tcol).
     template <bool kPush>
     __device__ __forceinline__ void node(int64_t u, int deg, const int32_t *colp) {
@@ -493,16 +638,22 @@ struct SpGen {
         if (want_ls) {
             bool need_hi;
             const double G2 = scan_gradient(m, need_hi);
-            // ---------------- LS (:172-182) ----------------
+            // ---------------- LS (:172-182): only if the bounds leave a candidate that can pass ----------------
+            unsigned surv = 0xffffu;
+            if (sp->ls_prune > 1 && nsteps <= 16) surv = bound_mask(colp, deg, m, G2, llh_u, fusf, fufu, nchunks == 1 ? ne_last : 0);
+            if (sp->stats != nullptr && lane == 0) {
+                atomicAdd(sp->stats + 3, 1u);
+                if (surv != 0u) atomicAdd(sp->stats + 2, 1u);
+            }
 #pragma unroll 1
-            for (int tg = 0; tg < nsteps && jstar < 0; tg += 16) {
+            for (int tg = 0; tg < nsteps && jstar < 0 && surv != 0u; tg += 16) {
                 const int j = tg + j16;
                 const bool jok = j < nsteps;
                 const double s = s_steps[jok ? j : 0];
                 // a node whose neighbours fitted one chunk still has them staged from PRE
                 double sumterms = ls_range(colp, 0, deg, s, need_hi, (nchunks == 1 && tg == 0) ? ne_last : 0);
                 sumterms += __shfl_xor_sync(0xffffffffu, sumterms, 16);
-                jstar = decide(tg, s, jok, sumterms, m, need_hi, llh_u, G2);
+                jstar = decide(tg, s, jok, sumterms, m, need_hi, llh_u, G2, surv);
             }
         }
         if (lane == 0) sp->node_llh[u] = llh_u;

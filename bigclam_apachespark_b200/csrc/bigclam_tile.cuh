@@ -1061,6 +1061,7 @@ __global__ void __launch_bounds__(kTlThreads, kTlBlocksPerSM) tile_step_kernel(c
     G.sp = &sp;
     G.s_steps = s_steps;
     G.s_sumF = s_sumF;
+    G.s_lns = s_lns;
     G.ec = {a.x_lo, a.x_hi, a.t_lo, a.t_hi, a.w_lo, a.w_hi};
     G.carve(wbase, ld, lane);
     TlWarp T;

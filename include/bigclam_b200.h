@@ -134,8 +134,8 @@ int bigclam_get_kernel_time(bigclam_ctx *ctx, double *step_kernel_ms_sum, int64_
 int bigclam_get_tile_stats(bigclam_ctx *ctx, int64_t *tiles_done, int64_t *tiles_fallback, int64_t *n_tiles,
                            int64_t *n_general_nodes, int64_t *n_split_hubs);
 
-/* Sparse rows, line search by bounds: of the tile-path nodes that asked for a line search since the previous read, how many
- * had at least one candidate that the bounds could not exclude (and were therefore evaluated). */
+/* Sparse rows, line search by bounds: of the nodes that asked for a line search since the previous read (split hubs not
+ * counted), how many had at least one candidate that the bounds could not exclude (and were therefore evaluated). */
 int bigclam_get_ls_stats(bigclam_ctx *ctx, int64_t *nodes_asked, int64_t *nodes_searched);
 
 /* Sparse rows: re-cut the tiles of small nodes for the current average row size (rows grow or shrink while the solver

@@ -68,6 +68,19 @@ def test_bounds_change_nothing_random_graphs(oracle, k, n, deg, dens, steps, big
         assert searched < asked, f"the bounds excluded nothing ({searched} of {asked} nodes searched)"
 
 
+@pytest.mark.parametrize("k,n,deg,hub,big", [(64, 260, 40, 0, 900), (200, 300, 12, 250, 700)])
+def test_bounds_on_the_general_path(oracle, k, n, deg, hub, big, monkeypatch):
+    """Nodes above the tile budget (more than 32 edges: one warp per node, chunks of 32 staged rows) and a split hub.
+    The bounds of the general path are off by default (they only pay off on few workloads): BIGCLAM_LS_PRUNE=2."""
+    monkeypatch.setenv("BIGCLAM_LS_PRUNE", "2")
+    rp, col = random_graph(n, deg, seed=300 + k, hub=hub)
+    rng = np.random.default_rng(300 + k)
+    F0 = rng.random((n, k)) * (rng.random((n, k)) < 0.08)
+    asked, searched = _run_both(rp, col, k, F0, oracle.colsum(F0) * big, 4, oracle=oracle, where=f"general k={k}")
+    print(f"general path k={k}: {searched} of {asked} nodes line-searched")
+    assert 0 < searched < asked
+
+
 def test_bounds_with_tiny_and_clamped_values(oracle):
     """Rows with values next to the clamps: x just above / below x_lo = -log(MAX_P_), very large products (p at
     MIN_P_), rows near MAX_F_ (the bounds switch themselves off for a tile that can reach it)."""
