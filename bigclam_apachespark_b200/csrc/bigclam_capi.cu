@@ -355,7 +355,7 @@ static int rebuild_sparse_lists(bigclam_ctx *ctx, const std::vector<NodeMeta> &m
         if (!tcol.empty()) CU(cudaMemcpy(ctx->d_tcol, tcol.data(), sizeof(int32_t) * tcol.size(), cudaMemcpyHostToDevice));
     }
     // the reduction walks the processing order with a fixed grid
-    ctx->red_grid = (int)std::max<int64_t>(1, std::min<int64_t>(2 * (int64_t)ctx->num_sms, (cnt + 32 * kRedWarps - 1) / (32 * kRedWarps)));
+    ctx->red_grid = (int)std::max<int64_t>(1, std::min<int64_t>(2 * (int64_t)ctx->num_sms, (cnt + 32 * red_warps(ctx->ld) - 1) / (32 * red_warps(ctx->ld))));
     cudaFree(ctx->d_block_part); ctx->d_block_part = nullptr;
     CU(cudaMalloc(&ctx->d_block_part, sizeof(double) * (size_t)ctx->red_grid * ((size_t)ctx->ld + 2)));
     invalidate_resets(ctx);
@@ -561,7 +561,7 @@ extern "C" int bigclam_create(bigclam_ctx **out, int64_t n, const int64_t *rowpt
         CUC(cudaFuncSetAttribute(tile_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
         CUC(cudaFuncSetAttribute(tile_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
         CUC(cudaFuncSetAttribute(tile_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->sp_smem));
-        CUC(cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kRedWarps * (size_t)sp_ldp(ld))));
+        CUC(cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * red_warps(ld) * (size_t)sp_ldp(ld))));
         int sb2 = 0;                         // the grid must be resident for every variant (hub items wait for each other)
         CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sbps, tile_step_kernel<true, true>, 32 * ctx->sp_wpb, ctx->sp_smem));
         CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sb2, tile_step_kernel<false, false>, 32 * ctx->sp_wpb, ctx->sp_smem));
@@ -1122,7 +1122,7 @@ static int timed_launch(bigclam_ctx *ctx, const StepArgs &a, bool is_step) {
         r.pool_top_in = a.do_linesearch ? ctx->d_pool_top + in : nullptr;
         ctx->work_clean = true;
         if (a.do_linesearch) ctx->top_clean[in] = true;
-        reduce_kernel<<<ctx->red_grid, kRedWarps * 32, sizeof(double) * kRedWarps * (size_t)sp_ldp(ctx->ld), ctx->stream>>>(r);
+        reduce_kernel<<<ctx->red_grid, red_warps(ctx->ld) * 32, sizeof(double) * red_warps(ctx->ld) * (size_t)sp_ldp(ctx->ld), ctx->stream>>>(r);
         CU(cudaGetLastError());
         if (is_step) ++ctx->last_step_launches;
         ctx->last_all_launches += 2;

@@ -39,6 +39,10 @@
 
 namespace bigclam {
 
+#ifndef BIGCLAM_GEN_INLINE          // how the general path (one node / one hub item per call, a single call site each) is compiled into the kernel
+#define BIGCLAM_GEN_INLINE __forceinline__
+#endif
+
 constexpr int kSpBlocksPerSM = 2;
 constexpr int kSpWarps = 8;            // warps per block at most; wide rows run fewer (sp_warps_per_block)
 constexpr int kSpThreads = kSpWarps * 32;
@@ -618,7 +622,7 @@ struct SpGen {
 
     // One node, start to finish.  colp: the node's neighbour list (ids in the low 28 bits when it comes from tcol).
     template <bool kPush>
-    __device__ __forceinline__ void node(int64_t u, int deg, const int32_t *colp) {
+    __device__ BIGCLAM_GEN_INLINE void node(int64_t u, int deg, const int32_t *colp) {
         const uint64_t hu = __ldg(sp->hdr_in + u);
         const int cu = (int)sp_cnt(hu);
         const double *uval = sp->pool_in + sp_off8(hu);
@@ -673,7 +677,7 @@ struct SpGen {
 
     // One item of a split hub (see above).
     template <bool kPush>
-    __device__ __forceinline__ void hub_item(const HubItem item) {
+    __device__ BIGCLAM_GEN_INLINE void hub_item(const HubItem item) {
         const NodeMeta nm = a->meta[item.hub];
         const int64_t u = nm.u, e0 = nm.e0;
         const int deg = nm.deg;

@@ -1154,7 +1154,8 @@ struct ReduceArgs {
     unsigned long long *xflag[8];        // this rank's flag in rank p's flag array
     unsigned long long seq;
 };
-constexpr int kRedWarps = 16;
+constexpr int kRedWarps = 32;      // at most; every warp keeps a dense vector of ldp doubles in shared memory: wide rows run fewer warps
+inline int red_warps(int ld) { const int ldp = sp_ldp(ld); return ldp <= 384 ? 32 : ldp <= 768 ? 16 : 8; }
 
 __global__ void __launch_bounds__(kRedWarps * 32) reduce_kernel(const ReduceArgs r) {
     if (r.done_flag != nullptr && *r.done_flag != 0) return;
@@ -1164,35 +1165,61 @@ __global__ void __launch_bounds__(kRedWarps * 32) reduce_kernel(const ReduceArgs
     double *Dw = reinterpret_cast<double *>(smem_raw) + (size_t)wib * ldp;
     __shared__ double s_llh[kRedWarps];
     __shared__ unsigned int s_nupd[kRedWarps];
+    __shared__ double s_cnt[kRedWarps];
     __shared__ unsigned int s_last;
     for (int c = lane; c < ldp; c += 32) Dw[c] = 0.0;
     __syncwarp();
-    const int64_t nwarps = (int64_t)gridDim.x * kRedWarps;
-    const int64_t chunk = (r.order_n + nwarps - 1) / nwarps;
-    const int64_t gw = (int64_t)blockIdx.x * kRedWarps + wib;
-    const int64_t lo = min(r.order_n, gw * chunk), hi = min(r.order_n, lo + chunk);
+    // group q = 32 positions of the processing order, one per lane: q, q + G, q + 2 G, ... (G groups in all).  The order is
+    // sorted by degree and the nodes that keep moving (and their long delta blocks) cluster in it: taking every G-th position
+    // gives every warp the same mix.  Warp gw takes the groups gw, gw + #warps, ...; a fixed assignment: reproducible sums.
+    const int nw = (int)(blockDim.x >> 5);               // warps of this block (red_warps(ld) <= kRedWarps)
+    const int64_t nwarps = (int64_t)gridDim.x * nw;
+    const int64_t gw = (int64_t)blockIdx.x * nw + wib;
+    const int64_t G = (r.order_n + 31) / 32;
     double llh = 0.0;
     unsigned int nupd = 0;
-    for (int64_t p0 = lo; p0 < hi; p0 += 32) {
-        const int64_t p = p0 + lane;
-        const bool ok = p < hi;
+    for (int64_t q = gw; q < G; q += nwarps) {
+        const int64_t p = (int64_t)lane * G + q;
+        const bool ok = p < r.order_n;
         const int32_t u = ok ? r.meta[p].u : 0;
         if (ok) llh += r.node_llh[u];
-        const bool acc = ok && r.do_linesearch && r.accepted[u] >= 0;
+        // (header and delta count are loaded together with the accepted flag, not after it: one dependent load less)
+        int8_t af = -1;
         uint64_t h = 0;
         int dc = 0;
-        if (acc) { h = r.hdr_out[u]; dc = r.dcnt[u]; }
+        if (ok && r.do_linesearch) { af = r.accepted[u]; h = r.hdr_out[u]; dc = r.dcnt[u]; }
+        const bool acc = af >= 0;
         unsigned bal = __ballot_sync(0xffffffffu, acc);
         nupd += __popc(bal);
+        // the delta blocks of the accepted nodes, four at a time: their first 32 entries are loaded together (independent
+        // loads in flight), then added node by node in position order (entries of one node never collide)
         while (bal) {
-            const int src = __ffs(bal) - 1;
-            bal &= bal - 1u;
-            const uint64_t hs = __shfl_sync(0xffffffffu, h, src);
-            const int d = __shfl_sync(0xffffffffu, dc, src);
-            const double *dv = r.pool_out + sp_off8(hs) + sp_words(sp_cnt(hs));
-            const unsigned short *di = sp_idx(dv, (uint32_t)d);
-            for (int i = lane; i < d; i += 32) Dw[di[i]] += dv[i];
-            __syncwarp();
+            int c4[4], d4[4];
+            double v4[4];
+            const double *dv4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int src = bal ? __ffs(bal) - 1 : 0;
+                const bool live = bal != 0u;
+                bal &= bal - 1u;
+                const uint64_t hs = __shfl_sync(0xffffffffu, h, src);
+                const int d = __shfl_sync(0xffffffffu, dc, src);
+                d4[k] = live ? d : 0;
+                dv4[k] = r.pool_out + sp_off8(hs) + sp_words(sp_cnt(hs));
+                const unsigned short *di = sp_idx(dv4[k], (uint32_t)d);
+                c4[k] = 0;
+                v4[k] = 0.0;
+                if (lane < d4[k]) { c4[k] = di[lane]; v4[k] = dv4[k][lane]; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (lane < d4[k]) Dw[c4[k]] += v4[k];
+                if (d4[k] > 32) {                                  // (long delta blocks: the rest of the entries)
+                    const unsigned short *di = sp_idx(dv4[k], (uint32_t)d4[k]);
+                    for (int i = 32 + lane; i < d4[k]; i += 32) Dw[di[i]] += dv4[k][i];
+                }
+                __syncwarp();
+            }
         }
     }
     llh = warp_sum(llh);
@@ -1202,13 +1229,13 @@ __global__ void __launch_bounds__(kRedWarps * 32) reduce_kernel(const ReduceArgs
     double *mine = r.block_part + (size_t)blockIdx.x * (ld + 2);
     for (int c = threadIdx.x; c < ld; c += blockDim.x) {
         double v = 0.0;
-        for (int w = 0; w < kRedWarps; ++w) v += D0[(size_t)w * ldp + c];
+        for (int w = 0; w < nw; ++w) v += D0[(size_t)w * ldp + c];
         mine[c] = v;
     }
     if (threadIdx.x == 0) {
         double l = 0.0;
         unsigned int nu = 0;
-        for (int w = 0; w < kRedWarps; ++w) { l += s_llh[w]; nu += s_nupd[w]; }
+        for (int w = 0; w < nw; ++w) { l += s_llh[w]; nu += s_nupd[w]; }
         mine[ld] = l;
         mine[ld + 1] = (double)nu;
     }
@@ -1218,23 +1245,50 @@ __global__ void __launch_bounds__(kRedWarps * 32) reduce_kernel(const ReduceArgs
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // block partials in block order, four independent running sums per component (blocks b, b+1, b+2, b+3 of every
-    // group of four) added up in a fixed association: the same bits from run to run, and four loads in flight
-    for (int c = threadIdx.x; c < ld + 2; c += blockDim.x) {
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    // block partials: warp w adds a contiguous range of blocks, in block order, for all components (lane-strided, every
+    // component's load of a round in flight together); the 16 warp sums are then added in warp order.  A fixed
+    // association: the same bits from run to run.
+    {
         const unsigned int nb = gridDim.x;
-        unsigned int b = 0;
-        for (; b + 4 <= nb; b += 4) {
-            v0 += __ldcg(r.block_part + (size_t)(b + 0) * (ld + 2) + c);
-            v1 += __ldcg(r.block_part + (size_t)(b + 1) * (ld + 2) + c);
-            v2 += __ldcg(r.block_part + (size_t)(b + 2) * (ld + 2) + c);
-            v3 += __ldcg(r.block_part + (size_t)(b + 3) * (ld + 2) + c);
+        const unsigned int per = (nb + nw - 1) / nw;
+        const unsigned int b0 = min(nb, (unsigned int)wib * per), b1 = min(nb, b0 + per);
+        double *Wp = reinterpret_cast<double *>(smem_raw) + (size_t)wib * ldp;          // (ld + 2 <= ldp + 2: the two scalars go to s_llh / s_nupd2)
+        double accl = 0.0, accn = 0.0;
+        for (int c0 = 0; c0 < ld; c0 += 32 * 4) {
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+            const int ca = c0 + lane, cb = ca + 32, cc = ca + 64, cd = ca + 96;
+            for (unsigned int b = b0; b < b1; ++b) {
+                const double *bp = r.block_part + (size_t)b * (ld + 2);
+                if (ca < ld) v0 += __ldcg(bp + ca);
+                if (cb < ld) v1 += __ldcg(bp + cb);
+                if (cc < ld) v2 += __ldcg(bp + cc);
+                if (cd < ld) v3 += __ldcg(bp + cd);
+            }
+            if (ca < ld) Wp[ca] = v0;
+            if (cb < ld) Wp[cb] = v1;
+            if (cc < ld) Wp[cc] = v2;
+            if (cd < ld) Wp[cd] = v3;
         }
-        for (; b < nb; ++b) v0 += __ldcg(r.block_part + (size_t)b * (ld + 2) + c);
-        const double v = (v0 + v1) + (v2 + v3);
-        if (c < ld) r.partials[c] = v;
-        else r.partials[2 * ld + (c - ld)] = v;
-        for (int p = 0; p < r.world; ++p) r.xslot[p][c] = v;
+        if (lane < 2) {
+            double v = 0.0;
+            for (unsigned int b = b0; b < b1; ++b) v += __ldcg(r.block_part + (size_t)b * (ld + 2) + ld + lane);
+            if (lane == 0) accl = v; else accn = v;
+        }
+        accn = __shfl_sync(0xffffffffu, accn, 1);
+        __syncthreads();                       // (every warp is done with s_llh / s_nupd of the first phase)
+        if (lane == 0) { s_llh[wib] = accl; s_cnt[wib] = accn; }
+        __syncthreads();
+        for (int c = threadIdx.x; c < ld + 2; c += blockDim.x) {
+            double v = 0.0;
+            if (c < ld) {
+                for (int w = 0; w < nw; ++w) v += D0[(size_t)w * ldp + c];
+                r.partials[c] = v;
+            } else {
+                for (int w = 0; w < nw; ++w) v += (c == ld) ? s_llh[w] : s_cnt[w];
+                r.partials[2 * ld + (c - ld)] = v;
+            }
+            for (int p = 0; p < r.world; ++p) r.xslot[p][c] = v;
+        }
     }
     // the next launch starts from a fresh work counter, and the buffer this step read becomes the next output pool
     if (threadIdx.x == 0) {
