@@ -298,6 +298,7 @@ def run_single(args):
             b.retile()
             b._run(4, 0.0, 2)
         b.tile_stats()                               # reset the counters
+        b.ls_stats()
     sampler = ClockSampler(0)
     sampler.start()
     torch.cuda.synchronize()
@@ -314,6 +315,7 @@ def run_single(args):
     value = nnz / (ms_per_step * 1e-3)
     llh_end = float(b.last_trace[-1])
     tiles = b.tile_stats() if sparse else None
+    ls = b.ls_stats() if sparse else None
 
     # ---- roofline of the dominant kernel ----
     peak, peak_src = hbm_peak()
@@ -360,6 +362,56 @@ def run_single(args):
                    "llh_end": float(b.last_trace[-1])}
     b.close()
 
+    # ---- the same steps with the exhaustive line search (all 16 candidates of every node, like the reference's cartesian,
+    #      bigclam4-7.scala:172-181; BIGCLAM_F_LS_EXHAUSTIVE).  The default engine skips candidates that a bound proves unable
+    #      to pass the Armijo test — same accepted steps, same rows, same LLH bits (tests/test_gpu_prune.py); this is the
+    #      price of evaluating them anyway, measured beside it (not the headline).
+    line_search = None
+    if sparse:
+        bx = BigClam(device=0, time_kernels=True, sparse_rows=True, exhaustive_linesearch=True)
+        bx.set_graph(rp, col).set_K(K)
+        bx.set_stream(stream.cuda_stream)
+        bx.set_F(F0)
+        bx._run(4, 0.0, args.warmup)
+        for _ in range(3):
+            bx.retile()
+            bx._run(4, 0.0, 2)
+        torch.cuda.synchronize()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record(stream)
+        bx._run(4, 0.0, args.steps)
+        x1.record(stream)
+        torch.cuda.synchronize()
+        xk_ms, xk_n, _ = bx.kernel_time()
+        x_llh = float(bx.last_trace[-1])
+        bx.close()
+        # the whole solver run from this F0 as the reference would do it (SGDFindC, :225-243: until |1 - new/old| < 1e-4):
+        # the early iterations, where most nodes still move and the bounds exclude the least, are in here
+        bc = BigClam(device=0, time_kernels=True, sparse_rows=True)
+        bc.set_graph(rp, col).set_K(K)
+        bc.set_stream(stream.cuda_stream)
+        bc.set_F(F0)
+        bc.ls_stats()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        bc.SGDFindC(rel_tol=1e-4, max_outer=500)
+        c1.record(stream)
+        torch.cuda.synchronize()
+        conv_calls = int(bc.last_calls)
+        conv_ls = bc.ls_stats()
+        conv = {"calls": conv_calls, "ms_total": c0.elapsed_time(c1), "ms_per_call": c0.elapsed_time(c1) / max(conv_calls, 1),
+                "nodes_asked": conv_ls["nodes_asked"], "nodes_line_searched": conv_ls["nodes_searched"],
+                "note": "SGDFindC from the synthetic F0 to the reference's stop rule (rel_tol 1e-4), cold start: tile cut and pool sizes settle inside"}
+        bc.close()
+        line_search = {"mode": "bounds (default): a candidate step is evaluated only if a bound on the node's objective cannot exclude it",
+                       "nodes_asked": ls["nodes_asked"], "nodes_line_searched": ls["nodes_searched"],
+                       "exhaustive": {"ms_per_step": x0.elapsed_time(x1) / args.steps, "step_kernel_ms": xk_ms / max(xk_n, 1),
+                                      "value": nnz / (x0.elapsed_time(x1) / args.steps * 1e-3), "llh_end": x_llh,
+                                      "same_llh_bits_as_default": x_llh == llh_end,
+                                      "roofline_frac": balg / (xk_ms / max(xk_n, 1) * 1e-3) / 1e9 / peak},
+                       "run_to_convergence": conv}
+
     # ---- DRAM traffic of one launch, measured now (side process under ncu) ----
     traffic, traffic_src = measure_traffic(args, kernel)
 
@@ -389,7 +441,7 @@ def run_single(args):
                      "layout_frac": layout_bytes / (kavg_ms * 1e-3) / 1e9 / peak,
                      "note": "achieved/frac use SURVEY 8(d)'s dense-model algorithmic bytes; layout_bytes_per_launch is what the sparse rows move, traffic what DRAM saw (the rest is L2)",
                      "tiles": tiles},
-        "cpu_baseline": cpu, "reference_init_workload": extra_a,
+        "cpu_baseline": cpu, "reference_init_workload": extra_a, "line_search": line_search,
     }))
 
 

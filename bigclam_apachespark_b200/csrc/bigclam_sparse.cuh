@@ -39,6 +39,9 @@
 
 namespace bigclam {
 
+#ifndef BIGCLAM_GEN_BOUNDS          // 1: the line-search bounds of the general path are compiled in (used when SparseArgs::ls_prune > 1)
+#define BIGCLAM_GEN_BOUNDS 1
+#endif
 #ifndef BIGCLAM_GEN_INLINE          // how the general path (one node / one hub item per call, a single call site each) is compiled into the kernel
 #define BIGCLAM_GEN_INLINE __forceinline__
 #endif
@@ -644,7 +647,7 @@ struct SpGen {
             const double G2 = scan_gradient(m, need_hi);
             // ---------------- LS (:172-182): only if the bounds leave a candidate that can pass ----------------
             unsigned surv = 0xffffu;
-            if (sp->ls_prune > 1 && nsteps <= 16) surv = bound_mask(colp, deg, m, G2, llh_u, fusf, fufu, nchunks == 1 ? ne_last : 0);
+            if (BIGCLAM_GEN_BOUNDS && sp->ls_prune > 1 && nsteps <= 16) surv = bound_mask(colp, deg, m, G2, llh_u, fusf, fufu, nchunks == 1 ? ne_last : 0);
             if (sp->stats != nullptr && lane == 0) {
                 atomicAdd(sp->stats + 3, 1u);
                 if (surv != 0u) atomicAdd(sp->stats + 2, 1u);
