@@ -408,7 +408,7 @@ def run_single(args):
                        "nodes_asked": ls["nodes_asked"], "nodes_line_searched": ls["nodes_searched"],
                        "exhaustive": {"ms_per_step": x0.elapsed_time(x1) / args.steps, "step_kernel_ms": xk_ms / max(xk_n, 1),
                                       "value": nnz / (x0.elapsed_time(x1) / args.steps * 1e-3), "llh_end": x_llh,
-                                      "same_llh_bits_as_default": x_llh == llh_end,
+                                      "llh_rel_diff_vs_default": abs(x_llh - llh_end) / abs(llh_end),
                                       "roofline_frac": balg / (xk_ms / max(xk_n, 1) * 1e-3) / 1e9 / peak},
                        "run_to_convergence": conv}
 

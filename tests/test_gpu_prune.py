@@ -36,7 +36,13 @@ def _run_both(rp, col, K, F0, sumF, steps, oracle=None, where=""):
         assert np.array_equal(ap, ax), f"{where} step {it}: accepted steps differ at nodes {np.nonzero(ap != ax)[0][:8]}"
         assert bp.F.tobytes() == bx.F.tobytes(), f"{where} step {it}: F differs"
         assert bp.sumF.tobytes() == bx.sumF.tobytes(), f"{where} step {it}: sumF differs"
-        assert lp == lx, f"{where} step {it}: llh {lp!r} vs {lx!r}"
+        # the LLH is a sum over nodes of per-node sums: the same bits as long as every node took the same path in both engines
+        # (a tile that overflows the line-search buffers only when ALL its nodes are searched goes node by node through the
+        # general path, which adds a node's terms in another order: rounding-level difference of the LLH, same rows)
+        if bp.tile_stats()["tiles_fallback"] == bx.tile_stats()["tiles_fallback"]:
+            assert lp == lx, f"{where} step {it}: llh {lp!r} vs {lx!r}"
+        else:
+            assert abs(lp - lx) <= 1e-13 * abs(lx), f"{where} step {it}: llh {lp!r} vs {lx!r}"
         st = bp.ls_stats()
         sx = bx.ls_stats()
         assert sx["nodes_searched"] == sx["nodes_asked"], f"{where}: the exhaustive engine skipped nodes: {sx}"
@@ -105,7 +111,7 @@ def test_bounds_with_uset_and_drifted_sumF(oracle):
     mask = np.nonzero(rng.random(n) < 0.6)[0]
     for it in range(3):
         lp, lx = bp.backtrackingLineSearchs(mask), bx.backtrackingLineSearchs(mask)
-        assert lp == lx and bp.F.tobytes() == bx.F.tobytes() and np.array_equal(bp.accepted(), bx.accepted()), f"step {it}"
+        assert abs(lp - lx) <= 1e-13 * abs(lx) and bp.F.tobytes() == bx.F.tobytes() and np.array_equal(bp.accepted(), bx.accepted()), f"step {it}"
     bp.close()
     bx.close()
 
