@@ -425,6 +425,7 @@ struct SpGen {
         const double max_f = a->max_f;
         int cnt_new = 0, nd = 0;
         double s = 0.0;
+        __syncwarp();                     // the entry buffers are reused: every lane is done reading the staged rows (PRE, bounds, LS)
         if (jstar >= 0) {
             s = s_steps[jstar];
 #pragma unroll 1
