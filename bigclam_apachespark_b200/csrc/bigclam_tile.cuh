@@ -92,6 +92,7 @@ __host__ __device__ inline size_t tl_warp_bytes(int ld) {
     b += 2 * ((size_t)kTlAct + 2);                      // loff
     b += 2 * 2 * kTlMaxNodes * W;                       // pref_t, pref_f
     b += 2 * (40 + 40 + 12 + 12 + 12 + 8 + 8);          // e_soff, e_cnt, n_es, n_sb, n_ab, n_m, n_tot
+    b += 2 * 32;                                        // e_io2
     b += 2 * (size_t)kTlEnt + 8 + 8;                    // ent_e, ent_a, n_js, n_want
     b += (size_t)kTlErow + 2 * 34 + 32;                 // erow, epos, e_ni
     b += 2 * 8 + 8;                                     // n_sv, n_sl (line search by bounds)
@@ -177,7 +178,7 @@ struct TlWarp {
     unsigned long long *mbar;
     unsigned int *tmask, *fmask, *lcnt;
     int *n_u;
-    unsigned short *slot_c, *amap, *loff, *plist, *pref_t, *pref_f, *e_soff, *e_cnt, *n_es, *n_sb, *n_ab, *n_m, *n_tot;
+    unsigned short *slot_c, *amap, *loff, *plist, *pref_t, *pref_f, *e_soff, *e_cnt, *e_io2, *n_es, *n_sb, *n_ab, *n_m, *n_tot;
     unsigned char *ent_e, *ent_a, *erow, *e_ni, *n_want;
     unsigned short *epos;
     signed char *n_js;
@@ -210,6 +211,7 @@ struct TlWarp {
         pref_f = reinterpret_cast<unsigned short *>(p);   p += 2 * (size_t)kTlMaxNodes * W;
         e_soff = reinterpret_cast<unsigned short *>(p);   p += 2 * 40;
         e_cnt = reinterpret_cast<unsigned short *>(p);    p += 2 * 40;
+        e_io2 = reinterpret_cast<unsigned short *>(p);    p += 2 * 32;     // flat entry t of row e: its index is stageN (as uint16) [(e_io2[e] + t) mod 2^16]
         n_es = reinterpret_cast<unsigned short *>(p);     p += 2 * 12;
         n_sb = reinterpret_cast<unsigned short *>(p);     p += 2 * 12;
         n_ab = reinterpret_cast<unsigned short *>(p);     p += 2 * 12;
@@ -292,6 +294,7 @@ struct TlWarp {
         if (lane < ne) {
             e_soff[lane] = (unsigned short)soff_e;
             e_cnt[lane] = (unsigned short)ce;
+            e_io2[lane] = (unsigned short)(8 * soff_e + 4 * (int)sp_vpad((uint32_t)ce) - (incl_c - ce));
             epos[lane] = (unsigned short)(incl_c - ce);
             e_ni[lane] = (unsigned char)ni;
             if (lane == 0) epos[ne] = (unsigned short)T;
@@ -368,12 +371,12 @@ struct TlWarp {
             for (int i = 0; i < ce; ++i) er[i] = (unsigned char)lane;         // flat entry -> row
         }
         __syncwarp();
+        unsigned short *stN16 = reinterpret_cast<unsigned short *>(stageN);
         // (from here on the loops over the neighbours' entries are FLAT: entry t of the tile = entry t - epos[row] of row erow[t])
 BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         for (int t = lane; t < T; t += 32) {
             const int row = erow[t];
-            const double *vv = reinterpret_cast<const double *>(stageN + 16 * (size_t)e_soff[row]);
-            const int c = sp_idx(vv, (uint32_t)e_cnt[row])[t - (int)epos[row]];
+            const int c = stN16[(unsigned short)(e_io2[row] + t)];
             atomicOr(tmask + (int)e_ni[row] * W + (c >> 5), 1u << (c & 31));
         }
         __syncwarp();
@@ -417,8 +420,7 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
 BIGCLAM_UNROLL(BIGCLAM_TL_UF)
         for (int t = lane; t < T; t += 32) {
             const int row = erow[t];
-            double *vv = reinterpret_cast<double *>(stageN + 16 * (size_t)e_soff[row]);
-            unsigned short *pc = sp_idx(vv, (uint32_t)e_cnt[row]) + (t - (int)epos[row]);
+            unsigned short *pc = stN16 + (unsigned short)(e_io2[row] + t);
             const int c = *pc;
             const int node = e_ni[row];
             const int w = c >> 5;
@@ -764,9 +766,7 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
                 const int thi = epos[n_es[na + len]];
 BIGCLAM_UNROLL(BIGCLAM_TL_UF)
                 for (int t = (int)epos[n_es[na]] + lane; t < thi; t += 32) {
-                    const int row = erow[t];
-                    const double *vv = reinterpret_cast<const double *>(stageN + 16 * (size_t)e_soff[row]);
-                    const unsigned an = amap[sp_idx(vv, (uint32_t)e_cnt[row])[t - (int)epos[row]]];
+                    const unsigned an = amap[stN16[(unsigned short)(e_io2[erow[t]] + t)]];
                     if (an != 0xffffu) atomicAdd(lcnt + an, 1u);
                 }
             }
@@ -811,7 +811,7 @@ BIGCLAM_UNROLL(BIGCLAM_TL_UF)
                     const int row = erow[t];
                     const double *vv = reinterpret_cast<const double *>(stageN + 16 * (size_t)e_soff[row]);
                     const int i = t - (int)epos[row];
-                    const unsigned an = amap[sp_idx(vv, (uint32_t)e_cnt[row])[i]];
+                    const unsigned an = amap[stN16[(unsigned short)(e_io2[row] + t)]];
                     if (an != 0xffffu) {
                         const unsigned q = atomicAdd(lcnt + an, 1u);
                         ent_val[q] = vv[i];
