@@ -22,6 +22,11 @@ The working set of the sparse layout is ~80 MB: it is L2-resident on purpose, no
           pinned memory, LLH/n_updated D2H every step)
   roofline  algorithmic bytes of one step kernel / its average duration (CUDA events in the library)
   cpu_baseline  the CPU restatement of the reference (oracle/, NOT Spark) on the host cores
+  line_search   the default engine evaluates a candidate step only if a bound on the node's objective cannot exclude it
+          (same accepted steps, rows and LLH as the reference's exhaustive 16 candidates: tests/test_gpu_prune.py); this
+          block says how many nodes were line-searched in the timed steps and times, beside the headline and never as
+          the headline, the exhaustive engine (BIGCLAM_F_LS_EXHAUSTIVE) on the same steps and a whole SGDFindC run from
+          the synthetic F0 to the reference's stop rule
 `--impl reference` times that CPU restatement alone (the reference needs a JVM + Spark: absent).
 """
 import argparse

@@ -12,9 +12,11 @@
 //   slots   the components a node touches (its own and its neighbours' non-zeros) get consecutive slots in
 //           ascending component order (bitmask + prefix popcounts): slot s holds (fu_c, grad_c);
 //   axpy    lane groups of 32/nn lanes per node add w_e * fv_e into the slots, edge by edge (CSR order);
-//   LS      lane = (edge parity, trial): dots over the ACTIVE entries only; (edge, trial) pairs whose x is
-//           outside (x_lo, x_hi) are constants after the clamp (:166), the others are compacted and exp/log runs
-//           on full warps of them (about half of the 16 x deg pairs on the bench workload);
+//   bounds  which (node, trial) pairs can pass the Armijo test at all (phase H2: a concavity bound on the node's objective
+//           from the PRE quantities); on the bench workload 9 of 10 nodes have no such pair and keep their row;
+//   LS      for the other nodes, two at a time, lane = (node, trial): dots over the ACTIVE entries only; (edge, trial)
+//           pairs whose x is outside (x_lo, x_hi) are constants after the clamp (:166), the others are compacted and
+//           exp/log runs on full warps of them;
 //   decide  lane = (node, trial); swap: rows written by the node's lane group, one pool allocation per tile.
 // A tile whose rows or touched components do not fit the warp's shared memory is processed node by node on the
 // general path (SpGen) by the same warp; nodes above 32 edges always are.
