@@ -250,7 +250,7 @@ def measure_traffic(args, kernel_regex):
            str(args.k), "5", "2", args.graph]
     env = dict(os.environ, BIGCLAM_AB_SPARSE="1" if args.layout == "sparse" else "0")
     try:
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env).stdout
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=env).stdout
     except Exception as exc:                # noqa: BLE001
         return None, f"ncu failed: {exc!r}"
     tot = 0.0
@@ -279,6 +279,46 @@ def sparse_layout_bytes(indptr, rp, col):
     cnt = np.diff(indptr)
     blk = 8 * ((cnt + 1) // 2 * 2) + 2 * ((cnt + 7) // 8 * 8)
     return int(blk[col].sum() + 12 * len(col) + 2 * blk.sum() + 16 * (len(rp) - 1))
+
+
+class ExtrasWatchdog:
+    """The headline numbers (value, roofline, e2e) are measured first; everything after them (the reference-style-init
+    workload, the exhaustive-line-search arm, the run to convergence, the ncu side process, the CPU baseline) explains them.
+    If that part stalls — a wedged side process, a stuck device call — the line measured so far is printed with
+    `extras_cut` set and the process ends, instead of the whole run being lost at the caller's limit."""
+
+    def __init__(self, limit_s):
+        self.limit_s = limit_s
+        self.lock = threading.Lock()
+        self.line = None
+        self.stage = "start"
+        self.printed = False
+        self.timer = None
+
+    def arm(self, line):
+        self.line = line
+        self.timer = threading.Timer(self.limit_s, self._fire)
+        self.timer.daemon = True
+        self.timer.start()
+
+    def _fire(self):
+        with self.lock:
+            if self.printed:
+                return
+            self.printed = True
+            out = dict(self.line, extras_cut=f"stopped after {self.limit_s:.0f} s in '{self.stage}': fields not reached are null")
+            sys.stdout.write(json.dumps(out) + "\n")
+            sys.stdout.flush()
+        os._exit(0)
+
+    def emit(self, line):
+        with self.lock:
+            if self.printed:
+                return
+            self.printed = True
+            if self.timer is not None:
+                self.timer.cancel()
+            print(json.dumps(line), flush=True)
 
 
 def run_single(args):
@@ -346,89 +386,9 @@ def run_single(args):
            "d2h_bytes_per_step": 72, "ms_per_step": e2e_ms,
            "note": "bigclam_step() per step: uset mask H2D (pinned) + sumF commit + the next call's step kernel launched speculatively (its PRE is this call's LLH) + LLH/n_updated D2H, synchronous; F stays resident like the reference's cached RDD"}
 
-    # ---- workload A of SURVEY §8d: the reference's own init (conductance seeds, 0/1 indicator columns) ----
-    extra_a = None
-    if not args.no_init_a and not hasattr(F0, "tocsr") and n <= 2_000_000:
-        t0 = time.perf_counter()
-        b.initNeighborComF(K)
-        init_s = time.perf_counter() - t0
-        b._run(4, 0.0, args.warmup)
-        torch.cuda.synchronize()
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ea.record(stream)
-        b._run(4, 0.0, args.steps)
-        eb.record(stream)
-        torch.cuda.synchronize()
-        ms_a = ea.elapsed_time(eb) / args.steps
-        kms_a, nk_a, _ = b.kernel_time()
-        extra_a = {"workload": f"{args.graph} K={K}, F0 = initNeighborComF({K}) (bigclam4-7.scala:81-108: 0/1 indicator columns of the best-conductance seeds)",
-                   "value": nnz / (ms_a * 1e-3), "unit": "edges/s", "ms_per_step": ms_a, "step_kernel_ms": kms_a / max(nk_a, 1),
-                   "roofline_frac": balg / (kms_a / max(nk_a, 1) * 1e-3) / 1e9 / peak, "init_seconds": init_s,
-                   "llh_end": float(b.last_trace[-1])}
-    b.close()
-
-    # ---- the same steps with the exhaustive line search (all 16 candidates of every node, like the reference's cartesian,
-    #      bigclam4-7.scala:172-181; BIGCLAM_F_LS_EXHAUSTIVE).  The default engine skips candidates that a bound proves unable
-    #      to pass the Armijo test — same accepted steps, same rows, same LLH bits (tests/test_gpu_prune.py); this is the
-    #      price of evaluating them anyway, measured beside it (not the headline).
-    line_search = None
-    if sparse:
-        bx = BigClam(device=0, time_kernels=True, sparse_rows=True, exhaustive_linesearch=True)
-        bx.set_graph(rp, col).set_K(K)
-        bx.set_stream(stream.cuda_stream)
-        bx.set_F(F0)
-        bx._run(4, 0.0, args.warmup)
-        for _ in range(3):
-            bx.retile()
-            bx._run(4, 0.0, 2)
-        torch.cuda.synchronize()
-        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        x0.record(stream)
-        bx._run(4, 0.0, args.steps)
-        x1.record(stream)
-        torch.cuda.synchronize()
-        xk_ms, xk_n, _ = bx.kernel_time()
-        x_llh = float(bx.last_trace[-1])
-        bx.close()
-        # the whole solver run from this F0 as the reference would do it (SGDFindC, :225-243: until |1 - new/old| < 1e-4):
-        # the early iterations, where most nodes still move and the bounds exclude the least, are in here
-        bc = BigClam(device=0, time_kernels=True, sparse_rows=True)
-        bc.set_graph(rp, col).set_K(K)
-        bc.set_stream(stream.cuda_stream)
-        bc.set_F(F0)
-        bc.ls_stats()
-        torch.cuda.synchronize()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record(stream)
-        bc.SGDFindC(rel_tol=1e-4, max_outer=500)
-        c1.record(stream)
-        torch.cuda.synchronize()
-        conv_calls = int(bc.last_calls)
-        conv_ls = bc.ls_stats()
-        conv = {"calls": conv_calls, "ms_total": c0.elapsed_time(c1), "ms_per_call": c0.elapsed_time(c1) / max(conv_calls, 1),
-                "nodes_asked": conv_ls["nodes_asked"], "nodes_line_searched": conv_ls["nodes_searched"],
-                "note": "SGDFindC from the synthetic F0 to the reference's stop rule (rel_tol 1e-4), cold start: tile cut and pool sizes settle inside"}
-        bc.close()
-        line_search = {"mode": "bounds (default): a candidate step is evaluated only if a bound on the node's objective cannot exclude it",
-                       "nodes_asked": ls["nodes_asked"], "nodes_line_searched": ls["nodes_searched"],
-                       "exhaustive": {"ms_per_step": x0.elapsed_time(x1) / args.steps, "step_kernel_ms": xk_ms / max(xk_n, 1),
-                                      "value": nnz / (x0.elapsed_time(x1) / args.steps * 1e-3), "llh_end": x_llh,
-                                      "llh_rel_diff_vs_default": abs(x_llh - llh_end) / abs(llh_end),
-                                      "roofline_frac": balg / (xk_ms / max(xk_n, 1) * 1e-3) / 1e9 / peak},
-                       "run_to_convergence": conv}
-
-    # ---- DRAM traffic of one launch, measured now (side process under ncu) ----
-    traffic, traffic_src = measure_traffic(args, kernel)
-
-    # ---- CPU baseline beside it (bounded: 5 faithful steps after 1 warm-up) ----
-    cpu = None
-    if not args.no_cpu and not hasattr(F0, "tocsr"):
-        val, cores, sample, sec = time_oracle(rp, col, F0, K, 5, 1, budget_s=45.0)
-        cpu = {"value": val, "unit": "edges/s", "cores": cores, "kind": "port",
-               "sample": sample + "; CPU restatement of the reference (oracle/, -O3 -march=native), not Spark", "ms_per_step": sec * 1e3}
-
+    # ---- the line as measured so far; what follows explains it and cannot lose it (ExtrasWatchdog) ----
     cfg = base_config(args.graph, K, n, nnz, args.layout)
-    print(json.dumps({
+    line = {
         "metric": "edges/sec in F-gradient step", "value": value, "unit": "edges/s",
         "unit_note": "directed neighbour-list entries per second (2 per undirected edge)", "value_undirected_edges_per_s": value / 2,
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -440,14 +400,123 @@ def run_single(args):
         "llh_end": llh_end, "parity": "PARITY UNPINNED: checked against oracle/ (CPU restatement), not against outputs of the reference",
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(n_all),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel,
+                     "traffic": None, "traffic_source": "not reached", "kernel": kernel,
                      "kernel_ms": kavg_ms, "alg_bytes_per_launch": balg, "peak_source": peak_src,
                      "f_layout": args.layout, "layout_bytes_per_launch": layout_bytes,
                      "layout_frac": layout_bytes / (kavg_ms * 1e-3) / 1e9 / peak,
                      "note": "achieved/frac use SURVEY 8(d)'s dense-model algorithmic bytes; layout_bytes_per_launch is what the sparse rows move, traffic what DRAM saw (the rest is L2)",
                      "tiles": tiles},
-        "cpu_baseline": cpu, "reference_init_workload": extra_a, "line_search": line_search,
-    }))
+        "cpu_baseline": None, "reference_init_workload": None, "line_search": None,
+    }
+    dog = ExtrasWatchdog(args.extras_limit)
+    dog.arm(line)
+
+    # ---- DRAM traffic of one launch, measured now (side process under ncu) ----
+    dog.stage = "roofline.traffic (ncu side process)"
+    traffic, traffic_src = measure_traffic(args, kernel)
+    line["roofline"]["traffic"] = traffic
+    line["roofline"]["traffic_source"] = traffic_src
+
+    # ---- CPU baseline beside it (bounded: 5 faithful steps after 1 warm-up) ----
+    dog.stage = "cpu_baseline"
+    if not args.no_cpu and not hasattr(F0, "tocsr"):
+        try:
+            val, cores, sample, sec = time_oracle(rp, col, F0, K, 5, 1, budget_s=45.0)
+            line["cpu_baseline"] = {"value": val, "unit": "edges/s", "cores": cores, "kind": "port",
+                                    "sample": sample + "; CPU restatement of the reference (oracle/, -O3 -march=native), not Spark",
+                                    "ms_per_step": sec * 1e3}
+        except Exception as exc:            # noqa: BLE001
+            line["cpu_baseline"] = {"unavailable": repr(exc)}
+
+    # ---- workload A of SURVEY §8d: the reference's own init (conductance seeds, 0/1 indicator columns) ----
+    dog.stage = "reference_init_workload"
+    try:
+        if not args.no_init_a and not hasattr(F0, "tocsr") and n <= 2_000_000:
+            t0 = time.perf_counter()
+            b.initNeighborComF(K)
+            init_s = time.perf_counter() - t0
+            b._run(4, 0.0, args.warmup)
+            torch.cuda.synchronize()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(stream)
+            b._run(4, 0.0, args.steps)
+            eb.record(stream)
+            torch.cuda.synchronize()
+            ms_a = ea.elapsed_time(eb) / args.steps
+            kms_a, nk_a, _ = b.kernel_time()
+            line["reference_init_workload"] = {
+                "workload": f"{args.graph} K={K}, F0 = initNeighborComF({K}) (bigclam4-7.scala:81-108: 0/1 indicator columns of the best-conductance seeds)",
+                "value": nnz / (ms_a * 1e-3), "unit": "edges/s", "ms_per_step": ms_a, "step_kernel_ms": kms_a / max(nk_a, 1),
+                "roofline_frac": balg / (kms_a / max(nk_a, 1) * 1e-3) / 1e9 / peak, "init_seconds": init_s,
+                "llh_end": float(b.last_trace[-1])}
+    except Exception as exc:                # noqa: BLE001
+        line["reference_init_workload"] = {"unavailable": repr(exc)}
+    try:
+        b.close()
+    except Exception:                       # noqa: BLE001
+        pass
+
+    # ---- the same steps with the exhaustive line search (all 16 candidates of every node, like the reference's cartesian,
+    #      bigclam4-7.scala:172-181; BIGCLAM_F_LS_EXHAUSTIVE).  The default engine skips candidates that a bound proves unable
+    #      to pass the Armijo test — same accepted steps, same rows, same LLH bits (tests/test_gpu_prune.py); this is the
+    #      price of evaluating them anyway, measured beside it (not the headline).
+    if sparse and not args.no_line_search:
+        line_search = {"mode": "bounds (default): a candidate step is evaluated only if a bound on the node's objective cannot exclude it",
+                       "nodes_asked": ls["nodes_asked"], "nodes_line_searched": ls["nodes_searched"],
+                       "exhaustive": None, "run_to_convergence": None}
+        line["line_search"] = line_search
+        dog.stage = "line_search.exhaustive"
+        try:
+            bx = BigClam(device=0, time_kernels=True, sparse_rows=True, exhaustive_linesearch=True)
+            bx.set_graph(rp, col).set_K(K)
+            bx.set_stream(stream.cuda_stream)
+            bx.set_F(F0)
+            bx._run(4, 0.0, args.warmup)
+            for _ in range(3):
+                bx.retile()
+                bx._run(4, 0.0, 2)
+            torch.cuda.synchronize()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record(stream)
+            bx._run(4, 0.0, args.steps)
+            x1.record(stream)
+            torch.cuda.synchronize()
+            xk_ms, xk_n, _ = bx.kernel_time()
+            x_llh = float(bx.last_trace[-1])
+            bx.close()
+            x_ms = x0.elapsed_time(x1) / args.steps
+            line_search["exhaustive"] = {"ms_per_step": x_ms, "step_kernel_ms": xk_ms / max(xk_n, 1),
+                                         "value": nnz / (x_ms * 1e-3), "llh_end": x_llh,
+                                         "llh_rel_diff_vs_default": abs(x_llh - llh_end) / abs(llh_end),
+                                         "roofline_frac": balg / (xk_ms / max(xk_n, 1) * 1e-3) / 1e9 / peak}
+        except Exception as exc:            # noqa: BLE001
+            line_search["exhaustive"] = {"unavailable": repr(exc)}
+        # the whole solver run from this F0 as the reference would do it (SGDFindC, :225-243: until |1 - new/old| < 1e-4):
+        # the early iterations, where most nodes still move and the bounds exclude the least, are in here
+        dog.stage = "line_search.run_to_convergence"
+        try:
+            bc = BigClam(device=0, time_kernels=True, sparse_rows=True)
+            bc.set_graph(rp, col).set_K(K)
+            bc.set_stream(stream.cuda_stream)
+            bc.set_F(F0)
+            bc.ls_stats()
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            bc.SGDFindC(rel_tol=1e-4, max_outer=500)
+            c1.record(stream)
+            torch.cuda.synchronize()
+            conv_calls = int(bc.last_calls)
+            conv_ls = bc.ls_stats()
+            bc.close()
+            line_search["run_to_convergence"] = {
+                "calls": conv_calls, "ms_total": c0.elapsed_time(c1), "ms_per_call": c0.elapsed_time(c1) / max(conv_calls, 1),
+                "nodes_asked": conv_ls["nodes_asked"], "nodes_line_searched": conv_ls["nodes_searched"],
+                "note": "SGDFindC from the synthetic F0 to the reference's stop rule (rel_tol 1e-4), cold start: tile cut and pool sizes settle inside"}
+        except Exception as exc:            # noqa: BLE001
+            line_search["run_to_convergence"] = {"unavailable": repr(exc)}
+
+    dog.emit(line)
 
 
 def main():
@@ -464,6 +533,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-init-a", action="store_true", help="skip the reference-style-init extra workload")
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu side process that measures DRAM traffic")
+    ap.add_argument("--no-line-search", action="store_true", help="skip the exhaustive-line-search arm and the run to convergence")
+    ap.add_argument("--extras-limit", type=float, default=420.0,
+                    help="seconds the explanatory legs after the timed regions may take before the line is printed without them")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     args.graph = args.graph or cfg["graph"]

@@ -93,7 +93,6 @@ struct bigclam_ctx {
     TileMeta *d_tiles = nullptr;
     int32_t *d_tcol = nullptr;
     int32_t ntiles = 0, n_gen = 0;
-    int64_t run_batch = 8;                        // steps bigclam_run enqueues between two looks at the device state (grows while the tile cut is stable)
     int32_t tile_edges = kTlMaxEdges;             // edge budget of a tile (0: no tiles), see retile()
     int32_t tile_nodes = kTlMaxNodes;             // node budget of a tile
     double tile_avg16 = 1.0;                      // average row size (16-byte chunks) the tiles were cut for
@@ -743,7 +742,6 @@ static int check_overflow(bigclam_ctx *ctx) {
 // Sparse rows: the edge budget of a tile follows the rows' average size (the rows of a tile are staged in
 // kTlStage16 16-byte chunks of shared memory); called when F is set.  BIGCLAM_TILE_EDGES pins it instead.
 static int retile(bigclam_ctx *ctx, uint64_t words_used) {
-    ctx->run_batch = 8;               // (F was set or the rows changed size: bigclam_run looks at the state often again)
     if (!ctx->sparse || std::getenv("BIGCLAM_TILE_EDGES") != nullptr) return BIGCLAM_OK;
     std::vector<uint64_t> hdr((size_t)ctx->n);
     CU(cudaMemcpy(hdr.data(), ctx->d_hdr[ctx->cur], sizeof(uint64_t) * (size_t)ctx->n, cudaMemcpyDeviceToHost));
@@ -1302,9 +1300,7 @@ extern "C" int bigclam_run(bigclam_ctx *ctx, int32_t variant, double rel_tol, in
 
     RunState *hst = reinterpret_cast<RunState *>(ctx->h_pinned + 8);
     const int start_cur = ctx->cur;
-    // the stream drains once per batch (the host reads the loop state and may re-cut the tiles): 8 steps while the rows are
-    // still changing size, up to 64 once the tile cut has been stable (a launch after convergence is a no-op)
-    int64_t batch = std::max<int64_t>(8, std::min<int64_t>(64, ctx->run_batch));
+    const int64_t batch = 8;       // the stream drains once per batch: the host reads the loop state and may re-cut the tiles
     int64_t c = 0;                 // step kernels enqueued so far (kernel c maps S_{c-1} -> S_c)
     bool done = false;
     StepArgs a;
@@ -1327,12 +1323,9 @@ extern "C" int bigclam_run(bigclam_ctx *ctx, int32_t variant, double rel_tol, in
         {   // the stream is idle: a good moment to re-cut the tiles when the rows have changed size a lot
             const int keep = ctx->cur;
             ctx->cur = (start_cur + (int)(c & 1)) & 1;            // S_c, the current state
-            const int32_t te = ctx->tile_edges, tn = ctx->tile_nodes, nt = ctx->ntiles;
             const int rt = maybe_retile(ctx);
             ctx->cur = keep;
             if (rt) return rt;
-            batch = (te == ctx->tile_edges && tn == ctx->tile_nodes && nt == ctx->ntiles) ? std::min<int64_t>(64, 2 * batch) : 8;
-            ctx->run_batch = batch;
         }
     }
     int64_t calls;

@@ -124,16 +124,17 @@ def test_bounds_with_uset_and_drifted_sumF(oracle):
     bx.close()
 
 
-@pytest.mark.timeout(900)
-@pytest.mark.parametrize("name,k,steps", [("facebook_combined", 10, 3), ("email-enron", 50, 3), ("com-amazon", 200, 8)])
-def test_bounds_change_nothing_on_the_baseline_graphs(graphs, name, k, steps):
-    """BASELINE configs 1-3, several steps from the synthetic F0 of the bench (on com-amazon far enough for a good part of
-    the nodes to have stopped moving: that is where the bounds exclude the most)."""
+def _baseline_graph_case(graphs, name, k, steps):
     rp, col, _ = graphs.load_npz_graph(name)
     n = len(rp) - 1
     F0 = graphs.synthetic_F0(n, k, seed=1234, density=0.05 if k >= 100 else 0.2)
     from oracle import oracle as O
-    asked, searched = _run_both(rp, col, k, F0, O.colsum(F0), steps, where=name)
+    return _run_both(rp, col, k, F0, O.colsum(F0), steps, where=name)
+
+
+@pytest.mark.parametrize("name,k,steps", [("facebook_combined", 10, 3), ("email-enron", 50, 3)])
+def test_bounds_change_nothing_on_the_baseline_graphs(graphs, name, k, steps):
+    """BASELINE configs 1-2, several steps from the synthetic F0 of the bench (config 3, com-amazon K=200, is the last test
+    of the suite: tests/test_gpu_zz_amazon_prune.py)."""
+    asked, searched = _baseline_graph_case(graphs, name, k, steps)
     assert searched <= asked
-    if name == "com-amazon":
-        assert searched < 0.75 * asked, f"{searched} of {asked}"
