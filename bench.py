@@ -392,6 +392,7 @@ def run_single(args):
         "metric": "edges/sec in F-gradient step", "value": value, "unit": "edges/s",
         "unit_note": "directed neighbour-list entries per second (2 per undirected edge)", "value_undirected_edges_per_s": value / 2,
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "untimed_steps_before_timing": args.warmup + (6 if sparse else 0),
         "iters_per_sec": 1e3 / ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "SNAP topology (package data) or generated R-MAT + synthetic F0",
         "config": cfg, "parallelism": "1 GPU",

@@ -348,6 +348,9 @@ class DistBigClam:
 
 
 # ------------------------------------------------------------------------------------------------
+SETTLE_STEPS = 6         # untimed steps after the W warm-up steps in both arms of bench.py (N = 1: 3 x (retile + 2 steps))
+
+
 def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, base_config):
     """bench.py for N > 1: launched by torchrun, one rank per GPU; torch.distributed (NCCL) is the plumbing (rendezvous,
     IPC-handle all-gather, timing reductions), the data path is the step kernel's NVLink row stores plus the fused
@@ -391,6 +394,9 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, base_conf
 
     for _ in range(args.warmup):
         d.step_nollh()
+    settle = SETTLE_STEPS if sparse else 0
+    for _ in range(settle):                  # (untimed) the same window of the trajectory as the single-GPU arm of bench.py,
+        d.step_nollh()                       # which lets its tile cut settle over this many steps after the warm-up
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -443,6 +449,7 @@ def bench_main(args, load_workload, alg_bytes, hbm_peak, ClockSampler, base_conf
             "metric": "edges/sec in F-gradient step", "value": value, "unit": "edges/s",
             "unit_note": "directed neighbour-list entries per second (2 per undirected edge)", "value_undirected_edges_per_s": value / 2,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "untimed_steps_before_timing": args.warmup + settle,
             "iters_per_sec": 1e3 / ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "SNAP topology (package data) or generated R-MAT + synthetic F0",
             "config": base_config(args.graph, K, n, nnz, args.layout),

@@ -80,6 +80,7 @@ def test_bench_single_gpu_arm_dry_run():
     d = _bench_dryrun()
     assert d["metric"] == "edges/sec in F-gradient step" and d["unit"] == "edges/s" and d["higher_is_better"] is True
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["untimed_steps_before_timing"] == 3 + 6          # warm-up + the steps over which the tile cut settles (both arms)
     assert set(d["config"]) == {"workload", "graph", "k", "n", "nnz_directed", "edges_undirected", "f0", "f_layout"}
     assert abs(d["value"] - d["config"]["nnz_directed"] / (d["ms_per_step"] * 1e-3)) <= 1e-9 * d["value"]
     assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] == d["config"]["n"] and d["e2e"]["d2h_bytes_per_step"] > 0
