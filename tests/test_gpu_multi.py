@@ -55,6 +55,38 @@ def test_multi_steps_match_oracle_and_replicas_agree(oracle, world, hub, monkeyp
     b.close()
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_multi_steps_in_the_large_graph_regime(oracle, world):
+    """sumF as if the graph were 900 times larger (the hot path takes sumF as given, :38,:192): most components of a node's
+    gradient are -sumF_c, fewer and fewer nodes move, and the line search by bounds excludes most candidates — on every rank
+    the same way: rows, LLH and the number of updated nodes against the oracle, replicas bit-identical."""
+    if world not in _worlds() or _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from bigclam_apachespark_b200 import BigClam
+    n, k = 400, 64
+    rp, col = random_graph(n, 4, seed=164)
+    rng = np.random.default_rng(64)
+    F0 = rng.random((n, k)) * (rng.random((n, k)) < 0.1)
+    sumF = oracle.colsum(F0) * 900
+    P = oracle.make_params(k)
+    b = BigClam(record_accepted=False, numGPUs=world)
+    b.set_graph(rp, col).set_K(k).set_F(F0, sumF=sumF)
+    F, s = F0, sumF
+    moved = []
+    for it in range(5):
+        llh = b.backtrackingLineSearchs()
+        r = oracle.step(rp, col, F, s, P)
+        assert abs(llh - r.llh) <= 1e-10 * abs(r.llh) and b.last_n_updated == r.n_updated, f"step {it}"
+        reps = [b.replica_F(q) for q in range(world)]
+        for q in range(1, world):
+            assert np.array_equal(reps[0], reps[q]), f"replica {q} differs from replica 0 after step {it}"
+        assert np.abs(reps[0] - r.F).max() <= 1e-9 * max(np.abs(r.F).max(), 1e-300)
+        moved.append(r.n_updated)
+        F, s = r.F, r.sumF
+    assert moved[-1] < 0.5 * moved[0], moved            # the regime the test is about
+    b.close()
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("variant", [4, 2])
 def test_multi_run_loop_matches_single_gpu(oracle, world, variant):
