@@ -109,6 +109,7 @@ SIGNATURES = {
     "bigclam_multi_loglikelihood": (C.c_int, [_vp, _pd]),
     "bigclam_multi_run": (C.c_int, [_vp, _i32, _dbl, _i64, _pd, _pi64, _vp, _i64]),
     "bigclam_multi_get_kernel_time": (C.c_int, [_vp, _pd, _pi64]),
+    "bigclam_multi_get_ls_stats": (C.c_int, [_vp, _pi64, _pi64]),
     "bigclam_set_F_csr": (C.c_int, [_vp, _vp, _vp, _vp]),
     "bigclam_get_F_nnz": (C.c_int, [_vp, _pi64]),
     "bigclam_get_F_csr": (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -2014,5 +2014,20 @@ extern "C" int bigclam_multi_get_kernel_time(bigclam_multi *m, double *max_rank_
     return BIGCLAM_OK;
 }
 
+extern "C" int bigclam_multi_get_ls_stats(bigclam_multi *m, int64_t *nodes_asked, int64_t *nodes_searched) {
+    if (m == nullptr) return BIGCLAM_EINVAL;
+    int64_t asked = 0, searched = 0;
+    for (bigclam_ctx *c : m->r) {                      // every rank counts the nodes it owns
+        int64_t a = 0, s = 0;
+        const int rc = bigclam_get_ls_stats(c, &a, &s);
+        if (rc) return mfail_from(m, rc, c);
+        asked += a;
+        searched += s;
+    }
+    if (nodes_asked) *nodes_asked = asked;
+    if (nodes_searched) *nodes_searched = searched;
+    return BIGCLAM_OK;
+}
+
 extern "C" int bigclam_multi_world(const bigclam_multi *m) { return m != nullptr ? m->world : BIGCLAM_EINVAL; }
 #undef MCALL

@@ -390,6 +390,9 @@ class BigClam:
         """Sparse rows: dict(nodes_asked, nodes_searched) of the tile path since the previous read — how many of the
         nodes that asked for a line search had a candidate the bounds could not exclude."""
         a, b = C.c_int64(), C.c_int64()
+        if self._multi is not None:          # summed over the ranks (every rank counts the nodes it owns)
+            self._mcheck(_lib.load().bigclam_multi_get_ls_stats(self._multi, C.byref(a), C.byref(b)))
+            return {"nodes_asked": a.value, "nodes_searched": b.value}
         check(_lib.load().bigclam_get_ls_stats(self._need(), C.byref(a), C.byref(b)), self._ctx)
         return {"nodes_asked": a.value, "nodes_searched": b.value}
 

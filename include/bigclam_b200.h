@@ -226,6 +226,7 @@ int  bigclam_multi_loglikelihood(bigclam_multi *m, double *llh_out);
 int  bigclam_multi_run(bigclam_multi *m, int32_t variant, double rel_tol, int64_t max_outer, double *llh_out,
                        int64_t *calls_out, double *llh_trace, int64_t trace_cap);
 int  bigclam_multi_get_kernel_time(bigclam_multi *m, double *max_rank_ms_sum, int64_t *step_kernel_launches);
+int  bigclam_multi_get_ls_stats(bigclam_multi *m, int64_t *nodes_asked, int64_t *nodes_searched);   /* bigclam_get_ls_stats summed over the ranks */
 
 /*
  * F as CSR rows, the shape of the reference's RDD[(Long, BSV[Double])] (bigclam4-7.scala:97-104): indptr[n + 1],

@@ -73,6 +73,7 @@ def test_multi_steps_in_the_large_graph_regime(oracle, world):
     b.set_graph(rp, col).set_K(k).set_F(F0, sumF=sumF)
     F, s = F0, sumF
     moved = []
+    b.ls_stats()
     for it in range(5):
         llh = b.backtrackingLineSearchs()
         r = oracle.step(rp, col, F, s, P)
@@ -84,6 +85,8 @@ def test_multi_steps_in_the_large_graph_regime(oracle, world):
         moved.append(r.n_updated)
         F, s = r.F, r.sumF
     assert moved[-1] < 0.5 * moved[0], moved            # the regime the test is about
+    st = b.ls_stats()                                   # (summed over the ranks: bigclam_multi_get_ls_stats)
+    assert 0 < st["nodes_searched"] < st["nodes_asked"], st
     b.close()
 
 
