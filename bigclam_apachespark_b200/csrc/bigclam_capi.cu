@@ -242,11 +242,13 @@ static cudaError_t configure_one(size_t smem, int *blocks_per_sm) {
 
 template <int C2>
 static cudaError_t configure_kernel(size_t smem, int *blocks_per_sm) {
+    // the persistent grid must be resident for EVERY variant that may be launched on it (mega-hub slices wait for each other
+    // across blocks): the smallest occupancy of the four sizes it (the hub variants use more static shared memory and registers)
     int b = 0;
     cudaError_t e = configure_one<C2, false, false>(smem, blocks_per_sm);
-    if (e == cudaSuccess) e = configure_one<C2, true, false>(smem, &b);
-    if (e == cudaSuccess) e = configure_one<C2, false, true>(smem, &b);
-    if (e == cudaSuccess) e = configure_one<C2, true, true>(smem, &b);
+    if (e == cudaSuccess) { e = configure_one<C2, true, false>(smem, &b); if (e == cudaSuccess && b > 0) *blocks_per_sm = std::min(*blocks_per_sm, b); }
+    if (e == cudaSuccess) { e = configure_one<C2, false, true>(smem, &b); if (e == cudaSuccess && b > 0) *blocks_per_sm = std::min(*blocks_per_sm, b); }
+    if (e == cudaSuccess) { e = configure_one<C2, true, true>(smem, &b); if (e == cudaSuccess && b > 0) *blocks_per_sm = std::min(*blocks_per_sm, b); }
     return e;
 }
 
