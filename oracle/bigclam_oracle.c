@@ -9,7 +9,10 @@
  * golden vectors or recorded outputs for this path, and cannot be executed here (no JVM /
  * Scala / Spark).  This file is a line-by-line restatement of the Scala; it is cross-checked
  * against an independent NumPy restatement (oracle/numpy_twin.py) and the self-consistency
- * properties in tests/, not against outputs of the reference itself.
+ * properties in tests/, not against outputs of the reference itself.  Its formulas (not its
+ * clamps or its rounding) are anchored on the published algorithm: tests/test_oracle_formula.py
+ * compares LLH, gradient, per-node term and accepted step with the BigCLAM objective of the
+ * thesis (eq. 3.6-3.11) evaluated over all node pairs.
  *
  * What is restated (all citations relative to /root/reference):
  *   codes/bigclam4-7.scala:28-34    step-size list by repeated `*= beta`          -> oracle_step_sizes
