@@ -382,6 +382,8 @@ class BigClam:
 
     def tile_stats(self):
         """Sparse rows + time_kernels: dict(tiles_done, tiles_fallback, n_tiles, n_general_nodes, n_split_hubs)."""
+        if self._multi is not None:
+            raise RuntimeError("tile_stats() reads one context; with numGPUs > 1 use ls_stats() (summed over the ranks)")
         v = [C.c_int64() for _ in range(5)]
         check(_lib.load().bigclam_get_tile_stats(self._need(), *[C.byref(x) for x in v]), self._ctx)
         return dict(zip(("tiles_done", "tiles_fallback", "n_tiles", "n_general_nodes", "n_split_hubs"), (x.value for x in v)))
