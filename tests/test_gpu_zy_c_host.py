@@ -1,0 +1,55 @@
+"""`-m gpu` part of tests/test_c_host.py: the plain-C caller (tests/c_host/sgd_find_c.c) on the B200 against the product
+library — edge list -> SGDFindC to the reference's stop rule (bigclam4-7.scala:225-243) -> F, sumF, LLH trace against the
+oracle's outer loop from the same F0; two GPUs behind one handle; the `init` mode against the Python driver."""
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_c_host import _build, _case, _check_against_oracle, _read_out, _write_edgelist, product_lib
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c_caller_matches_oracle_on_gpu(oracle, tmp_path):
+    rp, col, F0, edges, f0 = _case(tmp_path, n=600, deg=6, k=12, seed=77, dens=0.3)
+    exe = _build(str(tmp_path / "sgd_find_c"), *product_lib())
+    out = str(tmp_path / "out.bin")
+    r = subprocess.run([exe, edges, "12", "0", f0, out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    _check_against_oracle(oracle, rp, col, F0, 12, out, 0)
+
+
+def test_c_caller_two_gpus_behind_one_handle(oracle, tmp_path):
+    from bigclam_apachespark_b200 import _lib
+    if int(_lib.load().bigclam_device_count()) < 2:
+        pytest.skip("needs 2 GPUs")
+    rp, col, F0, edges, f0 = _case(tmp_path, n=600, deg=6, k=12, seed=78, dens=0.3)
+    exe = _build(str(tmp_path / "sgd_find_c"), *product_lib())
+    out = str(tmp_path / "out.bin")
+    r = subprocess.run([exe, edges, "12", "0", f0, out, "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    _check_against_oracle(oracle, rp, col, F0, 12, out, 0)
+
+
+def test_c_caller_init_mode_equals_the_driver(graphs, tmp_path):
+    """`init`: GPU conductance seeds + initNeighborComF + SGDFindC from C, against the Python driver on the same graph
+    (same library, same entry points: the two callers must agree bit for bit)."""
+    from bigclam_apachespark_b200 import BigClam
+    rp, col, _ = graphs.load_npz_graph("facebook_combined")
+    edges = str(tmp_path / "fb.txt")
+    _write_edgelist(edges, rp, col)
+    exe = _build(str(tmp_path / "sgd_find_c"), *product_lib())
+    out = str(tmp_path / "out.bin")
+    r = subprocess.run([exe, edges, "10", "5", "init", out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    calls, llh, trace, sumF, F = _read_out(out)
+    b = BigClam(device=0, sparse_rows=True)
+    b.set_graph(rp, col).set_K(10)
+    b.conductanceLocalMin(on_gpu=True)
+    b.initNeighborComF(10, pad_seed=1)
+    ret = b.SGDFindC(max_outer=5)
+    assert b.last_calls == calls and ret == llh
+    assert np.array_equal(np.asarray(b.last_trace), trace)
+    assert b.F.tobytes() == F.tobytes() and b.sumF.tobytes() == sumF.tobytes()
+    b.close()
