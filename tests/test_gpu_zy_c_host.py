@@ -1,6 +1,7 @@
 """`-m gpu` part of tests/test_c_host.py: the plain-C caller (tests/c_host/sgd_find_c.c) on the B200 against the product
 library — edge list -> SGDFindC to the reference's stop rule (bigclam4-7.scala:225-243) -> F, sumF, LLH trace against the
 oracle's outer loop from the same F0; two GPUs behind one handle; the `init` mode against the Python driver."""
+import os
 import subprocess
 
 import numpy as np
@@ -36,7 +37,10 @@ def test_c_caller_init_mode_equals_the_driver(graphs, tmp_path):
     """`init`: GPU conductance seeds + initNeighborComF + SGDFindC from C, against the Python driver on the same graph
     (same library, same entry points: the two callers must agree bit for bit)."""
     from bigclam_apachespark_b200 import BigClam
-    rp, col, _ = graphs.load_npz_graph("facebook_combined")
+    if os.environ.get("BIGCLAM_HOSTEMU") == "1":           # development run on a CPU box: a graph the emulation finishes
+        rp, col = _case(tmp_path, n=150, deg=5, k=10, seed=3)[:2]
+    else:
+        rp, col, _ = graphs.load_npz_graph("facebook_combined")
     edges = str(tmp_path / "fb.txt")
     _write_edgelist(edges, rp, col)
     exe = _build(str(tmp_path / "sgd_find_c"), *product_lib())
