@@ -57,3 +57,24 @@ def test_c_caller_init_mode_equals_the_driver(graphs, tmp_path):
     assert np.array_equal(np.asarray(b.last_trace), trace)
     assert b.F.tobytes() == F.tobytes() and b.sumF.tobytes() == sumF.tobytes()
     b.close()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_jni_shim_through_the_fake_jvm(oracle, tmp_path, world):
+    """integration/jni/bigclam_b200_jni.c driven by tests/jni_stub/fake_jvm.c (see tests/test_jni_shim.py) against the product
+    library: create(Multi) -> setF -> run(SGDFindC) -> getF / getSumF, against the oracle's outer loop."""
+    from bigclam_apachespark_b200 import _lib
+    from test_jni_shim import build_fake_jvm
+    if int(_lib.load().bigclam_device_count()) < world:
+        pytest.skip(f"needs {world} GPUs")
+    small = os.environ.get("BIGCLAM_HOSTEMU") == "1"
+    n, k = (150, 6) if small else (600, 12)
+    rp, col, F0, edges, f0 = _case(tmp_path, n=n, deg=5, k=k, seed=80 + world, dens=0.3)
+    exe = build_fake_jvm(str(tmp_path / "fake_jvm"), *product_lib())
+    out = str(tmp_path / "out.bin")
+    r = subprocess.run([exe, edges, str(k), "6", f0, out, str(world), "run"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    calls, llh, trace, sumF, F = _read_out(out)
+    Fo, so, llho, callso, tro = oracle.run(rp, col, F0, oracle.colsum(F0), oracle.make_params(k), variant=4, max_outer=6)
+    assert calls == callso and abs(llh - llho) <= 1e-9 * abs(llho)
+    assert np.abs(F - Fo).max() <= 1e-9 * np.abs(Fo).max() and np.allclose(sumF, so, rtol=1e-8)

@@ -57,8 +57,9 @@ def test_line_search_bounds_under_host_emulation():
 @pytest.mark.timeout(600)
 def test_c_caller_gpu_tests_under_host_emulation():
     """The `-m gpu` tests of the plain-C caller (tests/test_gpu_zy_c_host.py), linked with the emulation build: the init mode
-    against the Python driver bit for bit (the runs against the oracle are in tests/test_c_host.py)."""
-    _child("test_gpu_zy_c_host.py", "init_mode", nobuild=True)
+    against the Python driver bit for bit (the runs against the oracle are in tests/test_c_host.py), and the JNI shim
+    through the fake JVM on one and two emulated devices."""
+    _child("test_gpu_zy_c_host.py", "init_mode or jni", nobuild=True)
 
 
 @pytest.mark.timeout(600)
