@@ -18,6 +18,7 @@
  *   nUpdated Sx.size of the last call (:186)                                        -> (kept from bigclam_step)
  *   run      SGDFindC / MBSGD outer loop (:225-243; v3 :206-222; v2 :203-219)       -> bigclam_run
  *   getF     F.collect (:36)                                                        -> bigclam_get_F
+ *   setFCsr / getFNnz / getFCsr   F as RDD[(Long, BSV[Double])] rows (:36, :97-104)   -> bigclam_set_F_csr, _get_F_nnz, _get_F_csr
  *   createMulti / the same calls on a multi handle: all GPUs of the box             -> bigclam_multi_*
  */
 #include <jni.h>
@@ -158,6 +159,55 @@ JNIEXPORT void JNICALL Java_BigclamNative_00024_getSumF(JNIEnv *env, jobject sel
         rc = h->multi != NULL ? bigclam_multi_get_sumF(h->multi, 0, s) : bigclam_get_sumF(h->ctx, s);
         (*env)->ReleaseDoubleArrayElements(env, out, s, rc == BIGCLAM_OK ? 0 : JNI_ABORT);
     }
+    throw_on(env, rc, last_error(h));
+}
+
+/*
+ * F in the reference's own shape, RDD[(Long, BSV[Double])] (:36, :97-104): per row the BSV's (index, data) arrays,
+ * concatenated in dense-id order with an indptr — no dense n x K array on either side (bigclam_set_F_csr / _get_F_csr).
+ */
+JNIEXPORT void JNICALL Java_BigclamNative_00024_setFCsr(JNIEnv *env, jobject self, jlong handle, jlongArray indptr, jintArray indices,
+                                                        jdoubleArray values) {
+    (void)self;
+    jni_handle *h = (jni_handle *)(intptr_t)handle;
+    jlong *ip = (*env)->GetLongArrayElements(env, indptr, NULL);
+    jint *ix = (*env)->GetIntArrayElements(env, indices, NULL);
+    jdouble *v = (*env)->GetDoubleArrayElements(env, values, NULL);
+    int rc = BIGCLAM_ENOMEM;
+    if (ip != NULL && ix != NULL && v != NULL)
+        rc = h->multi != NULL ? bigclam_multi_set_F_csr(h->multi, (const int64_t *)ip, (const int32_t *)ix, v)
+                              : bigclam_set_F_csr(h->ctx, (const int64_t *)ip, (const int32_t *)ix, v);
+    if (ip != NULL) (*env)->ReleaseLongArrayElements(env, indptr, ip, JNI_ABORT);
+    if (ix != NULL) (*env)->ReleaseIntArrayElements(env, indices, ix, JNI_ABORT);
+    if (v != NULL) (*env)->ReleaseDoubleArrayElements(env, values, v, JNI_ABORT);
+    throw_on(env, rc, last_error(h));
+}
+
+JNIEXPORT jlong JNICALL Java_BigclamNative_00024_getFNnz(JNIEnv *env, jobject self, jlong handle) {
+    (void)self;
+    jni_handle *h = (jni_handle *)(intptr_t)handle;
+    int64_t nnz = 0;
+    int rc = h->multi != NULL ? bigclam_multi_get_F_nnz(h->multi, &nnz) : bigclam_get_F_nnz(h->ctx, &nnz);
+    throw_on(env, rc, last_error(h));
+    return (jlong)nnz;
+}
+
+/* indptr: n + 1 longs; indices / values: getFNnz() entries (ascending component inside a row, zeros never stored). */
+JNIEXPORT void JNICALL Java_BigclamNative_00024_getFCsr(JNIEnv *env, jobject self, jlong handle, jlongArray indptr, jintArray indices,
+                                                        jdoubleArray values) {
+    (void)self;
+    jni_handle *h = (jni_handle *)(intptr_t)handle;
+    jlong *ip = (*env)->GetLongArrayElements(env, indptr, NULL);
+    jint *ix = (*env)->GetIntArrayElements(env, indices, NULL);
+    jdouble *v = (*env)->GetDoubleArrayElements(env, values, NULL);
+    int rc = BIGCLAM_ENOMEM;
+    if (ip != NULL && ix != NULL && v != NULL)
+        rc = h->multi != NULL ? bigclam_multi_get_F_csr(h->multi, (int64_t *)ip, (int32_t *)ix, v)
+                              : bigclam_get_F_csr(h->ctx, (int64_t *)ip, (int32_t *)ix, v);
+    const jint mode = rc == BIGCLAM_OK ? 0 : JNI_ABORT;
+    if (ip != NULL) (*env)->ReleaseLongArrayElements(env, indptr, ip, mode);
+    if (ix != NULL) (*env)->ReleaseIntArrayElements(env, indices, ix, mode);
+    if (v != NULL) (*env)->ReleaseDoubleArrayElements(env, values, v, mode);
     throw_on(env, rc, last_error(h));
 }
 

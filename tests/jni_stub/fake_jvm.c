@@ -5,9 +5,10 @@
  * loses its result here as it would there; a pending exception is a recorded (class, message).  main() is the
  * changed part of the reference's driver script in C:
  *
- *   fake_jvm <edge list> <K> <max calls> <F0.f64> <out.bin> <world> <run | step>
+ *   fake_jvm <edge list> <K> <max calls> <F0.f64> <out.bin> <world> <run | step | csr>
  *     run : create(Multi) -> setF -> run(4, 1e-4, max calls) -> getF, getSumF          (SGDFindC, bigclam4-7.scala:225-243)
  *     step: create(Multi) -> setF -> max calls x { step(null); nUpdated } -> getF, getSumF   (:152-223 per call)
+ *     csr : like run, but F travels as rows of (index, data) both ways: setFCsr, getFNnz + getFCsr   (the BSV rows of :36)
  *   out.bin: int64 n, k, calls, ntrace | double llh | double trace[ntrace] | double sumF[k] | double F[n*k]
  *            (same layout as tests/c_host/sgd_find_c.c; trace = the LLH of every step in `step` mode)
  * Exit code 3 with "EXCEPTION <class>: <message>" on stderr when the shim threw.
@@ -28,6 +29,9 @@ jlong Java_BigclamNative_00024_nUpdated(JNIEnv *, jobject, jlong);
 jdouble Java_BigclamNative_00024_run(JNIEnv *, jobject, jlong, jint, jdouble, jlong, jlongArray);
 void Java_BigclamNative_00024_getF(JNIEnv *, jobject, jlong, jdoubleArray);
 void Java_BigclamNative_00024_getSumF(JNIEnv *, jobject, jlong, jdoubleArray);
+void Java_BigclamNative_00024_setFCsr(JNIEnv *, jobject, jlong, jlongArray, jintArray, jdoubleArray);
+jlong Java_BigclamNative_00024_getFNnz(JNIEnv *, jobject, jlong);
+void Java_BigclamNative_00024_getFCsr(JNIEnv *, jobject, jlong, jlongArray, jintArray, jdoubleArray);
 void Java_BigclamNative_00024_destroy(JNIEnv *, jobject, jlong);
 
 typedef struct {
@@ -115,6 +119,7 @@ int main(int argc, char **argv) {
     const jlong max_calls = (jlong)atoll(argv[3]);
     const jint world = (jint)atoi(argv[6]);
     const int step_mode = strcmp(argv[7], "step") == 0;
+    const int csr_mode = strcmp(argv[7], "csr") == 0;
 
     char errbuf[256] = {0};
     bigclam_graph g;
@@ -140,7 +145,32 @@ int main(int argc, char **argv) {
     if (pending()) return 3;
     /* BigclamNative.setF(ctx, denseRowMajor(F, ids, i)) */
     jobject F = new_array(sizeof(jdouble), (jsize)nk, F0);
-    Java_BigclamNative_00024_setF(env, NULL, ctx, F);
+    if (csr_mode) {
+        /* rows.flatMap(_._2.index) / rows.flatMap(_._2.data): the non-zeros of every row, in dense-id order */
+        jlong *ip = (jlong *)calloc((size_t)g.n + 1, sizeof(jlong));
+        jint *ix = (jint *)malloc((nk > 0 ? nk : 1) * sizeof(jint));
+        jdouble *v = (jdouble *)malloc((nk > 0 ? nk : 1) * sizeof(jdouble));
+        jlong cnt = 0;
+        for (int64_t u = 0; u < g.n; ++u) {
+            for (jint c = k - 1; c >= 0; --c)                                   /* any order inside a row is allowed: descending */
+                if (F0[(size_t)u * (size_t)k + (size_t)c] != 0.0) {
+                    ix[cnt] = c;
+                    v[cnt++] = F0[(size_t)u * (size_t)k + (size_t)c];
+                }
+            ip[u + 1] = cnt;
+        }
+        jobject a_ip = new_array(sizeof(jlong), (jsize)(g.n + 1), ip), a_ix = new_array(sizeof(jint), (jsize)cnt, ix),
+                a_v = new_array(sizeof(jdouble), (jsize)cnt, v);
+        Java_BigclamNative_00024_setFCsr(env, NULL, ctx, a_ip, a_ix, a_v);
+        free_array(a_ip);
+        free_array(a_ix);
+        free_array(a_v);
+        free(ip);
+        free(ix);
+        free(v);
+    } else {
+        Java_BigclamNative_00024_setF(env, NULL, ctx, F);
+    }
     if (pending()) return 3;
 
     double llh = 0.0;
@@ -164,8 +194,31 @@ int main(int argc, char **argv) {
         free_array(ncalls);
     }
     jobject sumF = new_array(sizeof(jdouble), (jsize)k, NULL);
-    Java_BigclamNative_00024_getF(env, NULL, ctx, F);
-    if (pending()) return 3;
+    if (csr_mode) {
+        const jlong nnz = Java_BigclamNative_00024_getFNnz(env, NULL, ctx);
+        if (pending()) return 3;
+        jobject a_ip = new_array(sizeof(jlong), (jsize)(g.n + 1), NULL), a_ix = new_array(sizeof(jint), (jsize)nnz, NULL),
+                a_v = new_array(sizeof(jdouble), (jsize)nnz, NULL);
+        Java_BigclamNative_00024_getFCsr(env, NULL, ctx, a_ip, a_ix, a_v);
+        if (pending()) return 3;
+        const jlong *ip = (const jlong *)((fake_array *)a_ip)->data;
+        const jint *ix = (const jint *)((fake_array *)a_ix)->data;
+        const jdouble *v = (const jdouble *)((fake_array *)a_v)->data;
+        double *dense = (double *)((fake_array *)F)->data;
+        memset(dense, 0, nk * sizeof(double));
+        if (ip[g.n] != nnz) {
+            fprintf(stderr, "getFCsr: indptr ends at %lld, getFNnz said %lld\n", (long long)ip[g.n], (long long)nnz);
+            return 4;
+        }
+        for (int64_t u = 0; u < g.n; ++u)
+            for (jlong e = ip[u]; e < ip[u + 1]; ++e) dense[(size_t)u * (size_t)k + (size_t)ix[e]] = v[e];
+        free_array(a_ip);
+        free_array(a_ix);
+        free_array(a_v);
+    } else {
+        Java_BigclamNative_00024_getF(env, NULL, ctx, F);
+        if (pending()) return 3;
+    }
     Java_BigclamNative_00024_getSumF(env, NULL, ctx, sumF);
     if (pending()) return 3;
     Java_BigclamNative_00024_destroy(env, NULL, ctx);

@@ -59,10 +59,11 @@ def test_c_caller_init_mode_equals_the_driver(graphs, tmp_path):
     b.close()
 
 
-@pytest.mark.parametrize("world", [1, 2])
-def test_jni_shim_through_the_fake_jvm(oracle, tmp_path, world):
+@pytest.mark.parametrize("world,mode", [(1, "run"), (1, "csr"), (2, "run"), (2, "csr")])
+def test_jni_shim_through_the_fake_jvm(oracle, tmp_path, world, mode):
     """integration/jni/bigclam_b200_jni.c driven by tests/jni_stub/fake_jvm.c (see tests/test_jni_shim.py) against the product
-    library: create(Multi) -> setF -> run(SGDFindC) -> getF / getSumF, against the oracle's outer loop."""
+    library: create(Multi) -> setF -> run(SGDFindC) -> getF / getSumF (mode csr: setFCsr, getFNnz + getFCsr — F as rows of
+    (index, data) like the reference's BSV rows), against the oracle's outer loop."""
     from bigclam_apachespark_b200 import _lib
     from test_jni_shim import build_fake_jvm
     if int(_lib.load().bigclam_device_count()) < world:
@@ -72,7 +73,7 @@ def test_jni_shim_through_the_fake_jvm(oracle, tmp_path, world):
     rp, col, F0, edges, f0 = _case(tmp_path, n=n, deg=5, k=k, seed=80 + world, dens=0.3)
     exe = build_fake_jvm(str(tmp_path / "fake_jvm"), *product_lib())
     out = str(tmp_path / "out.bin")
-    r = subprocess.run([exe, edges, str(k), "6", f0, out, str(world), "run"], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, edges, str(k), "6", f0, out, str(world), mode], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     calls, llh, trace, sumF, F = _read_out(out)
     Fo, so, llho, callso, tro = oracle.run(rp, col, F0, oracle.colsum(F0), oracle.make_params(k), variant=4, max_outer=6)

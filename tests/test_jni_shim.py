@@ -50,12 +50,14 @@ def test_shim_compiles_and_throws_without_a_device(tmp_path):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("world", [1, 2])
-def test_shim_run_under_host_emulation(oracle, tmp_path, world):
+@pytest.mark.parametrize("world,mode", [(1, "run"), (2, "run"), (1, "csr"), (2, "csr")])
+def test_shim_run_under_host_emulation(oracle, tmp_path, world, mode):
+    """mode csr: F travels as the reference keeps it — rows of (index, data), RDD[(Long, BSV[Double])] — through setFCsr and
+    getFNnz + getFCsr instead of a dense n x K array."""
     rp, col, F0, edges, f0 = _case(tmp_path, n=120, deg=4, k=6, seed=11)
     exe = build_fake_jvm(str(tmp_path / "fake_jvm"), *_emu())
     out = str(tmp_path / "out.bin")
-    r = subprocess.run([exe, edges, "6", "4", f0, out, str(world), "run"], capture_output=True, text=True, timeout=800)
+    r = subprocess.run([exe, edges, "6", "4", f0, out, str(world), mode], capture_output=True, text=True, timeout=800)
     assert r.returncode == 0, r.stderr[-2000:]
     calls, llh, trace, sumF, F = _read_out(out)
     Fo, so, llho, callso, tro = oracle.run(rp, col, F0, oracle.colsum(F0), oracle.make_params(6), variant=4, max_outer=4)
