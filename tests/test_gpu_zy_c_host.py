@@ -79,3 +79,42 @@ def test_jni_shim_through_the_fake_jvm(oracle, tmp_path, world, mode):
     Fo, so, llho, callso, tro = oracle.run(rp, col, F0, oracle.colsum(F0), oracle.make_params(k), variant=4, max_outer=6)
     assert calls == callso and abs(llh - llho) <= 1e-9 * abs(llho)
     assert np.abs(F - Fo).max() <= 1e-9 * np.abs(Fo).max() and np.allclose(sumF, so, rtol=1e-8)
+
+
+# ---- include/bigclam_b200.hpp: the C++ mirror of the script surface (tests/test_cpp_host.py), against the product library
+def _mirror(tmp_path):
+    from test_cpp_host import build_mirror
+    return build_mirror(str(tmp_path / "script_mirror"), *product_lib())
+
+
+def _sizes():
+    return (150, 6) if os.environ.get("BIGCLAM_HOSTEMU") == "1" else (600, 12)
+
+
+@pytest.mark.parametrize("mode,version", [("sgd", 4), ("mbsgd", 3), ("mbsgd", 2)])
+def test_cpp_mirror_outer_loops(oracle, tmp_path, mode, version):
+    """SGDFindC (bigclam4-7.scala:225-243) and MBSGD (bigclamv3-7.scala:206-222, Bigclamv2.scala:203-219) from C++."""
+    n, k = _sizes()
+    rp, col, F0, edges, f0 = _case(tmp_path, n=n, deg=6, k=k, seed=90 + version, dens=0.3)
+    out = str(tmp_path / "out.bin")
+    r = subprocess.run([_mirror(tmp_path), mode, edges, str(k), "8", f0, out, "1", str(version)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    calls, llh, trace, sumF, F = _read_out(out)
+    Fo, so, llho, callso, tro = oracle.run(rp, col, F0, oracle.colsum(F0), oracle.make_params(k), variant=version, max_outer=8)
+    assert calls == callso and np.allclose(trace, tro, rtol=1e-9)
+    assert np.abs(F - Fo).max() <= 1e-9 * np.abs(Fo).max() and np.allclose(sumF, so, rtol=1e-8)
+
+
+def test_cpp_mirror_k_sweep(oracle, tmp_path):
+    """conductanceLocalMin (GPU kernel) + for K in Kset: initNeighborComF, SGDFindC, stop rule (:244-266) from C++ against the
+    oracle-driven sweep."""
+    from bigclam_apachespark_b200.driver import Kset
+    from test_cpp_host import check_sweep_output
+    small = os.environ.get("BIGCLAM_HOSTEMU") == "1"
+    rp, col = _case(tmp_path, n=150 if small else 400, deg=6, k=4, seed=95)[:2]
+    edges = str(tmp_path / "sweep.txt")
+    _write_edgelist(edges, rp, col)
+    lo, hi, div, cap = (4, 8, 2, 5) if small else (4, 16, 4, 30)
+    r = subprocess.run([_mirror(tmp_path), "sweep", edges, str(lo), str(hi), str(div), str(cap)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    check_sweep_output(oracle, r.stdout, rp, col, Kset(lo, hi, div), cap)

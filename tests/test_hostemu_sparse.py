@@ -58,8 +58,8 @@ def test_line_search_bounds_under_host_emulation():
 def test_c_caller_gpu_tests_under_host_emulation():
     """The `-m gpu` tests of the plain-C caller (tests/test_gpu_zy_c_host.py), linked with the emulation build: the init mode
     against the Python driver bit for bit (the runs against the oracle are in tests/test_c_host.py), and the JNI shim
-    through the fake JVM on one and two emulated devices."""
-    _child("test_gpu_zy_c_host.py", "init_mode or jni", nobuild=True)
+    through the fake JVM on one and two emulated devices, the C++ mirror's outer loops and K sweep."""
+    _child("test_gpu_zy_c_host.py", "init_mode or jni or cpp_mirror", nobuild=True)
 
 
 @pytest.mark.timeout(600)
