@@ -15,6 +15,7 @@
 //   SGDFindC()                                        :225-243   SGDFindC()
 //   MBSGD()       bigclamv3-7.scala:206-222, Bigclamv2.scala:203-219   MBSGD(version)
 //   K sweep                                           :244-266   sweep_K()
+//   community extraction         Bigclamv2.scala:223-230         delta_threshold(), extract(delta)
 //
 // Errors: the reference throws JVM exceptions; here every negative return code of the C ABI becomes a bigclam::Error
 // (std::runtime_error carrying the code and bigclam_last_error()).  There is no CPU path: without a CUDA device
@@ -190,6 +191,27 @@ public:
     void MBSGD(int version = 3, double rel_tol = 1e-4, int64_t max_outer = 0) {
         if (version != 2 && version != 3) throw Error(BIGCLAM_EINVAL, "version must be 2 or 3");
         run(version, rel_tol, max_outer);
+    }
+
+    // Community extraction as coded in Bigclamv2.scala:223-230.  delta_threshold: `e = 2.0*count/(N*(N-1)); sqrt(-log(1-e))`
+    // (:223-224; in the script `count` is the number of vertices that have edges, the thesis uses |E|: pass what you mean).
+    // extract(): communities[c] = vertices u with F_uc >= delta, or, when the row maximum is below delta, with F_uc equal to
+    // the row maximum (:227); the flatMap / groupByKey of :229-230 is the regrouping by community id done here.
+    static double delta_threshold(int64_t n_vertices, int64_t count) {
+        const double e = 2.0 * (double)count / ((double)n_vertices * ((double)n_vertices - 1.0));
+        return std::sqrt(-std::log(1.0 - e));
+    }
+    std::vector<std::vector<int32_t>> extract(double delta) {
+        need();
+        if (multi_ != nullptr) throw Error(BIGCLAM_EUNSUPPORTED, "extract: single-GPU contexts only (read F() and regroup on the host)");
+        std::vector<uint8_t> member((size_t)(n_ * K_));
+        std::vector<double> fmax((size_t)n_);
+        check(bigclam_extract(ctx_, delta, member.data(), fmax.data()), "extract");
+        std::vector<std::vector<int32_t>> comms((size_t)K_);
+        for (int64_t u = 0; u < n_; ++u)
+            for (int c = 0; c < K_; ++c)
+                if (member[(size_t)(u * K_ + c)]) comms[(size_t)c].push_back((int32_t)u);
+        return comms;
     }
 
     std::vector<int> Kset() const { return bigclam::Kset(minCom, maxCom, divCom); }

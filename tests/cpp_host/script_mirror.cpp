@@ -11,6 +11,9 @@
 //   script_mirror sweep <edge list> <minCom> <maxCom> <divCom> <max calls per K>
 //        conductanceLocalMin(); for K in Kset: initNeighborComF(K); SGDFindC(); stop rule of :259         (:244-266)
 //        prints "K LLH" per K and "KforC k"
+//   script_mirror extract <edge list> <K> <calls> <F0.f64> <count>
+//        `calls` hot-path calls, then the extraction of Bigclamv2.scala:223-230 with delta from (N, count)
+//        prints "delta d" and one line per non-empty community: "c: u u u ..."
 //   out.bin: int64 n, k, calls, ntrace | double llh | double trace[ntrace] | double sumF[k] | double F[n*k]
 // Exit code 1 with the exception's message on stderr (what the JVM would print as an uncaught exception).
 #include <cstdio>
@@ -85,6 +88,23 @@ int main(int argc, char **argv) try {
             llh = trace.empty() ? 0.0 : trace.back();
         }
         write_out(argv[6], b, llh, trace);
+        return 0;
+    }
+    if (mode == "extract" && argc == 7) {
+        const int K = atoi(argv[3]);
+        bigclam::BigClam b;
+        b.load_edge_list(argv[2]).set_K(K);
+        b.set_F(read_f64(argv[5], (size_t)b.n() * (size_t)K));
+        for (int64_t it = 0; it < atoll(argv[4]); ++it) b.backtrackingLineSearchs();
+        const double delta = bigclam::BigClam::delta_threshold(b.n(), atoll(argv[6]));
+        std::printf("delta %.17g\n", delta);
+        const auto comms = b.extract(delta);
+        for (size_t c = 0; c < comms.size(); ++c) {
+            if (comms[c].empty()) continue;
+            std::printf("%zu:", c);
+            for (int32_t u : comms[c]) std::printf(" %d", (int)u);
+            std::printf("\n");
+        }
         return 0;
     }
     std::fprintf(stderr, "usage: see the header of tests/cpp_host/script_mirror.cpp\n");

@@ -134,3 +134,27 @@ def test_mirror_k_sweep(oracle, tmp_path):
     ks = Kset(4, 8, 2)
     out = _run(_emu_exe(tmp_path), "sweep", edges, 4, 8, 2, 5)
     check_sweep_output(oracle, out, rp, col, ks, 5)
+
+
+@pytest.mark.timeout(900)
+def test_mirror_extraction(oracle, tmp_path):
+    """Bigclamv2.scala:223-230 from C++ (delta_threshold + extract) against the rule restated in NumPy on the oracle's F."""
+    import math
+    rp, col, F0, edges, f0 = _case(tmp_path, n=120, deg=4, k=6, seed=25, dens=0.5)
+    n = len(rp) - 1
+    out = _run(_emu_exe(tmp_path), "extract", edges, 6, 2, f0, n)
+    lines = out.strip().splitlines()
+    e = 2.0 * n / (n * (n - 1.0))
+    delta = math.sqrt(-math.log(1.0 - e))
+    assert abs(float(lines[0].split()[1]) - delta) <= 1e-15
+    P, Fo, so = oracle.make_params(6), F0, oracle.colsum(F0)
+    for _ in range(2):
+        r = oracle.step(rp, col, Fo, so, P)
+        Fo, so = r.F, r.sumF
+    fmax = Fo.max(axis=1, keepdims=True)
+    member = np.where(fmax >= delta, Fo >= delta, Fo == fmax)                 # :227 (ties included)
+    margin = np.abs(Fo - delta).min()
+    assert margin > 1e-9, "an entry sits on the threshold: pick another seed"
+    got = {int(l.split(":")[0]): [int(x) for x in l.split(":")[1].split()] for l in lines[1:]}
+    want = {c: np.flatnonzero(member[:, c]).tolist() for c in range(6) if member[:, c].any()}
+    assert got == want
