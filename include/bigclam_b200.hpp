@@ -5,7 +5,7 @@
 // kept so that a driver reads like the script:
 //
 //   script (codes/bigclam4-7.scala)                              here
-//   numCore/minCom/maxCom/divCom/alpha/beta/MaxInter  :16-26     public members of BigClam
+//   numCore/minCom/maxCom/divCom/alpha/beta/MaxInter  :14-26     public members of BigClam (same defaults)
 //   GraphLoader.edgeListFile + collectNeighborIds     :45,50-51  load_edge_list / set_graph
 //   conductanceLocalMin()                             :58-73     conductanceLocalMin()
 //   initNeighborComF(K)                               :81-108    initNeighborComF(K)
@@ -59,8 +59,9 @@ inline std::vector<int> Kset(int minCom, int maxCom, int divCom, bool int_divisi
 
 class BigClam {
 public:
-    // script variables (:16-26)
-    int minCom = 1000, maxCom = 9000, divCom = 15;
+    // script variables (:14-26), the script's values as defaults
+    int numCore = 36;                                // :14 (Spark parallelism; informational here: numGPUs plays that role)
+    int minCom = 1000, maxCom = 9000, divCom = 100;
     double alpha = 0.05, beta = 0.1;
     int MaxInter = 15;
     // outcome of the most recent call
