@@ -40,7 +40,23 @@ def _cc():
     return "/usr/bin/gcc" if os.access("/usr/bin/gcc", os.X_OK) else (shutil.which("gcc") or shutil.which("cc"))
 
 
+_BUILT = {}
+
+
+def cached_build(key, out, build):
+    """One compilation per (program, library) and pytest process: later requests copy the first binary."""
+    if key not in _BUILT:
+        _BUILT[key] = build(out)
+        return out
+    shutil.copy2(_BUILT[key], out)
+    return out
+
+
 def _build(out, libdir, libname):
+    return cached_build(("c", libdir), out, lambda o: _build_now(o, libdir, libname))
+
+
+def _build_now(out, libdir, libname):
     cmd = [_cc(), "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-O1", "-I", os.path.join(REPO, "include"), SRC,
            "-o", out, "-L", libdir, f"-l:{libname}", f"-Wl,-rpath,{libdir}"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -16,12 +16,16 @@ import numpy as np
 import pytest
 
 from conftest import REPO, random_graph
-from test_c_host import EMU_DIR, PRODUCT_DIR, _case, _check_against_oracle, _read_out, _write_edgelist
+from test_c_host import EMU_DIR, PRODUCT_DIR, _case, _check_against_oracle, _read_out, _write_edgelist, cached_build
 
 SRC = os.path.join(REPO, "tests", "cpp_host", "script_mirror.cpp")
 
 
 def build_mirror(out, libdir, libname):
+    return cached_build(("cpp", libdir), out, lambda o: _build_now(o, libdir, libname))
+
+
+def _build_now(out, libdir, libname):
     cxx = "/usr/bin/g++" if os.access("/usr/bin/g++", os.X_OK) else shutil.which("g++")
     cmd = [cxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-O1", "-I", os.path.join(REPO, "include"), SRC, "-o", out,
            "-L", libdir, f"-l:{libname}", f"-Wl,-rpath,{libdir}"]

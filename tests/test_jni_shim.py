@@ -16,13 +16,17 @@ import numpy as np
 import pytest
 
 from conftest import REPO
-from test_c_host import EMU_DIR, PRODUCT_DIR, _case, _cc, _check_against_oracle, _read_out
+from test_c_host import EMU_DIR, PRODUCT_DIR, _case, _cc, _check_against_oracle, _read_out, cached_build
 
 SHIM = os.path.join(REPO, "integration", "jni", "bigclam_b200_jni.c")
 FAKE = os.path.join(REPO, "tests", "jni_stub", "fake_jvm.c")
 
 
 def build_fake_jvm(out, libdir, libname):
+    return cached_build(("jni", libdir), out, lambda o: _build_now(o, libdir, libname))
+
+
+def _build_now(out, libdir, libname):
     cmd = [_cc(), "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-O1", "-I", os.path.join(REPO, "tests", "jni_stub"),
            "-I", os.path.join(REPO, "include"), SHIM, FAKE, "-o", out, "-L", libdir, f"-l:{libname}", f"-Wl,-rpath,{libdir}"]
     r = subprocess.run(cmd, capture_output=True, text=True)
